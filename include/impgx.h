@@ -1,0 +1,222 @@
+/*
+ * impgx.h — C ABI of libimpgx, the B200-native projection engine.
+ *
+ * This is the drop-in boundary for ONE path of pangenome/impg: batch interval
+ * stabbing + per-hit CIGAR liftover + transitive BFS frontier + gap-merge,
+ * i.e. what `impg query -b <BED> [-x -m N]` does through `trait ImpgIndex`
+ * (reference src/impg_index.rs:21-121). Everything is `extern "C"`, plain
+ * pointers and sizes; no C++ or torch types cross this boundary.
+ *
+ * Each entry point cites the reference interface it replaces (file:line are
+ * relative to the reference checkout). INTEGRATION.md shows the Rust-side
+ * binding (`GpuImpg: ImpgIndex`) a maintainer would add.
+ *
+ * Error model: every function returns 0 on success or a negative
+ * impgx_status; impgx_last_error() returns a thread-local message. No C++
+ * exception, abort or panic crosses the ABI (the reference panics at
+ * src/impg.rs:88,506-511,1739 become IMPGX_E_* codes).
+ *
+ * There is no CPU fallback: without a usable CUDA device every compute entry
+ * point fails with IMPGX_E_NO_DEVICE.
+ */
+#ifndef IMPGX_H
+#define IMPGX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IMPGX_ABI_VERSION 1
+
+typedef enum impgx_status {
+  IMPGX_OK = 0,
+  IMPGX_E_INVALID = -1,   /* bad argument (NULL, out-of-range id, start>=end …) */
+  IMPGX_E_NO_DEVICE = -2, /* no CUDA device / driver; there is no CPU fallback  */
+  IMPGX_E_CUDA = -3,      /* a CUDA runtime call or kernel failed               */
+  IMPGX_E_NOMEM = -4,     /* host or device allocation failed                   */
+  IMPGX_E_IO = -5,        /* file could not be read / written                   */
+  IMPGX_E_PARSE = -6,     /* malformed PAF / BED / CIGAR text                   */
+  IMPGX_E_UNSUPPORTED = -7 /* feature outside the path (tracepoints, approximate) */
+} impgx_status;
+
+/* CIGAR run packing, identical to the reference's CigarOp (src/impg.rs:76-140):
+ * val = op << 29 | len, op in {'='=0, 'X'=1, 'I'=2, 'D'=3, 'M'=4}, len < 2^29. */
+#define IMPGX_OP_EQ 0u
+#define IMPGX_OP_X 1u
+#define IMPGX_OP_I 2u
+#define IMPGX_OP_D 3u
+#define IMPGX_OP_M 4u
+#define IMPGX_RUN(op, len) ((((uint32_t)(op)) << 29) | (uint32_t)(len))
+#define IMPGX_RUN_OP(v) ((uint32_t)(v) >> 29)
+#define IMPGX_RUN_LEN(v) ((uint32_t)(v) & 0x1fffffffu)
+
+/* One alignment = AlignmentRecord (src/alignment_record.rs:12-21) with the
+ * file offset replaced by an index into the decoded run stream. */
+typedef struct impgx_record {
+  uint32_t query_id;
+  uint32_t target_id;
+  int32_t query_start;
+  int32_t query_end;
+  int32_t target_start;
+  int32_t target_end;
+  uint32_t strand; /* 0 = '+', 1 = '-' (bit 63 of strand_and_data_offset) */
+  uint32_t reserved;
+} impgx_record;
+
+/* One query range = one BED row after name→id (src/main.rs:7435, :11620). */
+typedef struct impgx_range {
+  uint32_t target_id;
+  int32_t start;
+  int32_t end;
+} impgx_range;
+
+typedef enum impgx_mode {
+  IMPGX_MODE_QUERY = 0, /* Impg::query                 src/impg.rs:1852-1928 */
+  IMPGX_MODE_BFS = 1,   /* Impg::query_transitive_bfs  src/impg.rs:2311-2597 */
+  IMPGX_MODE_DFS = 2    /* Impg::query_transitive_dfs  src/impg.rs:2057-2309 */
+} impgx_mode;
+
+/* Arguments of ImpgIndex::query / query_transitive_* (src/impg_index.rs:30-80)
+ * plus the output-merge options of QueryOpts (src/main.rs:4319-4410). */
+typedef struct impgx_params {
+  uint32_t mode;                       /* impgx_mode */
+  uint32_t max_depth;                  /* -m, u16 in the reference; 0 = unlimited */
+  int32_t min_transitive_len;          /* --min-transitive-len (default 101) */
+  int32_t min_distance_between_ranges; /* --min-distance-between-ranges (default 10) */
+  int32_t min_output_length;           /* -l; < 0 means None */
+  uint32_t store_cigar;                /* carry clipped CIGAR runs per result */
+  double min_identity;                 /* --min-result-identity; NaN means None */
+  const uint8_t *subset_mask;          /* per sequence id, 1 = keep; NULL = no filter */
+  int32_t merge_distance;              /* -d; -1 = --no-merge (BED entry point only) */
+  uint32_t merge_strands;              /* !--consider-strandness (BED entry point only) */
+} impgx_params;
+
+typedef struct impgx_index impgx_index;
+typedef struct impgx_results impgx_results;
+
+/* Column view of a result set (AdjustedInterval = (query Interval, cigar,
+ * target Interval), src/impg.rs:225). Row r of the batch owns result slots
+ * [row_offsets[r], row_offsets[r+1]); within a row the order is the
+ * reference's result order (self interval first). For reverse-strand hits
+ * q_first > q_last, exactly as the reference reports them. Pointers are owned
+ * by the impgx_results object and live until impgx_results_free. */
+typedef struct impgx_view {
+  size_t n_rows;
+  size_t n_results;
+  const uint64_t *row_offsets; /* n_rows + 1 */
+  const uint32_t *q_id;
+  const int32_t *q_first;
+  const int32_t *q_last;
+  const uint32_t *t_id;
+  const int32_t *t_first;
+  const int32_t *t_last;
+  const uint64_t *cigar_offsets; /* n_results + 1, or NULL without store_cigar */
+  const uint32_t *cigar_runs;    /* reference packing, or NULL */
+} impgx_view;
+
+/* Counters of the last call on an index (for bench.py's roofline line). */
+typedef struct impgx_stats {
+  uint64_t kernel_launches; /* kernels of this library launched by the call */
+  uint64_t stab_ranges;     /* ranges stabbed over all hops */
+  uint64_t stab_candidates; /* interval columns scanned */
+  uint64_t liftovers;       /* hits lifted through a CIGAR */
+  uint64_t lift_runs;       /* CIGAR runs read by the liftover kernel */
+  uint64_t lift_bytes;      /* algorithmic bytes of the liftover kernel */
+  uint64_t results;         /* result intervals before merging */
+  uint64_t merged;          /* result intervals after merging (BED entry point) */
+  uint64_t h2d_bytes;
+  uint64_t d2h_bytes;
+  float lift_ms;            /* device time of the liftover launches (CUDA events) */
+  float stab_ms;
+  float fold_ms;
+  float merge_ms;
+  float total_ms;
+} impgx_stats;
+
+int impgx_abi_version(void);
+const char *impgx_last_error(void);
+int impgx_device_count(void);
+
+/* Replaces Impg::from_multi_alignment_records (src/impg.rs:1535-1652).
+ * `runs`/`run_offsets` hold the decoded CIGAR of every record (record i owns
+ * runs[run_offsets[i] .. run_offsets[i+1])), in PAF order; the library never
+ * reads PAF text at query time (the reference's per-hit pread+parse,
+ * src/impg.rs:495-552, is done once here). Inputs are borrowed for the call.
+ * `device` is the CUDA ordinal that will hold the index. */
+int impgx_index_build(const impgx_record *records, size_t n_records,
+                      const uint32_t *runs, const uint64_t *run_offsets,
+                      const uint64_t *seq_lens, uint32_t n_seqs,
+                      int bidirectional, int device, impgx_index **out);
+
+/* Convenience: parse_paf_file (src/paf.rs:118-194,306-362) + build. Sequence
+ * ids are assigned by first appearance in the file (query column first). */
+int impgx_index_from_paf(const char *paf_path, int bidirectional, int device,
+                         impgx_index **out);
+
+void impgx_index_free(impgx_index *idx);
+
+/* SequenceIndex accessors (src/seqidx.rs:22-56). */
+uint32_t impgx_index_num_seqs(const impgx_index *idx);
+uint64_t impgx_index_num_entries(const impgx_index *idx);
+uint64_t impgx_index_device_bytes(const impgx_index *idx);
+const char *impgx_index_seq_name(const impgx_index *idx, uint32_t id); /* NULL if unnamed */
+uint64_t impgx_index_seq_len(const impgx_index *idx, uint32_t id);
+int impgx_index_seq_id(const impgx_index *idx, const char *name, uint32_t *id_out);
+int impgx_index_set_names(impgx_index *idx, const char *const *names, uint32_t n);
+
+/* The batch entry: replaces the serial BED loop + perform_query
+ * (src/main.rs:7435-7456, :11605-11707). `ranges` is a HOST array. Results
+ * are every AdjustedInterval of every row in the reference's order. */
+int impgx_query_batch(impgx_index *idx, const impgx_range *ranges, size_t n,
+                      const impgx_params *params, impgx_results **out);
+
+/* Same, followed on the device by output_results_bed's two merges
+ * (merge_adjusted_intervals_gap_2d then merge_query_adjusted_intervals,
+ * src/main.rs:11849-11866, :12858-13011, :12474-12560). Result rows are the
+ * BED rows the reference would print (q columns; t columns are the merged
+ * boxes' targets and are not part of BED). */
+int impgx_query_batch_bed(impgx_index *idx, const impgx_range *ranges, size_t n,
+                          const impgx_params *params, impgx_results **out);
+
+/* Device-resident variants: `d_ranges` is a DEVICE pointer to n ranges that
+ * are already in HBM; results stay in HBM (impgx_results_device_view). Used to
+ * time the path with no host<->device copy in the timed region. `stream` is a
+ * cudaStream_t (NULL = default stream). */
+int impgx_query_batch_bed_device(impgx_index *idx, const impgx_range *d_ranges,
+                                 size_t n, const impgx_params *params,
+                                 void *stream, impgx_results **out);
+
+int impgx_results_view(const impgx_results *res, impgx_view *view);        /* host columns */
+int impgx_results_device_view(const impgx_results *res, impgx_view *view); /* device columns */
+void impgx_results_free(impgx_results *res);
+
+int impgx_index_stats(const impgx_index *idx, impgx_stats *out);
+
+/* Single-hit liftover, the KAT surface of project_target_range_through_alignment
+ * (src/impg.rs:2760-2898): runs the liftover kernel on n independent
+ * (request, record, runs) problems. out4 = {q_start,q_end,t_start,t_end} per
+ * problem, ok[i] = 1 iff the reference returns Some. With out_runs != NULL the
+ * clipped run slices are returned (out_run_offsets has n+1 entries). */
+int impgx_project_batch(int device, size_t n, const int32_t *req_start,
+                        const int32_t *req_end, const impgx_record *records,
+                        const uint32_t *runs, const uint64_t *run_offsets,
+                        int32_t *out4, uint8_t *ok, uint64_t *out_run_offsets,
+                        uint32_t *out_runs, size_t out_runs_cap);
+
+/* Host-side text helpers mirroring the reference's parsers and writers. */
+/* parse_cigar_to_delta (src/impg.rs:2935-2950). Returns run count or <0. */
+long impgx_parse_cigar(const char *text, size_t len, uint32_t *out, size_t cap);
+/* output_results_bed line formatting (src/main.rs:11867-11889) for row `row`
+ * of a merged result set. Returns a malloc'ed string (caller frees with
+ * impgx_free) or NULL. */
+char *impgx_format_bed(const impgx_index *idx, const impgx_results *res,
+                       size_t row, const char *name);
+void impgx_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMPGX_H */

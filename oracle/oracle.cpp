@@ -1,0 +1,1704 @@
+/*
+ * oracle.cpp — TEST INFRASTRUCTURE ONLY. Not part of the product.
+ *
+ * A single-threaded (optionally OpenMP for the baseline driver) CPU
+ * restatement of the reference algorithm for the projection hot path of
+ * pangenome/impg, written to be obviously faithful rather than fast. Only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+ * reference legs may load this library; libimpgx never links or calls it.
+ *
+ * Every function cites the reference file:line it follows (paths relative to
+ * the reference checkout).
+ *
+ * PARITY PINNING: the liftover, CIGAR parse/invert and PAF parse functions are
+ * pinned against every known-answer test the reference holds for them
+ * (src/impg.rs:2981-3264, src/paf.rs:368-415; see tests/test_oracle_kat.py).
+ * The behavioural CLI scenarios of tests/test_transitive_integrity.rs are
+ * replayed in tests/test_oracle_scenarios.py.
+ * PARITY UNPINNED for: (1) hit VISIT ORDER — it is defined by coitrees 0.4.0
+ * (Cargo.lock:643-646, crates.io, source not in /root/reference); the
+ * BasicCOITree construction/query below restates its published algorithm from
+ * memory (constant SIMPLE_SUBTREE_CUTOFF is the one tunable); (2) the three
+ * merge functions and SortedRanges::insert, which no reference test pins —
+ * they are restated literally from source; (3) sequence-id numbering, which
+ * in the reference follows FxHashMap iteration order (src/main.rs:11527-11540)
+ * — here ids are first-appearance order.
+ */
+#include <algorithm>
+#include <cassert>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fcntl.h>
+#include <map>
+#include <string>
+#include <sys/stat.h>
+#include <time.h>
+#include <unistd.h>
+#include <unordered_map>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "../include/impgx.h"
+
+namespace {
+
+// ---------------------------------------------------------------- CigarOp
+// src/impg.rs:76-140
+struct CigarOp {
+  uint32_t val;
+  static bool valid_char(char c) { return c == '=' || c == 'X' || c == 'I' || c == 'D' || c == 'M'; }
+  static CigarOp make(int32_t len, char op) {
+    uint32_t v = 0;
+    switch (op) {
+      case '=': v = 0; break;
+      case 'X': v = 1; break;
+      case 'I': v = 2; break;
+      case 'D': v = 3; break;
+      case 'M': v = 4; break;
+      default: fprintf(stderr, "oracle: invalid CIGAR op %c\n", op); abort();
+    }
+    return CigarOp{(v << 29) | (uint32_t)len};
+  }
+  char op() const {
+    switch (val >> 29) {
+      case 0: return '=';
+      case 1: return 'X';
+      case 2: return 'I';
+      case 3: return 'D';
+      case 4: return 'M';
+      default: fprintf(stderr, "oracle: invalid CIGAR code %u\n", val >> 29); abort();
+    }
+  }
+  int32_t len() const { return (int32_t)(val & ((1u << 29) - 1)); }
+  int32_t target_delta() const {
+    char o = op();
+    return o == 'I' ? 0 : len();
+  }
+  int32_t query_delta(bool rev) const {
+    char o = op();
+    if (o == 'D') return 0;
+    return rev ? -len() : len();
+  }
+  void adjust_len(int32_t d) { val = (val & (7u << 29)) | (uint32_t)(len() + d); }
+  bool operator==(const CigarOp &o) const { return val == o.val; }
+};
+
+// src/impg.rs:144-156
+void invert_cigar_ops_in_place(std::vector<CigarOp> &ops, bool strand_rev) {
+  for (auto &op : ops) {
+    char c = op.op();
+    char n = c == 'I' ? 'D' : (c == 'D' ? 'I' : c);
+    op = CigarOp::make(op.len(), n);
+  }
+  if (strand_rev) std::reverse(ops.begin(), ops.end());
+}
+
+// src/impg.rs:2935-2950. Returns false on an op the reference would panic on.
+bool parse_cigar_to_delta(const char *s, size_t n, std::vector<CigarOp> &ops) {
+  int32_t len = 0;
+  for (size_t i = 0; i < n; i++) {
+    unsigned char c = (unsigned char)s[i];
+    if (c >= '0' && c <= '9') {
+      len = len * 10 + (c - '0');
+    } else {
+      if (!CigarOp::valid_char((char)c)) return false;
+      ops.push_back(CigarOp::make(len, (char)c));
+      len = 0;
+    }
+  }
+  return true;
+}
+
+// src/impg.rs:2952-2973
+double calculate_gap_compressed_identity(const std::vector<CigarOp> &ops) {
+  int32_t m = 0, mm = 0, ins = 0, del = 0;
+  for (auto &op : ops) {
+    int32_t len = op.len();
+    switch (op.op()) {
+      case 'M':
+      case '=': m += len; break;
+      case 'X': mm += len; break;
+      case 'I': ins += 1; break;
+      case 'D': del += 1; break;
+    }
+  }
+  int32_t total = m + mm + ins + del;
+  if (total == 0) return 0.0;
+  return (double)m / (double)total;
+}
+
+// ---------------------------------------------------------------- liftover
+struct Projection {
+  int32_t q_start, q_end;
+  std::vector<CigarOp> ops;
+  int32_t t_start, t_end;
+};
+
+// src/impg.rs:2760-2898 (project_target_range_through_alignment)
+bool project_target_range_through_alignment(int32_t req_start, int32_t req_end,
+                                            int32_t target_start, int32_t target_end,
+                                            int32_t query_start, int32_t query_end,
+                                            bool strand_rev, const CigarOp *cigar_ops, size_t n_ops,
+                                            Projection &out) {
+  int32_t dir = strand_rev ? -1 : 1;
+  int32_t query_pos = strand_rev ? query_end : query_start;
+  int32_t target_pos = target_start;
+  size_t first_op_idx = 0, last_op_idx = 0;
+  bool found_overlap = false;
+  int32_t projected_query_start = -1, projected_query_end = -1;
+  int32_t projected_target_start = -1, projected_target_end = -1;
+  int32_t first_op_offset = 0, last_op_remaining = 0;
+  int32_t last_target_pos = std::min(target_end, req_end);
+
+  for (size_t curr_op_idx = 0; curr_op_idx < n_ops; curr_op_idx++) {
+    const CigarOp &cigar_op = cigar_ops[curr_op_idx];
+    if (target_pos > last_target_pos) break;
+    int32_t td = cigar_op.target_delta();
+    int32_t qd = cigar_op.query_delta(strand_rev);
+    if (td == 0) {
+      // (0, query_delta): insertion in query (or any zero-length op)
+      if (target_pos >= req_start) {
+        if (!found_overlap) {
+          projected_query_start = query_pos;
+          projected_target_start = target_pos;
+          first_op_idx = curr_op_idx;
+          found_overlap = true;
+        }
+        projected_query_end = query_pos + qd;
+        projected_target_end = target_pos;
+        last_op_idx = curr_op_idx + 1;
+      }
+      query_pos += qd;
+    } else if (qd == 0) {
+      // (target_delta, 0): deletion in query
+      int32_t overlap_start = std::max(target_pos, req_start);
+      int32_t overlap_end = std::min(target_pos + td, last_target_pos);
+      if (overlap_start < overlap_end) {
+        if (!found_overlap) {
+          projected_query_start = query_pos;
+          projected_target_start = overlap_start;
+          first_op_idx = curr_op_idx;
+          first_op_offset = overlap_start - target_pos;
+          found_overlap = true;
+        }
+        projected_query_end = query_pos;
+        projected_target_end = overlap_end;
+        last_op_idx = curr_op_idx + 1;
+        last_op_remaining = overlap_end - (target_pos + td);
+      }
+      target_pos += td;
+    } else {
+      // match / mismatch
+      int32_t overlap_start = std::max(target_pos, req_start);
+      int32_t overlap_end = std::min(target_pos + td, req_end);
+      if (overlap_start < overlap_end) {
+        int32_t overlap_length = overlap_end - overlap_start;
+        int32_t query_overlap_start = query_pos + (overlap_start - target_pos) * dir;
+        int32_t query_overlap_end = query_overlap_start + overlap_length * dir;
+        if (!found_overlap) {
+          projected_query_start = query_overlap_start;
+          projected_target_start = overlap_start;
+          first_op_idx = curr_op_idx;
+          first_op_offset = overlap_start - target_pos;
+          found_overlap = true;
+        }
+        projected_query_end = query_overlap_end;
+        projected_target_end = overlap_end;
+        last_op_idx = curr_op_idx + 1;
+        last_op_remaining = overlap_end - (target_pos + td);
+      }
+      target_pos += td;
+      query_pos += qd;
+    }
+  }
+
+  if (found_overlap && projected_query_start != projected_query_end &&
+      projected_target_start != projected_target_end) {
+    out.ops.assign(cigar_ops + first_op_idx, cigar_ops + last_op_idx);
+    if (first_op_offset > 0) out.ops[0].adjust_len(-first_op_offset);
+    if (last_op_remaining < 0) out.ops[last_op_idx - first_op_idx - 1].adjust_len(last_op_remaining);
+    out.q_start = projected_query_start;
+    out.q_end = projected_query_end;
+    out.t_start = projected_target_start;
+    out.t_end = projected_target_end;
+    return true;
+  }
+  return false;
+}
+
+// ---------------------------------------------------------------- SortedRanges
+// src/impg.rs:242-369
+struct SortedRanges {
+  std::vector<std::pair<int32_t, int32_t>> ranges;
+  int32_t sequence_length = 0;
+  int32_t min_distance = 0;
+  SortedRanges() {}
+  SortedRanges(int32_t len, int32_t md) : sequence_length(len), min_distance(md) {}
+
+  // binary_search_by_key(&key, |&(s,_)| s): Ok(pos)|Err(pos) both used as pos.
+  // Rust's binary search returns *a* matching index if several are equal;
+  // starts in `ranges` are strictly increasing so the match is unique.
+  size_t bsearch(int32_t key) const {
+    size_t lo = 0, hi = ranges.size();
+    while (lo < hi) {
+      size_t mid = lo + (hi - lo) / 2;
+      if (ranges[mid].first < key) lo = mid + 1;
+      else hi = mid;
+    }
+    return lo;
+  }
+
+  std::vector<std::pair<int32_t, int32_t>> insert(std::pair<int32_t, int32_t> new_range) {
+    int32_t start, end;
+    if (new_range.first <= new_range.second) {
+      start = new_range.first;
+      end = new_range.second;
+    } else {
+      start = new_range.second;
+      end = new_range.first;
+    }
+    size_t i = bsearch(start);
+    if (i > 0 && std::abs(start - ranges[i - 1].second) < min_distance) {
+      start = ranges[i - 1].second;
+      i -= 1;
+    } else if (start < min_distance) {
+      start = 0;
+    }
+    if (i < ranges.size() && std::abs(ranges[i].first - end) < min_distance) {
+      end = ranges[i].first;
+    } else if (end > (sequence_length - min_distance)) {
+      end = sequence_length;
+    }
+
+    std::vector<std::pair<int32_t, int32_t>> non_overlapping;
+    int32_t current = start;
+    i = bsearch(start);
+    if (i > 0 && ranges[i - 1].second > start) i -= 1;
+    while (i < ranges.size() && current < end) {
+      int32_t range_start = ranges[i].first, range_end = ranges[i].second;
+      if (range_start > end) break;
+      if (current < range_start) non_overlapping.push_back({current, range_start});
+      current = std::max(current, range_end);
+      i += 1;
+    }
+    if (current < end) non_overlapping.push_back({current, end});
+
+    size_t pos = bsearch(start);
+    if (pos > 0 && ranges[pos - 1].second >= start) {
+      ranges[pos - 1].second = std::max(ranges[pos - 1].second, end);
+      merge_forward_from(pos - 1);
+    } else if (pos < ranges.size() && end >= ranges[pos].first) {
+      ranges[pos].first = std::min(start, ranges[pos].first);
+      ranges[pos].second = std::max(end, ranges[pos].second);
+      merge_forward_from(pos);
+    } else {
+      ranges.insert(ranges.begin() + pos, {start, end});
+    }
+    return non_overlapping;
+  }
+
+  void merge_forward_from(size_t start_idx) {
+    size_t write = start_idx, read = start_idx + 1;
+    while (read < ranges.size()) {
+      if (ranges[write].second >= ranges[read].first) {
+        ranges[write].second = std::max(ranges[write].second, ranges[read].second);
+      } else {
+        write += 1;
+        std::swap(ranges[write], ranges[read]);
+      }
+      read += 1;
+    }
+    ranges.resize(write + 1);
+  }
+};
+
+// ---------------------------------------------------------------- index
+// src/impg.rs:164-223 (QueryMetadata); CIGAR source is either the decoded run
+// stream (aln ordinal) or, in faithful mode, (file offset, byte length).
+struct QueryMetadata {
+  uint32_t query_id;
+  int32_t target_start, target_end, query_start, query_end;
+  bool strand_rev;
+  bool reversed;
+  uint64_t aln;          // alignment ordinal into run_offsets
+  uint64_t data_offset;  // byte offset of CIGAR text in the PAF (faithful mode)
+  uint64_t data_bytes;
+};
+
+struct Node {
+  int32_t first, last;
+  QueryMetadata meta;
+};
+
+// coitrees 0.4.0 BasicCOITree, restated (third-party, un-vendored; see header).
+// Nodes are stably sorted by `first`; the search tree over the sorted array
+// [s,e) has root s+(e-s)/2; a "childless" van-Emde-Boas bottom subtree of size
+// <= SIMPLE_SUBTREE_CUTOFF is stored as a sorted run and scanned linearly.
+// query() visits: root, then left subtree, then right subtree; a simple
+// subtree is visited in sorted order. The vEB layout only changes memory
+// placement, so it is not modelled.
+static const size_t SIMPLE_SUBTREE_CUTOFF = 8;
+
+struct COITree {
+  std::vector<Node> nodes;           // sorted by first (stable)
+  std::vector<int32_t> subtree_last; // per tree node (indexed by sorted position of subtree root)
+  std::vector<uint8_t> simple_root;  // 1 if the subtree rooted here (as midpoint of its span) is simple
+
+  // Spans are implicit: the subtree whose root is at sorted position r is
+  // identified during the recursive descent by (s,e).
+  static int floor_log2(size_t n) {
+    int k = -1;
+    while (n) { n >>= 1; k++; }
+    return k;
+  }
+
+  void build(std::vector<Node> &&in) {
+    nodes = std::move(in);
+    // veb_order(): presorted check then LSD radix sort on `first` == stable sort
+    std::stable_sort(nodes.begin(), nodes.end(),
+                     [](const Node &a, const Node &b) { return a.first < b.first; });
+    size_t n = nodes.size();
+    subtree_last.assign(n, 0);
+    simple_root.assign(n, 0);
+    if (n) mark(0, n, 0, 0);
+  }
+
+  // Returns max `last` over [s,e). `chunk_depth` is the depth at which the
+  // next childless vEB bottom subtree starts (veb_order_recursion: childless
+  // && subtree_size <= cutoff → simple; else pivot = min + (max-min)/2 and the
+  // bottom subtrees start at pivot+1).
+  int32_t mark(size_t s, size_t e, int depth, int chunk_depth) {
+    size_t n = e - s;
+    size_t root = s + n / 2;
+    if (depth == chunk_depth) {
+      if (n <= SIMPLE_SUBTREE_CUTOFF) {
+        int32_t m = nodes[s].last;
+        for (size_t i = s; i < e; i++) m = std::max(m, nodes[i].last);
+        simple_root[root] = 1;
+        subtree_last[root] = m;
+        return m;
+      }
+      int max_depth = depth + floor_log2(n);
+      int pivot = depth + (max_depth - depth) / 2;
+      chunk_depth = pivot + 1;
+    }
+    int32_t m = nodes[root].last;
+    if (root > s) m = std::max(m, mark(s, root, depth + 1, chunk_depth));
+    if (root + 1 < e) m = std::max(m, mark(root + 1, e, depth + 1, chunk_depth));
+    subtree_last[root] = m;
+    return m;
+  }
+
+  template <class F>
+  void query(int32_t first, int32_t last, F &&visit) const {
+    if (!nodes.empty()) rec(0, nodes.size(), first, last, visit);
+  }
+
+  // query_recursion (closed-interval overlap: a.first <= last && first <= a.last)
+  template <class F>
+  void rec(size_t s, size_t e, int32_t first, int32_t last, F &visit) const {
+    size_t root = s + (e - s) / 2;
+    if (simple_root[root]) {
+      for (size_t i = s; i < e; i++) {
+        if (last < nodes[i].first) break;
+        if (first <= nodes[i].last) visit(nodes[i]);
+      }
+      return;
+    }
+    const Node &nd = nodes[root];
+    if (nd.first <= last && first <= nd.last) visit(nd);
+    if (root > s) {
+      size_t l = s + (root - s) / 2;
+      if (subtree_last[l] >= first) rec(s, root, first, last, visit);
+    }
+    if (root + 1 < e) {
+      size_t r = (root + 1) + (e - root - 1) / 2;
+      // overlaps(node.first, right.subtree_last, first, last)
+      if (nd.first <= last && first <= subtree_last[r]) rec(root + 1, e, first, last, visit);
+    }
+  }
+};
+
+struct Result {
+  uint32_t q_id;
+  int32_t q_first, q_last;
+  std::vector<CigarOp> cigar;
+  uint32_t t_id;
+  int32_t t_first, t_last;
+};
+
+struct Index {
+  std::vector<uint64_t> seq_lens;
+  std::vector<std::string> names;
+  std::unordered_map<std::string, uint32_t> name_to_id;
+  std::map<uint32_t, COITree> trees;
+  // decoded CIGAR source
+  std::vector<uint32_t> runs;
+  std::vector<uint64_t> run_offsets;
+  // faithful source (per-hit pread + parse, src/impg.rs:495-552,:2903-2950)
+  bool faithful = false;
+  std::string paf_path;
+  int fd = -1;
+  size_t n_records = 0;
+
+  ~Index() {
+    if (fd >= 0) close(fd);
+  }
+
+  // src/impg.rs:495-552 get_cigar_ops (PAF branch)
+  bool get_cigar_ops(const QueryMetadata &m, std::vector<CigarOp> &ops) const {
+    ops.clear();
+    if (faithful) {
+      if (m.data_bytes == 0) return false;  // reference panics: no cg:Z tag
+      static thread_local std::vector<char> buf;
+      buf.resize(m.data_bytes);
+      size_t got = 0;
+      while (got < m.data_bytes) {
+        ssize_t r = pread(fd, buf.data() + got, m.data_bytes - got, (off_t)(m.data_offset + got));
+        if (r <= 0) return false;
+        got += (size_t)r;
+      }
+      // std::str::from_utf8 validation (ASCII CIGAR: every byte < 0x80)
+      for (size_t i = 0; i < m.data_bytes; i++)
+        if ((unsigned char)buf[i] >= 0x80) return false;
+      ops.reserve(64);
+      if (!parse_cigar_to_delta(buf.data(), m.data_bytes, ops)) return false;
+    } else {
+      uint64_t a = run_offsets[m.aln], b = run_offsets[m.aln + 1];
+      ops.resize(b - a);
+      for (uint64_t i = a; i < b; i++) ops[i - a] = CigarOp{runs[i]};
+    }
+    if (m.reversed) invert_cigar_ops_in_place(ops, m.strand_rev);
+    return true;
+  }
+
+  // src/impg.rs:1102-1313 project_overlapping_interval (PAF fallback branch :1260-1312)
+  bool project_overlapping_interval(const QueryMetadata &m, uint32_t target_id, int32_t rs,
+                                    int32_t re, double min_identity, Result &out) const {
+    std::vector<CigarOp> ops;
+    if (!get_cigar_ops(m, ops)) {
+      fprintf(stderr, "oracle: cannot fetch CIGAR (reference would panic)\n");
+      abort();
+    }
+    Projection p;
+    if (!project_target_range_through_alignment(rs, re, m.target_start, m.target_end, m.query_start,
+                                                m.query_end, m.strand_rev, ops.data(), ops.size(), p))
+      return false;
+    if (!std::isnan(min_identity)) {
+      if (calculate_gap_compressed_identity(p.ops) < min_identity) return false;
+    }
+    out.q_id = m.query_id;
+    out.q_first = p.q_start;
+    out.q_last = p.q_end;
+    out.cigar = std::move(p.ops);
+    out.t_id = target_id;
+    out.t_first = p.t_start;
+    out.t_last = p.t_end;
+    return true;
+  }
+};
+
+// src/impg.rs:1535-1652 from_multi_alignment_records (single file)
+struct RecExtra {
+  uint64_t data_offset, data_bytes;
+};
+void build_trees(Index &idx, const impgx_record *recs, size_t n, const RecExtra *extra,
+                 bool bidirectional) {
+  std::map<uint32_t, std::vector<Node>> intervals;
+  for (size_t i = 0; i < n; i++) {
+    const impgx_record &r = recs[i];
+    QueryMetadata fwd{r.query_id,    r.target_start, r.target_end, r.query_start,
+                      r.query_end,   r.strand != 0,  false,        (uint64_t)i,
+                      extra ? extra[i].data_offset : 0, extra ? extra[i].data_bytes : 0};
+    intervals[r.target_id].push_back(Node{r.target_start, r.target_end, fwd});
+    if (bidirectional && r.query_id != r.target_id) {
+      QueryMetadata rev{r.target_id,    r.query_start, r.query_end, r.target_start,
+                        r.target_end,   r.strand != 0, true,        (uint64_t)i,
+                        extra ? extra[i].data_offset : 0, extra ? extra[i].data_bytes : 0};
+      intervals[r.query_id].push_back(Node{r.query_start, r.query_end, rev});
+    }
+  }
+  for (auto &kv : intervals) idx.trees[kv.first].build(std::move(kv.second));
+  idx.n_records = n;
+}
+
+// ---------------------------------------------------------------- queries
+struct QParams {
+  uint32_t max_depth;
+  int32_t min_transitive_len;
+  int32_t min_distance_between_ranges;
+  int32_t min_output_length;  // <0 none
+  bool store_cigar;
+  double min_identity;  // NaN none
+  const uint8_t *subset_mask;
+};
+
+// src/impg.rs:1852-1928
+std::vector<Result> query(const Index &idx, uint32_t target_id, int32_t rs, int32_t re,
+                          bool store_cigar, double min_identity) {
+  std::vector<Result> results;
+  Result self;
+  self.q_id = target_id;
+  self.q_first = rs;
+  self.q_last = re;
+  if (store_cigar) self.cigar.push_back(CigarOp::make(re - rs, '='));
+  self.t_id = target_id;
+  self.t_first = rs;
+  self.t_last = re;
+  results.push_back(std::move(self));
+  auto it = idx.trees.find(target_id);
+  if (it != idx.trees.end()) {
+    it->second.query(rs, re, [&](const Node &iv) {
+      Result r;
+      if (idx.project_overlapping_interval(iv.meta, target_id, rs, re, min_identity, r)) {
+        if (!store_cigar) r.cigar.clear();
+        results.push_back(std::move(r));
+      }
+    });
+  }
+  return results;
+}
+
+// Shared by BFS and DFS: the sequential fold step for one hit
+// (src/impg.rs:2507-2558 / :2231-2281). Appends expandable pieces to `out`.
+template <class PushPiece>
+void consider_for_expansion(const Index &idx, std::map<uint32_t, SortedRanges> &visited,
+                            uint32_t query_id, int32_t aq_start, int32_t aq_end,
+                            const QParams &p, bool short_circuit, PushPiece &&push) {
+  auto it = visited.find(query_id);
+  if (it == visited.end())
+    it = visited.emplace(query_id, SortedRanges((int32_t)idx.seq_lens[query_id], 0)).first;
+  SortedRanges &ranges = it->second;
+  bool should_add = true;
+  if (p.min_distance_between_ranges > 0) {
+    int32_t new_min = std::min(aq_start, aq_end), new_max = std::max(aq_start, aq_end);
+    size_t i = ranges.bsearch(new_min);
+    if (i > 0) {
+      int32_t prev_end = ranges.ranges[i - 1].second;
+      if (std::abs(new_min - prev_end) < p.min_distance_between_ranges) should_add = false;
+    }
+    if ((should_add || !short_circuit) && i < ranges.ranges.size()) {
+      int32_t next_start = ranges.ranges[i].first;
+      if (std::abs(next_start - new_max) < p.min_distance_between_ranges) should_add = false;
+    }
+  }
+  if (should_add) {
+    auto pieces = ranges.insert({aq_start, aq_end});
+    for (auto &pc : pieces)
+      if (std::abs(pc.second - pc.first) >= p.min_transitive_len) push(query_id, pc.first, pc.second);
+  }
+}
+
+struct Hit {
+  Result r;
+  uint32_t current_target_id;
+};
+
+// stab + project one frontier range (src/impg.rs:2388-2463); used by BFS and DFS
+void stab_range(const Index &idx, uint32_t original_target, uint32_t cur_id, int32_t cs, int32_t ce,
+                const QParams &p, std::vector<Result> &local) {
+  auto it = idx.trees.find(cur_id);
+  if (it == idx.trees.end()) return;
+  it->second.query(cs, ce, [&](const Node &iv) {
+    int32_t os = std::max(cs, iv.first), oe = std::min(ce, iv.last);
+    if (os >= oe) return;
+    Result r;
+    if (!idx.project_overlapping_interval(iv.meta, cur_id, os, oe, p.min_identity, r)) return;
+    bool keep = true;
+    if (p.subset_mask) keep = (r.q_id == original_target) || p.subset_mask[r.q_id] != 0;
+    if (!keep) return;
+    if (!p.store_cigar) r.cigar.clear();
+    local.push_back(std::move(r));
+  });
+}
+
+// src/impg.rs:2311-2597. `threads` > 1 parallelises the per-level stab like
+// rayon's par_iter (:2384-2465); results are identical for any thread count.
+std::vector<Result> query_transitive_bfs(const Index &idx, uint32_t target_id, int32_t rs, int32_t re,
+                                         const QParams &p, int threads) {
+  std::map<uint32_t, SortedRanges> visited;
+  auto vit = visited.emplace(target_id, SortedRanges((int32_t)idx.seq_lens[target_id], 0)).first;
+  auto filtered = vit->second.insert({rs, re});
+  std::vector<Result> results;
+  for (auto &f : filtered) {
+    Result r;
+    r.q_id = r.t_id = target_id;
+    r.q_first = r.t_first = f.first;
+    r.q_last = r.t_last = f.second;
+    if (p.store_cigar) r.cigar.push_back(CigarOp::make(f.second - f.first, '='));
+    results.push_back(std::move(r));
+  }
+  struct Rng {
+    uint32_t id;
+    int32_t s, e;
+  };
+  std::vector<Rng> current;
+  for (auto &f : filtered)
+    if (std::abs(f.first - f.second) >= p.min_transitive_len) current.push_back({target_id, f.first, f.second});
+  uint32_t depth = 0;
+  while (!current.empty() && (p.max_depth == 0 || depth < p.max_depth)) {
+    std::vector<std::vector<Result>> qres(current.size());
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads) if (threads > 1)
+#endif
+    for (long i = 0; i < (long)current.size(); i++)
+      stab_range(idx, target_id, current[i].id, current[i].s, current[i].e, p, qres[i]);
+    (void)threads;
+    std::vector<Rng> next;
+    for (size_t i = 0; i < current.size(); i++) {
+      uint32_t cur_id = current[i].id;
+      for (auto &r : qres[i]) {
+        int32_t length = std::abs(r.q_last - r.q_first);
+        bool out_ok = p.min_output_length < 0 || length >= p.min_output_length;
+        uint32_t qid = r.q_id;
+        int32_t aqs = r.q_first, aqe = r.q_last;
+        if (out_ok) results.push_back(std::move(r));
+        if (qid != cur_id) {
+          consider_for_expansion(idx, visited, qid, aqs, aqe, p, true,
+                                 [&](uint32_t id, int32_t s, int32_t e) { next.push_back({id, s, e}); });
+        }
+      }
+    }
+    depth += 1;
+    if (!next.empty()) {
+      std::stable_sort(next.begin(), next.end(), [](const Rng &a, const Rng &b) {
+        return a.id != b.id ? a.id < b.id : a.s < b.s;
+      });
+      size_t write = 0;
+      for (size_t read = 1; read < next.size(); read++) {
+        if (next[write].id == next[read].id && next[write].e >= next[read].s) {
+          next[write].e = std::max(next[write].e, next[read].e);
+        } else {
+          write += 1;
+          std::swap(next[write], next[read]);
+        }
+      }
+      next.resize(write + 1);
+    }
+    current = std::move(next);
+  }
+  return results;
+}
+
+// src/impg.rs:2057-2309
+std::vector<Result> query_transitive_dfs(const Index &idx, uint32_t target_id, int32_t rs, int32_t re,
+                                         const QParams &p) {
+  std::map<uint32_t, SortedRanges> visited;
+  auto vit = visited.emplace(target_id, SortedRanges((int32_t)idx.seq_lens[target_id], 0)).first;
+  auto filtered = vit->second.insert({rs, re});
+  std::vector<Result> results;
+  struct Item {
+    uint32_t id;
+    int32_t s, e;
+    uint32_t depth;
+  };
+  std::vector<Item> stack;
+  for (auto &f : filtered) {
+    Result r;
+    r.q_id = r.t_id = target_id;
+    r.q_first = r.t_first = f.first;
+    r.q_last = r.t_last = f.second;
+    if (p.store_cigar) r.cigar.push_back(CigarOp::make(f.second - f.first, '='));
+    results.push_back(std::move(r));
+    if (std::abs(f.first - f.second) >= p.min_transitive_len) stack.push_back({target_id, f.first, f.second, 0});
+  }
+  while (!stack.empty()) {
+    Item cur = stack.back();
+    stack.pop_back();
+    if (p.max_depth > 0 && cur.depth >= p.max_depth) continue;
+    std::vector<Result> hits;
+    stab_range(idx, target_id, cur.id, cur.s, cur.e, p, hits);
+    for (auto &r : hits) {
+      int32_t length = std::abs(r.q_last - r.q_first);
+      bool out_ok = p.min_output_length < 0 || length >= p.min_output_length;
+      uint32_t qid = r.q_id;
+      int32_t aqs = r.q_first, aqe = r.q_last;
+      if (out_ok) results.push_back(std::move(r));
+      if (qid != cur.id) {
+        consider_for_expansion(idx, visited, qid, aqs, aqe, p, false, [&](uint32_t id, int32_t s, int32_t e) {
+          stack.push_back({id, s, e, cur.depth + 1});
+        });
+      }
+    }
+    // :2289-2304 — note: runs even when the stack is empty (truncate(write+1)
+    // on an empty Vec is a no-op in Rust).
+    std::stable_sort(stack.begin(), stack.end(), [](const Item &a, const Item &b) {
+      return a.id != b.id ? a.id < b.id : a.s < b.s;
+    });
+    if (!stack.empty()) {
+      size_t write = 0;
+      for (size_t read = 1; read < stack.size(); read++) {
+        if (stack[write].id == stack[read].id && stack[write].e >= stack[read].s) {
+          stack[write].e = std::max(stack[write].e, stack[read].e);
+        } else {
+          write += 1;
+          std::swap(stack[write], stack[read]);
+        }
+      }
+      stack.resize(write + 1);
+    }
+  }
+  return results;
+}
+
+// src/main.rs:11605-11707 perform_query (after name→id)
+std::vector<Result> perform_query(const Index &idx, uint32_t target_id, int32_t rs, int32_t re,
+                                  uint32_t mode, const QParams &p, int threads) {
+  if (mode == IMPGX_MODE_BFS) return query_transitive_bfs(idx, target_id, rs, re, p, threads);
+  if (mode == IMPGX_MODE_DFS) return query_transitive_dfs(idx, target_id, rs, re, p);
+  auto res = query(idx, target_id, rs, re, p.store_cigar, p.min_identity);
+  if (p.min_output_length >= 0) {
+    res.erase(std::remove_if(res.begin(), res.end(),
+                             [&](const Result &r) { return std::abs(r.q_last - r.q_first) < p.min_output_length; }),
+              res.end());
+  }
+  if (p.subset_mask) {
+    // apply_subset_filter: keep the query target itself and whitelisted names
+    res.erase(std::remove_if(res.begin(), res.end(),
+                             [&](const Result &r) { return !(r.q_id == target_id || p.subset_mask[r.q_id]); }),
+              res.end());
+  }
+  return res;
+}
+
+// ---------------------------------------------------------------- merges
+// src/main.rs:13014-13034
+void merge_consecutive_cigar_ops(std::vector<CigarOp> &cigar) {
+  if (cigar.size() <= 1) return;
+  size_t w = 0;
+  for (size_t r = 1; r < cigar.size(); r++) {
+    if (cigar[w].op() == cigar[r].op()) {
+      cigar[w] = CigarOp::make(cigar[w].len() + cigar[r].len(), cigar[w].op());
+    } else {
+      w += 1;
+      if (w != r) cigar[w] = cigar[r];
+    }
+  }
+  cigar.resize(w + 1);
+}
+
+// src/main.rs:12474-12560
+void merge_query_adjusted_intervals(std::vector<Result> &results, int32_t merge_distance, bool merge_strands) {
+  if (!(results.size() > 1 && (merge_distance >= 0 || merge_strands))) return;
+  std::stable_sort(results.begin(), results.end(), [](const Result &a, const Result &b) {
+    bool af = a.q_first <= a.q_last, bf = b.q_first <= b.q_last;
+    int32_t as = af ? a.q_first : a.q_last, bs = bf ? b.q_first : b.q_last;
+    if (a.q_id != b.q_id) return a.q_id < b.q_id;
+    if (as != bs) return as < bs;
+    return (int)!af < (int)!bf;
+  });
+  size_t write_idx = 0;
+  for (size_t read_idx = 1; read_idx < results.size(); read_idx++) {
+    Result &cur = results[write_idx];
+    Result &nxt = results[read_idx];
+    bool cf = cur.q_first <= cur.q_last, nf = nxt.q_first <= nxt.q_last;
+    int32_t cs = cf ? cur.q_first : cur.q_last, ce = cf ? cur.q_last : cur.q_first;
+    int32_t ns = nf ? nxt.q_first : nxt.q_last, ne = nf ? nxt.q_last : nxt.q_first;
+    if (merge_distance < 0 || cur.q_id != nxt.q_id || (!merge_strands && cf != nf) ||
+        ns > ce + merge_distance) {
+      write_idx += 1;
+      if (write_idx != read_idx) std::swap(results[write_idx], results[read_idx]);
+    } else {
+      int32_t ms = std::min(cs, ns), me = std::max(ce, ne);
+      bool mf;
+      if (merge_strands && cf != nf) {
+        // saturating_sub on i32 with end>=start is plain subtraction
+        int64_t cl = (int64_t)ce - cs, nl = (int64_t)ne - ns;
+        mf = nl > cl ? nf : cf;
+      } else {
+        mf = cf;
+      }
+      if (mf) {
+        results[write_idx].q_first = ms;
+        results[write_idx].q_last = me;
+      } else {
+        results[write_idx].q_first = me;
+        results[write_idx].q_last = ms;
+      }
+    }
+  }
+  results.resize(write_idx + 1);
+}
+
+// src/main.rs:12858-13011
+void merge_adjusted_intervals_gap_2d(std::vector<Result> &results, int32_t merge_distance) {
+  if (results.size() <= 1 || merge_distance < 0) return;
+  int64_t d = merge_distance;
+  size_t n = results.size();
+  struct Key {
+    uint32_t q, t;
+    bool fwd;
+    bool operator<(const Key &o) const {
+      if (q != o.q) return q < o.q;
+      if (t != o.t) return t < o.t;
+      return fwd < o.fwd;
+    }
+  };
+  std::map<Key, std::vector<size_t>> groups;  // iteration order does not affect the partition
+  for (size_t i = 0; i < n; i++) {
+    bool fwd = results[i].q_first <= results[i].q_last;
+    groups[Key{results[i].q_id, results[i].t_id, fwd}].push_back(i);
+  }
+  std::vector<size_t> parent(n);
+  for (size_t i = 0; i < n; i++) parent[i] = i;
+  auto uf_find = [&](size_t x) {
+    while (parent[x] != x) {
+      parent[x] = parent[parent[x]];
+      x = parent[x];
+    }
+    return x;
+  };
+  for (auto &kv : groups) {
+    bool strand_fwd = kv.first.fwd;
+    auto &indices = kv.second;
+    std::stable_sort(indices.begin(), indices.end(), [&](size_t a, size_t b) {
+      int64_t ka = strand_fwd ? (int64_t)results[a].q_first : -(int64_t)results[a].q_first;
+      int64_t kb = strand_fwd ? (int64_t)results[b].q_first : -(int64_t)results[b].q_first;
+      return ka < kb;
+    });
+    for (size_t a_pos = 0; a_pos < indices.size(); a_pos++) {
+      size_t ia = indices[a_pos];
+      const Result &A = results[ia];
+      int64_t qa_start = strand_fwd ? A.q_first : A.q_last;
+      int64_t qa_end = strand_fwd ? A.q_last : A.q_first;
+      int64_t ta_start = A.t_first, ta_end = A.t_last;
+      for (size_t b_pos = a_pos + 1; b_pos < indices.size(); b_pos++) {
+        size_t ib = indices[b_pos];
+        const Result &B = results[ib];
+        int64_t qb_start = strand_fwd ? B.q_first : B.q_last;
+        if (qb_start < qa_start) continue;
+        int64_t q_gap = qb_start - qa_end;
+        if (q_gap > d) break;
+        int64_t tb_start = B.t_first, tb_end = B.t_last;
+        int64_t t_gap;
+        bool t_forward;
+        if (strand_fwd) {
+          t_gap = tb_start - ta_end;
+          t_forward = tb_start > ta_start;
+        } else {
+          t_gap = ta_start - tb_end;
+          t_forward = tb_end < ta_end;
+        }
+        if (!t_forward || t_gap > d) continue;
+        size_t ra = uf_find(ia), rb = uf_find(ib);
+        if (ra != rb) parent[ra] = rb;
+      }
+    }
+  }
+  std::map<size_t, std::vector<size_t>> buckets;
+  for (size_t i = 0; i < n; i++) buckets[uf_find(i)].push_back(i);
+  std::vector<Result> merged;
+  std::vector<bool> taken(n, false);
+  for (size_t i = 0; i < n; i++) {
+    if (taken[i]) continue;
+    size_t r = uf_find(i);
+    auto bit = buckets.find(r);
+    if (bit == buckets.end()) continue;
+    std::vector<size_t> members = std::move(bit->second);
+    buckets.erase(bit);
+    for (size_t m : members) taken[m] = true;
+    bool strand_fwd = results[members[0]].q_first <= results[members[0]].q_last;
+    std::vector<size_t> ordered = members;
+    std::stable_sort(ordered.begin(), ordered.end(), [&](size_t a, size_t b) {
+      int64_t ka = strand_fwd ? (int64_t)results[a].q_first : -(int64_t)results[a].q_first;
+      int64_t kb = strand_fwd ? (int64_t)results[b].q_first : -(int64_t)results[b].q_first;
+      return ka < kb;
+    });
+    const Result &first = results[ordered[0]];
+    int32_t q_lo = first.q_first, q_hi = first.q_last, t_lo = first.t_first, t_hi = first.t_last;
+    Result out;
+    out.q_id = first.q_id;
+    out.t_id = first.t_id;
+    for (size_t k : ordered) {
+      const Result &x = results[k];
+      if (strand_fwd) {
+        q_lo = std::min(q_lo, x.q_first);
+        q_hi = std::max(q_hi, x.q_last);
+      } else {
+        q_lo = std::max(q_lo, x.q_first);
+        q_hi = std::min(q_hi, x.q_last);
+      }
+      t_lo = std::min(t_lo, x.t_first);
+      t_hi = std::max(t_hi, x.t_last);
+      out.cigar.insert(out.cigar.end(), x.cigar.begin(), x.cigar.end());
+    }
+    merge_consecutive_cigar_ops(out.cigar);
+    out.q_first = q_lo;
+    out.q_last = q_hi;
+    out.t_first = t_lo;
+    out.t_last = t_hi;
+    merged.push_back(std::move(out));
+  }
+  results = std::move(merged);
+}
+
+// src/main.rs:13054-13089
+std::vector<CigarOp> extract_cigar_suffix(const std::vector<CigarOp> &cigar, int32_t query_len, bool forward) {
+  std::vector<CigarOp> result;
+  int32_t remaining = query_len;
+  for (auto it = cigar.rbegin(); it != cigar.rend(); ++it) {
+    if (remaining <= 0) break;
+    int32_t qd = std::abs(it->query_delta(!forward));
+    if (qd <= remaining) {
+      result.push_back(*it);
+      remaining -= qd;
+    } else if (qd > 0) {
+      float scale = (float)remaining / (float)qd;
+      int32_t new_len = (int32_t)((float)it->len() * scale);
+      result.push_back(CigarOp::make(new_len, it->op()));
+      remaining = 0;
+    }
+  }
+  std::reverse(result.begin(), result.end());
+  return result;
+}
+
+// src/main.rs:13092-13124
+std::vector<CigarOp> extract_cigar_prefix(const std::vector<CigarOp> &cigar, int32_t query_len, bool forward) {
+  std::vector<CigarOp> result;
+  int32_t remaining = query_len;
+  for (auto &op : cigar) {
+    if (remaining <= 0) break;
+    int32_t qd = std::abs(op.query_delta(!forward));
+    if (qd <= remaining) {
+      result.push_back(op);
+      remaining -= qd;
+    } else if (qd > 0) {
+      float scale = (float)remaining / (float)qd;
+      int32_t new_len = (int32_t)((float)op.len() * scale);
+      result.push_back(CigarOp::make(new_len, op.op()));
+      remaining = 0;
+    }
+  }
+  return result;
+}
+
+// src/main.rs:13127-13180
+std::vector<CigarOp> trim_cigar_prefix(const std::vector<CigarOp> &cigar, int32_t query_len, int32_t target_len) {
+  std::vector<CigarOp> result;
+  int32_t qc = 0, tc = 0;
+  size_t start_idx = 0;
+  for (size_t idx = 0; idx < cigar.size(); idx++) {
+    const CigarOp &op = cigar[idx];
+    int32_t q_delta = std::abs(op.query_delta(false));
+    int32_t t_delta = op.target_delta();
+    if (qc + q_delta > query_len || tc + t_delta > target_len) {
+      int32_t q_rem = query_len - qc, t_rem = target_len - tc;
+      float skip_ratio;
+      if (q_delta > 0 && t_delta > 0)
+        skip_ratio = std::min((float)q_rem / (float)q_delta, (float)t_rem / (float)t_delta);
+      else if (q_delta > 0)
+        skip_ratio = (float)q_rem / (float)q_delta;
+      else if (t_delta > 0)
+        skip_ratio = (float)t_rem / (float)t_delta;
+      else
+        skip_ratio = 0.0f;
+      int32_t skip_len = (int32_t)((float)op.len() * skip_ratio);
+      if (skip_len < op.len()) result.push_back(CigarOp::make(op.len() - skip_len, op.op()));
+      start_idx = idx + 1;
+      break;
+    }
+    qc += q_delta;
+    tc += t_delta;
+    if (qc >= query_len && tc >= target_len) {
+      start_idx = idx + 1;
+      break;
+    }
+  }
+  result.insert(result.end(), cigar.begin() + start_idx, cigar.end());
+  return result;
+}
+
+// src/main.rs:12563-12845
+void merge_adjusted_intervals(std::vector<Result> &results, int32_t merge_distance) {
+  if (!(results.size() > 1 && merge_distance >= 0)) return;
+  std::stable_sort(results.begin(), results.end(), [](const Result &a, const Result &b) {
+    bool af = a.q_first < a.q_last, bf = b.q_first < b.q_last;
+    int32_t ap = af ? a.q_first : a.q_last, bp = bf ? b.q_first : b.q_last;
+    if (a.q_id != b.q_id) return a.q_id < b.q_id;
+    if (af != bf) return (int)af < (int)bf;
+    if (ap != bp) return ap < bp;
+    if (a.t_id != b.t_id) return a.t_id < b.t_id;
+    return a.t_first < b.t_first;
+  });
+  std::vector<Result> merged;
+  merged.reserve(results.size());
+  Result cur = std::move(results[0]);
+  for (size_t k = 1; k < results.size(); k++) {
+    Result nxt = std::move(results[k]);
+    bool qf = cur.q_first <= cur.q_last, nqf = nxt.q_first <= nxt.q_last;
+    if (cur.q_id != nxt.q_id || cur.t_id != nxt.t_id || qf != nqf) {
+      merged.push_back(std::move(cur));
+      cur = std::move(nxt);
+      continue;
+    }
+    bool q_contig, t_contig, q_overlap, t_overlap;
+    if (qf) {
+      q_contig = cur.q_last == nxt.q_first;
+      t_contig = cur.t_last == nxt.t_first;
+      q_overlap = cur.q_last > nxt.q_first;
+      t_overlap = cur.t_last > nxt.t_first;
+    } else {
+      q_contig = cur.q_first == nxt.q_last;
+      t_contig = cur.t_first == nxt.t_last;
+      q_overlap = cur.q_first > nxt.q_last;
+      t_overlap = cur.t_first < nxt.t_last;
+    }
+    if (q_contig && t_contig) {
+      if (qf) {
+        cur.q_last = nxt.q_last;
+        cur.t_last = nxt.t_last;
+        cur.cigar.insert(cur.cigar.end(), nxt.cigar.begin(), nxt.cigar.end());
+      } else {
+        cur.q_first = nxt.q_first;
+        cur.t_first = nxt.t_first;
+        std::vector<CigarOp> nc(nxt.cigar);
+        nc.insert(nc.end(), cur.cigar.begin(), cur.cigar.end());
+        cur.cigar = std::move(nc);
+      }
+      merge_consecutive_cigar_ops(cur.cigar);
+      continue;
+    }
+    if (q_overlap && t_overlap) {
+      int32_t qol, tol;
+      if (qf) {
+        qol = nxt.q_first - cur.q_last;
+        tol = nxt.t_first - cur.t_last;
+      } else {
+        qol = nxt.q_last - cur.q_first;
+        tol = cur.t_first - nxt.t_last;
+      }
+      if (qol > 0 && tol > 0) {
+        bool match = extract_cigar_suffix(cur.cigar, qol, qf) == extract_cigar_prefix(nxt.cigar, qol, qf);
+        if (match) {
+          auto trimmed = trim_cigar_prefix(nxt.cigar, qol, tol);
+          if (qf) {
+            cur.q_last = nxt.q_last;
+            cur.t_last = nxt.t_last;
+            cur.cigar.insert(cur.cigar.end(), trimmed.begin(), trimmed.end());
+          } else {
+            cur.q_first = nxt.q_first;
+            cur.t_first = nxt.t_first;
+            trimmed.insert(trimmed.end(), cur.cigar.begin(), cur.cigar.end());
+            cur.cigar = std::move(trimmed);
+          }
+          continue;
+        }
+      }
+    }
+    if (!q_overlap && !t_overlap) {
+      int32_t qg, tg;
+      if (qf) {
+        qg = nxt.q_first - cur.q_last;
+        tg = nxt.t_first - cur.t_last;
+      } else {
+        qg = cur.q_first - nxt.q_last;
+        tg = cur.t_first - nxt.t_last;
+      }
+      if (qg >= 0 && tg >= 0 && (qg > 0 || tg > 0) && qg <= merge_distance && tg <= merge_distance) {
+        std::vector<CigarOp> gap;
+        if (qg > 0) gap.push_back(CigarOp::make(qg, 'I'));
+        if (tg > 0) gap.push_back(CigarOp::make(tg, 'D'));
+        if (qf) {
+          cur.q_last = nxt.q_last;
+          cur.t_last = nxt.t_last;
+          cur.cigar.insert(cur.cigar.end(), gap.begin(), gap.end());
+          cur.cigar.insert(cur.cigar.end(), nxt.cigar.begin(), nxt.cigar.end());
+        } else {
+          cur.q_first = nxt.q_first;
+          cur.t_first = nxt.t_first;
+          std::vector<CigarOp> nc(nxt.cigar);
+          nc.insert(nc.end(), gap.begin(), gap.end());
+          nc.insert(nc.end(), cur.cigar.begin(), cur.cigar.end());
+          cur.cigar = std::move(nc);
+        }
+        merge_consecutive_cigar_ops(cur.cigar);
+        continue;
+      }
+    }
+    merged.push_back(std::move(cur));
+    cur = std::move(nxt);
+  }
+  merged.push_back(std::move(cur));
+  results = std::move(merged);
+}
+
+// ---------------------------------------------------------------- writers
+// Rust `{:.6}` on f32 then trim_end_matches('0').trim_end_matches('.')
+std::string fmt_f32_trim(float v) {
+  char buf[64];
+  if (std::isnan(v)) return "NaN";  // Rust prints NaN; C would print nan
+  if (std::isinf(v)) return v > 0 ? "inf" : "-inf";
+  snprintf(buf, sizeof buf, "%.6f", (double)v);
+  std::string s(buf);
+  while (!s.empty() && s.back() == '0') s.pop_back();
+  while (!s.empty() && s.back() == '.') s.pop_back();
+  return s;
+}
+
+std::string seq_name(const Index &idx, uint32_t id) {
+  if (id < idx.names.size() && !idx.names[id].empty()) return idx.names[id];
+  return "seq" + std::to_string(id);
+}
+
+// src/main.rs:11849-11892
+std::string output_results_bed(const Index &idx, std::vector<Result> &results, const std::string &name,
+                               int32_t d, bool merge_strands) {
+  bool any_empty = false;
+  for (auto &r : results) any_empty |= r.cigar.empty();
+  if (any_empty) merge_adjusted_intervals_gap_2d(results, d);
+  merge_query_adjusted_intervals(results, d, merge_strands);
+  std::string out;
+  for (auto &r : results) {
+    int32_t first, last;
+    char strand;
+    if (r.q_first <= r.q_last) {
+      first = r.q_first; last = r.q_last; strand = '+';
+    } else {
+      first = r.q_last; last = r.q_first; strand = '-';
+    }
+    out += seq_name(idx, r.q_id) + "\t" + std::to_string((uint32_t)first) + "\t" +
+           std::to_string((uint32_t)last) + "\t" + name + "\t.\t" + strand + "\n";
+  }
+  return out;
+}
+
+struct CigarStats {
+  int32_t matches = 0, mismatches = 0, insertions = 0, inserted_bp = 0, deletions = 0, deleted_bp = 0, block_len = 0;
+};
+CigarStats cigar_stats(const std::vector<CigarOp> &cigar) {
+  CigarStats s;
+  for (auto &op : cigar) {
+    int32_t len = op.len();
+    switch (op.op()) {
+      case 'M':
+      case '=': s.matches += len; s.block_len += len; break;
+      case 'X': s.mismatches += len; s.block_len += len; break;
+      case 'I': s.insertions += 1; s.inserted_bp += len; s.block_len += len; break;
+      case 'D': s.deletions += 1; s.deleted_bp += len; s.block_len += len; break;
+    }
+  }
+  return s;
+}
+
+// src/main.rs:11894-11987 (caller drops result[0] first, src/main.rs:7474)
+std::string output_results_bedpe(const Index &idx, std::vector<Result> &results, const std::string &name, int32_t d) {
+  bool any_empty = false;
+  for (auto &r : results) any_empty |= r.cigar.empty();
+  if (any_empty) merge_adjusted_intervals_gap_2d(results, d);
+  else merge_adjusted_intervals(results, d);
+  std::string out;
+  for (auto &r : results) {
+    int32_t first, last;
+    char strand;
+    if (r.q_first <= r.q_last) {
+      first = r.q_first; last = r.q_last; strand = '+';
+    } else {
+      first = r.q_last; last = r.q_first; strand = '-';
+    }
+    CigarStats s = cigar_stats(r.cigar);
+    float gi = (float)s.matches / (float)(s.matches + s.mismatches + s.insertions + s.deletions);
+    int32_t edit = s.mismatches + s.inserted_bp + s.deleted_bp;
+    float bi = (float)s.matches / (float)(s.matches + edit);
+    out += seq_name(idx, r.q_id) + "\t" + std::to_string((uint32_t)first) + "\t" + std::to_string((uint32_t)last) +
+           "\t" + seq_name(idx, r.t_id) + "\t" + std::to_string((uint32_t)r.t_first) + "\t" +
+           std::to_string((uint32_t)r.t_last) + "\t" + name + "\t0\t" + strand + "\t+\tgi:f:" + fmt_f32_trim(gi) +
+           "\tbi:f:" + fmt_f32_trim(bi) + "\n";
+  }
+  return out;
+}
+
+// src/main.rs:11989-12103
+std::string output_results_paf(const Index &idx, std::vector<Result> &results, const std::string &name, int32_t d) {
+  merge_adjusted_intervals(results, d);
+  std::string out;
+  for (auto &r : results) {
+    int32_t first, last;
+    char strand;
+    if (r.q_first <= r.q_last) {
+      first = r.q_first; last = r.q_last; strand = '+';
+    } else {
+      first = r.q_last; last = r.q_first; strand = '-';
+    }
+    CigarStats s = cigar_stats(r.cigar);
+    float gi = (float)s.matches / (float)(s.matches + s.mismatches + s.insertions + s.deletions);
+    int32_t edit = s.mismatches + s.inserted_bp + s.deleted_bp;
+    float bi = (float)s.matches / (float)(s.matches + edit);
+    std::string cg;
+    for (auto &op : r.cigar) {
+      cg += std::to_string(op.len());
+      cg += op.op();
+    }
+    out += seq_name(idx, r.q_id) + "\t" + std::to_string(idx.seq_lens[r.q_id]) + "\t" +
+           std::to_string((uint32_t)first) + "\t" + std::to_string((uint32_t)last) + "\t" + strand + "\t" +
+           seq_name(idx, r.t_id) + "\t" + std::to_string(idx.seq_lens[r.t_id]) + "\t" +
+           std::to_string((uint32_t)r.t_first) + "\t" + std::to_string((uint32_t)r.t_last) + "\t" +
+           std::to_string(s.matches) + "\t" + std::to_string(s.block_len) + "\t255\tgi:f:" + fmt_f32_trim(gi) +
+           "\tbi:f:" + fmt_f32_trim(bi) + "\tcg:Z:" + cg + "\tan:Z:" + name + "\n";
+  }
+  return out;
+}
+
+// ---------------------------------------------------------------- PAF parse
+// src/paf.rs:118-194 + src/seqidx.rs:22-35
+struct PafParsed {
+  std::vector<impgx_record> recs;
+  std::vector<RecExtra> extra;
+  std::vector<std::string> names;
+  std::vector<uint64_t> lens;
+  std::unordered_map<std::string, uint32_t> name_to_id;
+  std::string err;
+};
+
+bool parse_usize(const std::string &s, uint64_t &v) {
+  // Rust usize::from_str: optional leading '+', digits only, non-empty
+  size_t i = 0;
+  if (!s.empty() && s[0] == '+') i = 1;
+  if (i >= s.size()) return false;
+  v = 0;
+  for (; i < s.size(); i++) {
+    if (s[i] < '0' || s[i] > '9') return false;
+    v = v * 10 + (uint64_t)(s[i] - '0');
+  }
+  return true;
+}
+
+bool parse_paf_text(const char *data, size_t size, PafParsed &out) {
+  uint64_t bytes_read = 0;
+  size_t pos = 0;
+  auto get_id = [&](const std::string &name, uint64_t len) {
+    auto it = out.name_to_id.find(name);
+    if (it != out.name_to_id.end()) return it->second;  // length: first insert wins (or_insert)
+    uint32_t id = (uint32_t)out.names.size();
+    out.name_to_id.emplace(name, id);
+    out.names.push_back(name);
+    out.lens.push_back(len);
+    return id;
+  };
+  while (pos < size) {
+    size_t eol = pos;
+    while (eol < size && data[eol] != '\n') eol++;
+    size_t line_len = eol - pos;
+    // BufRead::lines strips "\n" and a preceding "\r"
+    size_t eff_len = line_len;
+    if (eff_len > 0 && data[pos + eff_len - 1] == '\r') eff_len--;
+    std::string line(data + pos, eff_len);
+    std::vector<std::string> f;
+    {
+      size_t a = 0;
+      for (;;) {
+        size_t b = line.find('\t', a);
+        if (b == std::string::npos) {
+          f.push_back(line.substr(a));
+          break;
+        }
+        f.push_back(line.substr(a, b - a));
+        a = b + 1;
+      }
+    }
+    if (f.size() < 12) {
+      out.err = "Not enough fields in PAF record";
+      return false;
+    }
+    uint64_t ql, qs, qe, tl, ts, te;
+    if (!parse_usize(f[1], ql) || !parse_usize(f[2], qs) || !parse_usize(f[3], qe) || !parse_usize(f[6], tl) ||
+        !parse_usize(f[7], ts) || !parse_usize(f[8], te)) {
+      out.err = "Invalid field";
+      return false;
+    }
+    if (f[4].empty()) {
+      out.err = "Expected '+' or '-' for strand";
+      return false;
+    }
+    char sc = f[4][0];
+    if (sc != '+' && sc != '-') {
+      out.err = "Invalid strand";
+      return false;
+    }
+    uint32_t qid = get_id(f[0], ql);
+    uint32_t tid = get_id(f[5], tl);
+    uint64_t cigar_offset = bytes_read, cigar_bytes = 0;
+    for (auto &tag : f) {
+      if (tag.compare(0, 5, "cg:Z:") == 0) {
+        cigar_offset += 5;
+        cigar_bytes = tag.size() - 5;
+        break;
+      } else {
+        cigar_offset += tag.size() + 1;
+      }
+    }
+    impgx_record r;
+    r.query_id = qid;
+    r.target_id = tid;
+    r.query_start = (int32_t)qs;
+    r.query_end = (int32_t)qe;
+    r.target_start = (int32_t)ts;
+    r.target_end = (int32_t)te;
+    r.strand = sc == '-' ? 1 : 0;
+    r.reserved = 0;
+    out.recs.push_back(r);
+    out.extra.push_back(RecExtra{cigar_offset, cigar_bytes});
+    bytes_read += eff_len + 1;  // line.len() + 1 as in the reference (off by one on CRLF, like the reference)
+    pos = eol + 1;
+  }
+  return true;
+}
+
+struct ResultSet {
+  std::vector<Result> r;
+};
+
+}  // namespace
+
+// =================================================================== C API
+extern "C" {
+
+int orc_project(int32_t rs, int32_t re, int32_t ts, int32_t te, int32_t qs, int32_t qe, int strand_rev,
+                const uint32_t *ops, size_t n, int32_t *out4, uint32_t *out_ops, size_t *n_out) {
+  Projection p;
+  std::vector<CigarOp> v(n);
+  for (size_t i = 0; i < n; i++) v[i].val = ops[i];
+  if (!project_target_range_through_alignment(rs, re, ts, te, qs, qe, strand_rev != 0, v.data(), n, p)) return 0;
+  out4[0] = p.q_start;
+  out4[1] = p.q_end;
+  out4[2] = p.t_start;
+  out4[3] = p.t_end;
+  if (out_ops)
+    for (size_t i = 0; i < p.ops.size(); i++) out_ops[i] = p.ops[i].val;
+  if (n_out) *n_out = p.ops.size();
+  return 1;
+}
+
+long orc_parse_cigar(const char *s, size_t len, uint32_t *out, size_t cap) {
+  std::vector<CigarOp> ops;
+  if (!parse_cigar_to_delta(s, len, ops)) return -1;
+  if (ops.size() > cap) return -2;
+  for (size_t i = 0; i < ops.size(); i++) out[i] = ops[i].val;
+  return (long)ops.size();
+}
+
+void orc_invert(uint32_t *ops, size_t n, int strand_rev) {
+  std::vector<CigarOp> v(n);
+  for (size_t i = 0; i < n; i++) v[i].val = ops[i];
+  invert_cigar_ops_in_place(v, strand_rev != 0);
+  for (size_t i = 0; i < n; i++) ops[i] = v[i].val;
+}
+
+double orc_identity(const uint32_t *ops, size_t n) {
+  std::vector<CigarOp> v(n);
+  for (size_t i = 0; i < n; i++) v[i].val = ops[i];
+  return calculate_gap_compressed_identity(v);
+}
+
+// SortedRanges::insert exposed for unit tests: ranges in/out as flat pairs.
+size_t orc_sorted_ranges_insert(int32_t *ranges, size_t *n_ranges, size_t cap, int32_t seq_len, int32_t min_dist,
+                                int32_t s, int32_t e, int32_t *pieces, size_t pieces_cap) {
+  SortedRanges sr(seq_len, min_dist);
+  for (size_t i = 0; i < *n_ranges; i++) sr.ranges.push_back({ranges[2 * i], ranges[2 * i + 1]});
+  auto p = sr.insert({s, e});
+  for (size_t i = 0; i < sr.ranges.size() && i < cap; i++) {
+    ranges[2 * i] = sr.ranges[i].first;
+    ranges[2 * i + 1] = sr.ranges[i].second;
+  }
+  *n_ranges = sr.ranges.size();
+  for (size_t i = 0; i < p.size() && i < pieces_cap; i++) {
+    pieces[2 * i] = p[i].first;
+    pieces[2 * i + 1] = p[i].second;
+  }
+  return p.size();
+}
+
+void *orc_index_build(const impgx_record *recs, size_t n, const uint32_t *runs, const uint64_t *run_offsets,
+                      const uint64_t *seq_lens, uint32_t n_seqs, int bidirectional) {
+  Index *idx = new Index();
+  idx->seq_lens.assign(seq_lens, seq_lens + n_seqs);
+  idx->names.resize(n_seqs);
+  idx->run_offsets.assign(run_offsets, run_offsets + n + 1);
+  idx->runs.assign(runs, runs + run_offsets[n]);
+  build_trees(*idx, recs, n, nullptr, bidirectional != 0);
+  return idx;
+}
+
+// Parse a PAF file. faithful != 0 keeps CIGARs on disk and does a pread +
+// text parse per hit like the reference (src/impg.rs:495-552); otherwise the
+// CIGARs are decoded once into the run stream.
+void *orc_index_from_paf(const char *path, int bidirectional, int faithful, char *err, size_t err_cap) {
+  int fd = open(path, O_RDONLY);
+  if (fd < 0) {
+    if (err) snprintf(err, err_cap, "cannot open %s", path);
+    return nullptr;
+  }
+  struct stat st;
+  fstat(fd, &st);
+  std::vector<char> data((size_t)st.st_size);
+  size_t got = 0;
+  while (got < data.size()) {
+    ssize_t r = read(fd, data.data() + got, data.size() - got);
+    if (r <= 0) break;
+    got += (size_t)r;
+  }
+  PafParsed pp;
+  if (!parse_paf_text(data.data(), got, pp)) {
+    if (err) snprintf(err, err_cap, "%s", pp.err.c_str());
+    close(fd);
+    return nullptr;
+  }
+  Index *idx = new Index();
+  idx->seq_lens = pp.lens;
+  idx->names = pp.names;
+  idx->name_to_id = pp.name_to_id;
+  idx->paf_path = path;
+  idx->faithful = faithful != 0;
+  idx->run_offsets.push_back(0);
+  if (!idx->faithful) {
+    for (size_t i = 0; i < pp.recs.size(); i++) {
+      std::vector<CigarOp> ops;
+      if (pp.extra[i].data_bytes == 0 ||
+          !parse_cigar_to_delta(data.data() + pp.extra[i].data_offset, pp.extra[i].data_bytes, ops)) {
+        if (err) snprintf(err, err_cap, "record %zu: missing or invalid cg:Z: tag", i);
+        delete idx;
+        close(fd);
+        return nullptr;
+      }
+      for (auto &o : ops) idx->runs.push_back(o.val);
+      idx->run_offsets.push_back(idx->runs.size());
+    }
+    close(fd);
+  } else {
+    idx->fd = fd;
+    idx->run_offsets.resize(pp.recs.size() + 1, 0);
+  }
+  build_trees(*idx, pp.recs.data(), pp.recs.size(), pp.extra.data(), bidirectional != 0);
+  return idx;
+}
+
+// Attach a CIGAR text file to an index built from arrays so that the baseline
+// driver pays the reference's per-hit cost: record i's CIGAR text is at
+// [offsets[i], offsets[i]+lens[i]) in `path`.
+int orc_index_attach_cigar_file(void *h, const char *path, const uint64_t *offsets, const uint64_t *lens) {
+  Index *idx = (Index *)h;
+  int fd = open(path, O_RDONLY);
+  if (fd < 0) return -1;
+  idx->fd = fd;
+  idx->paf_path = path;
+  for (auto &kv : idx->trees)
+    for (auto &nd : kv.second.nodes) {
+      nd.meta.data_offset = offsets[nd.meta.aln];
+      nd.meta.data_bytes = lens[nd.meta.aln];
+    }
+  idx->faithful = true;
+  return 0;
+}
+void orc_index_set_faithful(void *h, int on) { ((Index *)h)->faithful = on != 0 && ((Index *)h)->fd >= 0; }
+
+void orc_index_free(void *h) { delete (Index *)h; }
+uint32_t orc_index_num_seqs(void *h) { return (uint32_t)((Index *)h)->seq_lens.size(); }
+size_t orc_index_num_records(void *h) { return ((Index *)h)->n_records; }
+const char *orc_index_seq_name(void *h, uint32_t id) { return ((Index *)h)->names[id].c_str(); }
+uint64_t orc_index_seq_len(void *h, uint32_t id) { return ((Index *)h)->seq_lens[id]; }
+long orc_index_seq_id(void *h, const char *name) {
+  Index *idx = (Index *)h;
+  auto it = idx->name_to_id.find(name);
+  return it == idx->name_to_id.end() ? -1 : (long)it->second;
+}
+void orc_index_set_names(void *h, const char *const *names, uint32_t n) {
+  Index *idx = (Index *)h;
+  idx->names.assign(names, names + n);
+  idx->name_to_id.clear();
+  for (uint32_t i = 0; i < n; i++) idx->name_to_id[idx->names[i]] = i;
+}
+// records / runs as parsed (so the product can be built from the same arrays)
+void orc_index_export(void *h, impgx_record *recs, uint64_t *run_offsets, uint32_t *runs) {
+  Index *idx = (Index *)h;
+  // records are recovered from forward entries
+  for (auto &kv : idx->trees)
+    for (auto &nd : kv.second.nodes)
+      if (!nd.meta.reversed) {
+        impgx_record r;
+        r.query_id = nd.meta.query_id;
+        r.target_id = kv.first;
+        r.query_start = nd.meta.query_start;
+        r.query_end = nd.meta.query_end;
+        r.target_start = nd.meta.target_start;
+        r.target_end = nd.meta.target_end;
+        r.strand = nd.meta.strand_rev;
+        r.reserved = 0;
+        recs[nd.meta.aln] = r;
+      }
+  if (run_offsets) memcpy(run_offsets, idx->run_offsets.data(), idx->run_offsets.size() * 8);
+  if (runs) memcpy(runs, idx->runs.data(), idx->runs.size() * 4);
+}
+size_t orc_index_num_runs(void *h) { return ((Index *)h)->runs.size(); }
+
+// Hit visit order of one stab, as sorted positions — pins the product's
+// visit_rank column against the tree restatement.
+size_t orc_stab_order(void *h, uint32_t target_id, int32_t s, int32_t e, uint64_t *aln_out, uint8_t *reversed_out,
+                      size_t cap) {
+  Index *idx = (Index *)h;
+  auto it = idx->trees.find(target_id);
+  size_t k = 0;
+  if (it == idx->trees.end()) return 0;
+  it->second.query(s, e, [&](const Node &nd) {
+    if (k < cap) {
+      aln_out[k] = nd.meta.aln;
+      reversed_out[k] = nd.meta.reversed;
+    }
+    k++;
+  });
+  return k;
+}
+
+static QParams to_qparams(const impgx_params *p) {
+  QParams q;
+  q.max_depth = p->max_depth;
+  q.min_transitive_len = p->min_transitive_len;
+  q.min_distance_between_ranges = p->min_distance_between_ranges;
+  q.min_output_length = p->min_output_length;
+  q.store_cigar = p->store_cigar != 0;
+  q.min_identity = p->min_identity;
+  q.subset_mask = p->subset_mask;
+  return q;
+}
+
+void *orc_perform_query(void *h, uint32_t target_id, int32_t s, int32_t e, const impgx_params *p, int threads) {
+  Index *idx = (Index *)h;
+  ResultSet *rs = new ResultSet();
+  rs->r = perform_query(*idx, target_id, s, e, p->mode, to_qparams(p), threads);
+  return rs;
+}
+void orc_results_free(void *r) { delete (ResultSet *)r; }
+size_t orc_results_len(void *r) { return ((ResultSet *)r)->r.size(); }
+size_t orc_results_cigar_len(void *r) {
+  size_t n = 0;
+  for (auto &x : ((ResultSet *)r)->r) n += x.cigar.size();
+  return n;
+}
+void orc_results_copy(void *r, uint32_t *qid, int32_t *qf, int32_t *ql, uint32_t *tid, int32_t *tf, int32_t *tl,
+                      uint64_t *cig_off, uint32_t *cig) {
+  auto &v = ((ResultSet *)r)->r;
+  uint64_t off = 0;
+  for (size_t i = 0; i < v.size(); i++) {
+    qid[i] = v[i].q_id;
+    qf[i] = v[i].q_first;
+    ql[i] = v[i].q_last;
+    tid[i] = v[i].t_id;
+    tf[i] = v[i].t_first;
+    tl[i] = v[i].t_last;
+    if (cig_off) cig_off[i] = off;
+    if (cig)
+      for (auto &o : v[i].cigar) cig[off++] = o.val;
+    else
+      off += v[i].cigar.size();
+  }
+  if (cig_off) cig_off[v.size()] = off;
+}
+void *orc_results_from_arrays(size_t n, const uint32_t *qid, const int32_t *qf, const int32_t *ql, const uint32_t *tid,
+                              const int32_t *tf, const int32_t *tl, const uint64_t *cig_off, const uint32_t *cig) {
+  ResultSet *rs = new ResultSet();
+  rs->r.resize(n);
+  for (size_t i = 0; i < n; i++) {
+    Result &x = rs->r[i];
+    x.q_id = qid[i]; x.q_first = qf[i]; x.q_last = ql[i];
+    x.t_id = tid[i]; x.t_first = tf[i]; x.t_last = tl[i];
+    if (cig_off)
+      for (uint64_t k = cig_off[i]; k < cig_off[i + 1]; k++) x.cigar.push_back(CigarOp{cig[k]});
+  }
+  return rs;
+}
+void orc_results_drop_first(void *r) {
+  auto &v = ((ResultSet *)r)->r;
+  if (!v.empty()) v.erase(v.begin());
+}
+void orc_merge_query(void *r, int32_t d, int merge_strands) {
+  merge_query_adjusted_intervals(((ResultSet *)r)->r, d, merge_strands != 0);
+}
+void orc_merge_2d(void *r, int32_t d) { merge_adjusted_intervals_gap_2d(((ResultSet *)r)->r, d); }
+void orc_merge_cigar(void *r, int32_t d) { merge_adjusted_intervals(((ResultSet *)r)->r, d); }
+
+static char *dup_string(const std::string &s) {
+  char *p = (char *)malloc(s.size() + 1);
+  memcpy(p, s.c_str(), s.size() + 1);
+  return p;
+}
+// format: 0 bed, 1 bedpe, 2 paf. Mutates the result set (merges), like the reference.
+char *orc_format(void *h, void *r, int format, const char *name, int32_t d, int merge_strands) {
+  Index *idx = (Index *)h;
+  auto &v = ((ResultSet *)r)->r;
+  if (format == 0) return dup_string(output_results_bed(*idx, v, name, d, merge_strands != 0));
+  if (format == 1) return dup_string(output_results_bedpe(*idx, v, name, d));
+  return dup_string(output_results_paf(*idx, v, name, d));
+}
+void orc_free(void *p) { free(p); }
+
+// The reference's batch driver (src/main.rs:7435-7456): rows processed
+// SERIALLY, parallelism only inside a BFS level (rayon → OpenMP). With
+// format >= 0 the row is also merged and formatted (output_results_*), and the
+// text length is accumulated so the work cannot be optimised away.
+// Returns seconds; *n_results = total results before merging,
+// *n_out_bytes = formatted bytes.
+double orc_run_batch(void *h, const impgx_range *ranges, size_t n, const impgx_params *p, int threads, int format,
+                     uint64_t *n_results, uint64_t *n_out_bytes, uint64_t *checksum) {
+  Index *idx = (Index *)h;
+  QParams q = to_qparams(p);
+  uint64_t total = 0, bytes = 0, sum = 0;
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  for (size_t i = 0; i < n; i++) {
+    auto res = perform_query(*idx, ranges[i].target_id, ranges[i].start, ranges[i].end, p->mode, q, threads);
+    total += res.size();
+    if (format >= 0) {
+      std::string name = "r" + std::to_string(i);
+      std::string s;
+      if (format == 0) s = output_results_bed(*idx, res, name, p->merge_distance, p->merge_strands != 0);
+      else {
+        if (!res.empty()) res.erase(res.begin());
+        s = format == 1 ? output_results_bedpe(*idx, res, name, p->merge_distance)
+                        : output_results_paf(*idx, res, name, p->merge_distance);
+      }
+      bytes += s.size();
+      for (auto &r : res) sum = sum * 1000003u + (uint64_t)(uint32_t)r.q_first * 31u + (uint64_t)(uint32_t)r.q_last + r.q_id;
+    }
+  }
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  if (n_results) *n_results = total;
+  if (n_out_bytes) *n_out_bytes = bytes;
+  if (checksum) *checksum = sum;
+  return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
+// Batch query returning every row's (optionally BED-merged) results as flat
+// columns, for parity tests against impgx_query_batch[_bed].
+void *orc_query_batch(void *h, const impgx_range *ranges, size_t n, const impgx_params *p, int bed_merge,
+                      uint64_t *row_offsets) {
+  Index *idx = (Index *)h;
+  QParams q = to_qparams(p);
+  ResultSet *all = new ResultSet();
+  row_offsets[0] = 0;
+  for (size_t i = 0; i < n; i++) {
+    auto res = perform_query(*idx, ranges[i].target_id, ranges[i].start, ranges[i].end, p->mode, q, 1);
+    if (bed_merge) {
+      bool any_empty = false;
+      for (auto &r : res) any_empty |= r.cigar.empty();
+      if (any_empty) merge_adjusted_intervals_gap_2d(res, p->merge_distance);
+      merge_query_adjusted_intervals(res, p->merge_distance, p->merge_strands != 0);
+    }
+    for (auto &r : res) all->r.push_back(std::move(r));
+    row_offsets[i + 1] = all->r.size();
+  }
+  return all;
+}
+
+int orc_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+}  // extern "C"
