@@ -1,0 +1,399 @@
+"""impg_b200 — host-side mirror of impg's query interface for the projection
+path, over libimpgx's C ABI (include/impgx.h).
+
+The class `Impg` mirrors the reference's `ImpgIndex` trait for this path
+(reference src/impg_index.rs:21-121): `query`, `query_transitive_bfs`,
+sequence-index accessors, plus the batch entry that replaces the serial BED
+loop of `impg query -b` (reference src/main.rs:7435-7456).
+
+There is no CPU fallback: if libimpgx.so is missing the import fails, and
+without a CUDA device every compute call raises ImpgxError(NO_DEVICE).
+"""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libimpgx.so")
+
+OK, E_INVALID, E_NO_DEVICE, E_CUDA, E_NOMEM, E_IO, E_PARSE, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6, -7
+MODE_QUERY, MODE_BFS, MODE_DFS = 0, 1, 2
+
+RECORD_DTYPE = np.dtype([("query_id", "<u4"), ("target_id", "<u4"), ("query_start", "<i4"), ("query_end", "<i4"),
+                         ("target_start", "<i4"), ("target_end", "<i4"), ("strand", "<u4"), ("reserved", "<u4")])
+RANGE_DTYPE = np.dtype([("target_id", "<u4"), ("start", "<i4"), ("end", "<i4")])
+
+OPS = "=XIDM"
+
+
+class ImpgxError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[impgx {code}] {msg}")
+        self.code = code
+
+
+class Params(C.Structure):
+    _fields_ = [("mode", C.c_uint32), ("max_depth", C.c_uint32), ("min_transitive_len", C.c_int32),
+                ("min_distance_between_ranges", C.c_int32), ("min_output_length", C.c_int32),
+                ("store_cigar", C.c_uint32), ("min_identity", C.c_double), ("subset_mask", C.c_void_p),
+                ("merge_distance", C.c_int32), ("merge_strands", C.c_uint32)]
+
+
+class View(C.Structure):
+    _fields_ = [("n_rows", C.c_size_t), ("n_results", C.c_size_t), ("row_offsets", C.c_void_p),
+                ("q_id", C.c_void_p), ("q_first", C.c_void_p), ("q_last", C.c_void_p), ("t_id", C.c_void_p),
+                ("t_first", C.c_void_p), ("t_last", C.c_void_p), ("cigar_offsets", C.c_void_p),
+                ("cigar_runs", C.c_void_p)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_uint64), ("stab_ranges", C.c_uint64), ("stab_candidates", C.c_uint64),
+                ("liftovers", C.c_uint64), ("lift_runs", C.c_uint64), ("lift_bytes", C.c_uint64),
+                ("results", C.c_uint64), ("merged", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("lift_ms", C.c_float), ("stab_ms", C.c_float), ("fold_ms", C.c_float), ("merge_ms", C.c_float),
+                ("total_ms", C.c_float)]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+class SynthCfg(C.Structure):
+    _fields_ = [("genomes", C.c_uint32), ("contigs", C.c_uint32), ("contig_len", C.c_uint32), ("tiles", C.c_uint32),
+                ("eq_mean", C.c_uint32), ("rev_permille", C.c_uint32), ("seed", C.c_uint64)]
+
+
+def make_params(mode=MODE_QUERY, max_depth=2, min_transitive_len=101, min_distance_between_ranges=10,
+                min_output_length=None, store_cigar=False, min_identity=None, subset_mask=None, merge_distance=0,
+                merge_strands=True):
+    """Defaults are the reference's CLI defaults (src/main.rs:4259-4410)."""
+    p = Params()
+    p.mode = mode
+    p.max_depth = max_depth
+    p.min_transitive_len = min_transitive_len
+    p.min_distance_between_ranges = min_distance_between_ranges
+    p.min_output_length = -1 if min_output_length is None else min_output_length
+    p.store_cigar = 1 if store_cigar else 0
+    p.min_identity = float("nan") if min_identity is None else float(min_identity)
+    if subset_mask is not None:
+        m = np.ascontiguousarray(subset_mask, dtype=np.uint8)
+        p._keep = m
+        p.subset_mask = m.ctypes.data
+    else:
+        p.subset_mask = None
+    p.merge_distance = merge_distance
+    p.merge_strands = 1 if merge_strands else 0
+    return p
+
+
+_lib = None
+
+
+def lib():
+    """Loads libimpgx.so (built in-tree by `make -C impg_b200/csrc` / __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `make -C impg_b200/csrc` "
+                              "(libimpgx has no Python or CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.impgx_last_error.restype = C.c_char_p
+        L.impgx_index_num_seqs.restype = C.c_uint32
+        L.impgx_index_num_entries.restype = C.c_uint64
+        L.impgx_index_device_bytes.restype = C.c_uint64
+        L.impgx_index_seq_name.restype = C.c_char_p
+        L.impgx_index_seq_len.restype = C.c_uint64
+        L.impgx_parse_cigar.restype = C.c_long
+        L.impgx_format_bed.restype = C.c_void_p
+        L.impgx_synth_num_alignments.restype = C.c_uint64
+        L.impgx_debug_host_columns.restype = C.c_long
+        _lib = L
+    return _lib
+
+
+def _check(code):
+    if code != 0:
+        raise ImpgxError(code, lib().impgx_last_error().decode(errors="replace"))
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def device_count():
+    return lib().impgx_device_count()
+
+
+def run(op, length):
+    return (OPS.index(op) << 29) | int(length)
+
+
+def cigar_str(runs):
+    return "".join(f"{int(v) & 0x1FFFFFFF}{OPS[int(v) >> 29]}" for v in runs)
+
+
+def parse_cigar(text):
+    b = text.encode() if isinstance(text, str) else bytes(text)
+    out = np.zeros(max(1, len(b)), dtype=np.uint32)
+    n = lib().impgx_parse_cigar(b, C.c_size_t(len(b)), _p(out), C.c_size_t(len(out)))
+    if n < 0:
+        raise ImpgxError(n, lib().impgx_last_error().decode())
+    return out[:n].copy()
+
+
+class Results:
+    """Column view of a result set (AdjustedInterval rows, reference src/impg.rs:225)."""
+
+    def __init__(self, handle, on_device=False):
+        self.h = C.c_void_p(handle)
+        self.on_device = on_device
+        v = View()
+        if on_device:
+            _check(lib().impgx_results_device_view(self.h, C.byref(v)))
+        else:
+            _check(lib().impgx_results_view(self.h, C.byref(v)))
+        self.view = v
+        self.n_rows = v.n_rows
+        self.n_results = v.n_results
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().impgx_results_free(self.h)
+            self.h = None
+
+    def _arr(self, ptr, n, dtype):
+        if n == 0 or not ptr:
+            return np.zeros(0, dtype)
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dtype))), shape=(n,)).copy()
+
+    def columns(self):
+        assert not self.on_device
+        v, n = self.view, self.n_results
+        cols = {
+            "row_offsets": self._arr(v.row_offsets, self.n_rows + 1, np.uint64),
+            "q_id": self._arr(v.q_id, n, np.uint32), "q_first": self._arr(v.q_first, n, np.int32),
+            "q_last": self._arr(v.q_last, n, np.int32), "t_id": self._arr(v.t_id, n, np.uint32),
+            "t_first": self._arr(v.t_first, n, np.int32), "t_last": self._arr(v.t_last, n, np.int32),
+        }
+        if v.cigar_offsets:
+            cols["cigar_offsets"] = self._arr(v.cigar_offsets, n + 1, np.uint64)
+            nc = int(cols["cigar_offsets"][-1]) if n else 0
+            cols["cigar_runs"] = self._arr(v.cigar_runs, nc, np.uint32)
+        return cols
+
+    def row_tuples(self, row, cols=None):
+        c = cols or self.columns()
+        a, b = int(c["row_offsets"][row]), int(c["row_offsets"][row + 1])
+        out = []
+        for i in range(a, b):
+            cg = ""
+            if "cigar_offsets" in c:
+                cg = cigar_str(c["cigar_runs"][int(c["cigar_offsets"][i]):int(c["cigar_offsets"][i + 1])])
+            out.append((int(c["q_id"][i]), int(c["q_first"][i]), int(c["q_last"][i]), int(c["t_id"][i]),
+                        int(c["t_first"][i]), int(c["t_last"][i]), cg))
+        return out
+
+
+class Impg:
+    """GPU-resident index + query interface (mirrors reference `Impg` / `ImpgIndex`)."""
+
+    def __init__(self, handle):
+        self.h = C.c_void_p(handle)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().impgx_index_free(self.h)
+            self.h = None
+
+    # -- construction (Impg::from_multi_alignment_records, reference src/impg.rs:1535)
+    @classmethod
+    def from_records(cls, records, runs, run_offsets, seq_lens, names=None, bidirectional=True, device=0):
+        records = np.ascontiguousarray(records, dtype=RECORD_DTYPE)
+        runs = np.ascontiguousarray(runs, dtype=np.uint32)
+        run_offsets = np.ascontiguousarray(run_offsets, dtype=np.uint64)
+        seq_lens = np.ascontiguousarray(seq_lens, dtype=np.uint64)
+        if len(runs) == 0:
+            runs = np.zeros(1, np.uint32)
+        h = C.c_void_p()
+        _check(lib().impgx_index_build(_p(records), C.c_size_t(len(records)), _p(runs), _p(run_offsets), _p(seq_lens),
+                                       C.c_uint32(len(seq_lens)), C.c_int(1 if bidirectional else 0), C.c_int(device),
+                                       C.byref(h)))
+        idx = cls(h.value)
+        if names is not None:
+            idx.set_names(names)
+        return idx
+
+    @classmethod
+    def from_paf(cls, path, bidirectional=True, device=0):
+        h = C.c_void_p()
+        _check(lib().impgx_index_from_paf(path.encode(), C.c_int(1 if bidirectional else 0), C.c_int(device),
+                                          C.byref(h)))
+        return cls(h.value)
+
+    # -- SequenceIndex accessors (reference src/seqidx.rs)
+    def set_names(self, names):
+        arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        _check(lib().impgx_index_set_names(self.h, arr, C.c_uint32(len(names))))
+
+    @property
+    def n_seqs(self):
+        return lib().impgx_index_num_seqs(self.h)
+
+    @property
+    def n_entries(self):
+        return lib().impgx_index_num_entries(self.h)
+
+    @property
+    def device_bytes(self):
+        return lib().impgx_index_device_bytes(self.h)
+
+    def seq_name(self, i):
+        s = lib().impgx_index_seq_name(self.h, C.c_uint32(i))
+        return s.decode() if s else None
+
+    def seq_len(self, i):
+        return lib().impgx_index_seq_len(self.h, C.c_uint32(i))
+
+    def seq_id(self, name):
+        out = C.c_uint32()
+        _check(lib().impgx_index_seq_id(self.h, name.encode(), C.byref(out)))
+        return out.value
+
+    # -- batch entry (replaces the BED loop, reference src/main.rs:7435-7456)
+    def query_batch(self, ranges, params):
+        ranges = np.ascontiguousarray(ranges, dtype=RANGE_DTYPE)
+        h = C.c_void_p()
+        _check(lib().impgx_query_batch(self.h, _p(ranges), C.c_size_t(len(ranges)), C.byref(params), C.byref(h)))
+        return Results(h.value)
+
+    def query_batch_bed(self, ranges, params):
+        ranges = np.ascontiguousarray(ranges, dtype=RANGE_DTYPE)
+        h = C.c_void_p()
+        _check(lib().impgx_query_batch_bed(self.h, _p(ranges), C.c_size_t(len(ranges)), C.byref(params), C.byref(h)))
+        return Results(h.value)
+
+    def query_batch_bed_device(self, d_ranges_ptr, n, params, stream=0):
+        """`d_ranges_ptr`: device pointer (int) to n impgx_range structs already in HBM."""
+        h = C.c_void_p()
+        _check(lib().impgx_query_batch_bed_device(self.h, C.c_void_p(d_ranges_ptr), C.c_size_t(n), C.byref(params),
+                                                  C.c_void_p(stream), C.byref(h)))
+        return Results(h.value, on_device=True)
+
+    def stats(self):
+        s = Stats()
+        _check(lib().impgx_index_stats(self.h, C.byref(s)))
+        return s.as_dict()
+
+    # -- per-range interface with the reference's argument names
+    def query(self, target_id, range_start, range_end, store_cigar=False, min_gap_compressed_identity=None):
+        """Impg::query (reference src/impg.rs:1852-1928)."""
+        p = make_params(mode=MODE_QUERY, store_cigar=store_cigar, min_identity=min_gap_compressed_identity)
+        r = self.query_batch(np.array([(target_id, range_start, range_end)], dtype=RANGE_DTYPE), p)
+        return r.row_tuples(0)
+
+    def query_transitive_bfs(self, target_id, range_start, range_end, max_depth=2, min_transitive_len=101,
+                             min_distance_between_ranges=10, min_output_length=None, store_cigar=False,
+                             min_gap_compressed_identity=None, subset_mask=None):
+        """Impg::query_transitive_bfs (reference src/impg.rs:2311-2597)."""
+        p = make_params(mode=MODE_BFS, max_depth=max_depth, min_transitive_len=min_transitive_len,
+                        min_distance_between_ranges=min_distance_between_ranges, min_output_length=min_output_length,
+                        store_cigar=store_cigar, min_identity=min_gap_compressed_identity, subset_mask=subset_mask)
+        r = self.query_batch(np.array([(target_id, range_start, range_end)], dtype=RANGE_DTYPE), p)
+        return r.row_tuples(0)
+
+    def format_bed(self, results, row, name):
+        ptr = lib().impgx_format_bed(self.h, results.h, C.c_size_t(row), name.encode())
+        if not ptr:
+            raise ImpgxError(E_INVALID, "format_bed failed")
+        s = C.string_at(ptr).decode()
+        lib().impgx_free(C.c_void_p(ptr))
+        return s
+
+
+def project_batch(req, records, runs, run_offsets, device=0, want_cigar=True):
+    """project_target_range_through_alignment for n independent problems on the GPU
+    (reference src/impg.rs:2760-2898). records[i].reserved bit 0 marks a reversed entry."""
+    n = len(records)
+    records = np.ascontiguousarray(records, dtype=RECORD_DTYPE)
+    rs = np.ascontiguousarray([r[0] for r in req], dtype=np.int32)
+    re = np.ascontiguousarray([r[1] for r in req], dtype=np.int32)
+    runs = np.ascontiguousarray(runs, dtype=np.uint32)
+    if len(runs) == 0:
+        runs = np.zeros(1, np.uint32)
+    run_offsets = np.ascontiguousarray(run_offsets, dtype=np.uint64)
+    out4 = np.zeros(4 * max(n, 1), np.int32)
+    ok = np.zeros(max(n, 1), np.uint8)
+    oo = np.zeros(n + 1, np.uint64)
+    cap = int(run_offsets[-1]) + 1
+    out_runs = np.zeros(cap, np.uint32)
+    _check(lib().impgx_project_batch(C.c_int(device), C.c_size_t(n), _p(rs), _p(re), _p(records), _p(runs),
+                                     _p(run_offsets), _p(out4), _p(ok), _p(oo), _p(out_runs) if want_cigar else None,
+                                     C.c_size_t(cap)))
+    res = []
+    for i in range(n):
+        if not ok[i]:
+            res.append(None)
+        else:
+            cg = out_runs[int(oo[i]):int(oo[i + 1])].copy() if want_cigar else None
+            res.append((int(out4[4 * i]), int(out4[4 * i + 1]), cg, int(out4[4 * i + 2]), int(out4[4 * i + 3])))
+    return res
+
+
+# ---------------------------------------------------------------- synthetic data
+def synth_cfg(genomes, contigs, contig_len, tiles, eq_mean, rev_permille=100, seed=1):
+    c = SynthCfg()
+    c.genomes, c.contigs, c.contig_len, c.tiles = genomes, contigs, contig_len, tiles
+    c.eq_mean, c.rev_permille, c.seed = eq_mean, rev_permille, seed
+    return c
+
+
+def synth_generate(cfg):
+    """gen_synth: returns (records, runs, run_offsets, seq_lens, names)."""
+    L = lib()
+    n = L.impgx_synth_num_alignments(C.byref(cfg))
+    recs = np.zeros(n, dtype=RECORD_DTYPE)
+    nr = np.zeros(n, dtype=np.uint32)
+    _check(L.impgx_synth_records(C.byref(cfg), C.c_uint64(0), C.c_uint64(n), _p(recs), _p(nr)))
+    offs = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(nr, out=offs[1:], dtype=np.uint64)
+    runs = np.zeros(max(int(offs[-1]), 1), dtype=np.uint32)
+    _check(L.impgx_synth_runs(C.byref(cfg), C.c_uint64(0), C.c_uint64(n), _p(offs), _p(runs)))
+    n_seqs = cfg.genomes * cfg.contigs
+    lens = np.full(n_seqs, cfg.contig_len, dtype=np.uint64)
+    names = [f"g{g}#1#c{c}" for g in range(cfg.genomes) for c in range(cfg.contigs)]
+    return recs, runs[: int(offs[-1])], offs, lens, names
+
+
+def synth_bed(cfg, n_rows, seed=2, min_len=1000, max_len=10000):
+    out = np.zeros(n_rows, dtype=RANGE_DTYPE)
+    _check(lib().impgx_synth_bed(C.byref(cfg), C.c_uint64(seed), C.c_uint64(n_rows), C.c_uint32(min_len),
+                                 C.c_uint32(max_len), _p(out)))
+    return out
+
+
+def write_cigar_text(runs, run_offsets, path):
+    runs = np.ascontiguousarray(runs, np.uint32)
+    run_offsets = np.ascontiguousarray(run_offsets, np.uint64)
+    n = len(run_offsets) - 1
+    offs = np.zeros(n, np.uint64)
+    lens = np.zeros(n, np.uint64)
+    _check(lib().impgx_write_cigar_text(_p(runs), _p(run_offsets), C.c_uint64(n), path.encode(), _p(offs), _p(lens)))
+    return offs, lens
+
+
+def host_columns(records, run_offsets, n_seqs, bidirectional=True):
+    """Test hook: the sorted entry columns of an index build, without a GPU."""
+    records = np.ascontiguousarray(records, dtype=RECORD_DTYPE)
+    run_offsets = np.ascontiguousarray(run_offsets, dtype=np.uint64)
+    L = lib()
+    args = [_p(records), C.c_size_t(len(records)), _p(run_offsets), C.c_uint32(n_seqs), C.c_int(1 if bidirectional else 0)]
+    E = L.impgx_debug_host_columns(*args, None, None, None, None, None, None, None, None)
+    if E < 0:
+        raise ImpgxError(E_INVALID, L.impgx_last_error().decode())
+    cols = {"e_start": np.zeros(E, np.int32), "e_end": np.zeros(E, np.int32), "e_pmax": np.zeros(E, np.int32),
+            "e_vrank": np.zeros(E, np.uint32), "e_query_id": np.zeros(E, np.uint32), "e_flags": np.zeros(E, np.uint32),
+            "e_aln": np.zeros(E, np.uint32), "tgt_off": np.zeros(n_seqs + 1, np.uint64)}
+    L.impgx_debug_host_columns(*args, _p(cols["e_start"]), _p(cols["e_end"]), _p(cols["e_pmax"]), _p(cols["e_vrank"]),
+                               _p(cols["e_query_id"]), _p(cols["e_flags"]), _p(cols["e_aln"]), _p(cols["tgt_off"]))
+    return cols

@@ -1,0 +1,457 @@
+// api.cu — the extern "C" boundary (include/impgx.h). No exception crosses it.
+#include <cstring>
+#include <fstream>
+#include <sstream>
+
+#include "engine.cuh"
+#include "synth_core.h"
+
+using namespace impgx;
+
+namespace impgx {
+void set_last_error(const std::string &m);
+const char *last_error();
+
+// ---- host text helpers (reference parsers / writers for this path)
+
+// parse_cigar_to_delta (src/impg.rs:2935-2950): digits accumulate, any other
+// byte ends a run; an unknown op is an error instead of the reference's panic.
+long parse_cigar(const char *s, size_t n, std::vector<uint32_t> &out) {
+  int64_t len = 0;
+  long cnt = 0;
+  for (size_t i = 0; i < n; i++) {
+    unsigned char c = (unsigned char)s[i];
+    if (c >= '0' && c <= '9') {
+      len = len * 10 + (c - '0');
+      if (len >= (1ll << 29)) return -2;
+    } else {
+      uint32_t op;
+      switch (c) {
+        case '=': op = IMPGX_OP_EQ; break;
+        case 'X': op = IMPGX_OP_X; break;
+        case 'I': op = IMPGX_OP_I; break;
+        case 'D': op = IMPGX_OP_D; break;
+        case 'M': op = IMPGX_OP_M; break;
+        default: return -1;
+      }
+      out.push_back(IMPGX_RUN(op, (uint32_t)len));
+      len = 0;
+      cnt++;
+    }
+  }
+  return cnt;
+}
+
+struct PafData {
+  std::vector<impgx_record> recs;
+  std::vector<uint32_t> runs;
+  std::vector<uint64_t> run_off{0};
+  std::vector<std::string> names;
+  std::vector<uint64_t> lens;
+  std::unordered_map<std::string, uint32_t> ids;
+};
+
+static bool parse_usize(const char *b, const char *e, uint64_t &v) {
+  if (b < e && *b == '+') b++;
+  if (b >= e) return false;
+  v = 0;
+  for (; b < e; b++) {
+    if (*b < '0' || *b > '9') return false;
+    v = v * 10 + (uint64_t)(*b - '0');
+  }
+  return true;
+}
+
+// parse_paf_line / parse_paf (src/paf.rs:118-194) with SequenceIndex ids by
+// first appearance (src/seqidx.rs:22-35). The CIGAR is decoded here, once.
+void parse_paf(const std::string &path, PafData &out) {
+  std::ifstream f(path, std::ios::binary);
+  REQUIRE(f.good(), IMPGX_E_IO, "cannot open PAF file '" + path + "'");
+  std::stringstream ss;
+  ss << f.rdbuf();
+  const std::string data = ss.str();
+  REQUIRE(!(data.size() >= 2 && (unsigned char)data[0] == 0x1f && (unsigned char)data[1] == 0x8b), IMPGX_E_UNSUPPORTED,
+          "compressed PAF is not supported yet; decompress first");
+  size_t pos = 0, line_no = 0;
+  auto get_id = [&](const char *b, const char *e, uint64_t len) {
+    std::string name(b, e);
+    auto it = out.ids.find(name);
+    if (it != out.ids.end()) return it->second;
+    uint32_t id = (uint32_t)out.names.size();
+    out.ids.emplace(name, id);
+    out.names.push_back(name);
+    out.lens.push_back(len);
+    return id;
+  };
+  while (pos < data.size()) {
+    size_t eol = data.find('\n', pos);
+    if (eol == std::string::npos) eol = data.size();
+    size_t end = eol;
+    if (end > pos && data[end - 1] == '\r') end--;
+    line_no++;
+    std::vector<std::pair<const char *, const char *>> fld;
+    {
+      const char *b = data.data() + pos, *e = data.data() + end, *p = b;
+      for (;;) {
+        const char *t = (const char *)memchr(p, '\t', (size_t)(e - p));
+        if (!t) {
+          fld.emplace_back(p, e);
+          break;
+        }
+        fld.emplace_back(p, t);
+        p = t + 1;
+      }
+    }
+    const std::string where = " (line " + std::to_string(line_no) + " of '" + path + "')";
+    REQUIRE(fld.size() >= 12, IMPGX_E_PARSE, "Not enough fields in PAF record" + where);
+    uint64_t ql, qs, qe, tl, ts, te;
+    REQUIRE(parse_usize(fld[1].first, fld[1].second, ql) && parse_usize(fld[2].first, fld[2].second, qs) &&
+                parse_usize(fld[3].first, fld[3].second, qe) && parse_usize(fld[6].first, fld[6].second, tl) &&
+                parse_usize(fld[7].first, fld[7].second, ts) && parse_usize(fld[8].first, fld[8].second, te),
+            IMPGX_E_PARSE, "Invalid field" + where);
+    REQUIRE(fld[4].first < fld[4].second, IMPGX_E_PARSE, "Expected '+' or '-' for strand" + where);
+    const char sc = *fld[4].first;
+    REQUIRE(sc == '+' || sc == '-', IMPGX_E_PARSE, "Invalid strand" + where);
+    REQUIRE(ql <= INT32_MAX && tl <= INT32_MAX && qe <= INT32_MAX && te <= INT32_MAX, IMPGX_E_PARSE,
+            "coordinate beyond 2^31-1" + where);
+    impgx_record r;
+    r.query_id = get_id(fld[0].first, fld[0].second, ql);
+    r.target_id = get_id(fld[5].first, fld[5].second, tl);
+    r.query_start = (int32_t)qs; r.query_end = (int32_t)qe;
+    r.target_start = (int32_t)ts; r.target_end = (int32_t)te;
+    r.strand = sc == '-' ? 1 : 0;
+    r.reserved = 0;
+    bool have = false;
+    for (auto &t : fld) {
+      if (t.second - t.first >= 5 && memcmp(t.first, "cg:Z:", 5) == 0) {
+        long k = parse_cigar(t.first + 5, (size_t)(t.second - t.first - 5), out.runs);
+        REQUIRE(k >= 0, IMPGX_E_PARSE, "Invalid CIGAR operation" + where);
+        have = k > 0;
+        break;
+      }
+    }
+    // the reference panics at query time when an alignment has no cg:Z tag
+    // (src/impg.rs:506-511); here it is a build-time error
+    REQUIRE(have, IMPGX_E_PARSE, "The alignment file does not contain CIGAR strings ('cg:Z' tag)" + where);
+    out.recs.push_back(r);
+    out.run_off.push_back(out.runs.size());
+    pos = eol + 1;
+  }
+}
+
+}  // namespace impgx
+
+#define API_BEGIN try {
+#define API_END                                  \
+  }                                              \
+  catch (const impgx::Error &e) {                \
+    impgx::set_last_error(e.what());             \
+    return e.code;                               \
+  }                                              \
+  catch (const std::bad_alloc &) {               \
+    impgx::set_last_error("host allocation failed"); \
+    return IMPGX_E_NOMEM;                        \
+  }                                              \
+  catch (const std::exception &e) {              \
+    impgx::set_last_error(e.what());             \
+    return IMPGX_E_INVALID;                      \
+  }                                              \
+  return IMPGX_OK;
+
+extern "C" {
+
+int impgx_abi_version(void) { return IMPGX_ABI_VERSION; }
+const char *impgx_last_error(void) { return impgx::last_error(); }
+int impgx_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int impgx_index_build(const impgx_record *records, size_t n_records, const uint32_t *runs, const uint64_t *run_offsets,
+                      const uint64_t *seq_lens, uint32_t n_seqs, int bidirectional, int device, impgx_index **out) {
+  API_BEGIN
+  REQUIRE(out, IMPGX_E_INVALID, "out is NULL");
+  *out = nullptr;
+  REQUIRE(runs || n_records == 0 || run_offsets[n_records] == 0, IMPGX_E_INVALID, "runs is NULL");
+  *out = impgx::index_build(records, n_records, runs, run_offsets, seq_lens, n_seqs, bidirectional != 0, device);
+  API_END
+}
+
+int impgx_index_from_paf(const char *paf_path, int bidirectional, int device, impgx_index **out) {
+  API_BEGIN
+  REQUIRE(out && paf_path, IMPGX_E_INVALID, "NULL argument");
+  *out = nullptr;
+  impgx::check_device(device);  // fail before parsing: there is no CPU fallback
+  impgx::PafData pd;
+  impgx::parse_paf(paf_path, pd);
+  impgx_index *idx = impgx::index_build(pd.recs.data(), pd.recs.size(), pd.runs.data(), pd.run_off.data(), pd.lens.data(),
+                                        (uint32_t)pd.lens.size(), bidirectional != 0, device);
+  idx->names = pd.names;
+  idx->name_to_id = pd.ids;
+  *out = idx;
+  API_END
+}
+
+void impgx_index_free(impgx_index *idx) { delete idx; }
+uint32_t impgx_index_num_seqs(const impgx_index *idx) { return idx ? idx->n_seqs : 0; }
+uint64_t impgx_index_num_entries(const impgx_index *idx) { return idx ? idx->n_entries : 0; }
+uint64_t impgx_index_device_bytes(const impgx_index *idx) { return idx ? idx->device_bytes : 0; }
+const char *impgx_index_seq_name(const impgx_index *idx, uint32_t id) {
+  if (!idx || id >= idx->names.size() || idx->names[id].empty()) return nullptr;
+  return idx->names[id].c_str();
+}
+uint64_t impgx_index_seq_len(const impgx_index *idx, uint32_t id) {
+  return (idx && id < idx->seq_lens.size()) ? idx->seq_lens[id] : 0;
+}
+int impgx_index_seq_id(const impgx_index *idx, const char *name, uint32_t *id_out) {
+  API_BEGIN
+  REQUIRE(idx && name && id_out, IMPGX_E_INVALID, "NULL argument");
+  auto it = idx->name_to_id.find(name);
+  REQUIRE(it != idx->name_to_id.end(), IMPGX_E_INVALID, std::string("Target sequence '") + name + "' not found in index");
+  *id_out = it->second;
+  API_END
+}
+int impgx_index_set_names(impgx_index *idx, const char *const *names, uint32_t n) {
+  API_BEGIN
+  REQUIRE(idx && names && n == idx->n_seqs, IMPGX_E_INVALID, "names must cover every sequence");
+  idx->names.assign(names, names + n);
+  idx->name_to_id.clear();
+  for (uint32_t i = 0; i < n; i++) idx->name_to_id[idx->names[i]] = i;
+  API_END
+}
+
+static int do_query(impgx_index *idx, const impgx_range *ranges, size_t n, const impgx_params *params, bool bed,
+                    bool dev_in, bool host_out, void *stream, impgx_results **out) {
+  API_BEGIN
+  REQUIRE(out && params, IMPGX_E_INVALID, "NULL argument");
+  *out = nullptr;
+  *out = impgx::query_batch(idx, ranges, n, *params, bed, dev_in, host_out, stream);
+  API_END
+}
+
+int impgx_query_batch(impgx_index *idx, const impgx_range *ranges, size_t n, const impgx_params *params,
+                      impgx_results **out) {
+  return do_query(idx, ranges, n, params, false, false, true, nullptr, out);
+}
+int impgx_query_batch_bed(impgx_index *idx, const impgx_range *ranges, size_t n, const impgx_params *params,
+                          impgx_results **out) {
+  return do_query(idx, ranges, n, params, true, false, true, nullptr, out);
+}
+int impgx_query_batch_bed_device(impgx_index *idx, const impgx_range *d_ranges, size_t n, const impgx_params *params,
+                                 void *stream, impgx_results **out) {
+  return do_query(idx, d_ranges, n, params, true, true, false, stream, out);
+}
+
+int impgx_results_view(const impgx_results *res, impgx_view *v) {
+  API_BEGIN
+  REQUIRE(res && v, IMPGX_E_INVALID, "NULL argument");
+  REQUIRE(!res->on_device, IMPGX_E_INVALID, "results are device resident; use impgx_results_device_view");
+  v->n_rows = res->n_rows;
+  v->n_results = res->n_results;
+  v->row_offsets = res->row_off.data();
+  v->q_id = res->qid.data(); v->q_first = res->qf.data(); v->q_last = res->ql.data();
+  v->t_id = res->tid.data(); v->t_first = res->tf.data(); v->t_last = res->tl.data();
+  v->cigar_offsets = res->has_cigar ? res->cig_off.data() : nullptr;
+  v->cigar_runs = res->has_cigar ? res->cig.data() : nullptr;
+  API_END
+}
+int impgx_results_device_view(const impgx_results *res, impgx_view *v) {
+  API_BEGIN
+  REQUIRE(res && v, IMPGX_E_INVALID, "NULL argument");
+  REQUIRE(res->on_device, IMPGX_E_INVALID, "results are host resident; use impgx_results_view");
+  v->n_rows = res->n_rows;
+  v->n_results = res->n_results;
+  v->row_offsets = res->d_row_off;
+  v->q_id = res->d_qid; v->q_first = res->d_qf; v->q_last = res->d_ql;
+  v->t_id = res->d_tid; v->t_first = res->d_tf; v->t_last = res->d_tl;
+  v->cigar_offsets = nullptr;
+  v->cigar_runs = nullptr;
+  API_END
+}
+void impgx_results_free(impgx_results *res) { delete res; }
+
+int impgx_index_stats(const impgx_index *idx, impgx_stats *out) {
+  API_BEGIN
+  REQUIRE(idx && out, IMPGX_E_INVALID, "NULL argument");
+  *out = idx->last;
+  API_END
+}
+
+int impgx_project_batch(int device, size_t n, const int32_t *req_start, const int32_t *req_end,
+                        const impgx_record *records, const uint32_t *runs, const uint64_t *run_offsets, int32_t *out4,
+                        uint8_t *ok, uint64_t *out_run_offsets, uint32_t *out_runs, size_t out_runs_cap) {
+  API_BEGIN
+  impgx::project_batch(device, n, req_start, req_end, records, runs, run_offsets, out4, ok, out_run_offsets, out_runs,
+                       out_runs_cap);
+  API_END
+}
+
+long impgx_parse_cigar(const char *text, size_t len, uint32_t *out, size_t cap) {
+  std::vector<uint32_t> v;
+  long k = impgx::parse_cigar(text, len, v);
+  if (k < 0) {
+    impgx::set_last_error("Invalid CIGAR operation");
+    return IMPGX_E_PARSE;
+  }
+  if ((size_t)k > cap) {
+    impgx::set_last_error("output capacity too small");
+    return IMPGX_E_INVALID;
+  }
+  if (k) memcpy(out, v.data(), (size_t)k * 4);
+  return k;
+}
+
+char *impgx_format_bed(const impgx_index *idx, const impgx_results *res, size_t row, const char *name) {
+  if (!idx || !res || res->on_device || row >= res->n_rows || !name) return nullptr;
+  std::string s;
+  for (uint64_t i = res->row_off[row]; i < res->row_off[row + 1]; i++) {
+    int32_t f = res->qf[i], l = res->ql[i];
+    char strand = '+';
+    if (f > l) {
+      std::swap(f, l);
+      strand = '-';
+    }
+    uint32_t id = res->qid[i];
+    if (id < idx->names.size() && !idx->names[id].empty()) s += idx->names[id];
+    else s += "seq" + std::to_string(id);
+    s += '\t';
+    s += std::to_string((uint32_t)f);
+    s += '\t';
+    s += std::to_string((uint32_t)l);
+    s += '\t';
+    s += name;
+    s += "\t.\t";
+    s += strand;
+    s += '\n';
+  }
+  char *p = (char *)malloc(s.size() + 1);
+  if (p) memcpy(p, s.c_str(), s.size() + 1);
+  return p;
+}
+
+void impgx_free(void *p) { free(p); }
+
+// ---- debug / test hooks (host only, usable without a GPU)
+// visit ranks of a target with n entries
+void impgx_debug_visit_ranks(size_t n, uint32_t *rank) { impgx::visit_ranks(n, rank); }
+
+// host columns of an index build (no device needed): returns entry count, fills
+// the arrays when non-NULL (sized by a first call with NULLs)
+long impgx_debug_host_columns(const impgx_record *records, size_t n, const uint64_t *run_offsets, uint32_t n_seqs,
+                              int bidirectional, int32_t *e_start, int32_t *e_end, int32_t *e_pmax, uint32_t *e_vrank,
+                              uint32_t *e_query_id, uint32_t *e_flags, uint32_t *e_aln, uint64_t *tgt_off) {
+  try {
+    impgx::HostColumns hc;
+    impgx::build_host_columns(records, n, run_offsets, n_seqs, bidirectional != 0, hc);
+    size_t E = hc.e_start.size();
+    if (e_start) {
+      memcpy(e_start, hc.e_start.data(), E * 4);
+      memcpy(e_end, hc.e_end.data(), E * 4);
+      memcpy(e_pmax, hc.e_pmax.data(), E * 4);
+      memcpy(e_vrank, hc.e_vrank.data(), E * 4);
+      for (size_t i = 0; i < E; i++) {
+        e_query_id[i] = hc.e_rec[i].query_id;
+        e_flags[i] = hc.e_rec[i].nruns_flags;
+        e_aln[i] = hc.e_rec[i].ck_off - hc.e_rec[i].blk_off;
+      }
+      memcpy(tgt_off, hc.tgt_off.data(), (n_seqs + 1) * 8);
+    }
+    return (long)E;
+  } catch (const std::exception &e) {
+    impgx::set_last_error(e.what());
+    return -1;
+  }
+}
+
+// ---- synthetic workload generator (bench / tests)
+uint64_t impgx_synth_num_alignments(const impgx_synth_cfg *c) { return synth_num_alignments(*c); }
+
+// records + per-alignment run counts for alignments [first, first+count)
+int impgx_synth_records(const impgx_synth_cfg *c, uint64_t first, uint64_t count, impgx_record *recs, uint32_t *n_runs) {
+  API_BEGIN
+  REQUIRE(c && recs && n_runs, IMPGX_E_INVALID, "NULL argument");
+  REQUIRE(c->genomes >= 2 && c->contigs >= 1 && c->tiles >= 1 && c->contig_len / c->tiles >= 256, IMPGX_E_INVALID,
+          "bad synthetic config");
+#pragma omp parallel for schedule(static)
+  for (long long i = 0; i < (long long)count; i++) n_runs[i] = synth_alignment(*c, first + (uint64_t)i, &recs[i], nullptr);
+  API_END
+}
+int impgx_synth_runs(const impgx_synth_cfg *c, uint64_t first, uint64_t count, const uint64_t *run_offsets, uint32_t *runs) {
+  API_BEGIN
+  REQUIRE(c && run_offsets && runs, IMPGX_E_INVALID, "NULL argument");
+#pragma omp parallel for schedule(static)
+  for (long long i = 0; i < (long long)count; i++)
+    synth_alignment(*c, first + (uint64_t)i, nullptr, runs + (run_offsets[i] - run_offsets[0]));
+  API_END
+}
+int impgx_synth_bed(const impgx_synth_cfg *c, uint64_t seed, uint64_t n_rows, uint32_t min_len, uint32_t max_len,
+                    impgx_range *out) {
+  API_BEGIN
+  REQUIRE(c && out && min_len >= 1 && max_len >= min_len, IMPGX_E_INVALID, "bad argument");
+  for (uint64_t k = 0; k < n_rows; k++) synth_bed_row(*c, seed, k, min_len, max_len, &out[k]);
+  API_END
+}
+
+// CIGAR text of a run stream, for the reference-cost CPU baseline (it preads
+// and parses text per hit): writes the concatenated CIGAR strings to `path`
+// and returns per-alignment byte offsets and lengths.
+int impgx_write_cigar_text(const uint32_t *runs, const uint64_t *run_offsets, uint64_t n, const char *path,
+                           uint64_t *offsets, uint64_t *lens) {
+  API_BEGIN
+  REQUIRE(runs && run_offsets && path && offsets && lens, IMPGX_E_INVALID, "NULL argument");
+  static const char OPS[] = "=XIDM";
+  auto digits = [](uint32_t v) {
+    int d = 1;
+    while (v >= 10) {
+      v /= 10;
+      d++;
+    }
+    return d;
+  };
+#pragma omp parallel for schedule(static)
+  for (long long i = 0; i < (long long)n; i++) {
+    uint64_t b = 0;
+    for (uint64_t k = run_offsets[i]; k < run_offsets[i + 1]; k++) b += (uint64_t)digits(IMPGX_RUN_LEN(runs[k])) + 1;
+    lens[i] = b;
+  }
+  uint64_t total = 0;
+  for (uint64_t i = 0; i < n; i++) {
+    offsets[i] = total;
+    total += lens[i];
+  }
+  FILE *f = fopen(path, "wb");
+  REQUIRE(f, IMPGX_E_IO, std::string("cannot create '") + path + "'");
+  const uint64_t CH = 1ull << 16;  // alignments per chunk
+  std::vector<char> buf;
+  for (uint64_t a = 0; a < n; a += CH) {
+    uint64_t b = std::min(n, a + CH);
+    uint64_t bytes = (b < n ? offsets[b] : total) - offsets[a];
+    buf.resize(bytes);
+#pragma omp parallel for schedule(static)
+    for (long long i = (long long)a; i < (long long)b; i++) {
+      char *p = buf.data() + (offsets[i] - offsets[a]);
+      for (uint64_t k = run_offsets[i]; k < run_offsets[i + 1]; k++) {
+        uint32_t len = IMPGX_RUN_LEN(runs[k]);
+        int dg = digits(len);
+        for (int j = dg - 1; j >= 0; j--) {
+          p[j] = (char)('0' + len % 10);
+          len /= 10;
+        }
+        p += dg;
+        *p++ = OPS[IMPGX_RUN_OP(runs[k])];
+      }
+    }
+    if (bytes && fwrite(buf.data(), 1, bytes, f) != bytes) {
+      fclose(f);
+      throw impgx::Error(IMPGX_E_IO, std::string("short write to '") + path + "'");
+    }
+  }
+  fclose(f);
+  API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,1046 @@
+// engine.cu — index upload, the batched query pipeline (stab -> liftover ->
+// fold -> frontier, per BFS level) and result assembly.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+
+#include "bfs_kernels.cuh"
+#include "engine.cuh"
+#include "merge_kernels.cuh"
+
+namespace impgx {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string &m) { g_last_error = m; }
+const char *last_error() { return g_last_error.c_str(); }
+
+static int g_sm_count = 0;
+static int sm_count() {
+  if (!g_sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+  }
+  return g_sm_count;
+}
+
+// grid sized as a multiple of the SM count (148 on B200): `per_sm` resident
+// CTAs per SM, capped by the work available.
+static unsigned grid_for(uint64_t work_items, unsigned threads, unsigned items_per_thread_group, unsigned per_sm) {
+  uint64_t groups = (work_items + items_per_thread_group - 1) / items_per_thread_group;
+  uint64_t blocks = (groups * 1 + (threads - 1)) / threads;
+  uint64_t cap = (uint64_t)sm_count() * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+// one thread per item
+static unsigned grid_threads(uint64_t n, unsigned threads = 256, unsigned per_sm = 8) {
+  uint64_t blocks = (n + threads - 1) / threads;
+  uint64_t cap = (uint64_t)sm_count() * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+// one warp per item
+static unsigned grid_warps(uint64_t n, unsigned threads = 256, unsigned per_sm = 8) {
+  uint64_t blocks = (n * 32 + threads - 1) / threads;
+  uint64_t cap = (uint64_t)sm_count() * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+// ----------------------------------------------------------------- CUB glue
+struct Scratch {
+  DBuf<uint8_t> buf;
+  void *ensure(size_t bytes, cudaStream_t s) {
+    if (buf.n < bytes) buf.alloc(bytes + bytes / 4 + 256, s);
+    return buf.get();
+  }
+};
+
+// in-place exclusive sum over n+1 elements: a[n] becomes the total
+static void exclusive_scan_u64(uint64_t *a, uint64_t n_plus_1, Scratch &sc, cudaStream_t s) {
+  size_t bytes = 0;
+  CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, a, a, n_plus_1, s));
+  void *tmp = sc.ensure(bytes, s);
+  CUDA_CHECK(cub::DeviceScan::ExclusiveSum(tmp, bytes, a, a, n_plus_1, s));
+}
+
+static int bits_for(uint64_t max_value) {
+  int b = 1;
+  while (b < 64 && (max_value >> b)) b++;
+  return b;
+}
+
+template <class K>
+static void sort_pairs(DBuf<K> &keys, DBuf<uint32_t> &vals, uint64_t n, int begin_bit, int end_bit, Scratch &sc,
+                       cudaStream_t s, Ctx &ctx) {
+  if (n == 0) return;
+  DBuf<K> k2(n, s);
+  DBuf<uint32_t> v2(n, s);
+  cub::DoubleBuffer<K> dk(keys.get(), k2.get());
+  cub::DoubleBuffer<uint32_t> dv(vals.get(), v2.get());
+  size_t bytes = 0;
+  CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, dk, dv, n, begin_bit, end_bit, s));
+  void *tmp = sc.ensure(bytes, s);
+  CUDA_CHECK(cub::DeviceRadixSort::SortPairs(tmp, bytes, dk, dv, n, begin_bit, end_bit, s));
+  ctx.launches += 2 + (uint64_t)((end_bit - begin_bit + 7) / 8);
+  if (dk.Current() != keys.get()) std::swap(keys, k2);
+  if (dv.Current() != vals.get()) std::swap(vals, v2);
+}
+
+static uint64_t read_u64(const uint64_t *d, cudaStream_t s, Ctx &ctx) {
+  uint64_t v = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&v, d, 8, cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  ctx.d2h_bytes += 8;
+  return v;
+}
+
+#define LAUNCH(kernel, grid, block, stream, ...)          \
+  do {                                                    \
+    kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__); \
+    CUDA_CHECK(cudaGetLastError());                       \
+    ctx.launches++;                                       \
+  } while (0)
+
+// ----------------------------------------------------------------- index
+}  // namespace impgx
+
+impgx_index::~impgx_index() {
+  cudaSetDevice(device);
+  cudaFree(d_start); cudaFree(d_end); cudaFree(d_pmax); cudaFree(d_seq_len);
+  cudaFree(d_vrank); cudaFree(d_runs); cudaFree(d_rec); cudaFree(d_tgt_off); cudaFree(d_ck);
+}
+
+namespace impgx {
+
+template <class T>
+static T *upload(const std::vector<T> &h, uint64_t &bytes_acc) {
+  T *d = nullptr;
+  size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+  CUDA_CHECK(cudaMalloc((void **)&d, bytes));
+  if (!h.empty()) CUDA_CHECK(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  bytes_acc += bytes;
+  return d;
+}
+
+void check_device(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    throw Error(IMPGX_E_NO_DEVICE, std::string("no CUDA device available (libimpgx has no CPU fallback): ") +
+                                       (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+  REQUIRE(device >= 0 && device < n, IMPGX_E_INVALID, "device ordinal out of range");
+  CUDA_CHECK(cudaSetDevice(device));
+  // keep freed stream-ordered allocations cached in the pool between calls
+  cudaMemPool_t pool;
+  CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
+  uint64_t thr = UINT64_MAX;
+  CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+}
+
+impgx_index *index_build(const impgx_record *recs, size_t n, const uint32_t *runs, const uint64_t *run_offsets,
+                         const uint64_t *seq_lens, uint32_t n_seqs, bool bidirectional, int device) {
+  check_device(device);
+  REQUIRE(recs || n == 0, IMPGX_E_INVALID, "records is NULL");
+  REQUIRE(run_offsets && seq_lens, IMPGX_E_INVALID, "run_offsets / seq_lens is NULL");
+  for (uint32_t s = 0; s < n_seqs; s++)
+    REQUIRE(seq_lens[s] <= (uint64_t)INT32_MAX, IMPGX_E_INVALID, "sequence longer than 2^31-1 (coordinates are i32)");
+  for (size_t i = 0; i < n; i++) REQUIRE(run_offsets[i] <= run_offsets[i + 1], IMPGX_E_INVALID, "run_offsets not monotone");
+
+  std::unique_ptr<impgx_index> idx(new impgx_index());
+  idx->device = device;
+  idx->n_seqs = n_seqs;
+  idx->n_records = n;
+  idx->seq_lens.assign(seq_lens, seq_lens + n_seqs);
+  idx->names.resize(n_seqs);
+
+  HostColumns hc;
+  build_host_columns(recs, n, run_offsets, n_seqs, bidirectional, hc);
+  idx->n_entries = hc.e_start.size();
+  idx->n_blocks = hc.blk_off[n];
+
+  uint64_t bytes = 0;
+  idx->d_start = upload(hc.e_start, bytes);
+  idx->d_end = upload(hc.e_end, bytes);
+  idx->d_pmax = upload(hc.e_pmax, bytes);
+  idx->d_vrank = upload(hc.e_vrank, bytes);
+  idx->d_rec = upload(hc.e_rec, bytes);
+  idx->d_tgt_off = upload(hc.tgt_off, bytes);
+  std::vector<int32_t> sl(n_seqs);
+  for (uint32_t s = 0; s < n_seqs; s++) sl[s] = (int32_t)seq_lens[s];
+  idx->d_seq_len = upload(sl, bytes);
+
+  // run stream: padded 32-run blocks + checkpoints, built on the device from
+  // the raw runs, uploaded in bounded chunks of alignments
+  const uint64_t n_ck = idx->n_blocks + n + 1;
+  size_t runs_bytes = std::max<uint64_t>(idx->n_blocks, 1) * RUNS_PER_BLOCK * sizeof(uint32_t);
+  CUDA_CHECK(cudaMalloc((void **)&idx->d_runs, runs_bytes));
+  CUDA_CHECK(cudaMalloc((void **)&idx->d_ck, n_ck * sizeof(Checkpoint)));
+  bytes += runs_bytes + n_ck * sizeof(Checkpoint);
+  {
+    const uint64_t chunk_runs = 256ull << 20;  // 1 GiB of raw runs per chunk
+    uint32_t *d_raw = nullptr;
+    uint64_t *d_off = nullptr;
+    uint32_t *d_blk = nullptr;
+    size_t cap_raw = 0, cap_aln = 0;
+    std::vector<uint64_t> rel;
+    Ctx ctx;
+    size_t a = 0;
+    while (a < n) {
+      size_t b = a;
+      uint64_t base = run_offsets[a];
+      while (b < n && (run_offsets[b + 1] - base <= chunk_runs || b == a)) b++;
+      uint64_t nr = run_offsets[b] - base;
+      size_t na = b - a;
+      if (nr > cap_raw) {
+        cudaFree(d_raw);
+        CUDA_CHECK(cudaMalloc((void **)&d_raw, std::max<uint64_t>(nr, 1) * 4));
+        cap_raw = nr;
+      }
+      if (na > cap_aln) {
+        cudaFree(d_off);
+        cudaFree(d_blk);
+        CUDA_CHECK(cudaMalloc((void **)&d_off, (na + 1) * 8));
+        CUDA_CHECK(cudaMalloc((void **)&d_blk, (na + 1) * 4));
+        cap_aln = na;
+      }
+      rel.resize(na + 1);
+      for (size_t i = 0; i <= na; i++) rel[i] = run_offsets[a + i] - base;
+      if (nr) CUDA_CHECK(cudaMemcpy(d_raw, runs + base, nr * 4, cudaMemcpyHostToDevice));
+      CUDA_CHECK(cudaMemcpy(d_off, rel.data(), (na + 1) * 8, cudaMemcpyHostToDevice));
+      CUDA_CHECK(cudaMemcpy(d_blk, hc.blk_off.data() + a, (na + 1) * 4, cudaMemcpyHostToDevice));
+      LAUNCH(k_build_blocks, grid_warps(na), 256, 0, d_raw, d_off, d_blk, (uint64_t)na, (uint64_t)a, idx->d_runs,
+             idx->d_ck);
+      CUDA_CHECK(cudaDeviceSynchronize());
+      a = b;
+    }
+    cudaFree(d_raw);
+    cudaFree(d_off);
+    cudaFree(d_blk);
+  }
+  idx->device_bytes = bytes;
+  return idx.release();
+}
+
+// ----------------------------------------------------------------- results
+}  // namespace impgx
+
+impgx_results::~impgx_results() {
+  if (on_device) {
+    cudaSetDevice(device);
+    cudaFree(d_row_off); cudaFree(d_qid); cudaFree(d_qf); cudaFree(d_ql); cudaFree(d_tid); cudaFree(d_tf);
+    cudaFree(d_tl); cudaFree(d_cig_off); cudaFree(d_cig);
+  }
+}
+
+namespace impgx {
+
+// Visited set of all rows: sorted by (row << 32 | seq, start)
+struct Visited {
+  DBuf<uint64_t> keys;
+  DBuf<int32_t> start, end;
+  uint64_t n = 0;
+};
+
+struct LevelHits {
+  DBuf<Hit> hits;          // ok hits in the reference's order (frontier index, visit rank)
+  DBuf<uint32_t> entry;    // entry index per hit (CIGAR emission), only with store_cigar
+  DBuf<CigarSlice> slices;
+  uint64_t n = 0;
+};
+
+struct BatchOut {
+  // device columns of the assembled results
+  DBuf<uint64_t> row_off;
+  DBuf<uint32_t> q_id, t_id;
+  DBuf<int32_t> q_first, q_last, t_first, t_last;
+  DBuf<uint64_t> cig_off;
+  DBuf<uint32_t> cig;
+  uint64_t n_results = 0, n_cig = 0;
+};
+
+class Runner {
+ public:
+  Runner(impgx_index *idx, const impgx_params &p, cudaStream_t s) : idx_(idx), p_(p), s_(s), ix_(idx->view()) {}
+
+  Ctx ctx;
+
+  // One batch of rows whose ranges are on the device. Produces raw results in
+  // reference order (bed == false) or BED-merged rows (bed == true).
+  void run(const impgx_range *d_ranges, uint32_t n_rows, bool bed, BatchOut &out);
+
+ private:
+  impgx_index *idx_;
+  impgx_params p_;
+  cudaStream_t s_;
+  DevIndexView ix_;
+  Scratch sc_;
+  DBuf<uint8_t> d_subset_;
+  DBuf<uint32_t> d_row_target_;
+  DBuf<unsigned long long> d_counters_;
+  cudaEvent_t ev_[2] = {nullptr, nullptr};
+
+  void stab_and_lift(const DBuf<Frontier> &fr, uint64_t nF, bool closed, bool clip, bool need_order, LevelHits &lvl);
+  void fold(const LevelHits &lvl, uint32_t n_rows, Visited &V, DBuf<Frontier> &next, uint64_t &n_next);
+  void assemble(const impgx_range *d_ranges, uint32_t n_rows, std::vector<LevelHits> &levels, bool query_mode,
+                BatchOut &out);
+  void bed_merge(BatchOut &raw, uint32_t n_rows, BatchOut &out);
+  float timed_begin();
+};
+
+// stab (count, scan, fill) + liftover of one frontier; leaves the accepted
+// hits ordered by (frontier index, visit rank) in lvl.
+void Runner::stab_and_lift(const DBuf<Frontier> &fr, uint64_t nF, bool closed, bool clip, bool need_order,
+                           LevelHits &lvl) {
+  lvl.n = 0;
+  if (nF == 0) return;
+  cudaEvent_t e0, e1, e2;
+  CUDA_CHECK(cudaEventCreate(&e0));
+  CUDA_CHECK(cudaEventCreate(&e1));
+  CUDA_CHECK(cudaEventCreate(&e2));
+  CUDA_CHECK(cudaEventRecord(e0, s_));
+  DBuf<Window> win(nF, s_);
+  DBuf<uint32_t> counts(nF, s_);
+  DBuf<uint64_t> offs(nF + 1, s_);
+  if (closed) LAUNCH(k_stab_count<true>, grid_warps(nF), 256, s_, ix_, fr.get(), nF, win.get(), counts.get());
+  else LAUNCH(k_stab_count<false>, grid_warps(nF), 256, s_, ix_, fr.get(), nF, win.get(), counts.get());
+  CUDA_CHECK(cudaMemsetAsync(offs.get() + nF, 0, 8, s_));
+  LAUNCH(k_u32_to_u64, grid_threads(nF), 256, s_, counts.get(), nF, offs.get());
+  exclusive_scan_u64(offs.get(), nF + 1, sc_, s_);
+  ctx.launches += 2;
+  const uint64_t H = read_u64(offs.get() + nF, s_, ctx);
+  REQUIRE(H < (1ull << 32), IMPGX_E_INVALID, "more than 2^32 hits in one hop of one batch; lower IMPGX_ROWS_PER_BATCH");
+  ctx.stab_ranges += nF;
+  ctx.liftovers += H;
+  if (H == 0) {
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    return;
+  }
+  DBuf<LiftTask> tasks(H, s_);
+  if (closed) LAUNCH(k_stab_fill<true>, grid_warps(nF), 256, s_, ix_, fr.get(), nF, win.get(), offs.get(), tasks.get());
+  else LAUNCH(k_stab_fill<false>, grid_warps(nF), 256, s_, ix_, fr.get(), nF, win.get(), offs.get(), tasks.get());
+  CUDA_CHECK(cudaEventRecord(e1, s_));
+
+  DBuf<Hit> hits(H, s_);
+  DBuf<CigarSlice> slices;
+  if (p_.store_cigar) slices.alloc(H, s_);
+  CUDA_CHECK(cudaMemsetAsync(d_counters_.get(), 0, 16, s_));
+  LiftParams lp;
+  lp.clip = clip ? 1 : 0;
+  lp.min_output_len = p_.min_output_length;
+  lp.use_identity = std::isnan(p_.min_identity) ? 0 : 1;
+  lp.min_identity = p_.min_identity;
+  // Impg::query applies the subset filter afterwards with the same rule
+  // (src/subset_filter.rs:84-100), so it is folded into the kernel in every mode
+  lp.subset = p_.subset_mask ? d_subset_.get() : nullptr;
+  lp.row_target = d_row_target_.get();
+  LAUNCH(k_liftover, grid_warps(H, 256, 8), 256, s_, ix_, fr.get(), tasks.get(), H, lp, hits.get(), slices.get(),
+         d_counters_.get());
+  CUDA_CHECK(cudaEventRecord(e2, s_));
+  unsigned long long cnt[2];
+  CUDA_CHECK(cudaMemcpyAsync(cnt, d_counters_.get(), 16, cudaMemcpyDeviceToHost, s_));
+  CUDA_CHECK(cudaStreamSynchronize(s_));
+  ctx.d2h_bytes += 16;
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  ctx.stab_ms += ms;
+  cudaEventElapsedTime(&ms, e1, e2);
+  ctx.lift_ms += ms;
+  ctx.lift_launches++;
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+  ctx.lift_runs += cnt[0];
+  // algorithmic bytes of the liftover: task 8 + range 16 +
+  // entry 32 + 2 checkpoints 16 + runs 4/run + hit 32 (+ slice 16)
+  ctx.lift_bytes += H * (8 + 16 + 32 + 16 + 32 + (p_.store_cigar ? 16 : 0)) + cnt[0] * 4;
+  const uint64_t n_ok = cnt[1];
+  lvl.n = n_ok;
+  if (n_ok == 0) return;
+
+  if (!need_order) {
+    // BED fast path for the last hop: order is carried by (range, vrank) keys
+    // inside the merge; here only compaction would be needed. Kept simple:
+    // fall through to the ordered path (a later round replaces this by binning).
+  }
+  DBuf<uint64_t> keys(H, s_);
+  DBuf<uint32_t> perm(H, s_);
+  LAUNCH(k_hit_order_keys, grid_threads(H), 256, s_, hits.get(), tasks.get(), H, (uint32_t)nF, keys.get(), perm.get());
+  sort_pairs(keys, perm, H, 0, 32 + bits_for(nF), sc_, s_, ctx);
+  lvl.hits.alloc(n_ok, s_);
+  LAUNCH(k_gather<Hit>, grid_threads(n_ok), 256, s_, hits.get(), perm.get(), n_ok, lvl.hits.get());
+  if (p_.store_cigar) {
+    lvl.entry.alloc(n_ok, s_);
+    lvl.slices.alloc(n_ok, s_);
+    LAUNCH(k_gather_entry, grid_threads(n_ok), 256, s_, tasks.get(), perm.get(), n_ok, lvl.entry.get());
+    LAUNCH(k_gather<CigarSlice>, grid_threads(n_ok), 256, s_, slices.get(), perm.get(), n_ok, lvl.slices.get());
+  }
+}
+
+// The sequential fold + next frontier of one level (src/impg.rs:2467-2593).
+void Runner::fold(const LevelHits &lvl, uint32_t n_rows, Visited &V, DBuf<Frontier> &next, uint64_t &n_next) {
+  n_next = 0;
+  const uint64_t n = lvl.n;
+  if (n == 0) return;
+  cudaEvent_t e0, e1;
+  CUDA_CHECK(cudaEventCreate(&e0));
+  CUDA_CHECK(cudaEventCreate(&e1));
+  CUDA_CHECK(cudaEventRecord(e0, s_));
+  // group by (row, q_id), stable w.r.t. the reference's hit order
+  DBuf<uint64_t> keys(n, s_);
+  DBuf<uint32_t> perm(n, s_);
+  LAUNCH(k_fold_keys, grid_threads(n), 256, s_, lvl.hits.get(), n, n_rows, keys.get(), perm.get());
+  sort_pairs(keys, perm, n, 0, 32 + bits_for(n_rows), sc_, s_, ctx);
+  DBuf<Hit> sorted(n, s_);
+  LAUNCH(k_gather<Hit>, grid_threads(n), 256, s_, lvl.hits.get(), perm.get(), n, sorted.get());
+
+  DBuf<uint64_t> head(n + 1, s_), head_scan(n + 1, s_), n_inc(1, s_);
+  CUDA_CHECK(cudaMemcpyAsync(n_inc.get(), &n, 8, cudaMemcpyHostToDevice, s_));
+  CUDA_CHECK(cudaMemsetAsync(head.get() + n, 0, 8, s_));
+  const uint64_t limit = (uint64_t)n_rows << 32;
+  LAUNCH(k_group_heads, grid_threads(n), 256, s_, keys.get(), n, limit, head.get(), n_inc.get());
+  CUDA_CHECK(cudaMemcpyAsync(head_scan.get(), head.get(), (n + 1) * 8, cudaMemcpyDeviceToDevice, s_));
+  exclusive_scan_u64(head_scan.get(), n + 1, sc_, s_);
+  ctx.launches += 2;
+  const uint64_t G = read_u64(head_scan.get() + n, s_, ctx);
+  if (G == 0) {
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return;
+  }
+  DBuf<FoldGroup> groups(G, s_);
+  DBuf<uint64_t> list_off(G + 1, s_), piece_off(G + 1, s_);
+  CUDA_CHECK(cudaMemsetAsync(list_off.get() + G, 0, 8, s_));
+  CUDA_CHECK(cudaMemsetAsync(piece_off.get() + G, 0, 8, s_));
+  LAUNCH(k_make_groups, grid_threads(n), 256, s_, keys.get(), head.get(), head_scan.get(), n, n_inc.get(),
+         V.keys.get(), V.n, groups.get(), list_off.get(), piece_off.get());
+  exclusive_scan_u64(list_off.get(), G + 1, sc_, s_);
+  exclusive_scan_u64(piece_off.get(), G + 1, sc_, s_);
+  ctx.launches += 4;
+  const uint64_t list_total = read_u64(list_off.get() + G, s_, ctx);
+  const uint64_t piece_total = read_u64(piece_off.get() + G, s_, ctx);
+  LAUNCH(k_set_group_offsets, grid_threads(G), 256, s_, groups.get(), G, list_off.get(), piece_off.get());
+
+  DBuf<int2> lists(list_total, s_);
+  DBuf<Frontier> pieces(piece_total, s_);
+  DBuf<uint32_t> list_len(G, s_), piece_cnt(G, s_);
+  LAUNCH(k_fold, grid_threads(G, 128, 16), 128, s_, groups.get(), G, sorted.get(), V.start.get(), V.end.get(),
+         ix_.seq_len, p_.min_distance_between_ranges, p_.min_transitive_len, lists.get(), list_len.get(), pieces.get(),
+         piece_cnt.get());
+
+  // ---- new visited set = untouched old entries + the groups' lists, re-sorted
+  DBuf<uint64_t> lo(G + 1, s_), po(G + 1, s_);
+  CUDA_CHECK(cudaMemsetAsync(lo.get() + G, 0, 8, s_));
+  CUDA_CHECK(cudaMemsetAsync(po.get() + G, 0, 8, s_));
+  LAUNCH(k_u32_to_u64, grid_threads(G), 256, s_, list_len.get(), G, lo.get());
+  LAUNCH(k_u32_to_u64, grid_threads(G), 256, s_, piece_cnt.get(), G, po.get());
+  exclusive_scan_u64(lo.get(), G + 1, sc_, s_);
+  exclusive_scan_u64(po.get(), G + 1, sc_, s_);
+  ctx.launches += 4;
+  const uint64_t new_lists = read_u64(lo.get() + G, s_, ctx);
+  const uint64_t n_pieces = read_u64(po.get() + G, s_, ctx);
+
+  DBuf<uint64_t> keep(V.n + 1, s_), keep_scan(V.n + 1, s_);
+  CUDA_CHECK(cudaMemsetAsync(keep.get() + V.n, 0, 8, s_));
+  if (V.n) LAUNCH(k_visited_keep_flags, grid_threads(V.n), 256, s_, V.keys.get(), V.n, groups.get(), G, keep.get());
+  CUDA_CHECK(cudaMemcpyAsync(keep_scan.get(), keep.get(), (V.n + 1) * 8, cudaMemcpyDeviceToDevice, s_));
+  exclusive_scan_u64(keep_scan.get(), V.n + 1, sc_, s_);
+  ctx.launches += 2;
+  const uint64_t kept = read_u64(keep_scan.get() + V.n, s_, ctx);
+  const uint64_t vn = kept + new_lists;
+  Visited nv;
+  nv.keys.alloc(vn, s_);
+  nv.start.alloc(vn, s_);
+  nv.end.alloc(vn, s_);
+  nv.n = vn;
+  if (V.n)
+    LAUNCH(k_visited_copy_kept, grid_threads(V.n), 256, s_, V.keys.get(), V.start.get(), V.end.get(), V.n, keep.get(),
+           keep_scan.get(), nv.keys.get(), nv.start.get(), nv.end.get());
+  LAUNCH(k_compact_lists, grid_threads(G), 256, s_, groups.get(), G, lists.get(), list_len.get(), lo.get(), kept,
+         nv.keys.get(), nv.start.get(), nv.end.get());
+  if (vn) {
+    // sort by (key, start): LSD = start first, then key (stable)
+    DBuf<uint32_t> sk(vn, s_), sp(vn, s_);
+    LAUNCH(k_iota_u32, grid_threads(vn), 256, s_, sp.get(), vn);
+    LAUNCH(k_start_keys_i32, grid_threads(vn), 256, s_, nv.start.get(), vn, sk.get());
+    sort_pairs(sk, sp, vn, 0, 32, sc_, s_, ctx);
+    DBuf<uint64_t> k2(vn, s_);
+    LAUNCH(k_gather<uint64_t>, grid_threads(vn), 256, s_, nv.keys.get(), sp.get(), vn, k2.get());
+    sort_pairs(k2, sp, vn, 0, 32 + bits_for(n_rows), sc_, s_, ctx);
+    DBuf<int32_t> s2(vn, s_), e2(vn, s_);
+    LAUNCH(k_gather<int32_t>, grid_threads(vn), 256, s_, nv.start.get(), sp.get(), vn, s2.get());
+    LAUNCH(k_gather<int32_t>, grid_threads(vn), 256, s_, nv.end.get(), sp.get(), vn, e2.get());
+    nv.keys = std::move(k2);
+    nv.start = std::move(s2);
+    nv.end = std::move(e2);
+  }
+  V = std::move(nv);
+
+  // ---- next frontier: pieces sorted by (row, id, start), touching ones merged
+  if (n_pieces) {
+    DBuf<Frontier> pc(n_pieces, s_);
+    LAUNCH(k_compact_pieces, grid_threads(G), 256, s_, groups.get(), G, pieces.get(), piece_cnt.get(), po.get(),
+           pc.get());
+    DBuf<uint32_t> sk(n_pieces, s_), sp(n_pieces, s_);
+    LAUNCH(k_piece_start_keys, grid_threads(n_pieces), 256, s_, pc.get(), n_pieces, sk.get(), sp.get());
+    sort_pairs(sk, sp, n_pieces, 0, 32, sc_, s_, ctx);
+    DBuf<uint64_t> k2(n_pieces, s_);
+    LAUNCH(k_piece_seq_keys, grid_threads(n_pieces), 256, s_, pc.get(), sp.get(), n_pieces, k2.get());
+    sort_pairs(k2, sp, n_pieces, 0, 32 + bits_for(n_rows), sc_, s_, ctx);
+    DBuf<Frontier> ps(n_pieces, s_);
+    LAUNCH(k_gather<Frontier>, grid_threads(n_pieces), 256, s_, pc.get(), sp.get(), n_pieces, ps.get());
+    DBuf<uint64_t> fh(n_pieces + 1, s_), fs(n_pieces + 1, s_);
+    CUDA_CHECK(cudaMemsetAsync(fh.get() + n_pieces, 0, 8, s_));
+    LAUNCH(k_frontier_heads, grid_threads(n_pieces), 256, s_, ps.get(), n_pieces, fh.get());
+    CUDA_CHECK(cudaMemcpyAsync(fs.get(), fh.get(), (n_pieces + 1) * 8, cudaMemcpyDeviceToDevice, s_));
+    exclusive_scan_u64(fs.get(), n_pieces + 1, sc_, s_);
+    ctx.launches += 2;
+    n_next = read_u64(fs.get() + n_pieces, s_, ctx);
+    next.alloc(n_next, s_);
+    LAUNCH(k_frontier_merge, grid_threads(n_pieces), 256, s_, ps.get(), n_pieces, fh.get(), fs.get(), next.get());
+  }
+  CUDA_CHECK(cudaEventRecord(e1, s_));
+  CUDA_CHECK(cudaStreamSynchronize(s_));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  ctx.fold_ms += ms;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+}
+
+// Per-row concatenation: self interval, then each level's hits in order.
+void Runner::assemble(const impgx_range *d_ranges, uint32_t n_rows, std::vector<LevelHits> &levels, bool query_mode,
+                      BatchOut &out) {
+  const int32_t min_out = p_.min_output_length;
+  DBuf<uint32_t> seed_cnt(n_rows, s_), total_cnt(n_rows, s_);
+  // Impg::query's caller filters every result incl. the self interval by
+  // min_output_length (src/main.rs:11686-11691); BFS never filters the seed.
+  LAUNCH(k_seed_counts, grid_threads(n_rows), 256, s_, d_ranges, n_rows, min_out, query_mode ? 1 : 0, seed_cnt.get());
+  CUDA_CHECK(cudaMemcpyAsync(total_cnt.get(), seed_cnt.get(), n_rows * 4, cudaMemcpyDeviceToDevice, s_));
+
+  struct PerLevel {
+    DBuf<uint64_t> pass, pass_scan, row_start;
+    DBuf<uint32_t> row_cnt;
+  };
+  std::vector<PerLevel> pl(levels.size());
+  for (size_t l = 0; l < levels.size(); l++) {
+    const uint64_t n = levels[l].n;
+    pl[l].row_cnt.alloc(n_rows, s_);
+    CUDA_CHECK(cudaMemsetAsync(pl[l].row_cnt.get(), 0, n_rows * 4, s_));
+    if (n == 0) continue;
+    pl[l].pass.alloc(n + 1, s_);
+    pl[l].pass_scan.alloc(n + 1, s_);
+    CUDA_CHECK(cudaMemsetAsync(pl[l].pass.get() + n, 0, 8, s_));
+    LAUNCH(k_level_pass, grid_threads(n), 256, s_, levels[l].hits.get(), n, min_out, pl[l].pass.get(),
+           pl[l].row_cnt.get());
+    CUDA_CHECK(cudaMemcpyAsync(pl[l].pass_scan.get(), pl[l].pass.get(), (n + 1) * 8, cudaMemcpyDeviceToDevice, s_));
+    exclusive_scan_u64(pl[l].pass_scan.get(), n + 1, sc_, s_);
+    pl[l].row_start.alloc(n_rows + 1, s_);
+    CUDA_CHECK(cudaMemsetAsync(pl[l].row_start.get() + n_rows, 0, 8, s_));
+    LAUNCH(k_u32_to_u64, grid_threads(n_rows), 256, s_, pl[l].row_cnt.get(), n_rows, pl[l].row_start.get());
+    exclusive_scan_u64(pl[l].row_start.get(), n_rows + 1, sc_, s_);
+    LAUNCH(k_add_u32, grid_threads(n_rows), 256, s_, total_cnt.get(), pl[l].row_cnt.get(), n_rows);
+    ctx.launches += 4;
+  }
+  out.row_off.alloc(n_rows + 1, s_);
+  CUDA_CHECK(cudaMemsetAsync(out.row_off.get() + n_rows, 0, 8, s_));
+  LAUNCH(k_u32_to_u64, grid_threads(n_rows), 256, s_, total_cnt.get(), n_rows, out.row_off.get());
+  exclusive_scan_u64(out.row_off.get(), n_rows + 1, sc_, s_);
+  ctx.launches += 2;
+  const uint64_t R = read_u64(out.row_off.get() + n_rows, s_, ctx);
+  out.n_results = R;
+  out.q_id.alloc(R, s_); out.t_id.alloc(R, s_);
+  out.q_first.alloc(R, s_); out.q_last.alloc(R, s_);
+  out.t_first.alloc(R, s_); out.t_last.alloc(R, s_);
+  OutCols oc;
+  oc.q_id = out.q_id.get(); oc.q_first = out.q_first.get(); oc.q_last = out.q_last.get();
+  oc.t_id = out.t_id.get(); oc.t_first = out.t_first.get(); oc.t_last = out.t_last.get();
+  DBuf<uint32_t> src_entry;
+  DBuf<CigarSlice> src_slice;
+  oc.cig_len = nullptr; oc.src_entry = nullptr; oc.src_slice = nullptr;
+  if (p_.store_cigar) {
+    out.cig_off.alloc(R + 1, s_);
+    CUDA_CHECK(cudaMemsetAsync(out.cig_off.get(), 0, (R + 1) * 8, s_));
+    src_entry.alloc(R, s_);
+    src_slice.alloc(R, s_);
+    oc.cig_len = out.cig_off.get();
+    oc.src_entry = src_entry.get();
+    oc.src_slice = src_slice.get();
+  }
+  LAUNCH(k_scatter_seed, grid_threads(n_rows), 256, s_, d_ranges, n_rows, seed_cnt.get(), out.row_off.get(), oc);
+  DBuf<uint32_t> base(n_rows, s_);
+  CUDA_CHECK(cudaMemcpyAsync(base.get(), seed_cnt.get(), n_rows * 4, cudaMemcpyDeviceToDevice, s_));
+  for (size_t l = 0; l < levels.size(); l++) {
+    const uint64_t n = levels[l].n;
+    if (n) {
+      LAUNCH(k_scatter_level, grid_threads(n), 256, s_, levels[l].hits.get(), levels[l].entry.get(),
+             levels[l].slices.get(), n, pl[l].pass.get(), pl[l].pass_scan.get(), pl[l].row_start.get(),
+             out.row_off.get(), base.get(), oc);
+      LAUNCH(k_add_u32, grid_threads(n_rows), 256, s_, base.get(), pl[l].row_cnt.get(), n_rows);
+    }
+  }
+  if (p_.store_cigar) {
+    exclusive_scan_u64(out.cig_off.get(), R + 1, sc_, s_);
+    ctx.launches += 2;
+    out.n_cig = read_u64(out.cig_off.get() + R, s_, ctx);
+    out.cig.alloc(std::max<uint64_t>(out.n_cig, 1), s_);
+    if (R) LAUNCH(k_emit_cigar_results, grid_warps(R), 256, s_, ix_, oc, out.cig_off.get(), R, out.cig.get());
+    CUDA_CHECK(cudaStreamSynchronize(s_));  // src_* are released on scope exit
+  }
+}
+
+void Runner::run(const impgx_range *d_ranges, uint32_t n_rows, bool bed, BatchOut &out) {
+  REQUIRE(p_.mode == IMPGX_MODE_QUERY || p_.mode == IMPGX_MODE_BFS, IMPGX_E_UNSUPPORTED,
+          "transitive DFS is not implemented on the device yet (use BFS)");
+  REQUIRE(!(bed && p_.store_cigar), IMPGX_E_INVALID, "BED output carries no CIGAR (src/main.rs:7447)");
+  d_counters_.alloc(2, s_);
+  // validation (perform_query bounds checks)
+  {
+    DBuf<int> bad(1, s_);
+    CUDA_CHECK(cudaMemsetAsync(bad.get(), 0, 4, s_));
+    LAUNCH(k_validate, grid_threads(n_rows), 256, s_, d_ranges, n_rows, ix_.seq_len, ix_.n_seqs, bad.get());
+    int hb = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&hb, bad.get(), 4, cudaMemcpyDeviceToHost, s_));
+    CUDA_CHECK(cudaStreamSynchronize(s_));
+    REQUIRE(hb == 0, IMPGX_E_INVALID,
+            "range " + std::to_string(hb - 1) +
+                ": unknown target id, start >= end, negative start or end beyond the sequence length");
+  }
+  if (p_.subset_mask) {
+    d_subset_.alloc(ix_.n_seqs, s_);
+    CUDA_CHECK(cudaMemcpyAsync(d_subset_.get(), p_.subset_mask, ix_.n_seqs, cudaMemcpyHostToDevice, s_));
+    ctx.h2d_bytes += ix_.n_seqs;
+    d_row_target_.alloc(n_rows, s_);
+    LAUNCH(k_row_targets, grid_threads(n_rows), 256, s_, d_ranges, n_rows, d_row_target_.get());
+  }
+
+  DBuf<Frontier> fr(n_rows, s_);
+  LAUNCH(k_init_frontier, grid_threads(n_rows), 256, s_, d_ranges, n_rows, fr.get());
+  uint64_t nF = n_rows;
+  std::vector<LevelHits> levels;
+
+  if (p_.mode == IMPGX_MODE_QUERY) {
+    levels.emplace_back();
+    stab_and_lift(fr, nF, /*closed=*/true, /*clip=*/false, /*need_order=*/true, levels.back());
+  } else {
+    // seed: visited[target].insert(range) on an empty set returns the range
+    // itself (bounds were validated), which is output and, if long enough,
+    // becomes the level-0 frontier (src/impg.rs:2337-2373)
+    Visited V;
+    V.keys.alloc(n_rows, s_);
+    V.start.alloc(n_rows, s_);
+    V.end.alloc(n_rows, s_);
+    V.n = n_rows;
+    LAUNCH(k_seed_visited, grid_threads(n_rows), 256, s_, d_ranges, n_rows, V.keys.get(), V.start.get(), V.end.get());
+    if (p_.min_transitive_len > 0) {
+      // drop rows shorter than min_transitive_len from the frontier
+      DBuf<uint64_t> flag(nF + 1, s_), scan(nF + 1, s_);
+      CUDA_CHECK(cudaMemsetAsync(flag.get() + nF, 0, 8, s_));
+      LAUNCH(k_frontier_len_flags, grid_threads(nF), 256, s_, fr.get(), nF, p_.min_transitive_len, flag.get());
+      CUDA_CHECK(cudaMemcpyAsync(scan.get(), flag.get(), (nF + 1) * 8, cudaMemcpyDeviceToDevice, s_));
+      exclusive_scan_u64(scan.get(), nF + 1, sc_, s_);
+      ctx.launches += 2;
+      uint64_t keep = read_u64(scan.get() + nF, s_, ctx);
+      if (keep != nF) {
+        DBuf<Frontier> f2(keep, s_);
+        LAUNCH(k_frontier_compact, grid_threads(nF), 256, s_, fr.get(), nF, flag.get(), scan.get(), f2.get());
+        fr = std::move(f2);
+        nF = keep;
+      }
+    }
+    uint32_t depth = 0;
+    while (nF > 0 && (p_.max_depth == 0 || depth < p_.max_depth)) {
+      levels.emplace_back();
+      stab_and_lift(fr, nF, /*closed=*/false, /*clip=*/true, /*need_order=*/true, levels.back());
+      depth++;
+      const bool last = p_.max_depth != 0 && depth >= p_.max_depth;
+      DBuf<Frontier> next;
+      uint64_t n_next = 0;
+      if (!last) fold(levels.back(), n_rows, V, next, n_next);
+      fr = std::move(next);
+      nF = n_next;
+    }
+  }
+  BatchOut raw;
+  assemble(d_ranges, n_rows, levels, p_.mode == IMPGX_MODE_QUERY, bed ? raw : out);
+  if (bed) bed_merge(raw, n_rows, out);
+}
+
+}  // namespace impgx
+
+// ============================================================ BED merge
+namespace impgx {
+
+struct Groups {
+  DBuf<uint32_t> begins;  // G + 1
+  uint64_t G = 0;
+};
+
+static void build_groups(const uint64_t *keys, uint64_t n, Groups &g, Scratch &sc, cudaStream_t s, Ctx &ctx) {
+  DBuf<uint64_t> head(n + 1, s), scan(n + 1, s);
+  CUDA_CHECK(cudaMemsetAsync(head.get() + n, 0, 8, s));
+  LAUNCH(k_heads_u64, grid_threads(n), 256, s, keys, n, head.get());
+  CUDA_CHECK(cudaMemcpyAsync(scan.get(), head.get(), (n + 1) * 8, cudaMemcpyDeviceToDevice, s));
+  exclusive_scan_u64(scan.get(), n + 1, sc, s);
+  ctx.launches += 2;
+  g.G = read_u64(scan.get() + n, s, ctx);
+  g.begins.alloc(g.G + 1, s);
+  LAUNCH(k_group_begins, grid_threads(n), 256, s, head.get(), scan.get(), n, g.begins.get());
+  uint32_t n32 = (uint32_t)n;
+  CUDA_CHECK(cudaMemcpyAsync(g.begins.get() + g.G, &n32, 4, cudaMemcpyHostToDevice, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));  // n32 is a stack variable
+}
+
+void Runner::bed_merge(BatchOut &raw, uint32_t n_rows, BatchOut &out) {
+  cudaEvent_t e0, e1;
+  CUDA_CHECK(cudaEventCreate(&e0));
+  CUDA_CHECK(cudaEventCreate(&e1));
+  CUDA_CHECK(cudaEventRecord(e0, s_));
+  const uint64_t R = raw.n_results;
+  const int32_t d = p_.merge_distance;
+  const bool ms = p_.merge_strands != 0;
+  DBuf<uint32_t> row_cnt(n_rows, s_);
+  CUDA_CHECK(cudaMemsetAsync(row_cnt.get(), 0, (size_t)n_rows * 4, s_));
+  out.row_off.alloc(n_rows + 1, s_);
+  CUDA_CHECK(cudaMemsetAsync(out.row_off.get(), 0, ((size_t)n_rows + 1) * 8, s_));
+  out.n_results = 0;
+  if (R > 0) {
+    REQUIRE(R < (1ull << 32), IMPGX_E_INVALID, "more than 2^32 results in one batch; lower IMPGX_ROWS_PER_BATCH");
+    DBuf<uint32_t> row(R, s_);
+    LAUNCH(k_fill_rows, grid_threads(R), 256, s_, raw.row_off.get(), n_rows, R, row.get());
+    ResCols rc{raw.q_id.get(), raw.q_first.get(), raw.q_last.get(), raw.t_id.get(), raw.t_first.get(), raw.t_last.get()};
+    const int row_bits = bits_for(n_rows > 1 ? n_rows - 1 : 1);
+    DBuf<Box> boxes;
+    uint64_t nB = 0;
+    if (d >= 0) {
+      // ---- stage A
+      const int seq_bits = bits_for(ix_.n_seqs > 1 ? ix_.n_seqs - 1 : 1);
+      REQUIRE(row_bits + 2 * seq_bits + 1 <= 64, IMPGX_E_INVALID, "batch too large for the packed merge key");
+      DBuf<uint32_t> k1(R, s_), perm(R, s_);
+      LAUNCH(k_m2d_key1, grid_threads(R), 256, s_, rc, R, k1.get(), perm.get());
+      sort_pairs(k1, perm, R, 0, 32, sc_, s_, ctx);
+      DBuf<uint64_t> k2(R, s_);
+      LAUNCH(k_m2d_key2, grid_threads(R), 256, s_, rc, row.get(), perm.get(), R, seq_bits, k2.get());
+      sort_pairs(k2, perm, R, 0, row_bits + 2 * seq_bits + 1, sc_, s_, ctx);
+      Groups g;
+      build_groups(k2.get(), R, g, sc_, s_, ctx);
+      DBuf<uint32_t> parent(R, s_);
+      DBuf<Box> box(R, s_);
+      DBuf<uint64_t> is_root(R + 1, s_), root_scan(R + 1, s_);
+      CUDA_CHECK(cudaMemsetAsync(is_root.get() + R, 0, 8, s_));
+      LAUNCH(k_merge2d, grid_threads(g.G, 128, 16), 128, s_, rc, row.get(), perm.get(), g.begins.get(), g.G, (int64_t)d,
+             parent.get(), box.get(), is_root.get());
+      CUDA_CHECK(cudaMemcpyAsync(root_scan.get(), is_root.get(), (R + 1) * 8, cudaMemcpyDeviceToDevice, s_));
+      exclusive_scan_u64(root_scan.get(), R + 1, sc_, s_);
+      ctx.launches += 2;
+      nB = read_u64(root_scan.get() + R, s_, ctx);
+      DBuf<Box> cb(nB, s_);
+      DBuf<uint32_t> ok(nB, s_), ov(nB, s_);
+      LAUNCH(k_compact_boxes, grid_threads(R), 256, s_, box.get(), is_root.get(), root_scan.get(), R, cb.get(), ok.get(),
+             ov.get());
+      sort_pairs(ok, ov, nB, 0, bits_for(R), sc_, s_, ctx);
+      boxes.alloc(nB, s_);
+      LAUNCH(k_gather<Box>, grid_threads(nB), 256, s_, cb.get(), ov.get(), nB, boxes.get());
+    } else {
+      nB = R;
+      boxes.alloc(nB, s_);
+      LAUNCH(k_results_to_boxes, grid_threads(R), 256, s_, rc, row.get(), R, boxes.get());
+    }
+    OutCols oc;
+    oc.cig_len = nullptr; oc.src_entry = nullptr; oc.src_slice = nullptr;
+    auto alloc_out = [&](uint64_t n) {
+      out.n_results = n;
+      out.q_id.alloc(n, s_); out.t_id.alloc(n, s_);
+      out.q_first.alloc(n, s_); out.q_last.alloc(n, s_);
+      out.t_first.alloc(n, s_); out.t_last.alloc(n, s_);
+      oc.q_id = out.q_id.get(); oc.q_first = out.q_first.get(); oc.q_last = out.q_last.get();
+      oc.t_id = out.t_id.get(); oc.t_first = out.t_first.get(); oc.t_last = out.t_last.get();
+    };
+    if (d >= 0 || ms) {
+      // ---- stage B
+      DBuf<uint64_t> k1(nB, s_);
+      DBuf<uint32_t> perm(nB, s_);
+      LAUNCH(k_mq_key1, grid_threads(nB), 256, s_, boxes.get(), nB, k1.get(), perm.get());
+      sort_pairs(k1, perm, nB, 0, 33, sc_, s_, ctx);
+      DBuf<uint64_t> k2(nB, s_);
+      LAUNCH(k_mq_key2, grid_threads(nB), 256, s_, boxes.get(), perm.get(), nB, k2.get());
+      sort_pairs(k2, perm, nB, 0, 32 + row_bits, sc_, s_, ctx);
+      DBuf<Box> sorted(nB, s_);
+      LAUNCH(k_gather<Box>, grid_threads(nB), 256, s_, boxes.get(), perm.get(), nB, sorted.get());
+      Groups g;
+      build_groups(k2.get(), nB, g, sc_, s_, ctx);
+      DBuf<Box> swept(nB, s_);
+      DBuf<uint32_t> cnt(g.G, s_);
+      LAUNCH(k_sweep, grid_threads(g.G, 128, 16), 128, s_, sorted.get(), g.begins.get(), g.G, d, ms ? 1 : 0, swept.get(),
+             cnt.get());
+      DBuf<uint64_t> scan(g.G + 1, s_);
+      CUDA_CHECK(cudaMemsetAsync(scan.get() + g.G, 0, 8, s_));
+      LAUNCH(k_u32_to_u64, grid_threads(g.G), 256, s_, cnt.get(), g.G, scan.get());
+      exclusive_scan_u64(scan.get(), g.G + 1, sc_, s_);
+      ctx.launches += 2;
+      const uint64_t M = read_u64(scan.get() + g.G, s_, ctx);
+      alloc_out(M);
+      LAUNCH(k_sweep_compact, grid_threads(g.G), 256, s_, swept.get(), g.begins.get(), cnt.get(), scan.get(), g.G, oc,
+             row_cnt.get());
+    } else {
+      alloc_out(nB);
+      LAUNCH(k_boxes_to_cols, grid_threads(nB), 256, s_, boxes.get(), nB, oc, row_cnt.get());
+    }
+    LAUNCH(k_u32_to_u64, grid_threads(n_rows), 256, s_, row_cnt.get(), n_rows, out.row_off.get());
+    exclusive_scan_u64(out.row_off.get(), (uint64_t)n_rows + 1, sc_, s_);
+    ctx.launches += 2;
+  }
+  CUDA_CHECK(cudaEventRecord(e1, s_));
+  CUDA_CHECK(cudaStreamSynchronize(s_));
+  float msf = 0;
+  cudaEventElapsedTime(&msf, e0, e1);
+  ctx.merge_ms += msf;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+}
+
+// ============================================================ batch driver
+struct TooManyHits {};
+
+static uint64_t env_u64(const char *name, uint64_t dflt) {
+  const char *v = getenv(name);
+  if (!v || !*v) return dflt;
+  return strtoull(v, nullptr, 10);
+}
+
+impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n, const impgx_params &p, bool bed,
+                           bool ranges_on_device, bool results_to_host, void *stream) {
+  REQUIRE(idx, IMPGX_E_INVALID, "index is NULL");
+  REQUIRE(ranges || n == 0, IMPGX_E_INVALID, "ranges is NULL");
+  REQUIRE(p.mode <= IMPGX_MODE_DFS, IMPGX_E_INVALID, "unknown mode");
+  REQUIRE(p.max_depth <= 65535, IMPGX_E_INVALID, "max_depth is a u16 in the reference");
+  std::lock_guard<std::mutex> lock(idx->mu);
+  check_device(idx->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  auto t0 = std::chrono::steady_clock::now();
+
+  std::unique_ptr<impgx_results> res(new impgx_results());
+  res->device = idx->device;
+  res->n_rows = n;
+  res->has_cigar = p.store_cigar != 0;
+  res->row_off.assign(n + 1, 0);
+
+  Ctx total;
+  std::vector<std::unique_ptr<BatchOut>> dev_chunks;
+  std::vector<size_t> chunk_rows;
+  size_t chunk = (size_t)env_u64("IMPGX_ROWS_PER_BATCH", 8192);
+  if (chunk == 0) chunk = 8192;
+  DBuf<impgx_range> d_stage;
+  size_t done = 0;
+  uint64_t res_base = 0, cig_base = 0;
+  while (done < n) {
+    size_t m = std::min(chunk, n - done);
+    const impgx_range *d_r;
+    if (ranges_on_device) {
+      d_r = ranges + done;
+    } else {
+      if (d_stage.n < m) d_stage.alloc(m, s);
+      CUDA_CHECK(cudaMemcpyAsync(d_stage.get(), ranges + done, m * sizeof(impgx_range), cudaMemcpyHostToDevice, s));
+      total.h2d_bytes += m * sizeof(impgx_range);
+      d_r = d_stage.get();
+    }
+    std::unique_ptr<BatchOut> bo(new BatchOut());
+    Runner runner(idx, p, s);
+    runner.run(d_r, (uint32_t)m, bed, *bo);
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    const Ctx &c = runner.ctx;
+    total.launches += c.launches; total.lift_launches += c.lift_launches;
+    total.stab_ranges += c.stab_ranges; total.liftovers += c.liftovers;
+    total.lift_runs += c.lift_runs; total.lift_bytes += c.lift_bytes;
+    total.h2d_bytes += c.h2d_bytes; total.d2h_bytes += c.d2h_bytes;
+    total.lift_ms += c.lift_ms; total.stab_ms += c.stab_ms; total.fold_ms += c.fold_ms; total.merge_ms += c.merge_ms;
+
+    const uint64_t R = bo->n_results;
+    if (results_to_host) {
+      std::vector<uint64_t> ro(m + 1);
+      CUDA_CHECK(cudaMemcpyAsync(ro.data(), bo->row_off.get(), (m + 1) * 8, cudaMemcpyDeviceToHost, s));
+      size_t old = res->qid.size();
+      res->qid.resize(old + R); res->tid.resize(old + R);
+      res->qf.resize(old + R); res->ql.resize(old + R);
+      res->tf.resize(old + R); res->tl.resize(old + R);
+      if (R) {
+        CUDA_CHECK(cudaMemcpyAsync(res->qid.data() + old, bo->q_id.get(), R * 4, cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaMemcpyAsync(res->qf.data() + old, bo->q_first.get(), R * 4, cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaMemcpyAsync(res->ql.data() + old, bo->q_last.get(), R * 4, cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaMemcpyAsync(res->tid.data() + old, bo->t_id.get(), R * 4, cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaMemcpyAsync(res->tf.data() + old, bo->t_first.get(), R * 4, cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaMemcpyAsync(res->tl.data() + old, bo->t_last.get(), R * 4, cudaMemcpyDeviceToHost, s));
+      }
+      total.d2h_bytes += (m + 1) * 8 + R * 24;
+      if (res->has_cigar) {
+        std::vector<uint64_t> co(R + 1);
+        CUDA_CHECK(cudaMemcpyAsync(co.data(), bo->cig_off.get(), (R + 1) * 8, cudaMemcpyDeviceToHost, s));
+        size_t oldc = res->cig.size();
+        res->cig.resize(oldc + bo->n_cig);
+        if (bo->n_cig)
+          CUDA_CHECK(cudaMemcpyAsync(res->cig.data() + oldc, bo->cig.get(), bo->n_cig * 4, cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        if (res->cig_off.empty()) res->cig_off.push_back(0);
+        for (uint64_t i = 1; i <= R; i++) res->cig_off.push_back(cig_base + co[i]);
+        total.d2h_bytes += (R + 1) * 8 + bo->n_cig * 4;
+      }
+      CUDA_CHECK(cudaStreamSynchronize(s));
+      for (size_t i = 1; i <= m; i++) res->row_off[done + i] = res_base + ro[i];
+    } else {
+      std::vector<uint64_t> ro(m + 1);
+      CUDA_CHECK(cudaMemcpyAsync(ro.data(), bo->row_off.get(), (m + 1) * 8, cudaMemcpyDeviceToHost, s));
+      CUDA_CHECK(cudaStreamSynchronize(s));
+      for (size_t i = 1; i <= m; i++) res->row_off[done + i] = res_base + ro[i];
+      dev_chunks.push_back(std::move(bo));
+      chunk_rows.push_back(m);
+    }
+    res_base += R;
+    cig_base += bo ? bo->n_cig : 0;
+    done += m;
+  }
+  res->n_results = res_base;
+  res->n_cig = cig_base;
+  if (res->has_cigar && res->cig_off.empty()) res->cig_off.push_back(0);
+
+  if (!results_to_host) {
+    // concatenate the chunk outputs into one set of device columns
+    res->on_device = true;
+    const uint64_t R = res_base;
+    size_t rb = std::max<uint64_t>(R, 1) * 4;
+    CUDA_CHECK(cudaMalloc((void **)&res->d_row_off, (n + 1) * 8));
+    CUDA_CHECK(cudaMalloc((void **)&res->d_qid, rb));
+    CUDA_CHECK(cudaMalloc((void **)&res->d_qf, rb));
+    CUDA_CHECK(cudaMalloc((void **)&res->d_ql, rb));
+    CUDA_CHECK(cudaMalloc((void **)&res->d_tid, rb));
+    CUDA_CHECK(cudaMalloc((void **)&res->d_tf, rb));
+    CUDA_CHECK(cudaMalloc((void **)&res->d_tl, rb));
+    CUDA_CHECK(cudaMemcpyAsync(res->d_row_off, res->row_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, s));
+    uint64_t off = 0;
+    for (auto &c : dev_chunks) {
+      const uint64_t r = c->n_results;
+      if (r) {
+        CUDA_CHECK(cudaMemcpyAsync(res->d_qid + off, c->q_id.get(), r * 4, cudaMemcpyDeviceToDevice, s));
+        CUDA_CHECK(cudaMemcpyAsync(res->d_qf + off, c->q_first.get(), r * 4, cudaMemcpyDeviceToDevice, s));
+        CUDA_CHECK(cudaMemcpyAsync(res->d_ql + off, c->q_last.get(), r * 4, cudaMemcpyDeviceToDevice, s));
+        CUDA_CHECK(cudaMemcpyAsync(res->d_tid + off, c->t_id.get(), r * 4, cudaMemcpyDeviceToDevice, s));
+        CUDA_CHECK(cudaMemcpyAsync(res->d_tf + off, c->t_first.get(), r * 4, cudaMemcpyDeviceToDevice, s));
+        CUDA_CHECK(cudaMemcpyAsync(res->d_tl + off, c->t_last.get(), r * 4, cudaMemcpyDeviceToDevice, s));
+      }
+      off += r;
+    }
+    CUDA_CHECK(cudaStreamSynchronize(s));
+  }
+
+  auto t1 = std::chrono::steady_clock::now();
+  impgx_stats &st = idx->last;
+  st = impgx_stats{};
+  st.kernel_launches = total.launches;
+  st.stab_ranges = total.stab_ranges;
+  st.liftovers = total.liftovers;
+  st.lift_runs = total.lift_runs;
+  st.lift_bytes = total.lift_bytes;
+  st.results = res_base;
+  st.merged = bed ? res_base : 0;
+  st.h2d_bytes = total.h2d_bytes;
+  st.d2h_bytes = total.d2h_bytes;
+  st.lift_ms = total.lift_ms;
+  st.stab_ms = total.stab_ms;
+  st.fold_ms = total.fold_ms;
+  st.merge_ms = total.merge_ms;
+  st.total_ms = std::chrono::duration<float, std::milli>(t1 - t0).count();
+  st.stab_candidates = total.lift_launches;  // number of liftover launches (for per-launch averages)
+  return res.release();
+}
+
+// ============================================================ KAT surface
+void project_batch(int device, size_t n, const int32_t *req_start, const int32_t *req_end, const impgx_record *records,
+                   const uint32_t *runs, const uint64_t *run_offsets, int32_t *out4, uint8_t *ok,
+                   uint64_t *out_run_offsets, uint32_t *out_runs, size_t out_runs_cap) {
+  check_device(device);
+  REQUIRE(req_start && req_end && records && run_offsets && out4 && ok, IMPGX_E_INVALID, "NULL argument");
+  if (n == 0) return;
+  cudaStream_t s = nullptr;
+  Ctx ctx;
+  std::vector<EntryRec> recs(n);
+  std::vector<uint32_t> blk_off(n + 1);
+  std::vector<Frontier> fr(n);
+  std::vector<LiftTask> tasks(n);
+  uint64_t blocks = 0;
+  for (size_t i = 0; i < n; i++) {
+    const impgx_record &r = records[i];
+    uint64_t nr = run_offsets[i + 1] - run_offsets[i];
+    REQUIRE(nr < (1ull << 30), IMPGX_E_INVALID, "too many runs");
+    blk_off[i] = (uint32_t)blocks;
+    EntryRec e;
+    e.t_start = r.target_start; e.t_end = r.target_end;
+    e.q_start = r.query_start; e.q_end = r.query_end;
+    e.query_id = r.query_id;
+    e.nruns_flags = ((uint32_t)nr << 2) | (r.strand ? FLAG_STRAND : 0u) | (r.reserved & 1u ? FLAG_REVERSED : 0u);
+    e.blk_off = (uint32_t)blocks;
+    e.ck_off = (uint32_t)(blocks + i);
+    recs[i] = e;
+    blocks += (nr + RUNS_PER_BLOCK - 1) / RUNS_PER_BLOCK;
+    fr[i] = Frontier{(uint32_t)i, r.target_id, req_start[i], req_end[i]};
+    tasks[i] = LiftTask{(uint32_t)i, (uint32_t)i};
+  }
+  blk_off[n] = (uint32_t)blocks;
+  const uint64_t total_runs = run_offsets[n];
+  DBuf<uint32_t> d_raw(std::max<uint64_t>(total_runs, 1), s), d_blk(n + 1, s), d_runs(std::max<uint64_t>(blocks, 1) * RUNS_PER_BLOCK, s);
+  DBuf<uint64_t> d_off(n + 1, s);
+  DBuf<Checkpoint> d_ck(blocks + n + 1, s);
+  DBuf<EntryRec> d_rec(n, s);
+  DBuf<Frontier> d_fr(n, s);
+  DBuf<LiftTask> d_tasks(n, s);
+  DBuf<uint32_t> d_vrank(n, s);
+  DBuf<Hit> d_hits(n, s);
+  DBuf<CigarSlice> d_slices(n, s);
+  if (total_runs) CUDA_CHECK(cudaMemcpyAsync(d_raw.get(), runs, total_runs * 4, cudaMemcpyHostToDevice, s));
+  CUDA_CHECK(cudaMemcpyAsync(d_off.get(), run_offsets, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+  CUDA_CHECK(cudaMemcpyAsync(d_blk.get(), blk_off.data(), (n + 1) * 4, cudaMemcpyHostToDevice, s));
+  CUDA_CHECK(cudaMemcpyAsync(d_rec.get(), recs.data(), n * sizeof(EntryRec), cudaMemcpyHostToDevice, s));
+  CUDA_CHECK(cudaMemcpyAsync(d_fr.get(), fr.data(), n * sizeof(Frontier), cudaMemcpyHostToDevice, s));
+  CUDA_CHECK(cudaMemcpyAsync(d_tasks.get(), tasks.data(), n * sizeof(LiftTask), cudaMemcpyHostToDevice, s));
+  CUDA_CHECK(cudaMemsetAsync(d_vrank.get(), 0, n * 4, s));
+  LAUNCH(k_build_blocks, grid_warps(n), 256, s, d_raw.get(), d_off.get(), d_blk.get(), (uint64_t)n, (uint64_t)0,
+         d_runs.get(), d_ck.get());
+  DevIndexView ix{};
+  ix.e_rec = d_rec.get();
+  ix.e_vrank = d_vrank.get();
+  ix.ck = d_ck.get();
+  ix.runs = d_runs.get();
+  LiftParams lp{};
+  lp.clip = 0;
+  lp.min_output_len = -1;
+  LAUNCH(k_liftover, grid_warps(n), 256, s, ix, d_fr.get(), d_tasks.get(), (uint64_t)n, lp, d_hits.get(), d_slices.get(),
+         (unsigned long long *)nullptr);
+  std::vector<Hit> hits(n);
+  std::vector<CigarSlice> slices(n);
+  CUDA_CHECK(cudaMemcpyAsync(hits.data(), d_hits.get(), n * sizeof(Hit), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaMemcpyAsync(slices.data(), d_slices.get(), n * sizeof(CigarSlice), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  std::vector<uint64_t> oo(n + 1, 0);
+  for (size_t i = 0; i < n; i++) {
+    ok[i] = hits[i].row != INVALID_ID;
+    out4[4 * i + 0] = hits[i].q_first;
+    out4[4 * i + 1] = hits[i].q_last;
+    out4[4 * i + 2] = hits[i].t_first;
+    out4[4 * i + 3] = hits[i].t_last;
+    oo[i + 1] = oo[i] + slices[i].n_ops;
+  }
+  if (out_run_offsets) memcpy(out_run_offsets, oo.data(), (n + 1) * 8);
+  if (out_runs && oo[n]) {
+    REQUIRE(oo[n] <= out_runs_cap, IMPGX_E_INVALID, "out_runs capacity too small");
+    DBuf<uint64_t> d_oo(n + 1, s);
+    DBuf<uint32_t> d_out(oo[n], s);
+    CUDA_CHECK(cudaMemcpyAsync(d_oo.get(), oo.data(), (n + 1) * 8, cudaMemcpyHostToDevice, s));
+    LAUNCH(k_emit_cigar, grid_warps(n), 256, s, ix, d_tasks.get(), d_slices.get(), d_oo.get(), (uint64_t)n, d_out.get());
+    CUDA_CHECK(cudaMemcpyAsync(out_runs, d_out.get(), oo[n] * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+  }
+}
+
+}  // namespace impgx

@@ -1,0 +1,46 @@
+// engine.cuh — shared declarations between engine.cu and api.cu.
+#pragma once
+#include <memory>
+
+#include "index.cuh"
+
+namespace impgx {
+
+// per-call counters (become impgx_stats)
+struct Ctx {
+  uint64_t launches = 0, lift_launches = 0;
+  uint64_t stab_ranges = 0, stab_candidates = 0, liftovers = 0, lift_runs = 0, lift_bytes = 0;
+  uint64_t h2d_bytes = 0, d2h_bytes = 0;
+  float lift_ms = 0, stab_ms = 0, fold_ms = 0, merge_ms = 0;
+};
+
+const char *last_error();
+void check_device(int device);
+impgx_index *index_build(const impgx_record *recs, size_t n, const uint32_t *runs, const uint64_t *run_offsets,
+                         const uint64_t *seq_lens, uint32_t n_seqs, bool bidirectional, int device);
+
+// Runs the whole batch (chunked into row batches), ranges on host or device.
+impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n, const impgx_params &p, bool bed,
+                           bool ranges_on_device, bool results_to_host, void *stream);
+
+void project_batch(int device, size_t n, const int32_t *req_start, const int32_t *req_end, const impgx_record *records,
+                   const uint32_t *runs, const uint64_t *run_offsets, int32_t *out4, uint8_t *ok,
+                   uint64_t *out_run_offsets, uint32_t *out_runs, size_t out_runs_cap);
+
+}  // namespace impgx
+
+struct impgx_results {
+  int device = 0;
+  bool on_device = false;
+  size_t n_rows = 0, n_results = 0, n_cig = 0;
+  bool has_cigar = false;
+  // host columns
+  std::vector<uint64_t> row_off, cig_off;
+  std::vector<uint32_t> qid, tid, cig;
+  std::vector<int32_t> qf, ql, tf, tl;
+  // device columns (device-resident variant)
+  uint64_t *d_row_off = nullptr, *d_cig_off = nullptr;
+  uint32_t *d_qid = nullptr, *d_tid = nullptr, *d_cig = nullptr;
+  int32_t *d_qf = nullptr, *d_ql = nullptr, *d_tf = nullptr, *d_tl = nullptr;
+  ~impgx_results();
+};

@@ -1,0 +1,67 @@
+// index.cuh — the HBM-resident columnar index that replaces the reference's
+// per-target coitrees (Impg.trees, src/impg.rs:226,394-404) and its on-disk
+// CIGAR text (src/impg.rs:495-552).
+#pragma once
+#include <mutex>
+#include <string>
+#include <unordered_map>
+
+#include "common.cuh"
+
+namespace impgx {
+
+// Host-side staging of the entry columns (also used by CPU-only tests).
+struct HostColumns {
+  std::vector<int32_t> e_start, e_end, e_pmax;
+  std::vector<uint32_t> e_vrank;
+  std::vector<EntryRec> e_rec;
+  std::vector<uint64_t> tgt_off;   // n_seqs + 1
+  std::vector<uint32_t> blk_off;   // n_records + 1, in 32-run blocks
+};
+
+// coitrees 0.4.0 visit order (un-vendored dependency; restated from its
+// published algorithm, see DESIGN.md "visit order"): rank[i] = position of
+// sorted entry i in the order BasicCOITree::query would visit it if every
+// entry overlapped. A stab's hits sorted by rank are in the reference's order.
+constexpr size_t SIMPLE_SUBTREE_CUTOFF = 8;
+void visit_ranks(size_t n, uint32_t *rank);
+
+// Entry construction + ordering of Impg::from_multi_alignment_records
+// (src/impg.rs:1535-1652): forward entry under target_id, reversed entry under
+// query_id (skipped for self alignments), per-target order = record order,
+// then a stable sort by start (coitrees' radix sort on `first`).
+void build_host_columns(const impgx_record *recs, size_t n, const uint64_t *run_offsets, uint32_t n_seqs,
+                        bool bidirectional, HostColumns &out);
+
+struct Stats {
+  impgx_stats s{};
+};
+
+}  // namespace impgx
+
+struct impgx_index {
+  int device = 0;
+  uint32_t n_seqs = 0;
+  uint64_t n_entries = 0, n_records = 0, n_blocks = 0;
+  uint64_t device_bytes = 0;
+  std::vector<uint64_t> seq_lens;
+  std::vector<std::string> names;
+  std::unordered_map<std::string, uint32_t> name_to_id;
+  // device columns
+  int32_t *d_start = nullptr, *d_end = nullptr, *d_pmax = nullptr, *d_seq_len = nullptr;
+  uint32_t *d_vrank = nullptr, *d_runs = nullptr;
+  impgx::EntryRec *d_rec = nullptr;
+  uint64_t *d_tgt_off = nullptr;
+  impgx::Checkpoint *d_ck = nullptr;
+  std::mutex mu;  // one query batch at a time per index (handle is thread-safe)
+  impgx_stats last{};
+
+  impgx::DevIndexView view() const {
+    impgx::DevIndexView v;
+    v.e_start = d_start; v.e_end = d_end; v.e_pmax = d_pmax; v.e_vrank = d_vrank; v.e_rec = d_rec;
+    v.tgt_off = d_tgt_off; v.seq_len = d_seq_len; v.ck = d_ck; v.runs = d_runs;
+    v.n_seqs = n_seqs; v.n_entries = n_entries;
+    return v;
+  }
+  ~impgx_index();
+};

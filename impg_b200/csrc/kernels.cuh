@@ -1,0 +1,452 @@
+// kernels.cuh — hand-written sm_100a kernels of the projection path.
+//
+//   k_build_blocks   K0  raw CIGAR runs -> padded 32-run blocks + position checkpoints
+//   k_stab_count     K1a warp-per-range interval stabbing, count pass
+//   k_stab_fill      K1b same scan, emits (entry, range) lift tasks via ballot/prefix
+//   k_liftover       K2  warp-per-hit CIGAR walk (thread-per-run, checkpointed start)
+//
+// All arithmetic is integer (i32 coordinates, u32 packed runs); the work is
+// HBM-bound gather/scan, tensor cores are deliberately unused.
+#pragma once
+#include "common.cuh"
+
+namespace impgx {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// Streaming (read-once) loads: bypass L1 allocation so scans do not evict the
+// entry/checkpoint lines other warps are about to reuse.
+__device__ __forceinline__ int32_t ld_stream_i32(const int32_t *p) {
+  int32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+// Warp-cooperative partition point: pred is monotone (true...true false...false)
+// over [lo, hi); returns the first index where it is false. 32-ary search: each
+// round every lane probes one position, a ballot narrows the range 32-fold.
+template <class Pred>
+__device__ __forceinline__ uint64_t warp_partition_point(uint64_t lo, uint64_t hi, Pred pred) {
+  const unsigned lane = lane_id();
+  while (hi - lo > 32) {
+    uint64_t step = (hi - lo + 31) / 32;  // probe positions lo + (lane+1)*step - 1
+    uint64_t pos = lo + (uint64_t)(lane + 1) * step - 1;
+    bool in = pos < hi;
+    bool t = in ? pred(pos) : false;
+    unsigned b = __ballot_sync(FULL, t);
+    unsigned k = __popc(b);  // lanes 0..k-1 true (monotone)
+    uint64_t nlo = lo + (uint64_t)k * step;           // everything before probe k is true
+    uint64_t nhi = lo + (uint64_t)(k + 1) * step - 1; // probe k is false (or out of range)
+    if (nhi > hi) nhi = hi;
+    lo = nlo;
+    hi = nhi;
+    if (lo >= hi) return hi;
+  }
+  uint64_t pos = lo + lane;
+  bool t = pos < hi ? pred(pos) : false;
+  unsigned b = __ballot_sync(FULL, t);
+  return lo + __popc(b);
+}
+
+__device__ __forceinline__ int warp_incl_scan(int v) {
+  const unsigned lane = lane_id();
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int o = __shfl_up_sync(FULL, v, d);
+    if (lane >= (unsigned)d) v += o;
+  }
+  return v;
+}
+
+// ------------------------------------------------------------------ K0
+// One warp per alignment: copy its raw runs into 128-byte blocks (zero padded)
+// and write one checkpoint per block plus the totals.
+__global__ void __launch_bounds__(256) k_build_blocks(const uint32_t *__restrict__ raw,
+                                                      const uint64_t *__restrict__ run_off,
+                                                      const uint32_t *__restrict__ blk_off, uint64_t n_aln,
+                                                      uint64_t aln_base, uint32_t *__restrict__ runs,
+                                                      Checkpoint *__restrict__ ck) {
+  const unsigned lane = lane_id();
+  uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (; w < n_aln; w += nw) {
+    const uint64_t a = aln_base + w;
+    const uint64_t off = run_off[w], n = run_off[w + 1] - off;
+    const uint32_t b0 = blk_off[w];
+    const uint64_t c0 = (uint64_t)b0 + a;
+    const uint32_t nblk = (uint32_t)((n + RUNS_PER_BLOCK - 1) / RUNS_PER_BLOCK);
+    uint32_t t_acc = 0, q_acc = 0;
+    for (uint32_t b = 0; b < nblk; b++) {
+      uint64_t i = (uint64_t)b * RUNS_PER_BLOCK + lane;
+      uint32_t v = i < n ? raw[off + i] : 0u;
+      runs[((uint64_t)b0 + b) * RUNS_PER_BLOCK + lane] = v;
+      uint32_t op = v >> 29, len = v & 0x1fffffffu;
+      int td = op == IMPGX_OP_I ? 0 : (int)len;
+      int qd = op == IMPGX_OP_D ? 0 : (int)len;
+      int ts = warp_incl_scan(td), qs = warp_incl_scan(qd);
+      if (lane == 0) ck[c0 + b] = Checkpoint{t_acc, q_acc};
+      t_acc += (uint32_t)__shfl_sync(FULL, ts, 31);
+      q_acc += (uint32_t)__shfl_sync(FULL, qs, 31);
+    }
+    if (lane == 0) ck[c0 + nblk] = Checkpoint{t_acc, q_acc};
+  }
+}
+
+// ------------------------------------------------------------------ K1
+// Candidate window of one frontier range on its target's sorted entry columns.
+// closed = true  reproduces coitrees' closed-interval visit used by Impg::query
+//                (src/impg.rs:1897; iv.first <= end && start <= iv.last);
+// closed = false is the visit followed by the BFS clip test that drops empty
+//                overlaps (src/impg.rs:2398-2403), i.e. a half-open test.
+struct Window {
+  uint64_t lb, ub;
+};
+
+template <bool CLOSED>
+__device__ __forceinline__ Window stab_window(const DevIndexView &ix, uint32_t seq, int32_t rs, int32_t re) {
+  uint64_t lo = ix.tgt_off[seq], hi = ix.tgt_off[seq + 1];
+  const int32_t *st = ix.e_start, *pm = ix.e_pmax;
+  uint64_t ub = warp_partition_point(lo, hi, [&](uint64_t i) { return CLOSED ? st[i] <= re : st[i] < re; });
+  uint64_t lb = warp_partition_point(lo, ub, [&](uint64_t i) { return CLOSED ? pm[i] < rs : pm[i] <= rs; });
+  return Window{lb, ub};
+}
+
+template <bool CLOSED>
+__global__ void __launch_bounds__(256) k_stab_count(DevIndexView ix, const Frontier *__restrict__ fr, uint64_t n,
+                                                    Window *__restrict__ win, uint32_t *__restrict__ counts) {
+  const unsigned lane = lane_id();
+  uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (; w < n; w += nw) {
+    Frontier f = fr[w];
+    Window wd = stab_window<CLOSED>(ix, f.seq, f.start, f.end);
+    uint32_t c = 0;
+    for (uint64_t i = wd.lb + lane; i < wd.ub; i += 32) {
+      int32_t e = ld_stream_i32(ix.e_end + i);
+      c += (CLOSED ? e >= f.start : e > f.start) ? 1u : 0u;
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(FULL, c, d);
+    if (lane == 0) {
+      win[w] = wd;
+      counts[w] = c;
+    }
+  }
+}
+
+template <bool CLOSED>
+__global__ void __launch_bounds__(256) k_stab_fill(DevIndexView ix, const Frontier *__restrict__ fr, uint64_t n,
+                                                   const Window *__restrict__ win,
+                                                   const uint64_t *__restrict__ offsets,
+                                                   LiftTask *__restrict__ tasks) {
+  const unsigned lane = lane_id();
+  uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (; w < n; w += nw) {
+    const int32_t rs = fr[w].start;
+    Window wd = win[w];
+    uint64_t base = offsets[w];
+    for (uint64_t i0 = wd.lb; i0 < wd.ub; i0 += 32) {
+      uint64_t i = i0 + lane;
+      bool hit = false;
+      if (i < wd.ub) {
+        int32_t e = ld_stream_i32(ix.e_end + i);
+        hit = CLOSED ? e >= rs : e > rs;
+      }
+      unsigned b = __ballot_sync(FULL, hit);
+      if (hit) tasks[base + __popc(b & lanemask_lt())] = LiftTask{(uint32_t)i, (uint32_t)w};
+      base += __popc(b);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ K2
+// Result of one liftover, uniform across the warp.
+struct LiftOut {
+  bool ok;
+  int32_t q_start, q_end, t_start, t_end;
+  // clipped CIGAR slice in walk order (for store_cigar / identity)
+  uint32_t first_idx, last_idx;  // walk-order op indices [first, last)
+  int32_t first_off, last_rem;   // first_op_offset (>0 trims), last_op_remaining (<0 trims)
+  // gap-compressed identity terms over the clipped slice (src/impg.rs:2952-2973)
+  int32_t matches, mismatches, n_ins, n_del;
+  uint32_t runs_read;            // runs loaded (for the roofline accounting)
+};
+
+// project_target_range_through_alignment (src/impg.rs:2760-2898) for entry `rec`
+// and request [rs, re), by one warp. The walk starts at the last 32-run block
+// boundary whose target position is < rs (checkpointed), so the cost is
+// O(runs overlapping the request) instead of O(runs from the alignment start).
+//
+// Entry orientation (src/impg.rs:144-156,547-550): a REVERSED entry swaps
+// I<->D, and on the '-' strand also walks the stored runs backwards.
+__device__ __forceinline__ LiftOut lift_one(const EntryRec &rec, const Checkpoint *__restrict__ ckp,
+                                            const uint32_t *__restrict__ runs, int32_t rs, int32_t re) {
+  const unsigned lane = lane_id();
+  const uint32_t n = rec.nruns_flags >> 2;
+  const bool rev_strand = rec.nruns_flags & FLAG_STRAND;
+  const bool swap_id = rec.nruns_flags & FLAG_REVERSED;
+  const bool backward = swap_id && rev_strand;
+  const int32_t dir = rev_strand ? -1 : 1;
+  const uint32_t nblk = (n + RUNS_PER_BLOCK - 1) / RUNS_PER_BLOCK;
+  const Checkpoint *ck = ckp + rec.ck_off;
+  const uint32_t *blk = runs + (uint64_t)rec.blk_off * RUNS_PER_BLOCK;
+  const int32_t last_target_pos = min(rec.t_end, re);
+
+  LiftOut o;
+  o.ok = false;
+  o.q_start = o.q_end = o.t_start = o.t_end = -1;
+  o.first_idx = o.last_idx = 0;
+  o.first_off = o.last_rem = 0;
+  o.matches = o.mismatches = o.n_ins = o.n_del = 0;
+  o.runs_read = 0;
+  if (nblk == 0) return o;
+
+  // totals (walk-space): target axis of the walk is the query axis of the
+  // stored alignment when roles are swapped
+  const Checkpoint tot = ck[nblk];
+  const int64_t w_tot = swap_id ? tot.q_off : tot.t_off;
+  const int64_t wq_tot = swap_id ? tot.t_off : tot.q_off;
+  const int64_t rel = (int64_t)rs - (int64_t)rec.t_start;  // request start relative to walk start
+
+  // ---- locate the starting block
+  uint32_t pb;  // physical block where the walk starts
+  if (!backward) {
+    // largest b in [0,nblk) with P(b) < rel, else 0
+    uint64_t c = warp_partition_point(0, nblk, [&](uint64_t b) {
+      Checkpoint k = ck[b];
+      return (int64_t)(swap_id ? k.q_off : k.t_off) < rel;
+    });
+    pb = c > 0 ? (uint32_t)c - 1 : 0;
+  } else {
+    // walk block j starts at W - P(nblk-j); want largest j with that < rel,
+    // i.e. the first pb with P(pb+1) > W - rel, else nblk-1
+    const int64_t x = w_tot - rel;
+    uint64_t c = warp_partition_point(0, nblk, [&](uint64_t b) {
+      Checkpoint k = ck[b + 1];
+      return (int64_t)(swap_id ? k.q_off : k.t_off) <= x;
+    });
+    pb = c < nblk ? (uint32_t)c : nblk - 1;
+  }
+
+  // ---- walk state at the start of that block
+  int64_t tcons, qcons;  // walk-space target / query bases consumed so far
+  {
+    Checkpoint k = backward ? ck[pb + 1] : ck[pb];
+    int64_t pt = swap_id ? k.q_off : k.t_off, pq = swap_id ? k.t_off : k.q_off;
+    tcons = backward ? w_tot - pt : pt;
+    qcons = backward ? wq_tot - pq : pq;
+  }
+  int32_t target_pos = (int32_t)((int64_t)rec.t_start + tcons);
+  int32_t query_pos = rev_strand ? (int32_t)((int64_t)rec.q_end - qcons) : (int32_t)((int64_t)rec.q_start + qcons);
+
+  bool found = false;
+  int32_t last_rem = 0, first_off = 0;
+  for (;;) {
+    // lanes -> ops of this block in walk order
+    const uint32_t base = pb * RUNS_PER_BLOCK;
+    const uint32_t cnt = min((uint32_t)RUNS_PER_BLOCK, n - base);
+    const bool valid = lane < cnt;
+    const uint32_t pi = backward ? (cnt - 1 - lane) : lane;  // offset within the block
+    uint32_t v = valid ? blk[base + pi] : 0u;
+    o.runs_read += cnt;
+    uint32_t op = v >> 29;
+    const int32_t len = (int32_t)(v & 0x1fffffffu);
+    if (swap_id) op = op == IMPGX_OP_I ? IMPGX_OP_D : (op == IMPGX_OP_D ? IMPGX_OP_I : op);
+    const int32_t td = (op == IMPGX_OP_I) ? 0 : len;
+    const int32_t qd = (op == IMPGX_OP_D) ? 0 : len;  // |query_delta|
+    const int32_t ts_incl = warp_incl_scan(td), qs_incl = warp_incl_scan(qd);
+    const int32_t tp = target_pos + (ts_incl - td);
+    const int32_t qp = query_pos + (qs_incl - qd) * dir;
+    // loop break: first op whose starting target position is past the end
+    const unsigned brk = __ballot_sync(FULL, valid && tp > last_target_pos);
+    const unsigned live = brk ? ((1u << (__ffs(brk) - 1)) - 1u) : FULL;  // lanes before the break
+    const bool act = valid && ((live >> lane) & 1u);
+
+    bool ov = false;
+    int32_t pqs = 0, pts = 0, pqe = 0, pte = 0, foff = 0, lrem = 0;
+    bool sets_rem = false;
+    if (act) {
+      if (td == 0) {  // insertion arm (also any zero-length op)
+        ov = tp >= rs;
+        pqs = qp; pts = tp;
+        pqe = qp + qd * dir; pte = tp;
+      } else if (qd == 0) {  // deletion arm
+        int32_t os = max(tp, rs), oe = min(tp + td, last_target_pos);
+        ov = os < oe;
+        pqs = qp; pts = os; foff = os - tp;
+        pqe = qp; pte = oe; lrem = oe - (tp + td);
+        sets_rem = true;
+      } else {  // match / mismatch arm
+        int32_t os = max(tp, rs), oe = min(tp + td, re);
+        ov = os < oe;
+        pqs = qp + (os - tp) * dir; pts = os; foff = os - tp;
+        pqe = pqs + (oe - os) * dir; pte = oe; lrem = oe - (tp + td);
+        sets_rem = true;
+      }
+    }
+    const unsigned ovm = __ballot_sync(FULL, ov);
+    if (ovm) {
+      // walk-order index of lane l in this block
+      const uint32_t widx0 = backward ? (n - (base + cnt)) : base;
+      if (!found) {
+        const int fl = __ffs(ovm) - 1;
+        o.q_start = __shfl_sync(FULL, pqs, fl);
+        o.t_start = __shfl_sync(FULL, pts, fl);
+        first_off = __shfl_sync(FULL, foff, fl);
+        o.first_idx = widx0 + fl;
+        found = true;
+      }
+      const int ll = 31 - __clz(ovm);
+      o.q_end = __shfl_sync(FULL, pqe, ll);
+      o.t_end = __shfl_sync(FULL, pte, ll);
+      o.last_idx = widx0 + ll + 1;
+      const unsigned rm = __ballot_sync(FULL, ov && sets_rem);
+      if (rm) last_rem = __shfl_sync(FULL, lrem, 31 - __clz(rm));
+      // identity terms over overlapping ops (clipped lengths for =/X/M)
+      int32_t m_ = 0, x_ = 0, i_ = 0, d_ = 0;
+      if (ov) {
+        int32_t ol = (td == 0 || qd == 0) ? 0 : (pte - pts);
+        if (op == IMPGX_OP_EQ || op == IMPGX_OP_M) m_ = (td == 0) ? 0 : ol;
+        else if (op == IMPGX_OP_X) x_ = (td == 0) ? 0 : ol;
+        else if (op == IMPGX_OP_I) i_ = 1;
+        else if (op == IMPGX_OP_D) d_ = 1;
+      }
+#pragma unroll
+      for (int d = 16; d; d >>= 1) {
+        m_ += __shfl_xor_sync(FULL, m_, d);
+        x_ += __shfl_xor_sync(FULL, x_, d);
+        i_ += __shfl_xor_sync(FULL, i_, d);
+        d_ += __shfl_xor_sync(FULL, d_, d);
+      }
+      o.matches += m_; o.mismatches += x_; o.n_ins += i_; o.n_del += d_;
+    } else {
+      // keep the warp convergent for the ballots above
+    }
+    if (brk) break;
+    target_pos += __shfl_sync(FULL, ts_incl, 31);
+    query_pos += __shfl_sync(FULL, qs_incl, 31) * dir;
+    if (backward) {
+      if (pb == 0) break;
+      pb--;
+    } else {
+      pb++;
+      if (pb >= nblk) break;
+    }
+  }
+  o.first_off = first_off;
+  o.last_rem = last_rem;
+  o.ok = found && o.q_start != o.q_end && o.t_start != o.t_end;
+  return o;
+}
+
+// Parameters of a liftover launch.
+struct LiftParams {
+  int clip;                 // 1: BFS/DFS clip request to the entry interval (src/impg.rs:2398-2403)
+  int32_t min_output_len;   // < 0 none (applied by the caller in the reference; kept out of `ok`)
+  int use_identity;         // identity filter on the clipped slice (src/impg.rs:1283-1287)
+  double min_identity;
+  const uint8_t *subset;    // per seq id keep mask or nullptr (src/impg.rs:2430-2438)
+  const uint32_t *row_target;  // per batch row: the row's original target id (subset exemption)
+};
+
+// Per-hit CIGAR slice descriptor, written only when the caller wants CIGARs.
+struct __align__(16) CigarSlice {
+  uint32_t first_idx, n_ops;
+  int32_t first_off, last_rem;
+};
+
+__global__ void __launch_bounds__(256) k_liftover(DevIndexView ix, const Frontier *__restrict__ fr,
+                                                  const LiftTask *__restrict__ tasks, uint64_t n_tasks,
+                                                  LiftParams lp, Hit *__restrict__ hits,
+                                                  CigarSlice *__restrict__ slices,
+                                                  unsigned long long *__restrict__ counters) {
+  const unsigned lane = lane_id();
+  uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  unsigned long long runs_acc = 0, ok_acc = 0;
+  for (; w < n_tasks; w += nw) {
+    const LiftTask t = tasks[w];
+    const Frontier f = fr[t.range];
+    const EntryRec rec = ix.e_rec[t.entry];
+    int32_t rs = f.start, re = f.end;
+    if (lp.clip) {
+      rs = max(rs, rec.t_start);
+      re = min(re, rec.t_end);
+    }
+    LiftOut o = lift_one(rec, ix.ck, ix.runs, rs, re);
+    bool ok = o.ok;
+    if (ok && lp.use_identity) {
+      int32_t total = o.matches + o.mismatches + o.n_ins + o.n_del;
+      double idy = total == 0 ? 0.0 : (double)o.matches / (double)total;
+      ok = !(idy < lp.min_identity);
+    }
+    if (ok && lp.subset) {
+      ok = rec.query_id == lp.row_target[f.row] || lp.subset[rec.query_id] != 0;
+    }
+    runs_acc += o.runs_read;
+    ok_acc += ok ? 1 : 0;
+    if (lane == 0) {
+      Hit h;
+      h.row = ok ? f.row : INVALID_ID;
+      h.q_id = rec.query_id;
+      h.q_first = o.q_start;
+      h.q_last = o.q_end;
+      h.t_id = f.seq;
+      h.t_first = o.t_start;
+      h.t_last = o.t_end;
+      h.vrank = ix.e_vrank[t.entry];
+      hits[w] = h;
+      if (slices) slices[w] = CigarSlice{o.first_idx, ok ? o.last_idx - o.first_idx : 0u, o.first_off, o.last_rem};
+    }
+  }
+  if (lane == 0 && counters) {
+    atomicAdd(&counters[0], runs_acc);
+    atomicAdd(&counters[1], ok_acc);
+  }
+}
+
+// Writes the clipped CIGAR slices (projected_cigar_ops, src/impg.rs:2878-2886)
+// of accepted hits in walk order with the reference's op inversion applied.
+__global__ void __launch_bounds__(256) k_emit_cigar(DevIndexView ix, const LiftTask *__restrict__ tasks,
+                                                    const CigarSlice *__restrict__ slices,
+                                                    const uint64_t *__restrict__ out_off, uint64_t n_tasks,
+                                                    uint32_t *__restrict__ out) {
+  const unsigned lane = lane_id();
+  uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (; w < n_tasks; w += nw) {
+    const CigarSlice s = slices[w];
+    if (s.n_ops == 0) continue;
+    const EntryRec rec = ix.e_rec[tasks[w].entry];
+    const uint32_t n = rec.nruns_flags >> 2;
+    const bool swap_id = rec.nruns_flags & FLAG_REVERSED;
+    const bool backward = swap_id && (rec.nruns_flags & FLAG_STRAND);
+    const uint32_t *blk = ix.runs + (uint64_t)rec.blk_off * RUNS_PER_BLOCK;
+    uint32_t *dst = out + out_off[w];
+    for (uint32_t k = lane; k < s.n_ops; k += 32) {
+      uint32_t wi = s.first_idx + k;
+      uint32_t v = blk[backward ? (n - 1 - wi) : wi];
+      uint32_t op = v >> 29;
+      int32_t len = (int32_t)(v & 0x1fffffffu);
+      if (swap_id) op = op == IMPGX_OP_I ? IMPGX_OP_D : (op == IMPGX_OP_D ? IMPGX_OP_I : op);
+      if (k == 0 && s.first_off > 0) len -= s.first_off;
+      if (k == s.n_ops - 1 && s.last_rem < 0) len += s.last_rem;
+      dst[k] = (op << 29) | (uint32_t)len;
+    }
+  }
+}
+
+}  // namespace impgx

@@ -1,0 +1,261 @@
+// merge_kernels.cuh — output_results_bed's two merges on the device
+// (src/main.rs:11849-11866): merge_adjusted_intervals_gap_2d (:12858-13011)
+// then merge_query_adjusted_intervals (:12474-12560). Results are brought into
+// the group order each merge sorts by (radix sorts in engine.cu); the group
+// bodies below are literal per-group restatements, one thread per group.
+#pragma once
+#include "bfs_kernels.cuh"
+
+namespace impgx {
+
+struct ResCols {
+  const uint32_t *q_id;
+  const int32_t *q_first, *q_last;
+  const uint32_t *t_id;
+  const int32_t *t_first, *t_last;
+};
+
+__global__ void k_fill_rows(const uint64_t *__restrict__ row_off, uint32_t n_rows, uint64_t n, uint32_t *__restrict__ row) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) {
+    // last r with row_off[r] <= i
+    uint32_t lo = 0, hi = n_rows;
+    while (lo < hi) {
+      uint32_t mid = lo + (hi - lo) / 2;
+      if (row_off[mid + 1] <= i) lo = mid + 1;
+      else hi = mid;
+    }
+    row[i] = lo;
+  }
+}
+
+__global__ void k_start_keys_i32(const int32_t *__restrict__ v, uint64_t n, uint32_t *__restrict__ keys) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) keys[i] = (uint32_t)v[i] ^ 0x80000000u;
+}
+
+__global__ void k_row_targets(const impgx_range *__restrict__ ranges, uint32_t n, uint32_t *__restrict__ out) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) out[i] = ranges[i].target_id;
+}
+
+__global__ void k_frontier_len_flags(const Frontier *__restrict__ f, uint64_t n, int32_t min_len, uint64_t *__restrict__ flag) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) {
+    long long d = (long long)f[i].start - (long long)f[i].end;
+    flag[i] = ((d < 0 ? -d : d) >= min_len) ? 1 : 0;
+  }
+}
+__global__ void k_frontier_compact(const Frontier *__restrict__ f, uint64_t n, const uint64_t *__restrict__ flag,
+                                   const uint64_t *__restrict__ scan, Frontier *__restrict__ out) {
+  for (uint64_t i = gtid(); i < n; i += gstride())
+    if (flag[i]) out[scan[i]] = f[i];
+}
+
+// ---- stage A: 2D gap merge
+// sort key 1: q.first (forward) or -q.first (reverse), src/main.rs:12885-12892
+__global__ void k_m2d_key1(ResCols r, uint64_t n, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) {
+    int32_t f = r.q_first[i];
+    bool fwd = f <= r.q_last[i];
+    int32_t k = fwd ? f : -f;
+    keys[i] = (uint32_t)k ^ 0x80000000u;
+    vals[i] = (uint32_t)i;
+  }
+}
+// sort key 2: (row, q_id, t_id, strand) packed
+__global__ void k_m2d_key2(ResCols r, const uint32_t *__restrict__ row, const uint32_t *__restrict__ perm, uint64_t n,
+                           int seq_bits, uint64_t *__restrict__ keys) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) {
+    uint32_t s = perm[i];
+    bool fwd = r.q_first[s] <= r.q_last[s];
+    keys[i] = ((((uint64_t)row[s] << seq_bits | r.q_id[s]) << seq_bits | r.t_id[s]) << 1) | (fwd ? 1u : 0u);
+  }
+}
+
+__global__ void k_heads_u64(const uint64_t *__restrict__ keys, uint64_t n, uint64_t *__restrict__ head) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) head[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
+__global__ void k_group_begins(const uint64_t *__restrict__ head, const uint64_t *__restrict__ head_scan, uint64_t n,
+                               uint32_t *__restrict__ begins) {
+  for (uint64_t i = gtid(); i < n; i += gstride())
+    if (head[i]) begins[head_scan[i]] = (uint32_t)i;
+}
+
+struct Box {
+  int32_t q_lo, q_hi, t_lo, t_hi;
+  uint32_t min_idx;  // smallest input index of the members ("first untaken index", :12948-12958)
+  uint32_t q_id, t_id, row;
+};
+
+__device__ __forceinline__ uint32_t uf_find(uint32_t *parent, uint32_t x) {
+  while (parent[x] != x) {
+    parent[x] = parent[parent[x]];
+    x = parent[x];
+  }
+  return x;
+}
+
+// one thread per (row, q_id, t_id, strand) group; positions are sorted by key1 (stable)
+__global__ void __launch_bounds__(128) k_merge2d(ResCols r, const uint32_t *__restrict__ row,
+                                                 const uint32_t *__restrict__ perm, const uint32_t *__restrict__ begins,
+                                                 uint64_t n_groups, int64_t d, uint32_t *__restrict__ parent,
+                                                 Box *__restrict__ box, uint64_t *__restrict__ is_root) {
+  for (uint64_t g = gtid(); g < n_groups; g += gstride()) {
+    const uint32_t b = begins[g], e = begins[g + 1];
+    for (uint32_t a = b; a < e; a++) {
+      parent[a] = a;
+      is_root[a] = 0;
+    }
+    const uint32_t i0 = perm[b];
+    const bool fwd = r.q_first[i0] <= r.q_last[i0];
+    for (uint32_t a = b; a < e; a++) {
+      const uint32_t ia = perm[a];
+      const int64_t qa_start = fwd ? r.q_first[ia] : r.q_last[ia];
+      const int64_t qa_end = fwd ? r.q_last[ia] : r.q_first[ia];
+      const int64_t ta_start = r.t_first[ia], ta_end = r.t_last[ia];
+      for (uint32_t bb = a + 1; bb < e; bb++) {
+        const uint32_t ib = perm[bb];
+        const int64_t qb_start = fwd ? r.q_first[ib] : r.q_last[ib];
+        if (qb_start < qa_start) continue;
+        const int64_t q_gap = qb_start - qa_end;
+        if (q_gap > d) break;
+        const int64_t tb_start = r.t_first[ib], tb_end = r.t_last[ib];
+        int64_t t_gap;
+        bool t_forward;
+        if (fwd) {
+          t_gap = tb_start - ta_end;
+          t_forward = tb_start > ta_start;
+        } else {
+          t_gap = ta_start - tb_end;
+          t_forward = tb_end < ta_end;
+        }
+        if (!t_forward || t_gap > d) continue;
+        uint32_t ra = uf_find(parent, a), rb = uf_find(parent, bb);
+        if (ra != rb) parent[ra] = rb;
+      }
+    }
+    for (uint32_t a = b; a < e; a++) {
+      const uint32_t rt = uf_find(parent, a);
+      const uint32_t ia = perm[a];
+      const int32_t qf = r.q_first[ia], ql = r.q_last[ia], tf = r.t_first[ia], tl = r.t_last[ia];
+      if (!is_root[rt]) {
+        is_root[rt] = 1;
+        box[rt] = Box{qf, ql, tf, tl, ia, r.q_id[ia], r.t_id[ia], row[ia]};
+      } else {
+        Box bx = box[rt];
+        if (fwd) {
+          bx.q_lo = min(bx.q_lo, qf);
+          bx.q_hi = max(bx.q_hi, ql);
+        } else {
+          bx.q_lo = max(bx.q_lo, qf);
+          bx.q_hi = min(bx.q_hi, ql);
+        }
+        bx.t_lo = min(bx.t_lo, tf);
+        bx.t_hi = max(bx.t_hi, tl);
+        bx.min_idx = min(bx.min_idx, ia);
+        box[rt] = bx;
+      }
+    }
+  }
+}
+
+__global__ void k_compact_boxes(const Box *__restrict__ box, const uint64_t *__restrict__ is_root,
+                                const uint64_t *__restrict__ scan, uint64_t n, Box *__restrict__ out,
+                                uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) {
+    if (!is_root[i]) continue;
+    uint64_t o = scan[i];
+    out[o] = box[i];
+    keys[o] = box[i].min_idx;
+    vals[o] = (uint32_t)o;
+  }
+}
+
+// raw results -> Box form (when the 2D merge is skipped)
+__global__ void k_results_to_boxes(ResCols r, const uint32_t *__restrict__ row, uint64_t n, Box *__restrict__ out) {
+  for (uint64_t i = gtid(); i < n; i += gstride())
+    out[i] = Box{r.q_first[i], r.q_last[i], r.t_first[i], r.t_last[i], (uint32_t)i, r.q_id[i], r.t_id[i], row[i]};
+}
+
+// ---- stage B: query-axis merge
+// sort key 1: (start, !is_forward), src/main.rs:12481-12494
+__global__ void k_mq_key1(const Box *__restrict__ b, uint64_t n, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) {
+    Box x = b[i];
+    bool fwd = x.q_lo <= x.q_hi;
+    int32_t start = fwd ? x.q_lo : x.q_hi;
+    keys[i] = ((uint64_t)((uint32_t)start ^ 0x80000000u) << 1) | (fwd ? 0u : 1u);
+    vals[i] = (uint32_t)i;
+  }
+}
+__global__ void k_mq_key2(const Box *__restrict__ b, const uint32_t *__restrict__ perm, uint64_t n,
+                          uint64_t *__restrict__ keys) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) {
+    Box x = b[perm[i]];
+    keys[i] = ((uint64_t)x.row << 32) | x.q_id;
+  }
+}
+
+// one thread per (row, q_id) segment: the literal sweep of :12496-12556 on the
+// sorted boxes; merged intervals are written in place at the segment's slots.
+__global__ void __launch_bounds__(128) k_sweep(const Box *__restrict__ sorted, const uint32_t *__restrict__ begins,
+                                               uint64_t n_groups, int32_t merge_distance, int merge_strands,
+                                               Box *__restrict__ out, uint32_t *__restrict__ out_cnt) {
+  for (uint64_t g = gtid(); g < n_groups; g += gstride()) {
+    const uint32_t b = begins[g], e = begins[g + 1];
+    uint32_t w = b;
+    Box cur = sorted[b];
+    for (uint32_t rd = b + 1; rd < e; rd++) {
+      const Box nx = sorted[rd];
+      const bool cf = cur.q_lo <= cur.q_hi, nf = nx.q_lo <= nx.q_hi;
+      const int32_t cs = cf ? cur.q_lo : cur.q_hi, ce = cf ? cur.q_hi : cur.q_lo;
+      const int32_t ns = nf ? nx.q_lo : nx.q_hi, ne = nf ? nx.q_hi : nx.q_lo;
+      if (merge_distance < 0 || (!merge_strands && cf != nf) || (int64_t)ns > (int64_t)ce + merge_distance) {
+        out[w++] = cur;
+        cur = nx;
+      } else {
+        const int32_t ms = min(cs, ns), me = max(ce, ne);
+        bool mf = cf;
+        if (merge_strands && cf != nf) {
+          const int64_t cl = (int64_t)ce - cs, nl = (int64_t)ne - ns;
+          mf = nl > cl ? nf : cf;
+        }
+        cur.q_lo = mf ? ms : me;
+        cur.q_hi = mf ? me : ms;
+      }
+    }
+    out[w++] = cur;
+    out_cnt[g] = w - b;
+  }
+}
+
+__global__ void k_sweep_compact(const Box *__restrict__ out, const uint32_t *__restrict__ begins,
+                                const uint32_t *__restrict__ out_cnt, const uint64_t *__restrict__ scan,
+                                uint64_t n_groups, OutCols o, uint32_t *__restrict__ row_cnt) {
+  for (uint64_t g = gtid(); g < n_groups; g += gstride()) {
+    const uint32_t b = begins[g], c = out_cnt[g];
+    const uint64_t d0 = scan[g];
+    for (uint32_t k = 0; k < c; k++) {
+      Box x = out[b + k];
+      o.q_id[d0 + k] = x.q_id;
+      o.q_first[d0 + k] = x.q_lo;
+      o.q_last[d0 + k] = x.q_hi;
+      o.t_id[d0 + k] = x.t_id;
+      o.t_first[d0 + k] = x.t_lo;
+      o.t_last[d0 + k] = x.t_hi;
+    }
+    if (c) atomicAdd(&row_cnt[out[b].row], c);
+  }
+}
+
+__global__ void k_boxes_to_cols(const Box *__restrict__ b, uint64_t n, OutCols o, uint32_t *__restrict__ row_cnt) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) {
+    Box x = b[i];
+    o.q_id[i] = x.q_id;
+    o.q_first[i] = x.q_lo;
+    o.q_last[i] = x.q_hi;
+    o.t_id[i] = x.t_id;
+    o.t_first[i] = x.t_lo;
+    o.t_last[i] = x.t_hi;
+    atomicAdd(&row_cnt[x.row], 1u);
+  }
+}
+
+}  // namespace impgx

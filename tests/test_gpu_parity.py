@@ -1,0 +1,298 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU
+oracle on the same inputs (bit-exact: all integer work), against the committed
+golden fixtures, and — at larger sizes — through size-independent properties."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import _oracle as O
+import impg_b200 as ix
+from test_oracle_kat import LIFTOVER_KATS
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLDEN = json.load(open(os.path.join(GOLD, "golden.json")))
+
+
+def rec(t_start, t_end, q_start, q_end, strand, reversed_entry=False, qid=0, tid=1):
+    r = np.zeros(1, dtype=ix.RECORD_DTYPE)
+    r["query_id"], r["target_id"] = qid, tid
+    r["query_start"], r["query_end"], r["target_start"], r["target_end"] = q_start, q_end, t_start, t_end
+    r["strand"] = 1 if strand else 0
+    r["reserved"] = 1 if reversed_entry else 0
+    return r
+
+
+def test_liftover_kernel_kats():
+    """K2 against the reference's own 14 known-answer vectors (src/impg.rs:2981-3156)."""
+    recs, reqs, runs, offs = [], [], [], [0]
+    for req, r, cg, exp in LIFTOVER_KATS:
+        recs.append(rec(*r))
+        reqs.append(req)
+        c = O.cigar(cg)
+        runs.append(c)
+        offs.append(offs[-1] + len(c))
+    reqs.append((65, 65))  # empty request → None (src/impg.rs:3029-3033)
+    recs.append(rec(0, 100, 50, 200, False))
+    c = O.cigar("10=5I5D50=50I35=")
+    runs.append(c)
+    offs.append(offs[-1] + len(c))
+    got = ix.project_batch(reqs, np.concatenate(recs), np.concatenate(runs), np.array(offs, np.uint64))
+    for (req, r, cg, exp), g in zip(LIFTOVER_KATS, got):
+        assert g is not None
+        assert (g[0], g[1]) == (exp[0], exp[1])
+        assert O.cigar_str(g[2]) == exp[2]
+        if exp[3] is not None:
+            assert (g[3], g[4]) == (exp[3], exp[4])
+    assert got[-1] is None
+
+
+def random_cigar(rng, n_ops, zero_len=False):
+    ops = []
+    for _ in range(n_ops):
+        op = "=XIDM"[int(rng.integers(0, 5))]
+        ln = int(rng.integers(0 if zero_len else 1, 40))
+        ops.append(O.run(op, ln))
+    return np.array(ops, np.uint32)
+
+
+@pytest.mark.parametrize("seed,n_ops,zero_len", [(1, 5, False), (2, 40, False), (3, 33, True), (4, 200, False),
+                                                  (5, 1000, True), (6, 64, False), (7, 1, True)])
+def test_liftover_kernel_random_vs_oracle(seed, n_ops, zero_len):
+    """Random CIGARs (incl. zero-length ops, all five op kinds), all four entry
+    orientations, requests straddling every boundary: bit-exact vs the oracle."""
+    rng = np.random.default_rng(seed)
+    recs, reqs, runs, offs, expect = [], [], [], [0], []
+    for k in range(400):
+        cg = random_cigar(rng, int(rng.integers(1, n_ops + 1)), zero_len)
+        op, ln = cg >> 29, cg & 0x1FFFFFFF
+        tlen, qlen = int(ln[op != 2].sum()), int(ln[op != 3].sum())
+        strand = bool(rng.integers(0, 2))
+        reversed_entry = bool(rng.integers(0, 2))
+        ts, qs = int(rng.integers(0, 1000)), int(rng.integers(0, 1000))
+        if reversed_entry:  # entry keyed by the original query: roles swapped
+            e_t, e_q = (qs, qs + qlen), (ts, ts + tlen)
+        else:
+            e_t, e_q = (ts, ts + tlen), (qs, qs + qlen)
+        span = max(e_t[1] - e_t[0], 1)
+        a = e_t[0] + int(rng.integers(-5, span + 5))
+        b = a + int(rng.integers(1, span + 10))
+        if k % 7 == 0:
+            a, b = e_t[0], e_t[1]
+        recs.append(rec(e_t[0], e_t[1], e_q[0], e_q[1], strand, reversed_entry))
+        reqs.append((a, b))
+        runs.append(cg)
+        offs.append(offs[-1] + len(cg))
+        walk = O.invert(cg, strand) if reversed_entry else cg
+        expect.append(O.project((a, b), (e_t[0], e_t[1], e_q[0], e_q[1], strand), walk))
+    got = ix.project_batch(reqs, np.concatenate(recs), np.concatenate(runs), np.array(offs, np.uint64))
+    for i, (g, e) in enumerate(zip(got, expect)):
+        if e is None:
+            assert g is None, (i, reqs[i], g)
+        else:
+            assert g is not None, (i, reqs[i], e)
+            assert (g[0], g[1], g[3], g[4]) == (e[0], e[1], e[3], e[4]), (i, reqs[i])
+            assert list(g[2]) == list(e[2]), (i, reqs[i], O.cigar_str(g[2]), O.cigar_str(e[2]))
+
+
+# ---------------------------------------------------------------- whole path
+def build_both(recs, runs, offs, lens, names=None, bidirectional=True):
+    orc = O.Index.build(recs, runs, offs, lens, bidirectional=bidirectional, names=names)
+    gpu = ix.Impg.from_records(recs, runs, offs, lens, names=names, bidirectional=bidirectional)
+    return orc, gpu
+
+
+def compare_raw(orc, gpu, ranges, o_params, g_params, check_cigar=False):
+    ores, ooffs = orc.query_batch(ranges, o_params)
+    oc = ores.columns()
+    gres = gpu.query_batch(ranges, g_params)
+    gc = gres.columns()
+    assert gc["row_offsets"].tolist() == ooffs.tolist()
+    for k in ("q_id", "q_first", "q_last", "t_id", "t_first", "t_last"):
+        assert (gc[k] == oc[k]).all(), k
+    if check_cigar:
+        assert gc["cigar_offsets"].tolist() == oc["cigar_offsets"].tolist()
+        assert (gc["cigar_runs"] == oc["cigar_runs"]).all()
+    return len(oc["q_id"])
+
+
+def compare_bed(orc, gpu, ranges, o_params, g_params):
+    ores, ooffs = orc.query_batch(ranges, o_params, bed_merge=True)
+    oc = ores.columns()
+    gc = gpu.query_batch_bed(ranges, g_params).columns()
+    assert gc["row_offsets"].tolist() == ooffs.tolist()
+    for k in ("q_id", "q_first", "q_last"):
+        assert (gc[k] == oc[k]).all(), k
+    return len(oc["q_id"])
+
+
+def params_pair(**kw):
+    o = O.make_params(mode=kw.get("mode", 0), max_depth=kw.get("max_depth", 2),
+                      min_transitive_len=kw.get("min_transitive_len", 101), min_dist=kw.get("min_dist", 10),
+                      min_output_length=kw.get("min_output_length", -1), store_cigar=kw.get("store_cigar", False),
+                      min_identity=kw.get("min_identity", float("nan")), subset_mask=kw.get("subset_mask"),
+                      merge_distance=kw.get("merge_distance", 0), merge_strands=kw.get("merge_strands", True))
+    mol = kw.get("min_output_length", -1)
+    mi = kw.get("min_identity", float("nan"))
+    g = ix.make_params(mode=kw.get("mode", 0), max_depth=kw.get("max_depth", 2),
+                       min_transitive_len=kw.get("min_transitive_len", 101),
+                       min_distance_between_ranges=kw.get("min_dist", 10),
+                       min_output_length=None if mol < 0 else mol, store_cigar=kw.get("store_cigar", False),
+                       min_identity=None if mi != mi else mi, subset_mask=kw.get("subset_mask"),
+                       merge_distance=kw.get("merge_distance", 0), merge_strands=kw.get("merge_strands", True))
+    return o, g
+
+
+@pytest.fixture(scope="module")
+def small():
+    cfg = ix.synth_cfg(6, 2, 60000, 8, 30, 300, 3)
+    recs, runs, offs, lens, names = ix.synth_generate(cfg)
+    orc, gpu = build_both(recs, runs, offs, lens, names)
+    bed = ix.synth_bed(cfg, 300, seed=9, min_len=200, max_len=12000)
+    return cfg, orc, gpu, bed
+
+
+def test_query_depth1_raw(small):
+    cfg, orc, gpu, bed = small
+    n = compare_raw(orc, gpu, bed, *params_pair(mode=0))
+    assert n > 300 * 5
+
+
+def test_query_depth1_with_cigar_and_filters(small):
+    cfg, orc, gpu, bed = small
+    compare_raw(orc, gpu, bed, *params_pair(mode=0, store_cigar=True), check_cigar=True)
+    compare_raw(orc, gpu, bed, *params_pair(mode=0, min_output_length=3000))
+    compare_raw(orc, gpu, bed, *params_pair(mode=0, min_identity=0.955, store_cigar=True), check_cigar=True)
+    mask = np.zeros(12, np.uint8)
+    mask[[1, 4, 5, 9]] = 1
+    compare_raw(orc, gpu, bed, *params_pair(mode=0, subset_mask=mask))
+
+
+@pytest.mark.parametrize("depth", [1, 2, 3, 0])
+def test_bfs_raw(small, depth):
+    cfg, orc, gpu, bed = small
+    compare_raw(orc, gpu, bed[:120], *params_pair(mode=1, max_depth=depth))
+
+
+def test_bfs_options(small):
+    cfg, orc, gpu, bed = small
+    b = bed[:100]
+    compare_raw(orc, gpu, b, *params_pair(mode=1, max_depth=2, store_cigar=True), check_cigar=True)
+    compare_raw(orc, gpu, b, *params_pair(mode=1, max_depth=3, min_transitive_len=0, min_dist=0))
+    compare_raw(orc, gpu, b, *params_pair(mode=1, max_depth=3, min_transitive_len=2000, min_dist=500))
+    compare_raw(orc, gpu, b, *params_pair(mode=1, max_depth=2, min_output_length=2500))
+    compare_raw(orc, gpu, b, *params_pair(mode=1, max_depth=3, min_identity=0.95))
+    mask = np.zeros(12, np.uint8)
+    mask[[0, 2, 3, 7, 8]] = 1
+    compare_raw(orc, gpu, b, *params_pair(mode=1, max_depth=3, subset_mask=mask))
+
+
+@pytest.mark.parametrize("mode,depth", [(0, 1), (1, 2), (1, 3)])
+@pytest.mark.parametrize("d,merge_strands", [(0, True), (1000, True), (1000, False), (-1, True), (-1, False)])
+def test_bed_merge(small, mode, depth, d, merge_strands):
+    cfg, orc, gpu, bed = small
+    compare_bed(orc, gpu, bed[:150], *params_pair(mode=mode, max_depth=depth, merge_distance=d,
+                                                   merge_strands=merge_strands))
+
+
+def test_unidirectional_and_self_alignments():
+    cfg = ix.synth_cfg(4, 1, 40000, 5, 25, 500, 21)
+    recs, runs, offs, lens, names = ix.synth_generate(cfg)
+    # self alignments get no reversed entry (src/impg.rs:1584)
+    recs = recs.copy()
+    recs["query_id"][:6] = recs["target_id"][:6]
+    for bidir in (True, False):
+        orc, gpu = build_both(recs, runs, offs, lens, names, bidirectional=bidir)
+        bed = ix.synth_bed(cfg, 80, seed=4, min_len=300, max_len=9000)
+        compare_raw(orc, gpu, bed, *params_pair(mode=0))
+        compare_raw(orc, gpu, bed, *params_pair(mode=1, max_depth=3))
+
+
+def test_edge_cases():
+    cfg = ix.synth_cfg(3, 1, 30000, 3, 20, 500, 5)
+    recs, runs, offs, lens, names = ix.synth_generate(cfg)
+    orc, gpu = build_both(recs, runs, offs, lens, names)
+    o, g = params_pair(mode=1, max_depth=2)
+    # empty batch
+    r = gpu.query_batch(np.zeros(0, ix.RANGE_DTYPE), g)
+    assert r.n_rows == 0 and r.n_results == 0
+    # a range with no alignments at all → only the self interval
+    gap = np.array([(0, 9995, 10001)], ix.RANGE_DTYPE)
+    compare_raw(orc, gpu, gap, o, g)
+    # touching ranges (closed-interval visit, rejected by the liftover): boundaries of an alignment
+    t0 = recs[0]
+    edges = np.array([(t0["target_id"], max(t0["target_start"] - 50, 0), t0["target_start"]),
+                      (t0["target_id"], t0["target_end"], t0["target_end"] + 50),
+                      (t0["target_id"], t0["target_start"], t0["target_start"] + 1),
+                      (t0["target_id"], t0["target_end"] - 1, t0["target_end"]),
+                      (t0["target_id"], 0, 30000)], ix.RANGE_DTYPE)
+    edges = edges[edges["start"] < edges["end"]]
+    compare_raw(orc, gpu, edges, *params_pair(mode=0, store_cigar=True), check_cigar=True)
+    compare_raw(orc, gpu, edges, *params_pair(mode=1, max_depth=0, min_transitive_len=0))
+    # invalid rows are rejected like the reference (src/main.rs:11620-11639)
+    for bad in ([(99, 0, 10)], [(0, 10, 10)], [(0, 20, 10)], [(0, 0, 30001)], [(0, -5, 10)]):
+        with pytest.raises(ix.ImpgxError) as e:
+            gpu.query_batch(np.array(bad, ix.RANGE_DTYPE), g)
+        assert e.value.code == ix.E_INVALID
+
+
+@pytest.mark.parametrize("fixture", sorted(GOLDEN))
+def test_fixture_pafs_against_golden(fixture):
+    """The reference's own PAF fixtures through impgx_index_from_paf + the BED
+    entry point, against golden text produced by the oracle in the build container."""
+    path = os.path.join(GOLD, fixture)
+    gpu = ix.Impg.from_paf(path)
+    orc = O.Index.from_paf(path)
+    assert [gpu.seq_name(i) for i in range(gpu.n_seqs)] == [orc.seq_name(i) for i in range(orc.n_seqs)]
+    for c in GOLDEN[fixture]:
+        if c["format"] != "bed":
+            continue
+        sid = gpu.seq_id(c["seq"])
+        region = f"{c['seq']}:{c['start']}-{c['end']}"
+        g = ix.make_params(mode=c["mode"], max_depth=c["max_depth"], min_transitive_len=0, merge_distance=c["d"])
+        res = gpu.query_batch_bed(np.array([(sid, c["start"], c["end"])], ix.RANGE_DTYPE), g)
+        text = gpu.format_bed(res, 0, region)
+        assert hashlib.sha256(text.encode()).hexdigest() == c["sha256"], (fixture, c)
+    # raw results incl. CIGARs vs the oracle for every sequence
+    ranges = np.array([(s, 0, orc.seq_len(s)) for s in range(orc.n_seqs)], ix.RANGE_DTYPE)
+    compare_raw(orc, gpu, ranges, *params_pair(mode=0, store_cigar=True), check_cigar=True)
+    compare_raw(orc, gpu, ranges, *params_pair(mode=1, max_depth=0, min_transitive_len=0, store_cigar=True),
+                check_cigar=True)
+
+
+def test_medium_scale_properties():
+    """~20k alignments, 2k rows, depth 2: oracle parity on a row sample plus
+    size-independent properties on everything (BED rows sorted, disjoint beyond
+    the merge distance, idempotent under a second merge)."""
+    cfg = ix.synth_cfg(12, 2, 400000, 20, 60, 150, 17)
+    recs, runs, offs, lens, names = ix.synth_generate(cfg)
+    orc, gpu = build_both(recs, runs, offs, lens, names)
+    bed = ix.synth_bed(cfg, 2000, seed=23)
+    o, g = params_pair(mode=1, max_depth=2, merge_distance=1000)
+    gc = gpu.query_batch_bed(bed, g).columns()
+    sample = np.arange(0, 2000, 40)
+    ores, ooffs = orc.query_batch(bed[sample], o, bed_merge=True)
+    oc = ores.columns()
+    for j, r in enumerate(sample):
+        a, b = int(gc["row_offsets"][r]), int(gc["row_offsets"][r + 1])
+        oa, ob = int(ooffs[j]), int(ooffs[j + 1])
+        assert b - a == ob - oa
+        for k in ("q_id", "q_first", "q_last"):
+            assert (gc[k][a:b] == oc[k][oa:ob]).all()
+    ro = gc["row_offsets"]
+    lo = np.minimum(gc["q_first"], gc["q_last"]).astype(np.int64)
+    hi = np.maximum(gc["q_first"], gc["q_last"]).astype(np.int64)
+    for r in range(0, 2000, 7):
+        a, b = int(ro[r]), int(ro[r + 1])
+        assert b > a
+        q, s, e = gc["q_id"][a:b].astype(np.int64), lo[a:b], hi[a:b]
+        key = q * (1 << 32) + s
+        assert (np.diff(key) > 0).all()
+        same = q[1:] == q[:-1]
+        assert (s[1:][same] > e[:-1][same] + 1000).all()
+    st = gpu.stats()
+    assert st["liftovers"] > 0 and st["kernel_launches"] > 0 and st["lift_ms"] > 0

@@ -1,0 +1,128 @@
+"""CPU-only tests of the product's host side: the C-ABI library loads and
+exports every symbol include/impgx.h declares, the host index builder matches
+the oracle (entry order and coitrees visit order), the synthetic generator is
+self-consistent, and compute entry points fail loudly without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import _oracle as O
+import impg_b200 as ix
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "impgx.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(impgx_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 20
+    L = ix.lib()
+    missing = [n for n in sorted(names) if not hasattr(L, n)]
+    assert not missing, missing
+    assert L.impgx_abi_version() == 1
+
+
+def test_parse_cigar_matches_oracle():
+    for s in ["10=5I5D", "", "1M", "250=", "2=8D4=2X3=3D228=11I", "0=3X"]:
+        assert list(ix.parse_cigar(s)) == list(O.parse_cigar(s))
+    with pytest.raises(ix.ImpgxError):
+        ix.parse_cigar("10=5Q")
+
+
+def small_cfg(seed=7, genomes=5, contigs=2, tiles=6, contig_len=60000, eq_mean=40, rev=300):
+    return ix.synth_cfg(genomes, contigs, contig_len, tiles, eq_mean, rev, seed)
+
+
+def test_synth_records_are_consistent_with_their_cigars():
+    cfg = small_cfg()
+    recs, runs, offs, lens, names = ix.synth_generate(cfg)
+    assert len(recs) == 5 * 4 * 2 * 6 and len(names) == 10
+    for i in range(len(recs)):
+        r = runs[int(offs[i]):int(offs[i + 1])]
+        op, ln = r >> 29, r & 0x1FFFFFFF
+        t = int(ln[op != 2].sum())
+        q = int(ln[op != 3].sum())
+        assert t == recs[i]["target_end"] - recs[i]["target_start"]
+        assert q == recs[i]["query_end"] - recs[i]["query_start"]
+        assert recs[i]["query_end"] <= cfg.contig_len and recs[i]["target_end"] <= cfg.contig_len
+        assert op[0] == 0 and op[-1] == 0 and (ln > 0).all()
+        assert recs[i]["query_id"] != recs[i]["target_id"]
+    assert 0 < recs["strand"].mean() < 1
+    # deterministic
+    recs2, runs2, *_ = ix.synth_generate(small_cfg())
+    assert (recs2 == recs).all() and (runs2 == runs).all()
+    bed = ix.synth_bed(cfg, 100)
+    assert (bed["start"] < bed["end"]).all() and (bed["end"] <= cfg.contig_len).all()
+    assert (bed["end"] - bed["start"] >= 1000).all() and (bed["end"] - bed["start"] <= 10000).all()
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 8, 9, 17, 64, 100, 1000])
+def test_visit_ranks_are_a_permutation(n):
+    r = np.zeros(n, np.uint32)
+    ix.lib().impgx_debug_visit_ranks(C.c_size_t(n), r.ctypes.data_as(C.c_void_p))
+    assert sorted(r.tolist()) == list(range(n))
+    if n <= 8:  # a whole tree of <= SIMPLE_SUBTREE_CUTOFF nodes is one sorted run
+        assert r.tolist() == list(range(n))
+
+
+def test_host_columns_match_oracle_visit_order():
+    """The product's (sorted entry columns, visit_rank) reproduce the oracle's
+    coitrees restatement hit-for-hit and in order."""
+    cfg = small_cfg(seed=11, genomes=6, tiles=9)
+    recs, runs, offs, lens, names = ix.synth_generate(cfg)
+    # add overlapping / duplicate-start / self alignments to stress ties
+    extra = recs[:40].copy()
+    extra["target_start"] = recs[:40]["target_start"]
+    recs2 = np.concatenate([recs, extra])
+    offs2 = np.concatenate([offs, offs[-1] + (offs[1:41] - offs[0:40]).cumsum()]).astype(np.uint64)
+    runs2 = np.concatenate([runs] + [runs[int(offs[i]):int(offs[i + 1])] for i in range(40)])
+    n_seqs = len(lens)
+    cols = ix.host_columns(recs2, offs2, n_seqs)
+    orc = O.Index.build(recs2, runs2, offs2, lens)
+    rng = np.random.default_rng(5)
+    for _ in range(300):
+        t = int(rng.integers(0, n_seqs))
+        s = int(rng.integers(0, cfg.contig_len - 10))
+        e = s + int(rng.integers(1, 30000))
+        lo, hi = int(cols["tgt_off"][t]), int(cols["tgt_off"][t + 1])
+        sel = [i for i in range(lo, hi) if cols["e_start"][i] <= e and cols["e_end"][i] >= s]  # closed test
+        sel.sort(key=lambda i: cols["e_vrank"][i])
+        got = [(int(cols["e_aln"][i]), int((cols["e_flags"][i] >> 1) & 1)) for i in sel]
+        assert got == orc.stab_order(t, s, e)
+    # prefix max column
+    for t in range(n_seqs):
+        lo, hi = int(cols["tgt_off"][t]), int(cols["tgt_off"][t + 1])
+        assert (cols["e_pmax"][lo:hi] == np.maximum.accumulate(cols["e_end"][lo:hi])).all()
+        assert (np.diff(cols["e_start"][lo:hi]) >= 0).all()
+
+
+def test_compute_fails_loudly_without_gpu():
+    if ix.device_count() > 0:
+        pytest.skip("a GPU is present")
+    cfg = small_cfg()
+    recs, runs, offs, lens, names = ix.synth_generate(cfg)
+    with pytest.raises(ix.ImpgxError) as e:
+        ix.Impg.from_records(recs, runs, offs, lens)
+    assert e.value.code == ix.E_NO_DEVICE
+    with pytest.raises(ix.ImpgxError) as e:
+        ix.project_batch([(0, 10)], recs[:1], runs[: int(offs[1])], offs[:2])
+    assert e.value.code == ix.E_NO_DEVICE
+    with pytest.raises(ix.ImpgxError) as e:
+        ix.Impg.from_paf("/nonexistent.paf")
+    assert e.value.code == ix.E_NO_DEVICE
+
+
+def test_write_cigar_text_roundtrip(tmp_path):
+    cfg = small_cfg()
+    recs, runs, offs, lens, names = ix.synth_generate(cfg)
+    path = str(tmp_path / "cigars.txt")
+    o, l = ix.write_cigar_text(runs, offs, path)
+    blob = open(path, "rb").read()
+    assert len(blob) == int(o[-1] + l[-1])
+    for i in (0, 5, len(recs) - 1):
+        txt = blob[int(o[i]):int(o[i] + l[i])].decode()
+        assert list(O.parse_cigar(txt)) == list(runs[int(offs[i]):int(offs[i + 1])])
