@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py — ranges projected/sec for `impg query -b <BED> -x -m 2 -o bed` on
+synthetic all-vs-all alignments (BASELINE.json metric), one process per GPU.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c3|c2|c4|tiny]
+
+A step = one pass of the hot path over one batch of BED rows (stab, liftover,
+BFS fold/frontier, BED merges). `value` times it with the rows already in HBM
+and the merged rows left in HBM; `e2e` times the reference-facing C-ABI call
+with HOST buffers (H2D of the rows, D2H of the merged rows inside the timed
+region). `--impl reference` times the reference's CPU algorithm (the oracle
+port with the reference's cost structure: per-hit pread + CIGAR text parse,
+rows serial, threads inside a BFS level) on a bounded sample of the same rows.
+Multi-GPU: rows are independent, so each rank holds an index replica and owns
+its own batch of rows (weak scaling, no data-path collective).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "ranges projected/sec (batch -b query, -x depth 2)"
+UNIT = "ranges/s"
+
+WORKLOADS = {
+    # name: (genomes, contigs, contig_len, tiles, eq_mean, rev_permille, seed, bed_rows)
+    "tiny": (8, 2, 200000, 10, 100, 100, 1, 512),
+    "c2": (50, 8, 2500000, 51, 100, 100, 1, 10000),   # BASELINE configs[1]: depth 1
+    "c3": (50, 8, 2500000, 51, 100, 100, 1, 10000),   # BASELINE configs[2]: -x -m 2
+    "c4": (200, 8, 2500000, 63, 200, 100, 1, 100000),  # BASELINE configs[3] on one GPU
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.stop_flag = threading.Event()
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag.is_set():
+                    break
+                self.samples.append(line.strip())
+        except Exception:
+            pass
+
+    def stop(self):
+        self.stop_flag.set()
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[4 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def gen_workload(ix, name, rank):
+    g, c, L, a, eq, rev, seed, rows = WORKLOADS[name]
+    cfg = ix.synth_cfg(g, c, L, a, eq, rev, seed)
+    t0 = time.time()
+    recs, runs, offs, lens, names = ix.synth_generate(cfg)
+    bed = ix.synth_bed(cfg, rows, seed=2 + 1000 * rank)
+    return cfg, recs, runs, offs, lens, names, bed, time.time() - t0
+
+
+def mode_params(ix_or_O, name, is_oracle=False):
+    depth1 = name == "c2"
+    if is_oracle:
+        return ix_or_O.make_params(mode=ix_or_O.MODE_QUERY if depth1 else ix_or_O.MODE_BFS, max_depth=2,
+                                   min_transitive_len=101, min_dist=10, merge_distance=1000, merge_strands=True)
+    return ix_or_O.make_params(mode=ix_or_O.MODE_QUERY if depth1 else ix_or_O.MODE_BFS, max_depth=2,
+                               min_transitive_len=101, min_distance_between_ranges=10, merge_distance=1000,
+                               merge_strands=True)
+
+
+def cpu_reference_setup(name, recs, runs, offs, lens, names, ix):
+    """Oracle index with the reference's cost structure: CIGARs stay as TEXT in a
+    file, every hit preads + parses its whole CIGAR (reference src/impg.rs:495-552)."""
+    import _oracle as O
+
+    tmpdir = os.environ.get("IMPGX_TMP", tempfile.gettempdir())
+    path = os.path.join(tmpdir, f"impgx_cigars_{name}_{os.getpid()}.txt")
+    t0 = time.time()
+    o_off, o_len = ix.write_cigar_text(runs, offs, path)
+    orc = O.Index.build(recs, np.zeros(1, np.uint32), np.zeros(len(recs) + 1, np.uint64), lens, names=names)
+    orc.attach_cigar_file(path, o_off, o_len)
+    return O, orc, path, time.time() - t0
+
+
+def cpu_reference_time(O, orc, bed, name, budget_s, threads):
+    """Times the reference driver on a bounded row sample sized for ~budget_s."""
+    p = mode_params(O, name, is_oracle=True)
+    n_probe = min(4, len(bed))
+    orc.run_batch(bed[:1], p, threads=threads, fmt="bed")  # warm the page cache / allocator
+    t, nres, _, _ = orc.run_batch(bed[:n_probe], p, threads=threads, fmt="bed")
+    per_row = max(t / n_probe, 1e-6)
+    n = int(max(n_probe, min(len(bed), budget_s / per_row)))
+    t, nres, nbytes, csum = orc.run_batch(bed[:n], p, threads=threads, fmt="bed")
+    return n / t, n, t, nres
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="impgx", choices=["impgx", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("IMPGX_BENCH_WORKLOAD", "c3"), choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    name = args.workload
+    g, c, L, a, eq, rev, seed, rows = WORKLOADS[name]
+    config = {"workload": f"{name}: synthetic {g}-genome all-vs-all PAF, {g * (g - 1) * c * a} alignments, "
+                          f"{rows}-row BED per GPU, " + ("depth 1" if name == "c2" else "-x -m 2") + ", -d 1000 -o bed",
+              "genomes": g, "contigs": c, "contig_len": L, "alignments": g * (g - 1) * c * a, "bed_rows_per_gpu": rows,
+              "parallelism": f"rows sharded over {world} index replica(s)", "cache": "inputs larger than L2 "
+              "(index run stream >> 126 MB; every step re-reads it from HBM)"}
+    import impg_b200 as ix
+
+    # ------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cfg, recs, runs, offs, lens, names, bed, gen_s = gen_workload(ix, name, 0)
+        O, orc, path, setup_s = cpu_reference_setup(name, recs, runs, offs, lens, names, ix)
+        threads = O.lib().orc_max_threads()
+        try:
+            per_step_budget = max(2.0, min(args.cpu_budget, 150.0 / max(1, args.steps + args.warmup)))
+            vals, n_used = [], 0
+            for i in range(args.warmup + args.steps):
+                v, n_used, t, nres = cpu_reference_time(O, orc, bed, name, per_step_budget, threads)
+                if i >= args.warmup:
+                    vals.append((v, t))
+            value = float(np.mean([v for v, _ in vals])) if vals else 0.0
+            ms = float(np.mean([t for _, t in vals]) * 1e3) if vals else 0.0
+        finally:
+            try:
+                os.unlink(path)
+            except OSError:
+                pass
+        sample = f"first {n_used} of {rows} BED rows per step (reference driver: rows serial, {threads} threads inside a BFS level, per-hit pread+parse of CIGAR text)"
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------ GPU arm
+    import torch
+
+    if not torch.cuda.is_available() or ix.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: libimpgx has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    cfg, recs, runs, offs, lens, names, bed, gen_s = gen_workload(ix, name, rank)
+    t0 = time.time()
+    idx = ix.Impg.from_records(recs, runs, offs, lens, names=names, device=local_rank)
+    build_s = time.time() - t0
+    p = mode_params(ix, name)
+    n = len(bed)
+
+    # rows resident in HBM (value) and in pinned host memory (e2e)
+    bed_bytes = torch.from_numpy(bed.view(np.uint8).copy())
+    d_bed = bed_bytes.cuda()
+    h_bed = bed_bytes.pin_memory()
+    h_bed_np = np.frombuffer(h_bed.numpy(), dtype=ix.RANGE_DTYPE)
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        r = idx.query_batch_bed_device(d_bed.data_ptr(), n, p, stream.cuda_stream)
+        st = idx.stats()
+        return r, st
+
+    def step_host():
+        r = idx.query_batch_bed(h_bed_np, p)
+        st = idx.stats()
+        return r, st
+
+    sampler = ClockSampler(local_rank)
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    for _ in range(1):
+        step_host()
+
+    # ---- value: device-resident timing (CUDA events on the launching stream)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = lift_bytes = liftovers = lift_launches = merged = 0
+    lift_ms = stab_ms = fold_ms = merge_ms = 0.0
+    e0.record(stream)
+    for _ in range(args.steps):
+        r, st = step_device()
+        launches += st["kernel_launches"]
+        lift_bytes += st["lift_bytes"]
+        liftovers += st["liftovers"]
+        lift_launches += st["stab_candidates"]
+        lift_ms += st["lift_ms"]; stab_ms += st["stab_ms"]; fold_ms += st["fold_ms"]; merge_ms += st["merge_ms"]
+        merged = st["merged"]
+        del r
+    e1.record(stream)
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region
+    barrier()
+    h2d = d2h = 0
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(stream)
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        r, st = step_host()
+        h2d += st["h2d_bytes"]; d2h += st["d2h_bytes"]
+        del r
+    f1.record(stream)
+    torch.cuda.synchronize()
+    host_wall_ms = (time.perf_counter() - w0) * 1e3
+    barrier()
+    e2e_ms = max(f0.elapsed_time(f1), host_wall_ms)
+    if rank == 0:
+        sampler.stop()
+
+    t = torch.tensor([dev_ms, e2e_ms], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    total_rows = n * world * args.steps
+    value = total_rows / (dev_ms / 1e3)
+    e2e_value = total_rows / (e2e_ms / 1e3)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = peaks()
+    achieved = (lift_bytes / 1e9) / (lift_ms / 1e3) if lift_ms > 0 else 0.0
+    roofline = {"kernel": "k_liftover", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": lift_bytes / max(1, lift_launches),
+                "avg_launch_ms": lift_ms / max(1, lift_launches), "liftovers_per_step": liftovers / args.steps,
+                "step_share": {"liftover_ms": lift_ms / args.steps, "stab_ms": stab_ms / args.steps,
+                               "fold_ms": fold_ms / args.steps, "merge_ms": merge_ms / args.steps,
+                               "step_ms": dev_ms / args.steps}}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get("k_liftover_dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        O, orc, path, setup_s = cpu_reference_setup(name, recs, runs, offs, lens, names, ix)
+        try:
+            threads = O.lib().orc_max_threads()
+            v, n_used, tsec, nres = cpu_reference_time(O, orc, bed, name, args.cpu_budget, threads)
+            cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                            "sample": f"first {n_used} of {rows} BED rows, {tsec:.1f} s (oracle port with the reference's "
+                                      "cost structure: rows serial, threads inside a BFS level, per-hit pread+parse)"}
+        finally:
+            try:
+                os.unlink(path)
+            except OSError:
+                pass
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic", "config": config,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps,
+                    "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "clocks": sampler.summary(), "bed_rows_out_per_step": int(merged),
+            "setup": {"generate_s": gen_s, "index_build_s": build_s, "index_device_bytes": idx.device_bytes}}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
