@@ -160,6 +160,8 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("IMPGX_BENCH_WORKLOAD", "c3"), choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="for ncu: exactly --warmup + --steps device-resident steps, no e2e / cpu legs")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -245,6 +247,14 @@ def main():
         r = idx.query_batch_bed(h_bed_np, p)
         st = idx.stats()
         return r, st
+
+    if args.profile:
+        for _ in range(args.warmup + args.steps):
+            step_device()
+        torch.cuda.synchronize()
+        print(json.dumps({"profile_run": True, "workload": name, "steps": args.steps, "warmup": args.warmup,
+                          "stats_last_step": idx.stats()}))
+        return 0
 
     sampler = ClockSampler(local_rank)
     for _ in range(max(args.warmup, 3)):

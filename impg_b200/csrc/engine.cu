@@ -236,8 +236,9 @@ impgx_index *index_build(const impgx_record *recs, size_t n, const uint32_t *run
 impgx_results::~impgx_results() {
   if (on_device) {
     cudaSetDevice(device);
-    cudaFree(d_row_off); cudaFree(d_qid); cudaFree(d_qf); cudaFree(d_ql); cudaFree(d_tid); cudaFree(d_tf);
-    cudaFree(d_tl); cudaFree(d_cig_off); cudaFree(d_cig);
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaFreeAsync(d_row_off, s); cudaFreeAsync(d_qid, s); cudaFreeAsync(d_qf, s); cudaFreeAsync(d_ql, s);
+    cudaFreeAsync(d_tid, s); cudaFreeAsync(d_tf, s); cudaFreeAsync(d_tl, s);
   }
 }
 
@@ -909,15 +910,16 @@ impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n
   if (!results_to_host) {
     // concatenate the chunk outputs into one set of device columns
     res->on_device = true;
+    res->stream = s;
     const uint64_t R = res_base;
     size_t rb = std::max<uint64_t>(R, 1) * 4;
-    CUDA_CHECK(cudaMalloc((void **)&res->d_row_off, (n + 1) * 8));
-    CUDA_CHECK(cudaMalloc((void **)&res->d_qid, rb));
-    CUDA_CHECK(cudaMalloc((void **)&res->d_qf, rb));
-    CUDA_CHECK(cudaMalloc((void **)&res->d_ql, rb));
-    CUDA_CHECK(cudaMalloc((void **)&res->d_tid, rb));
-    CUDA_CHECK(cudaMalloc((void **)&res->d_tf, rb));
-    CUDA_CHECK(cudaMalloc((void **)&res->d_tl, rb));
+    CUDA_CHECK(cudaMallocAsync((void **)&res->d_row_off, (n + 1) * 8, s));
+    CUDA_CHECK(cudaMallocAsync((void **)&res->d_qid, rb, s));
+    CUDA_CHECK(cudaMallocAsync((void **)&res->d_qf, rb, s));
+    CUDA_CHECK(cudaMallocAsync((void **)&res->d_ql, rb, s));
+    CUDA_CHECK(cudaMallocAsync((void **)&res->d_tid, rb, s));
+    CUDA_CHECK(cudaMallocAsync((void **)&res->d_tf, rb, s));
+    CUDA_CHECK(cudaMallocAsync((void **)&res->d_tl, rb, s));
     CUDA_CHECK(cudaMemcpyAsync(res->d_row_off, res->row_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, s));
     uint64_t off = 0;
     for (auto &c : dev_chunks) {

@@ -32,6 +32,7 @@ void project_batch(int device, size_t n, const int32_t *req_start, const int32_t
 struct impgx_results {
   int device = 0;
   bool on_device = false;
+  void *stream = nullptr;  // stream the device columns were allocated on
   size_t n_rows = 0, n_results = 0, n_cig = 0;
   bool has_cigar = false;
   // host columns
