@@ -103,6 +103,13 @@ static uint64_t read_u64(const uint64_t *d, cudaStream_t s, Ctx &ctx) {
   return v;
 }
 
+struct WallTimer {
+  double &acc;
+  std::chrono::steady_clock::time_point t0;
+  explicit WallTimer(double &a) : acc(a), t0(std::chrono::steady_clock::now()) {}
+  ~WallTimer() { acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
 #define LAUNCH(kernel, grid, block, stream, ...)          \
   do {                                                    \
     kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__); \
@@ -303,6 +310,7 @@ void Runner::stab_and_lift(const DBuf<Frontier> &fr, uint64_t nF, bool closed, b
                            LevelHits &lvl) {
   lvl.n = 0;
   if (nF == 0) return;
+  std::unique_ptr<WallTimer> wt(new WallTimer(ctx.w_stab));
   cudaEvent_t e0, e1, e2;
   CUDA_CHECK(cudaEventCreate(&e0));
   CUDA_CHECK(cudaEventCreate(&e1));
@@ -329,6 +337,7 @@ void Runner::stab_and_lift(const DBuf<Frontier> &fr, uint64_t nF, bool closed, b
   if (closed) LAUNCH(k_stab_fill<true>, grid_warps(nF), 256, s_, ix_, fr.get(), nF, win.get(), offs.get(), tasks.get());
   else LAUNCH(k_stab_fill<false>, grid_warps(nF), 256, s_, ix_, fr.get(), nF, win.get(), offs.get(), tasks.get());
   CUDA_CHECK(cudaEventRecord(e1, s_));
+  wt.reset(new WallTimer(ctx.w_lift));
 
   DBuf<Hit> hits(H, s_);
   DBuf<CigarSlice> slices;
@@ -364,6 +373,7 @@ void Runner::stab_and_lift(const DBuf<Frontier> &fr, uint64_t nF, bool closed, b
   const uint64_t n_ok = cnt[1];
   lvl.n = n_ok;
   if (n_ok == 0) return;
+  wt.reset(new WallTimer(ctx.w_order));
 
   if (!need_order) {
     // BED fast path for the last hop: order is carried by (range, vrank) keys
@@ -389,6 +399,7 @@ void Runner::fold(const LevelHits &lvl, uint32_t n_rows, Visited &V, DBuf<Fronti
   n_next = 0;
   const uint64_t n = lvl.n;
   if (n == 0) return;
+  WallTimer wt(ctx.w_fold);
   cudaEvent_t e0, e1;
   CUDA_CHECK(cudaEventCreate(&e0));
   CUDA_CHECK(cudaEventCreate(&e1));
@@ -516,6 +527,7 @@ void Runner::fold(const LevelHits &lvl, uint32_t n_rows, Visited &V, DBuf<Fronti
 // Per-row concatenation: self interval, then each level's hits in order.
 void Runner::assemble(const impgx_range *d_ranges, uint32_t n_rows, std::vector<LevelHits> &levels, bool query_mode,
                       BatchOut &out) {
+  WallTimer wt(ctx.w_assemble);
   const int32_t min_out = p_.min_output_length;
   DBuf<uint32_t> seed_cnt(n_rows, s_), total_cnt(n_rows, s_);
   // Impg::query's caller filters every result incl. the self interval by
@@ -697,6 +709,7 @@ static void build_groups(const uint64_t *keys, uint64_t n, Groups &g, Scratch &s
 }
 
 void Runner::bed_merge(BatchOut &raw, uint32_t n_rows, BatchOut &out) {
+  WallTimer wt(ctx.w_merge);
   cudaEvent_t e0, e1;
   CUDA_CHECK(cudaEventCreate(&e0));
   CUDA_CHECK(cudaEventCreate(&e1));
@@ -859,6 +872,9 @@ impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n
     total.lift_runs += c.lift_runs; total.lift_bytes += c.lift_bytes;
     total.h2d_bytes += c.h2d_bytes; total.d2h_bytes += c.d2h_bytes;
     total.lift_ms += c.lift_ms; total.stab_ms += c.stab_ms; total.fold_ms += c.fold_ms; total.merge_ms += c.merge_ms;
+    total.w_stab += c.w_stab; total.w_lift += c.w_lift; total.w_order += c.w_order; total.w_fold += c.w_fold;
+    total.w_assemble += c.w_assemble; total.w_merge += c.w_merge;
+    WallTimer wcopy(total.w_copy);
 
     const uint64_t R = bo->n_results;
     if (results_to_host) {
@@ -955,6 +971,12 @@ impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n
   st.merge_ms = total.merge_ms;
   st.total_ms = std::chrono::duration<float, std::milli>(t1 - t0).count();
   st.stab_candidates = total.lift_launches;  // number of liftover launches (for per-launch averages)
+  if (getenv("IMPGX_TRACE"))
+    fprintf(stderr,
+            "[impgx] rows=%zu total=%.2f ms | wall: stab %.2f lift %.2f order %.2f fold %.2f assemble %.2f merge %.2f "
+            "copy %.2f | dev: stab %.2f lift %.2f fold %.2f merge %.2f | launches %llu\n",
+            n, st.total_ms, total.w_stab, total.w_lift, total.w_order, total.w_fold, total.w_assemble, total.w_merge,
+            total.w_copy, st.stab_ms, st.lift_ms, st.fold_ms, st.merge_ms, (unsigned long long)st.kernel_launches);
   return res.release();
 }
 

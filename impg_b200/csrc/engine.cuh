@@ -12,6 +12,8 @@ struct Ctx {
   uint64_t stab_ranges = 0, stab_candidates = 0, liftovers = 0, lift_runs = 0, lift_bytes = 0;
   uint64_t h2d_bytes = 0, d2h_bytes = 0;
   float lift_ms = 0, stab_ms = 0, fold_ms = 0, merge_ms = 0;
+  // host wall-clock per phase (IMPGX_TRACE=1 prints them)
+  double w_stab = 0, w_lift = 0, w_order = 0, w_fold = 0, w_assemble = 0, w_merge = 0, w_copy = 0;
 };
 
 const char *last_error();
