@@ -342,7 +342,7 @@ void Runner::stab_and_lift(const DBuf<Frontier> &fr, uint64_t nF, bool closed, b
   DBuf<Hit> hits(H, s_);
   DBuf<CigarSlice> slices;
   if (p_.store_cigar) slices.alloc(H, s_);
-  CUDA_CHECK(cudaMemsetAsync(d_counters_.get(), 0, 16, s_));
+  CUDA_CHECK(cudaMemsetAsync(d_counters_.get(), 0, 24, s_));
   LiftParams lp;
   lp.clip = clip ? 1 : 0;
   lp.min_output_len = p_.min_output_length;
@@ -352,13 +352,19 @@ void Runner::stab_and_lift(const DBuf<Frontier> &fr, uint64_t nF, bool closed, b
   // (src/subset_filter.rs:84-100), so it is folded into the kernel in every mode
   lp.subset = p_.subset_mask ? d_subset_.get() : nullptr;
   lp.row_target = d_row_target_.get();
-  LAUNCH(k_liftover, grid_warps(H, 256, 8), 256, s_, ix_, fr.get(), tasks.get(), H, lp, hits.get(), slices.get(),
-         d_counters_.get());
+  // endpoint kernel when neither the clipped CIGAR nor the identity is needed
+  const bool ends = !p_.store_cigar && !lp.use_identity && !getenv("IMPGX_FULL_SCAN");
+  if (ends)
+    LAUNCH(k_liftover_ends, grid_warps((H + 3) / 4, 256, 8), 256, s_, ix_, fr.get(), tasks.get(), H, lp, hits.get(),
+           d_counters_.get());
+  else
+    LAUNCH(k_liftover, grid_warps(H, 256, 8), 256, s_, ix_, fr.get(), tasks.get(), H, lp, hits.get(), slices.get(),
+           d_counters_.get());
   CUDA_CHECK(cudaEventRecord(e2, s_));
-  unsigned long long cnt[2];
-  CUDA_CHECK(cudaMemcpyAsync(cnt, d_counters_.get(), 16, cudaMemcpyDeviceToHost, s_));
+  unsigned long long cnt[3];
+  CUDA_CHECK(cudaMemcpyAsync(cnt, d_counters_.get(), 24, cudaMemcpyDeviceToHost, s_));
   CUDA_CHECK(cudaStreamSynchronize(s_));
-  ctx.d2h_bytes += 16;
+  ctx.d2h_bytes += 24;
   float ms = 0;
   cudaEventElapsedTime(&ms, e0, e1);
   ctx.stab_ms += ms;
@@ -369,7 +375,8 @@ void Runner::stab_and_lift(const DBuf<Frontier> &fr, uint64_t nF, bool closed, b
   ctx.lift_runs += cnt[0];
   // algorithmic bytes of the liftover: task 8 + range 16 +
   // entry 32 + 2 checkpoints 16 + runs 4/run + hit 32 (+ slice 16)
-  ctx.lift_bytes += H * (8 + 16 + 32 + 16 + 32 + (p_.store_cigar ? 16 : 0)) + cnt[0] * 4;
+  if (ends) ctx.lift_bytes += H * (8 + 16 + 32 + 32) + cnt[2] * 8 + cnt[0] * 4;
+  else ctx.lift_bytes += H * (8 + 16 + 32 + 16 + 32 + (p_.store_cigar ? 16 : 0)) + cnt[0] * 4;
   const uint64_t n_ok = cnt[1];
   lvl.n = n_ok;
   if (n_ok == 0) return;
@@ -610,7 +617,7 @@ void Runner::run(const impgx_range *d_ranges, uint32_t n_rows, bool bed, BatchOu
   REQUIRE(p_.mode == IMPGX_MODE_QUERY || p_.mode == IMPGX_MODE_BFS, IMPGX_E_UNSUPPORTED,
           "transitive DFS is not implemented on the device yet (use BFS)");
   REQUIRE(!(bed && p_.store_cigar), IMPGX_E_INVALID, "BED output carries no CIGAR (src/main.rs:7447)");
-  d_counters_.alloc(2, s_);
+  d_counters_.alloc(3, s_);
   // validation (perform_query bounds checks)
   {
     DBuf<int> bad(1, s_);
@@ -1039,8 +1046,14 @@ void project_batch(int device, size_t n, const int32_t *req_start, const int32_t
   LiftParams lp{};
   lp.clip = 0;
   lp.min_output_len = -1;
-  LAUNCH(k_liftover, grid_warps(n), 256, s, ix, d_fr.get(), d_tasks.get(), (uint64_t)n, lp, d_hits.get(), d_slices.get(),
-         (unsigned long long *)nullptr);
+  if (!out_runs) {
+    CUDA_CHECK(cudaMemsetAsync(d_slices.get(), 0, n * sizeof(CigarSlice), s));
+    LAUNCH(k_liftover_ends, grid_warps((n + 3) / 4), 256, s, ix, d_fr.get(), d_tasks.get(), (uint64_t)n, lp, d_hits.get(),
+           (unsigned long long *)nullptr);
+  } else {
+    LAUNCH(k_liftover, grid_warps(n), 256, s, ix, d_fr.get(), d_tasks.get(), (uint64_t)n, lp, d_hits.get(),
+           d_slices.get(), (unsigned long long *)nullptr);
+  }
   std::vector<Hit> hits(n);
   std::vector<CigarSlice> slices(n);
   CUDA_CHECK(cudaMemcpyAsync(hits.data(), d_hits.get(), n * sizeof(Hit), cudaMemcpyDeviceToHost, s));

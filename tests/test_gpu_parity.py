@@ -49,6 +49,12 @@ def test_liftover_kernel_kats():
         if exp[3] is not None:
             assert (g[3], g[4]) == (exp[3], exp[4])
     assert got[-1] is None
+    got = ix.project_batch(reqs, np.concatenate(recs), np.concatenate(runs), np.array(offs, np.uint64), want_cigar=False)
+    for (req, r, cg, exp), g in zip(LIFTOVER_KATS, got):
+        assert g is not None and (g[0], g[1]) == (exp[0], exp[1])
+        if exp[3] is not None:
+            assert (g[3], g[4]) == (exp[3], exp[4])
+    assert got[-1] is None
 
 
 def random_cigar(rng, n_ops, zero_len=False):
@@ -97,6 +103,15 @@ def test_liftover_kernel_random_vs_oracle(seed, n_ops, zero_len):
             assert g is not None, (i, reqs[i], e)
             assert (g[0], g[1], g[3], g[4]) == (e[0], e[1], e[3], e[4]), (i, reqs[i])
             assert list(g[2]) == list(e[2]), (i, reqs[i], O.cigar_str(g[2]), O.cigar_str(e[2]))
+    # the endpoint kernel (8 lanes per hit, boundary blocks only) must agree on the coordinates
+    got = ix.project_batch(reqs, np.concatenate(recs), np.concatenate(runs), np.array(offs, np.uint64),
+                           want_cigar=False)
+    for i, (g, e) in enumerate(zip(got, expect)):
+        if e is None:
+            assert g is None, ("ends", i, reqs[i], g)
+        else:
+            assert g is not None, ("ends", i, reqs[i], e)
+            assert (g[0], g[1], g[3], g[4]) == (e[0], e[1], e[3], e[4]), ("ends", i, reqs[i])
 
 
 # ---------------------------------------------------------------- whole path
