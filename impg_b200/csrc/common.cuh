@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <stdexcept>
@@ -100,34 +101,132 @@ struct DevIndexView {
 };
 
 // ----------------------------------------------------------------- buffers
-// Stream-ordered device buffer (cudaMallocAsync pool).
+// Device scratch arena. The query pipeline allocates hundreds of temporaries
+// per batch; cudaMallocAsync showed sporadic 100-800 ms stalls when the pool
+// remapped memory for multi-GB requests, so scratch comes from slabs owned by
+// the index: bump allocation with stack discipline (a freed block is reclaimed
+// as soon as everything above it is freed — C++ scopes make that the common
+// case), whole-arena reset at the end of a batch. All work of a batch is
+// issued on one stream, so reuse in program order is safe.
+class Arena {
+ public:
+  Arena() {}
+  Arena(const Arena &) = delete;
+  Arena &operator=(const Arena &) = delete;
+  ~Arena() {
+    for (auto &sl : slabs_) cudaFree(sl.base);
+  }
+  void *alloc(size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes == 0) bytes = 256;
+    if (slabs_.empty() || top_ + bytes > slabs_.back().size) grow(bytes);
+    Block b{slabs_.size() - 1, top_, bytes, false};
+    blocks_.push_back(b);
+    top_ += bytes;
+    used_ += bytes;
+    if (used_ > peak_) peak_ = used_;
+    return slabs_.back().base + b.off;
+  }
+  void free(void *p) {
+    if (!p) return;
+    for (size_t i = blocks_.size(); i-- > 0;) {
+      Block &b = blocks_[i];
+      if (slabs_[b.slab].base + b.off == (char *)p) {
+        b.freed = true;
+        used_ -= b.size;
+        break;
+      }
+    }
+    while (!blocks_.empty() && blocks_.back().freed) {
+      const Block &b = blocks_.back();
+      if (b.slab == slabs_.size() - 1) top_ = b.off;
+      blocks_.pop_back();
+    }
+  }
+  // Call with the stream idle. Consolidates the slabs so the next batch of the
+  // same shape needs no cudaMalloc.
+  void reset() {
+    blocks_.clear();
+    top_ = 0;
+    used_ = 0;
+    if (slabs_.size() > 1) {
+      size_t total = 0;
+      for (auto &sl : slabs_) {
+        total += sl.size;
+        cudaFree(sl.base);
+      }
+      slabs_.clear();
+      char *p = nullptr;
+      if (cudaMalloc((void **)&p, total) == cudaSuccess) slabs_.push_back(Slab{p, total});
+      else cudaGetLastError();
+    }
+  }
+  size_t capacity() const {
+    size_t t = 0;
+    for (auto &sl : slabs_) t += sl.size;
+    return t;
+  }
+  size_t peak() const { return peak_; }
+
+ private:
+  struct Slab {
+    char *base;
+    size_t size;
+  };
+  struct Block {
+    size_t slab, off, size;
+    bool freed;
+  };
+  std::vector<Slab> slabs_;
+  std::vector<Block> blocks_;
+  size_t top_ = 0, used_ = 0, peak_ = 0;
+
+  void grow(size_t need) {
+    size_t sz = std::max<size_t>(need, std::max<size_t>(capacity(), (size_t)256 << 20));
+    char *p = nullptr;
+    cudaError_t e = cudaMalloc((void **)&p, sz);
+    if (e != cudaSuccess && sz > need) {
+      cudaGetLastError();
+      sz = need;
+      e = cudaMalloc((void **)&p, sz);
+    }
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      throw Error(IMPGX_E_NOMEM, "device scratch allocation of " + std::to_string(sz) + " bytes failed");
+    }
+    slabs_.push_back(Slab{p, sz});
+    top_ = 0;
+  }
+};
+
+// Typed view of an arena block; frees on scope exit.
 template <class T>
 struct DBuf {
   T *p = nullptr;
   size_t n = 0;
-  cudaStream_t s = nullptr;
+  Arena *a = nullptr;
   DBuf() {}
-  DBuf(size_t count, cudaStream_t stream) { alloc(count, stream); }
+  DBuf(size_t count, Arena &arena) { alloc(count, arena); }
   DBuf(const DBuf &) = delete;
   DBuf &operator=(const DBuf &) = delete;
-  DBuf(DBuf &&o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; o.n = 0; }
+  DBuf(DBuf &&o) noexcept : p(o.p), n(o.n), a(o.a) { o.p = nullptr; o.n = 0; }
   DBuf &operator=(DBuf &&o) noexcept {
     if (this != &o) {
       release();
-      p = o.p; n = o.n; s = o.s;
+      p = o.p; n = o.n; a = o.a;
       o.p = nullptr; o.n = 0;
     }
     return *this;
   }
   ~DBuf() { release(); }
-  void alloc(size_t count, cudaStream_t stream) {
+  void alloc(size_t count, Arena &arena) {
     release();
-    s = stream;
+    a = &arena;
     n = count;
-    if (count) CUDA_CHECK(cudaMallocAsync((void **)&p, count * sizeof(T), stream));
+    p = (T *)arena.alloc(std::max<size_t>(count, 1) * sizeof(T));
   }
   void release() {
-    if (p) cudaFreeAsync(p, s);
+    if (p && a) a->free(p);
     p = nullptr;
     n = 0;
   }

@@ -56,20 +56,17 @@ static unsigned grid_warps(uint64_t n, unsigned threads = 256, unsigned per_sm =
 }
 
 // ----------------------------------------------------------------- CUB glue
+// CUB temp storage: allocated per call from the arena (stack discipline frees it at once)
 struct Scratch {
-  DBuf<uint8_t> buf;
-  void *ensure(size_t bytes, cudaStream_t s) {
-    if (buf.n < bytes) buf.alloc(bytes + bytes / 4 + 256, s);
-    return buf.get();
-  }
+  Arena *a = nullptr;
 };
 
 // in-place exclusive sum over n+1 elements: a[n] becomes the total
 static void exclusive_scan_u64(uint64_t *a, uint64_t n_plus_1, Scratch &sc, cudaStream_t s) {
   size_t bytes = 0;
   CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, a, a, n_plus_1, s));
-  void *tmp = sc.ensure(bytes, s);
-  CUDA_CHECK(cub::DeviceScan::ExclusiveSum(tmp, bytes, a, a, n_plus_1, s));
+  DBuf<uint8_t> tmp(bytes, *sc.a);
+  CUDA_CHECK(cub::DeviceScan::ExclusiveSum(tmp.get(), bytes, a, a, n_plus_1, s));
 }
 
 static int bits_for(uint64_t max_value) {
@@ -82,17 +79,21 @@ template <class K>
 static void sort_pairs(DBuf<K> &keys, DBuf<uint32_t> &vals, uint64_t n, int begin_bit, int end_bit, Scratch &sc,
                        cudaStream_t s, Ctx &ctx) {
   if (n == 0) return;
-  DBuf<K> k2(n, s);
-  DBuf<uint32_t> v2(n, s);
+  DBuf<K> k2(n, *sc.a);
+  DBuf<uint32_t> v2(n, *sc.a);
   cub::DoubleBuffer<K> dk(keys.get(), k2.get());
   cub::DoubleBuffer<uint32_t> dv(vals.get(), v2.get());
   size_t bytes = 0;
   CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, dk, dv, n, begin_bit, end_bit, s));
-  void *tmp = sc.ensure(bytes, s);
-  CUDA_CHECK(cub::DeviceRadixSort::SortPairs(tmp, bytes, dk, dv, n, begin_bit, end_bit, s));
+  {
+    DBuf<uint8_t> tmp(bytes, *sc.a);
+    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(tmp.get(), bytes, dk, dv, n, begin_bit, end_bit, s));
+  }
   ctx.launches += 2 + (uint64_t)((end_bit - begin_bit + 7) / 8);
-  if (dk.Current() != keys.get()) std::swap(keys, k2);
-  if (dv.Current() != vals.get()) std::swap(vals, v2);
+  // sorted data may sit in the alternate buffers: copy back so the caller's
+  // (older, lower) blocks stay and the temporaries above them can be popped
+  if (dk.Current() != keys.get()) CUDA_CHECK(cudaMemcpyAsync(keys.get(), k2.get(), n * sizeof(K), cudaMemcpyDeviceToDevice, s));
+  if (dv.Current() != vals.get()) CUDA_CHECK(cudaMemcpyAsync(vals.get(), v2.get(), n * 4, cudaMemcpyDeviceToDevice, s));
 }
 
 static uint64_t read_u64(const uint64_t *d, cudaStream_t s, Ctx &ctx) {
@@ -277,7 +278,10 @@ struct BatchOut {
 
 class Runner {
  public:
-  Runner(impgx_index *idx, const impgx_params &p, cudaStream_t s) : idx_(idx), p_(p), s_(s), ix_(idx->view()) {}
+  Runner(impgx_index *idx, const impgx_params &p, cudaStream_t s)
+      : idx_(idx), p_(p), s_(s), ix_(idx->view()), ar_(idx->arena) {
+    sc_.a = &ar_;
+  }
 
   Ctx ctx;
 
@@ -290,6 +294,7 @@ class Runner {
   impgx_params p_;
   cudaStream_t s_;
   DevIndexView ix_;
+  Arena &ar_;
   Scratch sc_;
   DBuf<uint8_t> d_subset_;
   DBuf<uint32_t> d_row_target_;
@@ -316,9 +321,9 @@ void Runner::stab_and_lift(const DBuf<Frontier> &fr, uint64_t nF, bool closed, b
   CUDA_CHECK(cudaEventCreate(&e1));
   CUDA_CHECK(cudaEventCreate(&e2));
   CUDA_CHECK(cudaEventRecord(e0, s_));
-  DBuf<Window> win(nF, s_);
-  DBuf<uint32_t> counts(nF, s_);
-  DBuf<uint64_t> offs(nF + 1, s_);
+  DBuf<Window> win(nF, ar_);
+  DBuf<uint32_t> counts(nF, ar_);
+  DBuf<uint64_t> offs(nF + 1, ar_);
   if (closed) LAUNCH(k_stab_count<true>, grid_warps(nF), 256, s_, ix_, fr.get(), nF, win.get(), counts.get());
   else LAUNCH(k_stab_count<false>, grid_warps(nF), 256, s_, ix_, fr.get(), nF, win.get(), counts.get());
   CUDA_CHECK(cudaMemsetAsync(offs.get() + nF, 0, 8, s_));
@@ -333,15 +338,21 @@ void Runner::stab_and_lift(const DBuf<Frontier> &fr, uint64_t nF, bool closed, b
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     return;
   }
-  DBuf<LiftTask> tasks(H, s_);
+  // outputs that survive this function go below the temporaries (stack-discipline arena)
+  lvl.hits.alloc(H, ar_);
+  if (p_.store_cigar) {
+    lvl.entry.alloc(H, ar_);
+    lvl.slices.alloc(H, ar_);
+  }
+  DBuf<LiftTask> tasks(H, ar_);
   if (closed) LAUNCH(k_stab_fill<true>, grid_warps(nF), 256, s_, ix_, fr.get(), nF, win.get(), offs.get(), tasks.get());
   else LAUNCH(k_stab_fill<false>, grid_warps(nF), 256, s_, ix_, fr.get(), nF, win.get(), offs.get(), tasks.get());
   CUDA_CHECK(cudaEventRecord(e1, s_));
   wt.reset(new WallTimer(ctx.w_lift));
 
-  DBuf<Hit> hits(H, s_);
+  DBuf<Hit> hits(H, ar_);
   DBuf<CigarSlice> slices;
-  if (p_.store_cigar) slices.alloc(H, s_);
+  if (p_.store_cigar) slices.alloc(H, ar_);
   CUDA_CHECK(cudaMemsetAsync(d_counters_.get(), 0, 24, s_));
   LiftParams lp;
   lp.clip = clip ? 1 : 0;
@@ -387,15 +398,12 @@ void Runner::stab_and_lift(const DBuf<Frontier> &fr, uint64_t nF, bool closed, b
     // inside the merge; here only compaction would be needed. Kept simple:
     // fall through to the ordered path (a later round replaces this by binning).
   }
-  DBuf<uint64_t> keys(H, s_);
-  DBuf<uint32_t> perm(H, s_);
+  DBuf<uint64_t> keys(H, ar_);
+  DBuf<uint32_t> perm(H, ar_);
   LAUNCH(k_hit_order_keys, grid_threads(H), 256, s_, hits.get(), tasks.get(), H, (uint32_t)nF, keys.get(), perm.get());
   sort_pairs(keys, perm, H, 0, 32 + bits_for(nF), sc_, s_, ctx);
-  lvl.hits.alloc(n_ok, s_);
   LAUNCH(k_gather<Hit>, grid_threads(n_ok), 256, s_, hits.get(), perm.get(), n_ok, lvl.hits.get());
   if (p_.store_cigar) {
-    lvl.entry.alloc(n_ok, s_);
-    lvl.slices.alloc(n_ok, s_);
     LAUNCH(k_gather_entry, grid_threads(n_ok), 256, s_, tasks.get(), perm.get(), n_ok, lvl.entry.get());
     LAUNCH(k_gather<CigarSlice>, grid_threads(n_ok), 256, s_, slices.get(), perm.get(), n_ok, lvl.slices.get());
   }
@@ -412,14 +420,14 @@ void Runner::fold(const LevelHits &lvl, uint32_t n_rows, Visited &V, DBuf<Fronti
   CUDA_CHECK(cudaEventCreate(&e1));
   CUDA_CHECK(cudaEventRecord(e0, s_));
   // group by (row, q_id), stable w.r.t. the reference's hit order
-  DBuf<uint64_t> keys(n, s_);
-  DBuf<uint32_t> perm(n, s_);
+  DBuf<uint64_t> keys(n, ar_);
+  DBuf<uint32_t> perm(n, ar_);
   LAUNCH(k_fold_keys, grid_threads(n), 256, s_, lvl.hits.get(), n, n_rows, keys.get(), perm.get());
   sort_pairs(keys, perm, n, 0, 32 + bits_for(n_rows), sc_, s_, ctx);
-  DBuf<Hit> sorted(n, s_);
+  DBuf<Hit> sorted(n, ar_);
   LAUNCH(k_gather<Hit>, grid_threads(n), 256, s_, lvl.hits.get(), perm.get(), n, sorted.get());
 
-  DBuf<uint64_t> head(n + 1, s_), head_scan(n + 1, s_), n_inc(1, s_);
+  DBuf<uint64_t> head(n + 1, ar_), head_scan(n + 1, ar_), n_inc(1, ar_);
   CUDA_CHECK(cudaMemcpyAsync(n_inc.get(), &n, 8, cudaMemcpyHostToDevice, s_));
   CUDA_CHECK(cudaMemsetAsync(head.get() + n, 0, 8, s_));
   const uint64_t limit = (uint64_t)n_rows << 32;
@@ -432,8 +440,8 @@ void Runner::fold(const LevelHits &lvl, uint32_t n_rows, Visited &V, DBuf<Fronti
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return;
   }
-  DBuf<FoldGroup> groups(G, s_);
-  DBuf<uint64_t> list_off(G + 1, s_), piece_off(G + 1, s_);
+  DBuf<FoldGroup> groups(G, ar_);
+  DBuf<uint64_t> list_off(G + 1, ar_), piece_off(G + 1, ar_);
   CUDA_CHECK(cudaMemsetAsync(list_off.get() + G, 0, 8, s_));
   CUDA_CHECK(cudaMemsetAsync(piece_off.get() + G, 0, 8, s_));
   LAUNCH(k_make_groups, grid_threads(n), 256, s_, keys.get(), head.get(), head_scan.get(), n, n_inc.get(),
@@ -445,15 +453,15 @@ void Runner::fold(const LevelHits &lvl, uint32_t n_rows, Visited &V, DBuf<Fronti
   const uint64_t piece_total = read_u64(piece_off.get() + G, s_, ctx);
   LAUNCH(k_set_group_offsets, grid_threads(G), 256, s_, groups.get(), G, list_off.get(), piece_off.get());
 
-  DBuf<int2> lists(list_total, s_);
-  DBuf<Frontier> pieces(piece_total, s_);
-  DBuf<uint32_t> list_len(G, s_), piece_cnt(G, s_);
+  DBuf<int2> lists(list_total, ar_);
+  DBuf<Frontier> pieces(piece_total, ar_);
+  DBuf<uint32_t> list_len(G, ar_), piece_cnt(G, ar_);
   LAUNCH(k_fold, grid_threads(G, 128, 16), 128, s_, groups.get(), G, sorted.get(), V.start.get(), V.end.get(),
          ix_.seq_len, p_.min_distance_between_ranges, p_.min_transitive_len, lists.get(), list_len.get(), pieces.get(),
          piece_cnt.get());
 
   // ---- new visited set = untouched old entries + the groups' lists, re-sorted
-  DBuf<uint64_t> lo(G + 1, s_), po(G + 1, s_);
+  DBuf<uint64_t> lo(G + 1, ar_), po(G + 1, ar_);
   CUDA_CHECK(cudaMemsetAsync(lo.get() + G, 0, 8, s_));
   CUDA_CHECK(cudaMemsetAsync(po.get() + G, 0, 8, s_));
   LAUNCH(k_u32_to_u64, grid_threads(G), 256, s_, list_len.get(), G, lo.get());
@@ -464,7 +472,7 @@ void Runner::fold(const LevelHits &lvl, uint32_t n_rows, Visited &V, DBuf<Fronti
   const uint64_t new_lists = read_u64(lo.get() + G, s_, ctx);
   const uint64_t n_pieces = read_u64(po.get() + G, s_, ctx);
 
-  DBuf<uint64_t> keep(V.n + 1, s_), keep_scan(V.n + 1, s_);
+  DBuf<uint64_t> keep(V.n + 1, ar_), keep_scan(V.n + 1, ar_);
   CUDA_CHECK(cudaMemsetAsync(keep.get() + V.n, 0, 8, s_));
   if (V.n) LAUNCH(k_visited_keep_flags, grid_threads(V.n), 256, s_, V.keys.get(), V.n, groups.get(), G, keep.get());
   CUDA_CHECK(cudaMemcpyAsync(keep_scan.get(), keep.get(), (V.n + 1) * 8, cudaMemcpyDeviceToDevice, s_));
@@ -473,9 +481,9 @@ void Runner::fold(const LevelHits &lvl, uint32_t n_rows, Visited &V, DBuf<Fronti
   const uint64_t kept = read_u64(keep_scan.get() + V.n, s_, ctx);
   const uint64_t vn = kept + new_lists;
   Visited nv;
-  nv.keys.alloc(vn, s_);
-  nv.start.alloc(vn, s_);
-  nv.end.alloc(vn, s_);
+  nv.keys.alloc(vn, ar_);
+  nv.start.alloc(vn, ar_);
+  nv.end.alloc(vn, ar_);
   nv.n = vn;
   if (V.n)
     LAUNCH(k_visited_copy_kept, grid_threads(V.n), 256, s_, V.keys.get(), V.start.get(), V.end.get(), V.n, keep.get(),
@@ -484,14 +492,14 @@ void Runner::fold(const LevelHits &lvl, uint32_t n_rows, Visited &V, DBuf<Fronti
          nv.keys.get(), nv.start.get(), nv.end.get());
   if (vn) {
     // sort by (key, start): LSD = start first, then key (stable)
-    DBuf<uint32_t> sk(vn, s_), sp(vn, s_);
+    DBuf<uint32_t> sk(vn, ar_), sp(vn, ar_);
     LAUNCH(k_iota_u32, grid_threads(vn), 256, s_, sp.get(), vn);
     LAUNCH(k_start_keys_i32, grid_threads(vn), 256, s_, nv.start.get(), vn, sk.get());
     sort_pairs(sk, sp, vn, 0, 32, sc_, s_, ctx);
-    DBuf<uint64_t> k2(vn, s_);
+    DBuf<uint64_t> k2(vn, ar_);
     LAUNCH(k_gather<uint64_t>, grid_threads(vn), 256, s_, nv.keys.get(), sp.get(), vn, k2.get());
     sort_pairs(k2, sp, vn, 0, 32 + bits_for(n_rows), sc_, s_, ctx);
-    DBuf<int32_t> s2(vn, s_), e2(vn, s_);
+    DBuf<int32_t> s2(vn, ar_), e2(vn, ar_);
     LAUNCH(k_gather<int32_t>, grid_threads(vn), 256, s_, nv.start.get(), sp.get(), vn, s2.get());
     LAUNCH(k_gather<int32_t>, grid_threads(vn), 256, s_, nv.end.get(), sp.get(), vn, e2.get());
     nv.keys = std::move(k2);
@@ -502,25 +510,25 @@ void Runner::fold(const LevelHits &lvl, uint32_t n_rows, Visited &V, DBuf<Fronti
 
   // ---- next frontier: pieces sorted by (row, id, start), touching ones merged
   if (n_pieces) {
-    DBuf<Frontier> pc(n_pieces, s_);
+    DBuf<Frontier> pc(n_pieces, ar_);
     LAUNCH(k_compact_pieces, grid_threads(G), 256, s_, groups.get(), G, pieces.get(), piece_cnt.get(), po.get(),
            pc.get());
-    DBuf<uint32_t> sk(n_pieces, s_), sp(n_pieces, s_);
+    DBuf<uint32_t> sk(n_pieces, ar_), sp(n_pieces, ar_);
     LAUNCH(k_piece_start_keys, grid_threads(n_pieces), 256, s_, pc.get(), n_pieces, sk.get(), sp.get());
     sort_pairs(sk, sp, n_pieces, 0, 32, sc_, s_, ctx);
-    DBuf<uint64_t> k2(n_pieces, s_);
+    DBuf<uint64_t> k2(n_pieces, ar_);
     LAUNCH(k_piece_seq_keys, grid_threads(n_pieces), 256, s_, pc.get(), sp.get(), n_pieces, k2.get());
     sort_pairs(k2, sp, n_pieces, 0, 32 + bits_for(n_rows), sc_, s_, ctx);
-    DBuf<Frontier> ps(n_pieces, s_);
+    DBuf<Frontier> ps(n_pieces, ar_);
     LAUNCH(k_gather<Frontier>, grid_threads(n_pieces), 256, s_, pc.get(), sp.get(), n_pieces, ps.get());
-    DBuf<uint64_t> fh(n_pieces + 1, s_), fs(n_pieces + 1, s_);
+    DBuf<uint64_t> fh(n_pieces + 1, ar_), fs(n_pieces + 1, ar_);
     CUDA_CHECK(cudaMemsetAsync(fh.get() + n_pieces, 0, 8, s_));
     LAUNCH(k_frontier_heads, grid_threads(n_pieces), 256, s_, ps.get(), n_pieces, fh.get());
     CUDA_CHECK(cudaMemcpyAsync(fs.get(), fh.get(), (n_pieces + 1) * 8, cudaMemcpyDeviceToDevice, s_));
     exclusive_scan_u64(fs.get(), n_pieces + 1, sc_, s_);
     ctx.launches += 2;
     n_next = read_u64(fs.get() + n_pieces, s_, ctx);
-    next.alloc(n_next, s_);
+    next.alloc(n_next, ar_);
     LAUNCH(k_frontier_merge, grid_threads(n_pieces), 256, s_, ps.get(), n_pieces, fh.get(), fs.get(), next.get());
   }
   CUDA_CHECK(cudaEventRecord(e1, s_));
@@ -536,7 +544,7 @@ void Runner::assemble(const impgx_range *d_ranges, uint32_t n_rows, std::vector<
                       BatchOut &out) {
   WallTimer wt(ctx.w_assemble);
   const int32_t min_out = p_.min_output_length;
-  DBuf<uint32_t> seed_cnt(n_rows, s_), total_cnt(n_rows, s_);
+  DBuf<uint32_t> seed_cnt(n_rows, ar_), total_cnt(n_rows, ar_);
   // Impg::query's caller filters every result incl. the self interval by
   // min_output_length (src/main.rs:11686-11691); BFS never filters the seed.
   LAUNCH(k_seed_counts, grid_threads(n_rows), 256, s_, d_ranges, n_rows, min_out, query_mode ? 1 : 0, seed_cnt.get());
@@ -549,33 +557,33 @@ void Runner::assemble(const impgx_range *d_ranges, uint32_t n_rows, std::vector<
   std::vector<PerLevel> pl(levels.size());
   for (size_t l = 0; l < levels.size(); l++) {
     const uint64_t n = levels[l].n;
-    pl[l].row_cnt.alloc(n_rows, s_);
+    pl[l].row_cnt.alloc(n_rows, ar_);
     CUDA_CHECK(cudaMemsetAsync(pl[l].row_cnt.get(), 0, n_rows * 4, s_));
     if (n == 0) continue;
-    pl[l].pass.alloc(n + 1, s_);
-    pl[l].pass_scan.alloc(n + 1, s_);
+    pl[l].pass.alloc(n + 1, ar_);
+    pl[l].pass_scan.alloc(n + 1, ar_);
     CUDA_CHECK(cudaMemsetAsync(pl[l].pass.get() + n, 0, 8, s_));
     LAUNCH(k_level_pass, grid_threads(n), 256, s_, levels[l].hits.get(), n, min_out, pl[l].pass.get(),
            pl[l].row_cnt.get());
     CUDA_CHECK(cudaMemcpyAsync(pl[l].pass_scan.get(), pl[l].pass.get(), (n + 1) * 8, cudaMemcpyDeviceToDevice, s_));
     exclusive_scan_u64(pl[l].pass_scan.get(), n + 1, sc_, s_);
-    pl[l].row_start.alloc(n_rows + 1, s_);
+    pl[l].row_start.alloc(n_rows + 1, ar_);
     CUDA_CHECK(cudaMemsetAsync(pl[l].row_start.get() + n_rows, 0, 8, s_));
     LAUNCH(k_u32_to_u64, grid_threads(n_rows), 256, s_, pl[l].row_cnt.get(), n_rows, pl[l].row_start.get());
     exclusive_scan_u64(pl[l].row_start.get(), n_rows + 1, sc_, s_);
     LAUNCH(k_add_u32, grid_threads(n_rows), 256, s_, total_cnt.get(), pl[l].row_cnt.get(), n_rows);
     ctx.launches += 4;
   }
-  out.row_off.alloc(n_rows + 1, s_);
+  out.row_off.alloc(n_rows + 1, ar_);
   CUDA_CHECK(cudaMemsetAsync(out.row_off.get() + n_rows, 0, 8, s_));
   LAUNCH(k_u32_to_u64, grid_threads(n_rows), 256, s_, total_cnt.get(), n_rows, out.row_off.get());
   exclusive_scan_u64(out.row_off.get(), n_rows + 1, sc_, s_);
   ctx.launches += 2;
   const uint64_t R = read_u64(out.row_off.get() + n_rows, s_, ctx);
   out.n_results = R;
-  out.q_id.alloc(R, s_); out.t_id.alloc(R, s_);
-  out.q_first.alloc(R, s_); out.q_last.alloc(R, s_);
-  out.t_first.alloc(R, s_); out.t_last.alloc(R, s_);
+  out.q_id.alloc(R, ar_); out.t_id.alloc(R, ar_);
+  out.q_first.alloc(R, ar_); out.q_last.alloc(R, ar_);
+  out.t_first.alloc(R, ar_); out.t_last.alloc(R, ar_);
   OutCols oc;
   oc.q_id = out.q_id.get(); oc.q_first = out.q_first.get(); oc.q_last = out.q_last.get();
   oc.t_id = out.t_id.get(); oc.t_first = out.t_first.get(); oc.t_last = out.t_last.get();
@@ -583,16 +591,16 @@ void Runner::assemble(const impgx_range *d_ranges, uint32_t n_rows, std::vector<
   DBuf<CigarSlice> src_slice;
   oc.cig_len = nullptr; oc.src_entry = nullptr; oc.src_slice = nullptr;
   if (p_.store_cigar) {
-    out.cig_off.alloc(R + 1, s_);
+    out.cig_off.alloc(R + 1, ar_);
     CUDA_CHECK(cudaMemsetAsync(out.cig_off.get(), 0, (R + 1) * 8, s_));
-    src_entry.alloc(R, s_);
-    src_slice.alloc(R, s_);
+    src_entry.alloc(R, ar_);
+    src_slice.alloc(R, ar_);
     oc.cig_len = out.cig_off.get();
     oc.src_entry = src_entry.get();
     oc.src_slice = src_slice.get();
   }
   LAUNCH(k_scatter_seed, grid_threads(n_rows), 256, s_, d_ranges, n_rows, seed_cnt.get(), out.row_off.get(), oc);
-  DBuf<uint32_t> base(n_rows, s_);
+  DBuf<uint32_t> base(n_rows, ar_);
   CUDA_CHECK(cudaMemcpyAsync(base.get(), seed_cnt.get(), n_rows * 4, cudaMemcpyDeviceToDevice, s_));
   for (size_t l = 0; l < levels.size(); l++) {
     const uint64_t n = levels[l].n;
@@ -607,7 +615,7 @@ void Runner::assemble(const impgx_range *d_ranges, uint32_t n_rows, std::vector<
     exclusive_scan_u64(out.cig_off.get(), R + 1, sc_, s_);
     ctx.launches += 2;
     out.n_cig = read_u64(out.cig_off.get() + R, s_, ctx);
-    out.cig.alloc(std::max<uint64_t>(out.n_cig, 1), s_);
+    out.cig.alloc(std::max<uint64_t>(out.n_cig, 1), ar_);
     if (R) LAUNCH(k_emit_cigar_results, grid_warps(R), 256, s_, ix_, oc, out.cig_off.get(), R, out.cig.get());
     CUDA_CHECK(cudaStreamSynchronize(s_));  // src_* are released on scope exit
   }
@@ -617,10 +625,10 @@ void Runner::run(const impgx_range *d_ranges, uint32_t n_rows, bool bed, BatchOu
   REQUIRE(p_.mode == IMPGX_MODE_QUERY || p_.mode == IMPGX_MODE_BFS, IMPGX_E_UNSUPPORTED,
           "transitive DFS is not implemented on the device yet (use BFS)");
   REQUIRE(!(bed && p_.store_cigar), IMPGX_E_INVALID, "BED output carries no CIGAR (src/main.rs:7447)");
-  d_counters_.alloc(3, s_);
+  d_counters_.alloc(3, ar_);
   // validation (perform_query bounds checks)
   {
-    DBuf<int> bad(1, s_);
+    DBuf<int> bad(1, ar_);
     CUDA_CHECK(cudaMemsetAsync(bad.get(), 0, 4, s_));
     LAUNCH(k_validate, grid_threads(n_rows), 256, s_, d_ranges, n_rows, ix_.seq_len, ix_.n_seqs, bad.get());
     int hb = 0;
@@ -631,14 +639,14 @@ void Runner::run(const impgx_range *d_ranges, uint32_t n_rows, bool bed, BatchOu
                 ": unknown target id, start >= end, negative start or end beyond the sequence length");
   }
   if (p_.subset_mask) {
-    d_subset_.alloc(ix_.n_seqs, s_);
+    d_subset_.alloc(ix_.n_seqs, ar_);
     CUDA_CHECK(cudaMemcpyAsync(d_subset_.get(), p_.subset_mask, ix_.n_seqs, cudaMemcpyHostToDevice, s_));
     ctx.h2d_bytes += ix_.n_seqs;
-    d_row_target_.alloc(n_rows, s_);
+    d_row_target_.alloc(n_rows, ar_);
     LAUNCH(k_row_targets, grid_threads(n_rows), 256, s_, d_ranges, n_rows, d_row_target_.get());
   }
 
-  DBuf<Frontier> fr(n_rows, s_);
+  DBuf<Frontier> fr(n_rows, ar_);
   LAUNCH(k_init_frontier, grid_threads(n_rows), 256, s_, d_ranges, n_rows, fr.get());
   uint64_t nF = n_rows;
   std::vector<LevelHits> levels;
@@ -651,14 +659,14 @@ void Runner::run(const impgx_range *d_ranges, uint32_t n_rows, bool bed, BatchOu
     // itself (bounds were validated), which is output and, if long enough,
     // becomes the level-0 frontier (src/impg.rs:2337-2373)
     Visited V;
-    V.keys.alloc(n_rows, s_);
-    V.start.alloc(n_rows, s_);
-    V.end.alloc(n_rows, s_);
+    V.keys.alloc(n_rows, ar_);
+    V.start.alloc(n_rows, ar_);
+    V.end.alloc(n_rows, ar_);
     V.n = n_rows;
     LAUNCH(k_seed_visited, grid_threads(n_rows), 256, s_, d_ranges, n_rows, V.keys.get(), V.start.get(), V.end.get());
     if (p_.min_transitive_len > 0) {
       // drop rows shorter than min_transitive_len from the frontier
-      DBuf<uint64_t> flag(nF + 1, s_), scan(nF + 1, s_);
+      DBuf<uint64_t> flag(nF + 1, ar_), scan(nF + 1, ar_);
       CUDA_CHECK(cudaMemsetAsync(flag.get() + nF, 0, 8, s_));
       LAUNCH(k_frontier_len_flags, grid_threads(nF), 256, s_, fr.get(), nF, p_.min_transitive_len, flag.get());
       CUDA_CHECK(cudaMemcpyAsync(scan.get(), flag.get(), (nF + 1) * 8, cudaMemcpyDeviceToDevice, s_));
@@ -666,7 +674,7 @@ void Runner::run(const impgx_range *d_ranges, uint32_t n_rows, bool bed, BatchOu
       ctx.launches += 2;
       uint64_t keep = read_u64(scan.get() + nF, s_, ctx);
       if (keep != nF) {
-        DBuf<Frontier> f2(keep, s_);
+        DBuf<Frontier> f2(keep, ar_);
         LAUNCH(k_frontier_compact, grid_threads(nF), 256, s_, fr.get(), nF, flag.get(), scan.get(), f2.get());
         fr = std::move(f2);
         nF = keep;
@@ -701,14 +709,14 @@ struct Groups {
 };
 
 static void build_groups(const uint64_t *keys, uint64_t n, Groups &g, Scratch &sc, cudaStream_t s, Ctx &ctx) {
-  DBuf<uint64_t> head(n + 1, s), scan(n + 1, s);
+  DBuf<uint64_t> head(n + 1, *sc.a), scan(n + 1, *sc.a);
   CUDA_CHECK(cudaMemsetAsync(head.get() + n, 0, 8, s));
   LAUNCH(k_heads_u64, grid_threads(n), 256, s, keys, n, head.get());
   CUDA_CHECK(cudaMemcpyAsync(scan.get(), head.get(), (n + 1) * 8, cudaMemcpyDeviceToDevice, s));
   exclusive_scan_u64(scan.get(), n + 1, sc, s);
   ctx.launches += 2;
   g.G = read_u64(scan.get() + n, s, ctx);
-  g.begins.alloc(g.G + 1, s);
+  g.begins.alloc(g.G + 1, *sc.a);
   LAUNCH(k_group_begins, grid_threads(n), 256, s, head.get(), scan.get(), n, g.begins.get());
   uint32_t n32 = (uint32_t)n;
   CUDA_CHECK(cudaMemcpyAsync(g.begins.get() + g.G, &n32, 4, cudaMemcpyHostToDevice, s));
@@ -724,14 +732,14 @@ void Runner::bed_merge(BatchOut &raw, uint32_t n_rows, BatchOut &out) {
   const uint64_t R = raw.n_results;
   const int32_t d = p_.merge_distance;
   const bool ms = p_.merge_strands != 0;
-  DBuf<uint32_t> row_cnt(n_rows, s_);
+  DBuf<uint32_t> row_cnt(n_rows, ar_);
   CUDA_CHECK(cudaMemsetAsync(row_cnt.get(), 0, (size_t)n_rows * 4, s_));
-  out.row_off.alloc(n_rows + 1, s_);
+  out.row_off.alloc(n_rows + 1, ar_);
   CUDA_CHECK(cudaMemsetAsync(out.row_off.get(), 0, ((size_t)n_rows + 1) * 8, s_));
   out.n_results = 0;
   if (R > 0) {
     REQUIRE(R < (1ull << 32), IMPGX_E_INVALID, "more than 2^32 results in one batch; lower IMPGX_ROWS_PER_BATCH");
-    DBuf<uint32_t> row(R, s_);
+    DBuf<uint32_t> row(R, ar_);
     LAUNCH(k_fill_rows, grid_threads(R), 256, s_, raw.row_off.get(), n_rows, R, row.get());
     ResCols rc{raw.q_id.get(), raw.q_first.get(), raw.q_last.get(), raw.t_id.get(), raw.t_first.get(), raw.t_last.get()};
     const int row_bits = bits_for(n_rows > 1 ? n_rows - 1 : 1);
@@ -741,17 +749,17 @@ void Runner::bed_merge(BatchOut &raw, uint32_t n_rows, BatchOut &out) {
       // ---- stage A
       const int seq_bits = bits_for(ix_.n_seqs > 1 ? ix_.n_seqs - 1 : 1);
       REQUIRE(row_bits + 2 * seq_bits + 1 <= 64, IMPGX_E_INVALID, "batch too large for the packed merge key");
-      DBuf<uint32_t> k1(R, s_), perm(R, s_);
+      DBuf<uint32_t> k1(R, ar_), perm(R, ar_);
       LAUNCH(k_m2d_key1, grid_threads(R), 256, s_, rc, R, k1.get(), perm.get());
       sort_pairs(k1, perm, R, 0, 32, sc_, s_, ctx);
-      DBuf<uint64_t> k2(R, s_);
+      DBuf<uint64_t> k2(R, ar_);
       LAUNCH(k_m2d_key2, grid_threads(R), 256, s_, rc, row.get(), perm.get(), R, seq_bits, k2.get());
       sort_pairs(k2, perm, R, 0, row_bits + 2 * seq_bits + 1, sc_, s_, ctx);
       Groups g;
       build_groups(k2.get(), R, g, sc_, s_, ctx);
-      DBuf<uint32_t> parent(R, s_);
-      DBuf<Box> box(R, s_);
-      DBuf<uint64_t> is_root(R + 1, s_), root_scan(R + 1, s_);
+      DBuf<uint32_t> parent(R, ar_);
+      DBuf<Box> box(R, ar_);
+      DBuf<uint64_t> is_root(R + 1, ar_), root_scan(R + 1, ar_);
       CUDA_CHECK(cudaMemsetAsync(is_root.get() + R, 0, 8, s_));
       LAUNCH(k_merge2d, grid_threads(g.G, 128, 16), 128, s_, rc, row.get(), perm.get(), g.begins.get(), g.G, (int64_t)d,
              parent.get(), box.get(), is_root.get());
@@ -759,46 +767,46 @@ void Runner::bed_merge(BatchOut &raw, uint32_t n_rows, BatchOut &out) {
       exclusive_scan_u64(root_scan.get(), R + 1, sc_, s_);
       ctx.launches += 2;
       nB = read_u64(root_scan.get() + R, s_, ctx);
-      DBuf<Box> cb(nB, s_);
-      DBuf<uint32_t> ok(nB, s_), ov(nB, s_);
+      DBuf<Box> cb(nB, ar_);
+      DBuf<uint32_t> ok(nB, ar_), ov(nB, ar_);
       LAUNCH(k_compact_boxes, grid_threads(R), 256, s_, box.get(), is_root.get(), root_scan.get(), R, cb.get(), ok.get(),
              ov.get());
       sort_pairs(ok, ov, nB, 0, bits_for(R), sc_, s_, ctx);
-      boxes.alloc(nB, s_);
+      boxes.alloc(nB, ar_);
       LAUNCH(k_gather<Box>, grid_threads(nB), 256, s_, cb.get(), ov.get(), nB, boxes.get());
     } else {
       nB = R;
-      boxes.alloc(nB, s_);
+      boxes.alloc(nB, ar_);
       LAUNCH(k_results_to_boxes, grid_threads(R), 256, s_, rc, row.get(), R, boxes.get());
     }
     OutCols oc;
     oc.cig_len = nullptr; oc.src_entry = nullptr; oc.src_slice = nullptr;
     auto alloc_out = [&](uint64_t n) {
       out.n_results = n;
-      out.q_id.alloc(n, s_); out.t_id.alloc(n, s_);
-      out.q_first.alloc(n, s_); out.q_last.alloc(n, s_);
-      out.t_first.alloc(n, s_); out.t_last.alloc(n, s_);
+      out.q_id.alloc(n, ar_); out.t_id.alloc(n, ar_);
+      out.q_first.alloc(n, ar_); out.q_last.alloc(n, ar_);
+      out.t_first.alloc(n, ar_); out.t_last.alloc(n, ar_);
       oc.q_id = out.q_id.get(); oc.q_first = out.q_first.get(); oc.q_last = out.q_last.get();
       oc.t_id = out.t_id.get(); oc.t_first = out.t_first.get(); oc.t_last = out.t_last.get();
     };
     if (d >= 0 || ms) {
       // ---- stage B
-      DBuf<uint64_t> k1(nB, s_);
-      DBuf<uint32_t> perm(nB, s_);
+      DBuf<uint64_t> k1(nB, ar_);
+      DBuf<uint32_t> perm(nB, ar_);
       LAUNCH(k_mq_key1, grid_threads(nB), 256, s_, boxes.get(), nB, k1.get(), perm.get());
       sort_pairs(k1, perm, nB, 0, 33, sc_, s_, ctx);
-      DBuf<uint64_t> k2(nB, s_);
+      DBuf<uint64_t> k2(nB, ar_);
       LAUNCH(k_mq_key2, grid_threads(nB), 256, s_, boxes.get(), perm.get(), nB, k2.get());
       sort_pairs(k2, perm, nB, 0, 32 + row_bits, sc_, s_, ctx);
-      DBuf<Box> sorted(nB, s_);
+      DBuf<Box> sorted(nB, ar_);
       LAUNCH(k_gather<Box>, grid_threads(nB), 256, s_, boxes.get(), perm.get(), nB, sorted.get());
       Groups g;
       build_groups(k2.get(), nB, g, sc_, s_, ctx);
-      DBuf<Box> swept(nB, s_);
-      DBuf<uint32_t> cnt(g.G, s_);
+      DBuf<Box> swept(nB, ar_);
+      DBuf<uint32_t> cnt(g.G, ar_);
       LAUNCH(k_sweep, grid_threads(g.G, 128, 16), 128, s_, sorted.get(), g.begins.get(), g.G, d, ms ? 1 : 0, swept.get(),
              cnt.get());
-      DBuf<uint64_t> scan(g.G + 1, s_);
+      DBuf<uint64_t> scan(g.G + 1, ar_);
       CUDA_CHECK(cudaMemsetAsync(scan.get() + g.G, 0, 8, s_));
       LAUNCH(k_u32_to_u64, grid_threads(g.G), 256, s_, cnt.get(), g.G, scan.get());
       exclusive_scan_u64(scan.get(), g.G + 1, sc_, s_);
@@ -849,113 +857,156 @@ impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n
   res->n_rows = n;
   res->has_cigar = p.store_cigar != 0;
   res->row_off.assign(n + 1, 0);
+  if (res->has_cigar) res->cig_off.push_back(0);
+
+  // device-resident mode: per-chunk copies of the output columns (stream-ordered
+  // allocations, a few MB each) until they are concatenated at the end
+  struct DevChunk {
+    uint32_t *qid = nullptr, *tid = nullptr;
+    int32_t *qf = nullptr, *ql = nullptr, *tf = nullptr, *tl = nullptr;
+    uint64_t n = 0;
+  };
+  std::vector<DevChunk> dev_chunks;
+  auto free_chunks = [&]() {
+    for (auto &c : dev_chunks) {
+      cudaFreeAsync(c.qid, s); cudaFreeAsync(c.tid, s); cudaFreeAsync(c.qf, s);
+      cudaFreeAsync(c.ql, s); cudaFreeAsync(c.tf, s); cudaFreeAsync(c.tl, s);
+    }
+    dev_chunks.clear();
+  };
 
   Ctx total;
-  std::vector<std::unique_ptr<BatchOut>> dev_chunks;
-  std::vector<size_t> chunk_rows;
   size_t chunk = (size_t)env_u64("IMPGX_ROWS_PER_BATCH", 8192);
   if (chunk == 0) chunk = 8192;
-  DBuf<impgx_range> d_stage;
   size_t done = 0;
   uint64_t res_base = 0, cig_base = 0;
-  while (done < n) {
-    size_t m = std::min(chunk, n - done);
-    const impgx_range *d_r;
-    if (ranges_on_device) {
-      d_r = ranges + done;
-    } else {
-      if (d_stage.n < m) d_stage.alloc(m, s);
-      CUDA_CHECK(cudaMemcpyAsync(d_stage.get(), ranges + done, m * sizeof(impgx_range), cudaMemcpyHostToDevice, s));
-      total.h2d_bytes += m * sizeof(impgx_range);
-      d_r = d_stage.get();
-    }
-    std::unique_ptr<BatchOut> bo(new BatchOut());
-    Runner runner(idx, p, s);
-    runner.run(d_r, (uint32_t)m, bed, *bo);
-    CUDA_CHECK(cudaStreamSynchronize(s));
-    const Ctx &c = runner.ctx;
-    total.launches += c.launches; total.lift_launches += c.lift_launches;
-    total.stab_ranges += c.stab_ranges; total.liftovers += c.liftovers;
-    total.lift_runs += c.lift_runs; total.lift_bytes += c.lift_bytes;
-    total.h2d_bytes += c.h2d_bytes; total.d2h_bytes += c.d2h_bytes;
-    total.lift_ms += c.lift_ms; total.stab_ms += c.stab_ms; total.fold_ms += c.fold_ms; total.merge_ms += c.merge_ms;
-    total.w_stab += c.w_stab; total.w_lift += c.w_lift; total.w_order += c.w_order; total.w_fold += c.w_fold;
-    total.w_assemble += c.w_assemble; total.w_merge += c.w_merge;
-    WallTimer wcopy(total.w_copy);
+  try {
+    while (done < n) {
+      const size_t m = std::min(chunk, n - done);
+      {
+        const impgx_range *d_r;
+        DBuf<impgx_range> d_stage;
+        if (ranges_on_device) {
+          d_r = ranges + done;
+        } else {
+          d_stage.alloc(m, idx->arena);
+          CUDA_CHECK(cudaMemcpyAsync(d_stage.get(), ranges + done, m * sizeof(impgx_range), cudaMemcpyHostToDevice, s));
+          total.h2d_bytes += m * sizeof(impgx_range);
+          d_r = d_stage.get();
+        }
+        BatchOut bo;
+        Runner runner(idx, p, s);
+        runner.run(d_r, (uint32_t)m, bed, bo);
+        const Ctx &c = runner.ctx;
+        total.launches += c.launches; total.lift_launches += c.lift_launches;
+        total.stab_ranges += c.stab_ranges; total.liftovers += c.liftovers;
+        total.lift_runs += c.lift_runs; total.lift_bytes += c.lift_bytes;
+        total.h2d_bytes += c.h2d_bytes; total.d2h_bytes += c.d2h_bytes;
+        total.lift_ms += c.lift_ms; total.stab_ms += c.stab_ms; total.fold_ms += c.fold_ms; total.merge_ms += c.merge_ms;
+        total.w_stab += c.w_stab; total.w_lift += c.w_lift; total.w_order += c.w_order; total.w_fold += c.w_fold;
+        total.w_assemble += c.w_assemble; total.w_merge += c.w_merge;
+        WallTimer wcopy(total.w_copy);
 
-    const uint64_t R = bo->n_results;
-    if (results_to_host) {
-      std::vector<uint64_t> ro(m + 1);
-      CUDA_CHECK(cudaMemcpyAsync(ro.data(), bo->row_off.get(), (m + 1) * 8, cudaMemcpyDeviceToHost, s));
-      size_t old = res->qid.size();
-      res->qid.resize(old + R); res->tid.resize(old + R);
-      res->qf.resize(old + R); res->ql.resize(old + R);
-      res->tf.resize(old + R); res->tl.resize(old + R);
-      if (R) {
-        CUDA_CHECK(cudaMemcpyAsync(res->qid.data() + old, bo->q_id.get(), R * 4, cudaMemcpyDeviceToHost, s));
-        CUDA_CHECK(cudaMemcpyAsync(res->qf.data() + old, bo->q_first.get(), R * 4, cudaMemcpyDeviceToHost, s));
-        CUDA_CHECK(cudaMemcpyAsync(res->ql.data() + old, bo->q_last.get(), R * 4, cudaMemcpyDeviceToHost, s));
-        CUDA_CHECK(cudaMemcpyAsync(res->tid.data() + old, bo->t_id.get(), R * 4, cudaMemcpyDeviceToHost, s));
-        CUDA_CHECK(cudaMemcpyAsync(res->tf.data() + old, bo->t_first.get(), R * 4, cudaMemcpyDeviceToHost, s));
-        CUDA_CHECK(cudaMemcpyAsync(res->tl.data() + old, bo->t_last.get(), R * 4, cudaMemcpyDeviceToHost, s));
-      }
-      total.d2h_bytes += (m + 1) * 8 + R * 24;
-      if (res->has_cigar) {
-        std::vector<uint64_t> co(R + 1);
-        CUDA_CHECK(cudaMemcpyAsync(co.data(), bo->cig_off.get(), (R + 1) * 8, cudaMemcpyDeviceToHost, s));
-        size_t oldc = res->cig.size();
-        res->cig.resize(oldc + bo->n_cig);
-        if (bo->n_cig)
-          CUDA_CHECK(cudaMemcpyAsync(res->cig.data() + oldc, bo->cig.get(), bo->n_cig * 4, cudaMemcpyDeviceToHost, s));
+        const uint64_t R = bo.n_results;
+        std::vector<uint64_t> ro(m + 1);
+        CUDA_CHECK(cudaMemcpyAsync(ro.data(), bo.row_off.get(), (m + 1) * 8, cudaMemcpyDeviceToHost, s));
+        total.d2h_bytes += (m + 1) * 8;
+        if (results_to_host) {
+          const size_t old = res->qid.size();
+          res->qid.resize(old + R); res->tid.resize(old + R);
+          res->qf.resize(old + R); res->ql.resize(old + R);
+          res->tf.resize(old + R); res->tl.resize(old + R);
+          if (R) {
+            CUDA_CHECK(cudaMemcpyAsync(res->qid.data() + old, bo.q_id.get(), R * 4, cudaMemcpyDeviceToHost, s));
+            CUDA_CHECK(cudaMemcpyAsync(res->qf.data() + old, bo.q_first.get(), R * 4, cudaMemcpyDeviceToHost, s));
+            CUDA_CHECK(cudaMemcpyAsync(res->ql.data() + old, bo.q_last.get(), R * 4, cudaMemcpyDeviceToHost, s));
+            CUDA_CHECK(cudaMemcpyAsync(res->tid.data() + old, bo.t_id.get(), R * 4, cudaMemcpyDeviceToHost, s));
+            CUDA_CHECK(cudaMemcpyAsync(res->tf.data() + old, bo.t_first.get(), R * 4, cudaMemcpyDeviceToHost, s));
+            CUDA_CHECK(cudaMemcpyAsync(res->tl.data() + old, bo.t_last.get(), R * 4, cudaMemcpyDeviceToHost, s));
+          }
+          total.d2h_bytes += R * 24;
+          if (res->has_cigar) {
+            std::vector<uint64_t> co(R + 1);
+            CUDA_CHECK(cudaMemcpyAsync(co.data(), bo.cig_off.get(), (R + 1) * 8, cudaMemcpyDeviceToHost, s));
+            const size_t oldc = res->cig.size();
+            res->cig.resize(oldc + bo.n_cig);
+            if (bo.n_cig)
+              CUDA_CHECK(cudaMemcpyAsync(res->cig.data() + oldc, bo.cig.get(), bo.n_cig * 4, cudaMemcpyDeviceToHost, s));
+            CUDA_CHECK(cudaStreamSynchronize(s));
+            for (uint64_t i = 1; i <= R; i++) res->cig_off.push_back(cig_base + co[i]);
+            total.d2h_bytes += (R + 1) * 8 + bo.n_cig * 4;
+            cig_base += bo.n_cig;
+          }
+        } else {
+          DevChunk dc;
+          dc.n = R;
+          const size_t rb = std::max<uint64_t>(R, 1) * 4;
+          CUDA_CHECK(cudaMallocAsync((void **)&dc.qid, rb, s));
+          CUDA_CHECK(cudaMallocAsync((void **)&dc.tid, rb, s));
+          CUDA_CHECK(cudaMallocAsync((void **)&dc.qf, rb, s));
+          CUDA_CHECK(cudaMallocAsync((void **)&dc.ql, rb, s));
+          CUDA_CHECK(cudaMallocAsync((void **)&dc.tf, rb, s));
+          CUDA_CHECK(cudaMallocAsync((void **)&dc.tl, rb, s));
+          dev_chunks.push_back(dc);
+          if (R) {
+            CUDA_CHECK(cudaMemcpyAsync(dc.qid, bo.q_id.get(), R * 4, cudaMemcpyDeviceToDevice, s));
+            CUDA_CHECK(cudaMemcpyAsync(dc.qf, bo.q_first.get(), R * 4, cudaMemcpyDeviceToDevice, s));
+            CUDA_CHECK(cudaMemcpyAsync(dc.ql, bo.q_last.get(), R * 4, cudaMemcpyDeviceToDevice, s));
+            CUDA_CHECK(cudaMemcpyAsync(dc.tid, bo.t_id.get(), R * 4, cudaMemcpyDeviceToDevice, s));
+            CUDA_CHECK(cudaMemcpyAsync(dc.tf, bo.t_first.get(), R * 4, cudaMemcpyDeviceToDevice, s));
+            CUDA_CHECK(cudaMemcpyAsync(dc.tl, bo.t_last.get(), R * 4, cudaMemcpyDeviceToDevice, s));
+          }
+        }
         CUDA_CHECK(cudaStreamSynchronize(s));
-        if (res->cig_off.empty()) res->cig_off.push_back(0);
-        for (uint64_t i = 1; i <= R; i++) res->cig_off.push_back(cig_base + co[i]);
-        total.d2h_bytes += (R + 1) * 8 + bo->n_cig * 4;
+        for (size_t i = 1; i <= m; i++) res->row_off[done + i] = res_base + ro[i];
+        res_base += R;
       }
-      CUDA_CHECK(cudaStreamSynchronize(s));
-      for (size_t i = 1; i <= m; i++) res->row_off[done + i] = res_base + ro[i];
-    } else {
-      std::vector<uint64_t> ro(m + 1);
-      CUDA_CHECK(cudaMemcpyAsync(ro.data(), bo->row_off.get(), (m + 1) * 8, cudaMemcpyDeviceToHost, s));
-      CUDA_CHECK(cudaStreamSynchronize(s));
-      for (size_t i = 1; i <= m; i++) res->row_off[done + i] = res_base + ro[i];
-      dev_chunks.push_back(std::move(bo));
-      chunk_rows.push_back(m);
+      // every arena block of this batch is out of scope and the stream is idle
+      idx->arena.reset();
+      done += m;
     }
-    res_base += R;
-    cig_base += bo ? bo->n_cig : 0;
-    done += m;
+  } catch (...) {
+    cudaStreamSynchronize(s);
+    free_chunks();
+    idx->arena.reset();
+    throw;
   }
   res->n_results = res_base;
   res->n_cig = cig_base;
-  if (res->has_cigar && res->cig_off.empty()) res->cig_off.push_back(0);
 
   if (!results_to_host) {
     // concatenate the chunk outputs into one set of device columns
     res->on_device = true;
     res->stream = s;
     const uint64_t R = res_base;
-    size_t rb = std::max<uint64_t>(R, 1) * 4;
+    const size_t rb = std::max<uint64_t>(R, 1) * 4;
     CUDA_CHECK(cudaMallocAsync((void **)&res->d_row_off, (n + 1) * 8, s));
-    CUDA_CHECK(cudaMallocAsync((void **)&res->d_qid, rb, s));
-    CUDA_CHECK(cudaMallocAsync((void **)&res->d_qf, rb, s));
-    CUDA_CHECK(cudaMallocAsync((void **)&res->d_ql, rb, s));
-    CUDA_CHECK(cudaMallocAsync((void **)&res->d_tid, rb, s));
-    CUDA_CHECK(cudaMallocAsync((void **)&res->d_tf, rb, s));
-    CUDA_CHECK(cudaMallocAsync((void **)&res->d_tl, rb, s));
     CUDA_CHECK(cudaMemcpyAsync(res->d_row_off, res->row_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, s));
-    uint64_t off = 0;
-    for (auto &c : dev_chunks) {
-      const uint64_t r = c->n_results;
-      if (r) {
-        CUDA_CHECK(cudaMemcpyAsync(res->d_qid + off, c->q_id.get(), r * 4, cudaMemcpyDeviceToDevice, s));
-        CUDA_CHECK(cudaMemcpyAsync(res->d_qf + off, c->q_first.get(), r * 4, cudaMemcpyDeviceToDevice, s));
-        CUDA_CHECK(cudaMemcpyAsync(res->d_ql + off, c->q_last.get(), r * 4, cudaMemcpyDeviceToDevice, s));
-        CUDA_CHECK(cudaMemcpyAsync(res->d_tid + off, c->t_id.get(), r * 4, cudaMemcpyDeviceToDevice, s));
-        CUDA_CHECK(cudaMemcpyAsync(res->d_tf + off, c->t_first.get(), r * 4, cudaMemcpyDeviceToDevice, s));
-        CUDA_CHECK(cudaMemcpyAsync(res->d_tl + off, c->t_last.get(), r * 4, cudaMemcpyDeviceToDevice, s));
+    if (dev_chunks.size() == 1) {
+      DevChunk &c = dev_chunks[0];
+      res->d_qid = c.qid; res->d_tid = c.tid; res->d_qf = c.qf; res->d_ql = c.ql; res->d_tf = c.tf; res->d_tl = c.tl;
+      dev_chunks.clear();
+    } else {
+      CUDA_CHECK(cudaMallocAsync((void **)&res->d_qid, rb, s));
+      CUDA_CHECK(cudaMallocAsync((void **)&res->d_qf, rb, s));
+      CUDA_CHECK(cudaMallocAsync((void **)&res->d_ql, rb, s));
+      CUDA_CHECK(cudaMallocAsync((void **)&res->d_tid, rb, s));
+      CUDA_CHECK(cudaMallocAsync((void **)&res->d_tf, rb, s));
+      CUDA_CHECK(cudaMallocAsync((void **)&res->d_tl, rb, s));
+      uint64_t off = 0;
+      for (auto &c : dev_chunks) {
+        const uint64_t r = c.n;
+        if (r) {
+          CUDA_CHECK(cudaMemcpyAsync(res->d_qid + off, c.qid, r * 4, cudaMemcpyDeviceToDevice, s));
+          CUDA_CHECK(cudaMemcpyAsync(res->d_qf + off, c.qf, r * 4, cudaMemcpyDeviceToDevice, s));
+          CUDA_CHECK(cudaMemcpyAsync(res->d_ql + off, c.ql, r * 4, cudaMemcpyDeviceToDevice, s));
+          CUDA_CHECK(cudaMemcpyAsync(res->d_tid + off, c.tid, r * 4, cudaMemcpyDeviceToDevice, s));
+          CUDA_CHECK(cudaMemcpyAsync(res->d_tf + off, c.tf, r * 4, cudaMemcpyDeviceToDevice, s));
+          CUDA_CHECK(cudaMemcpyAsync(res->d_tl + off, c.tl, r * 4, cudaMemcpyDeviceToDevice, s));
+        }
+        off += r;
       }
-      off += r;
+      free_chunks();
     }
     CUDA_CHECK(cudaStreamSynchronize(s));
   }
@@ -981,9 +1032,10 @@ impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n
   if (getenv("IMPGX_TRACE"))
     fprintf(stderr,
             "[impgx] rows=%zu total=%.2f ms | wall: stab %.2f lift %.2f order %.2f fold %.2f assemble %.2f merge %.2f "
-            "copy %.2f | dev: stab %.2f lift %.2f fold %.2f merge %.2f | launches %llu\n",
+            "copy %.2f | dev: stab %.2f lift %.2f fold %.2f merge %.2f | launches %llu | arena %.2f GB peak %.2f GB\n",
             n, st.total_ms, total.w_stab, total.w_lift, total.w_order, total.w_fold, total.w_assemble, total.w_merge,
-            total.w_copy, st.stab_ms, st.lift_ms, st.fold_ms, st.merge_ms, (unsigned long long)st.kernel_launches);
+            total.w_copy, st.stab_ms, st.lift_ms, st.fold_ms, st.merge_ms, (unsigned long long)st.kernel_launches,
+            idx->arena.capacity() / 1e9, idx->arena.peak() / 1e9);
   return res.release();
 }
 
@@ -996,6 +1048,7 @@ void project_batch(int device, size_t n, const int32_t *req_start, const int32_t
   if (n == 0) return;
   cudaStream_t s = nullptr;
   Ctx ctx;
+  Arena arena;
   std::vector<EntryRec> recs(n);
   std::vector<uint32_t> blk_off(n + 1);
   std::vector<Frontier> fr(n);
@@ -1020,15 +1073,15 @@ void project_batch(int device, size_t n, const int32_t *req_start, const int32_t
   }
   blk_off[n] = (uint32_t)blocks;
   const uint64_t total_runs = run_offsets[n];
-  DBuf<uint32_t> d_raw(std::max<uint64_t>(total_runs, 1), s), d_blk(n + 1, s), d_runs(std::max<uint64_t>(blocks, 1) * RUNS_PER_BLOCK, s);
-  DBuf<uint64_t> d_off(n + 1, s);
-  DBuf<Checkpoint> d_ck(blocks + n + 1, s);
-  DBuf<EntryRec> d_rec(n, s);
-  DBuf<Frontier> d_fr(n, s);
-  DBuf<LiftTask> d_tasks(n, s);
-  DBuf<uint32_t> d_vrank(n, s);
-  DBuf<Hit> d_hits(n, s);
-  DBuf<CigarSlice> d_slices(n, s);
+  DBuf<uint32_t> d_raw(std::max<uint64_t>(total_runs, 1), arena), d_blk(n + 1, arena), d_runs(std::max<uint64_t>(blocks, 1) * RUNS_PER_BLOCK, arena);
+  DBuf<uint64_t> d_off(n + 1, arena);
+  DBuf<Checkpoint> d_ck(blocks + n + 1, arena);
+  DBuf<EntryRec> d_rec(n, arena);
+  DBuf<Frontier> d_fr(n, arena);
+  DBuf<LiftTask> d_tasks(n, arena);
+  DBuf<uint32_t> d_vrank(n, arena);
+  DBuf<Hit> d_hits(n, arena);
+  DBuf<CigarSlice> d_slices(n, arena);
   if (total_runs) CUDA_CHECK(cudaMemcpyAsync(d_raw.get(), runs, total_runs * 4, cudaMemcpyHostToDevice, s));
   CUDA_CHECK(cudaMemcpyAsync(d_off.get(), run_offsets, (n + 1) * 8, cudaMemcpyHostToDevice, s));
   CUDA_CHECK(cudaMemcpyAsync(d_blk.get(), blk_off.data(), (n + 1) * 4, cudaMemcpyHostToDevice, s));
@@ -1071,8 +1124,8 @@ void project_batch(int device, size_t n, const int32_t *req_start, const int32_t
   if (out_run_offsets) memcpy(out_run_offsets, oo.data(), (n + 1) * 8);
   if (out_runs && oo[n]) {
     REQUIRE(oo[n] <= out_runs_cap, IMPGX_E_INVALID, "out_runs capacity too small");
-    DBuf<uint64_t> d_oo(n + 1, s);
-    DBuf<uint32_t> d_out(oo[n], s);
+    DBuf<uint64_t> d_oo(n + 1, arena);
+    DBuf<uint32_t> d_out(oo[n], arena);
     CUDA_CHECK(cudaMemcpyAsync(d_oo.get(), oo.data(), (n + 1) * 8, cudaMemcpyHostToDevice, s));
     LAUNCH(k_emit_cigar, grid_warps(n), 256, s, ix, d_tasks.get(), d_slices.get(), d_oo.get(), (uint64_t)n, d_out.get());
     CUDA_CHECK(cudaMemcpyAsync(out_runs, d_out.get(), oo[n] * 4, cudaMemcpyDeviceToHost, s));

@@ -54,6 +54,7 @@ struct impgx_index {
   uint64_t *d_tgt_off = nullptr;
   impgx::Checkpoint *d_ck = nullptr;
   std::mutex mu;  // one query batch at a time per index (handle is thread-safe)
+  impgx::Arena arena;  // device scratch of the query pipeline
   impgx_stats last{};
 
   impgx::DevIndexView view() const {
