@@ -366,7 +366,7 @@ void Runner::stab_and_lift(const DBuf<Frontier> &fr, uint64_t nF, bool closed, b
   // endpoint kernel when neither the clipped CIGAR nor the identity is needed
   const bool ends = !p_.store_cigar && !lp.use_identity && !getenv("IMPGX_FULL_SCAN");
   if (ends)
-    LAUNCH(k_liftover_ends, grid_warps((H + 3) / 4, 256, 8), 256, s_, ix_, fr.get(), tasks.get(), H, lp, hits.get(),
+    LAUNCH(k_liftover_ends, grid_threads(H, 256, 8), 256, s_, ix_, fr.get(), tasks.get(), H, lp, hits.get(),
            d_counters_.get());
   else
     LAUNCH(k_liftover, grid_warps(H, 256, 8), 256, s_, ix_, fr.get(), tasks.get(), H, lp, hits.get(), slices.get(),
@@ -1101,7 +1101,7 @@ void project_batch(int device, size_t n, const int32_t *req_start, const int32_t
   lp.min_output_len = -1;
   if (!out_runs) {
     CUDA_CHECK(cudaMemsetAsync(d_slices.get(), 0, n * sizeof(CigarSlice), s));
-    LAUNCH(k_liftover_ends, grid_warps((n + 3) / 4), 256, s, ix, d_fr.get(), d_tasks.get(), (uint64_t)n, lp, d_hits.get(),
+    LAUNCH(k_liftover_ends, grid_threads(n), 256, s, ix, d_fr.get(), d_tasks.get(), (uint64_t)n, lp, d_hits.get(),
            (unsigned long long *)nullptr);
   } else {
     LAUNCH(k_liftover, grid_warps(n), 256, s, ix, d_fr.get(), d_tasks.get(), (uint64_t)n, lp, d_hits.get(),

@@ -419,184 +419,90 @@ __global__ void __launch_bounds__(256) k_liftover(DevIndexView ix, const Frontie
 }
 
 // ------------------------------------------------------------------ K2e
-// Endpoint liftover: 8 lanes ("octet") per hit, 4 hits per warp. When neither
-// the clipped CIGAR nor the identity is wanted, the result of
-// project_target_range_through_alignment depends only on the FIRST and the
-// LAST overlapping op (src/impg.rs:2806-2868: projected_*_start are written
-// once, projected_*_end by every overlapping op), so only the two run blocks
-// at the ends of the request are read; their start positions come from the
-// checkpoints. One lane loads 4 runs with a single 128-bit load, so a 32-run
-// block is one coalesced 128-byte request per octet.
-struct OctetCtx {
-  unsigned gmask;   // the octet's lanes
-  unsigned sub;     // lane within the octet
-  unsigned gbase;   // first lane of the octet
+// Endpoint liftover, ONE THREAD PER HIT. When neither the clipped CIGAR nor the
+// identity is wanted, the result of project_target_range_through_alignment
+// depends only on the FIRST and the LAST overlapping op (src/impg.rs:2806-2868:
+// projected_*_start are written once, projected_*_end by every overlapping
+// op), so only the run blocks at the two ends of the request are read; their
+// start positions come from the checkpoints. A thread streams a 128-byte block
+// as eight 128-bit loads and evaluates the runs branch-free; there are no
+// shuffles and no intra-warp dependencies, so the kernel is bound by the
+// gather traffic (entry 32 B + checkpoint probes + 2 blocks + hit 32 B).
+// (v1 = warp per hit, 1233 warp-instructions per hit; v2 = 8 lanes per hit,
+// 391; both were instruction-issue bound — see profiles/.)
+
+// first index b in [lo, hi) with !(P(b) < x) (strict) / !(P(b) <= x), P nondecreasing
+__device__ __forceinline__ uint32_t ck_partition(const Checkpoint *__restrict__ ck, bool swap_id, uint32_t lo,
+                                                 uint32_t hi, int64_t x, bool inclusive) {
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    const Checkpoint v = ck[mid];
+    const int64_t p = swap_id ? v.q_off : v.t_off;
+    const bool t = inclusive ? p <= x : p < x;
+    lo = t ? mid + 1 : lo;
+    hi = t ? hi : mid;
+  }
+  return lo;
+}
+
+struct EndsAcc {
+  int32_t f_q, f_t, l_q, l_t;
+  bool found, broke;
 };
 
-__device__ __forceinline__ int octet_incl_scan(const OctetCtx &c, int v) {
-#pragma unroll
-  for (int d = 1; d < 8; d <<= 1) {
-    int o = __shfl_up_sync(c.gmask, v, d, 8);
-    if (c.sub >= (unsigned)d) v += o;
-  }
-  return v;
-}
-__device__ __forceinline__ int octet_sum(const OctetCtx &c, int v) {
-#pragma unroll
-  for (int d = 4; d; d >>= 1) v += __shfl_xor_sync(c.gmask, v, d, 8);
-  return v;
-}
-__device__ __forceinline__ int octet_min(const OctetCtx &c, int v) {
-#pragma unroll
-  for (int d = 4; d; d >>= 1) v = min(v, __shfl_xor_sync(c.gmask, v, d, 8));
-  return v;
-}
-__device__ __forceinline__ int octet_max(const OctetCtx &c, int v) {
-#pragma unroll
-  for (int d = 4; d; d >>= 1) v = max(v, __shfl_xor_sync(c.gmask, v, d, 8));
-  return v;
-}
-
-// #{ b in [lo, hi) : P(b) < x }  (strict) or <= x, P = walk-space target prefix
-// at checkpoint b; P is nondecreasing. Octet-cooperative, 32 checkpoints a round.
-__device__ __forceinline__ uint32_t octet_count_below(const OctetCtx &c, const Checkpoint *__restrict__ ck, bool swap_id,
-                                                      uint32_t lo, uint32_t hi, int64_t x, bool inclusive) {
-  // coarse 32-ary narrowing for long alignments
-  while (hi - lo > 32) {
-    const uint32_t step = (hi - lo + 31) / 32;
-    int cnt = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const uint64_t pos = (uint64_t)lo + (uint64_t)(c.sub * 4 + k + 1) * step - 1;
-      if (pos < hi) {
-        const Checkpoint v = ck[pos];
-        const int64_t p = swap_id ? v.q_off : v.t_off;
-        cnt += (inclusive ? p <= x : p < x) ? 1 : 0;
-      }
-    }
-    const uint32_t k = (uint32_t)octet_sum(c, cnt);  // probes 0..k-1 are true
-    uint32_t nlo = lo + k * step, nhi = lo + (k + 1) * step - 1;
-    if (nhi > hi) nhi = hi;
-    if (nlo >= nhi) return nhi;
-    lo = nlo;
-    hi = nhi;
-  }
-  int cnt = 0;
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const uint32_t pos = lo + c.sub * 4 + k;
-    if (pos < hi) {
-      const Checkpoint v = ck[pos];
-      const int64_t p = swap_id ? v.q_off : v.t_off;
-      cnt += (inclusive ? p <= x : p < x) ? 1 : 0;
-    }
-  }
-  return lo + (uint32_t)octet_sum(c, cnt);
-}
-
-// One 32-run block evaluated by an octet. Outputs (uniform across the octet):
-// first/last overlapping processed op of the block in walk order.
-struct BlockEval {
-  bool any_ov;       // some processed op overlaps
-  bool broke;        // the loop break (target_pos > last_target_pos) falls inside this block
-  int32_t f_q, f_t;  // projected_query_start / projected_target_start of the first overlapping op
-  int32_t l_q, l_t;  // projected_query_end / projected_target_end of the last overlapping op
-};
-
-__device__ __forceinline__ BlockEval octet_eval_block(const OctetCtx &c, const uint32_t *__restrict__ blk, uint32_t n,
-                                                      uint32_t pb, bool swap_id, bool backward, int32_t dir,
-                                                      int32_t tp0, int32_t qp0, int32_t rs, int32_t re,
-                                                      int32_t last_target_pos) {
+// evaluates the (up to) 32 runs of physical block pb in walk order
+__device__ __forceinline__ void thread_eval_block(const uint32_t *__restrict__ blk, uint32_t n, uint32_t pb, bool swap_id,
+                                                  bool backward, int32_t dir, int32_t tp, int32_t qp, int32_t rs,
+                                                  int32_t re, int32_t last_target_pos, EndsAcc &acc) {
   const uint32_t base = pb * RUNS_PER_BLOCK;
   const uint32_t cnt = min((uint32_t)RUNS_PER_BLOCK, n - base);
-  // lane holds physical runs [4*sub, 4*sub+4) of the block (zero padded beyond n)
-  const uint4 v4 = *reinterpret_cast<const uint4 *>(blk + base + c.sub * 4);
-  const uint32_t v[4] = {v4.x, v4.y, v4.z, v4.w};
-  int32_t td[4], qd[4];
-  int32_t tsum = 0, qsum = 0;
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    uint32_t op = v[k] >> 29;
-    const int32_t len = (int32_t)(v[k] & 0x1fffffffu);
-    if (swap_id) op = op == IMPGX_OP_I ? IMPGX_OP_D : (op == IMPGX_OP_D ? IMPGX_OP_I : op);
-    td[k] = (op == IMPGX_OP_I) ? 0 : len;
-    qd[k] = (op == IMPGX_OP_D) ? 0 : len;
-    tsum += td[k];
-    qsum += qd[k];
-  }
-  const int32_t tincl = octet_incl_scan(c, tsum), qincl = octet_incl_scan(c, qsum);
-  const int32_t ttot = __shfl_sync(c.gmask, tincl, c.gbase + 7), qtot = __shfl_sync(c.gmask, qincl, c.gbase + 7);
-  // bases consumed before this lane's runs, in walk order
-  int32_t tb = backward ? (ttot - tincl) : (tincl - tsum);
-  int32_t qb = backward ? (qtot - qincl) : (qincl - qsum);
-  int first_w = 64, last_w = -1;
-  int32_t f_q = 0, f_t = 0, l_q = 0, l_t = 0;
-  bool broke = false;
-#pragma unroll
-  for (int kk = 0; kk < 4; kk++) {
-    const int k = backward ? 3 - kk : kk;  // walk order within the lane
-    const uint32_t off = c.sub * 4 + k;     // physical offset in the block
-    const bool valid = off < cnt;
-    const int32_t tp = tp0 + tb, qp = qp0 + qb * dir;
-    const int32_t t = td[k], q = qd[k];
-    tb += t;
-    qb += q;
-    if (!valid) continue;
-    if (tp > last_target_pos) {
-      broke = true;
-      continue;
+  const uint4 *src = reinterpret_cast<const uint4 *>(blk + base);
+#pragma unroll 2
+  for (int c = 0; c < 8; c++) {
+    const int ci = backward ? 7 - c : c;
+    uint4 v4 = src[ci];
+    if (backward) {  // walk order within the chunk is reversed too
+      uint32_t t0 = v4.x, t1 = v4.y;
+      v4.x = v4.w; v4.y = v4.z; v4.z = t1; v4.w = t0;
     }
-    bool ov;
-    int32_t pqs, pts, pqe, pte;
-    if (t == 0) {
-      ov = tp >= rs;
-      pqs = qp; pts = tp; pqe = qp + q * dir; pte = tp;
-    } else if (q == 0) {
-      const int32_t os = max(tp, rs), oe = min(tp + t, last_target_pos);
-      ov = os < oe;
-      pqs = qp; pts = os; pqe = qp; pte = oe;
-    } else {
-      const int32_t os = max(tp, rs), oe = min(tp + t, re);
-      ov = os < oe;
-      pqs = qp + (os - tp) * dir; pts = os;
-      pqe = pqs + (oe - os) * dir; pte = oe;
-    }
-    if (ov) {
-      const int w = backward ? (int)(cnt - 1 - off) : (int)off;  // walk index within the block
-      if (w < first_w) { first_w = w; f_q = pqs; f_t = pts; }
-      if (w > last_w) { last_w = w; l_q = pqe; l_t = pte; }
+    const uint32_t v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t off = (uint32_t)(ci * 4 + (backward ? 3 - k : k));  // physical offset in the block
+      uint32_t op = v[k] >> 29;
+      const int32_t len = (int32_t)(v[k] & 0x1fffffffu);
+      if (swap_id) op = op == IMPGX_OP_I ? IMPGX_OP_D : (op == IMPGX_OP_D ? IMPGX_OP_I : op);
+      const int32_t t = (op == IMPGX_OP_I) ? 0 : len;
+      const int32_t q = (op == IMPGX_OP_D) ? 0 : len;
+      const bool valid = off < cnt;
+      const bool processed = valid && tp <= last_target_pos;
+      acc.broke |= valid && tp > last_target_pos;
+      const bool is_ins = t == 0, is_del = !is_ins && q == 0;
+      const int32_t os = max(tp, rs);
+      const int32_t oe = min(tp + t, is_del ? last_target_pos : re);
+      const bool ov = processed && (is_ins ? tp >= rs : os < oe);
+      const int32_t pts = is_ins ? tp : os, pte = is_ins ? tp : oe;
+      const int32_t pqs = (is_ins || is_del) ? qp : qp + (os - tp) * dir;
+      const int32_t pqe = is_ins ? qp + q * dir : (is_del ? qp : pqs + (oe - os) * dir);
+      const bool first = ov && !acc.found;
+      acc.f_q = first ? pqs : acc.f_q;
+      acc.f_t = first ? pts : acc.f_t;
+      acc.found |= ov;
+      acc.l_q = ov ? pqe : acc.l_q;
+      acc.l_t = ov ? pte : acc.l_t;
+      tp += t;
+      qp += q * dir;
     }
   }
-  BlockEval r;
-  const int fw = octet_min(c, first_w), lw = octet_max(c, last_w);
-  r.any_ov = lw >= 0;
-  r.broke = __any_sync(c.gmask, broke);
-  // owners broadcast their values
-  const unsigned bal_f = __ballot_sync(c.gmask, first_w == fw && fw < 64);
-  const unsigned bal_l = __ballot_sync(c.gmask, last_w == lw && lw >= 0);
-  const int of = bal_f ? __ffs(bal_f) - 1 : (int)c.gbase, ol = bal_l ? __ffs(bal_l) - 1 : (int)c.gbase;
-  r.f_q = __shfl_sync(c.gmask, f_q, of);
-  r.f_t = __shfl_sync(c.gmask, f_t, of);
-  r.l_q = __shfl_sync(c.gmask, l_q, ol);
-  r.l_t = __shfl_sync(c.gmask, l_t, ol);
-  return r;
 }
 
 __global__ void __launch_bounds__(256, 4) k_liftover_ends(DevIndexView ix, const Frontier *__restrict__ fr,
                                                        const LiftTask *__restrict__ tasks, uint64_t n_tasks,
                                                        LiftParams lp, Hit *__restrict__ hits,
                                                        unsigned long long *__restrict__ counters) {
-  const unsigned lane = lane_id();
-  OctetCtx c;
-  c.sub = lane & 7u;
-  c.gbase = lane & ~7u;
-  c.gmask = 0xffu << c.gbase;
-  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   unsigned long long runs_acc = 0, ok_acc = 0, ck_acc = 0;
-  for (uint64_t w0 = warp * 4; w0 < n_tasks; w0 += nwarps * 4) {
-    const uint64_t w = w0 + (lane >> 3);
-    if (w >= n_tasks) continue;  // whole octet leaves together
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_tasks; w += stride) {
     const LiftTask t = tasks[w];
     const Frontier f = fr[t.range];
     const uint4 *rp = reinterpret_cast<const uint4 *>(ix.e_rec + t.entry);
@@ -619,29 +525,31 @@ __global__ void __launch_bounds__(256, 4) k_liftover_ends(DevIndexView ix, const
     const int32_t last_target_pos = min(t_end, re);
     const int64_t rel = (int64_t)rs - t_start, rel_l = (int64_t)last_target_pos - t_start;
 
-    bool found = false;
-    int32_t o_qs = -1, o_qe = -1, o_ts = -1, o_te = -1;
-    uint32_t nread = 0;
+    EndsAcc acc;
+    acc.f_q = acc.f_t = acc.l_q = acc.l_t = -1;
+    acc.found = false;
+    acc.broke = false;
+    uint32_t nread = 0, nck = 0;
     if (nblk > 0 && rel_l >= 0) {
       const Checkpoint tot = ck[nblk];
       const int64_t w_tot = swap_id ? tot.q_off : tot.t_off, wq_tot = swap_id ? tot.t_off : tot.q_off;
       // walk blocks j in [0, nblk): js = last block starting before rs, je = last block starting at or before L
       uint32_t js, je;
       if (!backward) {
-        const uint32_t a = octet_count_below(c, ck, swap_id, 0, nblk, rel, false);
-        const uint32_t b = octet_count_below(c, ck, swap_id, 0, nblk, rel_l, true);
+        const uint32_t a = ck_partition(ck, swap_id, 0, nblk, rel, false);
+        const uint32_t b = ck_partition(ck, swap_id, a ? a - 1 : 0, nblk, rel_l, true);
         js = a ? a - 1 : 0;
         je = b ? b - 1 : 0;
       } else {
-        // walk block j starts at W - P(nblk - j): count j with W - P(nblk-j) < rel  <=>  P(b) > W - rel, b in [1, nblk]
-        const uint32_t a = nblk - (octet_count_below(c, ck, swap_id, 1, nblk + 1, w_tot - rel, true) - 1);
-        const uint32_t b = nblk - (octet_count_below(c, ck, swap_id, 1, nblk + 1, w_tot - rel_l, false) - 1);
+        // walk block j starts at W - P(nblk - j):  #{j : W - P(nblk-j) < rel} = nblk - #{b in [1,nblk] : P(b) <= W - rel}
+        const uint32_t a = nblk - (ck_partition(ck, swap_id, 1, nblk + 1, w_tot - rel, true) - 1);
+        const uint32_t b = nblk - (ck_partition(ck, swap_id, 1, nblk + 1, w_tot - rel_l, false) - 1);
         js = a ? a - 1 : 0;
         je = b ? b - 1 : 0;
       }
-      // ---- start side: first overlapping op, walking forward from block js
+      nck = 2 * (32 - __clz(nblk | 1)) + 3;
+      // ---- start side: walk forward from block js until the first overlap (or the loop break)
       uint32_t j = js;
-      BlockEval ev;
       for (;;) {
         const uint32_t pb = backward ? nblk - 1 - j : j;
         const Checkpoint k = backward ? ck[pb + 1] : ck[pb];
@@ -649,62 +557,51 @@ __global__ void __launch_bounds__(256, 4) k_liftover_ends(DevIndexView ix, const
         const int64_t tcons = backward ? w_tot - pt : pt, qcons = backward ? wq_tot - pq : pq;
         const int32_t tp0 = (int32_t)(t_start + tcons);
         const int32_t qp0 = rev_strand ? (int32_t)(q_end - qcons) : (int32_t)(q_start + qcons);
-        ev = octet_eval_block(c, blk, n, pb, swap_id, backward, dir, tp0, qp0, rs, re, last_target_pos);
+        thread_eval_block(blk, n, pb, swap_id, backward, dir, tp0, qp0, rs, re, last_target_pos, acc);
         nread += RUNS_PER_BLOCK;
-        if (ev.any_ov || ev.broke || j + 1 >= nblk) break;
+        if (acc.found || acc.broke || j + 1 >= nblk) break;
         j++;
       }
-      if (ev.any_ov) {
-        found = true;
-        o_qs = ev.f_q;
-        o_ts = ev.f_t;
-        // ---- end side: last overlapping op, walking backward from block max(je, j)
+      // ---- end side: the last overlapping op lies in blocks [j, max(je, j)]; walk backward from the top
+      if (acc.found) {
         uint32_t jl = je > j ? je : j;
-        if (jl == j) {
-          o_qe = ev.l_q;
-          o_te = ev.l_t;
-        } else {
-          for (;;) {
-            const uint32_t pb = backward ? nblk - 1 - jl : jl;
-            const Checkpoint k = backward ? ck[pb + 1] : ck[pb];
-            const int64_t pt = swap_id ? k.q_off : k.t_off, pq = swap_id ? k.t_off : k.q_off;
-            const int64_t tcons = backward ? w_tot - pt : pt, qcons = backward ? wq_tot - pq : pq;
-            const int32_t tp0 = (int32_t)(t_start + tcons);
-            const int32_t qp0 = rev_strand ? (int32_t)(q_end - qcons) : (int32_t)(q_start + qcons);
-            BlockEval e2 = octet_eval_block(c, blk, n, pb, swap_id, backward, dir, tp0, qp0, rs, re, last_target_pos);
-            nread += RUNS_PER_BLOCK;
-            if (e2.any_ov) {
-              o_qe = e2.l_q;
-              o_te = e2.l_t;
-              break;
-            }
-            jl--;
-            if (jl == j) {  // back at the block of the first overlap
-              o_qe = ev.l_q;
-              o_te = ev.l_t;
-              break;
-            }
+        while (jl > j) {
+          const uint32_t pb = backward ? nblk - 1 - jl : jl;
+          const Checkpoint k = backward ? ck[pb + 1] : ck[pb];
+          const int64_t pt = swap_id ? k.q_off : k.t_off, pq = swap_id ? k.t_off : k.q_off;
+          const int64_t tcons = backward ? w_tot - pt : pt, qcons = backward ? wq_tot - pq : pq;
+          const int32_t tp0 = (int32_t)(t_start + tcons);
+          const int32_t qp0 = rev_strand ? (int32_t)(q_end - qcons) : (int32_t)(q_start + qcons);
+          EndsAcc a2;
+          a2.f_q = a2.f_t = a2.l_q = a2.l_t = -1;
+          a2.found = false;
+          a2.broke = false;
+          thread_eval_block(blk, n, pb, swap_id, backward, dir, tp0, qp0, rs, re, last_target_pos, a2);
+          nread += RUNS_PER_BLOCK;
+          if (a2.found) {
+            acc.l_q = a2.l_q;
+            acc.l_t = a2.l_t;
+            break;
           }
+          jl--;  // nothing overlapped up there: try the block below (block j already holds its own last)
         }
       }
     }
-    bool ok = found && o_qs != o_qe && o_ts != o_te;
+    bool ok = acc.found && acc.f_q != acc.l_q && acc.f_t != acc.l_t;
     if (ok && lp.subset) ok = query_id == lp.row_target[f.row] || lp.subset[query_id] != 0;
-    if (c.sub == 0) {
-      runs_acc += nread;
-      ok_acc += ok ? 1 : 0;
-      ck_acc += min(nblk + 1, 32u) + 2;  // one search window + the two block-start lookups
-      Hit h;
-      h.row = ok ? f.row : INVALID_ID;
-      h.q_id = query_id;
-      h.q_first = o_qs;
-      h.q_last = o_qe;
-      h.t_id = f.seq;
-      h.t_first = o_ts;
-      h.t_last = o_te;
-      h.vrank = ix.e_vrank[t.entry];
-      hits[w] = h;
-    }
+    runs_acc += nread;
+    ck_acc += nck;
+    ok_acc += ok ? 1 : 0;
+    Hit h;
+    h.row = ok ? f.row : INVALID_ID;
+    h.q_id = query_id;
+    h.q_first = acc.f_q;
+    h.q_last = acc.l_q;
+    h.t_id = f.seq;
+    h.t_first = acc.f_t;
+    h.t_last = acc.l_t;
+    h.vrank = ix.e_vrank[t.entry];
+    hits[w] = h;
   }
   // one atomic per warp
 #pragma unroll
@@ -713,7 +610,7 @@ __global__ void __launch_bounds__(256, 4) k_liftover_ends(DevIndexView ix, const
     ok_acc += __shfl_xor_sync(FULL, ok_acc, d);
     ck_acc += __shfl_xor_sync(FULL, ck_acc, d);
   }
-  if (lane == 0 && counters) {
+  if (lane_id() == 0 && counters) {
     atomicAdd(&counters[0], runs_acc);
     atomicAdd(&counters[1], ok_acc);
     atomicAdd(&counters[2], ck_acc);
