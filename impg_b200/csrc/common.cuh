@@ -38,7 +38,7 @@ void set_last_error(const std::string &m);
   } while (0)
 
 // ----------------------------------------------------------------- layout
-constexpr int RUNS_PER_BLOCK = 32;  // K: CIGAR runs per 128-byte block / per checkpoint
+constexpr int RUNS_PER_BLOCK = 8;   // K: CIGAR runs per 32-byte block (one DRAM sector) = per checkpoint
 constexpr uint32_t FLAG_STRAND = 1u;    // '-' strand (bit 63 of strand_and_data_offset)
 constexpr uint32_t FLAG_REVERSED = 2u;  // reversed (bidirectional) entry (bit 62)
 constexpr uint32_t INVALID_ID = 0xffffffffu;
@@ -50,7 +50,7 @@ struct __align__(32) EntryRec {
   int32_t q_start, q_end;    // interval on the other sequence
   uint32_t query_id;         // the other sequence
   uint32_t nruns_flags;      // n_runs << 2 | FLAG_REVERSED | FLAG_STRAND
-  uint32_t blk_off;          // first 32-run block of the alignment in the run stream
+  uint32_t blk_off;          // first 8-run block of the alignment in the run stream
   uint32_t ck_off;           // first checkpoint (blk_off + alignment ordinal)
 };
 static_assert(sizeof(EntryRec) == 32, "EntryRec must be one sector");

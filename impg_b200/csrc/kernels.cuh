@@ -71,8 +71,9 @@ __device__ __forceinline__ int warp_incl_scan(int v) {
 }
 
 // ------------------------------------------------------------------ K0
-// One warp per alignment: copy its raw runs into 128-byte blocks (zero padded)
-// and write one checkpoint per block plus the totals.
+// One warp per alignment: copy its raw runs into 8-run (32-byte) blocks, zero
+// padded, and write one checkpoint per block plus the totals. A warp iteration
+// covers 32 runs = 4 blocks; lanes 0, 8, 16, 24 own the checkpoints.
 __global__ void __launch_bounds__(256) k_build_blocks(const uint32_t *__restrict__ raw,
                                                       const uint64_t *__restrict__ run_off,
                                                       const uint32_t *__restrict__ blk_off, uint64_t n_aln,
@@ -87,16 +88,18 @@ __global__ void __launch_bounds__(256) k_build_blocks(const uint32_t *__restrict
     const uint32_t b0 = blk_off[w];
     const uint64_t c0 = (uint64_t)b0 + a;
     const uint32_t nblk = (uint32_t)((n + RUNS_PER_BLOCK - 1) / RUNS_PER_BLOCK);
+    const uint64_t padded = (uint64_t)nblk * RUNS_PER_BLOCK;
     uint32_t t_acc = 0, q_acc = 0;
-    for (uint32_t b = 0; b < nblk; b++) {
-      uint64_t i = (uint64_t)b * RUNS_PER_BLOCK + lane;
-      uint32_t v = i < n ? raw[off + i] : 0u;
-      runs[((uint64_t)b0 + b) * RUNS_PER_BLOCK + lane] = v;
-      uint32_t op = v >> 29, len = v & 0x1fffffffu;
-      int td = op == IMPGX_OP_I ? 0 : (int)len;
-      int qd = op == IMPGX_OP_D ? 0 : (int)len;
-      int ts = warp_incl_scan(td), qs = warp_incl_scan(qd);
-      if (lane == 0) ck[c0 + b] = Checkpoint{t_acc, q_acc};
+    for (uint64_t i0 = 0; i0 < padded; i0 += 32) {
+      const uint64_t i = i0 + lane;
+      const uint32_t v = i < n ? raw[off + i] : 0u;
+      if (i < padded) runs[(uint64_t)b0 * RUNS_PER_BLOCK + i] = v;
+      const uint32_t op = v >> 29, len = v & 0x1fffffffu;
+      const int td = op == IMPGX_OP_I ? 0 : (int)len;
+      const int qd = op == IMPGX_OP_D ? 0 : (int)len;
+      const int ts = warp_incl_scan(td), qs = warp_incl_scan(qd);
+      if ((lane % RUNS_PER_BLOCK) == 0 && i < padded)
+        ck[c0 + i / RUNS_PER_BLOCK] = Checkpoint{t_acc + (uint32_t)(ts - td), q_acc + (uint32_t)(qs - qd)};
       t_acc += (uint32_t)__shfl_sync(FULL, ts, 31);
       q_acc += (uint32_t)__shfl_sync(FULL, qs, 31);
     }
@@ -221,7 +224,7 @@ __device__ __forceinline__ LiftOut lift_one(const EntryRec &rec, const Checkpoin
   const int64_t wq_tot = swap_id ? tot.t_off : tot.q_off;
   const int64_t rel = (int64_t)rs - (int64_t)rec.t_start;  // request start relative to walk start
 
-  // ---- locate the starting block
+  // ---- locate the starting checkpoint (8-run granularity)
   uint32_t pb;  // physical block where the walk starts
   if (!backward) {
     // largest b in [0,nblk) with P(b) < rel, else 0
@@ -252,15 +255,18 @@ __device__ __forceinline__ LiftOut lift_one(const EntryRec &rec, const Checkpoin
   int32_t target_pos = (int32_t)((int64_t)rec.t_start + tcons);
   int32_t query_pos = rev_strand ? (int32_t)((int64_t)rec.q_end - qcons) : (int32_t)((int64_t)rec.q_start + qcons);
 
+  // the warp scans 32 runs per iteration: forward from run `lo`, or backward
+  // below run `hi` (exclusive)
+  uint32_t lo = pb * RUNS_PER_BLOCK;
+  uint32_t hi = min(n, (pb + 1) * RUNS_PER_BLOCK);
   bool found = false;
   int32_t last_rem = 0, first_off = 0;
   for (;;) {
-    // lanes -> ops of this block in walk order
-    const uint32_t base = pb * RUNS_PER_BLOCK;
-    const uint32_t cnt = min((uint32_t)RUNS_PER_BLOCK, n - base);
+    // lanes -> ops in walk order
+    const uint32_t cnt = backward ? min(32u, hi) : min(32u, n - lo);
     const bool valid = lane < cnt;
-    const uint32_t pi = backward ? (cnt - 1 - lane) : lane;  // offset within the block
-    uint32_t v = valid ? blk[base + pi] : 0u;
+    const uint32_t pi = backward ? (hi - 1 - lane) : (lo + lane);  // physical run index
+    uint32_t v = valid ? blk[pi] : 0u;
     o.runs_read += cnt;
     uint32_t op = v >> 29;
     const int32_t len = (int32_t)(v & 0x1fffffffu);
@@ -299,8 +305,8 @@ __device__ __forceinline__ LiftOut lift_one(const EntryRec &rec, const Checkpoin
     }
     const unsigned ovm = __ballot_sync(FULL, ov);
     if (ovm) {
-      // walk-order index of lane l in this block
-      const uint32_t widx0 = backward ? (n - (base + cnt)) : base;
+      // walk-order index of lane 0 in this iteration
+      const uint32_t widx0 = backward ? (n - hi) : lo;
       if (!found) {
         const int fl = __ffs(ovm) - 1;
         o.q_start = __shfl_sync(FULL, pqs, fl);
@@ -332,18 +338,16 @@ __device__ __forceinline__ LiftOut lift_one(const EntryRec &rec, const Checkpoin
         d_ += __shfl_xor_sync(FULL, d_, d);
       }
       o.matches += m_; o.mismatches += x_; o.n_ins += i_; o.n_del += d_;
-    } else {
-      // keep the warp convergent for the ballots above
     }
     if (brk) break;
     target_pos += __shfl_sync(FULL, ts_incl, 31);
     query_pos += __shfl_sync(FULL, qs_incl, 31) * dir;
     if (backward) {
-      if (pb == 0) break;
-      pb--;
+      if (hi <= 32) break;
+      hi -= 32;
     } else {
-      pb++;
-      if (pb >= nblk) break;
+      lo += 32;
+      if (lo >= n) break;
     }
   }
   o.first_off = first_off;
@@ -424,8 +428,8 @@ __global__ void __launch_bounds__(256) k_liftover(DevIndexView ix, const Frontie
 // depends only on the FIRST and the LAST overlapping op (src/impg.rs:2806-2868:
 // projected_*_start are written once, projected_*_end by every overlapping
 // op), so only the run blocks at the two ends of the request are read; their
-// start positions come from the checkpoints. A thread streams a 128-byte block
-// as eight 128-bit loads and evaluates the runs branch-free; there are no
+// start positions come from the checkpoints (one per 8 runs). A thread reads a
+// 32-byte block as two 128-bit loads and evaluates the runs branch-free; there are no
 // shuffles and no intra-warp dependencies, so the kernel is bound by the
 // gather traffic (entry 32 B + checkpoint probes + 2 blocks + hit 32 B).
 // (v1 = warp per hit, 1233 warp-instructions per hit; v2 = 8 lanes per hit,
@@ -457,9 +461,9 @@ __device__ __forceinline__ void thread_eval_block(const uint32_t *__restrict__ b
   const uint32_t base = pb * RUNS_PER_BLOCK;
   const uint32_t cnt = min((uint32_t)RUNS_PER_BLOCK, n - base);
   const uint4 *src = reinterpret_cast<const uint4 *>(blk + base);
-#pragma unroll 2
-  for (int c = 0; c < 8; c++) {
-    const int ci = backward ? 7 - c : c;
+#pragma unroll
+  for (int c = 0; c < RUNS_PER_BLOCK / 4; c++) {
+    const int ci = backward ? RUNS_PER_BLOCK / 4 - 1 - c : c;
     uint4 v4 = src[ci];
     if (backward) {  // walk order within the chunk is reversed too
       uint32_t t0 = v4.x, t1 = v4.y;
@@ -496,7 +500,7 @@ __device__ __forceinline__ void thread_eval_block(const uint32_t *__restrict__ b
   }
 }
 
-__global__ void __launch_bounds__(256, 4) k_liftover_ends(DevIndexView ix, const Frontier *__restrict__ fr,
+__global__ void __launch_bounds__(256, 3) k_liftover_ends(DevIndexView ix, const Frontier *__restrict__ fr,
                                                        const LiftTask *__restrict__ tasks, uint64_t n_tasks,
                                                        LiftParams lp, Hit *__restrict__ hits,
                                                        unsigned long long *__restrict__ counters) {
