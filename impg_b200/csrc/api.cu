@@ -356,7 +356,7 @@ long impgx_debug_host_columns(const impgx_record *records, size_t n, const uint6
       for (size_t i = 0; i < E; i++) {
         e_query_id[i] = hc.e_rec[i].query_id;
         e_flags[i] = hc.e_rec[i].nruns_flags;
-        e_aln[i] = hc.e_rec[i].ck_off - hc.e_rec[i].blk_off;
+        e_aln[i] = hc.e_aln[i];
       }
       memcpy(tgt_off, hc.tgt_off.data(), (n_seqs + 1) * 8);
     }

@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(256) k_emit_cigar_results(DevIndexView ix, Out
     const uint32_t n_runs = rec.nruns_flags >> 2;
     const bool swap_id = rec.nruns_flags & FLAG_REVERSED;
     const bool backward = swap_id && (rec.nruns_flags & FLAG_STRAND);
-    const uint32_t *blk = ix.runs + (uint64_t)rec.blk_off * RUNS_PER_BLOCK;
+    const uint32_t *blk = aln_runs(ix.stream, rec.aln_off, aln_nblk(n_runs));
     for (uint32_t k = lane; k < s.n_ops; k += 32) {
       uint32_t wi = s.first_idx + k;
       uint32_t v = blk[backward ? (n_runs - 1 - wi) : wi];

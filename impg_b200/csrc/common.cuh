@@ -50,8 +50,8 @@ struct __align__(32) EntryRec {
   int32_t q_start, q_end;    // interval on the other sequence
   uint32_t query_id;         // the other sequence
   uint32_t nruns_flags;      // n_runs << 2 | FLAG_REVERSED | FLAG_STRAND
-  uint32_t blk_off;          // first 8-run block of the alignment in the run stream
-  uint32_t ck_off;           // first checkpoint (blk_off + alignment ordinal)
+  uint32_t aln_off;          // the alignment's region in the stream, in 32-byte sectors
+  uint32_t vrank;            // rank of this entry in the coitrees visit order of its target
 };
 static_assert(sizeof(EntryRec) == 32, "EntryRec must be one sector");
 
@@ -60,6 +60,24 @@ static_assert(sizeof(EntryRec) == 32, "EntryRec must be one sector");
 struct __align__(8) Checkpoint {
   uint32_t t_off, q_off;
 };
+
+// Stream layout of one alignment (all in 32-byte sectors, so every block is
+// one DRAM sector and checkpoints sit next to the runs they index):
+//   [ checkpoints 0..nblk (nblk+1 of them, padded to a multiple of 4) ][ nblk run blocks ]
+#if defined(__CUDACC__)
+#define IMPGX_HD __host__ __device__ __forceinline__
+#else
+#define IMPGX_HD inline
+#endif
+IMPGX_HD uint32_t aln_nblk(uint32_t n_runs) { return (n_runs + RUNS_PER_BLOCK - 1) / RUNS_PER_BLOCK; }
+IMPGX_HD uint32_t aln_ck_sectors(uint32_t nblk) { return (nblk + 1 + 3) / 4; }
+IMPGX_HD uint32_t aln_sectors(uint32_t n_runs) { return aln_ck_sectors(aln_nblk(n_runs)) + aln_nblk(n_runs); }
+IMPGX_HD const Checkpoint *aln_ck(const uint32_t *stream, uint32_t aln_off) {
+  return reinterpret_cast<const Checkpoint *>(stream + (uint64_t)aln_off * 8);
+}
+IMPGX_HD const uint32_t *aln_runs(const uint32_t *stream, uint32_t aln_off, uint32_t nblk) {
+  return stream + ((uint64_t)aln_off + aln_ck_sectors(nblk)) * 8;
+}
 
 // One stab hit to lift (output of the stab kernel, input of the liftover kernel).
 struct __align__(8) LiftTask {
@@ -90,12 +108,10 @@ struct DevIndexView {
   const int32_t *e_start;
   const int32_t *e_end;
   const int32_t *e_pmax;    // running max of e_end within the target
-  const uint32_t *e_vrank;  // rank in the coitrees visit order of the target's tree
   const EntryRec *e_rec;
   const uint64_t *tgt_off;  // n_seqs + 1
   const int32_t *seq_len;   // n_seqs
-  const Checkpoint *ck;
-  const uint32_t *runs;     // padded to RUNS_PER_BLOCK per alignment
+  const uint32_t *stream;   // per alignment: checkpoints, then 8-run blocks (see aln_* helpers)
   uint32_t n_seqs;
   uint64_t n_entries;
 };

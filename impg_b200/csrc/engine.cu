@@ -124,7 +124,7 @@ struct WallTimer {
 impgx_index::~impgx_index() {
   cudaSetDevice(device);
   cudaFree(d_start); cudaFree(d_end); cudaFree(d_pmax); cudaFree(d_seq_len);
-  cudaFree(d_vrank); cudaFree(d_runs); cudaFree(d_rec); cudaFree(d_tgt_off); cudaFree(d_ck);
+  cudaFree(d_stream); cudaFree(d_rec); cudaFree(d_tgt_off);
 }
 
 namespace impgx {
@@ -173,26 +173,23 @@ impgx_index *index_build(const impgx_record *recs, size_t n, const uint32_t *run
   HostColumns hc;
   build_host_columns(recs, n, run_offsets, n_seqs, bidirectional, hc);
   idx->n_entries = hc.e_start.size();
-  idx->n_blocks = hc.blk_off[n];
+  idx->n_blocks = hc.aln_off[n];
 
   uint64_t bytes = 0;
   idx->d_start = upload(hc.e_start, bytes);
   idx->d_end = upload(hc.e_end, bytes);
   idx->d_pmax = upload(hc.e_pmax, bytes);
-  idx->d_vrank = upload(hc.e_vrank, bytes);
   idx->d_rec = upload(hc.e_rec, bytes);
   idx->d_tgt_off = upload(hc.tgt_off, bytes);
   std::vector<int32_t> sl(n_seqs);
   for (uint32_t s = 0; s < n_seqs; s++) sl[s] = (int32_t)seq_lens[s];
   idx->d_seq_len = upload(sl, bytes);
 
-  // run stream: padded 32-run blocks + checkpoints, built on the device from
+  // stream: per alignment checkpoints + 8-run blocks, built on the device from
   // the raw runs, uploaded in bounded chunks of alignments
-  const uint64_t n_ck = idx->n_blocks + n + 1;
-  size_t runs_bytes = std::max<uint64_t>(idx->n_blocks, 1) * RUNS_PER_BLOCK * sizeof(uint32_t);
-  CUDA_CHECK(cudaMalloc((void **)&idx->d_runs, runs_bytes));
-  CUDA_CHECK(cudaMalloc((void **)&idx->d_ck, n_ck * sizeof(Checkpoint)));
-  bytes += runs_bytes + n_ck * sizeof(Checkpoint);
+  size_t stream_bytes = std::max<uint64_t>(idx->n_blocks, 1) * 32;
+  CUDA_CHECK(cudaMalloc((void **)&idx->d_stream, stream_bytes));
+  bytes += stream_bytes;
   {
     const uint64_t chunk_runs = 256ull << 20;  // 1 GiB of raw runs per chunk
     uint32_t *d_raw = nullptr;
@@ -224,9 +221,8 @@ impgx_index *index_build(const impgx_record *recs, size_t n, const uint32_t *run
       for (size_t i = 0; i <= na; i++) rel[i] = run_offsets[a + i] - base;
       if (nr) CUDA_CHECK(cudaMemcpy(d_raw, runs + base, nr * 4, cudaMemcpyHostToDevice));
       CUDA_CHECK(cudaMemcpy(d_off, rel.data(), (na + 1) * 8, cudaMemcpyHostToDevice));
-      CUDA_CHECK(cudaMemcpy(d_blk, hc.blk_off.data() + a, (na + 1) * 4, cudaMemcpyHostToDevice));
-      LAUNCH(k_build_blocks, grid_warps(na), 256, 0, d_raw, d_off, d_blk, (uint64_t)na, (uint64_t)a, idx->d_runs,
-             idx->d_ck);
+      CUDA_CHECK(cudaMemcpy(d_blk, hc.aln_off.data() + a, (na + 1) * 4, cudaMemcpyHostToDevice));
+      LAUNCH(k_build_blocks, grid_warps(na), 256, 0, d_raw, d_off, d_blk, (uint64_t)na, idx->d_stream);
       CUDA_CHECK(cudaDeviceSynchronize());
       a = b;
     }
@@ -1064,22 +1060,20 @@ void project_batch(int device, size_t n, const int32_t *req_start, const int32_t
     e.q_start = r.query_start; e.q_end = r.query_end;
     e.query_id = r.query_id;
     e.nruns_flags = ((uint32_t)nr << 2) | (r.strand ? FLAG_STRAND : 0u) | (r.reserved & 1u ? FLAG_REVERSED : 0u);
-    e.blk_off = (uint32_t)blocks;
-    e.ck_off = (uint32_t)(blocks + i);
+    e.aln_off = (uint32_t)blocks;
+    e.vrank = 0;
     recs[i] = e;
-    blocks += (nr + RUNS_PER_BLOCK - 1) / RUNS_PER_BLOCK;
+    blocks += aln_sectors((uint32_t)nr);
     fr[i] = Frontier{(uint32_t)i, r.target_id, req_start[i], req_end[i]};
     tasks[i] = LiftTask{(uint32_t)i, (uint32_t)i};
   }
   blk_off[n] = (uint32_t)blocks;
   const uint64_t total_runs = run_offsets[n];
-  DBuf<uint32_t> d_raw(std::max<uint64_t>(total_runs, 1), arena), d_blk(n + 1, arena), d_runs(std::max<uint64_t>(blocks, 1) * RUNS_PER_BLOCK, arena);
+  DBuf<uint32_t> d_raw(std::max<uint64_t>(total_runs, 1), arena), d_blk(n + 1, arena), d_stream(std::max<uint64_t>(blocks, 1) * 8, arena);
   DBuf<uint64_t> d_off(n + 1, arena);
-  DBuf<Checkpoint> d_ck(blocks + n + 1, arena);
   DBuf<EntryRec> d_rec(n, arena);
   DBuf<Frontier> d_fr(n, arena);
   DBuf<LiftTask> d_tasks(n, arena);
-  DBuf<uint32_t> d_vrank(n, arena);
   DBuf<Hit> d_hits(n, arena);
   DBuf<CigarSlice> d_slices(n, arena);
   if (total_runs) CUDA_CHECK(cudaMemcpyAsync(d_raw.get(), runs, total_runs * 4, cudaMemcpyHostToDevice, s));
@@ -1088,14 +1082,10 @@ void project_batch(int device, size_t n, const int32_t *req_start, const int32_t
   CUDA_CHECK(cudaMemcpyAsync(d_rec.get(), recs.data(), n * sizeof(EntryRec), cudaMemcpyHostToDevice, s));
   CUDA_CHECK(cudaMemcpyAsync(d_fr.get(), fr.data(), n * sizeof(Frontier), cudaMemcpyHostToDevice, s));
   CUDA_CHECK(cudaMemcpyAsync(d_tasks.get(), tasks.data(), n * sizeof(LiftTask), cudaMemcpyHostToDevice, s));
-  CUDA_CHECK(cudaMemsetAsync(d_vrank.get(), 0, n * 4, s));
-  LAUNCH(k_build_blocks, grid_warps(n), 256, s, d_raw.get(), d_off.get(), d_blk.get(), (uint64_t)n, (uint64_t)0,
-         d_runs.get(), d_ck.get());
+  LAUNCH(k_build_blocks, grid_warps(n), 256, s, d_raw.get(), d_off.get(), d_blk.get(), (uint64_t)n, d_stream.get());
   DevIndexView ix{};
   ix.e_rec = d_rec.get();
-  ix.e_vrank = d_vrank.get();
-  ix.ck = d_ck.get();
-  ix.runs = d_runs.get();
+  ix.stream = d_stream.get();
   LiftParams lp{};
   lp.clip = 0;
   lp.min_output_len = -1;

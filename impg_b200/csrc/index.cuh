@@ -13,10 +13,11 @@ namespace impgx {
 // Host-side staging of the entry columns (also used by CPU-only tests).
 struct HostColumns {
   std::vector<int32_t> e_start, e_end, e_pmax;
-  std::vector<uint32_t> e_vrank;
+  std::vector<uint32_t> e_vrank;   // also stored in e_rec
+  std::vector<uint32_t> e_aln;     // alignment ordinal of each entry (host only, tests)
   std::vector<EntryRec> e_rec;
   std::vector<uint64_t> tgt_off;   // n_seqs + 1
-  std::vector<uint32_t> blk_off;   // n_records + 1, in 32-run blocks
+  std::vector<uint32_t> aln_off;   // n_records + 1, stream offset of each alignment in 32-byte sectors
 };
 
 // coitrees 0.4.0 visit order (un-vendored dependency; restated from its
@@ -49,18 +50,17 @@ struct impgx_index {
   std::unordered_map<std::string, uint32_t> name_to_id;
   // device columns
   int32_t *d_start = nullptr, *d_end = nullptr, *d_pmax = nullptr, *d_seq_len = nullptr;
-  uint32_t *d_vrank = nullptr, *d_runs = nullptr;
+  uint32_t *d_stream = nullptr;
   impgx::EntryRec *d_rec = nullptr;
   uint64_t *d_tgt_off = nullptr;
-  impgx::Checkpoint *d_ck = nullptr;
   std::mutex mu;  // one query batch at a time per index (handle is thread-safe)
   impgx::Arena arena;  // device scratch of the query pipeline
   impgx_stats last{};
 
   impgx::DevIndexView view() const {
     impgx::DevIndexView v;
-    v.e_start = d_start; v.e_end = d_end; v.e_pmax = d_pmax; v.e_vrank = d_vrank; v.e_rec = d_rec;
-    v.tgt_off = d_tgt_off; v.seq_len = d_seq_len; v.ck = d_ck; v.runs = d_runs;
+    v.e_start = d_start; v.e_end = d_end; v.e_pmax = d_pmax; v.e_rec = d_rec;
+    v.tgt_off = d_tgt_off; v.seq_len = d_seq_len; v.stream = d_stream;
     v.n_seqs = n_seqs; v.n_entries = n_entries;
     return v;
   }

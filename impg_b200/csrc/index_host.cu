@@ -49,17 +49,17 @@ void visit_ranks(size_t n, uint32_t *rank) {
 
 void build_host_columns(const impgx_record *recs, size_t n, const uint64_t *run_offsets, uint32_t n_seqs,
                         bool bidirectional, HostColumns &out) {
-  // 32-run block offsets per alignment
-  out.blk_off.resize(n + 1);
-  uint64_t blocks = 0;
+  // stream offset (32-byte sectors) of each alignment
+  out.aln_off.resize(n + 1);
+  uint64_t sectors = 0;
   for (size_t i = 0; i < n; i++) {
-    out.blk_off[i] = (uint32_t)blocks;
+    out.aln_off[i] = (uint32_t)sectors;
     uint64_t nr = run_offsets[i + 1] - run_offsets[i];
     REQUIRE(nr < (1ull << 30), IMPGX_E_INVALID, "alignment with >= 2^30 CIGAR runs");
-    blocks += (nr + RUNS_PER_BLOCK - 1) / RUNS_PER_BLOCK;
-    REQUIRE(blocks + n + 1 < (1ull << 32), IMPGX_E_INVALID, "run stream exceeds 2^32 blocks; shard the index");
+    sectors += aln_sectors((uint32_t)nr);
+    REQUIRE(sectors < (1ull << 32), IMPGX_E_INVALID, "run stream exceeds 2^32 sectors (137 GB); shard the index");
   }
-  out.blk_off[n] = (uint32_t)blocks;
+  out.aln_off[n] = (uint32_t)sectors;
 
   // count entries per target
   std::vector<uint64_t> cnt(n_seqs + 1, 0);
@@ -94,6 +94,7 @@ void build_host_columns(const impgx_record *recs, size_t n, const uint64_t *run_
   out.e_end.resize(E);
   out.e_pmax.resize(E);
   out.e_vrank.resize(E);
+  out.e_aln.resize(E);
   out.e_rec.resize(E);
 #pragma omp parallel for schedule(dynamic, 16)
   for (long s = 0; s < (long)n_seqs; s++) {
@@ -118,8 +119,9 @@ void build_host_columns(const impgx_record *recs, size_t n, const uint64_t *run_
       }
       const uint32_t nr = (uint32_t)(run_offsets[ri + 1] - run_offsets[ri]);
       e.nruns_flags = (nr << 2) | (reversed ? FLAG_REVERSED : 0u) | (r.strand ? FLAG_STRAND : 0u);
-      e.blk_off = out.blk_off[ri];
-      e.ck_off = out.blk_off[ri] + ri;
+      e.aln_off = out.aln_off[ri];
+      e.vrank = out.e_vrank[k];
+      out.e_aln[k] = ri;
       out.e_rec[k] = e;
       out.e_start[k] = e.t_start;
       out.e_end[k] = e.t_end;

@@ -71,39 +71,40 @@ __device__ __forceinline__ int warp_incl_scan(int v) {
 }
 
 // ------------------------------------------------------------------ K0
-// One warp per alignment: copy its raw runs into 8-run (32-byte) blocks, zero
-// padded, and write one checkpoint per block plus the totals. A warp iteration
+// One warp per alignment: write its region of the stream — checkpoints first,
+// then the raw runs as zero-padded 8-run (32-byte) blocks. A warp iteration
 // covers 32 runs = 4 blocks; lanes 0, 8, 16, 24 own the checkpoints.
 __global__ void __launch_bounds__(256) k_build_blocks(const uint32_t *__restrict__ raw,
                                                       const uint64_t *__restrict__ run_off,
-                                                      const uint32_t *__restrict__ blk_off, uint64_t n_aln,
-                                                      uint64_t aln_base, uint32_t *__restrict__ runs,
-                                                      Checkpoint *__restrict__ ck) {
+                                                      const uint32_t *__restrict__ aln_off, uint64_t n_aln,
+                                                      uint32_t *__restrict__ stream) {
   const unsigned lane = lane_id();
   uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   for (; w < n_aln; w += nw) {
-    const uint64_t a = aln_base + w;
     const uint64_t off = run_off[w], n = run_off[w + 1] - off;
-    const uint32_t b0 = blk_off[w];
-    const uint64_t c0 = (uint64_t)b0 + a;
-    const uint32_t nblk = (uint32_t)((n + RUNS_PER_BLOCK - 1) / RUNS_PER_BLOCK);
+    const uint32_t nblk = aln_nblk((uint32_t)n);
+    Checkpoint *ck = const_cast<Checkpoint *>(aln_ck(stream, aln_off[w]));
+    uint32_t *runs = const_cast<uint32_t *>(aln_runs(stream, aln_off[w], nblk));
     const uint64_t padded = (uint64_t)nblk * RUNS_PER_BLOCK;
     uint32_t t_acc = 0, q_acc = 0;
     for (uint64_t i0 = 0; i0 < padded; i0 += 32) {
       const uint64_t i = i0 + lane;
       const uint32_t v = i < n ? raw[off + i] : 0u;
-      if (i < padded) runs[(uint64_t)b0 * RUNS_PER_BLOCK + i] = v;
+      if (i < padded) runs[i] = v;
       const uint32_t op = v >> 29, len = v & 0x1fffffffu;
       const int td = op == IMPGX_OP_I ? 0 : (int)len;
       const int qd = op == IMPGX_OP_D ? 0 : (int)len;
       const int ts = warp_incl_scan(td), qs = warp_incl_scan(qd);
       if ((lane % RUNS_PER_BLOCK) == 0 && i < padded)
-        ck[c0 + i / RUNS_PER_BLOCK] = Checkpoint{t_acc + (uint32_t)(ts - td), q_acc + (uint32_t)(qs - qd)};
+        ck[i / RUNS_PER_BLOCK] = Checkpoint{t_acc + (uint32_t)(ts - td), q_acc + (uint32_t)(qs - qd)};
       t_acc += (uint32_t)__shfl_sync(FULL, ts, 31);
       q_acc += (uint32_t)__shfl_sync(FULL, qs, 31);
     }
-    if (lane == 0) ck[c0 + nblk] = Checkpoint{t_acc, q_acc};
+    if (lane == 0) {
+      ck[nblk] = Checkpoint{t_acc, q_acc};
+      for (uint32_t k = nblk + 1; k < aln_ck_sectors(nblk) * 4; k++) ck[k] = Checkpoint{t_acc, q_acc};  // padding
+    }
   }
 }
 
@@ -195,17 +196,17 @@ struct LiftOut {
 //
 // Entry orientation (src/impg.rs:144-156,547-550): a REVERSED entry swaps
 // I<->D, and on the '-' strand also walks the stored runs backwards.
-__device__ __forceinline__ LiftOut lift_one(const EntryRec &rec, const Checkpoint *__restrict__ ckp,
-                                            const uint32_t *__restrict__ runs, int32_t rs, int32_t re) {
+__device__ __forceinline__ LiftOut lift_one(const EntryRec &rec, const uint32_t *__restrict__ stream, int32_t rs,
+                                            int32_t re) {
   const unsigned lane = lane_id();
   const uint32_t n = rec.nruns_flags >> 2;
   const bool rev_strand = rec.nruns_flags & FLAG_STRAND;
   const bool swap_id = rec.nruns_flags & FLAG_REVERSED;
   const bool backward = swap_id && rev_strand;
   const int32_t dir = rev_strand ? -1 : 1;
-  const uint32_t nblk = (n + RUNS_PER_BLOCK - 1) / RUNS_PER_BLOCK;
-  const Checkpoint *ck = ckp + rec.ck_off;
-  const uint32_t *blk = runs + (uint64_t)rec.blk_off * RUNS_PER_BLOCK;
+  const uint32_t nblk = aln_nblk(n);
+  const Checkpoint *ck = aln_ck(stream, rec.aln_off);
+  const uint32_t *blk = aln_runs(stream, rec.aln_off, nblk);
   const int32_t last_target_pos = min(rec.t_end, re);
 
   LiftOut o;
@@ -390,7 +391,7 @@ __global__ void __launch_bounds__(256) k_liftover(DevIndexView ix, const Frontie
       rs = max(rs, rec.t_start);
       re = min(re, rec.t_end);
     }
-    LiftOut o = lift_one(rec, ix.ck, ix.runs, rs, re);
+    LiftOut o = lift_one(rec, ix.stream, rs, re);
     bool ok = o.ok;
     if (ok && lp.use_identity) {
       int32_t total = o.matches + o.mismatches + o.n_ins + o.n_del;
@@ -411,7 +412,7 @@ __global__ void __launch_bounds__(256) k_liftover(DevIndexView ix, const Frontie
       h.t_id = f.seq;
       h.t_first = o.t_start;
       h.t_last = o.t_end;
-      h.vrank = ix.e_vrank[t.entry];
+      h.vrank = rec.vrank;
       hits[w] = h;
       if (slices) slices[w] = CigarSlice{o.first_idx, ok ? o.last_idx - o.first_idx : 0u, o.first_off, o.last_rem};
     }
@@ -435,14 +436,51 @@ __global__ void __launch_bounds__(256) k_liftover(DevIndexView ix, const Frontie
 // (v1 = warp per hit, 1233 warp-instructions per hit; v2 = 8 lanes per hit,
 // 391; both were instruction-issue bound — see profiles/.)
 
-// first index b in [lo, hi) with !(P(b) < x) (strict) / !(P(b) <= x), P nondecreasing
+// first index b in [lo, hi) with !(P(b) < x) (strict) / !(P(b) <= x); P is
+// nondecreasing. Galloping search from `guess`: alignments have a near-uniform
+// run density, so an interpolated guess is within a few checkpoints of the
+// answer and the probes stay inside one or two 32-byte sectors (a plain binary
+// search touched ~7 different sectors per lookup and dominated the DRAM
+// traffic of the kernel).
 __device__ __forceinline__ uint32_t ck_partition(const Checkpoint *__restrict__ ck, bool swap_id, uint32_t lo,
-                                                 uint32_t hi, int64_t x, bool inclusive) {
+                                                 uint32_t hi, int64_t x, bool inclusive, uint32_t guess) {
+  if (lo >= hi) return lo;
+  auto pred = [&](uint32_t i) {
+    const Checkpoint v = ck[i];
+    const int64_t p = swap_id ? v.q_off : v.t_off;
+    return inclusive ? p <= x : p < x;
+  };
+  uint32_t g = guess < lo ? lo : (guess >= hi ? hi - 1 : guess);
+  if (pred(g)) {  // answer in (g, hi]
+    lo = g + 1;
+    uint32_t step = 1;
+    while (lo < hi) {
+      const uint32_t m = (hi - lo > step) ? lo + step - 1 : hi - 1;
+      if (pred(m)) {
+        lo = m + 1;
+        step <<= 1;
+      } else {
+        hi = m;
+        break;
+      }
+    }
+  } else {  // answer in [lo, g]
+    hi = g;
+    uint32_t step = 1;
+    while (hi > lo) {
+      const uint32_t m = (hi - lo > step) ? hi - step : lo;
+      if (!pred(m)) {
+        hi = m;
+        step <<= 1;
+      } else {
+        lo = m + 1;
+        break;
+      }
+    }
+  }
   while (lo < hi) {
     const uint32_t mid = lo + ((hi - lo) >> 1);
-    const Checkpoint v = ck[mid];
-    const int64_t p = swap_id ? v.q_off : v.t_off;
-    const bool t = inclusive ? p <= x : p < x;
+    const bool t = pred(mid);
     lo = t ? mid + 1 : lo;
     hi = t ? hi : mid;
   }
@@ -512,7 +550,7 @@ __global__ void __launch_bounds__(256, 3) k_liftover_ends(DevIndexView ix, const
     const uint4 *rp = reinterpret_cast<const uint4 *>(ix.e_rec + t.entry);
     const uint4 r0 = rp[0], r1 = rp[1];
     const int32_t t_start = (int32_t)r0.x, t_end = (int32_t)r0.y, q_start = (int32_t)r0.z, q_end = (int32_t)r0.w;
-    const uint32_t query_id = r1.x, nruns_flags = r1.y, blk_off = r1.z, ck_off = r1.w;
+    const uint32_t query_id = r1.x, nruns_flags = r1.y, aln_off = r1.z, vrank = r1.w;
     int32_t rs = f.start, re = f.end;
     if (lp.clip) {
       rs = max(rs, t_start);
@@ -523,9 +561,9 @@ __global__ void __launch_bounds__(256, 3) k_liftover_ends(DevIndexView ix, const
     const bool swap_id = nruns_flags & FLAG_REVERSED;
     const bool backward = swap_id && rev_strand;
     const int32_t dir = rev_strand ? -1 : 1;
-    const uint32_t nblk = (n + RUNS_PER_BLOCK - 1) / RUNS_PER_BLOCK;
-    const Checkpoint *ck = ix.ck + ck_off;
-    const uint32_t *blk = ix.runs + (uint64_t)blk_off * RUNS_PER_BLOCK;
+    const uint32_t nblk = aln_nblk(n);
+    const Checkpoint *ck = aln_ck(ix.stream, aln_off);
+    const uint32_t *blk = aln_runs(ix.stream, aln_off, nblk);
     const int32_t last_target_pos = min(t_end, re);
     const int64_t rel = (int64_t)rs - t_start, rel_l = (int64_t)last_target_pos - t_start;
 
@@ -535,23 +573,35 @@ __global__ void __launch_bounds__(256, 3) k_liftover_ends(DevIndexView ix, const
     acc.broke = false;
     uint32_t nread = 0, nck = 0;
     if (nblk > 0 && rel_l >= 0) {
-      const Checkpoint tot = ck[nblk];
-      const int64_t w_tot = swap_id ? tot.q_off : tot.t_off, wq_tot = swap_id ? tot.t_off : tot.q_off;
+      // totals: needed exactly only when walking backwards; otherwise the record's
+      // own span is a good enough denominator for the interpolation guess
+      int64_t w_tot = (int64_t)t_end - t_start, wq_tot = 0;
+      if (backward) {
+        const Checkpoint tot = ck[nblk];
+        w_tot = swap_id ? tot.q_off : tot.t_off;
+        wq_tot = swap_id ? tot.t_off : tot.q_off;
+      }
+      const float scale = (float)nblk / (float)(w_tot > 0 ? w_tot : 1);
       // walk blocks j in [0, nblk): js = last block starting before rs, je = last block starting at or before L
       uint32_t js, je;
       if (!backward) {
-        const uint32_t a = ck_partition(ck, swap_id, 0, nblk, rel, false);
-        const uint32_t b = ck_partition(ck, swap_id, a ? a - 1 : 0, nblk, rel_l, true);
+        const uint32_t g0 = rel > 0 ? (uint32_t)((float)rel * scale) : 0u;
+        const uint32_t a = ck_partition(ck, swap_id, 0, nblk, rel, false, g0);
         js = a ? a - 1 : 0;
+        const uint32_t g1 = js + (uint32_t)((float)(rel_l - (rel > 0 ? rel : 0)) * scale) + 1;
+        const uint32_t b = ck_partition(ck, swap_id, js, nblk, rel_l, true, g1);
         je = b ? b - 1 : 0;
       } else {
         // walk block j starts at W - P(nblk - j):  #{j : W - P(nblk-j) < rel} = nblk - #{b in [1,nblk] : P(b) <= W - rel}
-        const uint32_t a = nblk - (ck_partition(ck, swap_id, 1, nblk + 1, w_tot - rel, true) - 1);
-        const uint32_t b = nblk - (ck_partition(ck, swap_id, 1, nblk + 1, w_tot - rel_l, false) - 1);
+        const int64_t x0 = w_tot - rel, x1 = w_tot - rel_l;
+        const uint32_t g0 = x0 > 0 ? (uint32_t)((float)x0 * scale) : 0u;
+        const uint32_t a = nblk - (ck_partition(ck, swap_id, 1, nblk + 1, x0, true, g0) - 1);
+        const uint32_t g1 = x1 > 0 ? (uint32_t)((float)x1 * scale) : 0u;
+        const uint32_t b = nblk - (ck_partition(ck, swap_id, 1, nblk + 1, x1, false, g1) - 1);
         js = a ? a - 1 : 0;
         je = b ? b - 1 : 0;
       }
-      nck = 2 * (32 - __clz(nblk | 1)) + 3;
+      nck = 8;  // ~2 sectors of checkpoints per lookup (galloping from an interpolated guess)
       // ---- start side: walk forward from block js until the first overlap (or the loop break)
       uint32_t j = js;
       for (;;) {
@@ -604,7 +654,7 @@ __global__ void __launch_bounds__(256, 3) k_liftover_ends(DevIndexView ix, const
     h.t_id = f.seq;
     h.t_first = acc.f_t;
     h.t_last = acc.l_t;
-    h.vrank = ix.e_vrank[t.entry];
+    h.vrank = vrank;
     hits[w] = h;
   }
   // one atomic per warp
@@ -637,7 +687,7 @@ __global__ void __launch_bounds__(256) k_emit_cigar(DevIndexView ix, const LiftT
     const uint32_t n = rec.nruns_flags >> 2;
     const bool swap_id = rec.nruns_flags & FLAG_REVERSED;
     const bool backward = swap_id && (rec.nruns_flags & FLAG_STRAND);
-    const uint32_t *blk = ix.runs + (uint64_t)rec.blk_off * RUNS_PER_BLOCK;
+    const uint32_t *blk = aln_runs(ix.stream, rec.aln_off, aln_nblk(n));
     uint32_t *dst = out + out_off[w];
     for (uint32_t k = lane; k < s.n_ops; k += 32) {
       uint32_t wi = s.first_idx + k;
