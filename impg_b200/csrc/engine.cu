@@ -262,6 +262,16 @@ struct LevelHits {
   uint64_t n = 0;
 };
 
+// Collector of the direct BED path: boxes of every result of the batch.
+struct BedSink {
+  DBuf<BoxD> boxes;
+  DBuf<unsigned long long> counters;  // [0] valid boxes, [1] stage-A roots
+  uint64_t prefix = 0;                // slots reserved for the seeds and the earlier (sorted) levels
+  uint64_t n = 0;                     // slots in use
+  uint32_t level = 0;                 // ord level of the raw (last) hop
+  bool filled = false;
+};
+
 struct BatchOut {
   // device columns of the assembled results
   DBuf<uint64_t> row_off;
@@ -297,7 +307,8 @@ class Runner {
   DBuf<unsigned long long> d_counters_;
   cudaEvent_t ev_[2] = {nullptr, nullptr};
 
-  void stab_and_lift(const DBuf<Frontier> &fr, uint64_t nF, bool closed, bool clip, bool need_order, LevelHits &lvl);
+  void stab_and_lift(const DBuf<Frontier> &fr, uint64_t nF, bool closed, bool clip, BedSink *sink, LevelHits &lvl);
+  void bed_merge_direct(BedSink &sink, uint32_t n_rows, BatchOut &out);
   void fold(const LevelHits &lvl, uint32_t n_rows, Visited &V, DBuf<Frontier> &next, uint64_t &n_next);
   void assemble(const impgx_range *d_ranges, uint32_t n_rows, std::vector<LevelHits> &levels, bool query_mode,
                 BatchOut &out);
@@ -307,7 +318,7 @@ class Runner {
 
 // stab (count, scan, fill) + liftover of one frontier; leaves the accepted
 // hits ordered by (frontier index, visit rank) in lvl.
-void Runner::stab_and_lift(const DBuf<Frontier> &fr, uint64_t nF, bool closed, bool clip, bool need_order,
+void Runner::stab_and_lift(const DBuf<Frontier> &fr, uint64_t nF, bool closed, bool clip, BedSink *sink,
                            LevelHits &lvl) {
   lvl.n = 0;
   if (nF == 0) return;
@@ -335,7 +346,8 @@ void Runner::stab_and_lift(const DBuf<Frontier> &fr, uint64_t nF, bool closed, b
     return;
   }
   // outputs that survive this function go below the temporaries (stack-discipline arena)
-  lvl.hits.alloc(H, ar_);
+  if (sink) sink->boxes.alloc(sink->prefix + H, ar_);
+  else lvl.hits.alloc(H, ar_);
   if (p_.store_cigar) {
     lvl.entry.alloc(H, ar_);
     lvl.slices.alloc(H, ar_);
@@ -386,13 +398,18 @@ void Runner::stab_and_lift(const DBuf<Frontier> &fr, uint64_t nF, bool closed, b
   else ctx.lift_bytes += H * (8 + 16 + 32 + 16 + 32 + (p_.store_cigar ? 16 : 0)) + cnt[0] * 4;
   const uint64_t n_ok = cnt[1];
   lvl.n = n_ok;
-  if (n_ok == 0) return;
+  if (n_ok == 0 && !sink) return;
   wt.reset(new WallTimer(ctx.w_order));
 
-  if (!need_order) {
-    // BED fast path for the last hop: order is carried by (range, vrank) keys
-    // inside the merge; here only compaction would be needed. Kept simple:
-    // fall through to the ordered path (a later round replaces this by binning).
+  if (sink) {
+    // direct BED path, last hop: no ordering sort — the reference order travels
+    // as (range, visit rank) inside each box
+    LAUNCH(k_boxes_from_raw_level, grid_threads(H), 256, s_, hits.get(), tasks.get(), H, sink->level,
+           p_.min_output_length, sink->boxes.get() + sink->prefix, sink->counters.get());
+    sink->n = sink->prefix + H;
+    sink->filled = true;
+    lvl.n = 0;
+    return;
   }
   DBuf<uint64_t> keys(H, ar_);
   DBuf<uint32_t> perm(H, ar_);
@@ -647,9 +664,24 @@ void Runner::run(const impgx_range *d_ranges, uint32_t n_rows, bool bed, BatchOu
   uint64_t nF = n_rows;
   std::vector<LevelHits> levels;
 
+  // direct BED path: boxes straight from the hits (no raw result assembly)
+  const bool direct = bed && !getenv("IMPGX_BED_GENERIC");
+  BedSink sink;
+  uint64_t prior = 0;  // hits held by the sorted levels so far
+  if (direct) {
+    sink.counters.alloc(2, ar_);
+    CUDA_CHECK(cudaMemsetAsync(sink.counters.get(), 0, 16, s_));
+  }
+  auto sink_for = [&](uint32_t level) -> BedSink * {
+    if (!direct || nF >= (1ull << 26) || level >= 58) return nullptr;
+    sink.prefix = (uint64_t)n_rows + prior;
+    sink.level = level + 1;
+    return &sink;
+  };
+
   if (p_.mode == IMPGX_MODE_QUERY) {
     levels.emplace_back();
-    stab_and_lift(fr, nF, /*closed=*/true, /*clip=*/false, /*need_order=*/true, levels.back());
+    stab_and_lift(fr, nF, /*closed=*/true, /*clip=*/false, sink_for(0), levels.back());
   } else {
     // seed: visited[target].insert(range) on an empty set returns the range
     // itself (bounds were validated), which is output and, if long enough,
@@ -678,16 +710,37 @@ void Runner::run(const impgx_range *d_ranges, uint32_t n_rows, bool bed, BatchOu
     }
     uint32_t depth = 0;
     while (nF > 0 && (p_.max_depth == 0 || depth < p_.max_depth)) {
+      const bool last = p_.max_depth != 0 && depth + 1 >= p_.max_depth;
       levels.emplace_back();
-      stab_and_lift(fr, nF, /*closed=*/false, /*clip=*/true, /*need_order=*/true, levels.back());
+      stab_and_lift(fr, nF, /*closed=*/false, /*clip=*/true, last ? sink_for(depth) : nullptr, levels.back());
+      prior += levels.back().n;
       depth++;
-      const bool last = p_.max_depth != 0 && depth >= p_.max_depth;
       DBuf<Frontier> next;
       uint64_t n_next = 0;
       if (!last) fold(levels.back(), n_rows, V, next, n_next);
       fr = std::move(next);
       nF = n_next;
     }
+  }
+  if (direct && levels.size() < 60) {
+    WallTimer wt(ctx.w_assemble);
+    if (!sink.filled) {
+      sink.prefix = (uint64_t)n_rows + prior;
+      sink.boxes.alloc(sink.prefix, ar_);
+      sink.n = sink.prefix;
+    }
+    // seeds, then the levels that were ordered for the fold (their index is their ordinal)
+    LAUNCH(k_boxes_from_seeds, grid_threads(n_rows), 256, s_, d_ranges, n_rows, p_.min_output_length,
+           p_.mode == IMPGX_MODE_QUERY ? 1 : 0, sink.boxes.get(), sink.counters.get());
+    uint64_t off = n_rows;
+    for (size_t l = 0; l < levels.size(); l++) {
+      if (!levels[l].n) continue;
+      LAUNCH(k_boxes_from_sorted_level, grid_threads(levels[l].n), 256, s_, levels[l].hits.get(), levels[l].n,
+             (uint32_t)l + 1, p_.min_output_length, sink.boxes.get() + off, sink.counters.get());
+      off += levels[l].n;
+    }
+    bed_merge_direct(sink, n_rows, out);
+    return;
   }
   BatchOut raw;
   assemble(d_ranges, n_rows, levels, p_.mode == IMPGX_MODE_QUERY, bed ? raw : out);
@@ -814,6 +867,113 @@ void Runner::bed_merge(BatchOut &raw, uint32_t n_rows, BatchOut &out) {
     } else {
       alloc_out(nB);
       LAUNCH(k_boxes_to_cols, grid_threads(nB), 256, s_, boxes.get(), nB, oc, row_cnt.get());
+    }
+    LAUNCH(k_u32_to_u64, grid_threads(n_rows), 256, s_, row_cnt.get(), n_rows, out.row_off.get());
+    exclusive_scan_u64(out.row_off.get(), (uint64_t)n_rows + 1, sc_, s_);
+    ctx.launches += 2;
+  }
+  CUDA_CHECK(cudaEventRecord(e1, s_));
+  CUDA_CHECK(cudaStreamSynchronize(s_));
+  float msf = 0;
+  cudaEventElapsedTime(&msf, e0, e1);
+  ctx.merge_ms += msf;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+}
+
+
+// output_results_bed's two merges straight from the boxes of the batch.
+void Runner::bed_merge_direct(BedSink &sink, uint32_t n_rows, BatchOut &out) {
+  WallTimer wt(ctx.w_merge);
+  cudaEvent_t e0, e1;
+  CUDA_CHECK(cudaEventCreate(&e0));
+  CUDA_CHECK(cudaEventCreate(&e1));
+  CUDA_CHECK(cudaEventRecord(e0, s_));
+  const int32_t d = p_.merge_distance;
+  const bool ms = p_.merge_strands != 0;
+  const uint64_t nB = sink.n;
+  DBuf<uint32_t> row_cnt(n_rows, ar_);
+  CUDA_CHECK(cudaMemsetAsync(row_cnt.get(), 0, (size_t)n_rows * 4, s_));
+  out.row_off.alloc(n_rows + 1, ar_);
+  CUDA_CHECK(cudaMemsetAsync(out.row_off.get(), 0, ((size_t)n_rows + 1) * 8, s_));
+  out.n_results = 0;
+  unsigned long long nv = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&nv, sink.counters.get(), 8, cudaMemcpyDeviceToHost, s_));
+  CUDA_CHECK(cudaStreamSynchronize(s_));
+  ctx.d2h_bytes += 8;
+  OutCols oc;
+  oc.cig_len = nullptr; oc.src_entry = nullptr; oc.src_slice = nullptr;
+  auto alloc_out = [&](uint64_t n) {
+    out.n_results = n;
+    out.q_id.alloc(n, ar_); out.t_id.alloc(n, ar_);
+    out.q_first.alloc(n, ar_); out.q_last.alloc(n, ar_);
+    out.t_first.alloc(n, ar_); out.t_last.alloc(n, ar_);
+    oc.q_id = out.q_id.get(); oc.q_first = out.q_first.get(); oc.q_last = out.q_last.get();
+    oc.t_id = out.t_id.get(); oc.t_first = out.t_first.get(); oc.t_last = out.t_last.get();
+  };
+  if (nv > 0) {
+    REQUIRE(nB < (1ull << 32), IMPGX_E_INVALID, "more than 2^32 results in one batch; lower IMPGX_ROWS_PER_BATCH");
+    const int row_bits = bits_for(n_rows > 1 ? n_rows - 1 : 1);
+    const int seq_bits = bits_for(ix_.n_seqs > 1 ? ix_.n_seqs - 1 : 1);
+    if (d < 0 && !ms) {
+      // nothing merges and nothing is sorted (src/main.rs:12479,12859): reference order per row
+      DBuf<uint64_t> k1(nB, ar_);
+      DBuf<uint32_t> perm(nB, ar_);
+      LAUNCH(k_bd_key_ord, grid_threads(nB), 256, s_, sink.boxes.get(), nB, k1.get(), perm.get());
+      sort_pairs(k1, perm, nB, 0, 64, sc_, s_, ctx);
+      DBuf<uint64_t> k2(nB, ar_);
+      LAUNCH(k_bd_key_row, grid_threads(nB), 256, s_, sink.boxes.get(), perm.get(), nB, n_rows, k2.get());
+      sort_pairs(k2, perm, nB, 0, bits_for(n_rows), sc_, s_, ctx);
+      alloc_out(nv);
+      LAUNCH(k_boxd_to_cols, grid_threads(nv), 256, s_, sink.boxes.get(), perm.get(), (uint64_t)nv, oc, row_cnt.get());
+    } else {
+      const int bits_a = row_bits + 2 * seq_bits + 1, bits_b = row_bits + seq_bits + 33;
+      REQUIRE(bits_a <= 63 && bits_b <= 63, IMPGX_E_INVALID,
+              "batch too large for the packed merge keys; lower IMPGX_ROWS_PER_BATCH");
+      // ---- stage A: group by (row, q, t, strand), pairwise union-find
+      DBuf<BoxD> acc(nv, ar_);
+      DBuf<uint64_t> is_root(nv, ar_);
+      {
+        DBuf<uint64_t> ka(nB, ar_);
+        DBuf<uint32_t> perm(nB, ar_);
+        LAUNCH(k_bd_key_a, grid_threads(nB), 256, s_, sink.boxes.get(), nB, seq_bits, 1ull << bits_a, ka.get(),
+               perm.get());
+        sort_pairs(ka, perm, nB, 0, bits_a + 1, sc_, s_, ctx);
+        Groups g;
+        build_groups(ka.get(), nv, g, sc_, s_, ctx);
+        DBuf<uint32_t> parent(nv, ar_);
+        LAUNCH(k_merge2d_direct, grid_threads(g.G, 128, 16), 128, s_, sink.boxes.get(), perm.get(), g.begins.get(), g.G,
+               (int64_t)d, parent.get(), acc.get(), is_root.get());
+      }
+      // ---- stage B: sort by (row, q, start, strand), sweep per (row, q)
+      DBuf<uint64_t> kb(nv, ar_);
+      DBuf<uint32_t> permb(nv, ar_);
+      LAUNCH(k_bd_key_b, grid_threads(nv), 256, s_, acc.get(), is_root.get(), (uint64_t)nv, seq_bits, 1ull << bits_b,
+             kb.get(), permb.get(), sink.counters.get() + 1);
+      sort_pairs(kb, permb, nv, 0, bits_b + 1, sc_, s_, ctx);
+      unsigned long long nr = 0;
+      CUDA_CHECK(cudaMemcpyAsync(&nr, sink.counters.get() + 1, 8, cudaMemcpyDeviceToHost, s_));
+      CUDA_CHECK(cudaStreamSynchronize(s_));
+      ctx.d2h_bytes += 8;
+      DBuf<BoxD> sorted(nr, ar_);
+      LAUNCH(k_gather<BoxD>, grid_threads(nr), 256, s_, acc.get(), permb.get(), (uint64_t)nr, sorted.get());
+      DBuf<uint64_t> seg(nr, ar_);
+      LAUNCH(k_keys_shift, grid_threads(nr), 256, s_, kb.get(), (uint64_t)nr, 33, seg.get());
+      Groups g;
+      build_groups(seg.get(), nr, g, sc_, s_, ctx);
+      DBuf<BoxD> swept(nr, ar_);
+      DBuf<uint32_t> cnt(g.G, ar_);
+      LAUNCH(k_sweep_direct, grid_threads(g.G, 128, 16), 128, s_, sorted.get(), kb.get(), g.begins.get(), g.G, d,
+             ms ? 1 : 0, swept.get(), cnt.get());
+      DBuf<uint64_t> scan(g.G + 1, ar_);
+      CUDA_CHECK(cudaMemsetAsync(scan.get() + g.G, 0, 8, s_));
+      LAUNCH(k_u32_to_u64, grid_threads(g.G), 256, s_, cnt.get(), g.G, scan.get());
+      exclusive_scan_u64(scan.get(), g.G + 1, sc_, s_);
+      ctx.launches += 2;
+      const uint64_t M = read_u64(scan.get() + g.G, s_, ctx);
+      alloc_out(M);
+      LAUNCH(k_sweep_compact_direct, grid_threads(g.G), 256, s_, swept.get(), g.begins.get(), cnt.get(), scan.get(), g.G,
+             oc, row_cnt.get());
     }
     LAUNCH(k_u32_to_u64, grid_threads(n_rows), 256, s_, row_cnt.get(), n_rows, out.row_off.get());
     exclusive_scan_u64(out.row_off.get(), (uint64_t)n_rows + 1, sc_, s_);

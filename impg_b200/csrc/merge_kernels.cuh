@@ -259,3 +259,265 @@ __global__ void k_boxes_to_cols(const Box *__restrict__ b, uint64_t n, OutCols o
 }
 
 }  // namespace impgx
+
+// ===================================================================
+// Direct BED path: the two merges straight from the lifted hits, without
+// materialising the raw per-row result list. Reference order is carried by a
+// 64-bit ordinal per result (`ord`): it is only needed to break ties exactly
+// as the reference's stable sorts would.
+namespace impgx {
+
+struct __align__(8) BoxD {
+  int32_t q_lo, q_hi, t_lo, t_hi;
+  uint32_t q_id, t_id, row, valid;
+  uint64_t ord;  // position in the reference's result order of the row: level << 58 | (range << 32 | vrank) or index
+};
+
+__device__ __forceinline__ uint64_t make_ord(uint32_t level, uint64_t low) { return ((uint64_t)level << 58) | low; }
+
+__global__ void k_boxes_from_seeds(const impgx_range *__restrict__ ranges, uint32_t n, int32_t min_out, int apply_len,
+                                   BoxD *__restrict__ out, unsigned long long *__restrict__ n_valid) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) {
+    impgx_range r = ranges[i];
+    bool ok = true;
+    if (apply_len && min_out >= 0) ok = (r.end - r.start) >= min_out;
+    out[i] = BoxD{r.start, r.end, r.start, r.end, r.target_id, r.target_id, (uint32_t)i, ok ? 1u : 0u, make_ord(0, 0)};
+    if (ok) atomicAdd(n_valid, 1ull);
+  }
+}
+
+// hits already in reference order (levels that were sorted for the fold)
+__global__ void k_boxes_from_sorted_level(const Hit *__restrict__ hits, uint64_t n, uint32_t level, int32_t min_out,
+                                          BoxD *__restrict__ out, unsigned long long *__restrict__ n_valid) {
+  unsigned long long c = 0;
+  for (uint64_t i = gtid(); i < n; i += gstride()) {
+    Hit h = hits[i];
+    bool ok = passes_len(h, min_out);
+    out[i] = BoxD{h.q_first, h.q_last, h.t_first, h.t_last, h.q_id, h.t_id, h.row, ok ? 1u : 0u, make_ord(level, i)};
+    c += ok ? 1 : 0;
+  }
+  if (c) atomicAdd(n_valid, c);
+}
+
+// hits of the last level in task order (frontier range, sorted position); ord from (range, visit rank)
+__global__ void k_boxes_from_raw_level(const Hit *__restrict__ hits, const LiftTask *__restrict__ tasks, uint64_t n,
+                                       uint32_t level, int32_t min_out, BoxD *__restrict__ out,
+                                       unsigned long long *__restrict__ n_valid) {
+  unsigned long long c = 0;
+  for (uint64_t i = gtid(); i < n; i += gstride()) {
+    Hit h = hits[i];
+    bool ok = h.row != INVALID_ID && passes_len(h, min_out);
+    out[i] = BoxD{h.q_first, h.q_last, h.t_first, h.t_last, h.q_id, h.t_id, h.row, ok ? 1u : 0u,
+                  make_ord(level, ((uint64_t)tasks[i].range << 32) | h.vrank)};
+    c += ok ? 1 : 0;
+  }
+  if (c) atomicAdd(n_valid, c);
+}
+
+// stage A key: (row, q_id, t_id, strand); invalid boxes sort last
+__global__ void k_bd_key_a(const BoxD *__restrict__ b, uint64_t n, int seq_bits, uint64_t invalid_key,
+                           uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) {
+    BoxD x = b[i];
+    bool fwd = x.q_lo <= x.q_hi;
+    keys[i] = x.valid ? (((((uint64_t)x.row << seq_bits | x.q_id) << seq_bits | x.t_id) << 1) | (fwd ? 1u : 0u)) : invalid_key;
+    vals[i] = (uint32_t)i;
+  }
+}
+
+// merge_adjusted_intervals_gap_2d (src/main.rs:12858-13011) on an UNSORTED
+// group: the reference sorts the group by (q.first | -q.first, input order) and
+// scans pairs a < b; the relation tested for a pair does not depend on the
+// other members (its `break` only prunes pairs that fail q_gap <= d anyway on
+// the forward strand and never fires on the reverse strand, where
+// qb.last < qb.first <= qa.first), so the partition is a pure pairwise
+// property; `a` is the member with the smaller (sort key, ord).
+__global__ void __launch_bounds__(128) k_merge2d_direct(const BoxD *__restrict__ boxes, const uint32_t *__restrict__ perm,
+                                                        const uint32_t *__restrict__ begins, uint64_t n_groups, int64_t d,
+                                                        uint32_t *__restrict__ parent, BoxD *__restrict__ acc,
+                                                        uint64_t *__restrict__ is_root) {
+  for (uint64_t g = gtid(); g < n_groups; g += gstride()) {
+    const uint32_t b = begins[g], e = begins[g + 1];
+    if (e - b == 1 || d < 0) {  // singleton (the common case), or merging disabled (:12859)
+      for (uint32_t a = b; a < e; a++) {
+        acc[a] = boxes[perm[a]];
+        is_root[a] = 1;
+      }
+      continue;
+    }
+    for (uint32_t a = b; a < e; a++) {
+      parent[a] = a;
+      is_root[a] = 0;
+    }
+    const BoxD first = boxes[perm[b]];
+    const bool fwd = first.q_lo <= first.q_hi;
+    for (uint32_t i = b; i < e; i++) {
+      const BoxD X = boxes[perm[i]];
+      const int64_t kx = fwd ? (int64_t)X.q_lo : -(int64_t)X.q_lo;
+      for (uint32_t j = i + 1; j < e; j++) {
+        const BoxD Y = boxes[perm[j]];
+        const int64_t ky = fwd ? (int64_t)Y.q_lo : -(int64_t)Y.q_lo;
+        const bool x_first = kx < ky || (kx == ky && X.ord < Y.ord);
+        const BoxD &A = x_first ? X : Y;
+        const BoxD &B = x_first ? Y : X;
+        const int64_t qa_start = fwd ? A.q_lo : A.q_hi, qa_end = fwd ? A.q_hi : A.q_lo;
+        const int64_t qb_start = fwd ? B.q_lo : B.q_hi;
+        if (qb_start < qa_start) continue;
+        if (qb_start - qa_end > d) continue;
+        int64_t t_gap;
+        bool t_forward;
+        if (fwd) {
+          t_gap = (int64_t)B.t_lo - A.t_hi;
+          t_forward = B.t_lo > A.t_lo;
+        } else {
+          t_gap = (int64_t)A.t_lo - B.t_hi;
+          t_forward = B.t_hi < A.t_hi;
+        }
+        if (!t_forward || t_gap > d) continue;
+        uint32_t ra = uf_find(parent, i), rb = uf_find(parent, j);
+        if (ra != rb) parent[ra] = rb;
+      }
+    }
+    for (uint32_t a = b; a < e; a++) {
+      const uint32_t rt = uf_find(parent, a);
+      const BoxD X = boxes[perm[a]];
+      if (!is_root[rt]) {
+        is_root[rt] = 1;
+        acc[rt] = X;
+      } else {
+        BoxD bx = acc[rt];
+        if (fwd) {
+          bx.q_lo = min(bx.q_lo, X.q_lo);
+          bx.q_hi = max(bx.q_hi, X.q_hi);
+        } else {
+          bx.q_lo = max(bx.q_lo, X.q_lo);
+          bx.q_hi = min(bx.q_hi, X.q_hi);
+        }
+        bx.t_lo = min(bx.t_lo, X.t_lo);
+        bx.t_hi = max(bx.t_hi, X.t_hi);
+        bx.ord = min(bx.ord, X.ord);  // output order = first member in input order (:12948-12958)
+        acc[rt] = bx;
+      }
+    }
+  }
+}
+
+// stage B key: (row, q_id, start, !is_forward) — src/main.rs:12481-12494
+__global__ void k_bd_key_b(const BoxD *__restrict__ acc, const uint64_t *__restrict__ is_root, uint64_t n, int seq_bits,
+                           uint64_t invalid_key, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals,
+                           unsigned long long *__restrict__ n_roots) {
+  unsigned long long c = 0;
+  for (uint64_t i = gtid(); i < n; i += gstride()) {
+    if (!is_root[i]) {
+      keys[i] = invalid_key;
+      vals[i] = (uint32_t)i;
+      continue;
+    }
+    c++;
+    BoxD x = acc[i];
+    bool fwd = x.q_lo <= x.q_hi;
+    uint32_t start = (uint32_t)(fwd ? x.q_lo : x.q_hi);
+    keys[i] = ((((uint64_t)x.row << seq_bits | x.q_id) << 32 | start) << 1) | (fwd ? 0u : 1u);
+    vals[i] = (uint32_t)i;
+  }
+  if (c) atomicAdd(n_roots, c);
+}
+
+// one thread per (row, q_id) segment: restore the reference's tie order (equal
+// (start, strand) keys are ordered by ord, as its stable sort leaves them),
+// then the literal sweep of src/main.rs:12496-12556.
+__global__ void __launch_bounds__(128) k_sweep_direct(BoxD *__restrict__ sorted, const uint64_t *__restrict__ keys,
+                                                      const uint32_t *__restrict__ begins, uint64_t n_groups,
+                                                      int32_t merge_distance, int merge_strands, BoxD *__restrict__ out,
+                                                      uint32_t *__restrict__ out_cnt) {
+  for (uint64_t g = gtid(); g < n_groups; g += gstride()) {
+    const uint32_t b = begins[g], e = begins[g + 1];
+    // tie fix-up: insertion sort by ord inside runs of equal keys
+    for (uint32_t i = b + 1; i < e; i++) {
+      if (keys[i] != keys[i - 1]) continue;
+      BoxD x = sorted[i];
+      uint32_t j = i;
+      while (j > b && keys[j - 1] == keys[i] && sorted[j - 1].ord > x.ord) {
+        sorted[j] = sorted[j - 1];
+        j--;
+      }
+      sorted[j] = x;
+    }
+    uint32_t w = b;
+    BoxD cur = sorted[b];
+    for (uint32_t rd = b + 1; rd < e; rd++) {
+      const BoxD nx = sorted[rd];
+      const bool cf = cur.q_lo <= cur.q_hi, nf = nx.q_lo <= nx.q_hi;
+      const int32_t cs = cf ? cur.q_lo : cur.q_hi, ce = cf ? cur.q_hi : cur.q_lo;
+      const int32_t ns = nf ? nx.q_lo : nx.q_hi, ne = nf ? nx.q_hi : nx.q_lo;
+      if (merge_distance < 0 || (!merge_strands && cf != nf) || (int64_t)ns > (int64_t)ce + merge_distance) {
+        out[w++] = cur;
+        cur = nx;
+      } else {
+        const int32_t ms = min(cs, ns), me = max(ce, ne);
+        bool mf = cf;
+        if (merge_strands && cf != nf) {
+          const int64_t cl = (int64_t)ce - cs, nl = (int64_t)ne - ns;
+          mf = nl > cl ? nf : cf;
+        }
+        cur.q_lo = mf ? ms : me;
+        cur.q_hi = mf ? me : ms;
+      }
+    }
+    out[w++] = cur;
+    out_cnt[g] = w - b;
+  }
+}
+
+__global__ void k_sweep_compact_direct(const BoxD *__restrict__ out, const uint32_t *__restrict__ begins,
+                                       const uint32_t *__restrict__ out_cnt, const uint64_t *__restrict__ scan,
+                                       uint64_t n_groups, OutCols o, uint32_t *__restrict__ row_cnt) {
+  for (uint64_t g = gtid(); g < n_groups; g += gstride()) {
+    const uint32_t b = begins[g], c = out_cnt[g];
+    const uint64_t d0 = scan[g];
+    for (uint32_t k = 0; k < c; k++) {
+      BoxD x = out[b + k];
+      o.q_id[d0 + k] = x.q_id;
+      o.q_first[d0 + k] = x.q_lo;
+      o.q_last[d0 + k] = x.q_hi;
+      o.t_id[d0 + k] = x.t_id;
+      o.t_first[d0 + k] = x.t_lo;
+      o.t_last[d0 + k] = x.t_hi;
+    }
+    if (c) atomicAdd(&row_cnt[out[b].row], c);
+  }
+}
+
+__global__ void k_keys_shift(const uint64_t *__restrict__ keys, uint64_t n, int shift, uint64_t *__restrict__ out) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) out[i] = keys[i] >> shift;
+}
+
+// no merging at all (-d < 0 and strands kept apart): boxes in reference order
+__global__ void k_bd_key_ord(const BoxD *__restrict__ b, uint64_t n, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) {
+    keys[i] = b[i].ord;
+    vals[i] = (uint32_t)i;
+  }
+}
+__global__ void k_bd_key_row(const BoxD *__restrict__ b, const uint32_t *__restrict__ perm, uint64_t n, uint32_t n_rows,
+                             uint64_t *__restrict__ keys) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) {
+    BoxD x = b[perm[i]];
+    keys[i] = x.valid ? x.row : n_rows;
+  }
+}
+__global__ void k_boxd_to_cols(const BoxD *__restrict__ b, const uint32_t *__restrict__ perm, uint64_t n, OutCols o,
+                               uint32_t *__restrict__ row_cnt) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) {
+    BoxD x = b[perm[i]];
+    o.q_id[i] = x.q_id;
+    o.q_first[i] = x.q_lo;
+    o.q_last[i] = x.q_hi;
+    o.t_id[i] = x.t_id;
+    o.t_first[i] = x.t_lo;
+    o.t_last[i] = x.t_hi;
+    atomicAdd(&row_cnt[x.row], 1u);
+  }
+}
+
+}  // namespace impgx
