@@ -111,7 +111,9 @@ def gen_workload(ix, name, rank):
     cfg = ix.synth_cfg(g, c, L, a, eq, rev, seed)
     t0 = time.time()
     recs, runs, offs, lens, names = ix.synth_generate(cfg)
-    bed = ix.synth_bed(cfg, rows, seed=2 + 1000 * rank)
+    from impg_b200 import dist as D
+
+    bed = ix.synth_bed(cfg, rows, seed=D.rank_seed(2, rank))
     return cfg, recs, runs, offs, lens, names, bed, time.time() - t0
 
 
@@ -267,7 +269,7 @@ def main():
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches = lift_bytes = liftovers = lift_launches = merged = 0
+    launches = lift_bytes = liftovers = lift_launches = merged = touched = window_runs = 0
     lift_ms = stab_ms = fold_ms = merge_ms = 0.0
     e0.record(stream)
     for _ in range(args.steps):
@@ -275,7 +277,9 @@ def main():
         launches += st["kernel_launches"]
         lift_bytes += st["lift_bytes"]
         liftovers += st["liftovers"]
-        lift_launches += st["stab_candidates"]
+        lift_launches += st["lift_launches"]
+        touched += st["lift_touched_bytes"]
+        window_runs += st["lift_window_runs"]
         lift_ms += st["lift_ms"]; stab_ms += st["stab_ms"]; fold_ms += st["fold_ms"]; merge_ms += st["merge_ms"]
         merged = st["merged"]
         del r
@@ -301,11 +305,10 @@ def main():
     if rank == 0:
         sampler.stop()
 
-    t = torch.tensor([dev_ms, e2e_ms], device="cuda", dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
-    total_rows = n * world * args.steps
+    from impg_b200 import dist as D
+
+    dev_ms, e2e_ms = D.max_over_ranks([dev_ms, e2e_ms], device="cuda")  # slowest rank defines the step
+    total_rows = D.gather_row_counts(n, device="cuda") * args.steps
     value = total_rows / (dev_ms / 1e3)
     e2e_value = total_rows / (e2e_ms / 1e3)
 
@@ -316,9 +319,14 @@ def main():
 
     peak, peak_src = peaks()
     achieved = (lift_bytes / 1e9) / (lift_ms / 1e3) if lift_ms > 0 else 0.0
-    roofline = {"kernel": "k_liftover", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"kernel": "k_liftover_ends", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": lift_bytes / max(1, lift_launches),
+                "algorithmic_bytes_formula": "SURVEY.md 8(d): per liftover 32 (entry) + 16 (2 checkpoints) + 4*r_ov "
+                                             "(runs intersecting the request) + 24 (hit out)",
+                "r_ov_mean": window_runs / max(1, liftovers),
+                "touched_bytes_per_launch": touched / max(1, lift_launches),
+                "touched_GBps": (touched / 1e9) / (lift_ms / 1e3) if lift_ms > 0 else 0.0,
                 "avg_launch_ms": lift_ms / max(1, lift_launches), "liftovers_per_step": liftovers / args.steps,
                 "step_share": {"liftover_ms": lift_ms / args.steps, "stab_ms": stab_ms / args.steps,
                                "fold_ms": fold_ms / args.steps, "merge_ms": merge_ms / args.steps,

@@ -49,8 +49,9 @@ class View(C.Structure):
 
 
 class Stats(C.Structure):
-    _fields_ = [("kernel_launches", C.c_uint64), ("stab_ranges", C.c_uint64), ("stab_candidates", C.c_uint64),
+    _fields_ = [("kernel_launches", C.c_uint64), ("stab_ranges", C.c_uint64), ("lift_launches", C.c_uint64),
                 ("liftovers", C.c_uint64), ("lift_runs", C.c_uint64), ("lift_bytes", C.c_uint64),
+                ("lift_touched_bytes", C.c_uint64), ("lift_window_runs", C.c_uint64),
                 ("results", C.c_uint64), ("merged", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("lift_ms", C.c_float), ("stab_ms", C.c_float), ("fold_ms", C.c_float), ("merge_ms", C.c_float),
                 ("total_ms", C.c_float)]

@@ -361,7 +361,7 @@ void Runner::stab_and_lift(const DBuf<Frontier> &fr, uint64_t nF, bool closed, b
   DBuf<Hit> hits(H, ar_);
   DBuf<CigarSlice> slices;
   if (p_.store_cigar) slices.alloc(H, ar_);
-  CUDA_CHECK(cudaMemsetAsync(d_counters_.get(), 0, 24, s_));
+  CUDA_CHECK(cudaMemsetAsync(d_counters_.get(), 0, 32, s_));
   LiftParams lp;
   lp.clip = clip ? 1 : 0;
   lp.min_output_len = p_.min_output_length;
@@ -380,10 +380,10 @@ void Runner::stab_and_lift(const DBuf<Frontier> &fr, uint64_t nF, bool closed, b
     LAUNCH(k_liftover, grid_warps(H, 256, 8), 256, s_, ix_, fr.get(), tasks.get(), H, lp, hits.get(), slices.get(),
            d_counters_.get());
   CUDA_CHECK(cudaEventRecord(e2, s_));
-  unsigned long long cnt[3];
-  CUDA_CHECK(cudaMemcpyAsync(cnt, d_counters_.get(), 24, cudaMemcpyDeviceToHost, s_));
+  unsigned long long cnt[4];
+  CUDA_CHECK(cudaMemcpyAsync(cnt, d_counters_.get(), 32, cudaMemcpyDeviceToHost, s_));
   CUDA_CHECK(cudaStreamSynchronize(s_));
-  ctx.d2h_bytes += 24;
+  ctx.d2h_bytes += 32;
   float ms = 0;
   cudaEventElapsedTime(&ms, e0, e1);
   ctx.stab_ms += ms;
@@ -394,8 +394,13 @@ void Runner::stab_and_lift(const DBuf<Frontier> &fr, uint64_t nF, bool closed, b
   ctx.lift_runs += cnt[0];
   // algorithmic bytes of the liftover: task 8 + range 16 +
   // entry 32 + 2 checkpoints 16 + runs 4/run + hit 32 (+ slice 16)
-  if (ends) ctx.lift_bytes += H * (8 + 16 + 32 + 32) + cnt[2] * 8 + cnt[0] * 4;
-  else ctx.lift_bytes += H * (8 + 16 + 32 + 16 + 32 + (p_.store_cigar ? 16 : 0)) + cnt[0] * 4;
+  // bytes the kernel's own algorithm touches
+  if (ends) ctx.lift_touched += H * (8 + 16 + 32 + 32) + cnt[2] * 8 + cnt[0] * 4;
+  else ctx.lift_touched += H * (8 + 16 + 32 + 16 + 32 + (p_.store_cigar ? 16 : 0)) + cnt[0] * 4;
+  // algorithmic bytes per SURVEY.md §8(d): 32 (entry) + 16 (two checkpoints) + 4 r_ov (runs
+  // intersecting the request) + 24 (hit out) [+ 4 r_ov with store_cigar]
+  ctx.lift_bytes += H * (32 + 16 + 24) + cnt[3] * 4 * (p_.store_cigar ? 2 : 1);
+  ctx.lift_rov += cnt[3];
   const uint64_t n_ok = cnt[1];
   lvl.n = n_ok;
   if (n_ok == 0 && !sink) return;
@@ -638,7 +643,7 @@ void Runner::run(const impgx_range *d_ranges, uint32_t n_rows, bool bed, BatchOu
   REQUIRE(p_.mode == IMPGX_MODE_QUERY || p_.mode == IMPGX_MODE_BFS, IMPGX_E_UNSUPPORTED,
           "transitive DFS is not implemented on the device yet (use BFS)");
   REQUIRE(!(bed && p_.store_cigar), IMPGX_E_INVALID, "BED output carries no CIGAR (src/main.rs:7447)");
-  d_counters_.alloc(3, ar_);
+  d_counters_.alloc(4, ar_);
   // validation (perform_query bounds checks)
   {
     DBuf<int> bad(1, ar_);
@@ -1032,13 +1037,25 @@ impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n
   };
 
   Ctx total;
-  size_t chunk = (size_t)env_u64("IMPGX_ROWS_PER_BATCH", 8192);
-  if (chunk == 0) chunk = 8192;
+  // Row batches are sized so that one batch lifts about IMPGX_HITS_PER_BATCH hits
+  // (scratch memory is proportional to the hits in flight); the hits-per-row
+  // figure is learned from the first, small batch and kept on the index.
+  const size_t fixed_chunk = (size_t)env_u64("IMPGX_ROWS_PER_BATCH", 0);
+  const double target_hits = (double)env_u64("IMPGX_HITS_PER_BATCH", 200000000ull);
+  auto next_chunk = [&]() -> size_t {
+    if (fixed_chunk) return fixed_chunk;
+    if (idx->hits_per_row <= 0) return 512;
+    double c = target_hits / idx->hits_per_row;
+    if (c < 64) c = 64;
+    if (c > 4194304) c = 4194304;
+    return (size_t)c;
+  };
   size_t done = 0;
   uint64_t res_base = 0, cig_base = 0;
   try {
     while (done < n) {
-      const size_t m = std::min(chunk, n - done);
+      const size_t m = std::min(next_chunk(), n - done);
+      uint64_t chunk_hits = 0;
       {
         const impgx_range *d_r;
         DBuf<impgx_range> d_stage;
@@ -1056,7 +1073,9 @@ impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n
         const Ctx &c = runner.ctx;
         total.launches += c.launches; total.lift_launches += c.lift_launches;
         total.stab_ranges += c.stab_ranges; total.liftovers += c.liftovers;
+        chunk_hits = c.liftovers;
         total.lift_runs += c.lift_runs; total.lift_bytes += c.lift_bytes;
+        total.lift_touched += c.lift_touched; total.lift_rov += c.lift_rov;
         total.h2d_bytes += c.h2d_bytes; total.d2h_bytes += c.d2h_bytes;
         total.lift_ms += c.lift_ms; total.stab_ms += c.stab_ms; total.fold_ms += c.fold_ms; total.merge_ms += c.merge_ms;
         total.w_stab += c.w_stab; total.w_lift += c.w_lift; total.w_order += c.w_order; total.w_fold += c.w_fold;
@@ -1119,6 +1138,7 @@ impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n
       }
       // every arena block of this batch is out of scope and the stream is idle
       idx->arena.reset();
+      idx->hits_per_row = std::max(idx->hits_per_row * 0.9, (double)chunk_hits / (double)m + 1.0);
       done += m;
     }
   } catch (...) {
@@ -1175,6 +1195,9 @@ impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n
   st.liftovers = total.liftovers;
   st.lift_runs = total.lift_runs;
   st.lift_bytes = total.lift_bytes;
+  st.lift_touched_bytes = total.lift_touched;
+  st.lift_window_runs = total.lift_rov;
+  st.lift_launches = total.lift_launches;
   st.results = res_base;
   st.merged = bed ? res_base : 0;
   st.h2d_bytes = total.h2d_bytes;
@@ -1184,7 +1207,6 @@ impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n
   st.fold_ms = total.fold_ms;
   st.merge_ms = total.merge_ms;
   st.total_ms = std::chrono::duration<float, std::milli>(t1 - t0).count();
-  st.stab_candidates = total.lift_launches;  // number of liftover launches (for per-launch averages)
   if (getenv("IMPGX_TRACE"))
     fprintf(stderr,
             "[impgx] rows=%zu total=%.2f ms | wall: stab %.2f lift %.2f order %.2f fold %.2f assemble %.2f merge %.2f "

@@ -56,6 +56,7 @@ struct impgx_index {
   std::mutex mu;  // one query batch at a time per index (handle is thread-safe)
   impgx::Arena arena;  // device scratch of the query pipeline
   impgx_stats last{};
+  double hits_per_row = 0;  // observed liftovers per row (sizes the row batches)
 
   impgx::DevIndexView view() const {
     impgx::DevIndexView v;

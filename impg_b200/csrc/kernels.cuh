@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(256) k_liftover(DevIndexView ix, const Frontie
   const unsigned lane = lane_id();
   uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-  unsigned long long runs_acc = 0, ok_acc = 0;
+  unsigned long long runs_acc = 0, ok_acc = 0, rov_acc = 0;
   for (; w < n_tasks; w += nw) {
     const LiftTask t = tasks[w];
     const Frontier f = fr[t.range];
@@ -402,6 +402,7 @@ __global__ void __launch_bounds__(256) k_liftover(DevIndexView ix, const Frontie
       ok = rec.query_id == lp.row_target[f.row] || lp.subset[rec.query_id] != 0;
     }
     runs_acc += o.runs_read;
+    rov_acc += o.last_idx > o.first_idx ? o.last_idx - o.first_idx : 1;
     ok_acc += ok ? 1 : 0;
     if (lane == 0) {
       Hit h;
@@ -489,6 +490,7 @@ __device__ __forceinline__ uint32_t ck_partition(const Checkpoint *__restrict__ 
 
 struct EndsAcc {
   int32_t f_q, f_t, l_q, l_t;
+  int32_t f_w, l_w;  // walk position inside the block of the first / last overlapping op (for r_ov accounting)
   bool found, broke;
 };
 
@@ -529,9 +531,11 @@ __device__ __forceinline__ void thread_eval_block(const uint32_t *__restrict__ b
       const bool first = ov && !acc.found;
       acc.f_q = first ? pqs : acc.f_q;
       acc.f_t = first ? pts : acc.f_t;
+      acc.f_w = first ? c * 4 + k : acc.f_w;
       acc.found |= ov;
       acc.l_q = ov ? pqe : acc.l_q;
       acc.l_t = ov ? pte : acc.l_t;
+      acc.l_w = ov ? c * 4 + k : acc.l_w;
       tp += t;
       qp += q * dir;
     }
@@ -542,7 +546,7 @@ __global__ void __launch_bounds__(256, 3) k_liftover_ends(DevIndexView ix, const
                                                        const LiftTask *__restrict__ tasks, uint64_t n_tasks,
                                                        LiftParams lp, Hit *__restrict__ hits,
                                                        unsigned long long *__restrict__ counters) {
-  unsigned long long runs_acc = 0, ok_acc = 0, ck_acc = 0;
+  unsigned long long runs_acc = 0, ok_acc = 0, ck_acc = 0, rov_acc = 0;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_tasks; w += stride) {
     const LiftTask t = tasks[w];
@@ -569,9 +573,10 @@ __global__ void __launch_bounds__(256, 3) k_liftover_ends(DevIndexView ix, const
 
     EndsAcc acc;
     acc.f_q = acc.f_t = acc.l_q = acc.l_t = -1;
+    acc.f_w = acc.l_w = 0;
     acc.found = false;
     acc.broke = false;
-    uint32_t nread = 0, nck = 0;
+    uint32_t nread = 0, nck = 0, r_ov = 1;
     if (nblk > 0 && rel_l >= 0) {
       // totals: needed exactly only when walking backwards; otherwise the record's
       // own span is a good enough denominator for the interpolation guess
@@ -619,6 +624,7 @@ __global__ void __launch_bounds__(256, 3) k_liftover_ends(DevIndexView ix, const
       // ---- end side: the last overlapping op lies in blocks [j, max(je, j)]; walk backward from the top
       if (acc.found) {
         uint32_t jl = je > j ? je : j;
+        r_ov = (uint32_t)(acc.l_w - acc.f_w + 1);
         while (jl > j) {
           const uint32_t pb = backward ? nblk - 1 - jl : jl;
           const Checkpoint k = backward ? ck[pb + 1] : ck[pb];
@@ -628,6 +634,7 @@ __global__ void __launch_bounds__(256, 3) k_liftover_ends(DevIndexView ix, const
           const int32_t qp0 = rev_strand ? (int32_t)(q_end - qcons) : (int32_t)(q_start + qcons);
           EndsAcc a2;
           a2.f_q = a2.f_t = a2.l_q = a2.l_t = -1;
+          a2.f_w = a2.l_w = 0;
           a2.found = false;
           a2.broke = false;
           thread_eval_block(blk, n, pb, swap_id, backward, dir, tp0, qp0, rs, re, last_target_pos, a2);
@@ -635,6 +642,7 @@ __global__ void __launch_bounds__(256, 3) k_liftover_ends(DevIndexView ix, const
           if (a2.found) {
             acc.l_q = a2.l_q;
             acc.l_t = a2.l_t;
+            r_ov = (jl - j) * RUNS_PER_BLOCK + (uint32_t)(a2.l_w - acc.f_w + 1);
             break;
           }
           jl--;  // nothing overlapped up there: try the block below (block j already holds its own last)
@@ -645,6 +653,7 @@ __global__ void __launch_bounds__(256, 3) k_liftover_ends(DevIndexView ix, const
     if (ok && lp.subset) ok = query_id == lp.row_target[f.row] || lp.subset[query_id] != 0;
     runs_acc += nread;
     ck_acc += nck;
+    rov_acc += r_ov;
     ok_acc += ok ? 1 : 0;
     Hit h;
     h.row = ok ? f.row : INVALID_ID;
@@ -663,11 +672,13 @@ __global__ void __launch_bounds__(256, 3) k_liftover_ends(DevIndexView ix, const
     runs_acc += __shfl_xor_sync(FULL, runs_acc, d);
     ok_acc += __shfl_xor_sync(FULL, ok_acc, d);
     ck_acc += __shfl_xor_sync(FULL, ck_acc, d);
+    rov_acc += __shfl_xor_sync(FULL, rov_acc, d);
   }
   if (lane_id() == 0 && counters) {
     atomicAdd(&counters[0], runs_acc);
     atomicAdd(&counters[1], ok_acc);
     atomicAdd(&counters[2], ck_acc);
+    atomicAdd(&counters[3], rov_acc);
   }
 }
 

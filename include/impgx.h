@@ -121,10 +121,12 @@ typedef struct impgx_view {
 typedef struct impgx_stats {
   uint64_t kernel_launches; /* kernels of this library launched by the call */
   uint64_t stab_ranges;     /* ranges stabbed over all hops */
-  uint64_t stab_candidates; /* interval columns scanned */
+  uint64_t lift_launches;   /* liftover kernel launches of the call */
   uint64_t liftovers;       /* hits lifted through a CIGAR */
   uint64_t lift_runs;       /* CIGAR runs read by the liftover kernel */
-  uint64_t lift_bytes;      /* algorithmic bytes of the liftover kernel */
+  uint64_t lift_bytes;      /* algorithmic bytes of the liftover (SURVEY.md 8d formula) */
+  uint64_t lift_touched_bytes; /* bytes the kernel's own algorithm touches (entry, checkpoints, blocks read, hit) */
+  uint64_t lift_window_runs;   /* sum over hits of r_ov = runs intersecting the request */
   uint64_t results;         /* result intervals before merging */
   uint64_t merged;          /* result intervals after merging (BED entry point) */
   uint64_t h2d_bytes;
