@@ -107,6 +107,8 @@ def lib():
         L.impgx_index_seq_len.restype = C.c_uint64
         L.impgx_parse_cigar.restype = C.c_long
         L.impgx_format_bed.restype = C.c_void_p
+        L.impgx_format_bedpe.restype = C.c_void_p
+        L.impgx_format_paf.restype = C.c_void_p
         L.impgx_synth_num_alignments.restype = C.c_uint64
         L.impgx_debug_host_columns.restype = C.c_long
         _lib = L
@@ -310,6 +312,25 @@ class Impg:
         s = C.string_at(ptr).decode()
         lib().impgx_free(C.c_void_p(ptr))
         return s
+
+
+def _format_rows(fn, idx, results, row, name, merge_distance):
+    ptr = fn(idx.h, results.h, C.c_size_t(row), name.encode(), C.c_int32(merge_distance))
+    if not ptr:
+        raise ImpgxError(E_INVALID, "format failed: " + lib().impgx_last_error().decode())
+    s = C.string_at(ptr).decode()
+    lib().impgx_free(C.c_void_p(ptr))
+    return s
+
+
+def format_bedpe(idx, results, row, name, merge_distance):
+    """output_results_bedpe (reference src/main.rs:11894) on a raw result set with CIGARs."""
+    return _format_rows(lib().impgx_format_bedpe, idx, results, row, name, merge_distance)
+
+
+def format_paf(idx, results, row, name, merge_distance):
+    """output_results_paf (reference src/main.rs:11989) on a raw result set with CIGARs."""
+    return _format_rows(lib().impgx_format_paf, idx, results, row, name, merge_distance)
 
 
 def project_batch(req, records, runs, run_offsets, device=0, want_cigar=True):

@@ -11,6 +11,8 @@ using namespace impgx;
 namespace impgx {
 void set_last_error(const std::string &m);
 const char *last_error();
+std::string format_rows(const impgx_index *idx, const impgx_results *res, size_t row, const char *name, int32_t d,
+                        int format);
 
 // ---- host text helpers (reference parsers / writers for this path)
 
@@ -331,6 +333,28 @@ char *impgx_format_bed(const impgx_index *idx, const impgx_results *res, size_t 
   char *p = (char *)malloc(s.size() + 1);
   if (p) memcpy(p, s.c_str(), s.size() + 1);
   return p;
+}
+
+static char *format_with(const impgx_index *idx, const impgx_results *res, size_t row, const char *name, int32_t d,
+                         int fmt) {
+  if (!idx || !res || res->on_device || row >= res->n_rows || !name) return nullptr;
+  try {
+    std::string s = impgx::format_rows(idx, res, row, name, d, fmt);
+    char *p = (char *)malloc(s.size() + 1);
+    if (p) memcpy(p, s.c_str(), s.size() + 1);
+    return p;
+  } catch (const std::exception &e) {
+    impgx::set_last_error(e.what());
+    return nullptr;
+  }
+}
+char *impgx_format_bedpe(const impgx_index *idx, const impgx_results *res, size_t row, const char *name,
+                         int32_t merge_distance) {
+  return format_with(idx, res, row, name, merge_distance, 1);
+}
+char *impgx_format_paf(const impgx_index *idx, const impgx_results *res, size_t row, const char *name,
+                       int32_t merge_distance) {
+  return format_with(idx, res, row, name, merge_distance, 2);
 }
 
 void impgx_free(void *p) { free(p); }

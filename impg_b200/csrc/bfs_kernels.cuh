@@ -351,6 +351,88 @@ __global__ void k_frontier_merge(const Frontier *__restrict__ p, uint64_t n, con
   }
 }
 
+// ----------------------------------------------------------- DFS stacks
+struct __align__(8) DfsEntry {
+  uint32_t row, id;
+  int32_t start, end;
+  uint32_t depth, pad;
+};
+
+__global__ void k_dfs_init_stack(const Frontier *__restrict__ fr, uint64_t n, DfsEntry *__restrict__ st) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) st[i] = DfsEntry{fr[i].row, fr[i].seq, fr[i].start, fr[i].end, 0u, 0u};
+}
+
+// the stack array is sorted by (row, id, start): the top of a row is the last entry of its segment
+__global__ void k_dfs_pop(const DfsEntry *__restrict__ st, uint64_t n, uint32_t max_depth, uint64_t *__restrict__ popped,
+                          Frontier *__restrict__ cand, uint64_t *__restrict__ is_fr, uint32_t *__restrict__ cur_depth) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) {
+    const DfsEntry e = st[i];
+    if (i + 1 < n && st[i + 1].row == e.row) continue;  // not the top
+    popped[i] = 1;
+    if (max_depth > 0 && e.depth >= max_depth) continue;  // :2125-2127, popped and dropped
+    cand[e.row] = Frontier{e.row, e.id, e.start, e.end};
+    is_fr[e.row] = 1;
+    cur_depth[e.row] = e.depth;
+  }
+}
+
+__global__ void k_dfs_keep_flags(const uint64_t *__restrict__ popped, uint64_t n, uint64_t *__restrict__ keep) {
+  for (uint64_t i = gtid(); i <= n; i += gstride()) keep[i] = (i < n && !popped[i]) ? 1 : 0;
+}
+__global__ void k_dfs_copy_kept(const DfsEntry *__restrict__ st, uint64_t n, const uint64_t *__restrict__ popped,
+                                const uint64_t *__restrict__ scan, DfsEntry *__restrict__ out) {
+  for (uint64_t i = gtid(); i < n; i += gstride())
+    if (!popped[i]) out[scan[i]] = st[i];
+}
+__global__ void k_dfs_push(const Frontier *__restrict__ pieces, uint64_t n, const uint32_t *__restrict__ cur_depth,
+                           DfsEntry *__restrict__ out) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) {
+    const Frontier p = pieces[i];
+    out[i] = DfsEntry{p.row, p.seq, p.start, p.end, cur_depth[p.row] + 1, 0u};
+  }
+}
+__global__ void k_dfs_start_keys(const DfsEntry *__restrict__ st, uint64_t n, uint32_t *__restrict__ keys,
+                                 uint32_t *__restrict__ vals) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) {
+    keys[i] = (uint32_t)st[i].start ^ 0x80000000u;
+    vals[i] = (uint32_t)i;
+  }
+}
+__global__ void k_dfs_seq_keys(const DfsEntry *__restrict__ st, const uint32_t *__restrict__ perm, uint64_t n,
+                               uint64_t *__restrict__ keys) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) {
+    const DfsEntry e = st[perm[i]];
+    keys[i] = ((uint64_t)e.row << 32) | e.id;
+  }
+}
+// one thread per row: the write/read merge of src/impg.rs:2291-2304 (depth of the survivor kept)
+__global__ void __launch_bounds__(128) k_dfs_merge(DfsEntry *__restrict__ st, const uint32_t *__restrict__ begins,
+                                                   uint64_t n_groups, uint32_t *__restrict__ cnt) {
+  for (uint64_t g = gtid(); g < n_groups; g += gstride()) {
+    const uint32_t b = begins[g], e = begins[g + 1];
+    uint32_t w = b;
+    for (uint32_t r = b + 1; r < e; r++) {
+      if (st[w].id == st[r].id && st[w].end >= st[r].start) {
+        st[w].end = max(st[w].end, st[r].end);
+      } else {
+        w++;
+        DfsEntry t = st[w];
+        st[w] = st[r];
+        st[r] = t;
+      }
+    }
+    cnt[g] = w - b + 1;
+  }
+}
+__global__ void k_dfs_compact(const DfsEntry *__restrict__ st, const uint32_t *__restrict__ begins,
+                              const uint32_t *__restrict__ cnt, const uint64_t *__restrict__ scan, uint64_t n_groups,
+                              DfsEntry *__restrict__ out) {
+  for (uint64_t g = gtid(); g < n_groups; g += gstride()) {
+    const uint32_t b = begins[g];
+    for (uint32_t k = 0; k < cnt[g]; k++) out[scan[g] + k] = st[b + k];
+  }
+}
+
 // ----------------------------------------------------------- result assembly
 __device__ __forceinline__ bool passes_len(const Hit &h, int32_t min_out) {
   if (min_out < 0) return true;

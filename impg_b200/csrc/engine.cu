@@ -309,7 +309,10 @@ class Runner {
 
   void stab_and_lift(const DBuf<Frontier> &fr, uint64_t nF, bool closed, bool clip, BedSink *sink, LevelHits &lvl);
   void bed_merge_direct(BedSink &sink, uint32_t n_rows, BatchOut &out);
-  void fold(const LevelHits &lvl, uint32_t n_rows, Visited &V, DBuf<Frontier> &next, uint64_t &n_next);
+  void fold(const LevelHits &lvl, uint32_t n_rows, Visited &V, DBuf<Frontier> &next, uint64_t &n_next,
+            bool raw_pieces = false);
+  void run_dfs(const impgx_range *d_ranges, uint32_t n_rows, DBuf<Frontier> &fr, uint64_t nF, Visited &V,
+               std::vector<LevelHits> &levels);
   void assemble(const impgx_range *d_ranges, uint32_t n_rows, std::vector<LevelHits> &levels, bool query_mode,
                 BatchOut &out);
   void bed_merge(BatchOut &raw, uint32_t n_rows, BatchOut &out);
@@ -428,7 +431,8 @@ void Runner::stab_and_lift(const DBuf<Frontier> &fr, uint64_t nF, bool closed, b
 }
 
 // The sequential fold + next frontier of one level (src/impg.rs:2467-2593).
-void Runner::fold(const LevelHits &lvl, uint32_t n_rows, Visited &V, DBuf<Frontier> &next, uint64_t &n_next) {
+void Runner::fold(const LevelHits &lvl, uint32_t n_rows, Visited &V, DBuf<Frontier> &next, uint64_t &n_next,
+                  bool raw_pieces) {
   n_next = 0;
   const uint64_t n = lvl.n;
   if (n == 0) return;
@@ -527,7 +531,13 @@ void Runner::fold(const LevelHits &lvl, uint32_t n_rows, Visited &V, DBuf<Fronti
   V = std::move(nv);
 
   // ---- next frontier: pieces sorted by (row, id, start), touching ones merged
-  if (n_pieces) {
+  if (n_pieces && raw_pieces) {
+    // DFS: the pieces are pushed on the per-row stacks as they are
+    next.alloc(n_pieces, ar_);
+    n_next = n_pieces;
+    LAUNCH(k_compact_pieces, grid_threads(G), 256, s_, groups.get(), G, pieces.get(), piece_cnt.get(), po.get(),
+           next.get());
+  } else if (n_pieces) {
     DBuf<Frontier> pc(n_pieces, ar_);
     LAUNCH(k_compact_pieces, grid_threads(G), 256, s_, groups.get(), G, pieces.get(), piece_cnt.get(), po.get(),
            pc.get());
@@ -640,8 +650,7 @@ void Runner::assemble(const impgx_range *d_ranges, uint32_t n_rows, std::vector<
 }
 
 void Runner::run(const impgx_range *d_ranges, uint32_t n_rows, bool bed, BatchOut &out) {
-  REQUIRE(p_.mode == IMPGX_MODE_QUERY || p_.mode == IMPGX_MODE_BFS, IMPGX_E_UNSUPPORTED,
-          "transitive DFS is not implemented on the device yet (use BFS)");
+  REQUIRE(p_.mode <= IMPGX_MODE_DFS, IMPGX_E_INVALID, "unknown mode");
   REQUIRE(!(bed && p_.store_cigar), IMPGX_E_INVALID, "BED output carries no CIGAR (src/main.rs:7447)");
   d_counters_.alloc(4, ar_);
   // validation (perform_query bounds checks)
@@ -714,6 +723,10 @@ void Runner::run(const impgx_range *d_ranges, uint32_t n_rows, bool bed, BatchOu
       }
     }
     uint32_t depth = 0;
+    if (p_.mode == IMPGX_MODE_DFS) {
+      run_dfs(d_ranges, n_rows, fr, nF, V, levels);
+      nF = 0;
+    }
     while (nF > 0 && (p_.max_depth == 0 || depth < p_.max_depth)) {
       const bool last = p_.max_depth != 0 && depth + 1 >= p_.max_depth;
       levels.emplace_back();
@@ -730,7 +743,9 @@ void Runner::run(const impgx_range *d_ranges, uint32_t n_rows, bool bed, BatchOu
   if (direct && levels.size() < 60) {
     WallTimer wt(ctx.w_assemble);
     if (!sink.filled) {
-      sink.prefix = (uint64_t)n_rows + prior;
+      uint64_t held = 0;  // hits held by the ordered levels (BFS hops or DFS rounds)
+      for (auto &l : levels) held += l.n;
+      sink.prefix = (uint64_t)n_rows + held;
       sink.boxes.alloc(sink.prefix, ar_);
       sink.n = sink.prefix;
     }
@@ -991,6 +1006,83 @@ void Runner::bed_merge_direct(BedSink &sink, uint32_t n_rows, BatchOut &out) {
   ctx.merge_ms += msf;
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
+}
+
+// Transitive DFS (src/impg.rs:2057-2309). The walk of one row is inherently
+// sequential (pop one range, expand, re-sort the stack), so the device runs it
+// in lock step over the rows of the batch: every round each row with a
+// non-empty stack pops its top range; the popped ranges are stabbed, lifted and
+// folded together, the pieces are pushed with depth + 1 and every stack is
+// re-sorted by (id, start) and merged exactly like the reference does after
+// each pop (:2289-2304). The stacks of all rows live in one array sorted by
+// (row, id, start); a row's top is the last entry of its segment.
+void Runner::run_dfs(const impgx_range *d_ranges, uint32_t n_rows, DBuf<Frontier> &fr0, uint64_t nF0, Visited &V,
+                     std::vector<LevelHits> &levels) {
+  (void)d_ranges;
+  DBuf<DfsEntry> stack(nF0, ar_);
+  uint64_t n_stack = nF0;
+  if (nF0) LAUNCH(k_dfs_init_stack, grid_threads(nF0), 256, s_, fr0.get(), nF0, stack.get());
+  DBuf<uint32_t> cur_depth(n_rows, ar_);
+  while (n_stack > 0) {
+    // ---- pop the top of every non-empty stack
+    DBuf<uint64_t> popped(n_stack + 1, ar_), is_fr(n_rows + 1, ar_), fr_scan(n_rows + 1, ar_);
+    CUDA_CHECK(cudaMemsetAsync(popped.get(), 0, (n_stack + 1) * 8, s_));
+    CUDA_CHECK(cudaMemsetAsync(is_fr.get(), 0, ((size_t)n_rows + 1) * 8, s_));
+    DBuf<Frontier> cand(n_rows, ar_);
+    LAUNCH(k_dfs_pop, grid_threads(n_stack), 256, s_, stack.get(), n_stack, p_.max_depth, popped.get(), cand.get(),
+           is_fr.get(), cur_depth.get());
+    CUDA_CHECK(cudaMemcpyAsync(fr_scan.get(), is_fr.get(), ((size_t)n_rows + 1) * 8, cudaMemcpyDeviceToDevice, s_));
+    exclusive_scan_u64(fr_scan.get(), (uint64_t)n_rows + 1, sc_, s_);
+    ctx.launches += 2;
+    const uint64_t nF = read_u64(fr_scan.get() + n_rows, s_, ctx);
+    DBuf<Frontier> fr(nF, ar_);
+    if (nF) LAUNCH(k_frontier_compact, grid_threads(n_rows), 256, s_, cand.get(), (uint64_t)n_rows, is_fr.get(), fr_scan.get(), fr.get());
+    // ---- expand
+    DBuf<Frontier> pieces;
+    uint64_t n_pieces = 0;
+    if (nF) {
+      levels.emplace_back();
+      stab_and_lift(fr, nF, /*closed=*/false, /*clip=*/true, nullptr, levels.back());
+      fold(levels.back(), n_rows, V, pieces, n_pieces, /*raw_pieces=*/true);
+    }
+    // ---- new stack = kept entries + pushed pieces, sorted by (row, id, start), merged per row
+    DBuf<uint64_t> keep_scan(n_stack + 1, ar_);
+    LAUNCH(k_dfs_keep_flags, grid_threads(n_stack + 1), 256, s_, popped.get(), n_stack, keep_scan.get());
+    exclusive_scan_u64(keep_scan.get(), n_stack + 1, sc_, s_);
+    ctx.launches += 2;
+    const uint64_t kept = read_u64(keep_scan.get() + n_stack, s_, ctx);
+    const uint64_t m = kept + n_pieces;
+    if (m == 0) break;
+    DBuf<DfsEntry> tmp(m, ar_);
+    LAUNCH(k_dfs_copy_kept, grid_threads(n_stack), 256, s_, stack.get(), n_stack, popped.get(), keep_scan.get(), tmp.get());
+    if (n_pieces)
+      LAUNCH(k_dfs_push, grid_threads(n_pieces), 256, s_, pieces.get(), n_pieces, cur_depth.get(), tmp.get() + kept);
+    DBuf<uint32_t> sk(m, ar_), sp(m, ar_);
+    LAUNCH(k_dfs_start_keys, grid_threads(m), 256, s_, tmp.get(), m, sk.get(), sp.get());
+    sort_pairs(sk, sp, m, 0, 32, sc_, s_, ctx);
+    DBuf<uint64_t> k2(m, ar_);
+    LAUNCH(k_dfs_seq_keys, grid_threads(m), 256, s_, tmp.get(), sp.get(), m, k2.get());
+    sort_pairs(k2, sp, m, 0, 32 + bits_for(n_rows), sc_, s_, ctx);
+    DBuf<DfsEntry> sorted(m, ar_);
+    LAUNCH(k_gather<DfsEntry>, grid_threads(m), 256, s_, tmp.get(), sp.get(), m, sorted.get());
+    // per-row sequential merge (write/read sweep of :2291-2304)
+    DBuf<uint64_t> rowkeys(m, ar_);
+    LAUNCH(k_keys_shift, grid_threads(m), 256, s_, k2.get(), m, 32, rowkeys.get());
+    Groups g;
+    build_groups(rowkeys.get(), m, g, sc_, s_, ctx);
+    DBuf<uint32_t> cnt(g.G, ar_);
+    LAUNCH(k_dfs_merge, grid_threads(g.G, 128, 16), 128, s_, sorted.get(), g.begins.get(), g.G, cnt.get());
+    DBuf<uint64_t> scan(g.G + 1, ar_);
+    CUDA_CHECK(cudaMemsetAsync(scan.get() + g.G, 0, 8, s_));
+    LAUNCH(k_u32_to_u64, grid_threads(g.G), 256, s_, cnt.get(), g.G, scan.get());
+    exclusive_scan_u64(scan.get(), g.G + 1, sc_, s_);
+    ctx.launches += 2;
+    const uint64_t n_new = read_u64(scan.get() + g.G, s_, ctx);
+    DBuf<DfsEntry> ns(n_new, ar_);
+    LAUNCH(k_dfs_compact, grid_threads(g.G), 256, s_, sorted.get(), g.begins.get(), cnt.get(), scan.get(), g.G, ns.get());
+    stack = std::move(ns);
+    n_stack = n_new;
+  }
 }
 
 // ============================================================ batch driver

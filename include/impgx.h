@@ -216,6 +216,15 @@ long impgx_parse_cigar(const char *text, size_t len, uint32_t *out, size_t cap);
  * impgx_free) or NULL. */
 char *impgx_format_bed(const impgx_index *idx, const impgx_results *res,
                        size_t row, const char *name);
+/* output_results_bedpe / output_results_paf (src/main.rs:11894-12103) for row
+ * `row` of a RAW result set obtained with store_cigar = 1: drops the self
+ * interval (src/main.rs:7474,7486), runs merge_adjusted_intervals
+ * (src/main.rs:12563-12845, host side: f32 CIGAR surgery) and formats the
+ * lines. malloc'ed string, free with impgx_free. */
+char *impgx_format_bedpe(const impgx_index *idx, const impgx_results *res,
+                         size_t row, const char *name, int32_t merge_distance);
+char *impgx_format_paf(const impgx_index *idx, const impgx_results *res,
+                       size_t row, const char *name, int32_t merge_distance);
 void impgx_free(void *p);
 
 #ifdef __cplusplus

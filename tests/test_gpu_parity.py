@@ -193,6 +193,23 @@ def test_bfs_raw(small, depth):
     compare_raw(orc, gpu, bed[:120], *params_pair(mode=1, max_depth=depth))
 
 
+@pytest.mark.parametrize("depth", [1, 2, 3, 0])
+def test_dfs_raw(small, depth):
+    """Transitive DFS (reference src/impg.rs:2057-2309): lock-step over rows on the device."""
+    cfg, orc, gpu, bed = small
+    compare_raw(orc, gpu, bed[:60], *params_pair(mode=2, max_depth=depth))
+
+
+def test_dfs_options_and_bed(small):
+    cfg, orc, gpu, bed = small
+    b = bed[:40]
+    compare_raw(orc, gpu, b, *params_pair(mode=2, max_depth=3, store_cigar=True), check_cigar=True)
+    compare_raw(orc, gpu, b, *params_pair(mode=2, max_depth=0, min_transitive_len=0, min_dist=0))
+    compare_raw(orc, gpu, b, *params_pair(mode=2, max_depth=3, min_output_length=2500, min_identity=0.95))
+    compare_bed(orc, gpu, b, *params_pair(mode=2, max_depth=2, merge_distance=1000))
+    compare_bed(orc, gpu, b, *params_pair(mode=2, max_depth=0, merge_distance=0, merge_strands=False))
+
+
 def test_bfs_options(small):
     cfg, orc, gpu, bed = small
     b = bed[:100]
@@ -264,19 +281,38 @@ def test_fixture_pafs_against_golden(fixture):
     orc = O.Index.from_paf(path)
     assert [gpu.seq_name(i) for i in range(gpu.n_seqs)] == [orc.seq_name(i) for i in range(orc.n_seqs)]
     for c in GOLDEN[fixture]:
-        if c["format"] != "bed":
-            continue
         sid = gpu.seq_id(c["seq"])
         region = f"{c['seq']}:{c['start']}-{c['end']}"
-        g = ix.make_params(mode=c["mode"], max_depth=c["max_depth"], min_transitive_len=0, merge_distance=c["d"])
-        res = gpu.query_batch_bed(np.array([(sid, c["start"], c["end"])], ix.RANGE_DTYPE), g)
-        text = gpu.format_bed(res, 0, region)
+        rng = np.array([(sid, c["start"], c["end"])], ix.RANGE_DTYPE)
+        if c["format"] == "bed":
+            g = ix.make_params(mode=c["mode"], max_depth=c["max_depth"], min_transitive_len=0, merge_distance=c["d"])
+            text = gpu.format_bed(gpu.query_batch_bed(rng, g), 0, region)
+        else:  # bedpe / paf: raw results with CIGARs from the device, merge + text on the host side of the library
+            g = ix.make_params(mode=c["mode"], max_depth=c["max_depth"], min_transitive_len=0, store_cigar=True)
+            res = gpu.query_batch(rng, g)
+            text = (ix.format_bedpe if c["format"] == "bedpe" else ix.format_paf)(gpu, res, 0, region, c["d"])
         assert hashlib.sha256(text.encode()).hexdigest() == c["sha256"], (fixture, c)
     # raw results incl. CIGARs vs the oracle for every sequence
     ranges = np.array([(s, 0, orc.seq_len(s)) for s in range(orc.n_seqs)], ix.RANGE_DTYPE)
     compare_raw(orc, gpu, ranges, *params_pair(mode=0, store_cigar=True), check_cigar=True)
     compare_raw(orc, gpu, ranges, *params_pair(mode=1, max_depth=0, min_transitive_len=0, store_cigar=True),
                 check_cigar=True)
+
+
+def test_bedpe_paf_text_vs_oracle(small):
+    """BEDPE / PAF lines (CIGAR merge with f32 surgery, gi/bi formatting) against the oracle's writers."""
+    cfg, orc, gpu, bed = small
+    rows = bed[:40]
+    for mode, depth in ((0, 1), (1, 2)):
+        for d in (0, 500, -1):
+            o, g = params_pair(mode=mode, max_depth=depth, store_cigar=True)
+            gres = gpu.query_batch(rows, g)
+            for r in range(len(rows)):
+                name = f"r{r}"
+                for fmt, fn in (("bedpe", ix.format_bedpe), ("paf", ix.format_paf)):
+                    ores = orc.perform_query(int(rows[r]["target_id"]), int(rows[r]["start"]), int(rows[r]["end"]), o)
+                    ores.drop_first()
+                    assert fn(gpu, gres, r, name, d) == orc.format(ores, fmt, name, d), (mode, d, r, fmt)
 
 
 def test_medium_scale_properties():
