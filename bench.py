@@ -106,6 +106,15 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
+def host_threads():
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which must not
+    throttle the CPU reference: it is given every core, like rayon would take)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def gen_workload(ix, name, rank):
     g, c, L, a, eq, rev, seed, rows = WORKLOADS[name]
     cfg = ix.synth_cfg(g, c, L, a, eq, rev, seed)
@@ -184,7 +193,7 @@ def main():
             return 0
         cfg, recs, runs, offs, lens, names, bed, gen_s = gen_workload(ix, name, 0)
         O, orc, path, setup_s = cpu_reference_setup(name, recs, runs, offs, lens, names, ix)
-        threads = O.lib().orc_max_threads()
+        threads = host_threads()
         try:
             per_step_budget = max(2.0, min(args.cpu_budget, 150.0 / max(1, args.steps + args.warmup)))
             vals, n_used = [], 0
@@ -342,7 +351,7 @@ def main():
     if not args.no_cpu_baseline:
         O, orc, path, setup_s = cpu_reference_setup(name, recs, runs, offs, lens, names, ix)
         try:
-            threads = O.lib().orc_max_threads()
+            threads = host_threads()
             v, n_used, tsec, nres = cpu_reference_time(O, orc, bed, name, args.cpu_budget, threads)
             cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                             "sample": f"first {n_used} of {rows} BED rows, {tsec:.1f} s (oracle port with the reference's "
