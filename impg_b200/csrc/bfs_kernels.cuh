@@ -26,11 +26,23 @@ __global__ void k_validate(const impgx_range *__restrict__ ranges, uint32_t n, c
 }
 
 // sort key of a lifted hit: (frontier index, coitrees visit rank); rejected hits last
-__global__ void k_hit_order_keys(const Hit *__restrict__ hits, const LiftTask *__restrict__ tasks, uint64_t n,
-                                 uint32_t n_frontier, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+// `orig` maps the processing order of the frontier (sorted by target position
+// for cache locality) back to the reference's frontier index; nullptr = identity
+__global__ void k_hit_order_keys(const Hit *__restrict__ hits, const LiftTask *__restrict__ tasks,
+                                 const uint32_t *__restrict__ orig, uint64_t n, uint32_t n_frontier,
+                                 uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
   for (uint64_t i = gtid(); i < n; i += gstride()) {
     Hit h = hits[i];
-    keys[i] = h.row == INVALID_ID ? ((uint64_t)n_frontier << 32) : (((uint64_t)tasks[i].range << 32) | h.vrank);
+    const uint32_t r = orig ? orig[tasks[i].range] : tasks[i].range;
+    keys[i] = h.row == INVALID_ID ? ((uint64_t)n_frontier << 32) : (((uint64_t)r << 32) | h.vrank);
+    vals[i] = (uint32_t)i;
+  }
+}
+
+__global__ void k_locality_keys(const Frontier *__restrict__ fr, uint64_t n, uint64_t *__restrict__ keys,
+                                uint32_t *__restrict__ vals) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) {
+    keys[i] = ((uint64_t)fr[i].seq << 32) | (uint32_t)fr[i].start;
     vals[i] = (uint32_t)i;
   }
 }

@@ -321,7 +321,7 @@ class Runner {
 
 // stab (count, scan, fill) + liftover of one frontier; leaves the accepted
 // hits ordered by (frontier index, visit rank) in lvl.
-void Runner::stab_and_lift(const DBuf<Frontier> &fr, uint64_t nF, bool closed, bool clip, BedSink *sink,
+void Runner::stab_and_lift(const DBuf<Frontier> &fr_ref, uint64_t nF, bool closed, bool clip, BedSink *sink,
                            LevelHits &lvl) {
   lvl.n = 0;
   if (nF == 0) return;
@@ -331,6 +331,24 @@ void Runner::stab_and_lift(const DBuf<Frontier> &fr, uint64_t nF, bool closed, b
   CUDA_CHECK(cudaEventCreate(&e1));
   CUDA_CHECK(cudaEventCreate(&e2));
   CUDA_CHECK(cudaEventRecord(e0, s_));
+  // Process the frontier in (target sequence, start) order rather than row
+  // order: neighbouring threads then stab the same entry windows and lift
+  // through the same alignments, so entry records, checkpoints and run blocks
+  // are reused from L1/L2 instead of being re-fetched from HBM. `orig` maps
+  // back to the reference's frontier index, which the order keys are built on.
+  DBuf<Frontier> fr_loc;
+  DBuf<uint32_t> orig;
+  const bool locality = nF >= 4096 && !getenv("IMPGX_NO_LOCALITY");
+  if (locality) {
+    DBuf<uint64_t> lk(nF, ar_);
+    orig.alloc(nF, ar_);
+    LAUNCH(k_locality_keys, grid_threads(nF), 256, s_, fr_ref.get(), nF, lk.get(), orig.get());
+    sort_pairs(lk, orig, nF, 0, 32 + bits_for(ix_.n_seqs), sc_, s_, ctx);
+    fr_loc.alloc(nF, ar_);
+    LAUNCH(k_gather<Frontier>, grid_threads(nF), 256, s_, fr_ref.get(), orig.get(), nF, fr_loc.get());
+  }
+  const DBuf<Frontier> &fr = locality ? fr_loc : fr_ref;
+  const uint32_t *d_orig = locality ? orig.get() : nullptr;
   DBuf<Window> win(nF, ar_);
   DBuf<uint32_t> counts(nF, ar_);
   DBuf<uint64_t> offs(nF + 1, ar_);
@@ -412,8 +430,17 @@ void Runner::stab_and_lift(const DBuf<Frontier> &fr, uint64_t nF, bool closed, b
   if (sink) {
     // direct BED path, last hop: no ordering sort — the reference order travels
     // as (range, visit rank) inside each box
-    LAUNCH(k_boxes_from_raw_level, grid_threads(H), 256, s_, hits.get(), tasks.get(), H, sink->level,
-           p_.min_output_length, sink->boxes.get() + sink->prefix, sink->counters.get());
+    DBuf<uint64_t> dst_off;
+    if (d_orig) {
+      dst_off.alloc(nF + 1, ar_);
+      CUDA_CHECK(cudaMemsetAsync(dst_off.get() + nF, 0, 8, s_));
+      LAUNCH(k_scatter_counts, grid_threads(nF), 256, s_, counts.get(), d_orig, nF, dst_off.get());
+      exclusive_scan_u64(dst_off.get(), nF + 1, sc_, s_);
+      ctx.launches += 2;
+    }
+    LAUNCH(k_boxes_from_raw_level, grid_threads(H), 256, s_, hits.get(), tasks.get(), d_orig, offs.get(),
+           dst_off.get(), H, sink->level, p_.min_output_length, sink->boxes.get() + sink->prefix,
+           sink->counters.get());
     sink->n = sink->prefix + H;
     sink->filled = true;
     lvl.n = 0;
@@ -421,7 +448,8 @@ void Runner::stab_and_lift(const DBuf<Frontier> &fr, uint64_t nF, bool closed, b
   }
   DBuf<uint64_t> keys(H, ar_);
   DBuf<uint32_t> perm(H, ar_);
-  LAUNCH(k_hit_order_keys, grid_threads(H), 256, s_, hits.get(), tasks.get(), H, (uint32_t)nF, keys.get(), perm.get());
+  LAUNCH(k_hit_order_keys, grid_threads(H), 256, s_, hits.get(), tasks.get(), d_orig, H, (uint32_t)nF, keys.get(),
+         perm.get());
   sort_pairs(keys, perm, H, 0, 32 + bits_for(nF), sc_, s_, ctx);
   LAUNCH(k_gather<Hit>, grid_threads(n_ok), 256, s_, hits.get(), perm.get(), n_ok, lvl.hits.get());
   if (p_.store_cigar) {

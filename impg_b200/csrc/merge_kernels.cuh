@@ -300,15 +300,22 @@ __global__ void k_boxes_from_sorted_level(const Hit *__restrict__ hits, uint64_t
 }
 
 // hits of the last level in task order (frontier range, sorted position); ord from (range, visit rank)
-__global__ void k_boxes_from_raw_level(const Hit *__restrict__ hits, const LiftTask *__restrict__ tasks, uint64_t n,
-                                       uint32_t level, int32_t min_out, BoxD *__restrict__ out,
-                                       unsigned long long *__restrict__ n_valid) {
+// With a locality-permuted frontier (`orig` != nullptr) the boxes are written
+// back in the reference's frontier order (dst_off = offsets of the ranges in
+// that order), so the merge sorts see row-grouped input.
+__global__ void k_boxes_from_raw_level(const Hit *__restrict__ hits, const LiftTask *__restrict__ tasks,
+                                       const uint32_t *__restrict__ orig, const uint64_t *__restrict__ offs,
+                                       const uint64_t *__restrict__ dst_off, uint64_t n, uint32_t level, int32_t min_out,
+                                       BoxD *__restrict__ out, unsigned long long *__restrict__ n_valid) {
   unsigned long long c = 0;
   for (uint64_t i = gtid(); i < n; i += gstride()) {
     Hit h = hits[i];
     bool ok = h.row != INVALID_ID && passes_len(h, min_out);
-    out[i] = BoxD{h.q_first, h.q_last, h.t_first, h.t_last, h.q_id, h.t_id, h.row, ok ? 1u : 0u,
-                  make_ord(level, ((uint64_t)tasks[i].range << 32) | h.vrank)};
+    const uint32_t k = tasks[i].range;
+    const uint32_t r = orig ? orig[k] : k;
+    const uint64_t dst = orig ? dst_off[r] + (i - offs[k]) : i;
+    out[dst] = BoxD{h.q_first, h.q_last, h.t_first, h.t_last, h.q_id, h.t_id, h.row, ok ? 1u : 0u,
+                    make_ord(level, ((uint64_t)r << 32) | h.vrank)};
     c += ok ? 1 : 0;
   }
   if (c) atomicAdd(n_valid, c);
@@ -486,6 +493,12 @@ __global__ void k_sweep_compact_direct(const BoxD *__restrict__ out, const uint3
     }
     if (c) atomicAdd(&row_cnt[out[b].row], c);
   }
+}
+
+// counts in processing order -> counts in reference frontier order
+__global__ void k_scatter_counts(const uint32_t *__restrict__ counts, const uint32_t *__restrict__ orig, uint64_t n,
+                                 uint64_t *__restrict__ out) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) out[orig[i]] = counts[i];
 }
 
 __global__ void k_keys_shift(const uint64_t *__restrict__ keys, uint64_t n, int shift, uint64_t *__restrict__ out) {
