@@ -981,8 +981,8 @@ void Runner::bed_merge_direct(BedSink &sink, uint32_t n_rows, BatchOut &out) {
       // ---- stage A: group by (row, q, t, strand), pairwise union-find
       DBuf<BoxD> acc(nv, ar_);
       DBuf<uint64_t> is_root(nv, ar_);
+      DBuf<uint64_t> ka(nB, ar_);
       {
-        DBuf<uint64_t> ka(nB, ar_);
         DBuf<uint32_t> perm(nB, ar_);
         LAUNCH(k_bd_key_a, grid_threads(nB), 256, s_, sink.boxes.get(), nB, seq_bits, 1ull << bits_a, ka.get(),
                perm.get());
@@ -993,35 +993,89 @@ void Runner::bed_merge_direct(BedSink &sink, uint32_t n_rows, BatchOut &out) {
         LAUNCH(k_merge2d_direct, grid_threads(g.G, 128, 16), 128, s_, sink.boxes.get(), perm.get(), g.begins.get(), g.G,
                (int64_t)d, parent.get(), acc.get(), is_root.get());
       }
-      // ---- stage B: sort by (row, q, start, strand), sweep per (row, q)
-      DBuf<uint64_t> kb(nv, ar_);
-      DBuf<uint32_t> permb(nv, ar_);
-      LAUNCH(k_bd_key_b, grid_threads(nv), 256, s_, acc.get(), is_root.get(), (uint64_t)nv, seq_bits, 1ull << bits_b,
-             kb.get(), permb.get(), sink.counters.get() + 1);
-      sort_pairs(kb, permb, nv, 0, bits_b + 1, sc_, s_, ctx);
-      unsigned long long nr = 0;
-      CUDA_CHECK(cudaMemcpyAsync(&nr, sink.counters.get() + 1, 8, cudaMemcpyDeviceToHost, s_));
-      CUDA_CHECK(cudaStreamSynchronize(s_));
-      ctx.d2h_bytes += 8;
-      DBuf<BoxD> sorted(nr, ar_);
-      LAUNCH(k_gather<BoxD>, grid_threads(nr), 256, s_, acc.get(), permb.get(), (uint64_t)nr, sorted.get());
-      DBuf<uint64_t> seg(nr, ar_);
-      LAUNCH(k_keys_shift, grid_threads(nr), 256, s_, kb.get(), (uint64_t)nr, 33, seg.get());
-      Groups g;
-      build_groups(seg.get(), nr, g, sc_, s_, ctx);
-      DBuf<BoxD> swept(nr, ar_);
-      DBuf<uint32_t> cnt(g.G, ar_);
-      LAUNCH(k_sweep_direct, grid_threads(g.G, 128, 16), 128, s_, sorted.get(), kb.get(), g.begins.get(), g.G, d,
-             ms ? 1 : 0, swept.get(), cnt.get());
-      DBuf<uint64_t> scan(g.G + 1, ar_);
-      CUDA_CHECK(cudaMemsetAsync(scan.get() + g.G, 0, 8, s_));
-      LAUNCH(k_u32_to_u64, grid_threads(g.G), 256, s_, cnt.get(), g.G, scan.get());
-      exclusive_scan_u64(scan.get(), g.G + 1, sc_, s_);
-      ctx.launches += 2;
-      const uint64_t M = read_u64(scan.get() + g.G, s_, ctx);
-      alloc_out(M);
-      LAUNCH(k_sweep_compact_direct, grid_threads(g.G), 256, s_, swept.get(), g.begins.get(), cnt.get(), scan.get(), g.G,
-             oc, row_cnt.get());
+      // ---- stage B. The boxes are already grouped by (row, q): sort each segment by
+      // (start, strand, ord) in shared memory and sweep it (no second global sort).
+      bool done_b = false;
+      if (getenv("IMPGX_MERGE_SMEM")) {  // measured slower than the global sort on C3 and C4; kept for experiments
+        DBuf<uint64_t> seg(nv, ar_);
+        LAUNCH(k_keys_shift, grid_threads(nv), 256, s_, ka.get(), (uint64_t)nv, seq_bits + 1, seg.get());
+        Groups g;
+        build_groups(seg.get(), nv, g, sc_, s_, ctx);
+        DBuf<uint32_t> list_warp(g.G, ar_), list_cta(g.G, ar_);
+        DBuf<unsigned int> cls(4, ar_);
+        CUDA_CHECK(cudaMemsetAsync(cls.get(), 0, 16, s_));
+        LAUNCH(k_seg_classify, grid_threads(g.G), 256, s_, g.begins.get(), g.G, is_root.get(), list_warp.get(),
+               list_cta.get(), cls.get());
+        unsigned int hc[4];
+        CUDA_CHECK(cudaMemcpyAsync(hc, cls.get(), 16, cudaMemcpyDeviceToHost, s_));
+        CUDA_CHECK(cudaStreamSynchronize(s_));
+        ctx.d2h_bytes += 16;
+        if (hc[2] == 0) {
+          DBuf<BoxD> swept(nv, ar_);
+          DBuf<uint32_t> cnt(g.G, ar_);
+          if (hc[0]) {
+            auto kern = k_segment_sweep<32, SEG_WARP_CAP>;
+            const size_t smem = (size_t)4 * SEG_WARP_CAP * 24;
+            CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const unsigned grid = (unsigned)std::min<uint64_t>((hc[0] + 3) / 4, (uint64_t)sm_count() * 4);
+            kern<<<grid, 128, smem, s_>>>(acc.get(), is_root.get(), g.begins.get(), list_warp.get(), hc[0], d, ms ? 1 : 0,
+                                          swept.get(), cnt.get());
+            CUDA_CHECK(cudaGetLastError());
+            ctx.launches++;
+          }
+          if (hc[1]) {
+            auto kern = k_segment_sweep<256, SEG_CTA_CAP>;
+            const size_t smem = (size_t)SEG_CTA_CAP * 24;
+            CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const unsigned grid = (unsigned)std::min<uint64_t>(hc[1], (uint64_t)sm_count() * 2);
+            kern<<<grid, 256, smem, s_>>>(acc.get(), is_root.get(), g.begins.get(), list_cta.get(), hc[1], d, ms ? 1 : 0,
+                                          swept.get(), cnt.get());
+            CUDA_CHECK(cudaGetLastError());
+            ctx.launches++;
+          }
+          DBuf<uint64_t> scan(g.G + 1, ar_);
+          CUDA_CHECK(cudaMemsetAsync(scan.get() + g.G, 0, 8, s_));
+          LAUNCH(k_u32_to_u64, grid_threads(g.G), 256, s_, cnt.get(), g.G, scan.get());
+          exclusive_scan_u64(scan.get(), g.G + 1, sc_, s_);
+          ctx.launches += 2;
+          const uint64_t M = read_u64(scan.get() + g.G, s_, ctx);
+          alloc_out(M);
+          LAUNCH(k_sweep_compact_direct, grid_threads(g.G), 256, s_, swept.get(), g.begins.get(), cnt.get(), scan.get(),
+                 g.G, oc, row_cnt.get());
+          done_b = true;
+        }
+      }
+      if (!done_b) {
+        // fallback: global sort by (row, q, start, strand), sweep per (row, q)
+        DBuf<uint64_t> kb(nv, ar_);
+        DBuf<uint32_t> permb(nv, ar_);
+        LAUNCH(k_bd_key_b, grid_threads(nv), 256, s_, acc.get(), is_root.get(), (uint64_t)nv, seq_bits, 1ull << bits_b,
+               kb.get(), permb.get(), sink.counters.get() + 1);
+        sort_pairs(kb, permb, nv, 0, bits_b + 1, sc_, s_, ctx);
+        unsigned long long nr = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&nr, sink.counters.get() + 1, 8, cudaMemcpyDeviceToHost, s_));
+        CUDA_CHECK(cudaStreamSynchronize(s_));
+        ctx.d2h_bytes += 8;
+        DBuf<BoxD> sorted(nr, ar_);
+        LAUNCH(k_gather<BoxD>, grid_threads(nr), 256, s_, acc.get(), permb.get(), (uint64_t)nr, sorted.get());
+        DBuf<uint64_t> seg(nr, ar_);
+        LAUNCH(k_keys_shift, grid_threads(nr), 256, s_, kb.get(), (uint64_t)nr, 33, seg.get());
+        Groups g;
+        build_groups(seg.get(), nr, g, sc_, s_, ctx);
+        DBuf<BoxD> swept(nr, ar_);
+        DBuf<uint32_t> cnt(g.G, ar_);
+        LAUNCH(k_sweep_direct, grid_threads(g.G, 128, 16), 128, s_, sorted.get(), kb.get(), g.begins.get(), g.G, d,
+               ms ? 1 : 0, swept.get(), cnt.get());
+        DBuf<uint64_t> scan(g.G + 1, ar_);
+        CUDA_CHECK(cudaMemsetAsync(scan.get() + g.G, 0, 8, s_));
+        LAUNCH(k_u32_to_u64, grid_threads(g.G), 256, s_, cnt.get(), g.G, scan.get());
+        exclusive_scan_u64(scan.get(), g.G + 1, sc_, s_);
+        ctx.launches += 2;
+        const uint64_t M = read_u64(scan.get() + g.G, s_, ctx);
+        alloc_out(M);
+        LAUNCH(k_sweep_compact_direct, grid_threads(g.G), 256, s_, swept.get(), g.begins.get(), cnt.get(), scan.get(),
+               g.G, oc, row_cnt.get());
+      }
     }
     LAUNCH(k_u32_to_u64, grid_threads(n_rows), 256, s_, row_cnt.get(), n_rows, out.row_off.get());
     exclusive_scan_u64(out.row_off.get(), (uint64_t)n_rows + 1, sc_, s_);
