@@ -333,6 +333,35 @@ def format_paf(idx, results, row, name, merge_distance):
     return _format_rows(lib().impgx_format_paf, idx, results, row, name, merge_distance)
 
 
+def parse_bed_file(path):
+    """parse_bed_file (reference src/commands/partition.rs:1719-1753) -> [(seq, (start, end), name)]."""
+    L = lib()
+    L.impgx_bed_len.restype = C.c_size_t
+    for f in ("impgx_bed_seq", "impgx_bed_name"):
+        getattr(L, f).restype = C.c_char_p
+    for f in ("impgx_bed_start", "impgx_bed_end"):
+        getattr(L, f).restype = C.c_int32
+    h = C.c_void_p()
+    _check(L.impgx_bed_parse(path.encode(), C.byref(h)))
+    try:
+        n = L.impgx_bed_len(h)
+        return [(L.impgx_bed_seq(h, C.c_size_t(i)).decode(),
+                 (L.impgx_bed_start(h, C.c_size_t(i)), L.impgx_bed_end(h, C.c_size_t(i))),
+                 L.impgx_bed_name(h, C.c_size_t(i)).decode()) for i in range(n)]
+    finally:
+        L.impgx_bed_free(h)
+
+
+def parse_target_range(text):
+    """parse_target_range (reference src/commands/partition.rs:1755-1768): split on the LAST ':'."""
+    seq = C.create_string_buffer(4096)
+    name = C.create_string_buffer(4200)
+    s, e = C.c_int32(), C.c_int32()
+    _check(lib().impgx_parse_target_range(text.encode(), seq, C.c_size_t(4096), C.byref(s), C.byref(e), name,
+                                          C.c_size_t(4200)))
+    return seq.value.decode(), (s.value, e.value), name.value.decode()
+
+
 def project_batch(req, records, runs, run_offsets, device=0, want_cigar=True):
     """project_target_range_through_alignment for n independent problems on the GPU
     (reference src/impg.rs:2760-2898). records[i].reserved bit 0 marks a reversed entry."""

@@ -1,4 +1,6 @@
 // api.cu — the extern "C" boundary (include/impgx.h). No exception crosses it.
+#include <zlib.h>
+
 #include <cstring>
 #include <fstream>
 #include <sstream>
@@ -67,13 +69,20 @@ static bool parse_usize(const char *b, const char *e, uint64_t &v) {
 // parse_paf_line / parse_paf (src/paf.rs:118-194) with SequenceIndex ids by
 // first appearance (src/seqidx.rs:22-35). The CIGAR is decoded here, once.
 void parse_paf(const std::string &path, PafData &out) {
-  std::ifstream f(path, std::ios::binary);
-  REQUIRE(f.good(), IMPGX_E_IO, "cannot open PAF file '" + path + "'");
-  std::stringstream ss;
-  ss << f.rdbuf();
-  const std::string data = ss.str();
-  REQUIRE(!(data.size() >= 2 && (unsigned char)data[0] == 0x1f && (unsigned char)data[1] == 0x8b), IMPGX_E_UNSUPPORTED,
-          "compressed PAF is not supported yet; decompress first");
+  // gzopen reads plain text transparently and inflates gzip / BGZF (a BGZF file
+  // is a series of gzip members, src/paf.rs:199-302); the CIGARs are decoded
+  // here once, so no virtual offsets need to be kept.
+  gzFile gz = gzopen(path.c_str(), "rb");
+  REQUIRE(gz != nullptr, IMPGX_E_IO, "cannot open PAF file '" + path + "'");
+  std::string data;
+  {
+    std::vector<char> buf(1 << 20);
+    int k;
+    while ((k = gzread(gz, buf.data(), (unsigned)buf.size())) > 0) data.append(buf.data(), (size_t)k);
+    const bool bad = k < 0;
+    gzclose(gz);
+    REQUIRE(!bad, IMPGX_E_IO, "error while reading / inflating '" + path + "'");
+  }
   size_t pos = 0, line_no = 0;
   auto get_id = [&](const char *b, const char *e, uint64_t len) {
     std::string name(b, e);
@@ -358,6 +367,124 @@ char *impgx_format_paf(const impgx_index *idx, const impgx_results *res, size_t 
 }
 
 void impgx_free(void *p) { free(p); }
+
+// ---- BED / range parsing (src/commands/partition.rs:1719-1789)
+}  // extern "C"
+struct impgx_bed {
+  std::vector<std::string> seq, name;
+  std::vector<int32_t> start, end;
+};
+namespace {
+bool parse_i32(const std::string &t, int32_t &v) {
+  // Rust i32::from_str: optional sign, digits only, no whitespace
+  if (t.empty()) return false;
+  size_t i = 0;
+  bool neg = false;
+  if (t[0] == '+' || t[0] == '-') {
+    neg = t[0] == '-';
+    i = 1;
+  }
+  if (i >= t.size()) return false;
+  int64_t x = 0;
+  for (; i < t.size(); i++) {
+    if (t[i] < '0' || t[i] > '9') return false;
+    x = x * 10 + (t[i] - '0');
+    if (x > (int64_t)INT32_MAX + 1) return false;
+  }
+  x = neg ? -x : x;
+  if (x > INT32_MAX || x < INT32_MIN) return false;
+  v = (int32_t)x;
+  return true;
+}
+void parse_range(const std::string &a, const std::string &b, int32_t &s, int32_t &e) {
+  REQUIRE(parse_i32(a, s), IMPGX_E_PARSE, "Invalid start value");
+  REQUIRE(parse_i32(b, e), IMPGX_E_PARSE, "Invalid end value");
+  REQUIRE(s < e, IMPGX_E_PARSE, "Start value must be less than end value");
+}
+std::string trim(const std::string &t) {
+  size_t a = 0, b = t.size();
+  while (a < b && isspace((unsigned char)t[a])) a++;
+  while (b > a && isspace((unsigned char)t[b - 1])) b--;
+  return t.substr(a, b - a);
+}
+}  // namespace
+extern "C" {
+
+int impgx_bed_parse(const char *path, impgx_bed **out) {
+  API_BEGIN
+  REQUIRE(path && out, IMPGX_E_INVALID, "NULL argument");
+  *out = nullptr;
+  std::ifstream f(path, std::ios::binary);
+  REQUIRE(f.good(), IMPGX_E_IO, std::string("cannot open BED file '") + path + "'");
+  std::unique_ptr<impgx_bed> bed(new impgx_bed());
+  std::string line;
+  while (std::getline(f, line)) {
+    if (!line.empty() && line.back() == '\r') line.pop_back();
+    std::vector<std::string> parts;
+    size_t a = 0;
+    for (;;) {
+      size_t b = line.find('\t', a);
+      if (b == std::string::npos) {
+        parts.push_back(line.substr(a));
+        break;
+      }
+      parts.push_back(line.substr(a, b - a));
+      a = b + 1;
+    }
+    REQUIRE(parts.size() >= 3, IMPGX_E_PARSE, "Invalid BED file format");
+    int32_t s, e;
+    parse_range(parts[1], parts[2], s, e);
+    std::string name;
+    if (parts.size() > 3) {
+      name = trim(parts[3]);
+      if (name == ".") name.clear();
+    }
+    if (name.empty()) name = parts[0] + ":" + std::to_string(s) + "-" + std::to_string(e);
+    bed->seq.push_back(parts[0]);
+    bed->name.push_back(name);
+    bed->start.push_back(s);
+    bed->end.push_back(e);
+  }
+  *out = bed.release();
+  API_END
+}
+size_t impgx_bed_len(const impgx_bed *b) { return b ? b->seq.size() : 0; }
+const char *impgx_bed_seq(const impgx_bed *b, size_t i) { return (b && i < b->seq.size()) ? b->seq[i].c_str() : nullptr; }
+const char *impgx_bed_name(const impgx_bed *b, size_t i) { return (b && i < b->name.size()) ? b->name[i].c_str() : nullptr; }
+int32_t impgx_bed_start(const impgx_bed *b, size_t i) { return (b && i < b->start.size()) ? b->start[i] : 0; }
+int32_t impgx_bed_end(const impgx_bed *b, size_t i) { return (b && i < b->end.size()) ? b->end[i] : 0; }
+void impgx_bed_free(impgx_bed *b) { delete b; }
+
+int impgx_parse_target_range(const char *text, char *seq_out, size_t seq_cap, int32_t *start, int32_t *end,
+                             char *name_out, size_t name_cap) {
+  API_BEGIN
+  REQUIRE(text && seq_out && start && end, IMPGX_E_INVALID, "NULL argument");
+  const std::string t(text);
+  const size_t c = t.rfind(':');
+  REQUIRE(c != std::string::npos, IMPGX_E_PARSE, "Target range format should be `seq_name:start-end`");
+  const std::string seq = t.substr(0, c), rng = t.substr(c + 1);
+  std::vector<std::string> p;
+  size_t a = 0;
+  for (;;) {
+    size_t b = rng.find('-', a);
+    if (b == std::string::npos) {
+      p.push_back(rng.substr(a));
+      break;
+    }
+    p.push_back(rng.substr(a, b - a));
+    a = b + 1;
+  }
+  REQUIRE(p.size() == 2, IMPGX_E_PARSE, "Range format should be `start-end`");
+  parse_range(p[0], p[1], *start, *end);
+  REQUIRE(seq.size() + 1 <= seq_cap, IMPGX_E_INVALID, "seq_out too small");
+  memcpy(seq_out, seq.c_str(), seq.size() + 1);
+  if (name_out) {
+    const std::string name = seq + ":" + std::to_string(*start) + "-" + std::to_string(*end);
+    REQUIRE(name.size() + 1 <= name_cap, IMPGX_E_INVALID, "name_out too small");
+    memcpy(name_out, name.c_str(), name.size() + 1);
+  }
+  API_END
+}
 
 // ---- debug / test hooks (host only, usable without a GPU)
 // visit ranks of a target with n entries

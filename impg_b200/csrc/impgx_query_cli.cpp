@@ -1,0 +1,177 @@
+// impgx-query — command-line driver over libimpgx's C ABI that mirrors the
+// flags of `impg query` for the PAF -> BED / BEDPE / PAF path (reference
+// src/main.rs:6513-7496, option structs :4259-4410). It exists so the drop-in
+// can be exercised end to end exactly like the reference binary:
+//
+//   impgx-query -a X.paf -b regions.bed -x -m 2 -d 1000 -o bed
+//
+// Only the path of SURVEY.md §8 is supported; everything else the reference's
+// `query` offers (gfa/maf/fasta outputs, tracepoint inputs, --approximate, …)
+// is rejected with an error.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <string>
+#include <vector>
+
+#include "../../include/impgx.h"
+
+static void die(const std::string &m) {
+  fprintf(stderr, "Error: %s\n", m.c_str());
+  exit(1);
+}
+static void check(int code) {
+  if (code != 0) die(impgx_last_error());
+}
+
+// parse_merge_distance: integer with optional k/m/g suffix (src/main.rs: parse_merge_distance)
+static int32_t parse_distance(const std::string &s) {
+  if (s.empty()) die("empty merge distance");
+  double mul = 1;
+  std::string num = s;
+  char c = (char)tolower((unsigned char)s.back());
+  if (c == 'k' || c == 'm' || c == 'g') {
+    mul = c == 'k' ? 1e3 : (c == 'm' ? 1e6 : 1e9);
+    num = s.substr(0, s.size() - 1);
+  }
+  char *end = nullptr;
+  double v = strtod(num.c_str(), &end);
+  if (!end || *end || v < 0 || v * mul > 2147483647.0) die("invalid merge distance '" + s + "'");
+  return (int32_t)llround(v * mul);
+}
+
+int main(int argc, char **argv) {
+  std::string paf, bed_path, range_text, out_format = "auto", subset_path;
+  bool transitive = false, dfs = false, unidirectional = false, consider_strand = false, no_merge = false, have_d = false;
+  int32_t d = 0, min_transitive_len = 101, min_dist = 10, min_out = -1;
+  uint32_t max_depth = 2;
+  double min_identity = NAN;
+  int device = 0;
+  for (int i = 1; i < argc; i++) {
+    std::string a = argv[i];
+    auto val = [&]() -> std::string {
+      if (i + 1 >= argc) die("missing value for " + a);
+      return argv[++i];
+    };
+    if (a == "-a" || a == "--alignment-files") paf = val();
+    else if (a == "-b" || a == "--target-bed") bed_path = val();
+    else if (a == "-r" || a == "--target-range") range_text = val();
+    else if (a == "-x" || a == "--transitive") transitive = true;
+    else if (a == "--transitive-dfs") dfs = true;
+    else if (a == "-m" || a == "--max-depth") max_depth = (uint32_t)atoi(val().c_str());
+    else if (a == "-d" || a == "--merge-distance") { d = parse_distance(val()); have_d = true; }
+    else if (a == "--no-merge") no_merge = true;
+    else if (a == "-l" || a == "--min-output-length") min_out = atoi(val().c_str());
+    else if (a == "-o" || a == "--output-format") out_format = val();
+    else if (a == "--min-transitive-len") min_transitive_len = atoi(val().c_str());
+    else if (a == "--min-distance-between-ranges") min_dist = atoi(val().c_str());
+    else if (a == "--unidirectional") unidirectional = true;
+    else if (a == "--consider-strandness") consider_strand = true;
+    else if (a == "--min-result-identity") min_identity = atof(val().c_str());
+    else if (a == "--subset-sequence-list") subset_path = val();
+    else if (a == "--device") device = atoi(val().c_str());
+    else if (a == "-h" || a == "--help") {
+      printf("usage: impgx-query -a X.paf (-b BED | -r seq:start-end) [-x] [-m N] (-d D | --no-merge) [-l L]\n"
+             "       [-o auto|bed|bedpe|paf] [--min-transitive-len N] [--min-distance-between-ranges N]\n"
+             "       [--transitive-dfs] [--unidirectional] [--consider-strandness] [--min-result-identity F]\n"
+             "       [--subset-sequence-list FILE] [--device N]\n");
+      return 0;
+    } else die("unsupported option '" + a + "' (only the PAF -> BED/BEDPE/PAF query path is implemented)");
+  }
+  if (paf.empty()) die("-a/--alignment-files is required");
+  if (bed_path.empty() == range_text.empty()) die("exactly one of -r/--target-range and -b/--target-bed is required");
+  if (have_d && no_merge) die("-d and --no-merge are mutually exclusive");
+  if (!have_d && !no_merge)
+    die("-d/--merge-distance is required. Use `--no-merge` to explicitly disable merging.");  // src/main.rs:4288-4315
+  if (no_merge) d = -1;
+  if (out_format == "auto") out_format = range_text.empty() ? "bedpe" : "bed";  // src/main.rs:7365-7373
+  if (out_format != "bed" && out_format != "bedpe" && out_format != "paf")
+    die("output format '" + out_format + "' is outside the accelerated path (bed, bedpe, paf)");
+
+  impgx_index *idx = nullptr;
+  check(impgx_index_from_paf(paf.c_str(), unidirectional ? 0 : 1, device, &idx));
+
+  // rows
+  std::vector<impgx_range> rows;
+  std::vector<std::string> names;
+  auto add_row = [&](const std::string &seq, int32_t s, int32_t e, const std::string &name) {
+    uint32_t id = 0;
+    if (impgx_index_seq_id(idx, seq.c_str(), &id) != 0) die("Sequence '" + seq + "' not found in index");
+    // validate_sequence_range / validate_range_min_length (src/main.rs:10387-10512)
+    if (s < 0) die("Start position " + std::to_string(s) + " cannot be negative");
+    if (s >= e) die("Start position " + std::to_string(s) + " must be less than end position " + std::to_string(e));
+    if ((uint64_t)e > impgx_index_seq_len(idx, id))
+      die("End position " + std::to_string(e) + " exceeds sequence length " + std::to_string(impgx_index_seq_len(idx, id)) +
+          " for sequence '" + seq + "'");
+    if (e - s < min_transitive_len)
+      die("Range '" + name + "' (" + std::to_string(e - s) + " bp) is below minimum of " + std::to_string(min_transitive_len) +
+          " bp. Lower --min-transitive-len or use a longer range");
+    rows.push_back(impgx_range{id, s, e});
+    names.push_back(name);
+  };
+  if (!range_text.empty()) {
+    char seq[4096], name[4200];
+    int32_t s, e;
+    check(impgx_parse_target_range(range_text.c_str(), seq, sizeof seq, &s, &e, name, sizeof name));
+    add_row(seq, s, e, name);
+  } else {
+    impgx_bed *bed = nullptr;
+    check(impgx_bed_parse(bed_path.c_str(), &bed));
+    for (size_t i = 0; i < impgx_bed_len(bed); i++)
+      add_row(impgx_bed_seq(bed, i), impgx_bed_start(bed, i), impgx_bed_end(bed, i), impgx_bed_name(bed, i));
+    impgx_bed_free(bed);
+  }
+
+  // subset list: exact names, or names without the ":coords" suffix (src/subset_filter.rs:23-41;
+  // the PanSN sample / haplotype shorthands of the reference are not implemented)
+  std::vector<uint8_t> mask;
+  if (!subset_path.empty()) {
+    std::ifstream f(subset_path);
+    if (!f.good()) die("Failed to read subset sequence list '" + subset_path + "'");
+    mask.assign(impgx_index_num_seqs(idx), 0);
+    std::string line;
+    size_t entries = 0;
+    while (std::getline(f, line)) {
+      while (!line.empty() && isspace((unsigned char)line.back())) line.pop_back();
+      if (line.empty() || line[0] == '#') continue;
+      entries++;
+      for (uint32_t s = 0; s < mask.size(); s++) {
+        const char *nm = impgx_index_seq_name(idx, s);
+        if (!nm) continue;
+        std::string n(nm);
+        if (n == line || n.substr(0, n.find(':')) == line) mask[s] = 1;
+      }
+    }
+    if (!entries) die("Subset sequence list '" + subset_path + "' did not contain any sequence names");
+  }
+
+  impgx_params p;
+  memset(&p, 0, sizeof p);
+  p.mode = transitive ? (dfs ? IMPGX_MODE_DFS : IMPGX_MODE_BFS) : IMPGX_MODE_QUERY;
+  p.max_depth = max_depth;
+  p.min_transitive_len = min_transitive_len;
+  p.min_distance_between_ranges = min_dist;
+  p.min_output_length = min_out;
+  p.store_cigar = out_format == "bed" ? 0 : 1;  // src/main.rs:7447
+  p.min_identity = min_identity;
+  p.subset_mask = mask.empty() ? nullptr : mask.data();
+  p.merge_distance = d;
+  p.merge_strands = consider_strand ? 0 : 1;  // src/main.rs:4395-4409
+
+  impgx_results *res = nullptr;
+  if (out_format == "bed") check(impgx_query_batch_bed(idx, rows.data(), rows.size(), &p, &res));
+  else check(impgx_query_batch(idx, rows.data(), rows.size(), &p, &res));
+  for (size_t r = 0; r < rows.size(); r++) {
+    char *text = out_format == "bed"     ? impgx_format_bed(idx, res, r, names[r].c_str())
+                 : out_format == "bedpe" ? impgx_format_bedpe(idx, res, r, names[r].c_str(), d)
+                                         : impgx_format_paf(idx, res, r, names[r].c_str(), d);
+    if (!text) die(impgx_last_error());
+    fputs(text, stdout);
+    impgx_free(text);
+  }
+  impgx_results_free(res);
+  impgx_index_free(idx);
+  return 0;
+}

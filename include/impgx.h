@@ -208,6 +208,20 @@ int impgx_project_batch(int device, size_t n, const int32_t *req_start,
                         int32_t *out4, uint8_t *ok, uint64_t *out_run_offsets,
                         uint32_t *out_runs, size_t out_runs_cap);
 
+/* BED / range parsing of the query driver (src/commands/partition.rs:1719-1789):
+ * >= 3 tab-separated fields, start < end, row name = column 4 unless empty or
+ * ".", else "chrom:start-end"; `-r` text is split on the LAST ':'. */
+typedef struct impgx_bed impgx_bed;
+int impgx_bed_parse(const char *path, impgx_bed **out);
+size_t impgx_bed_len(const impgx_bed *bed);
+const char *impgx_bed_seq(const impgx_bed *bed, size_t i);
+const char *impgx_bed_name(const impgx_bed *bed, size_t i);
+int32_t impgx_bed_start(const impgx_bed *bed, size_t i);
+int32_t impgx_bed_end(const impgx_bed *bed, size_t i);
+void impgx_bed_free(impgx_bed *bed);
+int impgx_parse_target_range(const char *text, char *seq_out, size_t seq_cap,
+                             int32_t *start, int32_t *end, char *name_out, size_t name_cap);
+
 /* Host-side text helpers mirroring the reference's parsers and writers. */
 /* parse_cigar_to_delta (src/impg.rs:2935-2950). Returns run count or <0. */
 long impgx_parse_cigar(const char *text, size_t len, uint32_t *out, size_t cap);

@@ -347,3 +347,86 @@ def test_medium_scale_properties():
         assert (s[1:][same] > e[:-1][same] + 1000).all()
     st = gpu.stats()
     assert st["liftovers"] > 0 and st["kernel_launches"] > 0 and st["lift_ms"] > 0
+
+
+def test_cli_driver_matches_golden_and_oracle(tmp_path):
+    """impgx-query (the `impg query` look-alike) end to end: BASELINE config 1 plus a BED batch
+    with -x, all three output formats, and a gzip-compressed PAF."""
+    import gzip
+    import subprocess
+    cli = os.path.join(os.path.dirname(GOLD), "..", "impg_b200", "impgx-query")
+    paf = os.path.join(GOLD, "short_floor.paf")
+    out = subprocess.run([cli, "-a", paf, "-r", "C4FIXTURE#0#short_floor:0-250:0-250", "-d", "0",
+                          "--min-transitive-len", "0", "-o", "bed"], capture_output=True, text=True, check=True).stdout
+    c = [x for x in GOLDEN["short_floor.paf"] if x["seq"] == "C4FIXTURE#0#short_floor:0-250" and x["start"] == 0 and
+         x["end"] == 250 and x["mode"] == 0 and x["d"] == 0 and x["format"] == "bed"][0]
+    assert out == c["text"]
+    # BED batch, transitive, every format, against the oracle's writers; PAF read through gzip
+    gz = tmp_path / "short_floor.paf.gz"
+    gz.write_bytes(gzip.compress(open(paf, "rb").read()))
+    orc = O.Index.from_paf(paf)
+    bed = tmp_path / "q.bed"
+    rows = [(orc.seq_name(s), 0, orc.seq_len(s), "." if s % 2 else f"row{s}") for s in range(orc.n_seqs)]
+    bed.write_text("".join(f"{a}\t{b}\t{c}\t{d}\n" for a, b, c, d in rows))
+    for fmt in ("bed", "bedpe", "paf"):
+        got = subprocess.run([cli, "-a", str(gz), "-b", str(bed), "-x", "-m", "3", "-d", "50", "--min-transitive-len", "0",
+                              "-o", fmt], capture_output=True, text=True, check=True).stdout
+        want = ""
+        for a, b, c, d in rows:
+            name = d if d != "." else f"{a}:{b}-{c}"
+            p = O.make_params(mode=O.MODE_BFS, max_depth=3, min_transitive_len=0, merge_distance=50,
+                              store_cigar=fmt != "bed")
+            res = orc.perform_query(orc.seq_id(a), b, c, p)
+            if fmt != "bed":
+                res.drop_first()
+            want += orc.format(res, fmt, name, 50)
+        assert got == want, fmt
+    # default --min-transitive-len 101 rejects short rows like the reference (src/main.rs:10387-10403)
+    r = subprocess.run([cli, "-a", paf, "-r", "C4FIXTURE#0#short_floor:0-250:0-50", "-d", "0"], capture_output=True,
+                       text=True)
+    assert r.returncode != 0 and "below minimum of 101 bp" in r.stderr
+
+
+def test_full_size_c3_properties_and_sample_parity():
+    """BASELINE configs[2] at full size (50 genomes, 999,600 alignments, 10,000-row BED, -x -m 2,
+    -d 1000 -o bed): oracle parity on a row sample, size-independent properties on every row
+    (rows sorted by (sequence, start), merged rows further apart than -d, every row contains its
+    own query range, device-resident and host paths agree, checksum stable across two runs)."""
+    cfg = ix.synth_cfg(50, 8, 2500000, 51, 100, 100, 1)
+    recs, runs, offs, lens, names = ix.synth_generate(cfg)
+    assert len(recs) == 999600
+    gpu = ix.Impg.from_records(recs, runs, offs, lens, names=names)
+    bed = ix.synth_bed(cfg, 10000, seed=2)
+    o, g = params_pair(mode=1, max_depth=2, merge_distance=1000)
+    gc = gpu.query_batch_bed(bed, g).columns()
+    st = gpu.stats()
+    assert st["liftovers"] > 5e7 and st["lift_window_runs"] > st["liftovers"]
+    ro = gc["row_offsets"].astype(np.int64)
+    assert len(ro) == 10001 and (np.diff(ro) > 0).all()
+    lo = np.minimum(gc["q_first"], gc["q_last"]).astype(np.int64)
+    hi = np.maximum(gc["q_first"], gc["q_last"]).astype(np.int64)
+    rowid = np.repeat(np.arange(10000), np.diff(ro))
+    key = (rowid.astype(np.int64) << 44) + (gc["q_id"].astype(np.int64) << 32) + lo
+    assert (np.diff(key) > 0).all()                                   # sorted, no duplicates
+    same = (rowid[1:] == rowid[:-1]) & (gc["q_id"][1:] == gc["q_id"][:-1])
+    assert (lo[1:][same] > hi[:-1][same] + 1000).all()                # nothing left to merge
+    # the self interval survives inside a merged row on the query's own sequence
+    for r in range(0, 10000, 97):
+        a, b = ro[r], ro[r + 1]
+        m = gc["q_id"][a:b] == bed["target_id"][r]
+        assert ((lo[a:b][m] <= bed["start"][r]) & (hi[a:b][m] >= bed["end"][r])).any()
+    # idempotence / determinism: a second run gives the same bytes
+    gc2 = gpu.query_batch_bed(bed, g).columns()
+    for k in ("row_offsets", "q_id", "q_first", "q_last"):
+        assert (gc[k] == gc2[k]).all()
+    # oracle parity on a sample of rows (the oracle needs seconds per row at this size)
+    orc = O.Index.build(recs, runs, offs, lens, names=names)
+    sample = np.array([0, 1234, 5000, 7777, 9999])
+    ores, ooffs = orc.query_batch(bed[sample], o, bed_merge=True)
+    oc = ores.columns()
+    for j, r in enumerate(sample):
+        a, b = ro[r], ro[r + 1]
+        oa, ob = int(ooffs[j]), int(ooffs[j + 1])
+        assert b - a == ob - oa
+        for k in ("q_id", "q_first", "q_last"):
+            assert (gc[k][a:b] == oc[k][oa:ob]).all()

@@ -126,3 +126,36 @@ def test_write_cigar_text_roundtrip(tmp_path):
     for i in (0, 5, len(recs) - 1):
         txt = blob[int(o[i]):int(o[i] + l[i])].decode()
         assert list(O.parse_cigar(txt)) == list(runs[int(offs[i]):int(offs[i + 1])])
+
+
+def test_bed_and_range_parsers(tmp_path):
+    """parse_bed_file / parse_target_range semantics (reference src/commands/partition.rs:1719-1789)."""
+    p = tmp_path / "r.bed"
+    p.write_text("chr1\t10\t200\tgeneA\nchr2:0-50\t5\t40\t.\nchr3\t0\t7\n" "chr4\t1\t9\t  spaced  \textra\n")
+    rows = ix.parse_bed_file(str(p))
+    assert rows == [("chr1", (10, 200), "geneA"), ("chr2:0-50", (5, 40), "chr2:0-50:5-40"),
+                    ("chr3", (0, 7), "chr3:0-7"), ("chr4", (1, 9), "spaced")]
+    for bad in ("chr1\t10\n", "chr1\t20\t10\n", "chr1\t5\t5\n", "chr1\tx\t10\n", "chr1\t 1\t10\n"):
+        p.write_text(bad)
+        with pytest.raises(ix.ImpgxError) as e:
+            ix.parse_bed_file(str(p))
+        assert e.value.code == ix.E_PARSE
+    # names that contain ':' need the range appended, the split is on the last ':'
+    assert ix.parse_target_range("C4FIXTURE#0#short_floor:0-250:0-250") == (
+        "C4FIXTURE#0#short_floor:0-250", (0, 250), "C4FIXTURE#0#short_floor:0-250:0-250")
+    assert ix.parse_target_range("A:25-75") == ("A", (25, 75), "A:25-75")
+    for bad in ("A", "A:10", "A:10-5", "A:1-2-3", "A:x-9"):
+        with pytest.raises(ix.ImpgxError):
+            ix.parse_target_range(bad)
+
+
+def test_cli_fails_loudly_without_gpu():
+    if ix.device_count() > 0:
+        pytest.skip("a GPU is present")
+    import subprocess
+    cli = os.path.join(ROOT, "impg_b200", "impgx-query")
+    r = subprocess.run([cli, "-a", os.path.join(ROOT, "tests", "golden", "short_floor.paf"), "-r",
+                        "C4FIXTURE#0#short_floor:0-250:0-250", "-d", "0"], capture_output=True, text=True)
+    assert r.returncode != 0 and "no CUDA device" in r.stderr
+    r = subprocess.run([cli, "-a", "x.paf", "-r", "A:0-10"], capture_output=True, text=True)
+    assert r.returncode != 0 and "merge-distance is required" in r.stderr
