@@ -132,7 +132,8 @@ namespace impgx {
 template <class T>
 static T *upload(const std::vector<T> &h, uint64_t &bytes_acc) {
   T *d = nullptr;
-  size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+  // 16 bytes of slack: the stab kernels' bulk copies round the last tile up to 16 bytes
+  size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T) + 16;
   CUDA_CHECK(cudaMalloc((void **)&d, bytes));
   if (!h.empty()) CUDA_CHECK(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
   bytes_acc += bytes;

@@ -127,20 +127,81 @@ __device__ __forceinline__ Window stab_window(const DevIndexView &ix, uint32_t s
   return Window{lb, ub};
 }
 
-template <bool CLOSED>
-__global__ void __launch_bounds__(256) k_stab_count(DevIndexView ix, const Frontier *__restrict__ fr, uint64_t n,
-                                                    Window *__restrict__ win, uint32_t *__restrict__ counts) {
+// ---- TMA staging of interval tiles -------------------------------------------
+// A warp stages the candidate window of the e_end column into its slice of
+// shared memory with a 1-D bulk async copy (cp.async.bulk -> UBLKCP in SASS):
+// one elected lane arms the warp's mbarrier with the byte count and issues the
+// copy; every lane then waits on the barrier phase and scans the tile from
+// shared memory. Tiles start on 16-byte boundaries of the column (the column
+// is allocated with 16 bytes of slack so the last tile may round up).
+constexpr int STAB_TILE = 1024;  // int32 entries per warp tile (4 KB)
+constexpr int STAB_WARPS = 8;    // warps per CTA
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load_tile(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+  } while (!ok);
+}
+
+// Scans the window [lb, ub) of `col` tile by tile through shared memory and
+// calls f(i, value) for every index (all lanes of the warp participate; the
+// callback may use warp collectives: `i` may be >= ub for padding lanes, which
+// must be ignored via the `live` flag).
+template <class F>
+__device__ __forceinline__ void stab_scan_tiles(const int32_t *__restrict__ col, uint64_t lb, uint64_t ub, int32_t *tile,
+                                                uint64_t *bar, uint32_t &phase, F f) {
   const unsigned lane = lane_id();
+  for (uint64_t t0 = lb & ~(uint64_t)3; t0 < ub; t0 += STAB_TILE) {
+    const uint64_t rem = ub - t0;
+    const uint32_t n = (uint32_t)(rem < (uint64_t)STAB_TILE ? ((rem + 3) & ~(uint64_t)3) : (uint64_t)STAB_TILE);
+    __syncwarp();  // every lane is done reading the previous tile
+    if (lane == 0) bulk_load_tile(tile, col + t0, n * 4u, bar);
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+    for (uint32_t k0 = 0; k0 < n; k0 += 32) {
+      const uint32_t k = k0 + lane;
+      const uint64_t i = t0 + k;
+      const bool live = k < n && i >= lb && i < ub;
+      f(i, live ? tile[k] : 0, live);
+    }
+  }
+}
+
+template <bool CLOSED>
+__global__ void __launch_bounds__(32 * STAB_WARPS) k_stab_count(DevIndexView ix, const Frontier *__restrict__ fr, uint64_t n,
+                                                                Window *__restrict__ win, uint32_t *__restrict__ counts) {
+  __shared__ __align__(16) int32_t tiles[STAB_WARPS][STAB_TILE];
+  __shared__ uint64_t bars[STAB_WARPS];
+  const unsigned lane = lane_id(), wib = threadIdx.x >> 5;
+  if (lane == 0) mbar_init(&bars[wib], 1);
+  __syncwarp();
+  uint32_t phase = 0;
   uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   for (; w < n; w += nw) {
     Frontier f = fr[w];
     Window wd = stab_window<CLOSED>(ix, f.seq, f.start, f.end);
     uint32_t c = 0;
-    for (uint64_t i = wd.lb + lane; i < wd.ub; i += 32) {
-      int32_t e = ld_stream_i32(ix.e_end + i);
-      c += (CLOSED ? e >= f.start : e > f.start) ? 1u : 0u;
-    }
+    stab_scan_tiles(ix.e_end, wd.lb, wd.ub, tiles[wib], &bars[wib], phase, [&](uint64_t, int32_t e, bool live) {
+      c += (live && (CLOSED ? e >= f.start : e > f.start)) ? 1u : 0u;
+    });
 #pragma unroll
     for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(FULL, c, d);
     if (lane == 0) {
@@ -151,28 +212,28 @@ __global__ void __launch_bounds__(256) k_stab_count(DevIndexView ix, const Front
 }
 
 template <bool CLOSED>
-__global__ void __launch_bounds__(256) k_stab_fill(DevIndexView ix, const Frontier *__restrict__ fr, uint64_t n,
-                                                   const Window *__restrict__ win,
-                                                   const uint64_t *__restrict__ offsets,
-                                                   LiftTask *__restrict__ tasks) {
-  const unsigned lane = lane_id();
+__global__ void __launch_bounds__(32 * STAB_WARPS) k_stab_fill(DevIndexView ix, const Frontier *__restrict__ fr, uint64_t n,
+                                                               const Window *__restrict__ win,
+                                                               const uint64_t *__restrict__ offsets,
+                                                               LiftTask *__restrict__ tasks) {
+  __shared__ __align__(16) int32_t tiles[STAB_WARPS][STAB_TILE];
+  __shared__ uint64_t bars[STAB_WARPS];
+  const unsigned lane = lane_id(), wib = threadIdx.x >> 5;
+  if (lane == 0) mbar_init(&bars[wib], 1);
+  __syncwarp();
+  uint32_t phase = 0;
   uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   for (; w < n; w += nw) {
     const int32_t rs = fr[w].start;
     Window wd = win[w];
     uint64_t base = offsets[w];
-    for (uint64_t i0 = wd.lb; i0 < wd.ub; i0 += 32) {
-      uint64_t i = i0 + lane;
-      bool hit = false;
-      if (i < wd.ub) {
-        int32_t e = ld_stream_i32(ix.e_end + i);
-        hit = CLOSED ? e >= rs : e > rs;
-      }
-      unsigned b = __ballot_sync(FULL, hit);
+    stab_scan_tiles(ix.e_end, wd.lb, wd.ub, tiles[wib], &bars[wib], phase, [&](uint64_t i, int32_t e, bool live) {
+      const bool hit = live && (CLOSED ? e >= rs : e > rs);
+      const unsigned b = __ballot_sync(FULL, hit);
       if (hit) tasks[base + __popc(b & lanemask_lt())] = LiftTask{(uint32_t)i, (uint32_t)w};
       base += __popc(b);
-    }
+    });
   }
 }
 
