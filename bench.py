@@ -348,7 +348,7 @@ def main():
             pass
 
     cpu_baseline = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N=1 only
         O, orc, path, setup_s = cpu_reference_setup(name, recs, runs, offs, lens, names, ix)
         try:
             threads = host_threads()
