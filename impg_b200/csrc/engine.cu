@@ -55,6 +55,55 @@ static unsigned grid_warps(uint64_t n, unsigned threads = 256, unsigned per_sm =
   return (unsigned)blocks;
 }
 
+// ----------------------------------------------------------------- pinned pool
+namespace {
+struct PinnedPool {
+  std::mutex mu;
+  std::vector<std::pair<void *, size_t>> free_list;
+  ~PinnedPool() {
+    for (auto &b : free_list) cudaFreeHost(b.first);
+  }
+};
+PinnedPool &pinned_pool() {
+  static PinnedPool p;
+  return p;
+}
+}  // namespace
+
+void *pinned_acquire(size_t bytes, size_t *cap_out) {
+  size_t cap = 4096;
+  while (cap < bytes) cap <<= 1;
+  {
+    PinnedPool &pool = pinned_pool();
+    std::lock_guard<std::mutex> lock(pool.mu);
+    for (size_t i = 0; i < pool.free_list.size(); i++) {
+      if (pool.free_list[i].second == cap) {
+        void *p = pool.free_list[i].first;
+        pool.free_list.erase(pool.free_list.begin() + i);
+        *cap_out = cap;
+        return p;
+      }
+    }
+  }
+  void *p = nullptr;
+  if (cudaMallocHost(&p, cap) != cudaSuccess) {
+    cudaGetLastError();
+    throw Error(IMPGX_E_NOMEM, "pinned host allocation of " + std::to_string(cap) + " bytes failed");
+  }
+  *cap_out = cap;
+  return p;
+}
+
+void pinned_release(void *p, size_t cap) {
+  PinnedPool &pool = pinned_pool();
+  std::lock_guard<std::mutex> lock(pool.mu);
+  if (pool.free_list.size() >= 64) {
+    cudaFreeHost(p);
+    return;
+  }
+  pool.free_list.emplace_back(p, cap);
+}
+
 // ----------------------------------------------------------------- CUB glue
 // CUB temp storage: allocated per call from the arena (stack discipline frees it at once)
 struct Scratch {
@@ -1283,7 +1332,11 @@ impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n
             if (bo.n_cig)
               CUDA_CHECK(cudaMemcpyAsync(res->cig.data() + oldc, bo.cig.get(), bo.n_cig * 4, cudaMemcpyDeviceToHost, s));
             CUDA_CHECK(cudaStreamSynchronize(s));
-            for (uint64_t i = 1; i <= R; i++) res->cig_off.push_back(cig_base + co[i]);
+            {
+              const size_t o0 = res->cig_off.size();
+              res->cig_off.resize(o0 + R);
+              for (uint64_t i = 1; i <= R; i++) res->cig_off[o0 + i - 1] = cig_base + co[i];
+            }
             total.d2h_bytes += (R + 1) * 8 + bo.n_cig * 4;
             cig_base += bo.n_cig;
           }

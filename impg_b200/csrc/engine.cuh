@@ -1,5 +1,6 @@
 // engine.cuh — shared declarations between engine.cu and api.cu.
 #pragma once
+#include <cstring>
 #include <memory>
 
 #include "index.cuh"
@@ -32,6 +33,59 @@ void project_batch(int device, size_t n, const int32_t *req_start, const int32_t
 
 }  // namespace impgx
 
+namespace impgx {
+// Pinned host memory recycled across calls (cudaMallocHost is expensive, result
+// columns are tens of MB per batch and device->host copies into pageable memory
+// run at a fraction of the PCIe rate).
+void *pinned_acquire(size_t bytes, size_t *cap_out);
+void pinned_release(void *p, size_t cap);
+
+// vector-like result column in pinned memory
+template <class T>
+class HostCol {
+ public:
+  HostCol() {}
+  HostCol(const HostCol &) = delete;
+  HostCol &operator=(const HostCol &) = delete;
+  ~HostCol() {
+    if (p_) pinned_release(p_, cap_bytes_);
+  }
+  size_t size() const { return n_; }
+  bool empty() const { return n_ == 0; }
+  T *data() { return p_; }
+  const T *data() const { return p_; }
+  T *begin() { return p_; }
+  const T *begin() const { return p_; }
+  T &operator[](size_t i) { return p_[i]; }
+  const T &operator[](size_t i) const { return p_[i]; }
+  void resize(size_t n) {
+    if (n * sizeof(T) > cap_bytes_) {
+      size_t cap = 0;
+      T *q = (T *)pinned_acquire(std::max(n * sizeof(T), cap_bytes_ * 2), &cap);
+      if (p_) {
+        memcpy(q, p_, n_ * sizeof(T));
+        pinned_release(p_, cap_bytes_);
+      }
+      p_ = q;
+      cap_bytes_ = cap;
+    }
+    n_ = n;
+  }
+  void assign(size_t n, const T &v) {
+    resize(n);
+    for (size_t i = 0; i < n; i++) p_[i] = v;
+  }
+  void push_back(const T &v) {
+    resize(n_ + 1);
+    p_[n_ - 1] = v;
+  }
+
+ private:
+  T *p_ = nullptr;
+  size_t n_ = 0, cap_bytes_ = 0;
+};
+}  // namespace impgx
+
 struct impgx_results {
   int device = 0;
   bool on_device = false;
@@ -39,9 +93,9 @@ struct impgx_results {
   size_t n_rows = 0, n_results = 0, n_cig = 0;
   bool has_cigar = false;
   // host columns
-  std::vector<uint64_t> row_off, cig_off;
-  std::vector<uint32_t> qid, tid, cig;
-  std::vector<int32_t> qf, ql, tf, tl;
+  impgx::HostCol<uint64_t> row_off, cig_off;
+  impgx::HostCol<uint32_t> qid, tid, cig;
+  impgx::HostCol<int32_t> qf, ql, tf, tl;
   // device columns (device-resident variant)
   uint64_t *d_row_off = nullptr, *d_cig_off = nullptr;
   uint32_t *d_qid = nullptr, *d_tid = nullptr, *d_cig = nullptr;
