@@ -11,8 +11,14 @@ with HOST buffers (H2D of the rows, D2H of the merged rows inside the timed
 region). `--impl reference` times the reference's CPU algorithm (the oracle
 port with the reference's cost structure: per-hit pread + CIGAR text parse,
 rows serial, threads inside a BFS level) on a bounded sample of the same rows.
-Multi-GPU: rows are independent, so each rank holds an index replica and owns
-its own batch of rows (weak scaling, no data-path collective).
+Multi-GPU (weak scaling: N x the rows of one GPU), two layouts measured in the
+same run on the same rows:
+  * rows over index replicas — rows are independent, each rank holds a replica
+    and owns its batch of rows, no data-path collective (the headline `value`
+    unless --parallelism targets);
+  * index sharded by target sequence — every rank owns 1/N of the
+    sequences, the batch of all N x rows is one collective call, lifted hits and
+    frontier ranges are exchanged over NCCL between hops (`target_sharded`).
 """
 import argparse
 import ctypes as C
@@ -171,6 +177,10 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("IMPGX_BENCH_WORKLOAD", "c3"), choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parallelism", default=os.environ.get("IMPGX_BENCH_PARALLELISM", "rows"),
+                    choices=["rows", "targets"], help="which multi-GPU layout is the headline value at N > 1")
+    ap.add_argument("--virtual-shards", type=int, default=int(os.environ.get("IMPGX_BENCH_VIRTUAL_SHARDS", "0")),
+                    help="N = 1 only: also time the target-sharded path with this many virtual ranks on the one GPU")
     ap.add_argument("--profile", action="store_true",
                     help="for ncu: exactly --warmup + --steps device-resident steps, no e2e / cpu legs")
     args = ap.parse_args()
@@ -321,6 +331,77 @@ def main():
     value = total_rows / (dev_ms / 1e3)
     e2e_value = total_rows / (e2e_ms / 1e3)
 
+    # ---- index sharded by target sequence: the same N x rows as ONE collective batch
+    sharded = None
+    n_shards = world if world > 1 else args.virtual_shards
+    if n_shards > 1:
+        merged_rows_mode = D.gather_row_counts(merged, device="cuda")
+        gbed = np.concatenate([ix.synth_bed(cfg, rows, seed=D.rank_seed(2, r)) for r in range(world)])
+        d_gbed = torch.from_numpy(gbed.view(np.uint8).copy()).cuda()
+        owner = ix.assign_owners(recs, offs, len(lens), n_shards)
+        t0 = time.time()
+        if world > 1:
+            comm = D.nccl_comm(rank, world, local_rank)
+            shard = ix.Impg.from_records_shard(recs, runs, offs, lens, owner, rank, world, device=local_rank)
+            sh_stats = lambda: [shard.stats()]
+            sh_bytes = shard.device_bytes
+            traffic = lambda: comm.traffic()
+
+            def step_sharded():
+                return [shard.query_batch_bed_sharded_device(comm, d_gbed.data_ptr(), len(gbed), p, stream.cuda_stream)]
+        else:
+            sh = ix.ShardedImpg.from_records(recs, runs, offs, lens, [local_rank] * n_shards)
+            sh_stats = sh.stats
+            sh_bytes = max(x.device_bytes for x in sh.shards)
+
+            def traffic():
+                t = [c.traffic() for c in sh.comms]
+                return {k: sum(x[k] for x in t) for k in t[0]}
+
+            def step_sharded():
+                return sh._collective(lambda r: sh.shards[r].query_batch_bed_sharded_device(
+                    sh.comms[r], d_gbed.data_ptr(), len(gbed), p, 0))
+        shard_build_s = time.time() - t0
+        for _ in range(max(args.warmup, 3)):
+            step_sharded()
+        barrier()
+        tr0 = traffic()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sh_merged = sh_lift = sh_launches = 0
+        sh_lift_ms = sh_merge_ms = sh_fold_ms = sh_stab_ms = 0.0
+        w0 = time.perf_counter()
+        g0.record(stream)
+        for _ in range(args.steps):
+            rs = step_sharded()
+            sts = sh_stats()
+            sh_merged = sum(x["merged"] for x in sts)
+            sh_lift += sum(x["liftovers"] for x in sts)
+            sh_launches += sum(x["kernel_launches"] for x in sts)
+            sh_lift_ms += max(x["lift_ms"] for x in sts); sh_merge_ms += max(x["merge_ms"] for x in sts)
+            sh_fold_ms += max(x["fold_ms"] for x in sts); sh_stab_ms += max(x["stab_ms"] for x in sts)
+            del rs
+        g1.record(stream)
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - w0) * 1e3
+        barrier()
+        tr1 = traffic()
+        # virtual ranks run on their own streams: the host wall clock (all threads joined) is the time
+        sh_ms = g0.elapsed_time(g1) if world > 1 else wall_ms
+        (sh_ms,) = D.max_over_ranks([sh_ms], device="cuda")
+        sh_merged_total = D.gather_row_counts(sh_merged, device="cuda")
+        sent = D.gather_row_counts(tr1["bytes_sent"] - tr0["bytes_sent"], device="cuda") if world > 1 \
+            else tr1["bytes_sent"] - tr0["bytes_sent"]
+        sharded = {"value": len(gbed) * args.steps / (sh_ms / 1e3), "unit": UNIT, "ms_per_step": sh_ms / args.steps,
+                   "n_shards": n_shards, "transport": "nccl" if world > 1 else "in-process (virtual ranks on one GPU)",
+                   "rows_per_step": len(gbed), "exchange_bytes_per_step": int(sent) // args.steps,
+                   "exchanges_per_step": (tr1["exchanges"] - tr0["exchanges"]) // args.steps,
+                   "bed_rows_out_per_step": int(sh_merged_total),
+                   "bed_rows_out_match_rows_mode": bool(sh_merged_total == merged_rows_mode),
+                   "liftovers_per_step_this_rank": sh_lift // args.steps, "shard_device_bytes": int(sh_bytes),
+                   "shard_build_s": shard_build_s, "gpu_launches": int(sh_launches),
+                   "step_share_slowest_rank": {"liftover_ms": sh_lift_ms / args.steps, "stab_ms": sh_stab_ms / args.steps,
+                                               "fold_ms": sh_fold_ms / args.steps, "merge_ms": sh_merge_ms / args.steps}}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -362,13 +443,20 @@ def main():
             except OSError:
                 pass
 
+    rows_mode = {"value": value, "unit": UNIT, "ms_per_step": dev_ms / args.steps}
+    if args.parallelism == "targets" and sharded is not None and world > 1:
+        value, dev_ms = sharded["value"], sharded["ms_per_step"] * args.steps
+        launches = sharded["gpu_launches"]
+        config["parallelism"] = (f"index sharded by target sequence over {world} GPUs, one collective batch of "
+                                 f"{world} x {rows} rows, NCCL hit / frontier exchange between hops")
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps,
                     "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "clocks": sampler.summary(), "bed_rows_out_per_step": int(merged),
+            "clocks": sampler.summary(), "bed_rows_out_per_step": int(merged), "rows_over_replicas": rows_mode,
+            "target_sharded": sharded,
             "setup": {"generate_s": gen_s, "index_build_s": build_s, "index_device_bytes": idx.device_bytes}}
     print(json.dumps(line))
     if dist is not None:

@@ -111,6 +111,7 @@ def lib():
         L.impgx_format_paf.restype = C.c_void_p
         L.impgx_synth_num_alignments.restype = C.c_uint64
         L.impgx_debug_host_columns.restype = C.c_long
+        L.impgx_debug_host_columns_shard.restype = C.c_long
         _lib = L
     return _lib
 
@@ -283,6 +284,42 @@ class Impg:
                                                   C.c_void_p(stream), C.byref(h)))
         return Results(h.value, on_device=True)
 
+    # -- target-sharded index: this object is ONE shard; queries are collective
+    @classmethod
+    def from_records_shard(cls, records, runs, run_offsets, seq_lens, owner, rank, n_ranks, names=None,
+                           bidirectional=True, device=0):
+        records = np.ascontiguousarray(records, dtype=RECORD_DTYPE)
+        runs = np.ascontiguousarray(runs, dtype=np.uint32)
+        run_offsets = np.ascontiguousarray(run_offsets, dtype=np.uint64)
+        seq_lens = np.ascontiguousarray(seq_lens, dtype=np.uint64)
+        owner = np.ascontiguousarray(owner, dtype=np.uint32)
+        assert len(owner) == len(seq_lens)
+        if len(runs) == 0:
+            runs = np.zeros(1, np.uint32)
+        h = C.c_void_p()
+        _check(lib().impgx_index_build_shard(_p(records), C.c_size_t(len(records)), _p(runs), _p(run_offsets),
+                                             _p(seq_lens), C.c_uint32(len(seq_lens)),
+                                             C.c_int(1 if bidirectional else 0), C.c_int(device), _p(owner),
+                                             C.c_uint32(rank), C.c_uint32(n_ranks), C.byref(h)))
+        idx = cls(h.value)
+        if names is not None:
+            idx.set_names(names)
+        return idx
+
+    def query_batch_bed_sharded(self, comm, ranges, params):
+        """Collective: every rank calls it with the same ranges/params; returns this rank's BED rows."""
+        ranges = np.ascontiguousarray(ranges, dtype=RANGE_DTYPE)
+        h = C.c_void_p()
+        _check(lib().impgx_query_batch_bed_sharded(self.h, comm.h, _p(ranges), C.c_size_t(len(ranges)),
+                                                   C.byref(params), C.byref(h)))
+        return Results(h.value)
+
+    def query_batch_bed_sharded_device(self, comm, d_ranges_ptr, n, params, stream=0):
+        h = C.c_void_p()
+        _check(lib().impgx_query_batch_bed_sharded_device(self.h, comm.h, C.c_void_p(d_ranges_ptr), C.c_size_t(n),
+                                                          C.byref(params), C.c_void_p(stream), C.byref(h)))
+        return Results(h.value, on_device=True)
+
     def stats(self):
         s = Stats()
         _check(lib().impgx_index_stats(self.h, C.byref(s)))
@@ -312,6 +349,145 @@ class Impg:
         s = C.string_at(ptr).decode()
         lib().impgx_free(C.c_void_p(ptr))
         return s
+
+
+# ---------------------------------------------------------------- sharding
+class Comm:
+    """Exchange endpoint of one rank of a target-sharded index (include/impgx.h, impgx_comm)."""
+
+    def __init__(self, handle):
+        self.h = C.c_void_p(handle)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().impgx_comm_free(self.h)
+            self.h = None
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_uint8 * 128)()
+        _check(lib().impgx_comm_unique_id(buf))
+        return bytes(buf)
+
+    @classmethod
+    def nccl(cls, unique_id, rank, n_ranks, device):
+        """One process per GPU; `unique_id` comes from rank 0's Comm.unique_id()."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        h = C.c_void_p()
+        _check(lib().impgx_comm_init_nccl(buf, C.c_int(rank), C.c_int(n_ranks), C.c_int(device), C.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def local_group(cls, n_ranks):
+        """n_ranks endpoints inside this process, each to be driven by its own thread."""
+        arr = (C.c_void_p * n_ranks)()
+        _check(lib().impgx_comm_init_local(C.c_int(n_ranks), arr))
+        return [cls(arr[r]) for r in range(n_ranks)]
+
+    @property
+    def rank(self):
+        return lib().impgx_comm_rank(self.h)
+
+    @property
+    def size(self):
+        return lib().impgx_comm_size(self.h)
+
+    def traffic(self):
+        s, r, e = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _check(lib().impgx_comm_traffic(self.h, C.byref(s), C.byref(r), C.byref(e)))
+        return {"bytes_sent": s.value, "bytes_received": r.value, "exchanges": e.value}
+
+
+def assign_owners(records, run_offsets, n_seqs, n_ranks, bidirectional=True):
+    """Balanced sequence -> rank map of a target-sharded index (no GPU needed)."""
+    records = np.ascontiguousarray(records, dtype=RECORD_DTYPE)
+    run_offsets = np.ascontiguousarray(run_offsets, dtype=np.uint64)
+    owner = np.zeros(n_seqs, np.uint32)
+    _check(lib().impgx_assign_owners(_p(records), C.c_size_t(len(records)), _p(run_offsets), C.c_uint32(n_seqs),
+                                     C.c_int(1 if bidirectional else 0), C.c_uint32(n_ranks), _p(owner)))
+    return owner
+
+
+def shard_records(records, run_offsets, owner, rank, bidirectional=True):
+    """Indices of the alignments shard `rank` needs (those with an entry on an owned sequence)."""
+    records = np.asarray(records)
+    keep = owner[records["target_id"]] == rank
+    if bidirectional:
+        keep |= (owner[records["query_id"]] == rank) & (records["query_id"] != records["target_id"])
+    return np.nonzero(keep)[0]
+
+
+def merge_shards(parts):
+    """impgx_results_merge_shards: per-rank BED rows -> the reference's per-row output."""
+    arr = (C.c_void_p * len(parts))(*[p.h for p in parts])
+    h = C.c_void_p()
+    _check(lib().impgx_results_merge_shards(arr, C.c_int(len(parts)), C.byref(h)))
+    return Results(h.value)
+
+
+def merge_shard_columns(parts):
+    """Same reassembly on column dicts (e.g. gathered from other processes): rows of one
+    input row are ordered by sequence id, each part holds whole (row, q_id) groups."""
+    n_rows = len(parts[0]["row_offsets"]) - 1
+    rows = np.concatenate([np.repeat(np.arange(n_rows, dtype=np.int64), np.diff(p["row_offsets"].astype(np.int64)))
+                           for p in parts])
+    cat = {k: np.concatenate([p[k] for p in parts]) for k in ("q_id", "q_first", "q_last", "t_id", "t_first", "t_last")}
+    order = np.lexsort((cat["q_id"], rows))  # stable: keeps each part's order inside a (row, q_id) group
+    out = {k: v[order] for k, v in cat.items()}
+    ro = np.zeros(n_rows + 1, np.uint64)
+    np.cumsum(np.bincount(rows, minlength=n_rows), out=ro[1:])
+    out["row_offsets"] = ro
+    return out
+
+
+class ShardedImpg:
+    """A target-sharded index inside ONE process: shard r lives on devices[r] (devices may
+    repeat: several shards on one GPU), exchanges go through the in-process transport and
+    every collective call runs one host thread per shard."""
+
+    def __init__(self, shards, comms, owner):
+        self.shards, self.comms, self.owner = shards, comms, owner
+
+    @classmethod
+    def from_records(cls, records, runs, run_offsets, seq_lens, devices, names=None, bidirectional=True):
+        n = len(devices)
+        owner = assign_owners(records, run_offsets, len(seq_lens), n, bidirectional)
+        shards = [Impg.from_records_shard(records, runs, run_offsets, seq_lens, owner, r, n, names=names,
+                                          bidirectional=bidirectional, device=devices[r]) for r in range(n)]
+        return cls(shards, Comm.local_group(n), owner)
+
+    def _collective(self, fn):
+        import threading
+        n = len(self.shards)
+        out, err = [None] * n, [None] * n
+
+        def work(r):
+            try:
+                out[r] = fn(r)
+            except Exception as e:  # noqa: BLE001 - re-raised below
+                err[r] = e
+
+        ts = [threading.Thread(target=work, args=(r,)) for r in range(n)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        for e in err:
+            if e is not None and not (isinstance(e, ImpgxError) and "peer rank" in str(e)):
+                raise e
+        for e in err:
+            if e is not None:
+                raise e
+        return out
+
+    def query_batch_bed_parts(self, ranges, params):
+        return self._collective(lambda r: self.shards[r].query_batch_bed_sharded(self.comms[r], ranges, params))
+
+    def query_batch_bed(self, ranges, params):
+        return merge_shards(self.query_batch_bed_parts(ranges, params))
+
+    def stats(self):
+        return [s.stats() for s in self.shards]
 
 
 def _format_rows(fn, idx, results, row, name, merge_distance):
@@ -433,12 +609,26 @@ def write_cigar_text(runs, run_offsets, path):
     return offs, lens
 
 
-def host_columns(records, run_offsets, n_seqs, bidirectional=True):
-    """Test hook: the sorted entry columns of an index build, without a GPU."""
+def host_columns(records, run_offsets, n_seqs, bidirectional=True, owner=None, rank=0):
+    """Test hook: the sorted entry columns of an index build (or of one shard), without a GPU."""
     records = np.ascontiguousarray(records, dtype=RECORD_DTYPE)
     run_offsets = np.ascontiguousarray(run_offsets, dtype=np.uint64)
     L = lib()
     args = [_p(records), C.c_size_t(len(records)), _p(run_offsets), C.c_uint32(n_seqs), C.c_int(1 if bidirectional else 0)]
+    if owner is not None:
+        owner = np.ascontiguousarray(owner, dtype=np.uint32)
+        E = L.impgx_debug_host_columns_shard(*args, None, None, None, None, None, None, None, None, _p(owner),
+                                             C.c_uint32(rank))
+        if E < 0:
+            raise ImpgxError(E_INVALID, L.impgx_last_error().decode())
+        cols = {"e_start": np.zeros(E, np.int32), "e_end": np.zeros(E, np.int32), "e_pmax": np.zeros(E, np.int32),
+                "e_vrank": np.zeros(E, np.uint32), "e_query_id": np.zeros(E, np.uint32),
+                "e_flags": np.zeros(E, np.uint32), "e_aln": np.zeros(E, np.uint32),
+                "tgt_off": np.zeros(n_seqs + 1, np.uint64)}
+        L.impgx_debug_host_columns_shard(*args, _p(cols["e_start"]), _p(cols["e_end"]), _p(cols["e_pmax"]),
+                                         _p(cols["e_vrank"]), _p(cols["e_query_id"]), _p(cols["e_flags"]),
+                                         _p(cols["e_aln"]), _p(cols["tgt_off"]), _p(owner), C.c_uint32(rank))
+        return cols
     E = L.impgx_debug_host_columns(*args, None, None, None, None, None, None, None, None)
     if E < 0:
         raise ImpgxError(E_INVALID, L.impgx_last_error().decode())

@@ -6,6 +6,7 @@
 #include <sstream>
 
 #include "engine.cuh"
+#include "comm.cuh"
 #include "synth_core.h"
 
 using namespace impgx;
@@ -257,6 +258,131 @@ int impgx_query_batch_bed_device(impgx_index *idx, const impgx_range *d_ranges, 
   return do_query(idx, d_ranges, n, params, true, true, false, stream, out);
 }
 
+// ---- target-sharded index
+int impgx_comm_unique_id(uint8_t id[IMPGX_COMM_ID_BYTES]) {
+  API_BEGIN
+  REQUIRE(id, IMPGX_E_INVALID, "NULL argument");
+  impgx::nccl_unique_id(id);
+  API_END
+}
+int impgx_comm_init_nccl(const uint8_t id[IMPGX_COMM_ID_BYTES], int rank, int n_ranks, int device, impgx_comm **out) {
+  API_BEGIN
+  REQUIRE(id && out, IMPGX_E_INVALID, "NULL argument");
+  *out = nullptr;
+  impgx::check_device(device);
+  std::unique_ptr<impgx_comm> c(new impgx_comm());
+  c->c.reset(impgx::nccl_comm_create(id, rank, n_ranks, device));
+  *out = c.release();
+  API_END
+}
+int impgx_comm_init_local(int n_ranks, impgx_comm **out) {
+  API_BEGIN
+  REQUIRE(out, IMPGX_E_INVALID, "NULL argument");
+  std::vector<impgx::Comm *> g = impgx::local_comm_group(n_ranks);
+  for (int r = 0; r < n_ranks; r++) {
+    out[r] = new impgx_comm();
+    out[r]->c.reset(g[r]);
+  }
+  API_END
+}
+int impgx_comm_rank(const impgx_comm *c) { return c ? c->c->rank() : -1; }
+int impgx_comm_size(const impgx_comm *c) { return c ? c->c->size() : 0; }
+int impgx_comm_traffic(const impgx_comm *c, uint64_t *sent, uint64_t *received, uint64_t *exchanges) {
+  API_BEGIN
+  REQUIRE(c, IMPGX_E_INVALID, "NULL argument");
+  if (sent) *sent = c->c->bytes_sent;
+  if (received) *received = c->c->bytes_received;
+  if (exchanges) *exchanges = c->c->exchanges;
+  API_END
+}
+void impgx_comm_free(impgx_comm *c) { delete c; }
+
+int impgx_assign_owners(const impgx_record *records, size_t n_records, const uint64_t *run_offsets, uint32_t n_seqs,
+                        int bidirectional, uint32_t n_ranks, uint32_t *owner_out) {
+  API_BEGIN
+  REQUIRE((records || n_records == 0) && run_offsets && owner_out, IMPGX_E_INVALID, "NULL argument");
+  impgx::assign_owners(records, n_records, run_offsets, n_seqs, bidirectional != 0, n_ranks, owner_out);
+  API_END
+}
+int impgx_index_build_shard(const impgx_record *records, size_t n_records, const uint32_t *runs,
+                            const uint64_t *run_offsets, const uint64_t *seq_lens, uint32_t n_seqs, int bidirectional,
+                            int device, const uint32_t *owner, uint32_t rank, uint32_t n_ranks, impgx_index **out) {
+  API_BEGIN
+  REQUIRE(out && owner, IMPGX_E_INVALID, "NULL argument");
+  *out = nullptr;
+  REQUIRE(runs || n_records == 0 || run_offsets[n_records] == 0, IMPGX_E_INVALID, "runs is NULL");
+  *out = impgx::index_build(records, n_records, runs, run_offsets, seq_lens, n_seqs, bidirectional != 0, device, owner,
+                            rank, n_ranks);
+  API_END
+}
+int impgx_query_batch_bed_sharded(impgx_index *shard, impgx_comm *comm, const impgx_range *ranges, size_t n,
+                                  const impgx_params *params, impgx_results **out) {
+  API_BEGIN
+  REQUIRE(out && params && comm, IMPGX_E_INVALID, "NULL argument");
+  *out = nullptr;
+  *out = impgx::query_batch(shard, ranges, n, *params, true, false, true, nullptr, comm->c.get());
+  API_END
+}
+int impgx_query_batch_bed_sharded_device(impgx_index *shard, impgx_comm *comm, const impgx_range *d_ranges, size_t n,
+                                         const impgx_params *params, void *stream, impgx_results **out) {
+  API_BEGIN
+  REQUIRE(out && params && comm, IMPGX_E_INVALID, "NULL argument");
+  *out = nullptr;
+  *out = impgx::query_batch(shard, d_ranges, n, *params, true, true, false, stream, comm->c.get());
+  API_END
+}
+// Rows of one input row are sorted by sequence id in the reference's BED output
+// (stage B sorts by (q_id, start, strand)); each part holds whole (row, q_id)
+// groups, so the union is a k-way merge by q_id per row.
+int impgx_results_merge_shards(const impgx_results *const *parts, int n_parts, impgx_results **out) {
+  API_BEGIN
+  REQUIRE(parts && out && n_parts >= 1, IMPGX_E_INVALID, "NULL argument");
+  *out = nullptr;
+  const size_t n_rows = parts[0]->n_rows;
+  uint64_t total = 0;
+  for (int p = 0; p < n_parts; p++) {
+    REQUIRE(parts[p] && !parts[p]->on_device && parts[p]->n_rows == n_rows && !parts[p]->has_cigar, IMPGX_E_INVALID,
+            "parts must be host-resident BED results of the same batch");
+    total += parts[p]->n_results;
+  }
+  std::unique_ptr<impgx_results> res(new impgx_results());
+  res->device = parts[0]->device;
+  res->n_rows = n_rows;
+  res->n_results = total;
+  res->row_off.assign(n_rows + 1, 0);
+  res->qid.resize(total); res->tid.resize(total);
+  res->qf.resize(total); res->ql.resize(total); res->tf.resize(total); res->tl.resize(total);
+  uint64_t w = 0;
+  std::vector<uint64_t> cur((size_t)n_parts);
+  for (size_t r = 0; r < n_rows; r++) {
+    for (int p = 0; p < n_parts; p++) cur[p] = parts[p]->row_off[r];
+    for (;;) {
+      int best = -1;
+      uint32_t bq = 0;
+      for (int p = 0; p < n_parts; p++) {
+        if (cur[p] >= parts[p]->row_off[r + 1]) continue;
+        const uint32_t q = parts[p]->qid[cur[p]];
+        if (best < 0 || q < bq) {
+          best = p;
+          bq = q;
+        }
+      }
+      if (best < 0) break;
+      const impgx_results *P = parts[best];
+      uint64_t &c = cur[best];
+      while (c < P->row_off[r + 1] && P->qid[c] == bq) {
+        res->qid[w] = P->qid[c]; res->tid[w] = P->tid[c];
+        res->qf[w] = P->qf[c]; res->ql[w] = P->ql[c]; res->tf[w] = P->tf[c]; res->tl[w] = P->tl[c];
+        w++;
+        c++;
+      }
+    }
+    res->row_off[r + 1] = w;
+  }
+  *out = res.release();
+  API_END
+}
+
 int impgx_results_view(const impgx_results *res, impgx_view *v) {
   API_BEGIN
   REQUIRE(res && v, IMPGX_E_INVALID, "NULL argument");
@@ -492,12 +618,23 @@ void impgx_debug_visit_ranks(size_t n, uint32_t *rank) { impgx::visit_ranks(n, r
 
 // host columns of an index build (no device needed): returns entry count, fills
 // the arrays when non-NULL (sized by a first call with NULLs)
+long impgx_debug_host_columns_shard(const impgx_record *records, size_t n, const uint64_t *run_offsets, uint32_t n_seqs,
+                                    int bidirectional, int32_t *e_start, int32_t *e_end, int32_t *e_pmax,
+                                    uint32_t *e_vrank, uint32_t *e_query_id, uint32_t *e_flags, uint32_t *e_aln,
+                                    uint64_t *tgt_off, const uint32_t *owner, uint32_t rank);
 long impgx_debug_host_columns(const impgx_record *records, size_t n, const uint64_t *run_offsets, uint32_t n_seqs,
                               int bidirectional, int32_t *e_start, int32_t *e_end, int32_t *e_pmax, uint32_t *e_vrank,
                               uint32_t *e_query_id, uint32_t *e_flags, uint32_t *e_aln, uint64_t *tgt_off) {
+  return impgx_debug_host_columns_shard(records, n, run_offsets, n_seqs, bidirectional, e_start, e_end, e_pmax, e_vrank,
+                                        e_query_id, e_flags, e_aln, tgt_off, nullptr, 0);
+}
+long impgx_debug_host_columns_shard(const impgx_record *records, size_t n, const uint64_t *run_offsets, uint32_t n_seqs,
+                                    int bidirectional, int32_t *e_start, int32_t *e_end, int32_t *e_pmax,
+                                    uint32_t *e_vrank, uint32_t *e_query_id, uint32_t *e_flags, uint32_t *e_aln,
+                                    uint64_t *tgt_off, const uint32_t *owner, uint32_t rank) {
   try {
     impgx::HostColumns hc;
-    impgx::build_host_columns(records, n, run_offsets, n_seqs, bidirectional != 0, hc);
+    impgx::build_host_columns(records, n, run_offsets, n_seqs, bidirectional != 0, hc, owner, rank);
     size_t E = hc.e_start.size();
     if (e_start) {
       memcpy(e_start, hc.e_start.data(), E * 4);

@@ -7,9 +7,13 @@
 #include <cmath>
 #include <cstring>
 
+#include <functional>
+
 #include "bfs_kernels.cuh"
+#include "comm.cuh"
 #include "engine.cuh"
 #include "merge_kernels.cuh"
+#include "shard_kernels.cuh"
 
 namespace impgx {
 
@@ -173,7 +177,7 @@ struct WallTimer {
 impgx_index::~impgx_index() {
   cudaSetDevice(device);
   cudaFree(d_start); cudaFree(d_end); cudaFree(d_pmax); cudaFree(d_seq_len);
-  cudaFree(d_stream); cudaFree(d_rec); cudaFree(d_tgt_off);
+  cudaFree(d_stream); cudaFree(d_rec); cudaFree(d_tgt_off); cudaFree(d_owner);
 }
 
 namespace impgx {
@@ -205,13 +209,18 @@ void check_device(int device) {
 }
 
 impgx_index *index_build(const impgx_record *recs, size_t n, const uint32_t *runs, const uint64_t *run_offsets,
-                         const uint64_t *seq_lens, uint32_t n_seqs, bool bidirectional, int device) {
+                         const uint64_t *seq_lens, uint32_t n_seqs, bool bidirectional, int device,
+                         const uint32_t *owner, uint32_t rank, uint32_t n_ranks) {
   check_device(device);
   REQUIRE(recs || n == 0, IMPGX_E_INVALID, "records is NULL");
   REQUIRE(run_offsets && seq_lens, IMPGX_E_INVALID, "run_offsets / seq_lens is NULL");
   for (uint32_t s = 0; s < n_seqs; s++)
     REQUIRE(seq_lens[s] <= (uint64_t)INT32_MAX, IMPGX_E_INVALID, "sequence longer than 2^31-1 (coordinates are i32)");
   for (size_t i = 0; i < n; i++) REQUIRE(run_offsets[i] <= run_offsets[i + 1], IMPGX_E_INVALID, "run_offsets not monotone");
+  if (owner) {
+    REQUIRE(n_ranks >= 1 && rank < n_ranks, IMPGX_E_INVALID, "bad shard rank / n_ranks");
+    for (uint32_t s = 0; s < n_seqs; s++) REQUIRE(owner[s] < n_ranks, IMPGX_E_INVALID, "owner id out of range");
+  }
 
   std::unique_ptr<impgx_index> idx(new impgx_index());
   idx->device = device;
@@ -221,7 +230,7 @@ impgx_index *index_build(const impgx_record *recs, size_t n, const uint32_t *run
   idx->names.resize(n_seqs);
 
   HostColumns hc;
-  build_host_columns(recs, n, run_offsets, n_seqs, bidirectional, hc);
+  build_host_columns(recs, n, run_offsets, n_seqs, bidirectional, hc, owner, rank);
   idx->n_entries = hc.e_start.size();
   idx->n_blocks = hc.aln_off[n];
 
@@ -234,9 +243,16 @@ impgx_index *index_build(const impgx_record *recs, size_t n, const uint32_t *run
   std::vector<int32_t> sl(n_seqs);
   for (uint32_t s = 0; s < n_seqs; s++) sl[s] = (int32_t)seq_lens[s];
   idx->d_seq_len = upload(sl, bytes);
+  if (owner) {
+    idx->owner.assign(owner, owner + n_seqs);
+    idx->shard_rank = rank;
+    idx->shard_size = n_ranks;
+    idx->d_owner = upload(idx->owner, bytes);
+  }
 
   // stream: per alignment checkpoints + 8-run blocks, built on the device from
-  // the raw runs, uploaded in bounded chunks of alignments
+  // the raw runs, uploaded in bounded chunks of alignments. A shard uploads only
+  // the alignments its entries walk (gathered through a host staging buffer).
   size_t stream_bytes = std::max<uint64_t>(idx->n_blocks, 1) * 32;
   CUDA_CHECK(cudaMalloc((void **)&idx->d_stream, stream_bytes));
   bytes += stream_bytes;
@@ -247,33 +263,60 @@ impgx_index *index_build(const impgx_record *recs, size_t n, const uint32_t *run
     uint32_t *d_blk = nullptr;
     size_t cap_raw = 0, cap_aln = 0;
     std::vector<uint64_t> rel;
+    std::vector<uint32_t> blk, stage;
     Ctx ctx;
     size_t a = 0;
     while (a < n) {
+      // chunk [a, b) of the records; `rel`/`blk` list the alignments of the chunk that are uploaded
+      rel.assign(1, 0);
+      blk.clear();
+      uint64_t nr = 0;
       size_t b = a;
-      uint64_t base = run_offsets[a];
-      while (b < n && (run_offsets[b + 1] - base <= chunk_runs || b == a)) b++;
-      uint64_t nr = run_offsets[b] - base;
-      size_t na = b - a;
-      if (nr > cap_raw) {
-        cudaFree(d_raw);
-        CUDA_CHECK(cudaMalloc((void **)&d_raw, std::max<uint64_t>(nr, 1) * 4));
-        cap_raw = nr;
+      while (b < n) {
+        const bool needed = hc.aln_off[b + 1] != hc.aln_off[b];
+        const uint64_t r = needed ? run_offsets[b + 1] - run_offsets[b] : 0;
+        if (nr + r > chunk_runs && !blk.empty()) break;
+        if (needed) {
+          nr += r;
+          rel.push_back(nr);
+          blk.push_back(hc.aln_off[b]);
+        }
+        b++;
       }
-      if (na > cap_aln) {
-        cudaFree(d_off);
-        cudaFree(d_blk);
-        CUDA_CHECK(cudaMalloc((void **)&d_off, (na + 1) * 8));
-        CUDA_CHECK(cudaMalloc((void **)&d_blk, (na + 1) * 4));
-        cap_aln = na;
+      const size_t na = blk.size();
+      if (na) {
+        if (nr > cap_raw) {
+          cudaFree(d_raw);
+          CUDA_CHECK(cudaMalloc((void **)&d_raw, std::max<uint64_t>(nr, 1) * 4));
+          cap_raw = nr;
+        }
+        if (na > cap_aln) {
+          cudaFree(d_off);
+          cudaFree(d_blk);
+          CUDA_CHECK(cudaMalloc((void **)&d_off, (na + 1) * 8));
+          CUDA_CHECK(cudaMalloc((void **)&d_blk, (na + 1) * 4));
+          cap_aln = na;
+        }
+        if (nr) {
+          if (na == b - a) {  // every alignment of the chunk: one contiguous copy
+            CUDA_CHECK(cudaMemcpy(d_raw, runs + run_offsets[a], nr * 4, cudaMemcpyHostToDevice));
+          } else {
+            stage.resize(nr);
+            size_t k = 0;
+            for (size_t i = a; i < b; i++) {
+              if (hc.aln_off[i + 1] == hc.aln_off[i]) continue;
+              const uint64_t r = run_offsets[i + 1] - run_offsets[i];
+              memcpy(stage.data() + rel[k], runs + run_offsets[i], r * 4);
+              k++;
+            }
+            CUDA_CHECK(cudaMemcpy(d_raw, stage.data(), nr * 4, cudaMemcpyHostToDevice));
+          }
+        }
+        CUDA_CHECK(cudaMemcpy(d_off, rel.data(), (na + 1) * 8, cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(d_blk, blk.data(), na * 4, cudaMemcpyHostToDevice));
+        LAUNCH(k_build_blocks, grid_warps(na), 256, 0, d_raw, d_off, d_blk, (uint64_t)na, idx->d_stream);
+        CUDA_CHECK(cudaDeviceSynchronize());
       }
-      rel.resize(na + 1);
-      for (size_t i = 0; i <= na; i++) rel[i] = run_offsets[a + i] - base;
-      if (nr) CUDA_CHECK(cudaMemcpy(d_raw, runs + base, nr * 4, cudaMemcpyHostToDevice));
-      CUDA_CHECK(cudaMemcpy(d_off, rel.data(), (na + 1) * 8, cudaMemcpyHostToDevice));
-      CUDA_CHECK(cudaMemcpy(d_blk, hc.aln_off.data() + a, (na + 1) * 4, cudaMemcpyHostToDevice));
-      LAUNCH(k_build_blocks, grid_warps(na), 256, 0, d_raw, d_off, d_blk, (uint64_t)na, idx->d_stream);
-      CUDA_CHECK(cudaDeviceSynchronize());
       a = b;
     }
     cudaFree(d_raw);
@@ -332,10 +375,25 @@ struct BatchOut {
   uint64_t n_results = 0, n_cig = 0;
 };
 
+// Raw output of stab + liftover of one frontier, in processing order.
+struct Lifted {
+  DBuf<Frontier> fr_loc;   // frontier in processing (target position) order, if permuted
+  DBuf<uint32_t> orig;     // processing index -> frontier index
+  DBuf<Window> win;
+  DBuf<uint32_t> counts;
+  DBuf<uint64_t> offs;
+  DBuf<LiftTask> tasks;
+  DBuf<Hit> hits;
+  DBuf<CigarSlice> slices;
+  const Frontier *fr = nullptr;      // the frontier the tasks index
+  const uint32_t *d_orig = nullptr;  // orig.get() or nullptr (identity)
+  uint64_t H = 0, n_ok = 0;
+};
+
 class Runner {
  public:
-  Runner(impgx_index *idx, const impgx_params &p, cudaStream_t s)
-      : idx_(idx), p_(p), s_(s), ix_(idx->view()), ar_(idx->arena) {
+  Runner(impgx_index *idx, const impgx_params &p, cudaStream_t s, Comm *comm = nullptr)
+      : idx_(idx), p_(p), s_(s), ix_(idx->view()), ar_(idx->arena), comm_(comm) {
     sc_.a = &ar_;
   }
 
@@ -344,6 +402,9 @@ class Runner {
   // One batch of rows whose ranges are on the device. Produces raw results in
   // reference order (bed == false) or BED-merged rows (bed == true).
   void run(const impgx_range *d_ranges, uint32_t n_rows, bool bed, BatchOut &out);
+  // Same batch on a target-sharded index (collective over comm): BED rows of
+  // the (row, sequence) groups whose sequence this rank owns.
+  void run_sharded(const impgx_range *d_ranges, uint32_t n_rows, BatchOut &out);
 
  private:
   impgx_index *idx_;
@@ -356,7 +417,20 @@ class Runner {
   DBuf<uint32_t> d_row_target_;
   DBuf<unsigned long long> d_counters_;
   cudaEvent_t ev_[2] = {nullptr, nullptr};
+  Comm *comm_ = nullptr;  // sharded index only
 
+  void prepare(const impgx_range *d_ranges, uint32_t n_rows);
+  void lift_core(const DBuf<Frontier> &fr, uint64_t nF, bool closed, bool clip,
+                 const std::function<void(uint64_t)> &alloc_outputs, Lifted &L);
+  int bits_a_ = 0, bits_b_ = 0;  // widths of the packed merge keys of this batch
+  OutCols alloc_out_cols(BatchOut &out, uint64_t n);
+  void stage_a(const BoxD *boxes, uint64_t nB, uint64_t nv, DBuf<BoxD> &acc, DBuf<uint64_t> &is_root);
+  void stage_b(const BoxD *acc, const uint64_t *is_root, uint64_t n, unsigned long long *d_root_counter,
+               uint32_t n_rows, BatchOut &out, uint32_t *row_cnt);
+  void route_hits(const Lifted &L, const uint32_t *gmap, LevelHits &lvl);
+  void global_frontier(DBuf<Frontier> &fr, uint64_t &nF, DBuf<uint32_t> &gmap, uint64_t total,
+                       const std::vector<uint64_t> &cnt);
+  void route_roots(DBuf<BoxD> &acc, DBuf<uint64_t> &is_root, uint64_t nv, DBuf<BoxD> &recv, uint64_t &n_recv);
   void stab_and_lift(const DBuf<Frontier> &fr, uint64_t nF, bool closed, bool clip, BedSink *sink, LevelHits &lvl);
   void bed_merge_direct(BedSink &sink, uint32_t n_rows, BatchOut &out);
   void fold(const LevelHits &lvl, uint32_t n_rows, Visited &V, DBuf<Frontier> &next, uint64_t &n_next,
@@ -369,11 +443,12 @@ class Runner {
   float timed_begin();
 };
 
-// stab (count, scan, fill) + liftover of one frontier; leaves the accepted
-// hits ordered by (frontier index, visit rank) in lvl.
-void Runner::stab_and_lift(const DBuf<Frontier> &fr_ref, uint64_t nF, bool closed, bool clip, BedSink *sink,
-                           LevelHits &lvl) {
-  lvl.n = 0;
+// stab (count, scan, fill) + liftover of one frontier: raw hits in processing
+// order. `alloc_outputs(H)` runs as soon as the hit count is known, before the
+// temporaries, so that what the caller keeps sits below them in the arena.
+void Runner::lift_core(const DBuf<Frontier> &fr_ref, uint64_t nF, bool closed, bool clip,
+                       const std::function<void(uint64_t)> &alloc_outputs, Lifted &L) {
+  L.H = L.n_ok = 0;
   if (nF == 0) return;
   std::unique_ptr<WallTimer> wt(new WallTimer(ctx.w_stab));
   cudaEvent_t e0, e1, e2;
@@ -386,52 +461,45 @@ void Runner::stab_and_lift(const DBuf<Frontier> &fr_ref, uint64_t nF, bool close
   // through the same alignments, so entry records, checkpoints and run blocks
   // are reused from L1/L2 instead of being re-fetched from HBM. `orig` maps
   // back to the reference's frontier index, which the order keys are built on.
-  DBuf<Frontier> fr_loc;
-  DBuf<uint32_t> orig;
   const bool locality = nF >= 4096 && !getenv("IMPGX_NO_LOCALITY");
   if (locality) {
     DBuf<uint64_t> lk(nF, ar_);
-    orig.alloc(nF, ar_);
-    LAUNCH(k_locality_keys, grid_threads(nF), 256, s_, fr_ref.get(), nF, lk.get(), orig.get());
-    sort_pairs(lk, orig, nF, 0, 32 + bits_for(ix_.n_seqs), sc_, s_, ctx);
-    fr_loc.alloc(nF, ar_);
-    LAUNCH(k_gather<Frontier>, grid_threads(nF), 256, s_, fr_ref.get(), orig.get(), nF, fr_loc.get());
+    L.orig.alloc(nF, ar_);
+    LAUNCH(k_locality_keys, grid_threads(nF), 256, s_, fr_ref.get(), nF, lk.get(), L.orig.get());
+    sort_pairs(lk, L.orig, nF, 0, 32 + bits_for(ix_.n_seqs), sc_, s_, ctx);
+    L.fr_loc.alloc(nF, ar_);
+    LAUNCH(k_gather<Frontier>, grid_threads(nF), 256, s_, fr_ref.get(), L.orig.get(), nF, L.fr_loc.get());
   }
-  const DBuf<Frontier> &fr = locality ? fr_loc : fr_ref;
-  const uint32_t *d_orig = locality ? orig.get() : nullptr;
-  DBuf<Window> win(nF, ar_);
-  DBuf<uint32_t> counts(nF, ar_);
-  DBuf<uint64_t> offs(nF + 1, ar_);
-  if (closed) LAUNCH(k_stab_count<true>, grid_warps(nF), 256, s_, ix_, fr.get(), nF, win.get(), counts.get());
-  else LAUNCH(k_stab_count<false>, grid_warps(nF), 256, s_, ix_, fr.get(), nF, win.get(), counts.get());
-  CUDA_CHECK(cudaMemsetAsync(offs.get() + nF, 0, 8, s_));
-  LAUNCH(k_u32_to_u64, grid_threads(nF), 256, s_, counts.get(), nF, offs.get());
-  exclusive_scan_u64(offs.get(), nF + 1, sc_, s_);
+  L.fr = locality ? L.fr_loc.get() : fr_ref.get();
+  L.d_orig = locality ? L.orig.get() : nullptr;
+  L.win.alloc(nF, ar_);
+  L.counts.alloc(nF, ar_);
+  L.offs.alloc(nF + 1, ar_);
+  if (closed) LAUNCH(k_stab_count<true>, grid_warps(nF), 256, s_, ix_, L.fr, nF, L.win.get(), L.counts.get());
+  else LAUNCH(k_stab_count<false>, grid_warps(nF), 256, s_, ix_, L.fr, nF, L.win.get(), L.counts.get());
+  CUDA_CHECK(cudaMemsetAsync(L.offs.get() + nF, 0, 8, s_));
+  LAUNCH(k_u32_to_u64, grid_threads(nF), 256, s_, L.counts.get(), nF, L.offs.get());
+  exclusive_scan_u64(L.offs.get(), nF + 1, sc_, s_);
   ctx.launches += 2;
-  const uint64_t H = read_u64(offs.get() + nF, s_, ctx);
+  const uint64_t H = read_u64(L.offs.get() + nF, s_, ctx);
   REQUIRE(H < (1ull << 32), IMPGX_E_INVALID, "more than 2^32 hits in one hop of one batch; lower IMPGX_ROWS_PER_BATCH");
   ctx.stab_ranges += nF;
   ctx.liftovers += H;
+  L.H = H;
   if (H == 0) {
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     return;
   }
-  // outputs that survive this function go below the temporaries (stack-discipline arena)
-  if (sink) sink->boxes.alloc(sink->prefix + H, ar_);
-  else lvl.hits.alloc(H, ar_);
-  if (p_.store_cigar) {
-    lvl.entry.alloc(H, ar_);
-    lvl.slices.alloc(H, ar_);
-  }
-  DBuf<LiftTask> tasks(H, ar_);
-  if (closed) LAUNCH(k_stab_fill<true>, grid_warps(nF), 256, s_, ix_, fr.get(), nF, win.get(), offs.get(), tasks.get());
-  else LAUNCH(k_stab_fill<false>, grid_warps(nF), 256, s_, ix_, fr.get(), nF, win.get(), offs.get(), tasks.get());
+  // outputs that survive the hop go below the temporaries (stack-discipline arena)
+  if (alloc_outputs) alloc_outputs(H);
+  L.tasks.alloc(H, ar_);
+  if (closed) LAUNCH(k_stab_fill<true>, grid_warps(nF), 256, s_, ix_, L.fr, nF, L.win.get(), L.offs.get(), L.tasks.get());
+  else LAUNCH(k_stab_fill<false>, grid_warps(nF), 256, s_, ix_, L.fr, nF, L.win.get(), L.offs.get(), L.tasks.get());
   CUDA_CHECK(cudaEventRecord(e1, s_));
   wt.reset(new WallTimer(ctx.w_lift));
 
-  DBuf<Hit> hits(H, ar_);
-  DBuf<CigarSlice> slices;
-  if (p_.store_cigar) slices.alloc(H, ar_);
+  L.hits.alloc(H, ar_);
+  if (p_.store_cigar) L.slices.alloc(H, ar_);
   CUDA_CHECK(cudaMemsetAsync(d_counters_.get(), 0, 32, s_));
   LiftParams lp;
   lp.clip = clip ? 1 : 0;
@@ -445,10 +513,10 @@ void Runner::stab_and_lift(const DBuf<Frontier> &fr_ref, uint64_t nF, bool close
   // endpoint kernel when neither the clipped CIGAR nor the identity is needed
   const bool ends = !p_.store_cigar && !lp.use_identity && !getenv("IMPGX_FULL_SCAN");
   if (ends)
-    LAUNCH(k_liftover_ends, grid_threads(H, 256, 8), 256, s_, ix_, fr.get(), tasks.get(), H, lp, hits.get(),
+    LAUNCH(k_liftover_ends, grid_threads(H, 256, 8), 256, s_, ix_, L.fr, L.tasks.get(), H, lp, L.hits.get(),
            d_counters_.get());
   else
-    LAUNCH(k_liftover, grid_warps(H, 256, 8), 256, s_, ix_, fr.get(), tasks.get(), H, lp, hits.get(), slices.get(),
+    LAUNCH(k_liftover, grid_warps(H, 256, 8), 256, s_, ix_, L.fr, L.tasks.get(), H, lp, L.hits.get(), L.slices.get(),
            d_counters_.get());
   CUDA_CHECK(cudaEventRecord(e2, s_));
   unsigned long long cnt[4];
@@ -463,34 +531,55 @@ void Runner::stab_and_lift(const DBuf<Frontier> &fr_ref, uint64_t nF, bool close
   ctx.lift_launches++;
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
   ctx.lift_runs += cnt[0];
-  // algorithmic bytes of the liftover: task 8 + range 16 +
-  // entry 32 + 2 checkpoints 16 + runs 4/run + hit 32 (+ slice 16)
-  // bytes the kernel's own algorithm touches
+  // bytes the kernel's own algorithm touches: task 8 + range 16 + entry 32 + hit 32 (+ slice 16),
+  // the checkpoints probed and the run blocks read
   if (ends) ctx.lift_touched += H * (8 + 16 + 32 + 32) + cnt[2] * 8 + cnt[0] * 4;
   else ctx.lift_touched += H * (8 + 16 + 32 + 16 + 32 + (p_.store_cigar ? 16 : 0)) + cnt[0] * 4;
   // algorithmic bytes per SURVEY.md §8(d): 32 (entry) + 16 (two checkpoints) + 4 r_ov (runs
   // intersecting the request) + 24 (hit out) [+ 4 r_ov with store_cigar]
   ctx.lift_bytes += H * (32 + 16 + 24) + cnt[3] * 4 * (p_.store_cigar ? 2 : 1);
   ctx.lift_rov += cnt[3];
-  const uint64_t n_ok = cnt[1];
+  L.n_ok = cnt[1];
+}
+
+// One hop on a whole (unsharded) index: leaves the accepted hits ordered by
+// (frontier index, visit rank) in lvl, or — last hop of the direct BED path —
+// writes their boxes straight into the sink.
+void Runner::stab_and_lift(const DBuf<Frontier> &fr_ref, uint64_t nF, bool closed, bool clip, BedSink *sink,
+                           LevelHits &lvl) {
+  lvl.n = 0;
+  if (nF == 0) return;
+  Lifted L;
+  lift_core(fr_ref, nF, closed, clip,
+            [&](uint64_t H) {
+              if (sink) sink->boxes.alloc(sink->prefix + H, ar_);
+              else lvl.hits.alloc(H, ar_);
+              if (p_.store_cigar) {
+                lvl.entry.alloc(H, ar_);
+                lvl.slices.alloc(H, ar_);
+              }
+            },
+            L);
+  const uint64_t H = L.H, n_ok = L.n_ok;
+  if (H == 0) return;
   lvl.n = n_ok;
   if (n_ok == 0 && !sink) return;
-  wt.reset(new WallTimer(ctx.w_order));
+  WallTimer wt(ctx.w_order);
 
   if (sink) {
     // direct BED path, last hop: no ordering sort — the reference order travels
     // as (range, visit rank) inside each box
     DBuf<uint64_t> dst_off;
-    if (d_orig) {
+    if (L.d_orig) {
       dst_off.alloc(nF + 1, ar_);
       CUDA_CHECK(cudaMemsetAsync(dst_off.get() + nF, 0, 8, s_));
-      LAUNCH(k_scatter_counts, grid_threads(nF), 256, s_, counts.get(), d_orig, nF, dst_off.get());
+      LAUNCH(k_scatter_counts, grid_threads(nF), 256, s_, L.counts.get(), L.d_orig, nF, dst_off.get());
       exclusive_scan_u64(dst_off.get(), nF + 1, sc_, s_);
       ctx.launches += 2;
     }
-    LAUNCH(k_boxes_from_raw_level, grid_threads(H), 256, s_, hits.get(), tasks.get(), d_orig, offs.get(),
+    LAUNCH(k_boxes_from_raw_level, grid_threads(H), 256, s_, L.hits.get(), L.tasks.get(), L.d_orig, L.offs.get(),
            dst_off.get(), H, sink->level, p_.min_output_length, sink->boxes.get() + sink->prefix,
-           sink->counters.get());
+           sink->counters.get(), (const uint32_t *)nullptr);
     sink->n = sink->prefix + H;
     sink->filled = true;
     lvl.n = 0;
@@ -498,13 +587,13 @@ void Runner::stab_and_lift(const DBuf<Frontier> &fr_ref, uint64_t nF, bool close
   }
   DBuf<uint64_t> keys(H, ar_);
   DBuf<uint32_t> perm(H, ar_);
-  LAUNCH(k_hit_order_keys, grid_threads(H), 256, s_, hits.get(), tasks.get(), d_orig, H, (uint32_t)nF, keys.get(),
+  LAUNCH(k_hit_order_keys, grid_threads(H), 256, s_, L.hits.get(), L.tasks.get(), L.d_orig, H, (uint32_t)nF, keys.get(),
          perm.get());
   sort_pairs(keys, perm, H, 0, 32 + bits_for(nF), sc_, s_, ctx);
-  LAUNCH(k_gather<Hit>, grid_threads(n_ok), 256, s_, hits.get(), perm.get(), n_ok, lvl.hits.get());
+  LAUNCH(k_gather<Hit>, grid_threads(n_ok), 256, s_, L.hits.get(), perm.get(), n_ok, lvl.hits.get());
   if (p_.store_cigar) {
-    LAUNCH(k_gather_entry, grid_threads(n_ok), 256, s_, tasks.get(), perm.get(), n_ok, lvl.entry.get());
-    LAUNCH(k_gather<CigarSlice>, grid_threads(n_ok), 256, s_, slices.get(), perm.get(), n_ok, lvl.slices.get());
+    LAUNCH(k_gather_entry, grid_threads(n_ok), 256, s_, L.tasks.get(), perm.get(), n_ok, lvl.entry.get());
+    LAUNCH(k_gather<CigarSlice>, grid_threads(n_ok), 256, s_, L.slices.get(), perm.get(), n_ok, lvl.slices.get());
   }
 }
 
@@ -727,9 +816,7 @@ void Runner::assemble(const impgx_range *d_ranges, uint32_t n_rows, std::vector<
   }
 }
 
-void Runner::run(const impgx_range *d_ranges, uint32_t n_rows, bool bed, BatchOut &out) {
-  REQUIRE(p_.mode <= IMPGX_MODE_DFS, IMPGX_E_INVALID, "unknown mode");
-  REQUIRE(!(bed && p_.store_cigar), IMPGX_E_INVALID, "BED output carries no CIGAR (src/main.rs:7447)");
+void Runner::prepare(const impgx_range *d_ranges, uint32_t n_rows) {
   d_counters_.alloc(4, ar_);
   // validation (perform_query bounds checks)
   {
@@ -750,6 +837,14 @@ void Runner::run(const impgx_range *d_ranges, uint32_t n_rows, bool bed, BatchOu
     d_row_target_.alloc(n_rows, ar_);
     LAUNCH(k_row_targets, grid_threads(n_rows), 256, s_, d_ranges, n_rows, d_row_target_.get());
   }
+}
+
+void Runner::run(const impgx_range *d_ranges, uint32_t n_rows, bool bed, BatchOut &out) {
+  REQUIRE(p_.mode <= IMPGX_MODE_DFS, IMPGX_E_INVALID, "unknown mode");
+  REQUIRE(!(bed && p_.store_cigar), IMPGX_E_INVALID, "BED output carries no CIGAR (src/main.rs:7447)");
+  REQUIRE(idx_->owner.empty(), IMPGX_E_INVALID,
+          "this index is one shard of a target-sharded index: use impgx_query_batch_bed_sharded");
+  prepare(d_ranges, n_rows);
 
   DBuf<Frontier> fr(n_rows, ar_);
   LAUNCH(k_init_frontier, grid_threads(n_rows), 256, s_, d_ranges, n_rows, fr.get());
@@ -829,7 +924,7 @@ void Runner::run(const impgx_range *d_ranges, uint32_t n_rows, bool bed, BatchOu
     }
     // seeds, then the levels that were ordered for the fold (their index is their ordinal)
     LAUNCH(k_boxes_from_seeds, grid_threads(n_rows), 256, s_, d_ranges, n_rows, p_.min_output_length,
-           p_.mode == IMPGX_MODE_QUERY ? 1 : 0, sink.boxes.get(), sink.counters.get());
+           p_.mode == IMPGX_MODE_QUERY ? 1 : 0, sink.boxes.get(), sink.counters.get(), (const uint32_t *)nullptr, 0u);
     uint64_t off = n_rows;
     for (size_t l = 0; l < levels.size(); l++) {
       if (!levels[l].n) continue;
@@ -980,7 +1075,85 @@ void Runner::bed_merge(BatchOut &raw, uint32_t n_rows, BatchOut &out) {
 }
 
 
-// output_results_bed's two merges straight from the boxes of the batch.
+// Stage A of output_results_bed (merge_adjusted_intervals_gap_2d, src/main.rs:12858-13011):
+// group the valid boxes by (row, q, t, strand), pairwise union-find per group.
+// acc[i] / is_root[i] for i < nv hold the merged boxes.
+void Runner::stage_a(const BoxD *boxes, uint64_t nB, uint64_t nv, DBuf<BoxD> &acc, DBuf<uint64_t> &is_root) {
+  const int seq_bits = bits_for(ix_.n_seqs > 1 ? ix_.n_seqs - 1 : 1);
+  const int bits_a = bits_a_;
+  acc.alloc(nv, ar_);
+  is_root.alloc(nv, ar_);
+  if (nv == 0) return;
+  DBuf<uint64_t> ka(nB, ar_);
+  DBuf<uint32_t> perm(nB, ar_);
+  LAUNCH(k_bd_key_a, grid_threads(nB), 256, s_, boxes, nB, seq_bits, 1ull << bits_a, ka.get(), perm.get());
+  sort_pairs(ka, perm, nB, 0, bits_a + 1, sc_, s_, ctx);
+  Groups g;
+  build_groups(ka.get(), nv, g, sc_, s_, ctx);
+  DBuf<uint32_t> parent(nv, ar_);
+  LAUNCH(k_merge2d_direct, grid_threads(g.G, 128, 16), 128, s_, boxes, perm.get(), g.begins.get(), g.G,
+         (int64_t)p_.merge_distance, parent.get(), acc.get(), is_root.get());
+}
+
+// Stage B (merge_query_adjusted_intervals, src/main.rs:12474-12560): global sort of
+// the roots by (row, q, start, strand), sweep per (row, q), compaction into `out`.
+// is_root == nullptr: every box is a root.
+void Runner::stage_b(const BoxD *acc, const uint64_t *is_root, uint64_t n, unsigned long long *d_root_counter,
+                     uint32_t n_rows, BatchOut &out, uint32_t *row_cnt) {
+  if (n == 0) return;
+  const int seq_bits = bits_for(ix_.n_seqs > 1 ? ix_.n_seqs - 1 : 1);
+  const int bits_b = bits_b_;
+  const int32_t d = p_.merge_distance;
+  const bool ms = p_.merge_strands != 0;
+  (void)n_rows;
+  DBuf<uint64_t> kb(n, ar_);
+  DBuf<uint32_t> permb(n, ar_);
+  CUDA_CHECK(cudaMemsetAsync(d_root_counter, 0, 8, s_));
+  LAUNCH(k_bd_key_b, grid_threads(n), 256, s_, acc, is_root, n, seq_bits, 1ull << bits_b, kb.get(), permb.get(),
+         d_root_counter);
+  sort_pairs(kb, permb, n, 0, bits_b + 1, sc_, s_, ctx);
+  unsigned long long nr = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&nr, d_root_counter, 8, cudaMemcpyDeviceToHost, s_));
+  CUDA_CHECK(cudaStreamSynchronize(s_));
+  ctx.d2h_bytes += 8;
+  if (nr == 0) return;
+  DBuf<BoxD> sorted(nr, ar_);
+  LAUNCH(k_gather<BoxD>, grid_threads(nr), 256, s_, acc, permb.get(), (uint64_t)nr, sorted.get());
+  DBuf<uint64_t> seg(nr, ar_);
+  LAUNCH(k_keys_shift, grid_threads(nr), 256, s_, kb.get(), (uint64_t)nr, 33, seg.get());
+  Groups g;
+  build_groups(seg.get(), nr, g, sc_, s_, ctx);
+  DBuf<BoxD> swept(nr, ar_);
+  DBuf<uint32_t> cnt(g.G, ar_);
+  LAUNCH(k_sweep_direct, grid_threads(g.G, 128, 16), 128, s_, sorted.get(), kb.get(), g.begins.get(), g.G, d, ms ? 1 : 0,
+         swept.get(), cnt.get());
+  DBuf<uint64_t> scan(g.G + 1, ar_);
+  CUDA_CHECK(cudaMemsetAsync(scan.get() + g.G, 0, 8, s_));
+  LAUNCH(k_u32_to_u64, grid_threads(g.G), 256, s_, cnt.get(), g.G, scan.get());
+  exclusive_scan_u64(scan.get(), g.G + 1, sc_, s_);
+  ctx.launches += 2;
+  const uint64_t M = read_u64(scan.get() + g.G, s_, ctx);
+  OutCols oc = alloc_out_cols(out, M);
+  LAUNCH(k_sweep_compact_direct, grid_threads(g.G), 256, s_, swept.get(), g.begins.get(), cnt.get(), scan.get(), g.G, oc,
+         row_cnt);
+}
+
+OutCols Runner::alloc_out_cols(BatchOut &out, uint64_t n) {
+  OutCols oc;
+  oc.cig_len = nullptr; oc.src_entry = nullptr; oc.src_slice = nullptr;
+  out.n_results = n;
+  out.q_id.alloc(n, ar_); out.t_id.alloc(n, ar_);
+  out.q_first.alloc(n, ar_); out.q_last.alloc(n, ar_);
+  out.t_first.alloc(n, ar_); out.t_last.alloc(n, ar_);
+  oc.q_id = out.q_id.get(); oc.q_first = out.q_first.get(); oc.q_last = out.q_last.get();
+  oc.t_id = out.t_id.get(); oc.t_first = out.t_first.get(); oc.t_last = out.t_last.get();
+  return oc;
+}
+
+// output_results_bed's two merges straight from the boxes of the batch. On a
+// sharded index stage A runs where the hits were produced (owner of the target
+// sequence: a (row, q, t, strand) group never spans ranks), the merged boxes
+// travel to the owner of their query sequence, and stage B runs there.
 void Runner::bed_merge_direct(BedSink &sink, uint32_t n_rows, BatchOut &out) {
   WallTimer wt(ctx.w_merge);
   cudaEvent_t e0, e1;
@@ -999,21 +1172,16 @@ void Runner::bed_merge_direct(BedSink &sink, uint32_t n_rows, BatchOut &out) {
   CUDA_CHECK(cudaMemcpyAsync(&nv, sink.counters.get(), 8, cudaMemcpyDeviceToHost, s_));
   CUDA_CHECK(cudaStreamSynchronize(s_));
   ctx.d2h_bytes += 8;
-  OutCols oc;
-  oc.cig_len = nullptr; oc.src_entry = nullptr; oc.src_slice = nullptr;
-  auto alloc_out = [&](uint64_t n) {
-    out.n_results = n;
-    out.q_id.alloc(n, ar_); out.t_id.alloc(n, ar_);
-    out.q_first.alloc(n, ar_); out.q_last.alloc(n, ar_);
-    out.t_first.alloc(n, ar_); out.t_last.alloc(n, ar_);
-    oc.q_id = out.q_id.get(); oc.q_first = out.q_first.get(); oc.q_last = out.q_last.get();
-    oc.t_id = out.t_id.get(); oc.t_first = out.t_first.get(); oc.t_last = out.t_last.get();
-  };
-  if (nv > 0) {
-    REQUIRE(nB < (1ull << 32), IMPGX_E_INVALID, "more than 2^32 results in one batch; lower IMPGX_ROWS_PER_BATCH");
-    const int row_bits = bits_for(n_rows > 1 ? n_rows - 1 : 1);
-    const int seq_bits = bits_for(ix_.n_seqs > 1 ? ix_.n_seqs - 1 : 1);
-    if (d < 0 && !ms) {
+  REQUIRE(nB < (1ull << 32), IMPGX_E_INVALID, "more than 2^32 results in one batch; lower IMPGX_ROWS_PER_BATCH");
+  const int row_bits = bits_for(n_rows > 1 ? n_rows - 1 : 1);
+  const int seq_bits = bits_for(ix_.n_seqs > 1 ? ix_.n_seqs - 1 : 1);
+  bits_a_ = row_bits + 2 * seq_bits + 1;
+  bits_b_ = row_bits + seq_bits + 33;
+  if (d < 0 && !ms) {
+    REQUIRE(!comm_, IMPGX_E_UNSUPPORTED,
+            "--no-merge with --consider-strandness keeps the reference's unsorted result order, which a sharded "
+            "index does not assemble; use an unsharded index");
+    if (nv > 0) {
       // nothing merges and nothing is sorted (src/main.rs:12479,12859): reference order per row
       DBuf<uint64_t> k1(nB, ar_);
       DBuf<uint32_t> perm(nB, ar_);
@@ -1022,115 +1190,27 @@ void Runner::bed_merge_direct(BedSink &sink, uint32_t n_rows, BatchOut &out) {
       DBuf<uint64_t> k2(nB, ar_);
       LAUNCH(k_bd_key_row, grid_threads(nB), 256, s_, sink.boxes.get(), perm.get(), nB, n_rows, k2.get());
       sort_pairs(k2, perm, nB, 0, bits_for(n_rows), sc_, s_, ctx);
-      alloc_out(nv);
+      OutCols oc = alloc_out_cols(out, nv);
       LAUNCH(k_boxd_to_cols, grid_threads(nv), 256, s_, sink.boxes.get(), perm.get(), (uint64_t)nv, oc, row_cnt.get());
-    } else {
-      const int bits_a = row_bits + 2 * seq_bits + 1, bits_b = row_bits + seq_bits + 33;
-      REQUIRE(bits_a <= 63 && bits_b <= 63, IMPGX_E_INVALID,
-              "batch too large for the packed merge keys; lower IMPGX_ROWS_PER_BATCH");
-      // ---- stage A: group by (row, q, t, strand), pairwise union-find
-      DBuf<BoxD> acc(nv, ar_);
-      DBuf<uint64_t> is_root(nv, ar_);
-      DBuf<uint64_t> ka(nB, ar_);
-      {
-        DBuf<uint32_t> perm(nB, ar_);
-        LAUNCH(k_bd_key_a, grid_threads(nB), 256, s_, sink.boxes.get(), nB, seq_bits, 1ull << bits_a, ka.get(),
-               perm.get());
-        sort_pairs(ka, perm, nB, 0, bits_a + 1, sc_, s_, ctx);
-        Groups g;
-        build_groups(ka.get(), nv, g, sc_, s_, ctx);
-        DBuf<uint32_t> parent(nv, ar_);
-        LAUNCH(k_merge2d_direct, grid_threads(g.G, 128, 16), 128, s_, sink.boxes.get(), perm.get(), g.begins.get(), g.G,
-               (int64_t)d, parent.get(), acc.get(), is_root.get());
-      }
-      // ---- stage B. The boxes are already grouped by (row, q): sort each segment by
-      // (start, strand, ord) in shared memory and sweep it (no second global sort).
-      bool done_b = false;
-      if (getenv("IMPGX_MERGE_SMEM")) {  // measured slower than the global sort on C3 and C4; kept for experiments
-        DBuf<uint64_t> seg(nv, ar_);
-        LAUNCH(k_keys_shift, grid_threads(nv), 256, s_, ka.get(), (uint64_t)nv, seq_bits + 1, seg.get());
-        Groups g;
-        build_groups(seg.get(), nv, g, sc_, s_, ctx);
-        DBuf<uint32_t> list_warp(g.G, ar_), list_cta(g.G, ar_);
-        DBuf<unsigned int> cls(4, ar_);
-        CUDA_CHECK(cudaMemsetAsync(cls.get(), 0, 16, s_));
-        LAUNCH(k_seg_classify, grid_threads(g.G), 256, s_, g.begins.get(), g.G, is_root.get(), list_warp.get(),
-               list_cta.get(), cls.get());
-        unsigned int hc[4];
-        CUDA_CHECK(cudaMemcpyAsync(hc, cls.get(), 16, cudaMemcpyDeviceToHost, s_));
-        CUDA_CHECK(cudaStreamSynchronize(s_));
-        ctx.d2h_bytes += 16;
-        if (hc[2] == 0) {
-          DBuf<BoxD> swept(nv, ar_);
-          DBuf<uint32_t> cnt(g.G, ar_);
-          if (hc[0]) {
-            auto kern = k_segment_sweep<32, SEG_WARP_CAP>;
-            const size_t smem = (size_t)4 * SEG_WARP_CAP * 24;
-            CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const unsigned grid = (unsigned)std::min<uint64_t>((hc[0] + 3) / 4, (uint64_t)sm_count() * 4);
-            kern<<<grid, 128, smem, s_>>>(acc.get(), is_root.get(), g.begins.get(), list_warp.get(), hc[0], d, ms ? 1 : 0,
-                                          swept.get(), cnt.get());
-            CUDA_CHECK(cudaGetLastError());
-            ctx.launches++;
-          }
-          if (hc[1]) {
-            auto kern = k_segment_sweep<256, SEG_CTA_CAP>;
-            const size_t smem = (size_t)SEG_CTA_CAP * 24;
-            CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const unsigned grid = (unsigned)std::min<uint64_t>(hc[1], (uint64_t)sm_count() * 2);
-            kern<<<grid, 256, smem, s_>>>(acc.get(), is_root.get(), g.begins.get(), list_cta.get(), hc[1], d, ms ? 1 : 0,
-                                          swept.get(), cnt.get());
-            CUDA_CHECK(cudaGetLastError());
-            ctx.launches++;
-          }
-          DBuf<uint64_t> scan(g.G + 1, ar_);
-          CUDA_CHECK(cudaMemsetAsync(scan.get() + g.G, 0, 8, s_));
-          LAUNCH(k_u32_to_u64, grid_threads(g.G), 256, s_, cnt.get(), g.G, scan.get());
-          exclusive_scan_u64(scan.get(), g.G + 1, sc_, s_);
-          ctx.launches += 2;
-          const uint64_t M = read_u64(scan.get() + g.G, s_, ctx);
-          alloc_out(M);
-          LAUNCH(k_sweep_compact_direct, grid_threads(g.G), 256, s_, swept.get(), g.begins.get(), cnt.get(), scan.get(),
-                 g.G, oc, row_cnt.get());
-          done_b = true;
-        }
-      }
-      if (!done_b) {
-        // fallback: global sort by (row, q, start, strand), sweep per (row, q)
-        DBuf<uint64_t> kb(nv, ar_);
-        DBuf<uint32_t> permb(nv, ar_);
-        LAUNCH(k_bd_key_b, grid_threads(nv), 256, s_, acc.get(), is_root.get(), (uint64_t)nv, seq_bits, 1ull << bits_b,
-               kb.get(), permb.get(), sink.counters.get() + 1);
-        sort_pairs(kb, permb, nv, 0, bits_b + 1, sc_, s_, ctx);
-        unsigned long long nr = 0;
-        CUDA_CHECK(cudaMemcpyAsync(&nr, sink.counters.get() + 1, 8, cudaMemcpyDeviceToHost, s_));
-        CUDA_CHECK(cudaStreamSynchronize(s_));
-        ctx.d2h_bytes += 8;
-        DBuf<BoxD> sorted(nr, ar_);
-        LAUNCH(k_gather<BoxD>, grid_threads(nr), 256, s_, acc.get(), permb.get(), (uint64_t)nr, sorted.get());
-        DBuf<uint64_t> seg(nr, ar_);
-        LAUNCH(k_keys_shift, grid_threads(nr), 256, s_, kb.get(), (uint64_t)nr, 33, seg.get());
-        Groups g;
-        build_groups(seg.get(), nr, g, sc_, s_, ctx);
-        DBuf<BoxD> swept(nr, ar_);
-        DBuf<uint32_t> cnt(g.G, ar_);
-        LAUNCH(k_sweep_direct, grid_threads(g.G, 128, 16), 128, s_, sorted.get(), kb.get(), g.begins.get(), g.G, d,
-               ms ? 1 : 0, swept.get(), cnt.get());
-        DBuf<uint64_t> scan(g.G + 1, ar_);
-        CUDA_CHECK(cudaMemsetAsync(scan.get() + g.G, 0, 8, s_));
-        LAUNCH(k_u32_to_u64, grid_threads(g.G), 256, s_, cnt.get(), g.G, scan.get());
-        exclusive_scan_u64(scan.get(), g.G + 1, sc_, s_);
-        ctx.launches += 2;
-        const uint64_t M = read_u64(scan.get() + g.G, s_, ctx);
-        alloc_out(M);
-        LAUNCH(k_sweep_compact_direct, grid_threads(g.G), 256, s_, swept.get(), g.begins.get(), cnt.get(), scan.get(),
-               g.G, oc, row_cnt.get());
-      }
     }
-    LAUNCH(k_u32_to_u64, grid_threads(n_rows), 256, s_, row_cnt.get(), n_rows, out.row_off.get());
-    exclusive_scan_u64(out.row_off.get(), (uint64_t)n_rows + 1, sc_, s_);
-    ctx.launches += 2;
+  } else if (nv > 0 || comm_) {
+    REQUIRE(bits_a_ <= 63 && bits_b_ <= 63, IMPGX_E_INVALID,
+            "batch too large for the packed merge keys; lower IMPGX_ROWS_PER_BATCH");
+    DBuf<BoxD> acc;
+    DBuf<uint64_t> is_root;
+    stage_a(sink.boxes.get(), nB, nv, acc, is_root);
+    if (comm_) {
+      DBuf<BoxD> recv;
+      uint64_t n_recv = 0;
+      route_roots(acc, is_root, nv, recv, n_recv);
+      stage_b(recv.get(), nullptr, n_recv, sink.counters.get() + 1, n_rows, out, row_cnt.get());
+    } else {
+      stage_b(acc.get(), is_root.get(), nv, sink.counters.get() + 1, n_rows, out, row_cnt.get());
+    }
   }
+  LAUNCH(k_u32_to_u64, grid_threads(n_rows), 256, s_, row_cnt.get(), n_rows, out.row_off.get());
+  exclusive_scan_u64(out.row_off.get(), (uint64_t)n_rows + 1, sc_, s_);
+  ctx.launches += 2;
   CUDA_CHECK(cudaEventRecord(e1, s_));
   CUDA_CHECK(cudaStreamSynchronize(s_));
   float msf = 0;
@@ -1138,6 +1218,245 @@ void Runner::bed_merge_direct(BedSink &sink, uint32_t n_rows, BatchOut &out) {
   ctx.merge_ms += msf;
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
+}
+
+// ============================================================ sharded index
+// Partition `n` records by destination rank (dest[i] in [0, N], N = "nowhere")
+// and exchange them: returns the received records, grouped by source rank.
+template <class T>
+static void exchange_by_dest(Comm &cm, DBuf<T> &recs, DBuf<uint32_t> &dest, DBuf<uint32_t> &idx,
+                             const unsigned long long *d_dest_cnt, uint64_t n, DBuf<T> &recv, uint64_t &n_recv,
+                             Arena &ar, Scratch &sc, cudaStream_t s, Ctx &ctx) {
+  const int N = cm.size();
+  std::vector<uint64_t> cnt((size_t)N + 1, 0);
+  CUDA_CHECK(cudaMemcpyAsync(cnt.data(), d_dest_cnt, ((size_t)N + 1) * 8, cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  ctx.d2h_bytes += ((size_t)N + 1) * 8;
+  std::vector<uint64_t> all((size_t)N * N);
+  cm.allgather_u64(cnt.data(), (size_t)N, all.data(), s);
+  std::vector<uint64_t> send_off((size_t)N, 0), recv_cnt((size_t)N, 0), recv_off((size_t)N, 0);
+  uint64_t so = 0, ro = 0;
+  for (int p = 0; p < N; p++) {
+    send_off[p] = so;
+    so += cnt[p];
+    recv_cnt[p] = all[(size_t)p * N + cm.rank()];
+    recv_off[p] = ro;
+    ro += recv_cnt[p];
+  }
+  n_recv = ro;
+  REQUIRE(n_recv < (1ull << 32), IMPGX_E_INVALID, "more than 2^32 records received in one exchange; lower IMPGX_ROWS_PER_BATCH");
+  recv.alloc(n_recv, ar);
+  DBuf<T> send(so, ar);
+  if (n) {
+    sort_pairs(dest, idx, n, 0, bits_for((uint64_t)N), sc, s, ctx);  // stable: source order kept per destination
+    if (so) {
+      k_gather<T><<<grid_threads(so), 256, 0, s>>>(recs.get(), idx.get(), so, send.get());
+      CUDA_CHECK(cudaGetLastError());
+      ctx.launches++;
+    }
+  }
+  cm.alltoallv(send.get(), cnt.data(), send_off.data(), recv.get(), recv_cnt.data(), recv_off.data(), sizeof(T), s);
+  CUDA_CHECK(cudaStreamSynchronize(s));  // `send` is released on return
+}
+
+// Non-last hop on a shard: the accepted hits go to the owner of the sequence
+// they land on; what arrives is brought into the reference's hit order
+// (global frontier index, visit rank) for the fold.
+void Runner::route_hits(const Lifted &L, const uint32_t *gmap, LevelHits &lvl) {
+  Comm &cm = *comm_;
+  const uint32_t N = (uint32_t)cm.size();
+  const uint64_t H = L.H;
+  DBuf<unsigned long long> dcnt(N + 1, ar_);
+  CUDA_CHECK(cudaMemsetAsync(dcnt.get(), 0, (N + 1) * 8, s_));
+  DBuf<RoutedHit> routed(H, ar_), recv;
+  DBuf<uint32_t> dest(H, ar_), idx(H, ar_);
+  if (H)
+    LAUNCH(k_route_hits, grid_threads(H), 256, s_, L.hits.get(), L.tasks.get(), L.d_orig, gmap, idx_->d_owner, H, N,
+           routed.get(), dest.get(), idx.get(), dcnt.get());
+  uint64_t n_recv = 0;
+  exchange_by_dest(cm, routed, dest, idx, dcnt.get(), H, recv, n_recv, ar_, sc_, s_, ctx);
+  lvl.n = n_recv;
+  if (n_recv == 0) return;
+  lvl.hits.alloc(n_recv, ar_);
+  DBuf<Hit> tmp(n_recv, ar_);
+  DBuf<uint64_t> keys(n_recv, ar_);
+  DBuf<uint32_t> perm(n_recv, ar_);
+  LAUNCH(k_routed_to_hits, grid_threads(n_recv), 256, s_, recv.get(), n_recv, tmp.get(), keys.get(), perm.get());
+  sort_pairs(keys, perm, n_recv, 0, 64, sc_, s_, ctx);
+  LAUNCH(k_gather<Hit>, grid_threads(n_recv), 256, s_, tmp.get(), perm.get(), n_recv, lvl.hits.get());
+  CUDA_CHECK(cudaStreamSynchronize(s_));
+}
+
+// All-gather-v of the next frontier (the exchange north_star names): every rank
+// learns the global frontier, whose order (row, sequence, start) is the
+// reference's frontier order; a rank keeps the ranges on the sequences it owns,
+// tagged with their global index.
+void Runner::global_frontier(DBuf<Frontier> &fr, uint64_t &nF, DBuf<uint32_t> &gmap, uint64_t total,
+                             const std::vector<uint64_t> &cnt) {
+  Comm &cm = *comm_;
+  const int N = cm.size();
+  std::vector<uint64_t> off((size_t)N, 0);
+  for (int p = 1; p < N; p++) off[p] = off[p - 1] + cnt[p - 1];
+  DBuf<Frontier> all(total, ar_);
+  cm.allgatherv(fr.get(), nF, all.get(), cnt.data(), off.data(), sizeof(Frontier), s_);
+  const int seq_bits = bits_for(ix_.n_seqs > 1 ? ix_.n_seqs - 1 : 1);
+  DBuf<uint64_t> keys(total, ar_);
+  DBuf<uint32_t> perm(total, ar_);
+  LAUNCH(k_frontier_gkeys, grid_threads(total), 256, s_, all.get(), total, seq_bits, keys.get(), perm.get());
+  sort_pairs(keys, perm, total, 0, 26 + seq_bits, sc_, s_, ctx);  // row < 2^26 (checked in run_sharded)
+  DBuf<uint64_t> flag(total + 1, ar_), scan(total + 1, ar_);
+  CUDA_CHECK(cudaMemsetAsync(flag.get() + total, 0, 8, s_));
+  LAUNCH(k_frontier_own_flags, grid_threads(total), 256, s_, all.get(), perm.get(), total, idx_->d_owner,
+         (uint32_t)cm.rank(), flag.get());
+  CUDA_CHECK(cudaMemcpyAsync(scan.get(), flag.get(), (total + 1) * 8, cudaMemcpyDeviceToDevice, s_));
+  exclusive_scan_u64(scan.get(), total + 1, sc_, s_);
+  ctx.launches += 2;
+  const uint64_t mine = read_u64(scan.get() + total, s_, ctx);
+  REQUIRE(mine == nF, IMPGX_E_CUDA, "sharded frontier: a rank produced ranges on sequences it does not own");
+  DBuf<Frontier> f2(mine, ar_);
+  DBuf<uint32_t> g2(mine, ar_);
+  LAUNCH(k_frontier_take_owned, grid_threads(total), 256, s_, all.get(), perm.get(), total, flag.get(), scan.get(),
+         f2.get(), g2.get());
+  CUDA_CHECK(cudaStreamSynchronize(s_));
+  fr = std::move(f2);
+  gmap = std::move(g2);
+}
+
+// Stage-A roots travel to the owner of their query sequence.
+void Runner::route_roots(DBuf<BoxD> &acc, DBuf<uint64_t> &is_root, uint64_t nv, DBuf<BoxD> &recv, uint64_t &n_recv) {
+  Comm &cm = *comm_;
+  const uint32_t N = (uint32_t)cm.size();
+  DBuf<unsigned long long> dcnt(N + 1, ar_);
+  CUDA_CHECK(cudaMemsetAsync(dcnt.get(), 0, (N + 1) * 8, s_));
+  DBuf<uint32_t> dest(nv, ar_), idx(nv, ar_);
+  if (nv)
+    LAUNCH(k_root_dest, grid_threads(nv), 256, s_, acc.get(), is_root.get(), nv, idx_->d_owner, N, dest.get(), idx.get(),
+           dcnt.get());
+  exchange_by_dest(cm, acc, dest, idx, dcnt.get(), nv, recv, n_recv, ar_, sc_, s_, ctx);
+}
+
+void Runner::run_sharded(const impgx_range *d_ranges, uint32_t n_rows, BatchOut &out) {
+  REQUIRE(comm_ && !idx_->owner.empty() && idx_->d_owner, IMPGX_E_INVALID, "run_sharded needs a shard index and a comm");
+  REQUIRE((uint32_t)comm_->size() == idx_->shard_size && (uint32_t)comm_->rank() == idx_->shard_rank, IMPGX_E_INVALID,
+          "comm rank/size do not match the shard index");
+  REQUIRE(comm_->size() <= MAX_RANKS, IMPGX_E_INVALID, "too many ranks");
+  REQUIRE(p_.mode == IMPGX_MODE_QUERY || p_.mode == IMPGX_MODE_BFS, IMPGX_E_UNSUPPORTED,
+          "the sharded index runs Impg::query and the transitive BFS (DFS: use an unsharded index)");
+  REQUIRE(!p_.store_cigar, IMPGX_E_INVALID, "BED output carries no CIGAR (src/main.rs:7447)");
+  REQUIRE(n_rows < (1u << 26), IMPGX_E_INVALID, "more than 2^26 rows in one batch; lower IMPGX_ROWS_PER_BATCH");
+  Comm &cm = *comm_;
+  const int N = cm.size();
+  const uint32_t me = (uint32_t)cm.rank();
+  const bool bfs = p_.mode == IMPGX_MODE_BFS;
+  prepare(d_ranges, n_rows);
+
+  // level-0 frontier: the rows on targets this rank owns; the global frontier
+  // index of a row is the row itself
+  DBuf<Frontier> fr;
+  DBuf<uint32_t> gmap;
+  uint64_t nF = 0;
+  {
+    DBuf<Frontier> all(n_rows, ar_);
+    LAUNCH(k_init_frontier, grid_threads(n_rows), 256, s_, d_ranges, n_rows, all.get());
+    DBuf<uint64_t> flag((uint64_t)n_rows + 1, ar_), scan((uint64_t)n_rows + 1, ar_);
+    CUDA_CHECK(cudaMemsetAsync(flag.get() + n_rows, 0, 8, s_));
+    LAUNCH(k_shard_seed_flags, grid_threads(n_rows), 256, s_, all.get(), (uint64_t)n_rows,
+           bfs ? p_.min_transitive_len : 0, idx_->d_owner, me, flag.get());
+    CUDA_CHECK(cudaMemcpyAsync(scan.get(), flag.get(), ((uint64_t)n_rows + 1) * 8, cudaMemcpyDeviceToDevice, s_));
+    exclusive_scan_u64(scan.get(), (uint64_t)n_rows + 1, sc_, s_);
+    ctx.launches += 2;
+    nF = read_u64(scan.get() + n_rows, s_, ctx);
+    DBuf<Frontier> f2(nF, ar_);
+    DBuf<uint32_t> g2(nF, ar_);
+    LAUNCH(k_frontier_compact, grid_threads(n_rows), 256, s_, all.get(), (uint64_t)n_rows, flag.get(), scan.get(), f2.get());
+    if (nF) LAUNCH(k_frontier_rows, grid_threads(nF), 256, s_, f2.get(), nF, g2.get());
+    CUDA_CHECK(cudaStreamSynchronize(s_));
+    fr = std::move(f2);
+    gmap = std::move(g2);
+  }
+  // visited sets: seeded for every row; only the owner of a row's target ever touches its entry
+  Visited V;
+  if (bfs) {
+    V.keys.alloc(n_rows, ar_);
+    V.start.alloc(n_rows, ar_);
+    V.end.alloc(n_rows, ar_);
+    V.n = n_rows;
+    LAUNCH(k_seed_visited, grid_threads(n_rows), 256, s_, d_ranges, n_rows, V.keys.get(), V.start.get(), V.end.get());
+  }
+
+  BedSink sink;
+  sink.counters.alloc(2, ar_);
+  CUDA_CHECK(cudaMemsetAsync(sink.counters.get(), 0, 16, s_));
+  std::vector<DBuf<BoxD>> level_boxes;  // boxes of the non-last hops
+  std::vector<uint64_t> level_n;
+  uint64_t prior = 0;
+  uint32_t depth = 0;
+  std::vector<uint64_t> cnt((size_t)N);
+  for (;;) {
+    // every rank learns every rank's frontier size: loop control must agree
+    cm.allgather_u64(&nF, 1, cnt.data(), s_);
+    uint64_t total = 0;
+    for (int p = 0; p < N; p++) total += cnt[p];
+    if (total == 0) break;
+    if (bfs && p_.max_depth != 0 && depth >= p_.max_depth) break;
+    if (!bfs && depth >= 1) break;
+    REQUIRE(total < (1ull << 26) && depth < 58, IMPGX_E_INVALID,
+            "global frontier exceeds 2^26 ranges in one batch; lower IMPGX_ROWS_PER_BATCH");
+    if (depth > 0) global_frontier(fr, nF, gmap, total, cnt);
+    const bool last = !bfs || (p_.max_depth != 0 && depth + 1 >= p_.max_depth);
+    Lifted L;
+    DBuf<BoxD> boxes_h;
+    BoxD *dst = nullptr;
+    lift_core(fr, nF, /*closed=*/!bfs, /*clip=*/bfs,
+              [&](uint64_t H) {
+                if (last) {
+                  sink.prefix = (uint64_t)n_rows + prior;
+                  sink.boxes.alloc(sink.prefix + H, ar_);
+                  sink.n = sink.prefix + H;
+                  sink.filled = true;
+                  dst = sink.boxes.get() + sink.prefix;
+                } else {
+                  boxes_h.alloc(H, ar_);
+                  dst = boxes_h.get();
+                }
+              },
+              L);
+    if (L.H)
+      LAUNCH(k_boxes_from_raw_level, grid_threads(L.H), 256, s_, L.hits.get(), L.tasks.get(), L.d_orig, L.offs.get(),
+             (const uint64_t *)nullptr, L.H, depth + 1, p_.min_output_length, dst, sink.counters.get(), gmap.get());
+    depth++;
+    if (last) break;
+    prior += L.H;
+    level_n.push_back(L.H);
+    level_boxes.push_back(std::move(boxes_h));
+    LevelHits lvl;
+    route_hits(L, gmap.get(), lvl);
+    DBuf<Frontier> next;
+    uint64_t n_next = 0;
+    fold(lvl, n_rows, V, next, n_next);
+    fr = std::move(next);
+    nF = n_next;
+  }
+  {
+    WallTimer wt(ctx.w_assemble);
+    if (!sink.filled) {
+      sink.prefix = (uint64_t)n_rows + prior;
+      sink.boxes.alloc(sink.prefix, ar_);
+      sink.n = sink.prefix;
+    }
+    LAUNCH(k_boxes_from_seeds, grid_threads(n_rows), 256, s_, d_ranges, n_rows, p_.min_output_length, bfs ? 0 : 1,
+           sink.boxes.get(), sink.counters.get(), (const uint32_t *)idx_->d_owner, me);
+    uint64_t off = n_rows;
+    for (size_t l = 0; l < level_boxes.size(); l++) {
+      if (level_n[l])
+        CUDA_CHECK(cudaMemcpyAsync(sink.boxes.get() + off, level_boxes[l].get(), level_n[l] * sizeof(BoxD),
+                                   cudaMemcpyDeviceToDevice, s_));
+      off += level_n[l];
+    }
+    CUDA_CHECK(cudaStreamSynchronize(s_));
+    level_boxes.clear();
+  }
+  bed_merge_direct(sink, n_rows, out);
 }
 
 // Transitive DFS (src/impg.rs:2057-2309). The walk of one row is inherently
@@ -1227,8 +1546,9 @@ static uint64_t env_u64(const char *name, uint64_t dflt) {
 }
 
 impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n, const impgx_params &p, bool bed,
-                           bool ranges_on_device, bool results_to_host, void *stream) {
+                           bool ranges_on_device, bool results_to_host, void *stream, Comm *comm) {
   REQUIRE(idx, IMPGX_E_INVALID, "index is NULL");
+  REQUIRE(!comm || bed, IMPGX_E_UNSUPPORTED, "the sharded index returns BED rows only");
   REQUIRE(ranges || n == 0, IMPGX_E_INVALID, "ranges is NULL");
   REQUIRE(p.mode <= IMPGX_MODE_DFS, IMPGX_E_INVALID, "unknown mode");
   REQUIRE(p.max_depth <= 65535, IMPGX_E_INVALID, "max_depth is a u16 in the reference");
@@ -1292,8 +1612,9 @@ impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n
           d_r = d_stage.get();
         }
         BatchOut bo;
-        Runner runner(idx, p, s);
-        runner.run(d_r, (uint32_t)m, bed, bo);
+        Runner runner(idx, p, s, comm);
+        if (comm) runner.run_sharded(d_r, (uint32_t)m, bo);
+        else runner.run(d_r, (uint32_t)m, bed, bo);
         const Ctx &c = runner.ctx;
         total.launches += c.launches; total.lift_launches += c.lift_launches;
         total.stab_ranges += c.stab_ranges; total.liftovers += c.liftovers;
@@ -1366,10 +1687,17 @@ impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n
       }
       // every arena block of this batch is out of scope and the stream is idle
       idx->arena.reset();
+      if (comm) {
+        // every rank must cut the same row batches: size them by the busiest rank
+        std::vector<uint64_t> all((size_t)comm->size());
+        comm->allgather_u64(&chunk_hits, 1, all.data(), s);
+        chunk_hits = *std::max_element(all.begin(), all.end());
+      }
       idx->hits_per_row = std::max(idx->hits_per_row * 0.9, (double)chunk_hits / (double)m + 1.0);
       done += m;
     }
   } catch (...) {
+    if (comm) comm->abort();  // release peers blocked in an exchange
     cudaStreamSynchronize(s);
     free_chunks();
     idx->arena.reset();

@@ -21,11 +21,12 @@ struct Ctx {
 const char *last_error();
 void check_device(int device);
 impgx_index *index_build(const impgx_record *recs, size_t n, const uint32_t *runs, const uint64_t *run_offsets,
-                         const uint64_t *seq_lens, uint32_t n_seqs, bool bidirectional, int device);
+                         const uint64_t *seq_lens, uint32_t n_seqs, bool bidirectional, int device,
+                         const uint32_t *owner = nullptr, uint32_t rank = 0, uint32_t n_ranks = 1);
 
 // Runs the whole batch (chunked into row batches), ranges on host or device.
 impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n, const impgx_params &p, bool bed,
-                           bool ranges_on_device, bool results_to_host, void *stream);
+                           bool ranges_on_device, bool results_to_host, void *stream, class Comm *comm = nullptr);
 
 void project_batch(int device, size_t n, const int32_t *req_start, const int32_t *req_end, const impgx_record *records,
                    const uint32_t *runs, const uint64_t *run_offsets, int32_t *out4, uint8_t *ok,

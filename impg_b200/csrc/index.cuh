@@ -31,8 +31,13 @@ void visit_ranks(size_t n, uint32_t *rank);
 // (src/impg.rs:1535-1652): forward entry under target_id, reversed entry under
 // query_id (skipped for self alignments), per-target order = record order,
 // then a stable sort by start (coitrees' radix sort on `first`).
+// With `owner` != nullptr only the entries of the targets owned by `rank` are
+// built (a target-sharded index); the visit ranks are unchanged
+// because a target's entries are never split.
 void build_host_columns(const impgx_record *recs, size_t n, const uint64_t *run_offsets, uint32_t n_seqs,
-                        bool bidirectional, HostColumns &out);
+                        bool bidirectional, HostColumns &out, const uint32_t *owner = nullptr, uint32_t rank = 0);
+void assign_owners(const impgx_record *recs, size_t n, const uint64_t *run_offsets, uint32_t n_seqs, bool bidirectional,
+                   uint32_t n_ranks, uint32_t *owner);
 
 struct Stats {
   impgx_stats s{};
@@ -57,6 +62,11 @@ struct impgx_index {
   impgx::Arena arena;  // device scratch of the query pipeline
   impgx_stats last{};
   double hits_per_row = 0;  // observed liftovers per row (sizes the row batches)
+  // target-sharded index: this object holds the entries of the
+  // sequences with owner[seq] == shard_rank; empty owner = the whole index
+  std::vector<uint32_t> owner;
+  uint32_t *d_owner = nullptr;
+  uint32_t shard_rank = 0, shard_size = 1;
 
   impgx::DevIndexView view() const {
     impgx::DevIndexView v;

@@ -47,13 +47,50 @@ void visit_ranks(size_t n, uint32_t *rank) {
   walk(0, n, 0, 0, rank, ctr);
 }
 
+// Balanced assignment of target sequences to ranks: weight of
+// a sequence = bytes of its entry columns + the run-stream regions its entries
+// walk; longest-processing-time greedy, ties by id, so every rank computes the
+// same map from the same records.
+void assign_owners(const impgx_record *recs, size_t n, const uint64_t *run_offsets, uint32_t n_seqs, bool bidirectional,
+                   uint32_t n_ranks, uint32_t *owner) {
+  REQUIRE(n_ranks >= 1, IMPGX_E_INVALID, "n_ranks must be >= 1");
+  std::vector<uint64_t> w(n_seqs, 0);
+  for (size_t i = 0; i < n; i++) {
+    const impgx_record &r = recs[i];
+    REQUIRE(r.query_id < n_seqs && r.target_id < n_seqs, IMPGX_E_INVALID, "record references an unknown sequence id");
+    const uint64_t b = 44 + (uint64_t)aln_sectors((uint32_t)(run_offsets[i + 1] - run_offsets[i])) * 32;
+    w[r.target_id] += b;
+    if (bidirectional && r.query_id != r.target_id) w[r.query_id] += b;
+  }
+  std::vector<uint32_t> order(n_seqs);
+  std::iota(order.begin(), order.end(), 0u);
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return w[a] > w[b]; });
+  std::vector<uint64_t> load(n_ranks, 0);
+  for (uint32_t s : order) {
+    uint32_t best = 0;
+    for (uint32_t r = 1; r < n_ranks; r++)
+      if (load[r] < load[best]) best = r;
+    owner[s] = best;
+    load[best] += w[s] + 1;  // +1: sequences without alignments are spread too
+  }
+}
+
 void build_host_columns(const impgx_record *recs, size_t n, const uint64_t *run_offsets, uint32_t n_seqs,
-                        bool bidirectional, HostColumns &out) {
-  // stream offset (32-byte sectors) of each alignment
+                        bool bidirectional, HostColumns &out, const uint32_t *owner, uint32_t rank) {
+  auto owned = [&](uint32_t seq) { return !owner || owner[seq] == rank; };
+  for (size_t i = 0; i < n; i++) {
+    const impgx_record &r = recs[i];
+    REQUIRE(r.query_id < n_seqs && r.target_id < n_seqs, IMPGX_E_INVALID, "record references an unknown sequence id");
+    REQUIRE(r.strand <= 1, IMPGX_E_INVALID, "record strand must be 0 or 1");
+  }
+  // stream offset (32-byte sectors) of each alignment this shard walks
   out.aln_off.resize(n + 1);
   uint64_t sectors = 0;
   for (size_t i = 0; i < n; i++) {
     out.aln_off[i] = (uint32_t)sectors;
+    const impgx_record &r = recs[i];
+    const bool needed = owned(r.target_id) || (bidirectional && r.query_id != r.target_id && owned(r.query_id));
+    if (!needed) continue;
     uint64_t nr = run_offsets[i + 1] - run_offsets[i];
     REQUIRE(nr < (1ull << 30), IMPGX_E_INVALID, "alignment with >= 2^30 CIGAR runs");
     sectors += aln_sectors((uint32_t)nr);
@@ -65,10 +102,8 @@ void build_host_columns(const impgx_record *recs, size_t n, const uint64_t *run_
   std::vector<uint64_t> cnt(n_seqs + 1, 0);
   for (size_t i = 0; i < n; i++) {
     const impgx_record &r = recs[i];
-    REQUIRE(r.query_id < n_seqs && r.target_id < n_seqs, IMPGX_E_INVALID, "record references an unknown sequence id");
-    REQUIRE(r.strand <= 1, IMPGX_E_INVALID, "record strand must be 0 or 1");
-    cnt[r.target_id + 1]++;
-    if (bidirectional && r.query_id != r.target_id) cnt[r.query_id + 1]++;
+    if (owned(r.target_id)) cnt[r.target_id + 1]++;
+    if (bidirectional && r.query_id != r.target_id && owned(r.query_id)) cnt[r.query_id + 1]++;
   }
   out.tgt_off.assign(n_seqs + 1, 0);
   for (uint32_t s = 0; s < n_seqs; s++) out.tgt_off[s + 1] = out.tgt_off[s] + cnt[s + 1];
@@ -84,8 +119,9 @@ void build_host_columns(const impgx_record *recs, size_t n, const uint64_t *run_
     std::vector<uint64_t> cur(out.tgt_off.begin(), out.tgt_off.end() - 1);
     for (size_t i = 0; i < n; i++) {
       const impgx_record &r = recs[i];
-      tmp[cur[r.target_id]++] = Tmp{r.target_start, (uint32_t)(i << 1)};
-      if (bidirectional && r.query_id != r.target_id) tmp[cur[r.query_id]++] = Tmp{r.query_start, (uint32_t)(i << 1) | 1u};
+      if (owned(r.target_id)) tmp[cur[r.target_id]++] = Tmp{r.target_start, (uint32_t)(i << 1)};
+      if (bidirectional && r.query_id != r.target_id && owned(r.query_id))
+        tmp[cur[r.query_id]++] = Tmp{r.query_start, (uint32_t)(i << 1) | 1u};
     }
   }
   REQUIRE(n < (1ull << 31), IMPGX_E_INVALID, "more than 2^31 records; shard the index");

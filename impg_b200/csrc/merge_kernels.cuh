@@ -275,12 +275,14 @@ struct __align__(8) BoxD {
 
 __device__ __forceinline__ uint64_t make_ord(uint32_t level, uint64_t low) { return ((uint64_t)level << 58) | low; }
 
+// `owner` != nullptr (sharded index): only the rows on targets owned by `rank` are valid here
 __global__ void k_boxes_from_seeds(const impgx_range *__restrict__ ranges, uint32_t n, int32_t min_out, int apply_len,
-                                   BoxD *__restrict__ out, unsigned long long *__restrict__ n_valid) {
+                                   BoxD *__restrict__ out, unsigned long long *__restrict__ n_valid,
+                                   const uint32_t *__restrict__ owner, uint32_t rank) {
   for (uint64_t i = gtid(); i < n; i += gstride()) {
     impgx_range r = ranges[i];
-    bool ok = true;
-    if (apply_len && min_out >= 0) ok = (r.end - r.start) >= min_out;
+    bool ok = !owner || owner[r.target_id] == rank;
+    if (apply_len && min_out >= 0) ok = ok && (r.end - r.start) >= min_out;
     out[i] = BoxD{r.start, r.end, r.start, r.end, r.target_id, r.target_id, (uint32_t)i, ok ? 1u : 0u, make_ord(0, 0)};
     if (ok) atomicAdd(n_valid, 1ull);
   }
@@ -302,20 +304,22 @@ __global__ void k_boxes_from_sorted_level(const Hit *__restrict__ hits, uint64_t
 // hits of the last level in task order (frontier range, sorted position); ord from (range, visit rank)
 // With a locality-permuted frontier (`orig` != nullptr) the boxes are written
 // back in the reference's frontier order (dst_off = offsets of the ranges in
-// that order), so the merge sorts see row-grouped input.
+// that order), so the merge sorts see row-grouped input. `gmap` != nullptr
+// (sharded index): the order key uses the range's index in the GLOBAL frontier.
 __global__ void k_boxes_from_raw_level(const Hit *__restrict__ hits, const LiftTask *__restrict__ tasks,
                                        const uint32_t *__restrict__ orig, const uint64_t *__restrict__ offs,
                                        const uint64_t *__restrict__ dst_off, uint64_t n, uint32_t level, int32_t min_out,
-                                       BoxD *__restrict__ out, unsigned long long *__restrict__ n_valid) {
+                                       BoxD *__restrict__ out, unsigned long long *__restrict__ n_valid,
+                                       const uint32_t *__restrict__ gmap) {
   unsigned long long c = 0;
   for (uint64_t i = gtid(); i < n; i += gstride()) {
     Hit h = hits[i];
     bool ok = h.row != INVALID_ID && passes_len(h, min_out);
     const uint32_t k = tasks[i].range;
     const uint32_t r = orig ? orig[k] : k;
-    const uint64_t dst = orig ? dst_off[r] + (i - offs[k]) : i;
+    const uint64_t dst = (orig && dst_off) ? dst_off[r] + (i - offs[k]) : i;
     out[dst] = BoxD{h.q_first, h.q_last, h.t_first, h.t_last, h.q_id, h.t_id, h.row, ok ? 1u : 0u,
-                    make_ord(level, ((uint64_t)r << 32) | h.vrank)};
+                    make_ord(level, ((uint64_t)(gmap ? gmap[r] : r) << 32) | h.vrank)};
     c += ok ? 1 : 0;
   }
   if (c) atomicAdd(n_valid, c);
@@ -415,7 +419,7 @@ __global__ void k_bd_key_b(const BoxD *__restrict__ acc, const uint64_t *__restr
                            unsigned long long *__restrict__ n_roots) {
   unsigned long long c = 0;
   for (uint64_t i = gtid(); i < n; i += gstride()) {
-    if (!is_root[i]) {
+    if (is_root && !is_root[i]) {  // is_root == nullptr: every box is a root (received from the peers)
       keys[i] = invalid_key;
       vals[i] = (uint32_t)i;
       continue;
@@ -535,140 +539,3 @@ __global__ void k_boxd_to_cols(const BoxD *__restrict__ b, const uint32_t *__res
 
 }  // namespace impgx
 
-// ===================================================================
-// Stage B without a global sort: after stage A the boxes are grouped by
-// (row, q_id) already (sort-A order), so each (row, q_id) segment is sorted by
-// (start, strand, ord) in shared memory (bitonic) and swept in place. One
-// segment per warp (<= 512 roots) or per CTA (<= 4096); larger segments make
-// the batch fall back to the global-sort path.
-namespace impgx {
-
-constexpr int SEG_WARP_CAP = 512;
-constexpr int SEG_CTA_CAP = 4096;
-
-// per segment: number of roots -> class (0 warp, 1 CTA, 2 too large); appends the segment to its list
-__global__ void k_seg_classify(const uint32_t *__restrict__ begins, uint64_t n_seg, const uint64_t *__restrict__ is_root,
-                               uint32_t *__restrict__ list_warp, uint32_t *__restrict__ list_cta,
-                               unsigned int *__restrict__ counters /* [0] warp, [1] cta, [2] too large */) {
-  for (uint64_t g = gtid(); g < n_seg; g += gstride()) {
-    const uint32_t b = begins[g], e = begins[g + 1];
-    uint32_t c = 0;
-    for (uint32_t i = b; i < e; i++) c += is_root[i] ? 1u : 0u;
-    if (c <= (uint32_t)SEG_WARP_CAP) list_warp[atomicAdd(&counters[0], 1u)] = (uint32_t)g;
-    else if (c <= (uint32_t)SEG_CTA_CAP) list_cta[atomicAdd(&counters[1], 1u)] = (uint32_t)g;
-    else atomicAdd(&counters[2], 1u);
-  }
-}
-
-// THREADS cooperating threads per segment (32 = a warp, else the whole CTA), CAP roots at most.
-template <int THREADS, int CAP>
-__global__ void __launch_bounds__(THREADS == 32 ? 128 : THREADS)
-    k_segment_sweep(const BoxD *__restrict__ acc, const uint64_t *__restrict__ is_root, const uint32_t *__restrict__ begins,
-                    const uint32_t *__restrict__ seg_list, uint32_t n_list, int32_t merge_distance, int merge_strands,
-                    BoxD *__restrict__ swept, uint32_t *__restrict__ out_cnt) {
-  constexpr int GROUPS = (THREADS == 32) ? 4 : 1;  // segments processed concurrently by a CTA
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  // per group: key[CAP] u64 | ord[CAP] u64 | idx[CAP] u32 | end[CAP] i32
-  constexpr size_t PER_GROUP = (size_t)CAP * (8 + 8 + 4 + 4);
-  const int grp = (THREADS == 32) ? (threadIdx.x >> 5) : 0;
-  const int tid = (THREADS == 32) ? (threadIdx.x & 31) : threadIdx.x;
-  unsigned char *base = smem_raw + (size_t)grp * PER_GROUP;
-  uint64_t *key = reinterpret_cast<uint64_t *>(base);
-  uint64_t *ord = key + CAP;
-  uint32_t *idx = reinterpret_cast<uint32_t *>(ord + CAP);
-  int32_t *endv = reinterpret_cast<int32_t *>(idx + CAP);
-  __shared__ uint32_t s_cnt[GROUPS];
-  auto sync = [&]() {
-    if (THREADS == 32) __syncwarp();
-    else __syncthreads();
-  };
-
-  for (uint32_t li = blockIdx.x * GROUPS + grp; li < n_list; li += gridDim.x * GROUPS) {
-    const uint32_t g = seg_list[li];
-    const uint32_t b = begins[g], e = begins[g + 1];
-    // ---- load the roots of the segment
-    if (tid == 0) s_cnt[grp] = 0;
-    sync();
-    for (uint32_t i0 = b; i0 < e; i0 += THREADS) {
-      const uint32_t i = i0 + tid;
-      if (i < e && is_root[i]) {
-        const uint32_t pos = atomicAdd(&s_cnt[grp], 1u);  // order inside the segment is fixed by the sort below
-        const BoxD x = acc[i];
-        const bool fwd = x.q_lo <= x.q_hi;
-        const int32_t start = fwd ? x.q_lo : x.q_hi;
-        key[pos] = ((uint64_t)(uint32_t)start << 1) | (fwd ? 0u : 1u);
-        ord[pos] = x.ord;
-        idx[pos] = i;
-        endv[pos] = fwd ? x.q_hi : x.q_lo;
-      }
-    }
-    sync();
-    const uint32_t cnt = s_cnt[grp];
-    uint32_t N = 1;
-    while (N < cnt) N <<= 1;
-    for (uint32_t i = cnt + tid; i < N; i += THREADS) {
-      key[i] = ~0ull;
-      ord[i] = ~0ull;
-      idx[i] = 0xffffffffu;
-      endv[i] = 0;
-    }
-    sync();
-    // ---- bitonic sort by (key, ord): the reference's stable sort leaves equal keys in input order = ord order
-    for (uint32_t k = 2; k <= N; k <<= 1) {
-      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-        for (uint32_t t = tid; t < N; t += THREADS) {
-          const uint32_t p = t ^ j;
-          if (p > t) {
-            const bool up = (t & k) == 0;
-            const uint64_t ka = key[t], kb = key[p], oa = ord[t], ob = ord[p];
-            const bool a_gt_b = ka > kb || (ka == kb && oa > ob);
-            if (a_gt_b == up) {
-              key[t] = kb; key[p] = ka;
-              ord[t] = ob; ord[p] = oa;
-              const uint32_t ti = idx[t]; idx[t] = idx[p]; idx[p] = ti;
-              const int32_t te = endv[t]; endv[t] = endv[p]; endv[p] = te;
-            }
-          }
-        }
-        sync();
-      }
-    }
-    // ---- the literal sweep of src/main.rs:12496-12556 (sequential by nature), from shared memory
-    if (tid == 0) {
-      uint32_t w = b;
-      if (cnt > 0) {
-        uint32_t head = idx[0];
-        bool cf = (key[0] & 1ull) == 0;
-        int32_t cs = (int32_t)(uint32_t)(key[0] >> 1), ce = endv[0];
-        auto flush = [&]() {
-          BoxD x = acc[head];
-          x.q_lo = cf ? cs : ce;
-          x.q_hi = cf ? ce : cs;
-          swept[w++] = x;
-        };
-        for (uint32_t r = 1; r < cnt; r++) {
-          const bool nf = (key[r] & 1ull) == 0;
-          const int32_t ns = (int32_t)(uint32_t)(key[r] >> 1), ne = endv[r];
-          if (merge_distance < 0 || (!merge_strands && cf != nf) || (int64_t)ns > (int64_t)ce + merge_distance) {
-            flush();
-            head = idx[r];
-            cf = nf; cs = ns; ce = ne;
-          } else {
-            const int32_t ms = min(cs, ns), me = max(ce, ne);
-            bool mf = cf;
-            if (merge_strands && cf != nf) {
-              const int64_t cl = (int64_t)ce - cs, nl = (int64_t)ne - ns;
-              mf = nl > cl ? nf : cf;
-            }
-            cf = mf; cs = ms; ce = me;
-          }
-        }
-        flush();
-      }
-      out_cnt[g] = w - b;
-    }
-    sync();
-  }
-}
-
-}  // namespace impgx

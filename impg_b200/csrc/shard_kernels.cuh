@@ -1,0 +1,116 @@
+// shard_kernels.cuh — routing kernels of the target-sharded pipeline
+// (SURVEY.md §8e). A rank owns the sequences with owner[seq] == rank: it stabs
+// and lifts the frontier ranges that lie on them, keeps the visited sets of
+// (row, owned sequence) and merges the BED rows of (row, owned sequence).
+// Lifted hits travel to owner(hit.q_id); the reference's result order travels
+// with them as (global frontier index, coitrees visit rank).
+#pragma once
+#include "merge_kernels.cuh"
+
+namespace impgx {
+
+constexpr int MAX_RANKS = 64;
+
+// A lifted hit on its way to the rank that owns the sequence it lands on: what
+// the fold needs (src/impg.rs:2467-2560) plus the global order key. 32 bytes.
+struct __align__(32) RoutedHit {
+  uint32_t row, q_id;
+  int32_t q_first, q_last;
+  uint32_t t_id;
+  uint32_t gidx;   // index of the source range in the global frontier of the hop
+  uint32_t vrank;  // visit rank of the entry within its target
+  uint32_t pad;
+};
+static_assert(sizeof(RoutedHit) == 32, "RoutedHit must be one sector");
+
+// level-0 frontier of a shard: rows on owned targets (BFS: long enough to expand)
+__global__ void k_shard_seed_flags(const Frontier *__restrict__ f, uint64_t n, int32_t min_len,
+                                   const uint32_t *__restrict__ owner, uint32_t rank, uint64_t *__restrict__ flag) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) {
+    long long d = (long long)f[i].start - (long long)f[i].end;
+    flag[i] = ((d < 0 ? -d : d) >= min_len && owner[f[i].seq] == rank) ? 1 : 0;
+  }
+}
+__global__ void k_frontier_rows(const Frontier *__restrict__ f, uint64_t n, uint32_t *__restrict__ gmap) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) gmap[i] = f[i].row;
+}
+
+// accepted hits -> routed records + destination rank (rejected hits: dest = n_ranks, sorted last)
+__global__ void k_route_hits(const Hit *__restrict__ hits, const LiftTask *__restrict__ tasks,
+                             const uint32_t *__restrict__ orig, const uint32_t *__restrict__ gmap,
+                             const uint32_t *__restrict__ owner, uint64_t n, uint32_t n_ranks,
+                             RoutedHit *__restrict__ out, uint32_t *__restrict__ dest, uint32_t *__restrict__ idx,
+                             unsigned long long *__restrict__ dest_cnt) {
+  __shared__ unsigned int bins[MAX_RANKS + 1];
+  for (unsigned k = threadIdx.x; k <= n_ranks; k += blockDim.x) bins[k] = 0;
+  __syncthreads();
+  for (uint64_t i = gtid(); i < n; i += gstride()) {
+    const Hit h = hits[i];
+    const uint32_t k = tasks[i].range;
+    const uint32_t r = orig ? orig[k] : k;
+    // hits back onto the frontier's own sequence are never expanded (src/impg.rs:2507): not routed
+    const bool go = h.row != INVALID_ID && h.q_id != h.t_id;
+    const uint32_t d = go ? owner[h.q_id] : n_ranks;
+    out[i] = RoutedHit{h.row, h.q_id, h.q_first, h.q_last, h.t_id, gmap[r], h.vrank, 0u};
+    dest[i] = d;
+    idx[i] = (uint32_t)i;
+    atomicAdd(&bins[d], 1u);
+  }
+  __syncthreads();
+  for (unsigned k = threadIdx.x; k <= n_ranks; k += blockDim.x)
+    if (bins[k]) atomicAdd(&dest_cnt[k], (unsigned long long)bins[k]);
+}
+
+// received records -> Hit (target coordinates are not needed by the fold) + order key
+__global__ void k_routed_to_hits(const RoutedHit *__restrict__ in, uint64_t n, Hit *__restrict__ hits,
+                                 uint64_t *__restrict__ keys, uint32_t *__restrict__ idx) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) {
+    const RoutedHit r = in[i];
+    hits[i] = Hit{r.row, r.q_id, r.q_first, r.q_last, r.t_id, 0, 0, r.vrank};
+    keys[i] = ((uint64_t)r.gidx << 32) | r.vrank;
+    idx[i] = (uint32_t)i;
+  }
+}
+
+// global frontier order: (row, seq); ranges of one (row, seq) come from one rank, already sorted by start
+__global__ void k_frontier_gkeys(const Frontier *__restrict__ f, uint64_t n, int seq_bits, uint64_t *__restrict__ keys,
+                                 uint32_t *__restrict__ idx) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) {
+    keys[i] = ((uint64_t)f[i].row << seq_bits) | f[i].seq;
+    idx[i] = (uint32_t)i;
+  }
+}
+__global__ void k_frontier_own_flags(const Frontier *__restrict__ f, const uint32_t *__restrict__ perm, uint64_t n,
+                                     const uint32_t *__restrict__ owner, uint32_t rank, uint64_t *__restrict__ flag) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) flag[i] = owner[f[perm[i]].seq] == rank ? 1 : 0;
+}
+// local frontier in global order; gmap = position in the global order
+__global__ void k_frontier_take_owned(const Frontier *__restrict__ f, const uint32_t *__restrict__ perm, uint64_t n,
+                                      const uint64_t *__restrict__ flag, const uint64_t *__restrict__ scan,
+                                      Frontier *__restrict__ out, uint32_t *__restrict__ gmap) {
+  for (uint64_t i = gtid(); i < n; i += gstride())
+    if (flag[i]) {
+      out[scan[i]] = f[perm[i]];
+      gmap[scan[i]] = (uint32_t)i;
+    }
+}
+
+// stage-A roots -> destination rank = owner of the query sequence (non-roots sort last)
+__global__ void k_root_dest(const BoxD *__restrict__ acc, const uint64_t *__restrict__ is_root, uint64_t n,
+                            const uint32_t *__restrict__ owner, uint32_t n_ranks, uint32_t *__restrict__ dest,
+                            uint32_t *__restrict__ idx, unsigned long long *__restrict__ dest_cnt) {
+  __shared__ unsigned int bins[MAX_RANKS + 1];
+  for (unsigned k = threadIdx.x; k <= n_ranks; k += blockDim.x) bins[k] = 0;
+  __syncthreads();
+  for (uint64_t i = gtid(); i < n; i += gstride()) {
+    const uint32_t d = is_root[i] ? owner[acc[i].q_id] : n_ranks;
+    dest[i] = d;
+    idx[i] = (uint32_t)i;
+    atomicAdd(&bins[d], 1u);
+  }
+  __syncthreads();
+  for (unsigned k = threadIdx.x; k <= n_ranks; k += blockDim.x)
+    if (bins[k]) atomicAdd(&dest_cnt[k], (unsigned long long)bins[k]);
+}
+
+}  // namespace impgx

@@ -1,10 +1,19 @@
-"""Multi-GPU plumbing of the projection path.
+"""Multi-GPU plumbing of the projection path (one process per GPU).
 
-BED rows are independent queries (reference src/main.rs:7435: one
-perform_query per row), and the C4 index fits one B200, so N GPUs run N
-processes, each with an index replica and its own share of the rows: there is
-no data-path collective. torch.distributed is used only for the barrier and the
-max-over-ranks timing that bench.py reports (NCCL on GPUs, gloo in CPU tests).
+Two ways to spread a query batch over N GPUs:
+
+* rows over index replicas — BED rows are independent queries (reference
+  src/main.rs:7435: one perform_query per row); when the index fits one B200
+  every rank holds a replica and takes its own share of the rows: no data-path
+  collective;
+* index sharded by target sequence — rank r holds the entries,
+  run stream and visited sets of the sequences it owns; a batch is a collective
+  call and the library exchanges lifted hits (all-to-all-v) and the next
+  frontier (all-gather-v) over NCCL between transitive hops (csrc/comm.cu).
+
+torch.distributed carries only the plumbing: the NCCL unique id, the barrier,
+the max-over-ranks timing and the gather of result columns to rank 0 (NCCL on
+GPUs, gloo in CPU tests).
 """
 import os
 
@@ -55,3 +64,32 @@ def gather_row_counts(local_rows_done, device="cpu"):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return int(t[0])
+
+
+def nccl_comm(rank, world, device):
+    """NCCL endpoint of this rank for the sharded index: rank 0 creates the unique id,
+    torch.distributed (already initialised) hands it to the others."""
+    import torch.distributed as dist
+
+    import impg_b200 as ix
+
+    box = [ix.Comm.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    return ix.Comm.nccl(box[0], rank, world, device)
+
+
+def gather_columns(cols):
+    """Every rank's result columns on every rank (list indexed by rank); feed to
+    impg_b200.merge_shard_columns."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [cols]
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, cols)
+    return out
+
+
+def owner_histogram(owner, world):
+    """Sequences per rank of an owner map."""
+    return np.bincount(np.asarray(owner, dtype=np.int64), minlength=world)

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define IMPGX_ABI_VERSION 1
+#define IMPGX_ABI_VERSION 2
 
 typedef enum impgx_status {
   IMPGX_OK = 0,
@@ -190,6 +190,55 @@ int impgx_query_batch_bed(impgx_index *idx, const impgx_range *ranges, size_t n,
 int impgx_query_batch_bed_device(impgx_index *idx, const impgx_range *d_ranges,
                                  size_t n, const impgx_params *params,
                                  void *stream, impgx_results **out);
+
+/* ---- target-sharded index (replaces MultiImpg's role of
+ * spreading one logical index over several holders, src/multi_impg.rs:495-595).
+ * The index is partitioned by target sequence: rank r holds the interval
+ * columns, run stream and visited sets of the sequences with owner[seq] == r.
+ * A query batch is a COLLECTIVE call: every rank passes the same ranges and
+ * params; between transitive hops the ranks exchange lifted hits (all-to-all-v,
+ * to the owner of the sequence a hit lands on) and the next frontier
+ * (all-gather-v) over an impgx_comm. Rank r returns the BED rows whose
+ * sequence it owns; impgx_results_merge_shards reassembles the reference's
+ * per-row output (rows of one input row are ordered by sequence id). */
+typedef struct impgx_comm impgx_comm;
+#define IMPGX_COMM_ID_BYTES 128
+/* NCCL transport, one process per GPU: rank 0 creates the id (ncclGetUniqueId)
+ * and hands it to the other ranks by any out-of-band means. */
+int impgx_comm_unique_id(uint8_t id[IMPGX_COMM_ID_BYTES]);
+int impgx_comm_init_nccl(const uint8_t id[IMPGX_COMM_ID_BYTES], int rank, int n_ranks, int device,
+                         impgx_comm **out);
+/* In-process transport: n_ranks endpoints (out[0..n_ranks)), each driven by its
+ * own host thread; the shards may sit on different devices or share one. After
+ * a failed collective call the group is unusable and must be recreated. */
+int impgx_comm_init_local(int n_ranks, impgx_comm **out);
+int impgx_comm_rank(const impgx_comm *c);
+int impgx_comm_size(const impgx_comm *c);
+/* bytes this rank sent / received in exchanges so far, number of exchange steps */
+int impgx_comm_traffic(const impgx_comm *c, uint64_t *sent, uint64_t *received, uint64_t *exchanges);
+void impgx_comm_free(impgx_comm *c);
+
+/* Balanced sequence -> rank map (weight = entry bytes + run-stream bytes of the
+ * sequence's entries; deterministic, so every rank computes the same map). */
+int impgx_assign_owners(const impgx_record *records, size_t n_records, const uint64_t *run_offsets,
+                        uint32_t n_seqs, int bidirectional, uint32_t n_ranks, uint32_t *owner_out);
+/* As impgx_index_build, keeping only the entries of the sequences owned by
+ * `rank` (and the runs of the alignments those entries walk). `records` may be
+ * the full list or any subset that contains every alignment touching an owned
+ * sequence, in the original relative order. */
+int impgx_index_build_shard(const impgx_record *records, size_t n_records, const uint32_t *runs,
+                            const uint64_t *run_offsets, const uint64_t *seq_lens, uint32_t n_seqs,
+                            int bidirectional, int device, const uint32_t *owner, uint32_t rank,
+                            uint32_t n_ranks, impgx_index **out);
+/* Collective counterparts of impgx_query_batch_bed / _bed_device. Modes QUERY
+ * and BFS; DFS and raw (unmerged) results need an unsharded index. */
+int impgx_query_batch_bed_sharded(impgx_index *shard, impgx_comm *comm, const impgx_range *ranges, size_t n,
+                                  const impgx_params *params, impgx_results **out);
+int impgx_query_batch_bed_sharded_device(impgx_index *shard, impgx_comm *comm, const impgx_range *d_ranges,
+                                         size_t n, const impgx_params *params, void *stream,
+                                         impgx_results **out);
+/* Host-side reassembly of the per-rank BED rows into one result set. */
+int impgx_results_merge_shards(const impgx_results *const *parts, int n_parts, impgx_results **out);
 
 int impgx_results_view(const impgx_results *res, impgx_view *view);        /* host columns */
 int impgx_results_device_view(const impgx_results *res, impgx_view *view); /* device columns */

@@ -54,3 +54,52 @@ def test_two_rank_gloo_reductions(tmp_path):
     assert o[0]["total"] == 100 and o[1]["total"] == 100
     assert (o[0]["lo"], o[0]["hi"], o[1]["lo"], o[1]["hi"]) == (0, 51, 51, 101)
     assert o[0]["first"] != o[1]["first"]  # different BEDs per rank
+
+
+def test_two_rank_gloo_sharded_host_logic(tmp_path):
+    """Host side of the target-sharded path over gloo: both ranks derive the same
+    owner map, their record subsets cover every alignment (each at most twice),
+    and rank-local result columns gathered with all_gather_object reassemble into
+    the per-row, per-sequence order."""
+    script = tmp_path / "w.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys, json
+        sys.path.insert(0, {ROOT!r})
+        sys.path.insert(0, os.path.join({ROOT!r}, "tests"))
+        import numpy as np
+        from impg_b200 import dist as D
+        import impg_b200 as ix
+        rank, local, world = D.env_rank()
+        D.init("gloo")
+        cfg = ix.synth_cfg(5, 2, 40000, 4, 30, 100, 1)
+        recs, runs, offs, lens, names = ix.synth_generate(cfg)
+        owner = ix.assign_owners(recs, offs, len(lens), world)
+        keep = ix.shard_records(recs, offs, owner, rank)
+        # fake rank-local BED rows: one row per (input row, owned sequence)
+        n_rows = 4
+        mine = np.nonzero(owner == rank)[0].astype(np.uint32)
+        q = np.tile(mine, n_rows)
+        ro = (np.arange(n_rows + 1) * len(mine)).astype(np.uint64)
+        val = (np.repeat(np.arange(n_rows), len(mine)) * 1000 + q).astype(np.int32)
+        cols = dict(row_offsets=ro, q_id=q, q_first=val, q_last=val, t_id=q, t_first=val, t_last=val)
+        parts = D.gather_columns(cols)
+        merged = ix.merge_shard_columns(parts)
+        out = dict(rank=rank, owner=owner.tolist(), keep=keep.tolist(), merged=merged["q_first"].tolist(),
+                   ro=merged["row_offsets"].tolist(), hist=D.owner_histogram(owner, world).tolist())
+        open(os.path.join({str(tmp_path)!r}, f"out{{rank}}.json"), "w").write(json.dumps(out))
+    """))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29613")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29613", str(script)],
+                       env=env, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stderr[-2000:]
+    import json
+    o = [json.load(open(tmp_path / f"out{k}.json")) for k in range(2)]
+    assert o[0]["owner"] == o[1]["owner"] and sorted(set(o[0]["owner"])) == [0, 1]
+    assert o[0]["hist"] == [5, 5]
+    n_aln = 5 * 4 * 2 * 4
+    cover = np.bincount(np.array(o[0]["keep"] + o[1]["keep"]), minlength=n_aln)
+    assert cover.min() >= 1 and cover.max() <= 2
+    want = [r * 1000 + s for r in range(4) for s in range(10)]
+    assert o[0]["merged"] == want and o[1]["merged"] == want
+    assert o[0]["ro"] == [0, 10, 20, 30, 40]

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     L = ix.lib()
     missing = [n for n in sorted(names) if not hasattr(L, n)]
     assert not missing, missing
-    assert L.impgx_abi_version() == 1
+    assert L.impgx_abi_version() == 2
 
 
 def test_parse_cigar_matches_oracle():
@@ -159,3 +159,85 @@ def test_cli_fails_loudly_without_gpu():
     assert r.returncode != 0 and "no CUDA device" in r.stderr
     r = subprocess.run([cli, "-a", "x.paf", "-r", "A:0-10"], capture_output=True, text=True)
     assert r.returncode != 0 and "merge-distance is required" in r.stderr
+
+
+# ---------------------------------------------------------------- target-sharded index (host logic)
+def _small_world(seed=3):
+    cfg = ix.synth_cfg(6, 2, 60000, 8, 30, 300, seed)
+    return cfg, ix.synth_generate(cfg)
+
+
+@pytest.mark.parametrize("n_ranks", [1, 2, 3, 8])
+def test_owner_map_is_balanced_and_deterministic(n_ranks):
+    cfg, (recs, runs, offs, lens, names) = _small_world()
+    owner = ix.assign_owners(recs, offs, len(lens), n_ranks)
+    assert owner.max() < n_ranks and (owner == ix.assign_owners(recs, offs, len(lens), n_ranks)).all()
+    # weight per rank (entry bytes + stream bytes) within 1.5x of the mean on an all-vs-all set
+    nr = np.diff(offs.astype(np.int64))
+    w = np.zeros(len(lens))
+    np.add.at(w, recs["target_id"], nr)
+    np.add.at(w, recs["query_id"], nr)
+    load = np.bincount(owner, weights=w, minlength=n_ranks)
+    assert load.max() <= 1.5 * load.mean() + 1
+
+
+@pytest.mark.parametrize("n_ranks", [2, 3])
+def test_shard_columns_partition_the_full_index(n_ranks):
+    """The shards' entry columns are exactly the full index's, target by target
+    (same order, same visit ranks): a target's entries are never split."""
+    cfg, (recs, runs, offs, lens, names) = _small_world()
+    recs = recs.copy()
+    recs["query_id"][:5] = recs["target_id"][:5]  # self alignments: no reversed entry
+    n_seqs = len(lens)
+    full = ix.host_columns(recs, offs, n_seqs)
+    owner = ix.assign_owners(recs, offs, n_seqs, n_ranks)
+    seen = 0
+    for r in range(n_ranks):
+        part = ix.host_columns(recs, offs, n_seqs, owner=owner, rank=r)
+        for s in range(n_seqs):
+            a, b = int(part["tgt_off"][s]), int(part["tgt_off"][s + 1])
+            fa, fb = int(full["tgt_off"][s]), int(full["tgt_off"][s + 1])
+            if owner[s] != r:
+                assert a == b
+                continue
+            assert b - a == fb - fa
+            for k in ("e_start", "e_end", "e_pmax", "e_vrank", "e_query_id", "e_flags", "e_aln"):
+                assert (part[k][a:b] == full[k][fa:fb]).all(), (r, s, k)
+            seen += b - a
+        # a shard built from only the alignments it needs (relative order kept) is identical
+        keep = ix.shard_records(recs, offs, owner, r)
+        sub_offs = np.zeros(len(keep) + 1, np.uint64)
+        np.cumsum(np.diff(offs.astype(np.int64))[keep], out=sub_offs[1:])
+        sub = ix.host_columns(recs[keep], sub_offs, n_seqs, owner=owner, rank=r)
+        for k in ("e_start", "e_end", "e_pmax", "e_vrank", "e_query_id", "e_flags"):
+            assert (sub[k] == part[k]).all(), (r, k)
+    assert seen == len(full["e_start"])
+
+
+def test_merge_shard_columns_orders_by_row_then_sequence():
+    rng = np.random.default_rng(0)
+    n_rows, n_seqs, n_ranks = 7, 10, 3
+    owner = rng.integers(0, n_ranks, n_seqs)
+    rows = np.sort(rng.integers(0, n_rows, 200))
+    q = rng.integers(0, n_seqs, 200)
+    order = np.lexsort((q, rows))
+    rows, q = rows[order], q[order]
+    first = np.arange(200, dtype=np.int32)  # position in the full output: must come back as 0..199
+    parts = []
+    for r in range(n_ranks):
+        m = owner[q] == r
+        ro = np.zeros(n_rows + 1, np.uint64)
+        np.cumsum(np.bincount(rows[m], minlength=n_rows), out=ro[1:])
+        parts.append({"row_offsets": ro, "q_id": q[m].astype(np.uint32), "q_first": first[m], "q_last": first[m],
+                      "t_id": q[m].astype(np.uint32), "t_first": first[m], "t_last": first[m]})
+    out = ix.merge_shard_columns(parts)
+    assert out["q_first"].tolist() == list(range(200))
+    assert out["row_offsets"].tolist() == np.concatenate([[0], np.cumsum(np.bincount(rows, minlength=n_rows))]).tolist()
+
+
+def test_local_comm_group_without_gpu():
+    comms = ix.Comm.local_group(3)
+    assert [c.rank for c in comms] == [0, 1, 2] and all(c.size == 3 for c in comms)
+    assert comms[1].traffic() == {"bytes_sent": 0, "bytes_received": 0, "exchanges": 0}
+    with pytest.raises(ix.ImpgxError):
+        ix.Comm.local_group(0)
