@@ -168,6 +168,110 @@ def cpu_reference_time(O, orc, bed, name, budget_s, threads):
     return n / t, n, t, nres
 
 
+def run_shard_only(args, ix, torch, dist, name, rank, local_rank, world, config):
+    """N > 1, index sharded by target sequence, no replica anywhere: rank r generates and
+    uploads only the alignments its sequences walk; the batch of world x rows BED rows is one
+    collective call per step."""
+    from impg_b200 import dist as D
+
+    g, c, L, a, eq, rev, seed, rows = WORKLOADS[name]
+    cfg = ix.synth_cfg(g, c, L, a, eq, rev, seed)
+    t0 = time.time()
+    recs, runs, offs, lens, names, owner = ix.synth_generate_shard(cfg, world, rank)
+    gen_s = time.time() - t0
+    t0 = time.time()
+    shard = ix.Impg.from_records_shard(recs, runs, offs, lens, owner, rank, world, device=local_rank)
+    build_s = time.time() - t0
+    del runs
+    comm = D.nccl_comm(rank, world, local_rank)
+    p = mode_params(ix, name)
+    gbed = np.concatenate([ix.synth_bed(cfg, rows, seed=D.rank_seed(2, r)) for r in range(world)])
+    bed_bytes = torch.from_numpy(gbed.view(np.uint8).copy())
+    d_bed = bed_bytes.cuda()
+    h_bed_np = np.frombuffer(bed_bytes.pin_memory().numpy(), dtype=ix.RANGE_DTYPE)
+    stream = torch.cuda.current_stream()
+    n = len(gbed)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    for _ in range(max(args.warmup, 3)):
+        shard.query_batch_bed_sharded_device(comm, d_bed.data_ptr(), n, p, stream.cuda_stream)
+    shard.query_batch_bed_sharded(comm, h_bed_np, p)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    tr0 = comm.traffic()
+    acc = {k: 0 for k in ("kernel_launches", "lift_bytes", "liftovers", "lift_launches", "lift_touched_bytes",
+                          "lift_window_runs", "lift_ms", "stab_ms", "fold_ms", "merge_ms")}
+    merged = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        r = shard.query_batch_bed_sharded_device(comm, d_bed.data_ptr(), n, p, stream.cuda_stream)
+        st = shard.stats()
+        for k in acc:
+            acc[k] += st[k]
+        merged = st["merged"]
+        del r
+    e1.record(stream)
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+    tr1 = comm.traffic()
+    h2d = d2h = 0
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = shard.query_batch_bed_sharded(comm, h_bed_np, p)
+        st = shard.stats()
+        h2d += st["h2d_bytes"]; d2h += st["d2h_bytes"]
+        del r
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - w0) * 1e3
+    barrier()
+    if rank == 0:
+        sampler.stop()
+    dev_ms, e2e_ms = D.max_over_ranks([dev_ms, e2e_ms], device="cuda")
+    merged_total = D.gather_row_counts(merged, device="cuda")
+    lift_total = D.gather_row_counts(acc["liftovers"], device="cuda")
+    sent_total = D.gather_row_counts(tr1["bytes_sent"] - tr0["bytes_sent"], device="cuda")
+    bytes_max = D.max_over_ranks([float(shard.device_bytes)], device="cuda")[0]
+    if rank != 0:
+        dist.destroy_process_group()
+        return 0
+    peak, peak_src = peaks()
+    lift_ms = acc["lift_ms"]
+    achieved = (acc["lift_bytes"] / 1e9) / (lift_ms / 1e3) if lift_ms > 0 else 0.0
+    config["parallelism"] = (f"index sharded by target sequence over {world} GPUs (no replica), one collective batch of "
+                             f"{world} x {rows} rows per step, NCCL hit / frontier exchange between hops")
+    line = {"metric": METRIC, "value": n * args.steps / (dev_ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
+            "e2e": {"value": n * args.steps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps,
+                    "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": e2e_ms / args.steps,
+                    "note": "bytes of rank 0; every rank copies the rows in and its own share of the BED rows out"},
+            "gpu_launches": int(acc["kernel_launches"]),
+            "roofline": {"kernel": "k_liftover_ends", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "rank": 0,
+                         "algorithmic_bytes_per_launch": acc["lift_bytes"] / max(1, acc["lift_launches"]),
+                         "r_ov_mean": acc["lift_window_runs"] / max(1, acc["liftovers"]),
+                         "avg_launch_ms": lift_ms / max(1, acc["lift_launches"]),
+                         "liftovers_per_step_all_ranks": lift_total // args.steps,
+                         "step_share": {"liftover_ms": lift_ms / args.steps, "stab_ms": acc["stab_ms"] / args.steps,
+                                        "fold_ms": acc["fold_ms"] / args.steps, "merge_ms": acc["merge_ms"] / args.steps,
+                                        "step_ms": dev_ms / args.steps}},
+            "cpu_baseline": None, "clocks": sampler.summary(), "bed_rows_out_per_step": int(merged_total),
+            "target_sharded": {"n_shards": world, "transport": "nccl", "rows_per_step": n,
+                               "exchange_bytes_per_step": int(sent_total) // args.steps,
+                               "exchanges_per_step": (tr1["exchanges"] - tr0["exchanges"]) // args.steps,
+                               "shard_device_bytes_max": int(bytes_max)},
+            "setup": {"generate_s": gen_s, "index_build_s": build_s, "index_device_bytes": shard.device_bytes}}
+    print(json.dumps(line))
+    dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -181,6 +285,9 @@ def main():
                     choices=["rows", "targets"], help="which multi-GPU layout is the headline value at N > 1")
     ap.add_argument("--virtual-shards", type=int, default=int(os.environ.get("IMPGX_BENCH_VIRTUAL_SHARDS", "0")),
                     help="N = 1 only: also time the target-sharded path with this many virtual ranks on the one GPU")
+    ap.add_argument("--shard-only", action="store_true",
+                    help="N > 1: skip the replica leg; every rank generates and holds only its shard (for indexes "
+                         "whose full copy per rank would not fit the host, e.g. c4 on 8 GPUs)")
     ap.add_argument("--profile", action="store_true",
                     help="for ncu: exactly --warmup + --steps device-resident steps, no e2e / cpu legs")
     args = ap.parse_args()
@@ -239,6 +346,9 @@ def main():
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    if args.shard_only and world > 1:
+        return run_shard_only(args, ix, torch, dist, name, rank, local_rank, world, config)
 
     cfg, recs, runs, offs, lens, names, bed, gen_s = gen_workload(ix, name, rank)
     t0 = time.time()

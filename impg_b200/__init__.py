@@ -592,6 +592,29 @@ def synth_generate(cfg):
     return recs, runs[: int(offs[-1])], offs, lens, names
 
 
+def synth_generate_shard(cfg, n_ranks, rank, bidirectional=True):
+    """The part of gen_synth shard `rank` of `n_ranks` needs: records of every alignment are
+    generated (cheap) to derive the owner map, runs only for the alignments that have an entry
+    on an owned sequence. Returns (records, runs, run_offsets, seq_lens, names, owner)."""
+    L = lib()
+    n = L.impgx_synth_num_alignments(C.byref(cfg))
+    recs = np.zeros(n, dtype=RECORD_DTYPE)
+    nr = np.zeros(n, dtype=np.uint32)
+    _check(L.impgx_synth_records(C.byref(cfg), C.c_uint64(0), C.c_uint64(n), _p(recs), _p(nr)))
+    offs = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(nr, out=offs[1:], dtype=np.uint64)
+    n_seqs = cfg.genomes * cfg.contigs
+    owner = assign_owners(recs, offs, n_seqs, n_ranks, bidirectional)
+    keep = shard_records(recs, offs, owner, rank, bidirectional).astype(np.uint64)
+    sub_offs = np.zeros(len(keep) + 1, dtype=np.uint64)
+    np.cumsum(nr[keep], out=sub_offs[1:], dtype=np.uint64)
+    runs = np.zeros(max(int(sub_offs[-1]), 1), dtype=np.uint32)
+    _check(L.impgx_synth_runs_subset(C.byref(cfg), _p(keep), C.c_uint64(len(keep)), _p(sub_offs), _p(runs)))
+    lens = np.full(n_seqs, cfg.contig_len, dtype=np.uint64)
+    names = [f"g{g}#1#c{c}" for g in range(cfg.genomes) for c in range(cfg.contigs)]
+    return recs[keep], runs[: int(sub_offs[-1])], sub_offs, lens, names, owner
+
+
 def synth_bed(cfg, n_rows, seed=2, min_len=1000, max_len=10000):
     out = np.zeros(n_rows, dtype=RANGE_DTYPE)
     _check(lib().impgx_synth_bed(C.byref(cfg), C.c_uint64(seed), C.c_uint64(n_rows), C.c_uint32(min_len),

@@ -676,6 +676,15 @@ int impgx_synth_runs(const impgx_synth_cfg *c, uint64_t first, uint64_t count, c
     synth_alignment(*c, first + (uint64_t)i, nullptr, runs + (run_offsets[i] - run_offsets[0]));
   API_END
 }
+// runs of the alignments ids[0..count) only (a shard generates just what it walks)
+int impgx_synth_runs_subset(const impgx_synth_cfg *c, const uint64_t *ids, uint64_t count, const uint64_t *run_offsets,
+                            uint32_t *runs) {
+  API_BEGIN
+  REQUIRE(c && ids && run_offsets && runs, IMPGX_E_INVALID, "NULL argument");
+#pragma omp parallel for schedule(static)
+  for (long long i = 0; i < (long long)count; i++) synth_alignment(*c, ids[i], nullptr, runs + run_offsets[i]);
+  API_END
+}
 int impgx_synth_bed(const impgx_synth_cfg *c, uint64_t seed, uint64_t n_rows, uint32_t min_len, uint32_t max_len,
                     impgx_range *out) {
   API_BEGIN

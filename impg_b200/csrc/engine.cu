@@ -427,10 +427,11 @@ class Runner {
   void stage_a(const BoxD *boxes, uint64_t nB, uint64_t nv, DBuf<BoxD> &acc, DBuf<uint64_t> &is_root);
   void stage_b(const BoxD *acc, const uint64_t *is_root, uint64_t n, unsigned long long *d_root_counter,
                uint32_t n_rows, BatchOut &out, uint32_t *row_cnt);
+  bool merge_fused(const BoxD *boxes, uint64_t nB, uint64_t nv, BatchOut &out, uint32_t *row_cnt);
+  void route_boxes(const BoxD *boxes, uint64_t nB, DBuf<BoxD> &recv, uint64_t &n_recv);
   void route_hits(const Lifted &L, const uint32_t *gmap, LevelHits &lvl);
   void global_frontier(DBuf<Frontier> &fr, uint64_t &nF, DBuf<uint32_t> &gmap, uint64_t total,
                        const std::vector<uint64_t> &cnt);
-  void route_roots(DBuf<BoxD> &acc, DBuf<uint64_t> &is_root, uint64_t nv, DBuf<BoxD> &recv, uint64_t &n_recv);
   void stab_and_lift(const DBuf<Frontier> &fr, uint64_t nF, bool closed, bool clip, BedSink *sink, LevelHits &lvl);
   void bed_merge_direct(BedSink &sink, uint32_t n_rows, BatchOut &out);
   void fold(const LevelHits &lvl, uint32_t n_rows, Visited &V, DBuf<Frontier> &next, uint64_t &n_next,
@@ -1138,6 +1139,74 @@ void Runner::stage_b(const BoxD *acc, const uint64_t *is_root, uint64_t n, unsig
          row_cnt);
 }
 
+// Both stages on chip, one (row, q) segment per warp / CTA (merge_kernels.cuh,
+// k_merge_segments). Returns false (nothing written) when a segment exceeds
+// SEG_MAX boxes: the caller then runs the global two-sort path.
+bool Runner::merge_fused(const BoxD *boxes, uint64_t nB, uint64_t nv, BatchOut &out, uint32_t *row_cnt) {
+  if (nv == 0) return true;
+  const int seq_bits = bits_for(ix_.n_seqs > 1 ? ix_.n_seqs - 1 : 1);
+  DBuf<BoxD> swept(nv, ar_);
+  DBuf<uint32_t> cnt;
+  Groups g;
+  {
+    DBuf<uint64_t> ka(nB, ar_);
+    DBuf<uint32_t> perm(nB, ar_);
+    LAUNCH(k_bd_key_a, grid_threads(nB), 256, s_, boxes, nB, seq_bits, 1ull << bits_a_, ka.get(), perm.get());
+    sort_pairs(ka, perm, nB, 0, bits_a_ + 1, sc_, s_, ctx);
+    // segments = runs of equal (row, q)
+    {
+      DBuf<uint64_t> head(nv + 1, ar_), scan(nv + 1, ar_);
+      CUDA_CHECK(cudaMemsetAsync(head.get() + nv, 0, 8, s_));
+      LAUNCH(k_heads_u64_shift, grid_threads(nv), 256, s_, ka.get(), nv, seq_bits + 1, head.get());
+      CUDA_CHECK(cudaMemcpyAsync(scan.get(), head.get(), (nv + 1) * 8, cudaMemcpyDeviceToDevice, s_));
+      exclusive_scan_u64(scan.get(), nv + 1, sc_, s_);
+      ctx.launches += 2;
+      g.G = read_u64(scan.get() + nv, s_, ctx);
+      g.begins.alloc(g.G + 1, ar_);
+      LAUNCH(k_group_begins, grid_threads(nv), 256, s_, head.get(), scan.get(), nv, g.begins.get());
+      uint32_t n32 = (uint32_t)nv;
+      CUDA_CHECK(cudaMemcpyAsync(g.begins.get() + g.G, &n32, 4, cudaMemcpyHostToDevice, s_));
+      CUDA_CHECK(cudaStreamSynchronize(s_));
+    }
+    DBuf<uint32_t> lists((uint64_t)SEG_CLASSES * g.G, ar_);
+    DBuf<unsigned int> cls(SEG_CLASSES + 1, ar_);
+    CUDA_CHECK(cudaMemsetAsync(cls.get(), 0, (SEG_CLASSES + 1) * 4, s_));
+    LAUNCH(k_seg_classify, grid_threads(g.G), 256, s_, g.begins.get(), g.G, lists.get(), cls.get());
+    unsigned int hc[SEG_CLASSES + 1];
+    CUDA_CHECK(cudaMemcpyAsync(hc, cls.get(), sizeof(hc), cudaMemcpyDeviceToHost, s_));
+    CUDA_CHECK(cudaStreamSynchronize(s_));
+    ctx.d2h_bytes += sizeof(hc);
+    if (hc[SEG_CLASSES] != 0) return false;
+    cnt.alloc(g.G, ar_);
+    const int64_t d = p_.merge_distance;
+    const int ms = p_.merge_strands ? 1 : 0;
+    auto launch = [&](auto kern, unsigned threads, size_t smem, unsigned per_sm, unsigned seg_per_cta, int c) {
+      if (!hc[c]) return;
+      CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const unsigned grid =
+          (unsigned)std::min<uint64_t>(((uint64_t)hc[c] + seg_per_cta - 1) / seg_per_cta, (uint64_t)sm_count() * per_sm);
+      kern<<<grid, threads, smem, s_>>>(boxes, perm.get(), g.begins.get(), lists.get() + (uint64_t)c * g.G, hc[c], d, ms,
+                                        swept.get(), cnt.get());
+      CUDA_CHECK(cudaGetLastError());
+      ctx.launches++;
+    };
+    launch(k_merge_segments<32, seg_cap(0)>, 256, (size_t)8 * seg_cap(0) * 32, 3, 8, 0);
+    launch(k_merge_segments<128, seg_cap(1)>, 128, (size_t)seg_cap(1) * 32, 6, 1, 1);
+    launch(k_merge_segments<512, seg_cap(2)>, 512, (size_t)seg_cap(2) * 32, 1, 1, 2);
+  }
+  DBuf<uint64_t> scan(g.G + 1, ar_);
+  CUDA_CHECK(cudaMemsetAsync(scan.get() + g.G, 0, 8, s_));
+  LAUNCH(k_u32_to_u64, grid_threads(g.G), 256, s_, cnt.get(), g.G, scan.get());
+  exclusive_scan_u64(scan.get(), g.G + 1, sc_, s_);
+  ctx.launches += 2;
+  const uint64_t M = read_u64(scan.get() + g.G, s_, ctx);
+  OutCols oc = alloc_out_cols(out, M);
+  LAUNCH(k_sweep_compact_direct, grid_threads(g.G), 256, s_, swept.get(), g.begins.get(), cnt.get(), scan.get(), g.G, oc,
+         row_cnt);
+  CUDA_CHECK(cudaStreamSynchronize(s_));  // `swept` and the lists are released on return
+  return true;
+}
+
 OutCols Runner::alloc_out_cols(BatchOut &out, uint64_t n) {
   OutCols oc;
   oc.cig_len = nullptr; oc.src_entry = nullptr; oc.src_slice = nullptr;
@@ -1196,16 +1265,24 @@ void Runner::bed_merge_direct(BedSink &sink, uint32_t n_rows, BatchOut &out) {
   } else if (nv > 0 || comm_) {
     REQUIRE(bits_a_ <= 63 && bits_b_ <= 63, IMPGX_E_INVALID,
             "batch too large for the packed merge keys; lower IMPGX_ROWS_PER_BATCH");
-    DBuf<BoxD> acc;
-    DBuf<uint64_t> is_root;
-    stage_a(sink.boxes.get(), nB, nv, acc, is_root);
+    // sharded index: every valid box travels to the owner of its query sequence first,
+    // so that a (row, q) segment is complete on one rank
+    const BoxD *bx = sink.boxes.get();
+    uint64_t n_in = nB, n_valid = nv;
+    DBuf<BoxD> recv;
     if (comm_) {
-      DBuf<BoxD> recv;
       uint64_t n_recv = 0;
-      route_roots(acc, is_root, nv, recv, n_recv);
-      stage_b(recv.get(), nullptr, n_recv, sink.counters.get() + 1, n_rows, out, row_cnt.get());
-    } else {
-      stage_b(acc.get(), is_root.get(), nv, sink.counters.get() + 1, n_rows, out, row_cnt.get());
+      route_boxes(sink.boxes.get(), nB, recv, n_recv);
+      sink.boxes.release();
+      bx = recv.get();
+      n_in = n_valid = n_recv;
+      REQUIRE(n_in < (1ull << 32), IMPGX_E_INVALID, "more than 2^32 results in one batch; lower IMPGX_ROWS_PER_BATCH");
+    }
+    if (n_valid > 0 && (getenv("IMPGX_MERGE_GLOBAL") || !merge_fused(bx, n_in, n_valid, out, row_cnt.get()))) {
+      DBuf<BoxD> acc;
+      DBuf<uint64_t> is_root;
+      stage_a(bx, n_in, n_valid, acc, is_root);
+      stage_b(acc.get(), is_root.get(), n_valid, sink.counters.get() + 1, n_rows, out, row_cnt.get());
     }
   }
   LAUNCH(k_u32_to_u64, grid_threads(n_rows), 256, s_, row_cnt.get(), n_rows, out.row_off.get());
@@ -1224,7 +1301,7 @@ void Runner::bed_merge_direct(BedSink &sink, uint32_t n_rows, BatchOut &out) {
 // Partition `n` records by destination rank (dest[i] in [0, N], N = "nowhere")
 // and exchange them: returns the received records, grouped by source rank.
 template <class T>
-static void exchange_by_dest(Comm &cm, DBuf<T> &recs, DBuf<uint32_t> &dest, DBuf<uint32_t> &idx,
+static void exchange_by_dest(Comm &cm, const T *recs, DBuf<uint32_t> &dest, DBuf<uint32_t> &idx,
                              const unsigned long long *d_dest_cnt, uint64_t n, DBuf<T> &recv, uint64_t &n_recv,
                              Arena &ar, Scratch &sc, cudaStream_t s, Ctx &ctx) {
   const int N = cm.size();
@@ -1250,7 +1327,7 @@ static void exchange_by_dest(Comm &cm, DBuf<T> &recs, DBuf<uint32_t> &dest, DBuf
   if (n) {
     sort_pairs(dest, idx, n, 0, bits_for((uint64_t)N), sc, s, ctx);  // stable: source order kept per destination
     if (so) {
-      k_gather<T><<<grid_threads(so), 256, 0, s>>>(recs.get(), idx.get(), so, send.get());
+      k_gather<T><<<grid_threads(so), 256, 0, s>>>(recs, idx.get(), so, send.get());
       CUDA_CHECK(cudaGetLastError());
       ctx.launches++;
     }
@@ -1274,7 +1351,7 @@ void Runner::route_hits(const Lifted &L, const uint32_t *gmap, LevelHits &lvl) {
     LAUNCH(k_route_hits, grid_threads(H), 256, s_, L.hits.get(), L.tasks.get(), L.d_orig, gmap, idx_->d_owner, H, N,
            routed.get(), dest.get(), idx.get(), dcnt.get());
   uint64_t n_recv = 0;
-  exchange_by_dest(cm, routed, dest, idx, dcnt.get(), H, recv, n_recv, ar_, sc_, s_, ctx);
+  exchange_by_dest(cm, (const RoutedHit *)routed.get(), dest, idx, dcnt.get(), H, recv, n_recv, ar_, sc_, s_, ctx);
   lvl.n = n_recv;
   if (n_recv == 0) return;
   lvl.hits.alloc(n_recv, ar_);
@@ -1322,17 +1399,16 @@ void Runner::global_frontier(DBuf<Frontier> &fr, uint64_t &nF, DBuf<uint32_t> &g
   gmap = std::move(g2);
 }
 
-// Stage-A roots travel to the owner of their query sequence.
-void Runner::route_roots(DBuf<BoxD> &acc, DBuf<uint64_t> &is_root, uint64_t nv, DBuf<BoxD> &recv, uint64_t &n_recv) {
+// Valid boxes travel to the owner of their query sequence (both BED merges group by (row, q)).
+void Runner::route_boxes(const BoxD *boxes, uint64_t nB, DBuf<BoxD> &recv, uint64_t &n_recv) {
   Comm &cm = *comm_;
   const uint32_t N = (uint32_t)cm.size();
   DBuf<unsigned long long> dcnt(N + 1, ar_);
   CUDA_CHECK(cudaMemsetAsync(dcnt.get(), 0, (N + 1) * 8, s_));
-  DBuf<uint32_t> dest(nv, ar_), idx(nv, ar_);
-  if (nv)
-    LAUNCH(k_root_dest, grid_threads(nv), 256, s_, acc.get(), is_root.get(), nv, idx_->d_owner, N, dest.get(), idx.get(),
-           dcnt.get());
-  exchange_by_dest(cm, acc, dest, idx, dcnt.get(), nv, recv, n_recv, ar_, sc_, s_, ctx);
+  DBuf<uint32_t> dest(nB, ar_), idx(nB, ar_);
+  if (nB)
+    LAUNCH(k_box_dest, grid_threads(nB), 256, s_, boxes, nB, idx_->d_owner, N, dest.get(), idx.get(), dcnt.get());
+  exchange_by_dest(cm, boxes, dest, idx, dcnt.get(), nB, recv, n_recv, ar_, sc_, s_, ctx);
 }
 
 void Runner::run_sharded(const impgx_range *d_ranges, uint32_t n_rows, BatchOut &out) {

@@ -267,7 +267,7 @@ __global__ void k_boxes_to_cols(const Box *__restrict__ b, uint64_t n, OutCols o
 // as the reference's stable sorts would.
 namespace impgx {
 
-struct __align__(8) BoxD {
+struct __align__(16) BoxD {
   int32_t q_lo, q_hi, t_lo, t_hi;
   uint32_t q_id, t_id, row, valid;
   uint64_t ord;  // position in the reference's result order of the row: level << 58 | (range << 32 | vrank) or index
@@ -539,3 +539,209 @@ __global__ void k_boxd_to_cols(const BoxD *__restrict__ b, const uint32_t *__res
 
 }  // namespace impgx
 
+
+// ===================================================================
+// Fused BED merge: after ONE global sort of the boxes by (row, q, t, strand)
+// every (row, q) segment is merged on chip — stage A (pairwise union-find per
+// (t, strand) group, contiguous inside the segment), then stage B (sort of the
+// merged boxes by (start, strand, ord) in shared memory + the literal sweep).
+// A box is read from HBM once. One warp per small segment, one CTA per larger
+// one; a batch with a segment beyond SEG_MAX falls back to the global path.
+namespace impgx {
+
+constexpr int SEG_CLASSES = 3;
+// boxes per segment (powers of two: the sort pads to one): warp, 128-thread CTA, 512-thread CTA
+__host__ __device__ constexpr int seg_cap(int c) { return c == 0 ? 256 : (c == 1 ? 1024 : 4096); }
+constexpr int SEG_MAX = seg_cap(SEG_CLASSES - 1);
+
+__global__ void k_heads_u64_shift(const uint64_t *__restrict__ keys, uint64_t n, int shift, uint64_t *__restrict__ head) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) head[i] = (i == 0 || (keys[i - 1] >> shift) != (keys[i] >> shift)) ? 1 : 0;
+}
+
+// segment -> size class list; cls[c] = segments of class c, cls[SEG_CLASSES] = segments too large
+__global__ void k_seg_classify(const uint32_t *__restrict__ begins, uint64_t n_seg, uint32_t *__restrict__ lists,
+                               unsigned int *__restrict__ cls) {
+  for (uint64_t g = gtid(); g < n_seg; g += gstride()) {
+    const uint32_t n = begins[g + 1] - begins[g];
+    int c = 0;
+    while (c < SEG_CLASSES && n > (uint32_t)seg_cap(c)) c++;
+    const unsigned int k = atomicAdd(&cls[c], 1u);
+    if (c < SEG_CLASSES) lists[(uint64_t)c * n_seg + k] = (uint32_t)g;
+  }
+}
+
+__device__ __forceinline__ uint16_t seg_find(uint16_t *p, uint16_t x) {
+  while (p[x] != x) {
+    p[x] = p[p[x]];
+    x = p[x];
+  }
+  return x;
+}
+
+template <int T, int CAP>
+__global__ void __launch_bounds__(T == 32 ? 256 : T)
+    k_merge_segments(const BoxD *__restrict__ boxes, const uint32_t *__restrict__ idx, const uint32_t *__restrict__ begins,
+                     const uint32_t *__restrict__ list, uint32_t n_list, int64_t d, int merge_strands,
+                     BoxD *__restrict__ swept, uint32_t *__restrict__ out_cnt) {
+  extern __shared__ __align__(16) unsigned char seg_smem[];
+  constexpr int GROUPS = (T == 32) ? 8 : 1;  // segments in flight per CTA
+  const int gi = (T == 32) ? (int)(threadIdx.x >> 5) : 0;
+  const int lt = (T == 32) ? (int)(threadIdx.x & 31u) : (int)threadIdx.x;
+  unsigned char *base = seg_smem + (size_t)gi * CAP * 32;
+  uint64_t *ord = reinterpret_cast<uint64_t *>(base);
+  int32_t *qlo = reinterpret_cast<int32_t *>(ord + CAP);
+  int32_t *qhi = qlo + CAP, *tlo = qhi + CAP, *thi = tlo + CAP;
+  uint32_t *tid = reinterpret_cast<uint32_t *>(thi + CAP);
+  uint16_t *perm = reinterpret_cast<uint16_t *>(tid + CAP);
+  uint16_t *parent = perm + CAP;
+  __shared__ unsigned int s_nroots[GROUPS];
+  auto sync = [&]() {
+    if (T == 32) __syncwarp();
+    else __syncthreads();
+  };
+  const int32_t md = (int32_t)d;
+
+  for (uint32_t li = blockIdx.x * GROUPS + gi; li < n_list; li += gridDim.x * GROUPS) {
+    const uint32_t g = list[li];
+    const uint32_t b = begins[g], n = begins[g + 1] - b;
+    const BoxD first = boxes[idx[b]];
+    if (n == 1) {
+      if (lt == 0) {
+        swept[b] = first;
+        out_cnt[g] = 1;
+      }
+      continue;
+    }
+    for (uint32_t i = lt; i < n; i += T) {
+      const BoxD x = boxes[idx[b + i]];
+      ord[i] = x.ord;
+      qlo[i] = x.q_lo; qhi[i] = x.q_hi; tlo[i] = x.t_lo; thi[i] = x.t_hi;
+      tid[i] = x.t_id;
+      parent[i] = (uint16_t)i;
+    }
+    if (lt == 0) s_nroots[gi] = 0;
+    sync();
+    // ---- stage A: one thread per (t, strand) group (contiguous: the global sort key ends with t, strand)
+    if (d >= 0) {
+      for (uint32_t i = lt; i < n; i += T) {
+        const uint32_t t = tid[i];
+        const bool fwd = qlo[i] <= qhi[i];
+        if (i > 0 && tid[i - 1] == t && (qlo[i - 1] <= qhi[i - 1]) == fwd) continue;  // not a group head
+        uint32_t e = i + 1;
+        while (e < n && tid[e] == t && (qlo[e] <= qhi[e]) == fwd) e++;
+        if (e - i == 1) continue;
+        // pairwise relation of src/main.rs:12895-12946 on the ORIGINAL coordinates
+        // (see k_merge2d_direct); `a` is the member with the smaller (sort key, ord)
+        for (uint32_t x = i; x < e; x++) {
+          const int64_t kx = fwd ? (int64_t)qlo[x] : -(int64_t)qlo[x];
+          for (uint32_t y = x + 1; y < e; y++) {
+            const int64_t ky = fwd ? (int64_t)qlo[y] : -(int64_t)qlo[y];
+            const bool x_first = kx < ky || (kx == ky && ord[x] < ord[y]);
+            const uint32_t A = x_first ? x : y, B = x_first ? y : x;
+            const int64_t qa_start = fwd ? qlo[A] : qhi[A], qa_end = fwd ? qhi[A] : qlo[A];
+            const int64_t qb_start = fwd ? qlo[B] : qhi[B];
+            if (qb_start < qa_start) continue;
+            if (qb_start - qa_end > d) continue;
+            int64_t t_gap;
+            bool t_forward;
+            if (fwd) {
+              t_gap = (int64_t)tlo[B] - thi[A];
+              t_forward = tlo[B] > tlo[A];
+            } else {
+              t_gap = (int64_t)tlo[A] - thi[B];
+              t_forward = thi[B] < thi[A];
+            }
+            if (!t_forward || t_gap > d) continue;
+            const uint16_t ra = seg_find(parent, (uint16_t)x), rb = seg_find(parent, (uint16_t)y);
+            if (ra != rb) parent[ra] = rb;
+          }
+        }
+        // merged box of a component = min/max over its members (+ the earliest ord),
+        // accumulated into the root's slot; non-root slots keep their original values
+        for (uint32_t x = i; x < e; x++) {
+          const uint16_t r = seg_find(parent, (uint16_t)x);
+          if (r == x) continue;
+          if (fwd) {
+            qlo[r] = min(qlo[r], qlo[x]);
+            qhi[r] = max(qhi[r], qhi[x]);
+          } else {
+            qlo[r] = max(qlo[r], qlo[x]);
+            qhi[r] = min(qhi[r], qhi[x]);
+          }
+          tlo[r] = min(tlo[r], tlo[x]);
+          thi[r] = max(thi[r], thi[x]);
+          ord[r] = min(ord[r], ord[x]);
+        }
+      }
+      sync();
+    }
+    // ---- roots of the segment (any order: they are sorted next)
+    for (uint32_t i = lt; i < n; i += T)
+      if (parent[i] == i) perm[atomicAdd(&s_nroots[gi], 1u)] = (uint16_t)i;
+    sync();
+    const uint32_t nr = s_nroots[gi];
+    uint32_t P = 1;
+    while (P < nr) P <<= 1;
+    for (uint32_t i = nr + lt; i < P; i += T) perm[i] = 0xffffu;
+    sync();
+    // ---- stage B order: (start, !forward, ord) — src/main.rs:12481-12494; ord restores the stable sort's ties
+    auto less_b = [&](uint16_t x, uint16_t y) -> bool {
+      if (x == 0xffffu) return false;
+      if (y == 0xffffu) return true;
+      const bool fx = qlo[x] <= qhi[x], fy = qlo[y] <= qhi[y];
+      const uint32_t sx = (uint32_t)(fx ? qlo[x] : qhi[x]), sy = (uint32_t)(fy ? qlo[y] : qhi[y]);
+      if (sx != sy) return sx < sy;
+      if (fx != fy) return fx;
+      return ord[x] < ord[y];
+    };
+    for (uint32_t k = 2; k <= P; k <<= 1) {
+      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+        for (uint32_t i = lt; i < P; i += T) {
+          const uint32_t l = i ^ j;
+          if (l > i) {
+            const uint16_t x = perm[i], y = perm[l];
+            const bool up = (i & k) == 0;
+            if (less_b(y, x) == up) {
+              perm[i] = y;
+              perm[l] = x;
+            }
+          }
+        }
+        sync();
+      }
+    }
+    // ---- the literal sweep of src/main.rs:12496-12556
+    if (lt == 0) {
+      uint32_t w = 0;
+      uint16_t c = perm[0];
+      int32_t c_lo = qlo[c], c_hi = qhi[c];
+      for (uint32_t rd = 1; rd < nr; rd++) {
+        const uint16_t x = perm[rd];
+        const int32_t n_lo = qlo[x], n_hi = qhi[x];
+        const bool cf = c_lo <= c_hi, nf = n_lo <= n_hi;
+        const int32_t cs = cf ? c_lo : c_hi, ce = cf ? c_hi : c_lo;
+        const int32_t ns = nf ? n_lo : n_hi, ne = nf ? n_hi : n_lo;
+        if (md < 0 || (!merge_strands && cf != nf) || (int64_t)ns > (int64_t)ce + md) {
+          swept[b + w++] = BoxD{c_lo, c_hi, tlo[c], thi[c], first.q_id, tid[c], first.row, 1u, ord[c]};
+          c = x;
+          c_lo = n_lo;
+          c_hi = n_hi;
+        } else {
+          const int32_t ms = min(cs, ns), me = max(ce, ne);
+          bool mf = cf;
+          if (merge_strands && cf != nf) {
+            const int64_t cl = (int64_t)ce - cs, nl = (int64_t)ne - ns;
+            mf = nl > cl ? nf : cf;
+          }
+          c_lo = mf ? ms : me;
+          c_hi = mf ? me : ms;
+        }
+      }
+      swept[b + w++] = BoxD{c_lo, c_hi, tlo[c], thi[c], first.q_id, tid[c], first.row, 1u, ord[c]};
+      out_cnt[g] = w;
+    }
+    sync();  // the next segment reuses the shared arrays
+  }
+}
+
+}  // namespace impgx

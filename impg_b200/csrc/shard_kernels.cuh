@@ -95,15 +95,15 @@ __global__ void k_frontier_take_owned(const Frontier *__restrict__ f, const uint
     }
 }
 
-// stage-A roots -> destination rank = owner of the query sequence (non-roots sort last)
-__global__ void k_root_dest(const BoxD *__restrict__ acc, const uint64_t *__restrict__ is_root, uint64_t n,
-                            const uint32_t *__restrict__ owner, uint32_t n_ranks, uint32_t *__restrict__ dest,
-                            uint32_t *__restrict__ idx, unsigned long long *__restrict__ dest_cnt) {
+// valid boxes -> destination rank = owner of the query sequence (invalid ones go nowhere)
+__global__ void k_box_dest(const BoxD *__restrict__ boxes, uint64_t n, const uint32_t *__restrict__ owner,
+                           uint32_t n_ranks, uint32_t *__restrict__ dest, uint32_t *__restrict__ idx,
+                           unsigned long long *__restrict__ dest_cnt) {
   __shared__ unsigned int bins[MAX_RANKS + 1];
   for (unsigned k = threadIdx.x; k <= n_ranks; k += blockDim.x) bins[k] = 0;
   __syncthreads();
   for (uint64_t i = gtid(); i < n; i += gstride()) {
-    const uint32_t d = is_root[i] ? owner[acc[i].q_id] : n_ranks;
+    const uint32_t d = boxes[i].valid ? owner[boxes[i].q_id] : n_ranks;
     dest[i] = d;
     idx[i] = (uint32_t)i;
     atomicAdd(&bins[d], 1u);

@@ -241,3 +241,16 @@ def test_local_comm_group_without_gpu():
     assert comms[1].traffic() == {"bytes_sent": 0, "bytes_received": 0, "exchanges": 0}
     with pytest.raises(ix.ImpgxError):
         ix.Comm.local_group(0)
+
+
+def test_synth_generate_shard_matches_the_full_generator():
+    cfg, (recs, runs, offs, lens, names) = _small_world()
+    for r in range(3):
+        sr, sruns, soffs, sl, sn, owner = ix.synth_generate_shard(cfg, 3, r)
+        keep = ix.shard_records(recs, offs, owner, r)
+        assert (sr == recs[keep]).all() and sn == names
+        assert (np.concatenate([runs[int(offs[k]):int(offs[k + 1])] for k in keep]) == sruns).all()
+        a = ix.host_columns(recs, offs, len(lens), owner=owner, rank=r)
+        b = ix.host_columns(sr, soffs, len(lens), owner=owner, rank=r)
+        for k in ("e_start", "e_end", "e_vrank", "e_flags", "e_query_id"):
+            assert (a[k] == b[k]).all()
