@@ -544,15 +544,16 @@ __global__ void k_boxd_to_cols(const BoxD *__restrict__ b, const uint32_t *__res
 // Fused BED merge: after ONE global sort of the boxes by (row, q, t, strand)
 // every (row, q) segment is merged on chip — stage A (pairwise union-find per
 // (t, strand) group, contiguous inside the segment), then stage B (sort of the
-// merged boxes by (start, strand, ord) in shared memory + the literal sweep).
-// A box is read from HBM once. One warp per small segment, one CTA per larger
-// one; a batch with a segment beyond SEG_MAX falls back to the global path.
+// merged boxes by (start, strand, ord) in shared memory + the sweep). A box is
+// read from HBM once. One warp per small segment, one CTA per larger one; a
+// batch with a segment beyond SEG_MAX falls back to the global path.
 namespace impgx {
 
-constexpr int SEG_CLASSES = 3;
-// boxes per segment (powers of two: the sort pads to one): warp, 128-thread CTA, 512-thread CTA
-__host__ __device__ constexpr int seg_cap(int c) { return c == 0 ? 256 : (c == 1 ? 1024 : 4096); }
+constexpr int SEG_CLASSES = 4;
+// boxes per segment (powers of two: the sort pads to one): two warp classes, 128- and 512-thread CTAs
+__host__ __device__ constexpr int seg_cap(int c) { return c == 0 ? 128 : (c == 1 ? 256 : (c == 2 ? 1024 : 4096)); }
 constexpr int SEG_MAX = seg_cap(SEG_CLASSES - 1);
+constexpr int SEG_BYTES = 40;  // shared memory per box
 
 __global__ void k_heads_u64_shift(const uint64_t *__restrict__ keys, uint64_t n, int shift, uint64_t *__restrict__ head) {
   for (uint64_t i = gtid(); i < n; i += gstride()) head[i] = (i == 0 || (keys[i - 1] >> shift) != (keys[i] >> shift)) ? 1 : 0;
@@ -578,6 +579,26 @@ __device__ __forceinline__ uint16_t seg_find(uint16_t *p, uint16_t x) {
   return x;
 }
 
+__device__ __forceinline__ int warp_incl_max(int v) {
+  const unsigned lane = lane_id();
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int o = __shfl_up_sync(FULL, v, d);
+    if (lane >= (unsigned)d) v = max(v, o);
+  }
+  return v;
+}
+
+// Shared-memory view of one segment (40 bytes per box).
+struct SegMem {
+  uint64_t *ord;    // reference-order ordinal
+  uint64_t *skey;   // stage-B sort keys, then the sorted (start, end) pairs
+  int32_t *qlo, *qhi, *tlo, *thi;
+  uint32_t *tid;
+  uint16_t *parent; // union-find of stage A, then per sorted position: box index | forward << 15
+  uint16_t *heads;  // group heads with more than one member
+};
+
 template <int T, int CAP>
 __global__ void __launch_bounds__(T == 32 ? 256 : T)
     k_merge_segments(const BoxD *__restrict__ boxes, const uint32_t *__restrict__ idx, const uint32_t *__restrict__ begins,
@@ -587,14 +608,17 @@ __global__ void __launch_bounds__(T == 32 ? 256 : T)
   constexpr int GROUPS = (T == 32) ? 8 : 1;  // segments in flight per CTA
   const int gi = (T == 32) ? (int)(threadIdx.x >> 5) : 0;
   const int lt = (T == 32) ? (int)(threadIdx.x & 31u) : (int)threadIdx.x;
-  unsigned char *base = seg_smem + (size_t)gi * CAP * 32;
-  uint64_t *ord = reinterpret_cast<uint64_t *>(base);
-  int32_t *qlo = reinterpret_cast<int32_t *>(ord + CAP);
-  int32_t *qhi = qlo + CAP, *tlo = qhi + CAP, *thi = tlo + CAP;
-  uint32_t *tid = reinterpret_cast<uint32_t *>(thi + CAP);
-  uint16_t *perm = reinterpret_cast<uint16_t *>(tid + CAP);
-  uint16_t *parent = perm + CAP;
-  __shared__ unsigned int s_nroots[GROUPS];
+  const unsigned lane = threadIdx.x & 31u;
+  unsigned char *base = seg_smem + (size_t)gi * CAP * SEG_BYTES;
+  SegMem m;
+  m.ord = reinterpret_cast<uint64_t *>(base);
+  m.skey = m.ord + CAP;
+  m.qlo = reinterpret_cast<int32_t *>(m.skey + CAP);
+  m.qhi = m.qlo + CAP; m.tlo = m.qhi + CAP; m.thi = m.tlo + CAP;
+  m.tid = reinterpret_cast<uint32_t *>(m.thi + CAP);
+  m.parent = reinterpret_cast<uint16_t *>(m.tid + CAP);
+  m.heads = m.parent + CAP;
+  __shared__ unsigned int s_cnt[GROUPS][2];  // [0] roots, [1] multi-member group heads
   auto sync = [&]() {
     if (T == 32) __syncwarp();
     else __syncthreads();
@@ -614,130 +638,213 @@ __global__ void __launch_bounds__(T == 32 ? 256 : T)
     }
     for (uint32_t i = lt; i < n; i += T) {
       const BoxD x = boxes[idx[b + i]];
-      ord[i] = x.ord;
-      qlo[i] = x.q_lo; qhi[i] = x.q_hi; tlo[i] = x.t_lo; thi[i] = x.t_hi;
-      tid[i] = x.t_id;
-      parent[i] = (uint16_t)i;
+      m.ord[i] = x.ord;
+      m.qlo[i] = x.q_lo; m.qhi[i] = x.q_hi; m.tlo[i] = x.t_lo; m.thi[i] = x.t_hi;
+      m.tid[i] = x.t_id;
+      m.parent[i] = (uint16_t)i;
     }
-    if (lt == 0) s_nroots[gi] = 0;
+    if (lt == 0) s_cnt[gi][0] = s_cnt[gi][1] = 0;
     sync();
-    // ---- stage A: one thread per (t, strand) group (contiguous: the global sort key ends with t, strand)
+    // ---- stage A: (t, strand) groups are contiguous (the global sort key ends with t, strand);
+    // heads of groups with more than one member are listed first so that every thread gets one
     if (d >= 0) {
-      for (uint32_t i = lt; i < n; i += T) {
-        const uint32_t t = tid[i];
-        const bool fwd = qlo[i] <= qhi[i];
-        if (i > 0 && tid[i - 1] == t && (qlo[i - 1] <= qhi[i - 1]) == fwd) continue;  // not a group head
-        uint32_t e = i + 1;
-        while (e < n && tid[e] == t && (qlo[e] <= qhi[e]) == fwd) e++;
-        if (e - i == 1) continue;
+      for (uint32_t i = lt; i + 1 < n; i += T) {
+        const uint32_t t = m.tid[i];
+        const bool fwd = m.qlo[i] <= m.qhi[i];
+        const bool head = i == 0 || m.tid[i - 1] != t || (m.qlo[i - 1] <= m.qhi[i - 1]) != fwd;
+        if (head && m.tid[i + 1] == t && (m.qlo[i + 1] <= m.qhi[i + 1]) == fwd)
+          m.heads[atomicAdd(&s_cnt[gi][1], 1u)] = (uint16_t)i;
+      }
+      sync();
+      const uint32_t nh = s_cnt[gi][1];
+      for (uint32_t h = lt; h < nh; h += T) {
+        const uint32_t i = m.heads[h];
+        const uint32_t t = m.tid[i];
+        const bool fwd = m.qlo[i] <= m.qhi[i];
+        uint32_t e = i + 2;
+        while (e < n && m.tid[e] == t && (m.qlo[e] <= m.qhi[e]) == fwd) e++;
         // pairwise relation of src/main.rs:12895-12946 on the ORIGINAL coordinates
-        // (see k_merge2d_direct); `a` is the member with the smaller (sort key, ord)
+        // (see k_merge2d_direct); `A` is the member with the smaller (sort key, ord)
         for (uint32_t x = i; x < e; x++) {
-          const int64_t kx = fwd ? (int64_t)qlo[x] : -(int64_t)qlo[x];
+          const int64_t kx = fwd ? (int64_t)m.qlo[x] : -(int64_t)m.qlo[x];
           for (uint32_t y = x + 1; y < e; y++) {
-            const int64_t ky = fwd ? (int64_t)qlo[y] : -(int64_t)qlo[y];
-            const bool x_first = kx < ky || (kx == ky && ord[x] < ord[y]);
+            const int64_t ky = fwd ? (int64_t)m.qlo[y] : -(int64_t)m.qlo[y];
+            const bool x_first = kx < ky || (kx == ky && m.ord[x] < m.ord[y]);
             const uint32_t A = x_first ? x : y, B = x_first ? y : x;
-            const int64_t qa_start = fwd ? qlo[A] : qhi[A], qa_end = fwd ? qhi[A] : qlo[A];
-            const int64_t qb_start = fwd ? qlo[B] : qhi[B];
+            const int64_t qa_start = fwd ? m.qlo[A] : m.qhi[A], qa_end = fwd ? m.qhi[A] : m.qlo[A];
+            const int64_t qb_start = fwd ? m.qlo[B] : m.qhi[B];
             if (qb_start < qa_start) continue;
             if (qb_start - qa_end > d) continue;
             int64_t t_gap;
             bool t_forward;
             if (fwd) {
-              t_gap = (int64_t)tlo[B] - thi[A];
-              t_forward = tlo[B] > tlo[A];
+              t_gap = (int64_t)m.tlo[B] - m.thi[A];
+              t_forward = m.tlo[B] > m.tlo[A];
             } else {
-              t_gap = (int64_t)tlo[A] - thi[B];
-              t_forward = thi[B] < thi[A];
+              t_gap = (int64_t)m.tlo[A] - m.thi[B];
+              t_forward = m.thi[B] < m.thi[A];
             }
             if (!t_forward || t_gap > d) continue;
-            const uint16_t ra = seg_find(parent, (uint16_t)x), rb = seg_find(parent, (uint16_t)y);
-            if (ra != rb) parent[ra] = rb;
+            const uint16_t ra = seg_find(m.parent, (uint16_t)x), rb = seg_find(m.parent, (uint16_t)y);
+            if (ra != rb) m.parent[ra] = rb;
           }
         }
-        // merged box of a component = min/max over its members (+ the earliest ord),
-        // accumulated into the root's slot; non-root slots keep their original values
-        for (uint32_t x = i; x < e; x++) {
-          const uint16_t r = seg_find(parent, (uint16_t)x);
+      }
+      sync();
+      // merged box of a component = min/max over its members (+ the earliest ord), accumulated into the
+      // root's slot AFTER every pair was tested on original coordinates; non-root slots stay untouched.
+      // One thread per group again: members of a component are folded in sequence.
+      for (uint32_t h = lt; h < nh; h += T) {
+        const uint32_t i = m.heads[h];
+        const uint32_t t = m.tid[i];
+        const bool fwd = m.qlo[i] <= m.qhi[i];
+        for (uint32_t x = i; x < n && m.tid[x] == t && ((m.qlo[x] <= m.qhi[x]) == fwd); x++) {
+          const uint16_t r = seg_find(m.parent, (uint16_t)x);
           if (r == x) continue;
           if (fwd) {
-            qlo[r] = min(qlo[r], qlo[x]);
-            qhi[r] = max(qhi[r], qhi[x]);
+            m.qlo[r] = min(m.qlo[r], m.qlo[x]);
+            m.qhi[r] = max(m.qhi[r], m.qhi[x]);
           } else {
-            qlo[r] = max(qlo[r], qlo[x]);
-            qhi[r] = min(qhi[r], qhi[x]);
+            m.qlo[r] = max(m.qlo[r], m.qlo[x]);
+            m.qhi[r] = min(m.qhi[r], m.qhi[x]);
           }
-          tlo[r] = min(tlo[r], tlo[x]);
-          thi[r] = max(thi[r], thi[x]);
-          ord[r] = min(ord[r], ord[x]);
+          m.tlo[r] = min(m.tlo[r], m.tlo[x]);
+          m.thi[r] = max(m.thi[r], m.thi[x]);
+          m.ord[r] = min(m.ord[r], m.ord[x]);
         }
       }
       sync();
     }
-    // ---- roots of the segment (any order: they are sorted next)
+    // ---- roots -> stage-B sort keys: (start, !forward, box index); equal (start, strand) are
+    // put into ord order afterwards (src/main.rs:12481-12494 is a stable sort of the input order)
     for (uint32_t i = lt; i < n; i += T)
-      if (parent[i] == i) perm[atomicAdd(&s_nroots[gi], 1u)] = (uint16_t)i;
+      if (m.parent[i] == i) {
+        const bool fwd = m.qlo[i] <= m.qhi[i];
+        const uint32_t st = (uint32_t)(fwd ? m.qlo[i] : m.qhi[i]);
+        m.skey[atomicAdd(&s_cnt[gi][0], 1u)] = ((uint64_t)st << 17) | ((uint64_t)(fwd ? 0u : 1u) << 16) | i;
+      }
     sync();
-    const uint32_t nr = s_nroots[gi];
+    const uint32_t nr = s_cnt[gi][0];
     uint32_t P = 1;
     while (P < nr) P <<= 1;
-    for (uint32_t i = nr + lt; i < P; i += T) perm[i] = 0xffffu;
+    for (uint32_t i = nr + lt; i < P; i += T) m.skey[i] = ~0ull;
     sync();
-    // ---- stage B order: (start, !forward, ord) — src/main.rs:12481-12494; ord restores the stable sort's ties
-    auto less_b = [&](uint16_t x, uint16_t y) -> bool {
-      if (x == 0xffffu) return false;
-      if (y == 0xffffu) return true;
-      const bool fx = qlo[x] <= qhi[x], fy = qlo[y] <= qhi[y];
-      const uint32_t sx = (uint32_t)(fx ? qlo[x] : qhi[x]), sy = (uint32_t)(fy ? qlo[y] : qhi[y]);
-      if (sx != sy) return sx < sy;
-      if (fx != fy) return fx;
-      return ord[x] < ord[y];
-    };
     for (uint32_t k = 2; k <= P; k <<= 1) {
       for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-        for (uint32_t i = lt; i < P; i += T) {
-          const uint32_t l = i ^ j;
-          if (l > i) {
-            const uint16_t x = perm[i], y = perm[l];
-            const bool up = (i & k) == 0;
-            if (less_b(y, x) == up) {
-              perm[i] = y;
-              perm[l] = x;
-            }
+        for (uint32_t i = lt; i < (P >> 1); i += T) {
+          // i-th compare-exchange of this step: lo has bit j clear
+          const uint32_t lo = ((i & ~(j - 1)) << 1) | (i & (j - 1)), hi = lo | j;
+          const uint64_t x = m.skey[lo], y = m.skey[hi];
+          const bool up = (lo & k) == 0;
+          if ((y < x) == up) {
+            m.skey[lo] = y;
+            m.skey[hi] = x;
           }
         }
         sync();
       }
     }
-    // ---- the literal sweep of src/main.rs:12496-12556
-    if (lt == 0) {
-      uint32_t w = 0;
-      uint16_t c = perm[0];
-      int32_t c_lo = qlo[c], c_hi = qhi[c];
-      for (uint32_t rd = 1; rd < nr; rd++) {
-        const uint16_t x = perm[rd];
-        const int32_t n_lo = qlo[x], n_hi = qhi[x];
-        const bool cf = c_lo <= c_hi, nf = n_lo <= n_hi;
-        const int32_t cs = cf ? c_lo : c_hi, ce = cf ? c_hi : c_lo;
-        const int32_t ns = nf ? n_lo : n_hi, ne = nf ? n_hi : n_lo;
-        if (md < 0 || (!merge_strands && cf != nf) || (int64_t)ns > (int64_t)ce + md) {
-          swept[b + w++] = BoxD{c_lo, c_hi, tlo[c], thi[c], first.q_id, tid[c], first.row, 1u, ord[c]};
-          c = x;
-          c_lo = n_lo;
-          c_hi = n_hi;
-        } else {
-          const int32_t ms = min(cs, ns), me = max(ce, ne);
-          bool mf = cf;
-          if (merge_strands && cf != nf) {
-            const int64_t cl = (int64_t)ce - cs, nl = (int64_t)ne - ns;
-            mf = nl > cl ? nf : cf;
+    // ---- ties on (start, strand): restore ord order (insertion sort inside runs of equal keys; rare)
+    {
+      bool tie = false;
+      for (uint32_t i = 1 + lt; i < nr; i += T) tie |= (m.skey[i] >> 16) == (m.skey[i - 1] >> 16);
+      const bool any = (T == 32) ? __any_sync(FULL, tie) : (__syncthreads_or(tie) != 0);
+      if (any) {
+        if (lt == 0) {
+          for (uint32_t i = 1; i < nr; i++) {
+            const uint64_t ki = m.skey[i];
+            if ((ki >> 16) != (m.skey[i - 1] >> 16)) continue;
+            const uint64_t oi = m.ord[ki & 0xffffu];
+            uint32_t j = i;
+            while (j > 0 && (m.skey[j - 1] >> 16) == (ki >> 16) && m.ord[m.skey[j - 1] & 0xffffu] > oi) {
+              m.skey[j] = m.skey[j - 1];
+              j--;
+            }
+            m.skey[j] = ki;
           }
-          c_lo = mf ? ms : me;
-          c_hi = mf ? me : ms;
+        }
+        sync();
+      }
+    }
+    // sorted position -> (start, end) pair in place of the key, box index | forward << 15 in `parent`
+    for (uint32_t i = lt; i < nr; i += T) {
+      const uint32_t x = (uint32_t)(m.skey[i] & 0xffffu);
+      const bool fwd = m.qlo[x] <= m.qhi[x];
+      const int32_t st = fwd ? m.qlo[x] : m.qhi[x], en = fwd ? m.qhi[x] : m.qlo[x];
+      m.skey[i] = ((uint64_t)(uint32_t)en << 32) | (uint32_t)st;
+      m.parent[i] = (uint16_t)(x | (fwd ? 0x8000u : 0u));
+    }
+    sync();
+    auto emit = [&](uint32_t w, uint32_t first_pos, int32_t st, int32_t en, bool fwd) {
+      const uint32_t c = m.parent[first_pos] & 0x7fffu;
+      swept[b + w] = BoxD{fwd ? st : en, fwd ? en : st, m.tlo[c], m.thi[c], first.q_id, m.tid[c], first.row, 1u, m.ord[c]};
+    };
+    if (merge_strands) {
+      // ---- the sweep of src/main.rs:12496-12556 as scans over the sorted boxes (first warp):
+      //   a box starts a new output row iff its start exceeds every earlier end by more than d;
+      //   the row spans [start of its first box, max end]; its orientation is that of the last
+      //   box that was longer than the span merged before it (else of the first box).
+      if (threadIdx.x < 32 || T == 32) {
+        int carry_pm = INT32_MIN, carry_lb = -1, carry_os = -1;
+        uint32_t carry_cnt = 0;
+        for (uint32_t k0 = 0; k0 < nr; k0 += 32) {
+          const uint32_t k = k0 + lane;
+          const bool valid = k < nr;
+          const uint64_t se = valid ? m.skey[k] : 0ull;
+          const int32_t st = (int32_t)(uint32_t)se, en = (int32_t)(uint32_t)(se >> 32);
+          const int pm_in = max(carry_pm, warp_incl_max(valid ? en : INT32_MIN));
+          int pm_ex = __shfl_up_sync(FULL, pm_in, 1);
+          if (lane == 0) pm_ex = carry_pm;
+          const bool brk = valid && (k == 0 || md < 0 || (int64_t)st > (int64_t)pm_ex + md);
+          const int lb_in = max(carry_lb, warp_incl_max(brk ? (int)k : -1));
+          int lb_ex = __shfl_up_sync(FULL, lb_in, 1);
+          if (lane == 0) lb_ex = carry_lb;
+          bool cand = false;
+          if (valid && !brk) {
+            const int32_t s0 = (int32_t)(uint32_t)m.skey[lb_in];
+            cand = ((int64_t)en - st) > ((int64_t)pm_ex - s0);
+          }
+          const int os_in = max(carry_os, warp_incl_max((brk || cand) ? (int)k : -1));
+          int os_ex = __shfl_up_sync(FULL, os_in, 1);
+          if (lane == 0) os_ex = carry_os;
+          const unsigned bm = __ballot_sync(FULL, brk);
+          const uint32_t cnt_ex = carry_cnt + __popc(bm & lanemask_lt());
+          if (brk && k > 0) {  // the row that ended just before this box
+            const uint64_t fe = m.skey[lb_ex];  // md < 0: nothing merges, a row is its own box
+            emit(cnt_ex - 1, (uint32_t)lb_ex, (int32_t)(uint32_t)fe, md < 0 ? (int32_t)(uint32_t)(fe >> 32) : pm_ex,
+                 (m.parent[os_ex] & 0x8000u) != 0);
+          }
+          carry_pm = __shfl_sync(FULL, pm_in, 31);
+          carry_lb = __shfl_sync(FULL, lb_in, 31);
+          carry_os = __shfl_sync(FULL, os_in, 31);
+          carry_cnt += __popc(bm);
+        }
+        if (lane == 0) {
+          const uint64_t fe = m.skey[carry_lb];
+          emit(carry_cnt - 1, (uint32_t)carry_lb, (int32_t)(uint32_t)fe, md < 0 ? (int32_t)(uint32_t)(fe >> 32) : carry_pm,
+               (m.parent[carry_os] & 0x8000u) != 0);
+          out_cnt[g] = carry_cnt;
         }
       }
-      swept[b + w++] = BoxD{c_lo, c_hi, tlo[c], thi[c], first.q_id, tid[c], first.row, 1u, ord[c]};
+    } else if (lt == 0) {
+      // --consider-strandness: the literal sequential sweep (a strand change always starts a new row)
+      uint32_t w = 0, cpos = 0;
+      uint64_t se = m.skey[0];
+      int32_t cs = (int32_t)(uint32_t)se, ce = (int32_t)(uint32_t)(se >> 32);
+      bool cf = (m.parent[0] & 0x8000u) != 0;
+      for (uint32_t rd = 1; rd < nr; rd++) {
+        se = m.skey[rd];
+        const int32_t ns = (int32_t)(uint32_t)se, ne = (int32_t)(uint32_t)(se >> 32);
+        const bool nf = (m.parent[rd] & 0x8000u) != 0;
+        if (md < 0 || cf != nf || (int64_t)ns > (int64_t)ce + md) {
+          emit(w++, cpos, cs, ce, cf);
+          cpos = rd; cs = ns; ce = ne; cf = nf;
+        } else {
+          cs = min(cs, ns);
+          ce = max(ce, ne);
+        }
+      }
+      emit(w++, cpos, cs, ce, cf);
       out_cnt[g] = w;
     }
     sync();  // the next segment reuses the shared arrays
