@@ -45,6 +45,7 @@ WORKLOADS = {
     "c2": (50, 8, 2500000, 51, 100, 100, 1, 10000),   # BASELINE configs[1]: depth 1
     "c3": (50, 8, 2500000, 51, 100, 100, 1, 10000),   # BASELINE configs[2]: -x -m 2
     "c4": (200, 8, 2500000, 63, 200, 100, 1, 100000),  # BASELINE configs[3] on one GPU
+    "c4p": (200, 8, 2500000, 63, 200, 100, 1, 5000),   # the c4 index with a short BED (profiling: two row batches)
 }
 
 

@@ -636,12 +636,24 @@ __global__ void __launch_bounds__(T == 32 ? 256 : T)
       }
       continue;
     }
-    for (uint32_t i = lt; i < n; i += T) {
-      const BoxD x = boxes[idx[b + i]];
-      m.ord[i] = x.ord;
-      m.qlo[i] = x.q_lo; m.qhi[i] = x.q_hi; m.tlo[i] = x.t_lo; m.thi[i] = x.t_hi;
-      m.tid[i] = x.t_id;
-      m.parent[i] = (uint16_t)i;
+    // gather the boxes of the segment, four independent loads in flight per thread
+    for (uint32_t i0 = lt; i0 < n; i0 += 4 * T) {
+      BoxD x[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const uint32_t i = i0 + u * T;
+        if (i < n) x[u] = boxes[idx[b + i]];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const uint32_t i = i0 + u * T;
+        if (i < n) {
+          m.ord[i] = x[u].ord;
+          m.qlo[i] = x[u].q_lo; m.qhi[i] = x[u].q_hi; m.tlo[i] = x[u].t_lo; m.thi[i] = x[u].t_hi;
+          m.tid[i] = x[u].t_id;
+          m.parent[i] = (uint16_t)i;
+        }
+      }
     }
     if (lt == 0) s_cnt[gi][0] = s_cnt[gi][1] = 0;
     sync();
@@ -744,28 +756,23 @@ __global__ void __launch_bounds__(T == 32 ? 256 : T)
         sync();
       }
     }
-    // ---- ties on (start, strand): restore ord order (insertion sort inside runs of equal keys; rare)
-    {
-      bool tie = false;
-      for (uint32_t i = 1 + lt; i < nr; i += T) tie |= (m.skey[i] >> 16) == (m.skey[i - 1] >> 16);
-      const bool any = (T == 32) ? __any_sync(FULL, tie) : (__syncthreads_or(tie) != 0);
-      if (any) {
-        if (lt == 0) {
-          for (uint32_t i = 1; i < nr; i++) {
-            const uint64_t ki = m.skey[i];
-            if ((ki >> 16) != (m.skey[i - 1] >> 16)) continue;
-            const uint64_t oi = m.ord[ki & 0xffffu];
-            uint32_t j = i;
-            while (j > 0 && (m.skey[j - 1] >> 16) == (ki >> 16) && m.ord[m.skey[j - 1] & 0xffffu] > oi) {
-              m.skey[j] = m.skey[j - 1];
-              j--;
-            }
-            m.skey[j] = ki;
-          }
+    // ---- ties on (start, strand): restore ord order. The thread at the head of a run of equal
+    // keys insertion-sorts that run by ord (runs are short and disjoint, so this is parallel).
+    for (uint32_t i = lt; i + 1 < nr; i += T) {
+      const uint64_t hk = m.skey[i] >> 16;
+      if ((m.skey[i + 1] >> 16) != hk || (i > 0 && (m.skey[i - 1] >> 16) == hk)) continue;
+      for (uint32_t a = i + 1; a < nr && (m.skey[a] >> 16) == hk; a++) {
+        const uint64_t ka = m.skey[a];
+        const uint64_t oa = m.ord[ka & 0xffffu];
+        uint32_t j = a;
+        while (j > i && m.ord[m.skey[j - 1] & 0xffffu] > oa) {
+          m.skey[j] = m.skey[j - 1];
+          j--;
         }
-        sync();
+        m.skey[j] = ka;
       }
     }
+    sync();
     // sorted position -> (start, end) pair in place of the key, box index | forward << 15 in `parent`
     for (uint32_t i = lt; i < nr; i += T) {
       const uint32_t x = (uint32_t)(m.skey[i] & 0xffffu);
