@@ -1192,8 +1192,9 @@ bool Runner::merge_fused(const BoxD *boxes, uint64_t nB, uint64_t nv, BatchOut &
     };
     launch(k_merge_segments<32, seg_cap(0)>, 256, (size_t)8 * seg_cap(0) * SEG_BYTES, 5, 8, 0);
     launch(k_merge_segments<32, seg_cap(1)>, 256, (size_t)8 * seg_cap(1) * SEG_BYTES, 2, 8, 1);
-    launch(k_merge_segments<128, seg_cap(2)>, 128, (size_t)seg_cap(2) * SEG_BYTES, 5, 1, 2);
-    launch(k_merge_segments<512, seg_cap(3)>, 512, (size_t)seg_cap(3) * SEG_BYTES, 1, 1, 3);
+    launch(k_merge_segments<128, seg_cap(2)>, 128, (size_t)seg_cap(2) * SEG_BYTES, 10, 1, 2);
+    launch(k_merge_segments<128, seg_cap(3)>, 128, (size_t)seg_cap(3) * SEG_BYTES, 5, 1, 3);
+    launch(k_merge_segments<512, seg_cap(4)>, 512, (size_t)seg_cap(4) * SEG_BYTES, 1, 1, 4);
   }
   DBuf<uint64_t> scan(g.G + 1, ar_);
   CUDA_CHECK(cudaMemsetAsync(scan.get() + g.G, 0, 8, s_));

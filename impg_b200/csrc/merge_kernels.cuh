@@ -549,9 +549,11 @@ __global__ void k_boxd_to_cols(const BoxD *__restrict__ b, const uint32_t *__res
 // batch with a segment beyond SEG_MAX falls back to the global path.
 namespace impgx {
 
-constexpr int SEG_CLASSES = 4;
-// boxes per segment (powers of two: the sort pads to one): two warp classes, 128- and 512-thread CTAs
-__host__ __device__ constexpr int seg_cap(int c) { return c == 0 ? 128 : (c == 1 ? 256 : (c == 2 ? 1024 : 4096)); }
+constexpr int SEG_CLASSES = 5;
+// boxes per segment (powers of two: the sort pads to one): two warp classes, then 128-, 128- and 512-thread CTAs
+__host__ __device__ constexpr int seg_cap(int c) {
+  return c == 0 ? 128 : (c == 1 ? 256 : (c == 2 ? 512 : (c == 3 ? 1024 : 4096)));
+}
 constexpr int SEG_MAX = seg_cap(SEG_CLASSES - 1);
 constexpr int SEG_BYTES = 40;  // shared memory per box
 
@@ -741,20 +743,33 @@ __global__ void __launch_bounds__(T == 32 ? 256 : T)
     while (P < nr) P <<= 1;
     for (uint32_t i = nr + lt; i < P; i += T) m.skey[i] = ~0ull;
     sync();
-    for (uint32_t k = 2; k <= P; k <<= 1) {
-      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-        for (uint32_t i = lt; i < (P >> 1); i += T) {
-          // i-th compare-exchange of this step: lo has bit j clear
-          const uint32_t lo = ((i & ~(j - 1)) << 1) | (i & (j - 1)), hi = lo | j;
-          const uint64_t x = m.skey[lo], y = m.skey[hi];
-          const bool up = (lo & k) == 0;
-          if ((y < x) == up) {
-            m.skey[lo] = y;
-            m.skey[hi] = x;
+    {
+      // Bitonic network. Warp w owns the compare-exchanges [w * ppw, (w + 1) * ppw) of every step;
+      // for j <= ppw both elements of its pairs lie in the warp's own 2 * ppw keys, so those steps
+      // only need a warp barrier — the CTA barrier is paid for the few steps that cross warps.
+      const uint32_t half = P >> 1;
+      const uint32_t ppw = (T == 32) ? half : max(32u, half / (uint32_t)(T / 32));
+      const uint32_t wbase = (T == 32) ? 0u : (uint32_t)(threadIdx.x >> 5) * ppw;
+      for (uint32_t k = 2; k <= P; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+          for (uint32_t r = lane; r < ppw; r += 32) {
+            const uint32_t i = wbase + r;  // i-th compare-exchange of this step: lo has bit j clear
+            if (i < half) {
+              const uint32_t lo = ((i & ~(j - 1)) << 1) | (i & (j - 1)), hi = lo | j;
+              const uint64_t x = m.skey[lo], y = m.skey[hi];
+              const bool up = (lo & k) == 0;
+              if ((y < x) == up) {
+                m.skey[lo] = y;
+                m.skey[hi] = x;
+              }
+            }
           }
+          const uint32_t j_next = j > 1 ? (j >> 1) : k;  // first step of the next level has j = k
+          if (T != 32 && (j > ppw || j_next > ppw)) __syncthreads();
+          else __syncwarp();
         }
-        sync();
       }
+      sync();
     }
     // ---- ties on (start, strand): restore ord order. The thread at the head of a run of equal
     // keys insertion-sorts that run by ord (runs are short and disjoint, so this is parallel).
