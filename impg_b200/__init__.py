@@ -20,6 +20,7 @@ LIB_PATH = os.path.join(_HERE, "libimpgx.so")
 
 OK, E_INVALID, E_NO_DEVICE, E_CUDA, E_NOMEM, E_IO, E_PARSE, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6, -7
 MODE_QUERY, MODE_BFS, MODE_DFS = 0, 1, 2
+MODE_MULTI_QUERY, MODE_MULTI_BFS, MODE_MULTI_DFS = 3, 4, 5  # MultiImpg semantics (reference src/multi_impg.rs)
 
 RECORD_DTYPE = np.dtype([("query_id", "<u4"), ("target_id", "<u4"), ("query_start", "<i4"), ("query_end", "<i4"),
                          ("target_start", "<i4"), ("target_end", "<i4"), ("strand", "<u4"), ("reserved", "<u4")])
@@ -349,6 +350,72 @@ class Impg:
         s = C.string_at(ptr).decode()
         lib().impgx_free(C.c_void_p(ptr))
         return s
+
+
+class MultiImpg:
+    """Mirror of the reference's MultiImpg (src/multi_impg.rs): several alignment files behind
+    one ImpgIndex. The reference keeps one sub-index per file and re-sorts the union of their
+    hits by (query id, query first, query last, target first, target last); that order does not
+    depend on the file partition, so here ONE HBM index holds every file and the
+    IMPGX_MODE_MULTI_* modes reproduce MultiImpg's result order and traversal."""
+
+    _MODE = {MODE_QUERY: MODE_MULTI_QUERY, MODE_BFS: MODE_MULTI_BFS, MODE_DFS: MODE_MULTI_DFS}
+
+    def __init__(self, impg):
+        self.idx = impg
+
+    @classmethod
+    def from_pafs(cls, paths, bidirectional=True, device=0):
+        """MultiImpg::load_from_files over PAFs: unified ids by first appearance over the files."""
+        arr = (C.c_char_p * len(paths))(*[p.encode() for p in paths])
+        h = C.c_void_p()
+        _check(lib().impgx_index_from_pafs(arr, C.c_size_t(len(paths)), C.c_int(1 if bidirectional else 0),
+                                           C.c_int(device), C.byref(h)))
+        return cls(Impg(h.value))
+
+    @classmethod
+    def from_record_sets(cls, parts, seq_lens, names=None, bidirectional=True, device=0):
+        """`parts`: one (records, runs, run_offsets) per alignment file, records carrying unified ids."""
+        recs = np.concatenate([np.ascontiguousarray(p[0], dtype=RECORD_DTYPE) for p in parts])
+        runs = np.concatenate([np.ascontiguousarray(p[1], dtype=np.uint32) for p in parts])
+        offs, base = [np.zeros(1, np.uint64)], 0
+        for p in parts:
+            o = np.ascontiguousarray(p[2], dtype=np.uint64)
+            offs.append(o[1:] + np.uint64(base))
+            base += int(o[-1])
+        return cls(Impg.from_records(recs, runs, np.concatenate(offs), seq_lens, names=names,
+                                     bidirectional=bidirectional, device=device))
+
+    def _params(self, params):
+        q = Params()
+        C.memmove(C.byref(q), C.byref(params), C.sizeof(Params))
+        if hasattr(params, "_keep"):
+            q._keep = params._keep
+        q.mode = self._MODE.get(params.mode, params.mode)
+        return q
+
+    def query_batch(self, ranges, params):
+        return self.idx.query_batch(ranges, self._params(params))
+
+    def query_batch_bed(self, ranges, params):
+        return self.idx.query_batch_bed(ranges, self._params(params))
+
+    def query(self, target_id, range_start, range_end, store_cigar=False, min_gap_compressed_identity=None):
+        """MultiImpg::query (reference src/multi_impg.rs:630-649)."""
+        p = make_params(mode=MODE_MULTI_QUERY, store_cigar=store_cigar, min_identity=min_gap_compressed_identity)
+        return self.idx.query_batch(np.array([(target_id, range_start, range_end)], dtype=RANGE_DTYPE), p).row_tuples(0)
+
+    def _transitive(self, mode, target_id, range_start, range_end, **kw):
+        p = make_params(mode=mode, **kw)
+        return self.idx.query_batch(np.array([(target_id, range_start, range_end)], dtype=RANGE_DTYPE), p).row_tuples(0)
+
+    def query_transitive_bfs(self, target_id, range_start, range_end, **kw):
+        """MultiImpg::query_transitive_bfs (reference src/multi_impg.rs:722-755)."""
+        return self._transitive(MODE_MULTI_BFS, target_id, range_start, range_end, **kw)
+
+    def query_transitive_dfs(self, target_id, range_start, range_end, **kw):
+        """MultiImpg::query_transitive_dfs (reference src/multi_impg.rs:687-720)."""
+        return self._transitive(MODE_MULTI_DFS, target_id, range_start, range_end, **kw)
 
 
 # ---------------------------------------------------------------- sharding

@@ -208,6 +208,24 @@ int impgx_index_from_paf(const char *paf_path, int bidirectional, int device, im
   API_END
 }
 
+int impgx_index_from_pafs(const char *const *paf_paths, size_t n_paths, int bidirectional, int device, impgx_index **out) {
+  API_BEGIN
+  REQUIRE(out && paf_paths && n_paths >= 1, IMPGX_E_INVALID, "NULL argument");
+  *out = nullptr;
+  impgx::check_device(device);
+  impgx::PafData pd;  // shared SequenceIndex: unified ids by first appearance over the files (src/multi_impg.rs:159-176)
+  for (size_t f = 0; f < n_paths; f++) {
+    REQUIRE(paf_paths[f], IMPGX_E_INVALID, "NULL path");
+    impgx::parse_paf(paf_paths[f], pd);
+  }
+  impgx_index *idx = impgx::index_build(pd.recs.data(), pd.recs.size(), pd.runs.data(), pd.run_off.data(), pd.lens.data(),
+                                        (uint32_t)pd.lens.size(), bidirectional != 0, device);
+  idx->names = pd.names;
+  idx->name_to_id = pd.ids;
+  *out = idx;
+  API_END
+}
+
 void impgx_index_free(impgx_index *idx) { delete idx; }
 uint32_t impgx_index_num_seqs(const impgx_index *idx) { return idx ? idx->n_seqs : 0; }
 uint64_t impgx_index_num_entries(const impgx_index *idx) { return idx ? idx->n_entries : 0; }

@@ -39,6 +39,48 @@ __global__ void k_hit_order_keys(const Hit *__restrict__ hits, const LiftTask *_
   }
 }
 
+// ---- MultiImpg hit order (src/multi_impg.rs:582-592): hits of one range sorted by
+// (query id, query first, query last, target first, target last), signed compares.
+// drop_mode 1 (transitive walk): hits onto the walked sequence itself are skipped
+// before they are output (:888-891); drop_mode 2 (query): a hit equal to the self
+// interval is a "duplicate self interval" and is dropped (:556-571).
+__global__ void k_multi_drop(Hit *__restrict__ hits, const LiftTask *__restrict__ tasks, const Frontier *__restrict__ fr,
+                             uint64_t n, int drop_mode, unsigned long long *__restrict__ n_ok) {
+  unsigned long long c = 0;
+  for (uint64_t i = gtid(); i < n; i += gstride()) {
+    Hit h = hits[i];
+    if (h.row == INVALID_ID) continue;
+    bool drop = false;
+    if (drop_mode == 1) drop = h.q_id == h.t_id;
+    else if (drop_mode == 2) {
+      const Frontier f = fr[tasks[i].range];
+      drop = h.q_id == h.t_id && h.q_first == f.start && h.q_last == f.end;
+    }
+    if (drop) hits[i].row = INVALID_ID;
+    else c++;
+  }
+  if (c) atomicAdd(n_ok, c);
+}
+// field: 0 t_last, 1 t_first, 2 q_last, 3 q_first
+__global__ void k_multi_field_keys(const Hit *__restrict__ hits, const uint32_t *__restrict__ perm, uint64_t n, int field,
+                                   uint32_t *__restrict__ keys) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) {
+    const Hit h = hits[perm[i]];
+    const int32_t v = field == 0 ? h.t_last : (field == 1 ? h.t_first : (field == 2 ? h.q_last : h.q_first));
+    keys[i] = (uint32_t)v ^ 0x80000000u;
+  }
+}
+__global__ void k_multi_major_keys(const Hit *__restrict__ hits, const LiftTask *__restrict__ tasks,
+                                   const uint32_t *__restrict__ orig, const uint32_t *__restrict__ perm, uint64_t n,
+                                   uint32_t n_frontier, int seq_bits, uint64_t *__restrict__ keys) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) {
+    const uint32_t j = perm[i];
+    const Hit h = hits[j];
+    const uint32_t r = orig ? orig[tasks[j].range] : tasks[j].range;
+    keys[i] = h.row == INVALID_ID ? ((uint64_t)n_frontier << seq_bits) : (((uint64_t)r << seq_bits) | h.q_id);
+  }
+}
+
 __global__ void k_locality_keys(const Frontier *__restrict__ fr, uint64_t n, uint64_t *__restrict__ keys,
                                 uint32_t *__restrict__ vals) {
   for (uint64_t i = gtid(); i < n; i += gstride()) {
@@ -375,11 +417,13 @@ __global__ void k_dfs_init_stack(const Frontier *__restrict__ fr, uint64_t n, Df
 }
 
 // the stack array is sorted by (row, id, start): the top of a row is the last entry of its segment
-__global__ void k_dfs_pop(const DfsEntry *__restrict__ st, uint64_t n, uint32_t max_depth, uint64_t *__restrict__ popped,
-                          Frontier *__restrict__ cand, uint64_t *__restrict__ is_fr, uint32_t *__restrict__ cur_depth) {
+// pop_front: MultiImpg's BFS takes the FIRST entry of the sorted queue (src/multi_impg.rs:855-860)
+__global__ void k_dfs_pop(const DfsEntry *__restrict__ st, uint64_t n, uint32_t max_depth, int pop_front,
+                          uint64_t *__restrict__ popped, Frontier *__restrict__ cand, uint64_t *__restrict__ is_fr,
+                          uint32_t *__restrict__ cur_depth) {
   for (uint64_t i = gtid(); i < n; i += gstride()) {
     const DfsEntry e = st[i];
-    if (i + 1 < n && st[i + 1].row == e.row) continue;  // not the top
+    if (pop_front ? (i > 0 && st[i - 1].row == e.row) : (i + 1 < n && st[i + 1].row == e.row)) continue;  // not the one popped
     popped[i] = 1;
     if (max_depth > 0 && e.depth >= max_depth) continue;  // :2125-2127, popped and dropped
     cand[e.row] = Frontier{e.row, e.id, e.start, e.end};

@@ -418,6 +418,9 @@ class Runner {
   DBuf<unsigned long long> d_counters_;
   cudaEvent_t ev_[2] = {nullptr, nullptr};
   Comm *comm_ = nullptr;  // sharded index only
+  // MultiImpg modes: 0 = Impg order (frontier index, coitrees visit rank); 1 / 2 = the 5-key order of
+  // src/multi_impg.rs:582-592 with the transitive / query drop rule (k_multi_drop)
+  int multi_order_ = 0;
 
   void prepare(const impgx_range *d_ranges, uint32_t n_rows);
   void lift_core(const DBuf<Frontier> &fr, uint64_t nF, bool closed, bool clip,
@@ -561,8 +564,18 @@ void Runner::stab_and_lift(const DBuf<Frontier> &fr_ref, uint64_t nF, bool close
               }
             },
             L);
-  const uint64_t H = L.H, n_ok = L.n_ok;
+  const uint64_t H = L.H;
+  uint64_t n_ok = L.n_ok;
   if (H == 0) return;
+  if (multi_order_) {
+    CUDA_CHECK(cudaMemsetAsync(d_counters_.get(), 0, 8, s_));
+    LAUNCH(k_multi_drop, grid_threads(H), 256, s_, L.hits.get(), L.tasks.get(), L.fr, H, multi_order_, d_counters_.get());
+    unsigned long long c = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&c, d_counters_.get(), 8, cudaMemcpyDeviceToHost, s_));
+    CUDA_CHECK(cudaStreamSynchronize(s_));
+    ctx.d2h_bytes += 8;
+    n_ok = c;
+  }
   lvl.n = n_ok;
   if (n_ok == 0 && !sink) return;
   WallTimer wt(ctx.w_order);
@@ -588,9 +601,23 @@ void Runner::stab_and_lift(const DBuf<Frontier> &fr_ref, uint64_t nF, bool close
   }
   DBuf<uint64_t> keys(H, ar_);
   DBuf<uint32_t> perm(H, ar_);
-  LAUNCH(k_hit_order_keys, grid_threads(H), 256, s_, L.hits.get(), L.tasks.get(), L.d_orig, H, (uint32_t)nF, keys.get(),
-         perm.get());
-  sort_pairs(keys, perm, H, 0, 32 + bits_for(nF), sc_, s_, ctx);
+  if (multi_order_) {
+    // LSD over the five keys: four stable 32-bit passes, then (range, query id)
+    const int seq_bits = bits_for(ix_.n_seqs > 1 ? ix_.n_seqs - 1 : 1);
+    DBuf<uint32_t> k32(H, ar_);
+    LAUNCH(k_iota_u32, grid_threads(H), 256, s_, perm.get(), H);
+    for (int field = 0; field < 4; field++) {
+      LAUNCH(k_multi_field_keys, grid_threads(H), 256, s_, L.hits.get(), perm.get(), H, field, k32.get());
+      sort_pairs(k32, perm, H, 0, 32, sc_, s_, ctx);
+    }
+    LAUNCH(k_multi_major_keys, grid_threads(H), 256, s_, L.hits.get(), L.tasks.get(), L.d_orig, perm.get(), H,
+           (uint32_t)nF, seq_bits, keys.get());
+    sort_pairs(keys, perm, H, 0, seq_bits + bits_for(nF), sc_, s_, ctx);
+  } else {
+    LAUNCH(k_hit_order_keys, grid_threads(H), 256, s_, L.hits.get(), L.tasks.get(), L.d_orig, H, (uint32_t)nF,
+           keys.get(), perm.get());
+    sort_pairs(keys, perm, H, 0, 32 + bits_for(nF), sc_, s_, ctx);
+  }
   LAUNCH(k_gather<Hit>, grid_threads(n_ok), 256, s_, L.hits.get(), perm.get(), n_ok, lvl.hits.get());
   if (p_.store_cigar) {
     LAUNCH(k_gather_entry, grid_threads(n_ok), 256, s_, L.tasks.get(), perm.get(), n_ok, lvl.entry.get());
@@ -841,7 +868,11 @@ void Runner::prepare(const impgx_range *d_ranges, uint32_t n_rows) {
 }
 
 void Runner::run(const impgx_range *d_ranges, uint32_t n_rows, bool bed, BatchOut &out) {
-  REQUIRE(p_.mode <= IMPGX_MODE_DFS, IMPGX_E_INVALID, "unknown mode");
+  REQUIRE(p_.mode <= IMPGX_MODE_MULTI_DFS, IMPGX_E_INVALID, "unknown mode");
+  const bool multi = p_.mode >= IMPGX_MODE_MULTI_QUERY;
+  const bool query_mode = p_.mode == IMPGX_MODE_QUERY || p_.mode == IMPGX_MODE_MULTI_QUERY;
+  const bool dfs_like = p_.mode == IMPGX_MODE_DFS || p_.mode == IMPGX_MODE_MULTI_BFS || p_.mode == IMPGX_MODE_MULTI_DFS;
+  multi_order_ = multi ? (query_mode ? 2 : 1) : 0;
   REQUIRE(!(bed && p_.store_cigar), IMPGX_E_INVALID, "BED output carries no CIGAR (src/main.rs:7447)");
   REQUIRE(idx_->owner.empty(), IMPGX_E_INVALID,
           "this index is one shard of a target-sharded index: use impgx_query_batch_bed_sharded");
@@ -861,13 +892,14 @@ void Runner::run(const impgx_range *d_ranges, uint32_t n_rows, bool bed, BatchOu
     CUDA_CHECK(cudaMemsetAsync(sink.counters.get(), 0, 16, s_));
   }
   auto sink_for = [&](uint32_t level) -> BedSink * {
-    if (!direct || nF >= (1ull << 26) || level >= 58) return nullptr;
+    // MultiImpg order is not (range, visit rank): those levels are always sorted
+    if (!direct || multi || nF >= (1ull << 26) || level >= 58) return nullptr;
     sink.prefix = (uint64_t)n_rows + prior;
     sink.level = level + 1;
     return &sink;
   };
 
-  if (p_.mode == IMPGX_MODE_QUERY) {
+  if (query_mode) {
     levels.emplace_back();
     stab_and_lift(fr, nF, /*closed=*/true, /*clip=*/false, sink_for(0), levels.back());
   } else {
@@ -897,7 +929,7 @@ void Runner::run(const impgx_range *d_ranges, uint32_t n_rows, bool bed, BatchOu
       }
     }
     uint32_t depth = 0;
-    if (p_.mode == IMPGX_MODE_DFS) {
+    if (dfs_like) {
       run_dfs(d_ranges, n_rows, fr, nF, V, levels);
       nF = 0;
     }
@@ -925,7 +957,7 @@ void Runner::run(const impgx_range *d_ranges, uint32_t n_rows, bool bed, BatchOu
     }
     // seeds, then the levels that were ordered for the fold (their index is their ordinal)
     LAUNCH(k_boxes_from_seeds, grid_threads(n_rows), 256, s_, d_ranges, n_rows, p_.min_output_length,
-           p_.mode == IMPGX_MODE_QUERY ? 1 : 0, sink.boxes.get(), sink.counters.get(), (const uint32_t *)nullptr, 0u);
+           query_mode ? 1 : 0, sink.boxes.get(), sink.counters.get(), (const uint32_t *)nullptr, 0u);
     uint64_t off = n_rows;
     for (size_t l = 0; l < levels.size(); l++) {
       if (!levels[l].n) continue;
@@ -937,7 +969,7 @@ void Runner::run(const impgx_range *d_ranges, uint32_t n_rows, bool bed, BatchOu
     return;
   }
   BatchOut raw;
-  assemble(d_ranges, n_rows, levels, p_.mode == IMPGX_MODE_QUERY, bed ? raw : out);
+  assemble(d_ranges, n_rows, levels, query_mode, bed ? raw : out);
   if (bed) bed_merge(raw, n_rows, out);
 }
 
@@ -1558,8 +1590,8 @@ void Runner::run_dfs(const impgx_range *d_ranges, uint32_t n_rows, DBuf<Frontier
     CUDA_CHECK(cudaMemsetAsync(popped.get(), 0, (n_stack + 1) * 8, s_));
     CUDA_CHECK(cudaMemsetAsync(is_fr.get(), 0, ((size_t)n_rows + 1) * 8, s_));
     DBuf<Frontier> cand(n_rows, ar_);
-    LAUNCH(k_dfs_pop, grid_threads(n_stack), 256, s_, stack.get(), n_stack, p_.max_depth, popped.get(), cand.get(),
-           is_fr.get(), cur_depth.get());
+    LAUNCH(k_dfs_pop, grid_threads(n_stack), 256, s_, stack.get(), n_stack, p_.max_depth,
+           p_.mode == IMPGX_MODE_MULTI_BFS ? 1 : 0, popped.get(), cand.get(), is_fr.get(), cur_depth.get());
     CUDA_CHECK(cudaMemcpyAsync(fr_scan.get(), is_fr.get(), ((size_t)n_rows + 1) * 8, cudaMemcpyDeviceToDevice, s_));
     exclusive_scan_u64(fr_scan.get(), (uint64_t)n_rows + 1, sc_, s_);
     ctx.launches += 2;
@@ -1571,7 +1603,9 @@ void Runner::run_dfs(const impgx_range *d_ranges, uint32_t n_rows, DBuf<Frontier
     uint64_t n_pieces = 0;
     if (nF) {
       levels.emplace_back();
-      stab_and_lift(fr, nF, /*closed=*/false, /*clip=*/true, nullptr, levels.back());
+      // MultiImpg walks with Impg::query (closed visit, unclipped request: src/multi_impg.rs:875-883)
+      const bool mq = p_.mode != IMPGX_MODE_DFS;
+      stab_and_lift(fr, nF, /*closed=*/mq, /*clip=*/!mq, nullptr, levels.back());
       fold(levels.back(), n_rows, V, pieces, n_pieces, /*raw_pieces=*/true);
     }
     // ---- new stack = kept entries + pushed pieces, sorted by (row, id, start), merged per row
@@ -1628,7 +1662,7 @@ impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n
   REQUIRE(idx, IMPGX_E_INVALID, "index is NULL");
   REQUIRE(!comm || bed, IMPGX_E_UNSUPPORTED, "the sharded index returns BED rows only");
   REQUIRE(ranges || n == 0, IMPGX_E_INVALID, "ranges is NULL");
-  REQUIRE(p.mode <= IMPGX_MODE_DFS, IMPGX_E_INVALID, "unknown mode");
+  REQUIRE(p.mode <= IMPGX_MODE_MULTI_DFS, IMPGX_E_INVALID, "unknown mode");
   REQUIRE(p.max_depth <= 65535, IMPGX_E_INVALID, "max_depth is a u16 in the reference");
   std::lock_guard<std::mutex> lock(idx->mu);
   check_device(idx->device);

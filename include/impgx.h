@@ -76,7 +76,15 @@ typedef struct impgx_range {
 typedef enum impgx_mode {
   IMPGX_MODE_QUERY = 0, /* Impg::query                 src/impg.rs:1852-1928 */
   IMPGX_MODE_BFS = 1,   /* Impg::query_transitive_bfs  src/impg.rs:2311-2597 */
-  IMPGX_MODE_DFS = 2    /* Impg::query_transitive_dfs  src/impg.rs:2057-2309 */
+  IMPGX_MODE_DFS = 2,   /* Impg::query_transitive_dfs  src/impg.rs:2057-2309 */
+  /* MultiImpg (src/multi_impg.rs): one sub-index per alignment file, queries fanned
+   * out to every sub-index that holds the target and the hits re-sorted by
+   * (query id, query first, query last, target first, target last) — so the result
+   * does not depend on how the alignments are spread over files, and one unified
+   * HBM index (impgx_index_from_pafs) answers for all of them. */
+  IMPGX_MODE_MULTI_QUERY = 3, /* MultiImpg::query                 src/multi_impg.rs:495-595, :630-649 */
+  IMPGX_MODE_MULTI_BFS = 4,   /* MultiImpg::query_transitive_bfs  src/multi_impg.rs:722-755, :796-991 (queue popped at the front) */
+  IMPGX_MODE_MULTI_DFS = 5    /* MultiImpg::query_transitive_dfs  src/multi_impg.rs:687-720, :796-991 (popped at the back) */
 } impgx_mode;
 
 /* Arguments of ImpgIndex::query / query_transitive_* (src/impg_index.rs:30-80)
@@ -157,6 +165,13 @@ int impgx_index_build(const impgx_record *records, size_t n_records,
  * ids are assigned by first appearance in the file (query column first). */
 int impgx_index_from_paf(const char *paf_path, int bidirectional, int device,
                          impgx_index **out);
+
+/* MultiImpg::load_from_files (src/multi_impg.rs:140-216) over PAF files: unified
+ * sequence ids by first appearance over the files in the given order; one HBM
+ * index holds every file's alignments (query it with the IMPGX_MODE_MULTI_* modes
+ * for MultiImpg's result order, or with the plain modes for Impg's). */
+int impgx_index_from_pafs(const char *const *paf_paths, size_t n_paths, int bidirectional, int device,
+                          impgx_index **out);
 
 void impgx_index_free(impgx_index *idx);
 

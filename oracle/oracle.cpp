@@ -32,7 +32,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <fcntl.h>
+#include <deque>
 #include <map>
+#include <memory>
+#include <tuple>
 #include <string>
 #include <sys/stat.h>
 #include <time.h>
@@ -763,6 +766,144 @@ std::vector<Result> perform_query(const Index &idx, uint32_t target_id, int32_t 
                              [&](const Result &r) { return !(r.q_id == target_id || p.subset_mask[r.q_id]); }),
               res.end());
   }
+  return res;
+}
+
+// ---------------------------------------------------------------- MultiImpg
+// src/multi_impg.rs: one sub-index (Impg) per alignment file, unified sequence
+// ids, queries fanned out to every sub-index that has a tree for the target.
+struct MultiIndex {
+  std::vector<std::unique_ptr<Index>> subs;
+  std::vector<std::vector<uint32_t>> local_to_unified;                           // :127-129
+  std::map<uint32_t, std::vector<std::pair<uint32_t, uint32_t>>> forest_map;      // unified target -> (index_idx, local id), :178-195
+  std::vector<uint64_t> seq_lens;                                                 // unified
+};
+
+Result make_self_interval(uint32_t target_id, int32_t rs, int32_t re, bool store_cigar) {  // :598-622
+  Result self;
+  self.q_id = self.t_id = target_id;
+  self.q_first = self.t_first = rs;
+  self.q_last = self.t_last = re;
+  if (store_cigar) self.cigar.push_back(CigarOp::make(re - rs, '='));
+  return self;
+}
+
+// src/multi_impg.rs:495-595 query_all_indices
+std::vector<Result> multi_query_all_indices(const MultiIndex &mi, uint32_t unified_target_id, int32_t rs, int32_t re,
+                                            bool store_cigar, double min_identity) {
+  auto loc = mi.forest_map.find(unified_target_id);
+  if (loc == mi.forest_map.end()) return {make_self_interval(unified_target_id, rs, re, store_cigar)};
+  std::vector<Result> final_results;
+  bool seen_self = false;
+  for (auto &l : loc->second) {  // rayon par_iter + ordered collect = location order
+    const Index &sub = *mi.subs[l.first];
+    auto local = query(sub, l.second, rs, re, store_cigar, min_identity);
+    const auto &l2u = mi.local_to_unified[l.first];
+    for (auto &r : local) {
+      // translate_to_unified :462-492
+      if (r.q_id >= l2u.size() || r.t_id >= l2u.size()) continue;
+      r.q_id = l2u[r.q_id];
+      r.t_id = l2u[r.t_id];
+      if (r.q_id == UINT32_MAX || r.t_id == UINT32_MAX) continue;
+      const bool is_self = r.q_id == unified_target_id && r.t_id == unified_target_id && r.q_first == rs && r.q_last == re;
+      if (is_self) {
+        if (!seen_self) {
+          final_results.push_back(std::move(r));
+          seen_self = true;
+        }
+      } else {
+        final_results.push_back(std::move(r));
+      }
+    }
+  }
+  if (!seen_self) final_results.insert(final_results.begin(), make_self_interval(unified_target_id, rs, re, store_cigar));
+  if (final_results.size() > 1) {  // :580-592: the first element stays, the rest is sorted (stable sort_by)
+    Result self = std::move(final_results.front());
+    final_results.erase(final_results.begin());
+    std::stable_sort(final_results.begin(), final_results.end(), [](const Result &a, const Result &b) {
+      return std::make_tuple(a.q_id, a.q_first, a.q_last, a.t_first, a.t_last) <
+             std::make_tuple(b.q_id, b.q_first, b.q_last, b.t_first, b.t_last);
+    });
+    final_results.insert(final_results.begin(), std::move(self));
+  }
+  return final_results;
+}
+
+// src/multi_impg.rs:796-991 transitive_query_impl (masked_regions = None)
+std::vector<Result> multi_transitive_query(const MultiIndex &mi, uint32_t target_id, int32_t rs, int32_t re,
+                                           const QParams &p, bool use_dfs) {
+  Index lens_only;  // consider_for_expansion only needs the unified lengths
+  lens_only.seq_lens = mi.seq_lens;
+  std::map<uint32_t, SortedRanges> visited;
+  auto vit = visited.emplace(target_id, SortedRanges((int32_t)mi.seq_lens[target_id], 0)).first;
+  auto filtered = vit->second.insert({rs, re});
+  std::vector<Result> results;
+  struct Item {
+    uint32_t id;
+    int32_t s, e;
+    uint32_t depth;
+  };
+  std::deque<Item> stack;
+  for (auto &f : filtered) {
+    results.push_back(make_self_interval(target_id, f.first, f.second, p.store_cigar));
+    if (std::abs(f.first - f.second) >= p.min_transitive_len) stack.push_back({target_id, f.first, f.second, 0});
+  }
+  while (!stack.empty()) {
+    Item cur;
+    if (use_dfs) {
+      cur = stack.back();
+      stack.pop_back();
+    } else {
+      cur = stack.front();
+      stack.pop_front();
+    }
+    if (p.max_depth > 0 && cur.depth >= p.max_depth) continue;
+    auto step = multi_query_all_indices(mi, cur.id, cur.s, cur.e, p.store_cigar, p.min_identity);
+    for (auto &r : step) {
+      const uint32_t qid = r.q_id;
+      if (qid == cur.id) continue;  // :888-891 (also drops the self interval)
+      if (p.subset_mask && qid != target_id && !p.subset_mask[qid]) continue;  // :893-901
+      const int32_t aqs = std::min(r.q_first, r.q_last), aqe = std::max(r.q_first, r.q_last);
+      const int32_t length = std::abs(r.q_last - r.q_first);
+      if (p.min_output_length < 0 || length >= p.min_output_length) results.push_back(std::move(r));
+      consider_for_expansion(lens_only, visited, qid, aqs, aqe, p, false, [&](uint32_t id, int32_t s, int32_t e) {
+        stack.push_back({id, s, e, cur.depth + 1});
+      });
+    }
+    // :968-986
+    std::stable_sort(stack.begin(), stack.end(), [](const Item &a, const Item &b) {
+      return a.id != b.id ? a.id < b.id : a.s < b.s;
+    });
+    if (!stack.empty()) {
+      size_t write = 0;
+      for (size_t read = 1; read < stack.size(); read++) {
+        if (stack[write].id == stack[read].id && stack[write].e >= stack[read].s) {
+          stack[write].e = std::max(stack[write].e, stack[read].e);
+        } else {
+          write += 1;
+          std::swap(stack[write], stack[read]);
+        }
+      }
+      stack.resize(write + 1);
+    }
+  }
+  return results;
+}
+
+// perform_query (src/main.rs:11605-11707) over a MultiImpg
+std::vector<Result> perform_query_multi(const MultiIndex &mi, uint32_t target_id, int32_t rs, int32_t re, uint32_t mode,
+                                        const QParams &p) {
+  if (mode == IMPGX_MODE_MULTI_BFS) return multi_transitive_query(mi, target_id, rs, re, p, false);
+  if (mode == IMPGX_MODE_MULTI_DFS) return multi_transitive_query(mi, target_id, rs, re, p, true);
+  auto res = multi_query_all_indices(mi, target_id, rs, re, p.store_cigar, p.min_identity);
+  if (p.min_output_length >= 0)
+    res.erase(std::remove_if(res.begin(), res.end(),
+                             [&](const Result &r) { return std::abs(r.q_last - r.q_first) < p.min_output_length; }),
+              res.end());
+  if (p.subset_mask)
+    res.erase(std::remove_if(res.begin(), res.end(),
+                             [&](const Result &r) { return !(r.q_id == target_id || p.subset_mask[r.q_id]); }),
+              res.end());
   return res;
 }
 
@@ -1681,6 +1822,70 @@ void *orc_query_batch(void *h, const impgx_range *ranges, size_t n, const impgx_
   row_offsets[0] = 0;
   for (size_t i = 0; i < n; i++) {
     auto res = perform_query(*idx, ranges[i].target_id, ranges[i].start, ranges[i].end, p->mode, q, 1);
+    if (bed_merge) {
+      bool any_empty = false;
+      for (auto &r : res) any_empty |= r.cigar.empty();
+      if (any_empty) merge_adjusted_intervals_gap_2d(res, p->merge_distance);
+      merge_query_adjusted_intervals(res, p->merge_distance, p->merge_strands != 0);
+    }
+    for (auto &r : res) all->r.push_back(std::move(r));
+    row_offsets[i + 1] = all->r.size();
+  }
+  return all;
+}
+
+// MultiImpg from arrays: record i belongs to alignment file file_of_record[i]
+// (files in ascending order of id; records keep their relative order). Every
+// file becomes its own sub-index with LOCAL sequence ids assigned by first
+// appearance in that file (query column first, src/paf.rs:140-170); `ids` of
+// the records are the unified ids.
+void *orc_multi_build(const impgx_record *recs, size_t n, const uint32_t *runs, const uint64_t *run_offsets,
+                      const uint64_t *seq_lens, uint32_t n_seqs, const uint32_t *file_of_record, uint32_t n_files,
+                      int bidirectional) {
+  MultiIndex *mi = new MultiIndex();
+  mi->seq_lens.assign(seq_lens, seq_lens + n_seqs);
+  for (uint32_t f = 0; f < n_files; f++) {
+    std::unique_ptr<Index> sub(new Index());
+    std::vector<uint32_t> l2u;
+    std::unordered_map<uint32_t, uint32_t> u2l;
+    auto local = [&](uint32_t u) {
+      auto it = u2l.find(u);
+      if (it != u2l.end()) return it->second;
+      uint32_t id = (uint32_t)l2u.size();
+      u2l.emplace(u, id);
+      l2u.push_back(u);
+      return id;
+    };
+    std::vector<impgx_record> lr;
+    sub->run_offsets.push_back(0);
+    for (size_t i = 0; i < n; i++) {
+      if (file_of_record[i] != f) continue;
+      impgx_record r = recs[i];
+      r.query_id = local(r.query_id);
+      r.target_id = local(r.target_id);
+      lr.push_back(r);
+      sub->runs.insert(sub->runs.end(), runs + run_offsets[i], runs + run_offsets[i + 1]);
+      sub->run_offsets.push_back(sub->runs.size());
+    }
+    for (uint32_t u : l2u) sub->seq_lens.push_back(seq_lens[u]);
+    sub->names.resize(l2u.size());
+    build_trees(*sub, lr.data(), lr.size(), nullptr, bidirectional != 0);
+    for (auto &kv : sub->trees) mi->forest_map[l2u[kv.first]].push_back({f, kv.first});
+    mi->local_to_unified.push_back(std::move(l2u));
+    mi->subs.push_back(std::move(sub));
+  }
+  return mi;
+}
+void orc_multi_free(void *h) { delete (MultiIndex *)h; }
+
+void *orc_multi_query_batch(void *h, const impgx_range *ranges, size_t n, const impgx_params *p, int bed_merge,
+                            uint64_t *row_offsets) {
+  MultiIndex *mi = (MultiIndex *)h;
+  QParams q = to_qparams(p);
+  ResultSet *all = new ResultSet();
+  row_offsets[0] = 0;
+  for (size_t i = 0; i < n; i++) {
+    auto res = perform_query_multi(*mi, ranges[i].target_id, ranges[i].start, ranges[i].end, p->mode, q);
     if (bed_merge) {
       bool any_empty = false;
       for (auto &r : res) any_empty |= r.cigar.empty();

@@ -81,6 +81,7 @@ class Params(C.Structure):
 
 
 MODE_QUERY, MODE_BFS, MODE_DFS = 0, 1, 2
+MODE_MULTI_QUERY, MODE_MULTI_BFS, MODE_MULTI_DFS = 3, 4, 5
 
 
 def make_params(mode=MODE_QUERY, max_depth=2, min_transitive_len=101, min_dist=10, min_output_length=-1,
@@ -125,7 +126,7 @@ def lib():
         L.orc_identity.restype = C.c_double
         L.orc_sorted_ranges_insert.restype = C.c_size_t
         for f in ("orc_index_build", "orc_index_from_paf", "orc_perform_query", "orc_results_from_arrays",
-                  "orc_query_batch"):
+                  "orc_query_batch", "orc_multi_build", "orc_multi_query_batch"):
             getattr(L, f).restype = C.c_void_p
         L.orc_index_num_seqs.restype = C.c_uint32
         L.orc_index_num_records.restype = C.c_size_t
@@ -260,6 +261,41 @@ class Results:
         flat = np.ascontiguousarray(flat, np.uint32)
         return Results(lib().orc_results_from_arrays(C.c_size_t(n), _p(qid), _p(qf), _p(ql), _p(tid), _p(tf), _p(tl),
                                                      _p(off), _p(flat)))
+
+
+class MultiIndex:
+    """The oracle's MultiImpg (reference src/multi_impg.rs): one sub-index per alignment file."""
+
+    def __init__(self, handle):
+        if not handle:
+            raise RuntimeError("oracle multi index build failed")
+        self.h = C.c_void_p(handle)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_multi_free(self.h)
+            self.h = None
+
+    @staticmethod
+    def build(records, runs, run_offsets, seq_lens, file_of_record, n_files, bidirectional=True):
+        records = np.ascontiguousarray(records, dtype=RECORD_DTYPE)
+        runs = np.ascontiguousarray(runs, dtype=np.uint32)
+        run_offsets = np.ascontiguousarray(run_offsets, dtype=np.uint64)
+        seq_lens = np.ascontiguousarray(seq_lens, dtype=np.uint64)
+        fo = np.ascontiguousarray(file_of_record, dtype=np.uint32)
+        assert len(fo) == len(records)
+        if len(runs) == 0:
+            runs = np.zeros(1, np.uint32)
+        return MultiIndex(lib().orc_multi_build(_p(records), C.c_size_t(len(records)), _p(runs), _p(run_offsets),
+                                                _p(seq_lens), C.c_uint32(len(seq_lens)), _p(fo), C.c_uint32(n_files),
+                                                C.c_int(1 if bidirectional else 0)))
+
+    def query_batch(self, ranges, params, bed_merge=False):
+        ranges = np.ascontiguousarray(ranges, dtype=RANGE_DTYPE)
+        offs = np.zeros(len(ranges) + 1, np.uint64)
+        res = Results(lib().orc_multi_query_batch(self.h, _p(ranges), C.c_size_t(len(ranges)), C.byref(params),
+                                                  C.c_int(1 if bed_merge else 0), _p(offs)))
+        return res, offs
 
 
 class Index:
