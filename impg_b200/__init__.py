@@ -39,7 +39,8 @@ class Params(C.Structure):
     _fields_ = [("mode", C.c_uint32), ("max_depth", C.c_uint32), ("min_transitive_len", C.c_int32),
                 ("min_distance_between_ranges", C.c_int32), ("min_output_length", C.c_int32),
                 ("store_cigar", C.c_uint32), ("min_identity", C.c_double), ("subset_mask", C.c_void_p),
-                ("merge_distance", C.c_int32), ("merge_strands", C.c_uint32)]
+                ("merge_distance", C.c_int32), ("merge_strands", C.c_uint32),
+                ("mask_offsets", C.c_void_p), ("mask_ranges", C.c_void_p)]
 
 
 class View(C.Structure):
@@ -66,9 +67,21 @@ class SynthCfg(C.Structure):
                 ("eq_mean", C.c_uint32), ("rev_permille", C.c_uint32), ("seed", C.c_uint64)]
 
 
+def mask_csr(masked_regions, n_seqs):
+    """{seq id: [(start, end), ...]} (sorted, disjoint — a SortedRanges per sequence) -> CSR arrays."""
+    offs = np.zeros(n_seqs + 1, np.uint64)
+    flat = []
+    for s in range(n_seqs):
+        rs = masked_regions.get(s, ())
+        offs[s + 1] = offs[s] + np.uint64(len(rs))
+        for a, b in rs:
+            flat += [a, b]
+    return offs, np.array(flat if flat else [0, 0], dtype=np.int32)
+
+
 def make_params(mode=MODE_QUERY, max_depth=2, min_transitive_len=101, min_distance_between_ranges=10,
                 min_output_length=None, store_cigar=False, min_identity=None, subset_mask=None, merge_distance=0,
-                merge_strands=True):
+                merge_strands=True, masked_regions=None):
     """Defaults are the reference's CLI defaults (src/main.rs:4259-4410)."""
     p = Params()
     p.mode = mode
@@ -86,6 +99,13 @@ def make_params(mode=MODE_QUERY, max_depth=2, min_transitive_len=101, min_distan
         p.subset_mask = None
     p.merge_distance = merge_distance
     p.merge_strands = 1 if merge_strands else 0
+    if masked_regions is not None:  # (offsets, ranges) CSR, see mask_csr
+        mo = np.ascontiguousarray(masked_regions[0], dtype=np.uint64)
+        mr = np.ascontiguousarray(masked_regions[1], dtype=np.int32)
+        p._keep_mask = (mo, mr)
+        p.mask_offsets, p.mask_ranges = mo.ctypes.data, mr.ctypes.data
+    else:
+        p.mask_offsets = p.mask_ranges = None
     return p
 
 
@@ -389,8 +409,9 @@ class MultiImpg:
     def _params(self, params):
         q = Params()
         C.memmove(C.byref(q), C.byref(params), C.sizeof(Params))
-        if hasattr(params, "_keep"):
-            q._keep = params._keep
+        for k in ("_keep", "_keep_mask"):
+            if hasattr(params, k):
+                setattr(q, k, getattr(params, k))
         q.mode = self._MODE.get(params.mode, params.mode)
         return q
 

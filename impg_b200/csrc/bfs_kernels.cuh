@@ -140,10 +140,13 @@ __device__ __forceinline__ uint64_t lower_bound_u64(const uint64_t *a, uint64_t 
 }
 
 // head_scan = exclusive scan of head flags (head_scan[n] = group count)
+// mask_off != nullptr: a (row, sequence) group that has no visited entry yet starts from the
+// masked regions of the sequence (src/impg.rs:2331-2335) instead of an empty list
 __global__ void k_make_groups(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ head,
                               const uint64_t *__restrict__ head_scan, uint64_t n, const uint64_t *__restrict__ n_included,
                               const uint64_t *__restrict__ v_keys, uint64_t v_n, FoldGroup *__restrict__ groups,
-                              uint64_t *__restrict__ list_cap, uint64_t *__restrict__ piece_cap) {
+                              uint64_t *__restrict__ list_cap, uint64_t *__restrict__ piece_cap,
+                              const uint64_t *__restrict__ mask_off) {
   const uint64_t ninc = *n_included;
   for (uint64_t i = gtid(); i < ninc; i += gstride()) {
     if (!head[i]) continue;
@@ -170,7 +173,12 @@ __global__ void k_make_groups(const uint64_t *__restrict__ keys, const uint64_t 
     fg.v_end = (uint32_t)ve;
     fg.list_off = fg.piece_off = 0;
     groups[g] = fg;
-    const uint64_t n0 = ve - vb, h = e - i;
+    uint64_t n0 = ve - vb;
+    const uint64_t h = e - i;
+    if (n0 == 0 && mask_off) {
+      const uint32_t seq = (uint32_t)k;
+      n0 = mask_off[seq + 1] - mask_off[seq];
+    }
     list_cap[g] = n0 + h;
     piece_cap[g] = n0 + 2 * h;
   }
@@ -253,13 +261,16 @@ __global__ void __launch_bounds__(128) k_fold(const FoldGroup *__restrict__ grou
                                               const int32_t *__restrict__ v_end, const int32_t *__restrict__ seq_len,
                                               int32_t min_dist, int32_t min_transitive_len, int2 *__restrict__ lists,
                                               uint32_t *__restrict__ list_len, Frontier *__restrict__ pieces,
-                                              uint32_t *__restrict__ piece_cnt) {
+                                              uint32_t *__restrict__ piece_cnt, const uint64_t *__restrict__ mask_off,
+                                              const int2 *__restrict__ mask_rng) {
   for (uint64_t g = gtid(); g < n_groups; g += gstride()) {
     const FoldGroup fg = groups[g];
     int2 *L = lists + fg.list_off;
     uint32_t m = 0;
-    for (uint32_t v = fg.v_begin; v < fg.v_end; v++) L[m++] = make_int2(v_start[v], v_end[v]);
     const uint32_t row = (uint32_t)(fg.key >> 32), seq = (uint32_t)fg.key;
+    for (uint32_t v = fg.v_begin; v < fg.v_end; v++) L[m++] = make_int2(v_start[v], v_end[v]);
+    if (fg.v_begin == fg.v_end && mask_off)
+      for (uint64_t k = mask_off[seq]; k < mask_off[seq + 1]; k++) L[m++] = mask_rng[k];
     const int32_t slen = seq_len[seq];
     Frontier *P = pieces + fg.piece_off;
     uint32_t np = 0;
@@ -343,6 +354,59 @@ __global__ void k_visited_copy_kept(const uint64_t *__restrict__ v_keys, const i
     o_keys[o] = v_keys[i];
     o_start[o] = v_start[i];
     o_end[o] = v_end[i];
+  }
+}
+
+// ---- seeds under masked_regions: visited[target] starts from the mask, insert(range) returns
+// the unmasked pieces (src/impg.rs:2337-2373); each piece is a result and, if long enough, frontier
+__global__ void k_seed_mask_caps(const impgx_range *__restrict__ ranges, uint32_t n, const uint64_t *__restrict__ mask_off,
+                                 uint64_t *__restrict__ cap) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) {
+    const uint32_t t = ranges[i].target_id;
+    cap[i] = mask_off[t + 1] - mask_off[t] + 1;
+  }
+}
+__global__ void k_seed_masked(const impgx_range *__restrict__ ranges, uint32_t n, const uint64_t *__restrict__ mask_off,
+                              const int2 *__restrict__ mask_rng, const int32_t *__restrict__ seq_len,
+                              const uint64_t *__restrict__ off, int2 *__restrict__ lists, int2 *__restrict__ pieces,
+                              uint32_t *__restrict__ list_len, uint32_t *__restrict__ piece_cnt) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) {
+    const impgx_range r = ranges[i];
+    int2 *L = lists + off[i], *P = pieces + off[i];
+    uint32_t m = 0, np = 0;
+    for (uint64_t k = mask_off[r.target_id]; k < mask_off[r.target_id + 1]; k++) L[m++] = mask_rng[k];
+    ranges_insert(L, m, seq_len[r.target_id], r.start, r.end, [&](int32_t s, int32_t e) { P[np++] = make_int2(s, e); });
+    list_len[i] = m;
+    piece_cnt[i] = np;
+  }
+}
+__global__ void k_seed_masked_compact(const impgx_range *__restrict__ ranges, uint32_t n, const uint64_t *__restrict__ off,
+                                      const int2 *__restrict__ lists, const int2 *__restrict__ pieces,
+                                      const uint32_t *__restrict__ list_len, const uint32_t *__restrict__ piece_cnt,
+                                      const uint64_t *__restrict__ list_scan, const uint64_t *__restrict__ piece_scan,
+                                      uint64_t *__restrict__ v_keys, int32_t *__restrict__ v_start,
+                                      int32_t *__restrict__ v_end, Hit *__restrict__ seed_hits,
+                                      Frontier *__restrict__ seed_fr) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) {
+    const uint32_t t = ranges[i].target_id;
+    const int2 *L = lists + off[i], *P = pieces + off[i];
+    for (uint32_t k = 0; k < list_len[i]; k++) {
+      const uint64_t d = list_scan[i] + k;
+      v_keys[d] = ((uint64_t)i << 32) | t;
+      v_start[d] = L[k].x;
+      v_end[d] = L[k].y;
+    }
+    for (uint32_t k = 0; k < piece_cnt[i]; k++) {
+      const uint64_t d = piece_scan[i] + k;
+      seed_hits[d] = Hit{(uint32_t)i, t, P[k].x, P[k].y, t, P[k].x, P[k].y, 0u};
+      seed_fr[d] = Frontier{(uint32_t)i, t, P[k].x, P[k].y};
+    }
+  }
+}
+__global__ void k_fill_seed_slices(uint32_t *__restrict__ entry, CigarSlice *__restrict__ slices, uint64_t n) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) {
+    entry[i] = INVALID_ID;
+    slices[i] = CigarSlice{0, 1, 0, 0};
   }
 }
 

@@ -353,6 +353,7 @@ struct LevelHits {
   DBuf<uint32_t> entry;    // entry index per hit (CIGAR emission), only with store_cigar
   DBuf<CigarSlice> slices;
   uint64_t n = 0;
+  bool seeds = false;      // the self-interval pieces of a masked query: never filtered by min_output_length
 };
 
 // Collector of the direct BED path: boxes of every result of the batch.
@@ -421,6 +422,10 @@ class Runner {
   // MultiImpg modes: 0 = Impg order (frontier index, coitrees visit rank); 1 / 2 = the 5-key order of
   // src/multi_impg.rs:582-592 with the transitive / query drop rule (k_multi_drop)
   int multi_order_ = 0;
+  // masked_regions (CSR over all sequences) of the transitive modes, resident for the batch
+  DBuf<uint64_t> d_mask_off_;
+  DBuf<int2> d_mask_rng_;
+  bool masked_ = false;
 
   void prepare(const impgx_range *d_ranges, uint32_t n_rows);
   void lift_core(const DBuf<Frontier> &fr, uint64_t nF, bool closed, bool clip,
@@ -662,7 +667,8 @@ void Runner::fold(const LevelHits &lvl, uint32_t n_rows, Visited &V, DBuf<Fronti
   CUDA_CHECK(cudaMemsetAsync(list_off.get() + G, 0, 8, s_));
   CUDA_CHECK(cudaMemsetAsync(piece_off.get() + G, 0, 8, s_));
   LAUNCH(k_make_groups, grid_threads(n), 256, s_, keys.get(), head.get(), head_scan.get(), n, n_inc.get(),
-         V.keys.get(), V.n, groups.get(), list_off.get(), piece_off.get());
+         V.keys.get(), V.n, groups.get(), list_off.get(), piece_off.get(),
+         masked_ ? (const uint64_t *)d_mask_off_.get() : nullptr);
   exclusive_scan_u64(list_off.get(), G + 1, sc_, s_);
   exclusive_scan_u64(piece_off.get(), G + 1, sc_, s_);
   ctx.launches += 4;
@@ -675,7 +681,8 @@ void Runner::fold(const LevelHits &lvl, uint32_t n_rows, Visited &V, DBuf<Fronti
   DBuf<uint32_t> list_len(G, ar_), piece_cnt(G, ar_);
   LAUNCH(k_fold, grid_threads(G, 128, 16), 128, s_, groups.get(), G, sorted.get(), V.start.get(), V.end.get(),
          ix_.seq_len, p_.min_distance_between_ranges, p_.min_transitive_len, lists.get(), list_len.get(), pieces.get(),
-         piece_cnt.get());
+         piece_cnt.get(), masked_ ? (const uint64_t *)d_mask_off_.get() : nullptr,
+         masked_ ? (const int2 *)d_mask_rng_.get() : nullptr);
 
   // ---- new visited set = untouched old entries + the groups' lists, re-sorted
   DBuf<uint64_t> lo(G + 1, ar_), po(G + 1, ar_);
@@ -771,6 +778,8 @@ void Runner::assemble(const impgx_range *d_ranges, uint32_t n_rows, std::vector<
   // Impg::query's caller filters every result incl. the self interval by
   // min_output_length (src/main.rs:11686-11691); BFS never filters the seed.
   LAUNCH(k_seed_counts, grid_threads(n_rows), 256, s_, d_ranges, n_rows, min_out, query_mode ? 1 : 0, seed_cnt.get());
+  // masked query: the self intervals are the unmasked pieces, carried as a level of their own
+  if (masked_) CUDA_CHECK(cudaMemsetAsync(seed_cnt.get(), 0, (size_t)n_rows * 4, s_));
   CUDA_CHECK(cudaMemcpyAsync(total_cnt.get(), seed_cnt.get(), n_rows * 4, cudaMemcpyDeviceToDevice, s_));
 
   struct PerLevel {
@@ -786,8 +795,8 @@ void Runner::assemble(const impgx_range *d_ranges, uint32_t n_rows, std::vector<
     pl[l].pass.alloc(n + 1, ar_);
     pl[l].pass_scan.alloc(n + 1, ar_);
     CUDA_CHECK(cudaMemsetAsync(pl[l].pass.get() + n, 0, 8, s_));
-    LAUNCH(k_level_pass, grid_threads(n), 256, s_, levels[l].hits.get(), n, min_out, pl[l].pass.get(),
-           pl[l].row_cnt.get());
+    LAUNCH(k_level_pass, grid_threads(n), 256, s_, levels[l].hits.get(), n, levels[l].seeds ? -1 : min_out,
+           pl[l].pass.get(), pl[l].row_cnt.get());
     CUDA_CHECK(cudaMemcpyAsync(pl[l].pass_scan.get(), pl[l].pass.get(), (n + 1) * 8, cudaMemcpyDeviceToDevice, s_));
     exclusive_scan_u64(pl[l].pass_scan.get(), n + 1, sc_, s_);
     pl[l].row_start.alloc(n_rows + 1, ar_);
@@ -865,6 +874,26 @@ void Runner::prepare(const impgx_range *d_ranges, uint32_t n_rows) {
     d_row_target_.alloc(n_rows, ar_);
     LAUNCH(k_row_targets, grid_threads(n_rows), 256, s_, d_ranges, n_rows, d_row_target_.get());
   }
+  const bool transitive = p_.mode != IMPGX_MODE_QUERY && p_.mode != IMPGX_MODE_MULTI_QUERY;
+  masked_ = transitive && p_.mask_offsets != nullptr;
+  if (masked_) {
+    REQUIRE(p_.mask_ranges || p_.mask_offsets[ix_.n_seqs] == 0, IMPGX_E_INVALID, "mask_ranges is NULL");
+    const uint64_t nm = p_.mask_offsets[ix_.n_seqs];
+    for (uint32_t q = 0; q < ix_.n_seqs; q++) {
+      REQUIRE(p_.mask_offsets[q] <= p_.mask_offsets[q + 1], IMPGX_E_INVALID, "mask_offsets not monotone");
+      for (uint64_t k = p_.mask_offsets[q]; k < p_.mask_offsets[q + 1]; k++) {
+        const int32_t a = p_.mask_ranges[2 * k], b = p_.mask_ranges[2 * k + 1];
+        REQUIRE(a <= b && (k == p_.mask_offsets[q] || p_.mask_ranges[2 * k - 1] < a), IMPGX_E_INVALID,
+                "masked regions of a sequence must be sorted and disjoint (a SortedRanges)");
+      }
+    }
+    d_mask_off_.alloc((uint64_t)ix_.n_seqs + 1, ar_);
+    d_mask_rng_.alloc(std::max<uint64_t>(nm, 1), ar_);
+    CUDA_CHECK(cudaMemcpyAsync(d_mask_off_.get(), p_.mask_offsets, ((size_t)ix_.n_seqs + 1) * 8, cudaMemcpyHostToDevice, s_));
+    if (nm) CUDA_CHECK(cudaMemcpyAsync(d_mask_rng_.get(), p_.mask_ranges, nm * 8, cudaMemcpyHostToDevice, s_));
+    CUDA_CHECK(cudaStreamSynchronize(s_));
+    ctx.h2d_bytes += ((size_t)ix_.n_seqs + 1) * 8 + nm * 8;
+  }
 }
 
 void Runner::run(const impgx_range *d_ranges, uint32_t n_rows, bool bed, BatchOut &out) {
@@ -907,12 +936,58 @@ void Runner::run(const impgx_range *d_ranges, uint32_t n_rows, bool bed, BatchOu
     // itself (bounds were validated), which is output and, if long enough,
     // becomes the level-0 frontier (src/impg.rs:2337-2373)
     Visited V;
-    V.keys.alloc(n_rows, ar_);
-    V.start.alloc(n_rows, ar_);
-    V.end.alloc(n_rows, ar_);
-    V.n = n_rows;
-    LAUNCH(k_seed_visited, grid_threads(n_rows), 256, s_, d_ranges, n_rows, V.keys.get(), V.start.get(), V.end.get());
-    if (p_.min_transitive_len > 0) {
+    if (masked_) {
+      // visited[target] = mask[target] + range; the unmasked pieces are the self intervals (a level of
+      // their own, first) and the level-0 frontier
+      DBuf<uint64_t> off((uint64_t)n_rows + 1, ar_);
+      CUDA_CHECK(cudaMemsetAsync(off.get() + n_rows, 0, 8, s_));
+      LAUNCH(k_seed_mask_caps, grid_threads(n_rows), 256, s_, d_ranges, n_rows, d_mask_off_.get(), off.get());
+      exclusive_scan_u64(off.get(), (uint64_t)n_rows + 1, sc_, s_);
+      ctx.launches += 2;
+      const uint64_t cap = read_u64(off.get() + n_rows, s_, ctx);
+      DBuf<int2> lists(cap, ar_), pieces(cap, ar_);
+      DBuf<uint32_t> list_len(n_rows, ar_), piece_cnt(n_rows, ar_);
+      LAUNCH(k_seed_masked, grid_threads(n_rows), 256, s_, d_ranges, n_rows, d_mask_off_.get(), d_mask_rng_.get(),
+             ix_.seq_len, off.get(), lists.get(), pieces.get(), list_len.get(), piece_cnt.get());
+      DBuf<uint64_t> ls((uint64_t)n_rows + 1, ar_), ps((uint64_t)n_rows + 1, ar_);
+      CUDA_CHECK(cudaMemsetAsync(ls.get() + n_rows, 0, 8, s_));
+      CUDA_CHECK(cudaMemsetAsync(ps.get() + n_rows, 0, 8, s_));
+      LAUNCH(k_u32_to_u64, grid_threads(n_rows), 256, s_, list_len.get(), (uint64_t)n_rows, ls.get());
+      LAUNCH(k_u32_to_u64, grid_threads(n_rows), 256, s_, piece_cnt.get(), (uint64_t)n_rows, ps.get());
+      exclusive_scan_u64(ls.get(), (uint64_t)n_rows + 1, sc_, s_);
+      exclusive_scan_u64(ps.get(), (uint64_t)n_rows + 1, sc_, s_);
+      ctx.launches += 4;
+      const uint64_t nl = read_u64(ls.get() + n_rows, s_, ctx), np = read_u64(ps.get() + n_rows, s_, ctx);
+      V.keys.alloc(nl, ar_);
+      V.start.alloc(nl, ar_);
+      V.end.alloc(nl, ar_);
+      V.n = nl;
+      levels.emplace_back();
+      LevelHits &sl = levels.back();
+      sl.seeds = true;
+      sl.n = np;
+      sl.hits.alloc(np, ar_);
+      if (p_.store_cigar) {
+        sl.entry.alloc(np, ar_);
+        sl.slices.alloc(np, ar_);
+        if (np) LAUNCH(k_fill_seed_slices, grid_threads(np), 256, s_, sl.entry.get(), sl.slices.get(), np);
+      }
+      DBuf<Frontier> f2(np, ar_);
+      LAUNCH(k_seed_masked_compact, grid_threads(n_rows), 256, s_, d_ranges, n_rows, off.get(), lists.get(), pieces.get(),
+             list_len.get(), piece_cnt.get(), ls.get(), ps.get(), V.keys.get(), V.start.get(), V.end.get(),
+             sl.hits.get(), f2.get());
+      CUDA_CHECK(cudaStreamSynchronize(s_));
+      fr = std::move(f2);
+      nF = np;
+      prior += np;
+    } else {
+      V.keys.alloc(n_rows, ar_);
+      V.start.alloc(n_rows, ar_);
+      V.end.alloc(n_rows, ar_);
+      V.n = n_rows;
+      LAUNCH(k_seed_visited, grid_threads(n_rows), 256, s_, d_ranges, n_rows, V.keys.get(), V.start.get(), V.end.get());
+    }
+    if (p_.min_transitive_len > 0 && nF > 0) {
       // drop rows shorter than min_transitive_len from the frontier
       DBuf<uint64_t> flag(nF + 1, ar_), scan(nF + 1, ar_);
       CUDA_CHECK(cudaMemsetAsync(flag.get() + nF, 0, 8, s_));
@@ -956,13 +1031,16 @@ void Runner::run(const impgx_range *d_ranges, uint32_t n_rows, bool bed, BatchOu
       sink.n = sink.prefix;
     }
     // seeds, then the levels that were ordered for the fold (their index is their ordinal)
-    LAUNCH(k_boxes_from_seeds, grid_threads(n_rows), 256, s_, d_ranges, n_rows, p_.min_output_length,
-           query_mode ? 1 : 0, sink.boxes.get(), sink.counters.get(), (const uint32_t *)nullptr, 0u);
+    if (masked_)  // the self intervals are the seed level below; the per-row seed slots stay invalid
+      CUDA_CHECK(cudaMemsetAsync(sink.boxes.get(), 0, (size_t)n_rows * sizeof(BoxD), s_));
+    else
+      LAUNCH(k_boxes_from_seeds, grid_threads(n_rows), 256, s_, d_ranges, n_rows, p_.min_output_length,
+             query_mode ? 1 : 0, sink.boxes.get(), sink.counters.get(), (const uint32_t *)nullptr, 0u);
     uint64_t off = n_rows;
     for (size_t l = 0; l < levels.size(); l++) {
       if (!levels[l].n) continue;
       LAUNCH(k_boxes_from_sorted_level, grid_threads(levels[l].n), 256, s_, levels[l].hits.get(), levels[l].n,
-             (uint32_t)l + 1, p_.min_output_length, sink.boxes.get() + off, sink.counters.get());
+             (uint32_t)l + 1, levels[l].seeds ? -1 : p_.min_output_length, sink.boxes.get() + off, sink.counters.get());
       off += levels[l].n;
     }
     bed_merge_direct(sink, n_rows, out);
@@ -1453,6 +1531,7 @@ void Runner::run_sharded(const impgx_range *d_ranges, uint32_t n_rows, BatchOut 
   REQUIRE(p_.mode == IMPGX_MODE_QUERY || p_.mode == IMPGX_MODE_BFS, IMPGX_E_UNSUPPORTED,
           "the sharded index runs Impg::query and the transitive BFS (DFS: use an unsharded index)");
   REQUIRE(!p_.store_cigar, IMPGX_E_INVALID, "BED output carries no CIGAR (src/main.rs:7447)");
+  REQUIRE(!p_.mask_offsets, IMPGX_E_UNSUPPORTED, "masked_regions need an unsharded index");
   REQUIRE(n_rows < (1u << 26), IMPGX_E_INVALID, "more than 2^26 rows in one batch; lower IMPGX_ROWS_PER_BATCH");
   Comm &cm = *comm_;
   const int N = cm.size();

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define IMPGX_ABI_VERSION 2
+#define IMPGX_ABI_VERSION 3
 
 typedef enum impgx_status {
   IMPGX_OK = 0,
@@ -100,6 +100,15 @@ typedef struct impgx_params {
   const uint8_t *subset_mask;          /* per sequence id, 1 = keep; NULL = no filter */
   int32_t merge_distance;              /* -d; -1 = --no-merge (BED entry point only) */
   uint32_t merge_strands;              /* !--consider-strandness (BED entry point only) */
+  /* masked_regions of the transitive queries (src/impg.rs:2331-2340; partition passes the
+   * regions already assigned, src/commands/partition.rs:254-270, :359-391) as CSR over ALL
+   * sequences: sequence s owns the sorted, disjoint [start, end) pairs
+   * mask_ranges[2*mask_offsets[s] .. 2*mask_offsets[s+1]). The visited set of every row starts
+   * from it, so only the unmasked pieces of a row's range are output and walked. NULL = None.
+   * (A sequence missing from the reference's map gets length 0 there, src/impg.rs:2047-2053;
+   * the CSR form always carries every sequence, as partition builds its map.) HOST pointers. */
+  const uint64_t *mask_offsets;        /* n_seqs + 1, or NULL */
+  const int32_t *mask_ranges;          /* 2 * mask_offsets[n_seqs] */
 } impgx_params;
 
 typedef struct impgx_index impgx_index;

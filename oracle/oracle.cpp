@@ -539,7 +539,20 @@ struct QParams {
   bool store_cigar;
   double min_identity;  // NaN none
   const uint8_t *subset_mask;
+  // masked_regions as CSR over all sequences (every sequence present, min_distance 0,
+  // as src/commands/partition.rs:254-270 builds the map); nullptr = None
+  const uint64_t *mask_offsets = nullptr;
+  const int32_t *mask_ranges = nullptr;
 };
+
+// visited_entry (src/impg.rs:2041-2055) / the clone of masked_regions (:2331-2335)
+SortedRanges initial_ranges(const std::vector<uint64_t> &seq_lens, const QParams &p, uint32_t id) {
+  SortedRanges r((int32_t)seq_lens[id], 0);
+  if (p.mask_offsets)
+    for (uint64_t k = p.mask_offsets[id]; k < p.mask_offsets[id + 1]; k++)
+      r.ranges.push_back({p.mask_ranges[2 * k], p.mask_ranges[2 * k + 1]});
+  return r;
+}
 
 // src/impg.rs:1852-1928
 std::vector<Result> query(const Index &idx, uint32_t target_id, int32_t rs, int32_t re,
@@ -574,8 +587,7 @@ void consider_for_expansion(const Index &idx, std::map<uint32_t, SortedRanges> &
                             uint32_t query_id, int32_t aq_start, int32_t aq_end,
                             const QParams &p, bool short_circuit, PushPiece &&push) {
   auto it = visited.find(query_id);
-  if (it == visited.end())
-    it = visited.emplace(query_id, SortedRanges((int32_t)idx.seq_lens[query_id], 0)).first;
+  if (it == visited.end()) it = visited.emplace(query_id, initial_ranges(idx.seq_lens, p, query_id)).first;
   SortedRanges &ranges = it->second;
   bool should_add = true;
   if (p.min_distance_between_ranges > 0) {
@@ -625,7 +637,7 @@ void stab_range(const Index &idx, uint32_t original_target, uint32_t cur_id, int
 std::vector<Result> query_transitive_bfs(const Index &idx, uint32_t target_id, int32_t rs, int32_t re,
                                          const QParams &p, int threads) {
   std::map<uint32_t, SortedRanges> visited;
-  auto vit = visited.emplace(target_id, SortedRanges((int32_t)idx.seq_lens[target_id], 0)).first;
+  auto vit = visited.emplace(target_id, initial_ranges(idx.seq_lens, p, target_id)).first;
   auto filtered = vit->second.insert({rs, re});
   std::vector<Result> results;
   for (auto &f : filtered) {
@@ -692,7 +704,7 @@ std::vector<Result> query_transitive_bfs(const Index &idx, uint32_t target_id, i
 std::vector<Result> query_transitive_dfs(const Index &idx, uint32_t target_id, int32_t rs, int32_t re,
                                          const QParams &p) {
   std::map<uint32_t, SortedRanges> visited;
-  auto vit = visited.emplace(target_id, SortedRanges((int32_t)idx.seq_lens[target_id], 0)).first;
+  auto vit = visited.emplace(target_id, initial_ranges(idx.seq_lens, p, target_id)).first;
   auto filtered = vit->second.insert({rs, re});
   std::vector<Result> results;
   struct Item {
@@ -835,7 +847,7 @@ std::vector<Result> multi_transitive_query(const MultiIndex &mi, uint32_t target
   Index lens_only;  // consider_for_expansion only needs the unified lengths
   lens_only.seq_lens = mi.seq_lens;
   std::map<uint32_t, SortedRanges> visited;
-  auto vit = visited.emplace(target_id, SortedRanges((int32_t)mi.seq_lens[target_id], 0)).first;
+  auto vit = visited.emplace(target_id, initial_ranges(mi.seq_lens, p, target_id)).first;
   auto filtered = vit->second.insert({rs, re});
   std::vector<Result> results;
   struct Item {
@@ -1703,6 +1715,8 @@ static QParams to_qparams(const impgx_params *p) {
   q.store_cigar = p->store_cigar != 0;
   q.min_identity = p->min_identity;
   q.subset_mask = p->subset_mask;
+  q.mask_offsets = p->mask_offsets;
+  q.mask_ranges = p->mask_ranges;
   return q;
 }
 

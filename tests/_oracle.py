@@ -77,6 +77,8 @@ class Params(C.Structure):
         ("subset_mask", C.c_void_p),
         ("merge_distance", C.c_int32),
         ("merge_strands", C.c_uint32),
+        ("mask_offsets", C.c_void_p),
+        ("mask_ranges", C.c_void_p),
     ]
 
 
@@ -86,7 +88,7 @@ MODE_MULTI_QUERY, MODE_MULTI_BFS, MODE_MULTI_DFS = 3, 4, 5
 
 def make_params(mode=MODE_QUERY, max_depth=2, min_transitive_len=101, min_dist=10, min_output_length=-1,
                 store_cigar=False, min_identity=float("nan"), subset_mask=None, merge_distance=0,
-                merge_strands=True):
+                merge_strands=True, masked_regions=None):
     p = Params()
     p.mode = mode
     p.max_depth = max_depth
@@ -103,6 +105,13 @@ def make_params(mode=MODE_QUERY, max_depth=2, min_transitive_len=101, min_dist=1
         p.subset_mask = None
     p.merge_distance = merge_distance
     p.merge_strands = 1 if merge_strands else 0
+    if masked_regions is not None:
+        mo = np.ascontiguousarray(masked_regions[0], dtype=np.uint64)
+        mr = np.ascontiguousarray(masked_regions[1], dtype=np.int32)
+        p._keep_mask = (mo, mr)
+        p.mask_offsets, p.mask_ranges = mo.ctypes.data, mr.ctypes.data
+    else:
+        p.mask_offsets = p.mask_ranges = None
     return p
 
 

@@ -150,7 +150,8 @@ def params_pair(**kw):
                       min_transitive_len=kw.get("min_transitive_len", 101), min_dist=kw.get("min_dist", 10),
                       min_output_length=kw.get("min_output_length", -1), store_cigar=kw.get("store_cigar", False),
                       min_identity=kw.get("min_identity", float("nan")), subset_mask=kw.get("subset_mask"),
-                      merge_distance=kw.get("merge_distance", 0), merge_strands=kw.get("merge_strands", True))
+                      merge_distance=kw.get("merge_distance", 0), merge_strands=kw.get("merge_strands", True),
+                      masked_regions=kw.get("masked_regions"))
     mol = kw.get("min_output_length", -1)
     mi = kw.get("min_identity", float("nan"))
     g = ix.make_params(mode=kw.get("mode", 0), max_depth=kw.get("max_depth", 2),
@@ -158,7 +159,8 @@ def params_pair(**kw):
                        min_distance_between_ranges=kw.get("min_dist", 10),
                        min_output_length=None if mol < 0 else mol, store_cigar=kw.get("store_cigar", False),
                        min_identity=None if mi != mi else mi, subset_mask=kw.get("subset_mask"),
-                       merge_distance=kw.get("merge_distance", 0), merge_strands=kw.get("merge_strands", True))
+                       merge_distance=kw.get("merge_distance", 0), merge_strands=kw.get("merge_strands", True),
+                       masked_regions=kw.get("masked_regions"))
     return o, g
 
 
@@ -229,6 +231,52 @@ def test_bed_merge(small, mode, depth, d, merge_strands):
     cfg, orc, gpu, bed = small
     compare_bed(orc, gpu, bed[:150], *params_pair(mode=mode, max_depth=depth, merge_distance=d,
                                                    merge_strands=merge_strands))
+
+
+def random_mask(rng, n_seqs, seq_len, density):
+    """A SortedRanges per sequence: sorted, disjoint, non-touching [start, end) pairs."""
+    regions = {}
+    for s in range(n_seqs):
+        pos, out = int(rng.integers(0, 3000)), []
+        while pos < seq_len and rng.random() < density:
+            ln = int(rng.integers(50, 6000))
+            out.append((pos, min(pos + ln, seq_len)))
+            pos += ln + int(rng.integers(1, 9000))
+        regions[s] = out
+    return ix.mask_csr(regions, n_seqs)
+
+
+@pytest.mark.parametrize("mode", [1, 2, 4, 5])
+def test_masked_regions(small, mode):
+    """masked_regions of the transitive queries (src/impg.rs:2331-2373; what partition passes,
+    src/commands/partition.rs:359-391): the visited sets start from the mask, the self interval
+    becomes the unmasked pieces of the range. BFS, DFS and both MultiImpg walks."""
+    cfg, orc, gpu, bed = small
+    if mode >= 3:  # the MultiImpg walks are checked against the oracle's MultiImpg (one sub-index)
+        recs, runs, offs, lens, names = ix.synth_generate(cfg)
+        orc = O.MultiIndex.build(recs, runs, offs, lens, np.zeros(len(recs), np.uint32), 1)
+    rng = np.random.default_rng(100 + mode)
+    b = bed[:80]
+    for density, depth in ((0.5, 2), (0.9, 3), (0.0, 2), (0.97, 0)):
+        mask = random_mask(rng, 12, 60000, density)
+        compare_raw(orc, gpu, b, *params_pair(mode=mode, max_depth=depth, masked_regions=mask))
+    mask = random_mask(rng, 12, 60000, 0.8)
+    compare_raw(orc, gpu, b, *params_pair(mode=mode, max_depth=2, masked_regions=mask, store_cigar=True), check_cigar=True)
+    compare_raw(orc, gpu, b, *params_pair(mode=mode, max_depth=3, masked_regions=mask, min_output_length=2500,
+                                           min_transitive_len=0, min_dist=0))
+    compare_bed(orc, gpu, b, *params_pair(mode=mode, max_depth=2, masked_regions=mask, merge_distance=1000))
+    compare_bed(orc, gpu, b, *params_pair(mode=mode, max_depth=2, masked_regions=mask, merge_distance=0,
+                                           merge_strands=False))
+    # a mask that covers every row entirely: nothing is output
+    full = ix.mask_csr({s: [(0, 60000)] for s in range(12)}, 12)
+    res = gpu.query_batch(b, params_pair(mode=mode, masked_regions=full)[1])
+    assert res.n_results == 0
+    compare_raw(orc, gpu, b, *params_pair(mode=mode, masked_regions=full))
+    # malformed masks are rejected
+    bad = (np.array([0, 2] + [2] * 11, np.uint64), np.array([10, 50, 40, 90], np.int32))
+    with pytest.raises(ix.ImpgxError) as e:
+        gpu.query_batch(b, params_pair(mode=mode, masked_regions=bad)[1])
+    assert e.value.code == ix.E_INVALID
 
 
 def test_unidirectional_and_self_alignments():
