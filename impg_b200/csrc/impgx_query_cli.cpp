@@ -43,7 +43,8 @@ static int32_t parse_distance(const std::string &s) {
 }
 
 int main(int argc, char **argv) {
-  std::string paf, bed_path, range_text, out_format = "auto", subset_path;
+  std::vector<std::string> pafs;
+  std::string bed_path, range_text, out_format = "auto", subset_path, index_mode = "auto";
   bool transitive = false, dfs = false, unidirectional = false, consider_strand = false, no_merge = false, have_d = false;
   int32_t d = 0, min_transitive_len = 101, min_dist = 10, min_out = -1;
   uint32_t max_depth = 2;
@@ -55,7 +56,19 @@ int main(int argc, char **argv) {
       if (i + 1 >= argc) die("missing value for " + a);
       return argv[++i];
     };
-    if (a == "-a" || a == "--alignment-files") paf = val();
+    if (a == "-a" || a == "--alignment-files") {
+      pafs.push_back(val());
+      while (i + 1 < argc && argv[i + 1][0] != '-') pafs.push_back(argv[++i]);  // -a takes one or more files
+    } else if (a == "--alignment-list") {  // one path per line (src/main.rs: resolve_alignment_files)
+      const std::string lp = val();
+      std::ifstream f(lp);
+      if (!f.good()) die("Failed to read alignment list '" + lp + "'");
+      std::string line;
+      while (std::getline(f, line)) {
+        while (!line.empty() && isspace((unsigned char)line.back())) line.pop_back();
+        if (!line.empty() && line[0] != '#') pafs.push_back(line);
+      }
+    } else if (a == "--index-mode") index_mode = val();
     else if (a == "-b" || a == "--target-bed") bed_path = val();
     else if (a == "-r" || a == "--target-range") range_text = val();
     else if (a == "-x" || a == "--transitive") transitive = true;
@@ -73,14 +86,21 @@ int main(int argc, char **argv) {
     else if (a == "--subset-sequence-list") subset_path = val();
     else if (a == "--device") device = atoi(val().c_str());
     else if (a == "-h" || a == "--help") {
-      printf("usage: impgx-query -a X.paf (-b BED | -r seq:start-end) [-x] [-m N] (-d D | --no-merge) [-l L]\n"
+      printf("usage: impgx-query (-a X.paf [Y.paf ...] | --alignment-list FILE) [--index-mode auto|single|per-file]\n"
+             "       (-b BED | -r seq:start-end) [-x] [-m N] (-d D | --no-merge) [-l L]\n"
              "       [-o auto|bed|bedpe|paf] [--min-transitive-len N] [--min-distance-between-ranges N]\n"
              "       [--transitive-dfs] [--unidirectional] [--consider-strandness] [--min-result-identity F]\n"
              "       [--subset-sequence-list FILE] [--device N]\n");
       return 0;
     } else die("unsupported option '" + a + "' (only the PAF -> BED/BEDPE/PAF query path is implemented)");
   }
-  if (paf.empty()) die("-a/--alignment-files is required");
+  if (pafs.empty()) die("-a/--alignment-files or --alignment-list is required");
+  if (index_mode != "auto" && index_mode != "single" && index_mode != "per-file")
+    die("invalid --index-mode '" + index_mode + "' (auto, single, per-file)");
+  // the reference switches to MultiImpg (one sub-index per file, src/multi_impg.rs) with
+  // --index-mode per-file or, in auto mode, from 100 alignment files on; its result order and
+  // transitive walk differ from Impg's, which the IMPGX_MODE_MULTI_* modes reproduce
+  const bool multi = index_mode == "per-file" || (index_mode == "auto" && pafs.size() >= 100);
   if (bed_path.empty() == range_text.empty()) die("exactly one of -r/--target-range and -b/--target-bed is required");
   if (have_d && no_merge) die("-d and --no-merge are mutually exclusive");
   if (!have_d && !no_merge)
@@ -91,7 +111,11 @@ int main(int argc, char **argv) {
     die("output format '" + out_format + "' is outside the accelerated path (bed, bedpe, paf)");
 
   impgx_index *idx = nullptr;
-  check(impgx_index_from_paf(paf.c_str(), unidirectional ? 0 : 1, device, &idx));
+  {
+    std::vector<const char *> pp;
+    for (auto &f : pafs) pp.push_back(f.c_str());
+    check(impgx_index_from_pafs(pp.data(), pp.size(), unidirectional ? 0 : 1, device, &idx));
+  }
 
   // rows
   std::vector<impgx_range> rows;
@@ -150,6 +174,7 @@ int main(int argc, char **argv) {
   impgx_params p;
   memset(&p, 0, sizeof p);
   p.mode = transitive ? (dfs ? IMPGX_MODE_DFS : IMPGX_MODE_BFS) : IMPGX_MODE_QUERY;
+  if (multi) p.mode = transitive ? (dfs ? IMPGX_MODE_MULTI_DFS : IMPGX_MODE_MULTI_BFS) : IMPGX_MODE_MULTI_QUERY;
   p.max_depth = max_depth;
   p.min_transitive_len = min_transitive_len;
   p.min_distance_between_ranges = min_dist;
