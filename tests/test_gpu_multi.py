@@ -142,3 +142,36 @@ def test_multi_from_paf_files(tmp_path):
     for mode in (O.MODE_MULTI_QUERY, O.MODE_MULTI_BFS, O.MODE_MULTI_DFS):
         compare(orc, gpu.idx, ranges, mode, max_depth=0, min_transitive_len=0, store_cigar=True, check_cigar=True)
         compare(orc, gpu.idx, ranges, mode, max_depth=2, merge_distance=0, bed=True)
+
+
+def test_cli_per_file_index_mode(tmp_path):
+    """impgx-query with several alignment files and --index-mode per-file (the reference's MultiImpg
+    switch): BED text equals the oracle's MultiImpg + writers."""
+    import subprocess
+    files = [os.path.join(GOLD, f) for f in ("easy_shared_flank.paf", "duplicated_repeat.paf")]
+    cat = tmp_path / "cat.paf"
+    sizes = []
+    with open(cat, "w") as out:
+        for f in files:
+            lines = [l for l in open(f).read().splitlines() if l.strip()]
+            sizes.append(len(lines))
+            out.write("\n".join(lines) + "\n")
+    whole = O.Index.from_paf(str(cat))
+    recs, offs, runs, lens, names = whole.export()
+    orc = O.MultiIndex.build(recs, runs, offs, lens, np.repeat(np.arange(2, dtype=np.uint32), sizes), 2)
+    bed = tmp_path / "q.bed"
+    rows = [(names[s], 0, int(lens[s])) for s in range(len(names))]
+    bed.write_text("".join(f"{a}\t{b}\t{c}\n" for a, b, c in rows))
+    cli = os.path.join(os.path.dirname(GOLD), "..", "impg_b200", "impgx-query")
+    got = subprocess.run([cli, "-a", *files, "--index-mode", "per-file", "-b", str(bed), "-x", "-m", "2", "-d", "100",
+                          "--min-transitive-len", "0", "-o", "bed"], capture_output=True, text=True, check=True).stdout
+    p = O.make_params(mode=O.MODE_MULTI_BFS, max_depth=2, min_transitive_len=0, merge_distance=100)
+    ranges = np.array([(s, 0, int(lens[s])) for s in range(len(names))], ix.RANGE_DTYPE)
+    res, offs2 = orc.query_batch(ranges, p, bed_merge=True)
+    c = res.columns()
+    want = ""
+    for r, (a, b, e) in enumerate(rows):
+        for i in range(int(offs2[r]), int(offs2[r + 1])):
+            f, l = int(c["q_first"][i]), int(c["q_last"][i])
+            want += f"{names[int(c['q_id'][i])]}\t{min(f, l)}\t{max(f, l)}\t{a}:{b}-{e}\t.\t{'+' if f <= l else '-'}\n"
+    assert got == want
