@@ -358,6 +358,12 @@ struct LevelHits {
 
 // Collector of the direct BED path: boxes of every result of the batch.
 struct BedSink {
+  // the raw hits of the last hop stay as the liftover wrote them (BoxSrc, merge_kernels.cuh)
+  DBuf<Hit> raw_hits;
+  DBuf<LiftTask> raw_tasks;
+  DBuf<uint32_t> raw_orig;
+  uint64_t n_raw = 0;
+  bool raw_has_orig = false;
   DBuf<BoxD> boxes;
   DBuf<unsigned long long> counters;  // [0] valid boxes, [1] stage-A roots
   uint64_t prefix = 0;                // slots reserved for the seeds and the earlier (sorted) levels
@@ -435,7 +441,8 @@ class Runner {
   void stage_a(const BoxD *boxes, uint64_t nB, uint64_t nv, DBuf<BoxD> &acc, DBuf<uint64_t> &is_root);
   void stage_b(const BoxD *acc, const uint64_t *is_root, uint64_t n, unsigned long long *d_root_counter,
                uint32_t n_rows, BatchOut &out, uint32_t *row_cnt);
-  bool merge_fused(const BoxD *boxes, uint64_t nB, uint64_t nv, BatchOut &out, uint32_t *row_cnt);
+  bool merge_fused(const BoxSrc &src, uint64_t nB, BatchOut &out, uint32_t *row_cnt);
+  void materialize_boxes(BedSink &sink);
   void route_boxes(const BoxD *boxes, uint64_t nB, DBuf<BoxD> &recv, uint64_t &n_recv);
   void route_hits(const Lifted &L, const uint32_t *gmap, LevelHits &lvl);
   void global_frontier(DBuf<Frontier> &fr, uint64_t &nF, DBuf<uint32_t> &gmap, uint64_t total,
@@ -561,8 +568,7 @@ void Runner::stab_and_lift(const DBuf<Frontier> &fr_ref, uint64_t nF, bool close
   Lifted L;
   lift_core(fr_ref, nF, closed, clip,
             [&](uint64_t H) {
-              if (sink) sink->boxes.alloc(sink->prefix + H, ar_);
-              else lvl.hits.alloc(H, ar_);
+              if (!sink) lvl.hits.alloc(H, ar_);
               if (p_.store_cigar) {
                 lvl.entry.alloc(H, ar_);
                 lvl.slices.alloc(H, ar_);
@@ -586,20 +592,13 @@ void Runner::stab_and_lift(const DBuf<Frontier> &fr_ref, uint64_t nF, bool close
   WallTimer wt(ctx.w_order);
 
   if (sink) {
-    // direct BED path, last hop: no ordering sort — the reference order travels
-    // as (range, visit rank) inside each box
-    DBuf<uint64_t> dst_off;
-    if (L.d_orig) {
-      dst_off.alloc(nF + 1, ar_);
-      CUDA_CHECK(cudaMemsetAsync(dst_off.get() + nF, 0, 8, s_));
-      LAUNCH(k_scatter_counts, grid_threads(nF), 256, s_, L.counts.get(), L.d_orig, nF, dst_off.get());
-      exclusive_scan_u64(dst_off.get(), nF + 1, sc_, s_);
-      ctx.launches += 2;
-    }
-    LAUNCH(k_boxes_from_raw_level, grid_threads(H), 256, s_, L.hits.get(), L.tasks.get(), L.d_orig, L.offs.get(),
-           dst_off.get(), H, sink->level, p_.min_output_length, sink->boxes.get() + sink->prefix,
-           sink->counters.get(), (const uint32_t *)nullptr);
-    sink->n = sink->prefix + H;
+    // direct BED path, last hop: no ordering sort and no copy — the hits stay where the liftover
+    // wrote them; the reference order travels as (range, visit rank)
+    sink->raw_hits = std::move(L.hits);
+    sink->raw_tasks = std::move(L.tasks);
+    sink->raw_has_orig = L.d_orig != nullptr;
+    if (sink->raw_has_orig) sink->raw_orig = std::move(L.orig);
+    sink->n_raw = H;
     sink->filled = true;
     lvl.n = 0;
     return;
@@ -1023,12 +1022,12 @@ void Runner::run(const impgx_range *d_ranges, uint32_t n_rows, bool bed, BatchOu
   }
   if (direct && levels.size() < 60) {
     WallTimer wt(ctx.w_assemble);
-    if (!sink.filled) {
+    {
       uint64_t held = 0;  // hits held by the ordered levels (BFS hops or DFS rounds)
       for (auto &l : levels) held += l.n;
       sink.prefix = (uint64_t)n_rows + held;
       sink.boxes.alloc(sink.prefix, ar_);
-      sink.n = sink.prefix;
+      sink.n = sink.prefix + sink.n_raw;
     }
     // seeds, then the levels that were ordered for the fold (their index is their ordinal)
     if (masked_)  // the self intervals are the seed level below; the per-row seed slots stay invalid
@@ -1252,16 +1251,25 @@ void Runner::stage_b(const BoxD *acc, const uint64_t *is_root, uint64_t n, unsig
 // Both stages on chip, one (row, q) segment per warp / CTA (merge_kernels.cuh,
 // k_merge_segments). Returns false (nothing written) when a segment exceeds
 // SEG_MAX boxes: the caller then runs the global two-sort path.
-bool Runner::merge_fused(const BoxD *boxes, uint64_t nB, uint64_t nv, BatchOut &out, uint32_t *row_cnt) {
-  if (nv == 0) return true;
+bool Runner::merge_fused(const BoxSrc &src, uint64_t nB, BatchOut &out, uint32_t *row_cnt) {
+  if (nB == 0) return true;
   const int seq_bits = bits_for(ix_.n_seqs > 1 ? ix_.n_seqs - 1 : 1);
+  DBuf<uint64_t> ka0(nB, ar_);
+  DBuf<uint32_t> perm0(nB, ar_);
+  CUDA_CHECK(cudaMemsetAsync(d_counters_.get(), 0, 8, s_));
+  LAUNCH(k_bd_key_a_src, grid_threads(nB), 256, s_, src, nB, seq_bits, 1ull << bits_a_, ka0.get(), perm0.get(),
+         d_counters_.get());
+  unsigned long long nv = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&nv, d_counters_.get(), 8, cudaMemcpyDeviceToHost, s_));
+  CUDA_CHECK(cudaStreamSynchronize(s_));
+  ctx.d2h_bytes += 8;
+  if (nv == 0) return true;
   DBuf<BoxD> swept(nv, ar_);
   DBuf<uint32_t> cnt;
   Groups g;
   {
-    DBuf<uint64_t> ka(nB, ar_);
-    DBuf<uint32_t> perm(nB, ar_);
-    LAUNCH(k_bd_key_a, grid_threads(nB), 256, s_, boxes, nB, seq_bits, 1ull << bits_a_, ka.get(), perm.get());
+    DBuf<uint64_t> &ka = ka0;
+    DBuf<uint32_t> &perm = perm0;
     sort_pairs(ka, perm, nB, 0, bits_a_ + 1, sc_, s_, ctx);
     // segments = runs of equal (row, q)
     {
@@ -1295,7 +1303,7 @@ bool Runner::merge_fused(const BoxD *boxes, uint64_t nB, uint64_t nv, BatchOut &
       CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       const unsigned grid =
           (unsigned)std::min<uint64_t>(((uint64_t)hc[c] + seg_per_cta - 1) / seg_per_cta, (uint64_t)sm_count() * per_sm);
-      kern<<<grid, threads, smem, s_>>>(boxes, perm.get(), g.begins.get(), lists.get() + (uint64_t)c * g.G, hc[c], d, ms,
+      kern<<<grid, threads, smem, s_>>>(src, perm.get(), g.begins.get(), lists.get() + (uint64_t)c * g.G, hc[c], d, ms,
                                         swept.get(), cnt.get());
       CUDA_CHECK(cudaGetLastError());
       ctx.launches++;
@@ -1331,6 +1339,27 @@ OutCols Runner::alloc_out_cols(BatchOut &out, uint64_t n) {
   return oc;
 }
 
+// The raw hits of the last hop as BoxD records behind the seeds and the ordered levels (the
+// paths that need one array: unsorted --no-merge output, the global two-sort merge, routing).
+void Runner::materialize_boxes(BedSink &sink) {
+  if (sink.n_raw == 0) return;
+  const uint64_t H = sink.n_raw;
+  DBuf<BoxD> full(sink.prefix + H, ar_);
+  if (sink.prefix)
+    CUDA_CHECK(cudaMemcpyAsync(full.get(), sink.boxes.get(), sink.prefix * sizeof(BoxD), cudaMemcpyDeviceToDevice, s_));
+  LAUNCH(k_boxes_from_raw_level, grid_threads(H), 256, s_, sink.raw_hits.get(), sink.raw_tasks.get(),
+         sink.raw_has_orig ? (const uint32_t *)sink.raw_orig.get() : nullptr, (const uint64_t *)nullptr,
+         (const uint64_t *)nullptr, H, sink.level, p_.min_output_length, full.get() + sink.prefix, sink.counters.get(),
+         (const uint32_t *)nullptr);
+  CUDA_CHECK(cudaStreamSynchronize(s_));
+  sink.boxes = std::move(full);
+  sink.raw_hits.release();
+  sink.raw_tasks.release();
+  sink.raw_orig.release();
+  sink.n_raw = 0;
+  sink.n = sink.prefix + H;
+}
+
 // output_results_bed's two merges straight from the boxes of the batch. On a
 // sharded index stage A runs where the hits were produced (owner of the target
 // sequence: a (row, q, t, strand) group never spans ranks), the merged boxes
@@ -1343,58 +1372,76 @@ void Runner::bed_merge_direct(BedSink &sink, uint32_t n_rows, BatchOut &out) {
   CUDA_CHECK(cudaEventRecord(e0, s_));
   const int32_t d = p_.merge_distance;
   const bool ms = p_.merge_strands != 0;
-  const uint64_t nB = sink.n;
   DBuf<uint32_t> row_cnt(n_rows, ar_);
   CUDA_CHECK(cudaMemsetAsync(row_cnt.get(), 0, (size_t)n_rows * 4, s_));
   out.row_off.alloc(n_rows + 1, ar_);
   CUDA_CHECK(cudaMemsetAsync(out.row_off.get(), 0, ((size_t)n_rows + 1) * 8, s_));
   out.n_results = 0;
-  unsigned long long nv = 0;
-  CUDA_CHECK(cudaMemcpyAsync(&nv, sink.counters.get(), 8, cudaMemcpyDeviceToHost, s_));
-  CUDA_CHECK(cudaStreamSynchronize(s_));
-  ctx.d2h_bytes += 8;
-  REQUIRE(nB < (1ull << 32), IMPGX_E_INVALID, "more than 2^32 results in one batch; lower IMPGX_ROWS_PER_BATCH");
+  REQUIRE(sink.n < (1ull << 32), IMPGX_E_INVALID, "more than 2^32 results in one batch; lower IMPGX_ROWS_PER_BATCH");
   const int row_bits = bits_for(n_rows > 1 ? n_rows - 1 : 1);
   const int seq_bits = bits_for(ix_.n_seqs > 1 ? ix_.n_seqs - 1 : 1);
   bits_a_ = row_bits + 2 * seq_bits + 1;
   bits_b_ = row_bits + seq_bits + 33;
-  if (d < 0 && !ms) {
-    REQUIRE(!comm_, IMPGX_E_UNSUPPORTED,
-            "--no-merge with --consider-strandness keeps the reference's unsorted result order, which a sharded "
-            "index does not assemble; use an unsharded index");
-    if (nv > 0) {
-      // nothing merges and nothing is sorted (src/main.rs:12479,12859): reference order per row
-      DBuf<uint64_t> k1(nB, ar_);
-      DBuf<uint32_t> perm(nB, ar_);
-      LAUNCH(k_bd_key_ord, grid_threads(nB), 256, s_, sink.boxes.get(), nB, k1.get(), perm.get());
-      sort_pairs(k1, perm, nB, 0, 64, sc_, s_, ctx);
-      DBuf<uint64_t> k2(nB, ar_);
-      LAUNCH(k_bd_key_row, grid_threads(nB), 256, s_, sink.boxes.get(), perm.get(), nB, n_rows, k2.get());
-      sort_pairs(k2, perm, nB, 0, bits_for(n_rows), sc_, s_, ctx);
-      OutCols oc = alloc_out_cols(out, nv);
-      LAUNCH(k_boxd_to_cols, grid_threads(nv), 256, s_, sink.boxes.get(), perm.get(), (uint64_t)nv, oc, row_cnt.get());
-    }
-  } else if (nv > 0 || comm_) {
+  const bool unsorted_out = d < 0 && !ms;
+  REQUIRE(!(unsorted_out && comm_), IMPGX_E_UNSUPPORTED,
+          "--no-merge with --consider-strandness keeps the reference's unsorted result order, which a sharded "
+          "index does not assemble; use an unsharded index");
+  if (!unsorted_out)
     REQUIRE(bits_a_ <= 63 && bits_b_ <= 63, IMPGX_E_INVALID,
             "batch too large for the packed merge keys; lower IMPGX_ROWS_PER_BATCH");
-    // sharded index: every valid box travels to the owner of its query sequence first,
-    // so that a (row, q) segment is complete on one rank
-    const BoxD *bx = sink.boxes.get();
-    uint64_t n_in = nB, n_valid = nv;
-    DBuf<BoxD> recv;
-    if (comm_) {
-      uint64_t n_recv = 0;
-      route_boxes(sink.boxes.get(), nB, recv, n_recv);
-      sink.boxes.release();
-      bx = recv.get();
-      n_in = n_valid = n_recv;
-      REQUIRE(n_in < (1ull << 32), IMPGX_E_INVALID, "more than 2^32 results in one batch; lower IMPGX_ROWS_PER_BATCH");
-    }
-    if (n_valid > 0 && (getenv("IMPGX_MERGE_GLOBAL") || !merge_fused(bx, n_in, n_valid, out, row_cnt.get()))) {
-      DBuf<BoxD> acc;
-      DBuf<uint64_t> is_root;
-      stage_a(bx, n_in, n_valid, acc, is_root);
-      stage_b(acc.get(), is_root.get(), n_valid, sink.counters.get() + 1, n_rows, out, row_cnt.get());
+  bool done = false;
+  if (!unsorted_out && !comm_ && !getenv("IMPGX_MERGE_GLOBAL")) {
+    // the common path: both merges on chip, straight from the raw hits of the last hop
+    BoxSrc src{sink.boxes.get(), sink.prefix, sink.raw_hits.get(), sink.raw_tasks.get(),
+               sink.raw_has_orig ? sink.raw_orig.get() : nullptr, sink.level, p_.min_output_length};
+    done = merge_fused(src, sink.n, out, row_cnt.get());
+  }
+  if (!done) {
+    // every other path works on one BoxD array
+    materialize_boxes(sink);
+    const uint64_t nB = sink.n;
+    unsigned long long nv = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&nv, sink.counters.get(), 8, cudaMemcpyDeviceToHost, s_));
+    CUDA_CHECK(cudaStreamSynchronize(s_));
+    ctx.d2h_bytes += 8;
+    if (unsorted_out) {
+      if (nv > 0) {
+        // nothing merges and nothing is sorted (src/main.rs:12479,12859): reference order per row
+        DBuf<uint64_t> k1(nB, ar_);
+        DBuf<uint32_t> perm(nB, ar_);
+        LAUNCH(k_bd_key_ord, grid_threads(nB), 256, s_, sink.boxes.get(), nB, k1.get(), perm.get());
+        sort_pairs(k1, perm, nB, 0, 64, sc_, s_, ctx);
+        DBuf<uint64_t> k2(nB, ar_);
+        LAUNCH(k_bd_key_row, grid_threads(nB), 256, s_, sink.boxes.get(), perm.get(), nB, n_rows, k2.get());
+        sort_pairs(k2, perm, nB, 0, bits_for(n_rows), sc_, s_, ctx);
+        OutCols oc = alloc_out_cols(out, nv);
+        LAUNCH(k_boxd_to_cols, grid_threads(nv), 256, s_, sink.boxes.get(), perm.get(), (uint64_t)nv, oc, row_cnt.get());
+      }
+    } else if (nv > 0 || comm_) {
+      // sharded index: every valid box travels to the owner of its query sequence first,
+      // so that a (row, q) segment is complete on one rank
+      const BoxD *bx = sink.boxes.get();
+      uint64_t n_in = nB, n_valid = nv;
+      DBuf<BoxD> recv;
+      if (comm_) {
+        uint64_t n_recv = 0;
+        route_boxes(sink.boxes.get(), nB, recv, n_recv);
+        sink.boxes.release();
+        bx = recv.get();
+        n_in = n_valid = n_recv;
+        REQUIRE(n_in < (1ull << 32), IMPGX_E_INVALID, "more than 2^32 results in one batch; lower IMPGX_ROWS_PER_BATCH");
+      }
+      bool fused = false;
+      if (n_valid > 0 && !getenv("IMPGX_MERGE_GLOBAL")) {
+        BoxSrc src{bx, n_in, nullptr, nullptr, nullptr, 0, -1};
+        fused = merge_fused(src, n_in, out, row_cnt.get());
+      }
+      if (n_valid > 0 && !fused) {
+        DBuf<BoxD> acc;
+        DBuf<uint64_t> is_root;
+        stage_a(bx, n_in, n_valid, acc, is_root);
+        stage_b(acc.get(), is_root.get(), n_valid, sink.counters.get() + 1, n_rows, out, row_cnt.get());
+      }
     }
   }
   LAUNCH(k_u32_to_u64, grid_threads(n_rows), 256, s_, row_cnt.get(), n_rows, out.row_off.get());

@@ -275,6 +275,30 @@ struct __align__(16) BoxD {
 
 __device__ __forceinline__ uint64_t make_ord(uint32_t level, uint64_t low) { return ((uint64_t)level << 58) | low; }
 
+// Where the boxes of a batch live: the seeds and the ordered levels as BoxD records
+// [0, n_boxes), then the raw hits of the last hop exactly as the liftover kernel wrote them
+// (box i >= n_boxes is hit i - n_boxes; its ordinal comes from the lift task's range and the
+// hit's visit rank), so the bulk of the results is never copied into a second layout.
+struct BoxSrc {
+  const BoxD *boxes;
+  uint64_t n_boxes;
+  const Hit *hits;
+  const LiftTask *tasks;
+  const uint32_t *orig;  // processing index -> frontier index of the hop, or nullptr
+  uint32_t level;
+  int32_t min_out;
+};
+__device__ __forceinline__ BoxD load_box(const BoxSrc &s, uint32_t i) {
+  if (i < s.n_boxes) return s.boxes[i];
+  const uint64_t j = i - s.n_boxes;
+  const Hit h = s.hits[j];
+  const bool ok = h.row != INVALID_ID && passes_len(h, s.min_out);
+  const uint32_t k = s.tasks[j].range;
+  const uint32_t r = s.orig ? s.orig[k] : k;
+  return BoxD{h.q_first, h.q_last, h.t_first, h.t_last, h.q_id, h.t_id, h.row, ok ? 1u : 0u,
+              make_ord(s.level, ((uint64_t)r << 32) | h.vrank)};
+}
+
 // `owner` != nullptr (sharded index): only the rows on targets owned by `rank` are valid here
 __global__ void k_boxes_from_seeds(const impgx_range *__restrict__ ranges, uint32_t n, int32_t min_out, int apply_len,
                                    BoxD *__restrict__ out, unsigned long long *__restrict__ n_valid,
@@ -334,6 +358,31 @@ __global__ void k_bd_key_a(const BoxD *__restrict__ b, uint64_t n, int seq_bits,
     keys[i] = x.valid ? (((((uint64_t)x.row << seq_bits | x.q_id) << seq_bits | x.t_id) << 1) | (fwd ? 1u : 0u)) : invalid_key;
     vals[i] = (uint32_t)i;
   }
+}
+
+// the same key over a BoxSrc; counts the valid boxes
+__global__ void k_bd_key_a_src(BoxSrc src, uint64_t n, int seq_bits, uint64_t invalid_key, uint64_t *__restrict__ keys,
+                               uint32_t *__restrict__ vals, unsigned long long *__restrict__ n_valid) {
+  unsigned long long c = 0;
+  for (uint64_t i = gtid(); i < n; i += gstride()) {
+    uint32_t row, q, t;
+    bool fwd, ok;
+    if (i < src.n_boxes) {
+      const BoxD x = src.boxes[i];
+      row = x.row; q = x.q_id; t = x.t_id;
+      fwd = x.q_lo <= x.q_hi;
+      ok = x.valid != 0;
+    } else {
+      const Hit h = src.hits[i - src.n_boxes];
+      row = h.row; q = h.q_id; t = h.t_id;
+      fwd = h.q_first <= h.q_last;
+      ok = h.row != INVALID_ID && passes_len(h, src.min_out);
+    }
+    keys[i] = ok ? (((((uint64_t)row << seq_bits | q) << seq_bits | t) << 1) | (fwd ? 1u : 0u)) : invalid_key;
+    vals[i] = (uint32_t)i;
+    c += ok ? 1 : 0;
+  }
+  if (c) atomicAdd(n_valid, c);
 }
 
 // merge_adjusted_intervals_gap_2d (src/main.rs:12858-13011) on an UNSORTED
@@ -603,7 +652,7 @@ struct SegMem {
 
 template <int T, int CAP>
 __global__ void __launch_bounds__(T == 32 ? 256 : T)
-    k_merge_segments(const BoxD *__restrict__ boxes, const uint32_t *__restrict__ idx, const uint32_t *__restrict__ begins,
+    k_merge_segments(const BoxSrc src, const uint32_t *__restrict__ idx, const uint32_t *__restrict__ begins,
                      const uint32_t *__restrict__ list, uint32_t n_list, int64_t d, int merge_strands,
                      BoxD *__restrict__ swept, uint32_t *__restrict__ out_cnt) {
   extern __shared__ __align__(16) unsigned char seg_smem[];
@@ -630,7 +679,7 @@ __global__ void __launch_bounds__(T == 32 ? 256 : T)
   for (uint32_t li = blockIdx.x * GROUPS + gi; li < n_list; li += gridDim.x * GROUPS) {
     const uint32_t g = list[li];
     const uint32_t b = begins[g], n = begins[g + 1] - b;
-    const BoxD first = boxes[idx[b]];
+    const BoxD first = load_box(src, idx[b]);
     if (n == 1) {
       if (lt == 0) {
         swept[b] = first;
@@ -644,7 +693,7 @@ __global__ void __launch_bounds__(T == 32 ? 256 : T)
 #pragma unroll
       for (int u = 0; u < 4; u++) {
         const uint32_t i = i0 + u * T;
-        if (i < n) x[u] = boxes[idx[b + i]];
+        if (i < n) x[u] = load_box(src, idx[b + i]);
       }
 #pragma unroll
       for (int u = 0; u < 4; u++) {
