@@ -1310,7 +1310,7 @@ bool Runner::merge_fused(const BoxSrc &src, uint64_t nB, BatchOut &out, uint32_t
     };
     launch(k_merge_segments<32, seg_cap(0)>, 256, (size_t)8 * seg_cap(0) * SEG_BYTES, 5, 8, 0);
     launch(k_merge_segments<32, seg_cap(1)>, 256, (size_t)8 * seg_cap(1) * SEG_BYTES, 2, 8, 1);
-    launch(k_merge_segments<128, seg_cap(2)>, 128, (size_t)seg_cap(2) * SEG_BYTES, 10, 1, 2);
+    launch(k_merge_segments<256, seg_cap(2)>, 256, (size_t)seg_cap(2) * SEG_BYTES, 8, 1, 2);
     launch(k_merge_segments<128, seg_cap(3)>, 128, (size_t)seg_cap(3) * SEG_BYTES, 5, 1, 3);
     launch(k_merge_segments<512, seg_cap(4)>, 512, (size_t)seg_cap(4) * SEG_BYTES, 1, 1, 4);
   }

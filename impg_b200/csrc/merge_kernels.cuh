@@ -599,7 +599,7 @@ __global__ void k_boxd_to_cols(const BoxD *__restrict__ b, const uint32_t *__res
 namespace impgx {
 
 constexpr int SEG_CLASSES = 5;
-// boxes per segment (powers of two: the sort pads to one): two warp classes, then 128-, 128- and 512-thread CTAs
+// boxes per segment (powers of two: the sort pads to one): two warp classes, then 256-, 128- and 512-thread CTAs
 __host__ __device__ constexpr int seg_cap(int c) {
   return c == 0 ? 128 : (c == 1 ? 256 : (c == 2 ? 512 : (c == 3 ? 1024 : 4096)));
 }

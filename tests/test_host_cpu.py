@@ -254,3 +254,22 @@ def test_synth_generate_shard_matches_the_full_generator():
         b = ix.host_columns(sr, soffs, len(lens), owner=owner, rank=r)
         for k in ("e_start", "e_end", "e_vrank", "e_flags", "e_query_id"):
             assert (a[k] == b[k]).all()
+
+
+def test_bench_contig_subworld_is_exact():
+    """bench.py times the CPU reference of c4 on the alignments of one contig: rows on that contig
+    must give identical results in the sub-world and in the full index."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    cfg = ix.synth_cfg(6, 3, 60000, 8, 30, 300, 3)
+    recs, runs, offs, lens, names = ix.synth_generate(cfg)
+    bed = ix.synth_bed(cfg, 120, seed=9, min_len=200, max_len=12000)
+    sr, sruns, soffs, rows = bench.contig_subworld(cfg, recs, runs, offs, bed)
+    assert len(sr) * 3 == len(recs) and 0 < len(rows) < len(bed)
+    full, sub = O.Index.build(recs, runs, offs, lens), O.Index.build(sr, sruns, soffs, lens)
+    p = O.make_params(mode=O.MODE_BFS, max_depth=3, store_cigar=True)
+    a, ao = full.query_batch(rows[:25], p)
+    b, bo = sub.query_batch(rows[:25], p)
+    ac, bc = a.columns(), b.columns()
+    assert ao.tolist() == bo.tolist() and all((ac[k] == bc[k]).all() for k in ac)
