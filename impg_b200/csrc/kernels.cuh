@@ -513,6 +513,30 @@ __device__ __forceinline__ uint32_t ck_partition(const Checkpoint *__restrict__ 
     return inclusive ? p <= x : p < x;
   };
   uint32_t g = guess < lo ? lo : (guess >= hi ? hi - 1 : guess);
+  {
+    // fast path: the whole 32-byte sector of the guess (4 checkpoints; the array is padded to whole
+    // sectors with the totals, which keeps it nondecreasing) in one go. If the partition point lies
+    // inside it — the common case — no further probe is needed.
+    const uint32_t s4 = g & ~3u;
+    const uint4 *sp = reinterpret_cast<const uint4 *>(ck + s4);
+    const uint4 a = sp[0], b = sp[1];
+    const int64_t p0 = swap_id ? a.y : a.x, p1 = swap_id ? a.w : a.z, p2 = swap_id ? b.y : b.x, p3 = swap_id ? b.w : b.z;
+    const bool t0 = inclusive ? p0 <= x : p0 < x, t1 = inclusive ? p1 <= x : p1 < x;
+    const bool t2 = inclusive ? p2 <= x : p2 < x, t3 = inclusive ? p3 <= x : p3 < x;
+    if ((t0 || s4 <= lo) && (!t3 || s4 + 4 >= hi)) {
+      uint32_t r = s4 + (uint32_t)t0 + (uint32_t)t1 + (uint32_t)t2 + (uint32_t)t3;  // true entries are a prefix
+      r = r < lo ? lo : r;
+      return r > hi ? hi : r;
+    }
+    if (!t0) {  // partition point at or below the sector start
+      hi = s4;
+      g = s4 - 1;
+    } else {    // beyond the sector
+      lo = s4 + 4;
+      g = lo;
+    }
+    if (lo >= hi) return lo;
+  }
   if (pred(g)) {  // answer in (g, hi]
     lo = g + 1;
     uint32_t step = 1;
@@ -550,15 +574,18 @@ __device__ __forceinline__ uint32_t ck_partition(const Checkpoint *__restrict__ 
 }
 
 struct EndsAcc {
-  int32_t f_q, f_t, l_q, l_t;
-  int32_t f_w, l_w;  // walk position inside the block of the first / last overlapping op (for r_ov accounting)
+  // the first / last overlapping op of the walk so far: packed run + walk position before it
+  uint32_t f_v, l_v;
+  int32_t f_tp, f_qp, l_tp, l_qp;
+  uint32_t n_ov;  // overlapping ops seen (r_ov accounting)
   bool found, broke;
 };
 
-// evaluates the (up to) 32 runs of physical block pb in walk order
-__device__ __forceinline__ void thread_eval_block(const uint32_t *__restrict__ blk, uint32_t n, uint32_t pb, bool swap_id,
-                                                  bool backward, int32_t dir, int32_t tp, int32_t qp, int32_t rs,
-                                                  int32_t re, int32_t last_target_pos, EndsAcc &acc) {
+// evaluates the (up to) 8 runs of physical block pb in walk order; only the per-op overlap test runs
+// for every op — the projection arithmetic is done once, by ends_first / ends_last, on the selected ops
+__device__ __forceinline__ void thread_eval_block(const uint32_t *__restrict__ blk, uint32_t n, uint32_t pb, uint32_t op_t0,
+                                                  uint32_t op_q0, bool backward, int32_t dir, int32_t tp, int32_t qp,
+                                                  int32_t rs, int32_t re, int32_t last_target_pos, EndsAcc &acc) {
   const uint32_t base = pb * RUNS_PER_BLOCK;
   const uint32_t cnt = min((uint32_t)RUNS_PER_BLOCK, n - base);
   const uint4 *src = reinterpret_cast<const uint4 *>(blk + base);
@@ -574,11 +601,10 @@ __device__ __forceinline__ void thread_eval_block(const uint32_t *__restrict__ b
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       const uint32_t off = (uint32_t)(ci * 4 + (backward ? 3 - k : k));  // physical offset in the block
-      uint32_t op = v[k] >> 29;
+      const uint32_t op = v[k] >> 29;
       const int32_t len = (int32_t)(v[k] & 0x1fffffffu);
-      if (swap_id) op = op == IMPGX_OP_I ? IMPGX_OP_D : (op == IMPGX_OP_D ? IMPGX_OP_I : op);
-      const int32_t t = (op == IMPGX_OP_I) ? 0 : len;
-      const int32_t q = (op == IMPGX_OP_D) ? 0 : len;
+      const int32_t t = (op == op_t0) ? 0 : len;  // op_t0: the op without target length in this orientation
+      const int32_t q = (op == op_q0) ? 0 : len;
       const bool valid = off < cnt;
       const bool processed = valid && tp <= last_target_pos;
       acc.broke |= valid && tp > last_target_pos;
@@ -586,21 +612,44 @@ __device__ __forceinline__ void thread_eval_block(const uint32_t *__restrict__ b
       const int32_t os = max(tp, rs);
       const int32_t oe = min(tp + t, is_del ? last_target_pos : re);
       const bool ov = processed && (is_ins ? tp >= rs : os < oe);
-      const int32_t pts = is_ins ? tp : os, pte = is_ins ? tp : oe;
-      const int32_t pqs = (is_ins || is_del) ? qp : qp + (os - tp) * dir;
-      const int32_t pqe = is_ins ? qp + q * dir : (is_del ? qp : pqs + (oe - os) * dir);
       const bool first = ov && !acc.found;
-      acc.f_q = first ? pqs : acc.f_q;
-      acc.f_t = first ? pts : acc.f_t;
-      acc.f_w = first ? c * 4 + k : acc.f_w;
+      acc.f_v = first ? v[k] : acc.f_v;
+      acc.f_tp = first ? tp : acc.f_tp;
+      acc.f_qp = first ? qp : acc.f_qp;
       acc.found |= ov;
-      acc.l_q = ov ? pqe : acc.l_q;
-      acc.l_t = ov ? pte : acc.l_t;
-      acc.l_w = ov ? c * 4 + k : acc.l_w;
+      acc.l_v = ov ? v[k] : acc.l_v;
+      acc.l_tp = ov ? tp : acc.l_tp;
+      acc.l_qp = ov ? qp : acc.l_qp;
+      acc.n_ov += ov ? 1u : 0u;
       tp += t;
-      qp += q * dir;
+      qp += dir > 0 ? q : -q;
     }
   }
+}
+// start of the projection = start of the first overlapping op (src/impg.rs:2806-2868)
+__device__ __forceinline__ void ends_first(const EndsAcc &acc, uint32_t op_t0, uint32_t op_q0, int32_t dir, int32_t rs,
+                                           int32_t &f_q, int32_t &f_t) {
+  const uint32_t op = acc.f_v >> 29;
+  const int32_t len = (int32_t)(acc.f_v & 0x1fffffffu);
+  const int32_t t = (op == op_t0) ? 0 : len, q = (op == op_q0) ? 0 : len;
+  const bool is_ins = t == 0, is_del = !is_ins && q == 0;
+  const int32_t os = max(acc.f_tp, rs);
+  f_t = is_ins ? acc.f_tp : os;
+  f_q = (is_ins || is_del) ? acc.f_qp : acc.f_qp + (os - acc.f_tp) * dir;
+}
+// end of the projection = end of the last overlapping op
+__device__ __forceinline__ void ends_last(const EndsAcc &acc, uint32_t op_t0, uint32_t op_q0, int32_t dir, int32_t rs,
+                                          int32_t re, int32_t last_target_pos, int32_t &l_q, int32_t &l_t) {
+  const uint32_t op = acc.l_v >> 29;
+  const int32_t len = (int32_t)(acc.l_v & 0x1fffffffu);
+  const int32_t t = (op == op_t0) ? 0 : len, q = (op == op_q0) ? 0 : len;
+  const bool is_ins = t == 0, is_del = !is_ins && q == 0;
+  const int32_t tp = acc.l_tp, qp = acc.l_qp;
+  const int32_t os = max(tp, rs);
+  const int32_t oe = min(tp + t, is_del ? last_target_pos : re);
+  const int32_t pqs = (is_ins || is_del) ? qp : qp + (os - tp) * dir;
+  l_t = is_ins ? tp : oe;
+  l_q = is_ins ? qp + q * dir : (is_del ? qp : pqs + (oe - os) * dir);
 }
 
 __global__ void __launch_bounds__(256, 3) k_liftover_ends(DevIndexView ix, const Frontier *__restrict__ fr,
@@ -632,11 +681,15 @@ __global__ void __launch_bounds__(256, 3) k_liftover_ends(DevIndexView ix, const
     const int32_t last_target_pos = min(t_end, re);
     const int64_t rel = (int64_t)rs - t_start, rel_l = (int64_t)last_target_pos - t_start;
 
+    // in this orientation: the op that consumes no target (insertion) / no query (deletion)
+    const uint32_t op_t0 = swap_id ? IMPGX_OP_D : IMPGX_OP_I, op_q0 = swap_id ? IMPGX_OP_I : IMPGX_OP_D;
     EndsAcc acc;
-    acc.f_q = acc.f_t = acc.l_q = acc.l_t = -1;
-    acc.f_w = acc.l_w = 0;
+    acc.f_v = acc.l_v = 0;
+    acc.f_tp = acc.f_qp = acc.l_tp = acc.l_qp = 0;
+    acc.n_ov = 0;
     acc.found = false;
     acc.broke = false;
+    int32_t f_q = -1, f_t = -1, l_q = -1, l_t = -1;
     uint32_t nread = 0, nck = 0, r_ov = 1;
     if (nblk > 0 && rel_l >= 0) {
       // totals: needed exactly only when walking backwards; otherwise the record's
@@ -677,7 +730,7 @@ __global__ void __launch_bounds__(256, 3) k_liftover_ends(DevIndexView ix, const
         const int64_t tcons = backward ? w_tot - pt : pt, qcons = backward ? wq_tot - pq : pq;
         const int32_t tp0 = (int32_t)(t_start + tcons);
         const int32_t qp0 = rev_strand ? (int32_t)(q_end - qcons) : (int32_t)(q_start + qcons);
-        thread_eval_block(blk, n, pb, swap_id, backward, dir, tp0, qp0, rs, re, last_target_pos, acc);
+        thread_eval_block(blk, n, pb, op_t0, op_q0, backward, dir, tp0, qp0, rs, re, last_target_pos, acc);
         nread += RUNS_PER_BLOCK;
         if (acc.found || acc.broke || j + 1 >= nblk) break;
         j++;
@@ -685,7 +738,9 @@ __global__ void __launch_bounds__(256, 3) k_liftover_ends(DevIndexView ix, const
       // ---- end side: the last overlapping op lies in blocks [j, max(je, j)]; walk backward from the top
       if (acc.found) {
         uint32_t jl = je > j ? je : j;
-        r_ov = (uint32_t)(acc.l_w - acc.f_w + 1);
+        r_ov = acc.n_ov;
+        ends_first(acc, op_t0, op_q0, dir, rs, f_q, f_t);
+        ends_last(acc, op_t0, op_q0, dir, rs, re, last_target_pos, l_q, l_t);
         while (jl > j) {
           const uint32_t pb = backward ? nblk - 1 - jl : jl;
           const Checkpoint k = backward ? ck[pb + 1] : ck[pb];
@@ -694,23 +749,24 @@ __global__ void __launch_bounds__(256, 3) k_liftover_ends(DevIndexView ix, const
           const int32_t tp0 = (int32_t)(t_start + tcons);
           const int32_t qp0 = rev_strand ? (int32_t)(q_end - qcons) : (int32_t)(q_start + qcons);
           EndsAcc a2;
-          a2.f_q = a2.f_t = a2.l_q = a2.l_t = -1;
-          a2.f_w = a2.l_w = 0;
+          a2.f_v = a2.l_v = 0;
+          a2.f_tp = a2.f_qp = a2.l_tp = a2.l_qp = 0;
+          a2.n_ov = 0;
           a2.found = false;
           a2.broke = false;
-          thread_eval_block(blk, n, pb, swap_id, backward, dir, tp0, qp0, rs, re, last_target_pos, a2);
+          thread_eval_block(blk, n, pb, op_t0, op_q0, backward, dir, tp0, qp0, rs, re, last_target_pos, a2);
           nread += RUNS_PER_BLOCK;
           if (a2.found) {
-            acc.l_q = a2.l_q;
-            acc.l_t = a2.l_t;
-            r_ov = (jl - j) * RUNS_PER_BLOCK + (uint32_t)(a2.l_w - acc.f_w + 1);
+            ends_last(a2, op_t0, op_q0, dir, rs, re, last_target_pos, l_q, l_t);
+            // ops of block j from its first overlap on, whole blocks in between, ops of block jl up to its last overlap
+            r_ov = acc.n_ov + (jl - j - 1) * RUNS_PER_BLOCK + a2.n_ov;
             break;
           }
           jl--;  // nothing overlapped up there: try the block below (block j already holds its own last)
         }
       }
     }
-    bool ok = acc.found && acc.f_q != acc.l_q && acc.f_t != acc.l_t;
+    bool ok = acc.found && f_q != l_q && f_t != l_t;
     if (ok && lp.subset) ok = query_id == lp.row_target[f.row] || lp.subset[query_id] != 0;
     runs_acc += nread;
     ck_acc += nck;
@@ -719,11 +775,11 @@ __global__ void __launch_bounds__(256, 3) k_liftover_ends(DevIndexView ix, const
     Hit h;
     h.row = ok ? f.row : INVALID_ID;
     h.q_id = query_id;
-    h.q_first = acc.f_q;
-    h.q_last = acc.l_q;
+    h.q_first = f_q;
+    h.q_last = l_q;
     h.t_id = f.seq;
-    h.t_first = acc.f_t;
-    h.t_last = acc.l_t;
+    h.t_first = f_t;
+    h.t_last = l_t;
     h.vrank = vrank;
     hits[w] = h;
   }
