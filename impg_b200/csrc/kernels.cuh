@@ -700,7 +700,7 @@ __global__ void __launch_bounds__(256, 3) k_liftover_ends(DevIndexView ix, const
         w_tot = swap_id ? tot.q_off : tot.t_off;
         wq_tot = swap_id ? tot.t_off : tot.q_off;
       }
-      const float scale = (float)nblk / (float)(w_tot > 0 ? w_tot : 1);
+      const float scale = __fdividef((float)nblk, (float)(w_tot > 0 ? w_tot : 1));  // only seeds the search
       // walk blocks j in [0, nblk): js = last block starting before rs, je = last block starting at or before L
       uint32_t js, je;
       if (!backward) {
