@@ -32,6 +32,10 @@ import time
 
 import numpy as np
 
+# stdout carries exactly one JSON line: NCCL's banner ("NCCL version ...", printed at NCCL_DEBUG=VERSION/WARN)
+# and any other NCCL log go to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -291,12 +295,36 @@ def run_shard_only(args, ix, torch, dist, name, rank, local_rank, world, config)
                                "exchanges_per_step": (tr1["exchanges"] - tr0["exchanges"]) // args.steps,
                                "shard_device_bytes_max": int(bytes_max)},
             "setup": {"generate_s": gen_s, "index_build_s": build_s, "index_device_bytes": shard.device_bytes}}
-    print(json.dumps(line))
+    emit(line)
     dist.destroy_process_group()
     return 0
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout must carry exactly ONE JSON line. Libraries print there too (NCCL's version banner,
+    for one), so the process's fd 1 is pointed at stderr and the JSON line goes to a private
+    duplicate of the original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -358,7 +386,7 @@ def main():
                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ------------------------------------------------------------ GPU arm
@@ -409,8 +437,8 @@ def main():
         for _ in range(args.warmup + args.steps):
             step_device()
         torch.cuda.synchronize()
-        print(json.dumps({"profile_run": True, "workload": name, "steps": args.steps, "warmup": args.warmup,
-                          "stats_last_step": idx.stats()}))
+        emit({"profile_run": True, "workload": name, "steps": args.steps, "warmup": args.warmup,
+              "stats_last_step": idx.stats()})
         return 0
 
     sampler = ClockSampler(local_rank)
@@ -598,7 +626,7 @@ def main():
             "clocks": sampler.summary(), "bed_rows_out_per_step": int(merged), "rows_over_replicas": rows_mode,
             "target_sharded": sharded,
             "setup": {"generate_s": gen_s, "index_build_s": build_s, "index_device_bytes": idx.device_bytes}}
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
