@@ -233,7 +233,7 @@ def run_shard_only(args, ix, torch, dist, name, rank, local_rank, world, config)
         sampler.start()
     tr0 = comm.traffic()
     acc = {k: 0 for k in ("kernel_launches", "lift_bytes", "liftovers", "lift_launches", "lift_touched_bytes",
-                          "lift_window_runs", "lift_ms", "stab_ms", "fold_ms", "merge_ms")}
+                          "lift_window_runs", "lift_ms", "stab_ms", "fold_ms", "merge_ms", "exchange_ms")}
     merged = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -288,6 +288,7 @@ def run_shard_only(args, ix, torch, dist, name, rank, local_rank, world, config)
                          "liftovers_per_step_all_ranks": lift_total // args.steps,
                          "step_share": {"liftover_ms": lift_ms / args.steps, "stab_ms": acc["stab_ms"] / args.steps,
                                         "fold_ms": acc["fold_ms"] / args.steps, "merge_ms": acc["merge_ms"] / args.steps,
+                                        "exchange_ms_within_merge_and_fold": acc["exchange_ms"] / args.steps,
                                         "step_ms": dev_ms / args.steps}},
             "cpu_baseline": None, "clocks": sampler.summary(), "bed_rows_out_per_step": int(merged_total),
             "target_sharded": {"n_shards": world, "transport": "nccl", "rows_per_step": n,
@@ -532,7 +533,7 @@ def main():
         tr0 = traffic()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sh_merged = sh_lift = sh_launches = 0
-        sh_lift_ms = sh_merge_ms = sh_fold_ms = sh_stab_ms = 0.0
+        sh_lift_ms = sh_merge_ms = sh_fold_ms = sh_stab_ms = sh_exch_ms = 0.0
         w0 = time.perf_counter()
         g0.record(stream)
         for _ in range(args.steps):
@@ -543,6 +544,7 @@ def main():
             sh_launches += sum(x["kernel_launches"] for x in sts)
             sh_lift_ms += max(x["lift_ms"] for x in sts); sh_merge_ms += max(x["merge_ms"] for x in sts)
             sh_fold_ms += max(x["fold_ms"] for x in sts); sh_stab_ms += max(x["stab_ms"] for x in sts)
+            sh_exch_ms += max(x["exchange_ms"] for x in sts)
             del rs
         g1.record(stream)
         torch.cuda.synchronize()
@@ -564,7 +566,8 @@ def main():
                    "liftovers_per_step_this_rank": sh_lift // args.steps, "shard_device_bytes": int(sh_bytes),
                    "shard_build_s": shard_build_s, "gpu_launches": int(sh_launches),
                    "step_share_slowest_rank": {"liftover_ms": sh_lift_ms / args.steps, "stab_ms": sh_stab_ms / args.steps,
-                                               "fold_ms": sh_fold_ms / args.steps, "merge_ms": sh_merge_ms / args.steps}}
+                                               "fold_ms": sh_fold_ms / args.steps, "merge_ms": sh_merge_ms / args.steps,
+                                               "exchange_ms_within_merge_and_fold": sh_exch_ms / args.steps}}
 
     if rank != 0:
         if dist is not None:

@@ -1491,8 +1491,18 @@ static void exchange_by_dest(Comm &cm, const T *recs, DBuf<uint32_t> &dest, DBuf
       ctx.launches++;
     }
   }
+  cudaEvent_t x0, x1;
+  CUDA_CHECK(cudaEventCreate(&x0));
+  CUDA_CHECK(cudaEventCreate(&x1));
+  CUDA_CHECK(cudaEventRecord(x0, s));
   cm.alltoallv(send.get(), cnt.data(), send_off.data(), recv.get(), recv_cnt.data(), recv_off.data(), sizeof(T), s);
+  CUDA_CHECK(cudaEventRecord(x1, s));
   CUDA_CHECK(cudaStreamSynchronize(s));  // `send` is released on return
+  float xms = 0;
+  cudaEventElapsedTime(&xms, x0, x1);
+  ctx.exch_ms += xms;
+  cudaEventDestroy(x0);
+  cudaEventDestroy(x1);
 }
 
 // Non-last hop on a shard: the accepted hits go to the owner of the sequence
@@ -1861,6 +1871,7 @@ impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n
         total.lift_touched += c.lift_touched; total.lift_rov += c.lift_rov;
         total.h2d_bytes += c.h2d_bytes; total.d2h_bytes += c.d2h_bytes;
         total.lift_ms += c.lift_ms; total.stab_ms += c.stab_ms; total.fold_ms += c.fold_ms; total.merge_ms += c.merge_ms;
+        total.exch_ms += c.exch_ms;
         total.w_stab += c.w_stab; total.w_lift += c.w_lift; total.w_order += c.w_order; total.w_fold += c.w_fold;
         total.w_assemble += c.w_assemble; total.w_merge += c.w_merge;
         WallTimer wcopy(total.w_copy);
@@ -2000,6 +2011,7 @@ impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n
   st.stab_ms = total.stab_ms;
   st.fold_ms = total.fold_ms;
   st.merge_ms = total.merge_ms;
+  st.exchange_ms = total.exch_ms;
   st.total_ms = std::chrono::duration<float, std::milli>(t1 - t0).count();
   if (getenv("IMPGX_TRACE"))
     fprintf(stderr,

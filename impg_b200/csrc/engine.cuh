@@ -13,7 +13,7 @@ struct Ctx {
   uint64_t stab_ranges = 0, stab_candidates = 0, liftovers = 0, lift_runs = 0, lift_bytes = 0;
   uint64_t lift_touched = 0, lift_rov = 0;
   uint64_t h2d_bytes = 0, d2h_bytes = 0;
-  float lift_ms = 0, stab_ms = 0, fold_ms = 0, merge_ms = 0;
+  float lift_ms = 0, stab_ms = 0, fold_ms = 0, merge_ms = 0, exch_ms = 0;
   // host wall-clock per phase (IMPGX_TRACE=1 prints them)
   double w_stab = 0, w_lift = 0, w_order = 0, w_fold = 0, w_assemble = 0, w_merge = 0, w_copy = 0;
 };

@@ -153,6 +153,7 @@ typedef struct impgx_stats {
   float fold_ms;
   float merge_ms;
   float total_ms;
+  float exchange_ms;        /* sharded index: device time of the hit / frontier / box exchanges (CUDA events) */
 } impgx_stats;
 
 int impgx_abi_version(void);
