@@ -364,6 +364,7 @@ struct BedSink {
   DBuf<uint32_t> raw_orig;
   uint64_t n_raw = 0;
   bool raw_has_orig = false;
+  const uint32_t *raw_gmap = nullptr;  // sharded index: local -> global frontier index of the raw hop
   DBuf<BoxD> boxes;
   DBuf<unsigned long long> counters;  // [0] valid boxes, [1] stage-A roots
   uint64_t prefix = 0;                // slots reserved for the seeds and the earlier (sorted) levels
@@ -443,7 +444,7 @@ class Runner {
                uint32_t n_rows, BatchOut &out, uint32_t *row_cnt);
   bool merge_fused(const BoxSrc &src, uint64_t nB, BatchOut &out, uint32_t *row_cnt);
   void materialize_boxes(BedSink &sink);
-  void route_boxes(const BoxD *boxes, uint64_t nB, DBuf<BoxD> &recv, uint64_t &n_recv);
+  void route_boxes(const BoxSrc &src, uint64_t nB, DBuf<BoxD> &recv, uint64_t &n_recv);
   void route_hits(const Lifted &L, const uint32_t *gmap, LevelHits &lvl);
   void global_frontier(DBuf<Frontier> &fr, uint64_t &nF, DBuf<uint32_t> &gmap, uint64_t total,
                        const std::vector<uint64_t> &cnt);
@@ -1393,11 +1394,37 @@ void Runner::bed_merge_direct(BedSink &sink, uint32_t n_rows, BatchOut &out) {
   if (!unsorted_out && !comm_ && !getenv("IMPGX_MERGE_GLOBAL")) {
     // the common path: both merges on chip, straight from the raw hits of the last hop
     BoxSrc src{sink.boxes.get(), sink.prefix, sink.raw_hits.get(), sink.raw_tasks.get(),
-               sink.raw_has_orig ? sink.raw_orig.get() : nullptr, sink.level, p_.min_output_length};
+               sink.raw_has_orig ? sink.raw_orig.get() : nullptr, sink.level, p_.min_output_length, nullptr};
     done = merge_fused(src, sink.n, out, row_cnt.get());
   }
-  if (!done) {
-    // every other path works on one BoxD array
+  if (!done && comm_) {
+    // sharded index: every valid box travels to the owner of its query sequence first, so that a
+    // (row, q) segment is complete on one rank; what arrives is merged like an unsharded batch
+    DBuf<BoxD> recv;
+    uint64_t n_recv = 0;
+    {
+      BoxSrc src{sink.boxes.get(), sink.prefix, sink.raw_hits.get(), sink.raw_tasks.get(),
+                 sink.raw_has_orig ? sink.raw_orig.get() : nullptr, sink.level, p_.min_output_length, sink.raw_gmap};
+      route_boxes(src, sink.n, recv, n_recv);
+    }
+    sink.boxes.release();
+    sink.raw_hits.release();
+    sink.raw_tasks.release();
+    sink.raw_orig.release();
+    REQUIRE(n_recv < (1ull << 32), IMPGX_E_INVALID, "more than 2^32 results in one batch; lower IMPGX_ROWS_PER_BATCH");
+    bool fused = false;
+    if (n_recv > 0 && !getenv("IMPGX_MERGE_GLOBAL")) {
+      BoxSrc src{recv.get(), n_recv, nullptr, nullptr, nullptr, 0, -1, nullptr};
+      fused = merge_fused(src, n_recv, out, row_cnt.get());
+    }
+    if (n_recv > 0 && !fused) {
+      DBuf<BoxD> acc;
+      DBuf<uint64_t> is_root;
+      stage_a(recv.get(), n_recv, n_recv, acc, is_root);
+      stage_b(acc.get(), is_root.get(), n_recv, sink.counters.get() + 1, n_rows, out, row_cnt.get());
+    }
+  } else if (!done) {
+    // the remaining paths work on one BoxD array
     materialize_boxes(sink);
     const uint64_t nB = sink.n;
     unsigned long long nv = 0;
@@ -1417,31 +1444,11 @@ void Runner::bed_merge_direct(BedSink &sink, uint32_t n_rows, BatchOut &out) {
         OutCols oc = alloc_out_cols(out, nv);
         LAUNCH(k_boxd_to_cols, grid_threads(nv), 256, s_, sink.boxes.get(), perm.get(), (uint64_t)nv, oc, row_cnt.get());
       }
-    } else if (nv > 0 || comm_) {
-      // sharded index: every valid box travels to the owner of its query sequence first,
-      // so that a (row, q) segment is complete on one rank
-      const BoxD *bx = sink.boxes.get();
-      uint64_t n_in = nB, n_valid = nv;
-      DBuf<BoxD> recv;
-      if (comm_) {
-        uint64_t n_recv = 0;
-        route_boxes(sink.boxes.get(), nB, recv, n_recv);
-        sink.boxes.release();
-        bx = recv.get();
-        n_in = n_valid = n_recv;
-        REQUIRE(n_in < (1ull << 32), IMPGX_E_INVALID, "more than 2^32 results in one batch; lower IMPGX_ROWS_PER_BATCH");
-      }
-      bool fused = false;
-      if (n_valid > 0 && !getenv("IMPGX_MERGE_GLOBAL")) {
-        BoxSrc src{bx, n_in, nullptr, nullptr, nullptr, 0, -1};
-        fused = merge_fused(src, n_in, out, row_cnt.get());
-      }
-      if (n_valid > 0 && !fused) {
-        DBuf<BoxD> acc;
-        DBuf<uint64_t> is_root;
-        stage_a(bx, n_in, n_valid, acc, is_root);
-        stage_b(acc.get(), is_root.get(), n_valid, sink.counters.get() + 1, n_rows, out, row_cnt.get());
-      }
+    } else if (nv > 0) {
+      DBuf<BoxD> acc;
+      DBuf<uint64_t> is_root;
+      stage_a(sink.boxes.get(), nB, nv, acc, is_root);
+      stage_b(acc.get(), is_root.get(), nv, sink.counters.get() + 1, n_rows, out, row_cnt.get());
     }
   }
   LAUNCH(k_u32_to_u64, grid_threads(n_rows), 256, s_, row_cnt.get(), n_rows, out.row_off.get());
@@ -1459,8 +1466,9 @@ void Runner::bed_merge_direct(BedSink &sink, uint32_t n_rows, BatchOut &out) {
 // ============================================================ sharded index
 // Partition `n` records by destination rank (dest[i] in [0, N], N = "nowhere")
 // and exchange them: returns the received records, grouped by source rank.
-template <class T>
-static void exchange_by_dest(Comm &cm, const T *recs, DBuf<uint32_t> &dest, DBuf<uint32_t> &idx,
+// `gather(idx, count, send)` launches the kernel that writes record idx[i] to send[i].
+template <class T, class Gather>
+static void exchange_by_dest(Comm &cm, Gather gather, DBuf<uint32_t> &dest, DBuf<uint32_t> &idx,
                              const unsigned long long *d_dest_cnt, uint64_t n, DBuf<T> &recv, uint64_t &n_recv,
                              Arena &ar, Scratch &sc, cudaStream_t s, Ctx &ctx) {
   const int N = cm.size();
@@ -1486,7 +1494,7 @@ static void exchange_by_dest(Comm &cm, const T *recs, DBuf<uint32_t> &dest, DBuf
   if (n) {
     sort_pairs(dest, idx, n, 0, bits_for((uint64_t)N), sc, s, ctx);  // stable: source order kept per destination
     if (so) {
-      k_gather<T><<<grid_threads(so), 256, 0, s>>>(recs, idx.get(), so, send.get());
+      gather(idx.get(), so, send.get());
       CUDA_CHECK(cudaGetLastError());
       ctx.launches++;
     }
@@ -1520,7 +1528,11 @@ void Runner::route_hits(const Lifted &L, const uint32_t *gmap, LevelHits &lvl) {
     LAUNCH(k_route_hits, grid_threads(H), 256, s_, L.hits.get(), L.tasks.get(), L.d_orig, gmap, idx_->d_owner, H, N,
            routed.get(), dest.get(), idx.get(), dcnt.get());
   uint64_t n_recv = 0;
-  exchange_by_dest(cm, (const RoutedHit *)routed.get(), dest, idx, dcnt.get(), H, recv, n_recv, ar_, sc_, s_, ctx);
+  const RoutedHit *rp = routed.get();
+  cudaStream_t st = s_;
+  exchange_by_dest(
+      cm, [=](const uint32_t *ix, uint64_t cnt, RoutedHit *send) { k_gather<RoutedHit><<<grid_threads(cnt), 256, 0, st>>>(rp, ix, cnt, send); },
+      dest, idx, dcnt.get(), H, recv, n_recv, ar_, sc_, s_, ctx);
   lvl.n = n_recv;
   if (n_recv == 0) return;
   lvl.hits.alloc(n_recv, ar_);
@@ -1568,16 +1580,19 @@ void Runner::global_frontier(DBuf<Frontier> &fr, uint64_t &nF, DBuf<uint32_t> &g
   gmap = std::move(g2);
 }
 
-// Valid boxes travel to the owner of their query sequence (both BED merges group by (row, q)).
-void Runner::route_boxes(const BoxD *boxes, uint64_t nB, DBuf<BoxD> &recv, uint64_t &n_recv) {
+// Valid boxes travel to the owner of their query sequence (both BED merges group by (row, q));
+// they are gathered straight from the box source (raw hits of the last hop included).
+void Runner::route_boxes(const BoxSrc &src, uint64_t nB, DBuf<BoxD> &recv, uint64_t &n_recv) {
   Comm &cm = *comm_;
   const uint32_t N = (uint32_t)cm.size();
   DBuf<unsigned long long> dcnt(N + 1, ar_);
   CUDA_CHECK(cudaMemsetAsync(dcnt.get(), 0, (N + 1) * 8, s_));
   DBuf<uint32_t> dest(nB, ar_), idx(nB, ar_);
-  if (nB)
-    LAUNCH(k_box_dest, grid_threads(nB), 256, s_, boxes, nB, idx_->d_owner, N, dest.get(), idx.get(), dcnt.get());
-  exchange_by_dest(cm, boxes, dest, idx, dcnt.get(), nB, recv, n_recv, ar_, sc_, s_, ctx);
+  if (nB) LAUNCH(k_box_dest, grid_threads(nB), 256, s_, src, nB, idx_->d_owner, N, dest.get(), idx.get(), dcnt.get());
+  cudaStream_t st = s_;
+  exchange_by_dest(
+      cm, [=](const uint32_t *ix, uint64_t cnt, BoxD *send) { k_gather_src<<<grid_threads(cnt), 256, 0, st>>>(src, ix, cnt, send); },
+      dest, idx, dcnt.get(), nB, recv, n_recv, ar_, sc_, s_, ctx);
 }
 
 void Runner::run_sharded(const impgx_range *d_ranges, uint32_t n_rows, BatchOut &out) {
@@ -1655,23 +1670,31 @@ void Runner::run_sharded(const impgx_range *d_ranges, uint32_t n_rows, BatchOut 
     BoxD *dst = nullptr;
     lift_core(fr, nF, /*closed=*/!bfs, /*clip=*/bfs,
               [&](uint64_t H) {
-                if (last) {
-                  sink.prefix = (uint64_t)n_rows + prior;
-                  sink.boxes.alloc(sink.prefix + H, ar_);
-                  sink.n = sink.prefix + H;
-                  sink.filled = true;
-                  dst = sink.boxes.get() + sink.prefix;
-                } else {
+                if (!last) {
                   boxes_h.alloc(H, ar_);
                   dst = boxes_h.get();
                 }
               },
               L);
+    if (last) {
+      // the raw hits stay where the liftover wrote them; they are gathered into the send buffers
+      // of the box exchange with their global ordinals (BoxSrc)
+      if (L.H) {
+        sink.raw_hits = std::move(L.hits);
+        sink.raw_tasks = std::move(L.tasks);
+        sink.raw_has_orig = L.d_orig != nullptr;
+        if (sink.raw_has_orig) sink.raw_orig = std::move(L.orig);
+        sink.n_raw = L.H;
+        sink.raw_gmap = gmap.get();
+        sink.level = depth + 1;
+      }
+      sink.filled = true;
+      break;
+    }
     if (L.H)
       LAUNCH(k_boxes_from_raw_level, grid_threads(L.H), 256, s_, L.hits.get(), L.tasks.get(), L.d_orig, L.offs.get(),
              (const uint64_t *)nullptr, L.H, depth + 1, p_.min_output_length, dst, sink.counters.get(), gmap.get());
     depth++;
-    if (last) break;
     prior += L.H;
     level_n.push_back(L.H);
     level_boxes.push_back(std::move(boxes_h));
@@ -1685,11 +1708,9 @@ void Runner::run_sharded(const impgx_range *d_ranges, uint32_t n_rows, BatchOut 
   }
   {
     WallTimer wt(ctx.w_assemble);
-    if (!sink.filled) {
-      sink.prefix = (uint64_t)n_rows + prior;
-      sink.boxes.alloc(sink.prefix, ar_);
-      sink.n = sink.prefix;
-    }
+    sink.prefix = (uint64_t)n_rows + prior;
+    sink.boxes.alloc(sink.prefix, ar_);
+    sink.n = sink.prefix + sink.n_raw;
     LAUNCH(k_boxes_from_seeds, grid_threads(n_rows), 256, s_, d_ranges, n_rows, p_.min_output_length, bfs ? 0 : 1,
            sink.boxes.get(), sink.counters.get(), (const uint32_t *)idx_->d_owner, me);
     uint64_t off = n_rows;

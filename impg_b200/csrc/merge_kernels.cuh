@@ -287,6 +287,7 @@ struct BoxSrc {
   const uint32_t *orig;  // processing index -> frontier index of the hop, or nullptr
   uint32_t level;
   int32_t min_out;
+  const uint32_t *gmap;  // sharded index: local frontier index -> index in the GLOBAL frontier, or nullptr
 };
 __device__ __forceinline__ BoxD load_box(const BoxSrc &s, uint32_t i) {
   if (i < s.n_boxes) return s.boxes[i];
@@ -294,9 +295,13 @@ __device__ __forceinline__ BoxD load_box(const BoxSrc &s, uint32_t i) {
   const Hit h = s.hits[j];
   const bool ok = h.row != INVALID_ID && passes_len(h, s.min_out);
   const uint32_t k = s.tasks[j].range;
-  const uint32_t r = s.orig ? s.orig[k] : k;
+  uint32_t r = s.orig ? s.orig[k] : k;
+  r = s.gmap ? s.gmap[r] : r;
   return BoxD{h.q_first, h.q_last, h.t_first, h.t_last, h.q_id, h.t_id, h.row, ok ? 1u : 0u,
               make_ord(s.level, ((uint64_t)r << 32) | h.vrank)};
+}
+__global__ void k_gather_src(BoxSrc src, const uint32_t *__restrict__ idx, uint64_t n, BoxD *__restrict__ out) {
+  for (uint64_t i = gtid(); i < n; i += gstride()) out[i] = load_box(src, idx[i]);
 }
 
 // `owner` != nullptr (sharded index): only the rows on targets owned by `rank` are valid here

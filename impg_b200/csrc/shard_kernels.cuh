@@ -96,14 +96,24 @@ __global__ void k_frontier_take_owned(const Frontier *__restrict__ f, const uint
 }
 
 // valid boxes -> destination rank = owner of the query sequence (invalid ones go nowhere)
-__global__ void k_box_dest(const BoxD *__restrict__ boxes, uint64_t n, const uint32_t *__restrict__ owner,
+__global__ void k_box_dest(BoxSrc src, uint64_t n, const uint32_t *__restrict__ owner,
                            uint32_t n_ranks, uint32_t *__restrict__ dest, uint32_t *__restrict__ idx,
                            unsigned long long *__restrict__ dest_cnt) {
   __shared__ unsigned int bins[MAX_RANKS + 1];
   for (unsigned k = threadIdx.x; k <= n_ranks; k += blockDim.x) bins[k] = 0;
   __syncthreads();
   for (uint64_t i = gtid(); i < n; i += gstride()) {
-    const uint32_t d = boxes[i].valid ? owner[boxes[i].q_id] : n_ranks;
+    uint32_t q;
+    bool ok;
+    if (i < src.n_boxes) {
+      q = src.boxes[i].q_id;
+      ok = src.boxes[i].valid != 0;
+    } else {
+      const Hit h = src.hits[i - src.n_boxes];
+      q = h.q_id;
+      ok = h.row != INVALID_ID && passes_len(h, src.min_out);
+    }
+    const uint32_t d = ok ? owner[q] : n_ranks;
     dest[i] = d;
     idx[i] = (uint32_t)i;
     atomicAdd(&bins[d], 1u);
