@@ -22,7 +22,10 @@
  * merge functions and SortedRanges::insert, which no reference test pins —
  * they are restated literally from source; (3) sequence-id numbering, which
  * in the reference follows FxHashMap iteration order (src/main.rs:11527-11540)
- * — here ids are first-appearance order.
+ * — here ids are first-appearance order; (4) MultiImpg (src/multi_impg.rs:462-595,
+ * 796-991: per-file sub-indices, 5-key hit order, duplicate-self rule, sorted
+ * queue walk) and masked_regions (src/impg.rs:2331-2373, 2041-2055), which no
+ * reference test exercises — restated literally from source.
  */
 #include <algorithm>
 #include <cassert>
