@@ -21,6 +21,7 @@ static thread_local std::string g_last_error;
 void set_last_error(const std::string &m) { g_last_error = m; }
 const char *last_error() { return g_last_error.c_str(); }
 
+static uint64_t env_u64(const char *name, uint64_t dflt);
 static int g_sm_count = 0;
 static int sm_count() {
   if (!g_sm_count) {
@@ -1290,7 +1291,9 @@ bool Runner::merge_fused(const BoxSrc &src, uint64_t nB, BatchOut &out, uint32_t
     DBuf<uint32_t> lists((uint64_t)SEG_CLASSES * g.G, ar_);
     DBuf<unsigned int> cls(SEG_CLASSES + 1, ar_);
     CUDA_CHECK(cudaMemsetAsync(cls.get(), 0, (SEG_CLASSES + 1) * 4, s_));
-    LAUNCH(k_seg_classify, grid_threads(g.G), 256, s_, g.begins.get(), g.G, lists.get(), cls.get());
+    int min_class = (int)env_u64("IMPGX_SEG_MIN_CLASS", 0);  // test hook: run the larger-segment kernels on small data
+    if (min_class < 0 || min_class >= SEG_CLASSES) min_class = 0;
+    LAUNCH(k_seg_classify, grid_threads(g.G), 256, s_, g.begins.get(), g.G, lists.get(), cls.get(), min_class);
     unsigned int hc[SEG_CLASSES + 1];
     CUDA_CHECK(cudaMemcpyAsync(hc, cls.get(), sizeof(hc), cudaMemcpyDeviceToHost, s_));
     CUDA_CHECK(cudaStreamSynchronize(s_));

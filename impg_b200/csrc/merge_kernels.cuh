@@ -616,11 +616,12 @@ __global__ void k_heads_u64_shift(const uint64_t *__restrict__ keys, uint64_t n,
 }
 
 // segment -> size class list; cls[c] = segments of class c, cls[SEG_CLASSES] = segments too large
+// min_class > 0 pushes small segments into a larger class (tests run every kernel variant on small data)
 __global__ void k_seg_classify(const uint32_t *__restrict__ begins, uint64_t n_seg, uint32_t *__restrict__ lists,
-                               unsigned int *__restrict__ cls) {
+                               unsigned int *__restrict__ cls, int min_class) {
   for (uint64_t g = gtid(); g < n_seg; g += gstride()) {
     const uint32_t n = begins[g + 1] - begins[g];
-    int c = 0;
+    int c = min_class;
     while (c < SEG_CLASSES && n > (uint32_t)seg_cap(c)) c++;
     const unsigned int k = atomicAdd(&cls[c], 1u);
     if (c < SEG_CLASSES) lists[(uint64_t)c * n_seg + k] = (uint32_t)g;

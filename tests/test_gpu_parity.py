@@ -542,3 +542,45 @@ def test_device_resident_entry_on_a_side_stream(small):
     assert (dev(v.q_id, v.n_results, torch.int32).astype(np.uint32) == want["q_id"]).all()
     assert (dev(v.q_first, v.n_results, torch.int32) == want["q_first"]).all()
     assert (dev(v.q_last, v.n_results, torch.int32) == want["q_last"]).all()
+
+
+@pytest.mark.parametrize("min_class", [1, 2, 3, 4])
+def test_every_segment_kernel_variant(small, monkeypatch, min_class):
+    """The fused BED merge picks a kernel variant by segment size (warp: <= 128 / 256 boxes; CTA of
+    256 / 128 / 512 threads: <= 512 / 1024 / 4096). IMPGX_SEG_MIN_CLASS pushes the small segments of the
+    test world into the larger classes so that every variant is checked against the oracle."""
+    cfg, orc, gpu, bed = small
+    monkeypatch.setenv("IMPGX_SEG_MIN_CLASS", str(min_class))
+    b = bed[:120]
+    compare_bed(orc, gpu, b, *params_pair(mode=1, max_depth=2, merge_distance=1000))
+    compare_bed(orc, gpu, b, *params_pair(mode=1, max_depth=0, merge_distance=0, merge_strands=False))
+    compare_bed(orc, gpu, b, *params_pair(mode=1, max_depth=3, merge_distance=-1, merge_strands=True))
+    compare_bed(orc, gpu, b, *params_pair(mode=0, merge_distance=50000))
+
+
+def test_large_segments_and_global_fallback(monkeypatch):
+    """A world with few sequences and many alignments per pair: hundreds to thousands of boxes per
+    (row, sequence) segment, so the CTA variants run at their real sizes; with a tiny segment limit the
+    batch falls back to the global two-sort merge. All against the oracle."""
+    cfg = ix.synth_cfg(3, 1, 400000, 400, 12, 300, 17)
+    recs, runs, offs, lens, names = ix.synth_generate(cfg)
+    orc, gpu = build_both(recs, runs, offs, lens, names)
+    rows = np.array([(s, 1000 + 37 * k, 390000 - 91 * k) for s in range(3) for k in range(4)], ix.RANGE_DTYPE)
+    for d, ms in ((1000, True), (0, False), (-1, True)):
+        n = compare_bed(orc, gpu, rows, *params_pair(mode=1, max_depth=3, merge_distance=d, merge_strands=ms))
+    st = gpu.stats()
+    assert st["liftovers"] / len(rows) > 2000  # thousands of boxes per row over 3 sequences
+    monkeypatch.setenv("IMPGX_MERGE_GLOBAL", "1")
+    compare_bed(orc, gpu, rows, *params_pair(mode=1, max_depth=3, merge_distance=1000))
+
+
+def test_segment_beyond_the_largest_class_falls_back():
+    """One (row, sequence) segment with ~12,000 boxes (> 4096): the fused merge declines the batch and
+    the global two-sort path produces the same rows as the oracle."""
+    cfg = ix.synth_cfg(2, 1, 1600000, 6000, 8, 200, 23)
+    recs, runs, offs, lens, names = ix.synth_generate(cfg)
+    orc, gpu = build_both(recs, runs, offs, lens, names)
+    rows = np.array([(0, 0, 1600000), (1, 5, 1599000), (0, 1000, 2000)], ix.RANGE_DTYPE)
+    compare_bed(orc, gpu, rows, *params_pair(mode=0, merge_distance=10))
+    compare_bed(orc, gpu, rows, *params_pair(mode=0, merge_distance=0, merge_strands=False))
+    assert gpu.stats()["liftovers"] > 20000
