@@ -608,6 +608,16 @@ def main():
             cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                             "sample": f"first {n_used} of {rows} BED rows{note}, {tsec:.1f} s (oracle port with the reference's "
                                       "cost structure: rows serial, threads inside a BFS level, per-hit pread+parse)"}
+            # parity at full size on a row sample: the oracle's merged BED rows vs the C-ABI's, bit for bit
+            # (outside every timed region; the oracle is the checker, never the thing measured)
+            k = min(16, len(c_bed))
+            want, woffs = orc.query_batch(c_bed[:k], mode_params(O, name, is_oracle=True), bed_merge=True)
+            wc, gc = want.columns(), idx.query_batch_bed(c_bed[:k], p).columns()
+            exact = gc["row_offsets"].tolist() == woffs.tolist() and all(
+                (gc[c] == wc[c]).all() for c in ("q_id", "q_first", "q_last"))
+            cpu_baseline["parity_sample"] = {"rows": int(k), "bed_rows": int(len(wc["q_id"])), "bit_exact": bool(exact)}
+            if not exact:
+                raise SystemExit("bench.py: the CUDA path and the oracle disagree on the parity sample")
         finally:
             try:
                 os.unlink(path)
