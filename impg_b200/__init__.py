@@ -62,6 +62,48 @@ class Stats(C.Structure):
         return {f: getattr(self, f) for f, _ in self._fields_}
 
 
+class PartitionParams(C.Structure):
+    """impgx_partition_params (include/impgx.h)."""
+    _fields_ = [("window_size", C.c_uint64), ("starting_seqs", C.c_void_p), ("n_starting_seqs", C.c_size_t),
+                ("selection_mode", C.c_char_p), ("merge_distance", C.c_int32), ("min_missing_size", C.c_int32),
+                ("min_boundary_distance", C.c_int32), ("transitive_dfs", C.c_uint32), ("max_depth", C.c_uint32),
+                ("min_transitive_len", C.c_int32), ("min_distance_between_ranges", C.c_int32),
+                ("rehome_singletons", C.c_uint32), ("min_identity", C.c_double)]
+
+
+class PartitionView(C.Structure):
+    _fields_ = [("n_intervals", C.c_size_t), ("n_partitions", C.c_size_t), ("n_windows", C.c_uint64),
+                ("partitioned_bp", C.c_uint64), ("total_bp", C.c_uint64), ("partition_num", C.c_void_p),
+                ("seq_id", C.c_void_p), ("start", C.c_void_p), ("end", C.c_void_p)]
+
+
+def make_partition_params(window_size, merge_distance, starting_seqs=None, selection_mode="longest",
+                          min_missing_size=3000, min_boundary_distance=3000, transitive_dfs=False, max_depth=2,
+                          min_transitive_len=101, min_distance_between_ranges=10, rehome_singletons=True,
+                          min_identity=None):
+    """Arguments of partition_alignments (reference src/commands/partition.rs:158-181); defaults are
+    `impg partition`'s CLI defaults (src/main.rs:4765-4880, :4259-4279). -d has no default there."""
+    p = PartitionParams()
+    p.window_size = window_size
+    if starting_seqs is not None and len(starting_seqs):
+        a = np.ascontiguousarray(starting_seqs, dtype=np.uint32)
+        p._keep = a
+        p.starting_seqs, p.n_starting_seqs = a.ctypes.data, len(a)
+    else:
+        p.starting_seqs, p.n_starting_seqs = None, 0
+    p.selection_mode = selection_mode.encode() if selection_mode is not None else None
+    p.merge_distance = merge_distance
+    p.min_missing_size = min_missing_size
+    p.min_boundary_distance = min_boundary_distance
+    p.transitive_dfs = 1 if transitive_dfs else 0
+    p.max_depth = max_depth
+    p.min_transitive_len = min_transitive_len
+    p.min_distance_between_ranges = min_distance_between_ranges
+    p.rehome_singletons = 1 if rehome_singletons else 0
+    p.min_identity = float("nan") if min_identity is None else float(min_identity)
+    return p
+
+
 class SynthCfg(C.Structure):
     _fields_ = [("genomes", C.c_uint32), ("contigs", C.c_uint32), ("contig_len", C.c_uint32), ("tiles", C.c_uint32),
                 ("eq_mean", C.c_uint32), ("rev_permille", C.c_uint32), ("seed", C.c_uint64)]
@@ -131,6 +173,7 @@ def lib():
         L.impgx_format_bedpe.restype = C.c_void_p
         L.impgx_format_paf.restype = C.c_void_p
         L.impgx_synth_num_alignments.restype = C.c_uint64
+        L.impgx_partitions_format_bed.restype = C.c_void_p
         L.impgx_debug_host_columns.restype = C.c_long
         L.impgx_debug_host_columns_shard.restype = C.c_long
         _lib = L
@@ -363,6 +406,13 @@ class Impg:
         r = self.query_batch(np.array([(target_id, range_start, range_end)], dtype=RANGE_DTYPE), p)
         return r.row_tuples(0)
 
+    def partition(self, params):
+        """`impg partition -o bed` on this index (reference src/commands/partition.rs:158-712): one masked
+        transitive query + BED merge on the device per window."""
+        h = C.c_void_p()
+        _check(lib().impgx_partition(self.h, C.byref(params), C.byref(h)))
+        return Partitions(h.value)
+
     def format_bed(self, results, row, name):
         ptr = lib().impgx_format_bed(self.h, results.h, C.c_size_t(row), name.encode())
         if not ptr:
@@ -370,6 +420,85 @@ class Impg:
         s = C.string_at(ptr).decode()
         lib().impgx_free(C.c_void_p(ptr))
         return s
+
+
+class Partitions:
+    """Collected partitions (rows of partitions.bed, reference src/commands/partition.rs:1682-1717)."""
+
+    def __init__(self, handle):
+        self.h = C.c_void_p(handle)
+        v = PartitionView()
+        _check(lib().impgx_partitions_view(self.h, C.byref(v)))
+        n = v.n_intervals
+        arr = Results._arr
+        self.partition_num = arr(None, v.partition_num, n, np.uint32)
+        self.seq_id = arr(None, v.seq_id, n, np.uint32)
+        self.start = arr(None, v.start, n, np.int32)
+        self.end = arr(None, v.end, n, np.int32)
+        self.n_partitions, self.n_windows = v.n_partitions, v.n_windows
+        self.partitioned_bp, self.total_bp = v.partitioned_bp, v.total_bp
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().impgx_partitions_free(self.h)
+            self.h = None
+
+    def rows(self):
+        return list(zip(self.partition_num.tolist(), self.seq_id.tolist(), self.start.tolist(), self.end.tolist()))
+
+    def format_bed(self, impg, partition=-1):
+        """partitions.bed (partition < 0) or partition<N>.bed of --separate-files."""
+        ptr = lib().impgx_partitions_format_bed(impg.h, self.h, C.c_int64(partition))
+        if not ptr:
+            raise ImpgxError(E_INVALID, "format failed")
+        s = C.string_at(ptr).decode()
+        lib().impgx_free(C.c_void_p(ptr))
+        return s
+
+
+class Partitioner:
+    """partition_alignments as a stepper over any ImpgIndex implementor: `next()` hands out the next
+    window and the current masked_regions (CSR), the caller runs the transitive query and `feed`s the
+    query intervals back (reference src/commands/partition.rs:295-580)."""
+
+    def __init__(self, seq_lens, params, names=None):
+        lens = np.ascontiguousarray(seq_lens, dtype=np.uint64)
+        self.n_seqs = len(lens)
+        nm = None
+        if names is not None:
+            nm = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        h = C.c_void_p()
+        _check(lib().impgx_partitioner_new(_p(lens), nm, C.c_uint32(len(lens)), C.byref(params), C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().impgx_partitioner_free(self.h)
+            self.h = None
+
+    def next(self):
+        """(target_id, start, end), (mask_offsets, mask_ranges) or None when no window is left."""
+        w = np.zeros(1, RANGE_DTYPE)
+        mo, mr = C.c_void_p(), C.c_void_p()
+        r = lib().impgx_partitioner_next(self.h, _p(w), C.byref(mo), C.byref(mr))
+        if r < 0:
+            _check(r)
+        if r == 0:
+            return None
+        offs = Results._arr(None, mo.value, self.n_seqs + 1, np.uint64)
+        rng = Results._arr(None, mr.value, max(2 * int(offs[-1]), 2), np.int32)
+        return (int(w[0]["target_id"]), int(w[0]["start"]), int(w[0]["end"])), (offs, rng)
+
+    def feed(self, q_id, q_first, q_last):
+        a = np.ascontiguousarray(q_id, np.uint32)
+        b = np.ascontiguousarray(q_first, np.int32)
+        c = np.ascontiguousarray(q_last, np.int32)
+        _check(lib().impgx_partitioner_feed(self.h, C.c_size_t(len(a)), _p(a), _p(b), _p(c)))
+
+    def finish(self):
+        h = C.c_void_p()
+        _check(lib().impgx_partitioner_finish(self.h, C.byref(h)))
+        return Partitions(h.value)
 
 
 class MultiImpg:

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define IMPGX_ABI_VERSION 3
+#define IMPGX_ABI_VERSION 4
 
 typedef enum impgx_status {
   IMPGX_OK = 0,
@@ -314,6 +314,73 @@ char *impgx_format_bedpe(const impgx_index *idx, const impgx_results *res,
 char *impgx_format_paf(const impgx_index *idx, const impgx_results *res,
                        size_t row, const char *name, int32_t merge_distance);
 void impgx_free(void *p);
+
+/* ---- partition: the second driver of the same kernels ----
+ * partition_alignments (src/commands/partition.rs:158-712) for `-o bed`: windows are
+ * taken from the sequences still missing, each window runs ONE transitive query with
+ * the regions already assigned as masked_regions and store_cigar = false
+ * (:359-391); its query intervals are merged (merge_overlaps :939-976), pulled to close
+ * sequence ends (extend_to_close_boundaries :1369-1408), cut by the mask which they then
+ * join (mask_and_update_regions :978-1366), merged again with distance 0 and become one
+ * partition. Windows are inherently sequential (each depends on the mask the previous one
+ * left), so the device runs one masked BFS + BED merge per window; the bookkeeping between
+ * windows is host code. Only min/max of an interval reach `partitions.bed` (:1509-1542,
+ * :1682-1717), so intervals are reported as start < end. */
+typedef struct impgx_partition_params {
+  uint64_t window_size;                /* -w */
+  const uint32_t *starting_seqs;       /* --starting-sequences-file after name->id (:184-247), file order; NULL = none */
+  size_t n_starting_seqs;
+  const char *selection_mode;          /* "longest" (default when NULL) | "total" | "sample[,sep]" | "haplotype[,sep]" (:715-937) */
+  int32_t merge_distance;              /* -d; < 0 = --no-merge */
+  int32_t min_missing_size;            /* --min-missing-size (default 3000) */
+  int32_t min_boundary_distance;       /* --min-boundary-distance (default 3000) */
+  uint32_t transitive_dfs;             /* --transitive-dfs */
+  uint32_t max_depth;                  /* -m (default 2; 0 = unlimited) */
+  int32_t min_transitive_len;          /* default 101 */
+  int32_t min_distance_between_ranges; /* default 10 */
+  uint32_t rehome_singletons;          /* !--no-rehome-singletons (rehome_singleton_slivers :45-156) */
+  double min_identity;                 /* --min-result-identity; NaN = None */
+} impgx_partition_params;
+
+typedef struct impgx_partitions impgx_partitions;
+typedef struct impgx_partition_view {
+  size_t n_intervals;            /* rows of partitions.bed */
+  size_t n_partitions;           /* partitions computed (partition_num of the next one) */
+  uint64_t n_windows;            /* windows queried */
+  uint64_t partitioned_bp;       /* total_partitioned_length (:447) */
+  uint64_t total_bp;             /* total_sequence_length (:271-274) */
+  const uint32_t *partition_num; /* per interval, non-decreasing */
+  const uint32_t *seq_id;
+  const int32_t *start;
+  const int32_t *end;
+} impgx_partition_view;
+
+/* The whole window loop on an index resident in HBM (every window = one masked transitive
+ * query + BED merge on the device). Sequence names (impgx_index_set_names / the PAF) are
+ * needed for the sample / haplotype selection modes only. */
+int impgx_partition(impgx_index *idx, const impgx_partition_params *params, impgx_partitions **out);
+int impgx_partitions_view(const impgx_partitions *parts, impgx_partition_view *view);
+/* write_single_partition_file (:1682-1717; partition < 0: "name\tstart\tend\tpartition_num")
+ * or write_partition_bed of one partition (:1509-1542; "name\tstart\tend"). malloc'ed, impgx_free. */
+char *impgx_partitions_format_bed(const impgx_index *idx, const impgx_partitions *parts, int64_t partition);
+void impgx_partitions_free(impgx_partitions *parts);
+
+/* The same loop as a stepper over ANY ImpgIndex implementor (what partition_alignments is
+ * generic over, :159): next() hands out the next window together with the current
+ * masked_regions (CSR over all sequences, valid until the next call on the object), the
+ * caller runs query_transitive_bfs/dfs on it and feeds the query intervals back. */
+typedef struct impgx_partitioner impgx_partitioner;
+int impgx_partitioner_new(const uint64_t *seq_lens, const char *const *names /* NULL unless sample/haplotype */,
+                          uint32_t n_seqs, const impgx_partition_params *params, impgx_partitioner **out);
+/* returns 1 with *window filled, 0 when no window is left, < 0 on error */
+int impgx_partitioner_next(impgx_partitioner *p, impgx_range *window, const uint64_t **mask_offsets,
+                           const int32_t **mask_ranges);
+/* overlaps of the window in the order the query returned them (first > last on the reverse strand) */
+int impgx_partitioner_feed(impgx_partitioner *p, size_t n, const uint32_t *q_id, const int32_t *q_first,
+                           const int32_t *q_last);
+/* rehomes singletons if asked and returns the collected partitions; the stepper stays valid */
+int impgx_partitioner_finish(impgx_partitioner *p, impgx_partitions **out);
+void impgx_partitioner_free(impgx_partitioner *p);
 
 #ifdef __cplusplus
 }

@@ -1915,6 +1915,504 @@ void *orc_multi_query_batch(void *h, const impgx_range *ranges, size_t n, const 
   return all;
 }
 
+}  // extern "C"
+
+// ================================================================ partition
+// src/commands/partition.rs — the `-o bed` path of partition_alignments. PARITY
+// UNPINNED: the reference's only test of it (tests/test_transitive_integrity.rs:592-646)
+// asserts ">= 2 output lines" on one inline PAF (replayed in tests/test_oracle_partition.py);
+// everything below is restated literally from source. Two places depend on FxHashMap
+// iteration order in the reference and are fixed here instead: the order of the sequences
+// of the selected sample / haplotype group with equal lengths (sort_unstable_by on a
+// hash-ordered Vec, :877-885) — here (length desc, id asc). Target intervals carried
+// through mask_and_update_regions (f64 rescaling, :1120-1140, :1178-1226) never reach
+// any partition output and are not restated.
+namespace {
+
+struct PInterval {  // Interval<u32>{first, last, metadata} — the query interval of an overlap
+  int32_t first, last;
+  uint32_t metadata;
+};
+
+// :939-976
+void merge_overlaps(std::vector<PInterval> &overlaps, int32_t merge_distance) {
+  if (overlaps.size() > 1 && merge_distance >= 0) {
+    std::stable_sort(overlaps.begin(), overlaps.end(), [](const PInterval &a, const PInterval &b) {
+      int32_t am = std::min(a.first, a.last), bm = std::min(b.first, b.last);
+      return a.metadata != b.metadata ? a.metadata < b.metadata : am < bm;
+    });
+    size_t write_idx = 0;
+    for (size_t read_idx = 1; read_idx < overlaps.size(); read_idx++) {
+      const PInterval &curr = overlaps[write_idx], &next = overlaps[read_idx];
+      int32_t curr_min = std::min(curr.first, curr.last), curr_max = std::max(curr.first, curr.last);
+      int32_t next_min = std::min(next.first, next.last), next_max = std::max(next.first, next.last);
+      if (curr.metadata != next.metadata || next_min > curr_max + merge_distance) {
+        write_idx += 1;
+        if (write_idx != read_idx) std::swap(overlaps[write_idx], overlaps[read_idx]);
+      } else {
+        overlaps[write_idx].first = std::min(curr_min, next_min);
+        overlaps[write_idx].last = std::max(curr_max, next_max);
+      }
+    }
+    overlaps.resize(write_idx + 1);
+  }
+}
+
+// :1369-1408 (query side)
+void extend_to_close_boundaries(std::vector<PInterval> &overlaps, const std::vector<uint64_t> &seq_lens,
+                                int32_t min_boundary_distance) {
+  for (auto &q : overlaps) {
+    int32_t seq_len = (int32_t)seq_lens[q.metadata];
+    bool is_forward = q.first <= q.last;
+    if (is_forward) {
+      if (q.first < min_boundary_distance) q.first = 0;
+      if (seq_len - q.last < min_boundary_distance) q.last = seq_len;
+    } else {
+      if (q.last < min_boundary_distance) q.last = 0;
+      if (seq_len - q.first < min_boundary_distance) q.first = seq_len;
+    }
+  }
+}
+
+typedef std::map<uint32_t, SortedRanges> RegionMap;
+
+// binary_search_by_key(&key, |&(s,_)| s) then "previous range might overlap" (:1010-1028 and twins)
+size_t search_from(const SortedRanges &r, int32_t key) {
+  size_t pos = r.bsearch(key);
+  if (pos < r.ranges.size() && r.ranges[pos].first == key) return pos;  // Ok(pos)
+  if (pos > 0 && r.ranges[pos - 1].second > key) return pos - 1;
+  return pos;
+}
+
+// :984-1319
+void process_sequence_overlaps(uint32_t seq_id, std::vector<PInterval> &seq_overlaps, RegionMap &masked_regions,
+                               RegionMap &missing_regions, int32_t min_fragment_size, std::vector<PInterval> &result) {
+  if (seq_overlaps.empty()) return;
+  std::vector<std::pair<int32_t, int32_t>> extensions, mask_buffer;
+  auto mit = missing_regions.find(seq_id);
+  if (mit != missing_regions.end()) {
+    const SortedRanges &missing = mit->second;
+    for (auto &q : seq_overlaps) {
+      int32_t mask_start = std::min(q.first, q.last), mask_end = std::max(q.first, q.last);
+      for (size_t i = search_from(missing, mask_start); i < missing.ranges.size(); i++) {
+        int32_t miss_start = missing.ranges[i].first, miss_end = missing.ranges[i].second;
+        if (miss_start > mask_end) break;
+        if (mask_start > miss_start && mask_start < miss_end && mask_start - miss_start < min_fragment_size &&
+            mask_start - miss_start > 0)
+          extensions.push_back({miss_start, mask_start});
+        if (mask_end > miss_start && mask_end < miss_end && miss_end - mask_end < min_fragment_size &&
+            miss_end - mask_end > 0)
+          extensions.push_back({mask_end, miss_end});
+      }
+    }
+  }
+  if (!extensions.empty()) {
+    std::stable_sort(extensions.begin(), extensions.end(),
+                     [](const std::pair<int32_t, int32_t> &a, const std::pair<int32_t, int32_t> &b) { return a.first < b.first; });
+    size_t write = 0;
+    for (size_t read = 1; read < extensions.size(); read++) {
+      if (extensions[read].first <= extensions[write].second) {
+        extensions[write].second = std::max(extensions[write].second, extensions[read].second);
+      } else {
+        write += 1;
+        if (write != read) std::swap(extensions[write], extensions[read]);
+      }
+    }
+    extensions.resize(write + 1);
+  }
+  for (auto &q : seq_overlaps) {
+    bool fwd = q.first <= q.last;
+    int32_t start = std::min(q.first, q.last), end = std::max(q.first, q.last);
+    for (auto &ex : extensions) {
+      if ((ex.second >= start && ex.first <= start) || (ex.first <= end && ex.second >= end)) {
+        if (ex.first < start) start = ex.first;
+        if (ex.second > end) end = ex.second;
+      }
+    }
+    mask_buffer.push_back({start, end});
+    auto kit = masked_regions.find(seq_id);
+    if (kit != masked_regions.end()) {
+      const SortedRanges &masks = kit->second;
+      int32_t curr_pos = start;
+      size_t idx = search_from(masks, curr_pos);
+      while (idx < masks.ranges.size()) {
+        int32_t mask_start = masks.ranges[idx].first, mask_end = masks.ranges[idx].second;
+        if (mask_start > end) break;
+        if (mask_end <= curr_pos) {
+          idx += 1;
+          continue;
+        }
+        if (curr_pos < mask_start)
+          result.push_back(fwd ? PInterval{curr_pos, mask_start, q.metadata} : PInterval{mask_start, curr_pos, q.metadata});
+        curr_pos = std::max(curr_pos, mask_end);
+        idx += 1;
+        if (curr_pos >= end) break;
+      }
+      if (curr_pos < end)
+        result.push_back(fwd ? PInterval{curr_pos, end, q.metadata} : PInterval{end, curr_pos, q.metadata});
+    } else {
+      result.push_back(fwd ? PInterval{start, end, q.metadata} : PInterval{end, start, q.metadata});
+    }
+  }
+  seq_overlaps.clear();
+  SortedRanges &masked = masked_regions[seq_id];  // entry().or_default()
+  for (auto &m : mask_buffer) masked.insert(m);
+  mit = missing_regions.find(seq_id);
+  if (mit != missing_regions.end()) {
+    SortedRanges &missing = mit->second;
+    std::vector<std::pair<int32_t, int32_t>> original_missing;
+    original_missing.swap(missing.ranges);
+    for (auto &mr : original_missing) {
+      int32_t miss_start = mr.first, miss_end = mr.second, current = miss_start;
+      size_t idx = search_from(masked, miss_start);
+      while (idx < masked.ranges.size() && current < miss_end) {
+        int32_t mask_start = masked.ranges[idx].first, mask_end = masked.ranges[idx].second;
+        if (mask_start > miss_end) break;
+        if (mask_end <= current) {
+          idx += 1;
+          continue;
+        }
+        if (current < mask_start) missing.insert({current, mask_start});
+        current = std::max(current, mask_end);
+        idx += 1;
+      }
+      if (current < miss_end) missing.insert({current, miss_end});
+    }
+    if (missing.ranges.empty()) missing_regions.erase(mit);
+  }
+}
+
+// :978-1366
+std::vector<PInterval> mask_and_update_regions(std::vector<PInterval> &overlaps, RegionMap &masked_regions,
+                                               RegionMap &missing_regions, int32_t min_fragment_size) {
+  std::vector<PInterval> result;
+  if (overlaps.empty()) return result;
+  std::vector<PInterval> seq_overlaps;
+  uint32_t current_seq = overlaps[0].metadata;
+  for (auto &iv : overlaps) {
+    if (iv.metadata != current_seq) {
+      process_sequence_overlaps(current_seq, seq_overlaps, masked_regions, missing_regions, min_fragment_size, result);
+      seq_overlaps.clear();
+      current_seq = iv.metadata;
+    }
+    seq_overlaps.push_back(iv);
+  }
+  overlaps.clear();
+  process_sequence_overlaps(current_seq, seq_overlaps, masked_regions, missing_regions, min_fragment_size, result);
+  return result;
+}
+
+// :715-937
+bool select_and_window_sequences(std::vector<impgx_range> &windows, const Index &idx, const RegionMap &missing_regions,
+                                 const std::string &selection_mode, int64_t window_size) {
+  std::vector<impgx_range> ranges_to_window;
+  if (selection_mode == "longest") {
+    bool have = false;
+    uint32_t bid = 0;
+    int32_t bs = 0, be = 0, blen = 0;
+    for (auto &kv : missing_regions)
+      for (auto &r : kv.second.ranges) {
+        int32_t length = r.second - r.first;
+        // max_by((len, id)): on equal keys the later element wins (reduce keeps b unless a > b)
+        if (!have || length > blen || (length == blen && kv.first >= bid)) {
+          have = true;
+          bid = kv.first;
+          bs = r.first;
+          be = r.second;
+          blen = length;
+        }
+      }
+    if (have) ranges_to_window.push_back({bid, bs, be});
+  } else if (selection_mode == "total") {
+    bool have = false;
+    uint32_t bid = 0;
+    int64_t bm = 0;
+    for (auto &kv : missing_regions) {
+      int64_t total = 0;
+      for (auto &r : kv.second.ranges) total += (int64_t)(r.second - r.first);
+      if (!have || total > bm || (total == bm && kv.first > bid)) {
+        have = true;
+        bid = kv.first;
+        bm = total;
+      }
+    }
+    if (have) ranges_to_window.push_back({bid, 0, (int32_t)idx.seq_lens[bid]});
+  } else if (selection_mode == "sample" || selection_mode == "haplotype" || selection_mode.rfind("sample,", 0) == 0 ||
+             selection_mode.rfind("haplotype,", 0) == 0) {
+    size_t comma = selection_mode.find(',');
+    std::string field_type = comma == std::string::npos ? selection_mode : selection_mode.substr(0, comma);
+    std::string separator = comma == std::string::npos ? "#" : selection_mode.substr(comma + 1);
+    int field_count = field_type == "haplotype" ? 2 : 1;
+    // str::split(separator): an empty separator splits around every char with empty first and last pieces
+    auto split = [&](const std::string &name) {
+      std::vector<std::string> parts;
+      if (separator.empty()) {
+        parts.push_back("");
+        for (char c : name) parts.push_back(std::string(1, c));  // (bytes; names here are ASCII)
+        parts.push_back("");
+        return parts;
+      }
+      size_t pos = 0;
+      for (;;) {
+        size_t f = name.find(separator, pos);
+        if (f == std::string::npos) {
+          parts.push_back(name.substr(pos));
+          break;
+        }
+        parts.push_back(name.substr(pos, f - pos));
+        pos = f + separator.size();
+      }
+      return parts;
+    };
+    std::map<std::string, std::vector<uint32_t>> prefix_to_seqs;
+    for (auto &kv : missing_regions) {
+      const std::string &name = idx.names[kv.first];
+      auto parts = split(name);
+      std::string prefix;
+      if (field_count == 1) prefix = parts[0];
+      else prefix = parts[0] + separator + (parts.size() > 1 ? parts[1] : std::string());
+      prefix_to_seqs[prefix].push_back(kv.first);
+    }
+    bool have = false;
+    std::string best_prefix;
+    int64_t best_missing = 0;
+    for (auto &kv : prefix_to_seqs) {  // ascending prefix: the later of equal maxima = the greater prefix
+      int64_t missing = 0;
+      for (uint32_t id : kv.second)
+        for (auto &r : missing_regions.at(id).ranges) missing += (int64_t)(r.second - r.first);
+      if (!have || missing >= best_missing) {
+        have = true;
+        best_prefix = kv.first;
+        best_missing = missing;
+      }
+    }
+    if (have) {
+      std::vector<std::pair<uint32_t, uint64_t>> seqs_with_len;
+      for (uint32_t id : prefix_to_seqs[best_prefix]) seqs_with_len.push_back({id, idx.seq_lens[id]});
+      std::sort(seqs_with_len.begin(), seqs_with_len.end(),
+                [](const std::pair<uint32_t, uint64_t> &a, const std::pair<uint32_t, uint64_t> &b) {
+                  return a.second != b.second ? a.second > b.second : a.first < b.first;
+                });
+      for (auto &sl : seqs_with_len) ranges_to_window.push_back({sl.first, 0, (int32_t)sl.second});
+    }
+  } else {
+    return false;
+  }
+  for (auto &r : ranges_to_window) {
+    std::vector<impgx_range> range_windows;
+    int32_t pos = r.start;
+    while (pos < r.end) {
+      int32_t window_end = (int32_t)std::min<int64_t>((int64_t)pos + window_size, r.end);
+      if ((int64_t)(window_end - pos) < window_size && !range_windows.empty()) range_windows.back().end = r.end;
+      else range_windows.push_back({r.target_id, pos, window_end});
+      pos = window_end;
+    }
+    windows.insert(windows.end(), range_windows.begin(), range_windows.end());
+  }
+  return true;
+}
+
+typedef std::vector<std::pair<size_t, std::vector<PInterval>>> Collected;
+
+// :45-156
+void rehome_singleton_slivers(Collected &collected_partitions) {
+  if (collected_partitions.empty()) return;
+  struct Row {
+    uint32_t c;
+    int32_t s, e;
+    size_t pidx;
+    PInterval iv;
+  };
+  std::vector<Row> rows;
+  for (size_t pidx = 0; pidx < collected_partitions.size(); pidx++)
+    for (auto &iv : collected_partitions[pidx].second)
+      rows.push_back({iv.metadata, std::min(iv.first, iv.last), std::max(iv.first, iv.last), pidx, iv});
+  std::stable_sort(rows.begin(), rows.end(), [](const Row &a, const Row &b) {
+    return std::tie(a.c, a.s, a.e) < std::tie(b.c, b.s, b.e);
+  });
+  std::vector<size_t> counts(collected_partitions.size(), 0);
+  for (auto &r : rows) counts[r.pidx] += 1;
+  size_t initial_singletons = 0;
+  for (size_t c : counts) initial_singletons += c == 1;
+  if (initial_singletons == 0) return;
+  int pass = 0;
+  for (;;) {
+    pass += 1;
+    std::vector<char> singleton(counts.size());
+    for (size_t i = 0; i < counts.size(); i++) singleton[i] = counts[i] == 1;
+    std::vector<std::pair<size_t, size_t>> pending;
+    for (size_t i = 0; i < rows.size(); i++) {
+      const Row &r = rows[i];
+      if (!singleton[r.pidx]) continue;
+      bool has_left = i > 0 && rows[i - 1].c == r.c && rows[i - 1].e == r.s;
+      bool has_right = i + 1 < rows.size() && rows[i + 1].c == r.c && rows[i + 1].s == r.e;
+      size_t lp = has_left ? rows[i - 1].pidx : 0, rp = has_right ? rows[i + 1].pidx : 0;
+      bool ls = has_left && !singleton[lp], rs = has_right && !singleton[rp];
+      size_t target;
+      if (ls && rs) target = counts[lp] >= counts[rp] ? lp : rp;
+      else if (ls) target = lp;
+      else if (rs) target = rp;
+      else continue;
+      if (target != r.pidx) pending.push_back({i, target});
+    }
+    if (pending.empty() || pass > 100) break;
+    for (auto &pd : pending) {
+      size_t old_pidx = rows[pd.first].pidx;
+      counts[old_pidx] -= 1;
+      counts[pd.second] += 1;
+      rows[pd.first].pidx = pd.second;
+    }
+  }
+  std::vector<std::vector<PInterval>> new_intervals(collected_partitions.size());
+  for (auto &r : rows) new_intervals[r.pidx].push_back(r.iv);
+  Collected rebuilt;
+  for (size_t i = 0; i < collected_partitions.size(); i++)
+    if (!new_intervals[i].empty()) rebuilt.push_back({collected_partitions[i].first, std::move(new_intervals[i])});
+  collected_partitions.swap(rebuilt);
+}
+
+struct PartitionOut {
+  std::vector<uint32_t> pnum, seq;
+  std::vector<int32_t> first, last;
+  std::vector<impgx_range> windows;  // every window queried, in order
+  uint64_t n_partitions = 0, partitioned_bp = 0, total_bp = 0;
+  std::string error;
+};
+
+// :158-712, output_format "bed", separate_files = false (single partitions.bed)
+void partition_alignments(const Index &idx, const impgx_partition_params &pp, int threads, PartitionOut &out) {
+  const int64_t window_size = (int64_t)pp.window_size;
+  const std::string selection_mode = pp.selection_mode ? pp.selection_mode : "longest";
+  const uint32_t n_seqs = (uint32_t)idx.seq_lens.size();
+  std::vector<impgx_range> windows;
+  for (size_t k = 0; k < pp.n_starting_seqs; k++) {  // :184-247
+    uint32_t seq_id = pp.starting_seqs[k];
+    int32_t start = 0, end = (int32_t)idx.seq_lens[seq_id];
+    int32_t pos = start;
+    while (pos < end) {
+      int32_t window_end = (int32_t)std::min<int64_t>((int64_t)pos + window_size, end);
+      if ((int64_t)(window_end - pos) < window_size && !windows.empty() && windows.back().target_id == seq_id) {
+        windows.back().end = end;
+        break;
+      }
+      windows.push_back({seq_id, pos, window_end});
+      pos = window_end;
+    }
+  }
+  RegionMap masked_regions, missing_regions;
+  for (uint32_t id = 0; id < n_seqs; id++) {
+    int32_t len = (int32_t)idx.seq_lens[id];
+    masked_regions.emplace(id, SortedRanges(len, 0));
+    SortedRanges r(len, 0);
+    r.insert({0, len});
+    missing_regions.emplace(id, std::move(r));
+    out.total_bp += idx.seq_lens[id];
+  }
+  size_t partition_num = 0;
+  if (windows.empty() && !select_and_window_sequences(windows, idx, missing_regions, selection_mode, window_size)) {
+    out.error = "Invalid selection mode";
+    return;
+  }
+  Collected collected_partitions;
+  QParams q;
+  q.max_depth = pp.max_depth;
+  q.min_transitive_len = pp.min_transitive_len;
+  q.min_distance_between_ranges = pp.min_distance_between_ranges;
+  q.min_output_length = -1;
+  q.store_cigar = false;
+  q.min_identity = pp.min_identity;
+  q.subset_mask = nullptr;
+  std::vector<uint64_t> mask_off(n_seqs + 1);
+  std::vector<int32_t> mask_rng;
+  while (!windows.empty()) {
+    std::vector<impgx_range> drained;
+    drained.swap(windows);
+    for (auto &w : drained) {
+      out.windows.push_back(w);
+      mask_rng.clear();
+      for (uint32_t id = 0; id < n_seqs; id++) {
+        mask_off[id] = mask_rng.size() / 2;
+        for (auto &r : masked_regions[id].ranges) {
+          mask_rng.push_back(r.first);
+          mask_rng.push_back(r.second);
+        }
+      }
+      mask_off[n_seqs] = mask_rng.size() / 2;
+      q.mask_offsets = mask_off.data();
+      q.mask_ranges = mask_rng.data();
+      std::vector<Result> res = pp.transitive_dfs ? query_transitive_dfs(idx, w.target_id, w.start, w.end, q)
+                                                  : query_transitive_bfs(idx, w.target_id, w.start, w.end, q, threads);
+      std::vector<PInterval> overlaps;
+      overlaps.reserve(res.size());
+      for (auto &r : res) overlaps.push_back({r.q_first, r.q_last, r.q_id});
+      merge_overlaps(overlaps, pp.merge_distance);
+      if (pp.min_boundary_distance > 0) extend_to_close_boundaries(overlaps, idx.seq_lens, pp.min_boundary_distance);
+      overlaps = mask_and_update_regions(overlaps, masked_regions, missing_regions, pp.min_missing_size);
+      if (!overlaps.empty()) {
+        merge_overlaps(overlaps, 0);
+        for (auto &iv : overlaps) out.partitioned_bp += (uint64_t)std::abs(iv.last - iv.first);
+        collected_partitions.push_back({partition_num, overlaps});
+        partition_num += 1;
+      }
+    }
+    if (!select_and_window_sequences(windows, idx, missing_regions, selection_mode, window_size)) {
+      out.error = "Invalid selection mode";
+      return;
+    }
+  }
+  if (pp.rehome_singletons && !collected_partitions.empty()) rehome_singleton_slivers(collected_partitions);
+  out.n_partitions = partition_num;
+  for (auto &cp : collected_partitions)
+    for (auto &iv : cp.second) {
+      out.pnum.push_back((uint32_t)cp.first);
+      out.seq.push_back(iv.metadata);
+      out.first.push_back(iv.first);
+      out.last.push_back(iv.last);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+void *orc_partition(void *h, const impgx_partition_params *pp, int threads) {
+  PartitionOut *o = new PartitionOut();
+  partition_alignments(*(Index *)h, *pp, threads, *o);
+  return o;
+}
+const char *orc_partition_error(void *o) { return ((PartitionOut *)o)->error.c_str(); }
+size_t orc_partition_len(void *o) { return ((PartitionOut *)o)->pnum.size(); }
+size_t orc_partition_num_windows(void *o) { return ((PartitionOut *)o)->windows.size(); }
+void orc_partition_totals(void *o, uint64_t *n_partitions, uint64_t *partitioned_bp, uint64_t *total_bp) {
+  PartitionOut *p = (PartitionOut *)o;
+  *n_partitions = p->n_partitions;
+  *partitioned_bp = p->partitioned_bp;
+  *total_bp = p->total_bp;
+}
+// first/last keep the reference's orientation (first > last on the reverse strand)
+void orc_partition_copy(void *o, uint32_t *pnum, uint32_t *seq, int32_t *first, int32_t *last, impgx_range *windows) {
+  PartitionOut *p = (PartitionOut *)o;
+  size_t n = p->pnum.size();
+  if (n) {
+    memcpy(pnum, p->pnum.data(), n * 4);
+    memcpy(seq, p->seq.data(), n * 4);
+    memcpy(first, p->first.data(), n * 4);
+    memcpy(last, p->last.data(), n * 4);
+  }
+  if (windows && !p->windows.empty()) memcpy(windows, p->windows.data(), p->windows.size() * sizeof(impgx_range));
+}
+// write_single_partition_file (:1682-1717)
+char *orc_partition_format_bed(void *h, void *o) {
+  Index *idx = (Index *)h;
+  PartitionOut *p = (PartitionOut *)o;
+  std::string s;
+  for (size_t i = 0; i < p->pnum.size(); i++) {
+    int32_t a = std::min(p->first[i], p->last[i]), b = std::max(p->first[i], p->last[i]);
+    s += seq_name(*idx, p->seq[i]) + "\t" + std::to_string(a) + "\t" + std::to_string(b) + "\t" + std::to_string(p->pnum[i]) + "\n";
+  }
+  return dup_string(s);
+}
+void orc_partition_free(void *o) { delete (PartitionOut *)o; }
 int orc_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -119,6 +119,41 @@ def build_oracle():
     subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True)
 
 
+class PartitionParams(C.Structure):
+    """impgx_partition_params (include/impgx.h)."""
+    _fields_ = [("window_size", C.c_uint64), ("starting_seqs", C.c_void_p), ("n_starting_seqs", C.c_size_t),
+                ("selection_mode", C.c_char_p), ("merge_distance", C.c_int32), ("min_missing_size", C.c_int32),
+                ("min_boundary_distance", C.c_int32), ("transitive_dfs", C.c_uint32), ("max_depth", C.c_uint32),
+                ("min_transitive_len", C.c_int32), ("min_distance_between_ranges", C.c_int32),
+                ("rehome_singletons", C.c_uint32), ("min_identity", C.c_double)]
+
+
+def make_partition_params(window_size, merge_distance, starting_seqs=None, selection_mode="longest",
+                          min_missing_size=3000, min_boundary_distance=3000, transitive_dfs=False, max_depth=2,
+                          min_transitive_len=101, min_distance_between_ranges=10, rehome_singletons=True,
+                          min_identity=None):
+    """Defaults are `impg partition`'s (reference src/main.rs:4765-4880, :4259-4279)."""
+    p = PartitionParams()
+    p.window_size = window_size
+    if starting_seqs is not None and len(starting_seqs):
+        a = np.ascontiguousarray(starting_seqs, dtype=np.uint32)
+        p._keep = a
+        p.starting_seqs, p.n_starting_seqs = a.ctypes.data, len(a)
+    else:
+        p.starting_seqs, p.n_starting_seqs = None, 0
+    p.selection_mode = selection_mode.encode() if selection_mode is not None else None
+    p.merge_distance = merge_distance
+    p.min_missing_size = min_missing_size
+    p.min_boundary_distance = min_boundary_distance
+    p.transitive_dfs = 1 if transitive_dfs else 0
+    p.max_depth = max_depth
+    p.min_transitive_len = min_transitive_len
+    p.min_distance_between_ranges = min_distance_between_ranges
+    p.rehome_singletons = 1 if rehome_singletons else 0
+    p.min_identity = float("nan") if min_identity is None else float(min_identity)
+    return p
+
+
 _lib = None
 
 
@@ -135,7 +170,8 @@ def lib():
         L.orc_identity.restype = C.c_double
         L.orc_sorted_ranges_insert.restype = C.c_size_t
         for f in ("orc_index_build", "orc_index_from_paf", "orc_perform_query", "orc_results_from_arrays",
-                  "orc_query_batch", "orc_multi_build", "orc_multi_query_batch"):
+                  "orc_query_batch", "orc_multi_build", "orc_multi_query_batch", "orc_partition",
+                  "orc_partition_format_bed"):
             getattr(L, f).restype = C.c_void_p
         L.orc_index_num_seqs.restype = C.c_uint32
         L.orc_index_num_records.restype = C.c_size_t
@@ -149,6 +185,9 @@ def lib():
         L.orc_format.restype = C.c_void_p
         L.orc_run_batch.restype = C.c_double
         L.orc_index_attach_cigar_file.restype = C.c_int
+        L.orc_partition_error.restype = C.c_char_p
+        L.orc_partition_len.restype = C.c_size_t
+        L.orc_partition_num_windows.restype = C.c_size_t
         _lib = L
     return _lib
 
@@ -407,6 +446,31 @@ class Index:
         res = Results(lib().orc_query_batch(self.h, _p(ranges), C.c_size_t(len(ranges)), C.byref(params),
                                             C.c_int(1 if bed_merge else 0), _p(offs)))
         return res, offs
+
+    def partition(self, pp, threads=1):
+        """partition_alignments (-o bed, single file). Returns a dict: rows = [(partition_num, seq, first, last)]
+        with the reference's orientation, windows = every window queried, totals and the partitions.bed text."""
+        L = lib()
+        h = C.c_void_p(L.orc_partition(self.h, C.byref(pp), C.c_int(threads)))
+        try:
+            err = L.orc_partition_error(h).decode()
+            if err:
+                raise ValueError(err)
+            n, nw = L.orc_partition_len(h), L.orc_partition_num_windows(h)
+            pnum, seq = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+            first, last = np.zeros(n, np.int32), np.zeros(n, np.int32)
+            win = np.zeros(max(nw, 1), RANGE_DTYPE)
+            L.orc_partition_copy(h, _p(pnum), _p(seq), _p(first), _p(last), _p(win))
+            npart, pbp, tbp = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+            L.orc_partition_totals(h, C.byref(npart), C.byref(pbp), C.byref(tbp))
+            ptr = L.orc_partition_format_bed(self.h, h)
+            text = C.string_at(ptr).decode()
+            L.orc_free(C.c_void_p(ptr))
+            return {"rows": list(zip(pnum.tolist(), seq.tolist(), first.tolist(), last.tolist())),
+                    "windows": [tuple(int(x) for x in w) for w in win[:nw]], "n_partitions": npart.value,
+                    "partitioned_bp": pbp.value, "total_bp": tbp.value, "bed": text}
+        finally:
+            L.orc_partition_free(h)
 
     def format(self, results, fmt, name, d, merge_strands=True):
         """fmt: 'bed' | 'bedpe' | 'paf'. Mutates `results` (merges) like the reference writers."""

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     L = ix.lib()
     missing = [n for n in sorted(names) if not hasattr(L, n)]
     assert not missing, missing
-    assert L.impgx_abi_version() == 3
+    assert L.impgx_abi_version() == 4
 
 
 def test_parse_cigar_matches_oracle():

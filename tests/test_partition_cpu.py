@@ -1,0 +1,191 @@
+"""partition on the CPU: the oracle's restatement of partition_alignments
+(reference src/commands/partition.rs:158-712) against the reference's own scenario, and the
+product's HOST logic (the window / mask / missing bookkeeping of libimpgx's partitioner stepper)
+driven by the oracle's masked transitive queries — no device involved. The device path
+(impgx_partition) is compared with the same oracle in test_gpu_partition.py."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+import _oracle as O
+import impg_b200 as ix
+
+
+def small_world(seed=7, genomes=5, contigs=2, tiles=6, contig_len=60000, eq_mean=40, rev=300):
+    cfg = ix.synth_cfg(genomes, contigs, contig_len, tiles, eq_mean, rev, seed)
+    recs, runs, offs, lens, names = ix.synth_generate(cfg)
+    oidx = O.Index.build(recs, runs, offs, lens, names=names)
+    return oidx, lens, names
+
+
+def patchy_world(seed, keep=0.35, **kw):
+    """A random subset of the alignments: homology is patchy, so windows leave slivers, masks cut
+    later windows and the sliver-extension / boundary rules fire."""
+    cfg = ix.synth_cfg(kw.get("genomes", 6), kw.get("contigs", 2), kw.get("contig_len", 50000), kw.get("tiles", 9),
+                       40, kw.get("rev", 300), seed)
+    recs, runs, offs, lens, names = ix.synth_generate(cfg)
+    rng = np.random.default_rng(seed)
+    sel = np.flatnonzero(rng.random(len(recs)) < keep)
+    runs2 = np.concatenate([runs[int(offs[i]):int(offs[i + 1])] for i in sel])
+    offs2 = np.zeros(len(sel) + 1, np.uint64)
+    offs2[1:] = np.cumsum([int(offs[i + 1]) - int(offs[i]) for i in sel])
+    recs2 = recs[sel].copy()
+    return (recs2, runs2, offs2, lens, names), O.Index.build(recs2, runs2, offs2, lens, names=names)
+
+
+def norm(rows):
+    return [(p, s, min(a, b), max(a, b)) for p, s, a, b in rows]
+
+
+def step_with_oracle(oidx, lens, names, kw, bed_rows=False):
+    """The product's stepper, every window answered by the oracle's masked transitive query."""
+    pp = ix.make_partition_params(**kw)
+    st = ix.Partitioner(lens, pp, names=names)
+    mode = O.MODE_DFS if kw.get("transitive_dfs") else O.MODE_BFS
+    windows = []
+    while True:
+        nx = st.next()
+        if nx is None:
+            break
+        (t, s, e), mask = nx
+        windows.append((t, s, e))
+        qp = O.make_params(mode=mode, max_depth=kw.get("max_depth", 2), min_transitive_len=kw.get("min_transitive_len", 101),
+                           min_dist=kw.get("min_distance_between_ranges", 10), masked_regions=mask,
+                           merge_distance=kw["merge_distance"], merge_strands=True)
+        if bed_rows:  # what impgx_partition feeds for -d >= 0: the rows of output_results_bed's two merges
+            res, _ = oidx.query_batch(np.array([(t, s, e)], dtype=O.RANGE_DTYPE), qp, bed_merge=True)
+        else:
+            res = oidx.perform_query(t, s, e, qp)
+        c = res.columns()
+        st.feed(c["q_id"], c["q_first"], c["q_last"])
+    return st.finish(), windows
+
+
+def test_reference_scenario_partition_window_separation():
+    # tests/test_transitive_integrity.rs:592-646: `partition -d 100000 -w 2000 -o bed` must not merge the windows
+    lines = ["A\t10000\t0\t1000\t+\tB\t5000\t0\t1000\t1000\t1000\t60\tcg:Z:1000=",
+             "A\t10000\t5000\t6000\t+\tC\t5000\t0\t1000\t1000\t1000\t60\tcg:Z:1000="]
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "test.paf")
+        open(path, "w").write("\n".join(lines) + "\n")
+        oidx = O.Index.from_paf(path)
+    out = oidx.partition(O.make_partition_params(window_size=2000, merge_distance=100000))
+    bed = [l for l in out["bed"].splitlines() if l]
+    assert len(bed) >= 2
+    assert len({l.split("\t")[3] for l in bed}) >= 2  # several partitions, not one merged window
+    # hand-derived first partition: window A:0-2000 reaches B:0-1000 through the first alignment
+    a, b = oidx.seq_id("A"), oidx.seq_id("B")
+    raw = oidx.partition(O.make_partition_params(window_size=2000, merge_distance=100000, rehome_singletons=False))
+    assert norm([r for r in raw["rows"] if r[0] == 0]) == sorted([(0, a, 0, 2000), (0, b, 0, 1000)])
+    assert norm([r for r in raw["rows"] if r[0] == 1]) == [(1, a, 2000, 4000)]  # a singleton sliver ...
+    assert (0, a, 2000, 4000) in norm(out["rows"])  # ... that the default rehoming gives to its left flank
+    assert out["partitioned_bp"] == out["total_bp"] == 20000
+    # and the product's host logic walks the same windows to the same partitions
+    lens = np.array([oidx.seq_len(i) for i in range(oidx.n_seqs)], np.uint64)
+    got, windows = step_with_oracle(oidx, lens, None, dict(window_size=2000, merge_distance=100000))
+    assert windows == out["windows"] and got.rows() == norm(out["rows"])
+
+
+CASES = [
+    dict(window_size=20000, merge_distance=1000),
+    dict(window_size=20000, merge_distance=0, min_missing_size=0, min_boundary_distance=0),
+    dict(window_size=7000, merge_distance=100000, rehome_singletons=False),
+    dict(window_size=15000, merge_distance=-1),
+    dict(window_size=15000, merge_distance=500, transitive_dfs=True),
+    dict(window_size=25000, merge_distance=1000, selection_mode="total"),
+    dict(window_size=25000, merge_distance=1000, selection_mode="sample"),
+    dict(window_size=25000, merge_distance=1000, selection_mode="haplotype,#", max_depth=1),
+    dict(window_size=30000, merge_distance=200, starting_seqs=[3, 0], max_depth=3),
+    dict(window_size=100000, merge_distance=1000, max_depth=0, min_transitive_len=2000),
+    dict(window_size=9000, merge_distance=50, min_missing_size=12000, min_boundary_distance=8000),
+]
+
+
+@pytest.mark.parametrize("k", range(len(CASES)))
+def test_stepper_matches_oracle_partition(k):
+    kw = CASES[k]
+    oidx, lens, names = small_world(seed=11 + k)
+    want = oidx.partition(O.make_partition_params(**kw))
+    got, windows = step_with_oracle(oidx, lens, names, kw)
+    assert windows == want["windows"]
+    assert got.rows() == norm(want["rows"])
+    assert (got.n_partitions, got.partitioned_bp, got.total_bp, got.n_windows) == (
+        want["n_partitions"], want["partitioned_bp"], want["total_bp"], len(want["windows"]))
+    if kw["merge_distance"] >= 0:
+        # fed with the BED rows of the window (the device's merged output) instead of the raw result list
+        got2, windows2 = step_with_oracle(oidx, lens, names, kw, bed_rows=True)
+        assert windows2 == windows and got2.rows() == got.rows()
+
+
+@pytest.mark.parametrize("k", range(len(CASES)))
+def test_stepper_matches_oracle_partition_patchy(k):
+    kw = dict(CASES[k])
+    kw["window_size"] = max(3000, kw["window_size"] // 3)
+    (recs, runs, offs, lens, names), oidx = patchy_world(seed=101 + k, keep=0.2 + 0.05 * (k % 5))
+    want = oidx.partition(O.make_partition_params(**kw))
+    assert len(want["windows"]) > 3 and want["partitioned_bp"] == want["total_bp"]
+    got, windows = step_with_oracle(oidx, lens, names, kw)
+    assert windows == want["windows"]
+    assert got.rows() == norm(want["rows"])
+    assert (got.n_partitions, got.partitioned_bp, got.n_windows) == (want["n_partitions"], want["partitioned_bp"],
+                                                                     len(want["windows"]))
+    if kw["merge_distance"] >= 0:
+        got2, windows2 = step_with_oracle(oidx, lens, names, kw, bed_rows=True)
+        assert windows2 == windows and got2.rows() == got.rows()
+
+
+def test_partitions_tile_every_sequence_exactly_once():
+    oidx, lens, names = small_world(seed=3, genomes=6, rev=500)
+    for kw in (dict(window_size=10000, merge_distance=1000), dict(window_size=33333, merge_distance=0, max_depth=1)):
+        out = oidx.partition(O.make_partition_params(**kw))
+        assert out["partitioned_bp"] == out["total_bp"] == int(lens.sum())
+        per_seq = {}
+        for _, s, a, b in norm(out["rows"]):
+            per_seq.setdefault(s, []).append((a, b))
+        assert sorted(per_seq) == list(range(len(lens)))
+        for s, iv in per_seq.items():
+            iv.sort()
+            assert iv[0][0] == 0 and iv[-1][1] == int(lens[s])
+            assert all(iv[i][1] == iv[i + 1][0] for i in range(len(iv) - 1))  # disjoint and gap-free
+
+
+def test_rehoming_only_moves_singletons_next_to_a_flank():
+    oidx, lens, names = small_world(seed=5)
+    kw = dict(window_size=7000, merge_distance=100)
+    a = oidx.partition(O.make_partition_params(rehome_singletons=False, **kw))
+    b = oidx.partition(O.make_partition_params(rehome_singletons=True, **kw))
+    ia = sorted((s, x, y) for _, s, x, y in norm(a["rows"]))
+    ib = sorted((s, x, y) for _, s, x, y in norm(b["rows"]))
+    assert ia == ib  # the same intervals, possibly under another partition number
+    assert len({r[0] for r in b["rows"]}) <= len({r[0] for r in a["rows"]})
+
+
+def test_stepper_rejects_bad_arguments():
+    lens = np.array([1000, 2000], np.uint64)
+    with pytest.raises(ix.ImpgxError):
+        ix.Partitioner(lens, ix.make_partition_params(window_size=0, merge_distance=0))
+    with pytest.raises(ix.ImpgxError) as e:
+        ix.Partitioner(lens, ix.make_partition_params(window_size=100, merge_distance=0, selection_mode="widest"))
+    assert "Invalid selection mode" in str(e.value)
+    with pytest.raises(ix.ImpgxError):  # sample mode needs names
+        ix.Partitioner(lens, ix.make_partition_params(window_size=100, merge_distance=0, selection_mode="sample"))
+    st = ix.Partitioner(lens, ix.make_partition_params(window_size=1500, merge_distance=0))
+    (t, s, e), _ = st.next()
+    assert (t, s, e) == (1, 0, 2000)  # longest; the 500-base tail joins the first window
+    with pytest.raises(ix.ImpgxError):
+        st.next()  # the window was not fed back
+    with pytest.raises(ix.ImpgxError):
+        st.feed([7], [0], [10])  # unknown sequence
+
+
+def test_partition_without_device_fails_loudly():
+    if ix.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    # there is no CPU fallback behind impgx_partition either
+    cfg = ix.synth_cfg(3, 1, 20000, 2, 40, 100, 1)
+    recs, runs, offs, lens, names = ix.synth_generate(cfg)
+    with pytest.raises(ix.ImpgxError) as e:
+        ix.Impg.from_records(recs, runs, offs, lens, names=names)
+    assert e.value.code == ix.E_NO_DEVICE
