@@ -5,6 +5,8 @@
 //
 //   impgx-query -a X.paf -b regions.bed -x -m 2 -d 1000 -o bed
 //
+// and `impgx-query partition -a X.paf -w W -d D` mirrors `impg partition -o bed`.
+//
 // Only the path of SURVEY.md §8 is supported; everything else the reference's
 // `query` offers (gfa/maf/fasta outputs, tracepoint inputs, --approximate, …)
 // is rejected with an error.
@@ -42,7 +44,128 @@ static int32_t parse_distance(const std::string &s) {
   return (int32_t)llround(v * mul);
 }
 
+// impgx-query partition — `impg partition -o bed` (src/main.rs:4765-4880, :6286-6420;
+// src/commands/partition.rs:158-712): partitions.bed, or partition<N>.bed with --separate-files.
+static int partition_main(int argc, char **argv) {
+  std::vector<std::string> pafs;
+  std::string start_file, mode = "longest", folder, out_format = "bed";
+  bool have_d = false, no_merge = false, separate = false, unidirectional = false;
+  impgx_partition_params pp;
+  memset(&pp, 0, sizeof pp);
+  pp.min_missing_size = 3000;
+  pp.min_boundary_distance = 3000;
+  pp.max_depth = 2;
+  pp.min_transitive_len = 101;
+  pp.min_distance_between_ranges = 10;
+  pp.rehome_singletons = 1;
+  pp.min_identity = NAN;
+  int device = 0;
+  for (int i = 1; i < argc; i++) {
+    std::string a = argv[i];
+    auto val = [&]() -> std::string {
+      if (i + 1 >= argc) die("missing value for " + a);
+      return argv[++i];
+    };
+    if (a == "-a" || a == "--alignment-files") {
+      pafs.push_back(val());
+      while (i + 1 < argc && argv[i + 1][0] != '-') pafs.push_back(argv[++i]);
+    } else if (a == "-w" || a == "--window-size") pp.window_size = strtoull(val().c_str(), nullptr, 10);
+    else if (a == "--starting-sequences-file") start_file = val();
+    else if (a == "--selection-mode") mode = val();
+    else if (a == "--min-missing-size") pp.min_missing_size = atoi(val().c_str());
+    else if (a == "--min-boundary-distance") pp.min_boundary_distance = atoi(val().c_str());
+    else if (a == "--separate-files") separate = true;
+    else if (a == "--no-rehome-singletons") pp.rehome_singletons = 0;
+    else if (a == "-d" || a == "--merge-distance") { pp.merge_distance = parse_distance(val()); have_d = true; }
+    else if (a == "--no-merge") no_merge = true;
+    else if (a == "--min-result-identity") pp.min_identity = atof(val().c_str());
+    else if (a == "--transitive-dfs") pp.transitive_dfs = 1;
+    else if (a == "-m" || a == "--max-depth") pp.max_depth = (uint32_t)atoi(val().c_str());
+    else if (a == "--min-transitive-len") pp.min_transitive_len = atoi(val().c_str());
+    else if (a == "--min-distance-between-ranges") pp.min_distance_between_ranges = atoi(val().c_str());
+    else if (a == "-o" || a == "--output-format") out_format = val();
+    else if (a == "--output-folder") folder = val();
+    else if (a == "--unidirectional") unidirectional = true;
+    else if (a == "--device") device = atoi(val().c_str());
+    else if (a == "-h" || a == "--help") {
+      printf("usage: impgx-query partition -a X.paf [Y.paf ...] -w WINDOW (-d D | --no-merge)\n"
+             "       [--starting-sequences-file FILE] [--selection-mode longest|total|sample[,sep]|haplotype[,sep]]\n"
+             "       [--min-missing-size N] [--min-boundary-distance N] [--separate-files] [--no-rehome-singletons]\n"
+             "       [-m N] [--min-transitive-len N] [--min-distance-between-ranges N] [--transitive-dfs]\n"
+             "       [--min-result-identity F] [--output-folder DIR] [--device N]\n");
+      return 0;
+    } else die("unsupported option '" + a + "' (only `partition -o bed` over PAF input is implemented)");
+  }
+  if (pafs.empty()) die("-a/--alignment-files is required");
+  if (pp.window_size == 0) die("-w/--window-size is required");
+  if (have_d && no_merge) die("-d and --no-merge are mutually exclusive");
+  if (!have_d && !no_merge) die("-d/--merge-distance is required. Use `--no-merge` to explicitly disable merging.");
+  if (no_merge) pp.merge_distance = -1;
+  if (out_format != "bed") die("output format '" + out_format + "' needs sequence files and is outside the accelerated path (bed)");
+  pp.selection_mode = mode.c_str();
+
+  impgx_index *idx = nullptr;
+  {
+    std::vector<const char *> paths;
+    for (auto &f : pafs) paths.push_back(f.c_str());
+    check(impgx_index_from_pafs(paths.data(), paths.size(), unidirectional ? 0 : 1, device, &idx));
+  }
+  std::vector<uint32_t> starting;
+  if (!start_file.empty()) {  // first tab field of every line that is not blank or a comment (:184-212)
+    std::ifstream f(start_file);
+    if (!f.good()) die("Could not open starting sequences file " + start_file);
+    std::string line;
+    while (std::getline(f, line)) {
+      std::string nm = line.substr(0, line.find('\t'));
+      size_t b = nm.find_first_not_of(" \t\r\n"), e = nm.find_last_not_of(" \t\r\n");
+      if (b == std::string::npos) continue;
+      nm = nm.substr(b, e - b + 1);
+      if (nm[0] == '#') continue;
+      uint32_t id = 0;
+      if (impgx_index_seq_id(idx, nm.c_str(), &id) == 0) starting.push_back(id);  // unknown names are skipped
+    }
+  }
+  pp.starting_seqs = starting.data();
+  pp.n_starting_seqs = starting.size();
+  impgx_partitions *parts = nullptr;
+  check(impgx_partition(idx, &pp, &parts));
+  impgx_partition_view v;
+  check(impgx_partitions_view(parts, &v));
+  auto write_file = [&](const std::string &name, int64_t which) {
+    std::string path = folder.empty() ? name : folder + "/" + name;
+    if (!folder.empty()) {
+      std::string cmd = "mkdir -p '" + folder + "'";
+      if (system(cmd.c_str()) != 0) die("cannot create " + folder);
+    }
+    char *text = impgx_partitions_format_bed(idx, parts, which);
+    if (!text) die("formatting failed");
+    FILE *f = fopen(path.c_str(), "w");
+    if (!f) die("cannot write " + path);
+    fputs(text, f);
+    fclose(f);
+    impgx_free(text);
+  };
+  if (separate) {
+    int64_t last = -1;
+    for (size_t i = 0; i < v.n_intervals; i++)
+      if ((int64_t)v.partition_num[i] != last) {
+        last = v.partition_num[i];
+        write_file("partition" + std::to_string(last) + ".bed", last);
+      }
+  } else if (v.n_intervals) {
+    write_file("partitions.bed", -1);
+  }
+  double pct = v.total_bp ? 100.0 * (double)v.partitioned_bp / (double)v.total_bp : 0.0;
+  fprintf(stderr, "Partitioned into %zu regions: %llu bp total written / %llu bp total sequence (%.4g%%), %llu windows\n",
+          v.n_partitions, (unsigned long long)v.partitioned_bp, (unsigned long long)v.total_bp, pct,
+          (unsigned long long)v.n_windows);
+  impgx_partitions_free(parts);
+  impgx_index_free(idx);
+  return 0;
+}
+
 int main(int argc, char **argv) {
+  if (argc > 1 && !strcmp(argv[1], "partition")) return partition_main(argc - 1, argv + 1);
   std::vector<std::string> pafs;
   std::string bed_path, range_text, out_format = "auto", subset_path, index_mode = "auto";
   bool transitive = false, dfs = false, unidirectional = false, consider_strand = false, no_merge = false, have_d = false;

@@ -74,3 +74,41 @@ def test_partition_medium_world_tiles_the_pangenome():
     assert (a[first] == 0).all() and (b[last] == lens[s[last]].astype(np.int64)).all()
     assert (a[~first] == b[:-1][~first[1:]]).all()
     assert got.n_windows >= got.n_partitions > 0
+
+
+def test_cli_partition_writes_the_reference_files(tmp_path):
+    """`impgx-query partition` end to end on the reference's scenario PAF and a fixture PAF:
+    partitions.bed / partition<N>.bed equal to the oracle's text."""
+    import os
+    import subprocess
+    cli = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "impg_b200", "impgx-query")
+    paf = tmp_path / "t.paf"
+    paf.write_text("A\t10000\t0\t1000\t+\tB\t5000\t0\t1000\t1000\t1000\t60\tcg:Z:1000=\n"
+                   "A\t10000\t5000\t6000\t+\tC\t5000\t0\t1000\t1000\t1000\t60\tcg:Z:1000=\n")
+    o = O.Index.from_paf(str(paf))
+    want = o.partition(O.make_partition_params(window_size=2000, merge_distance=100000))
+    out = tmp_path / "single"
+    r = subprocess.run([cli, "partition", "-a", str(paf), "-w", "2000", "-d", "100k", "--output-folder", str(out)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert (out / "partitions.bed").read_text() == want["bed"]
+    assert "Partitioned into" in r.stderr
+    # --separate-files, no rehoming, a starting-sequences file
+    start = tmp_path / "start.txt"
+    start.write_text("# comment\n\nC\tignored\nnot_there\n")
+    want = o.partition(O.make_partition_params(window_size=3000, merge_distance=0, rehome_singletons=False,
+                                               starting_seqs=[o.seq_id("C")], selection_mode="total"))
+    out = tmp_path / "sep"
+    r = subprocess.run([cli, "partition", "-a", str(paf), "-w", "3000", "-d", "0", "--separate-files",
+                        "--no-rehome-singletons", "--starting-sequences-file", str(start), "--selection-mode", "total",
+                        "--output-folder", str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    by_part = {}
+    for l in want["bed"].splitlines():
+        body, p = l.rsplit("\t", 1)
+        by_part.setdefault(p, []).append(body + "\n")
+    assert sorted(f.name for f in out.iterdir()) == sorted(f"partition{p}.bed" for p in by_part)
+    for p, lines in by_part.items():
+        assert (out / f"partition{p}.bed").read_text() == "".join(lines)
+    r = subprocess.run([cli, "partition", "-a", str(paf), "-w", "3000"], capture_output=True, text=True)
+    assert r.returncode != 0 and "merge-distance is required" in r.stderr
