@@ -115,8 +115,109 @@ struct Scratch {
   Arena *a = nullptr;
 };
 
+// Small inputs (single-row calls: partition's windows, refine's candidates) are bound by the
+// number of launches, not by bandwidth: one CTA does the whole scan / sort in shared memory
+// instead of CUB's multi-kernel pipelines.
+constexpr uint32_t SMALL_SCAN_MAX = 4096;
+constexpr uint32_t SMALL_SORT_MAX = 2048;
+constexpr int SMALL_SORT_IDX_BITS = 11;
+
+__global__ void __launch_bounds__(1024) k_small_excl_scan_u64(uint64_t *__restrict__ a, uint32_t n) {
+  __shared__ uint64_t warp_tot[32];
+  uint64_t v[4];
+  uint64_t sum = 0;
+  const uint32_t base = threadIdx.x * 4;
+#pragma unroll
+  for (int u = 0; u < 4; u++) {
+    v[u] = base + u < n ? a[base + u] : 0;
+    sum += v[u];
+  }
+  uint64_t incl = sum;
+  const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint64_t o = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= (unsigned)d) incl += o;
+  }
+  if (lane == 31) warp_tot[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    uint64_t t = lane < (blockDim.x >> 5) ? warp_tot[lane] : 0;
+    uint64_t ti = t;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint64_t o = __shfl_up_sync(0xffffffffu, ti, d);
+      if (lane >= (unsigned)d) ti += o;
+    }
+    warp_tot[lane] = ti - t;
+  }
+  __syncthreads();
+  uint64_t run = warp_tot[w] + incl - sum;
+#pragma unroll
+  for (int u = 0; u < 4; u++) {
+    if (base + u < n) a[base + u] = run;
+    run += v[u];
+  }
+}
+
+// stable sort of (key, value) pairs on the key bits [begin_bit, end_bit): bitonic network over
+// (masked key, input position), so equal keys keep their input order like the LSD radix sort
+template <class K>
+__global__ void __launch_bounds__(1024) k_small_sort_pairs(K *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t n,
+                                                           uint32_t P, int begin_bit, int end_bit) {
+  __shared__ uint64_t sk[SMALL_SORT_MAX];
+  __shared__ K k0[SMALL_SORT_MAX];
+  __shared__ uint32_t v0[SMALL_SORT_MAX];
+  const int nb = end_bit - begin_bit;
+  const uint64_t mask = nb >= 64 ? ~0ull : ((1ull << nb) - 1);
+  for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
+    if (i < n) {
+      const K k = keys[i];
+      k0[i] = k;
+      v0[i] = vals[i];
+      sk[i] = ((((uint64_t)k >> begin_bit) & mask) << SMALL_SORT_IDX_BITS) | i;
+    } else {
+      sk[i] = ~0ull;
+    }
+  }
+  __syncthreads();
+  const uint32_t half = P >> 1;
+  for (uint32_t k = 2; k <= P; k <<= 1)
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t i = threadIdx.x; i < half; i += blockDim.x) {
+        const uint32_t lo = ((i & ~(j - 1)) << 1) | (i & (j - 1)), hi = lo | j;
+        const uint64_t x = sk[lo], y = sk[hi];
+        if ((y < x) == ((lo & k) == 0)) {
+          sk[lo] = y;
+          sk[hi] = x;
+        }
+      }
+      __syncthreads();
+    }
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint32_t src = (uint32_t)(sk[i] & ((1u << SMALL_SORT_IDX_BITS) - 1));
+    keys[i] = k0[src];
+    vals[i] = v0[src];
+  }
+}
+
+// callers count two launches per scan (CUB: init + scan); the single-CTA scan is one
+static thread_local uint64_t tl_small_scans = 0;
+
+static bool small_paths_enabled() {
+  static const bool on = !getenv("IMPGX_NO_SMALL_PATHS");
+  return on;
+}
+
 // in-place exclusive sum over n+1 elements: a[n] becomes the total
 static void exclusive_scan_u64(uint64_t *a, uint64_t n_plus_1, Scratch &sc, cudaStream_t s) {
+  if (n_plus_1 <= SMALL_SCAN_MAX && small_paths_enabled()) {
+    const unsigned threads = (unsigned)std::min<uint64_t>(1024, ((n_plus_1 + 3) / 4 + 31) / 32 * 32);
+    k_small_excl_scan_u64<<<1, threads, 0, s>>>(a, (uint32_t)n_plus_1);
+    CUDA_CHECK(cudaGetLastError());
+    tl_small_scans++;
+    return;
+  }
   size_t bytes = 0;
   CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, a, a, n_plus_1, s));
   DBuf<uint8_t> tmp(bytes, *sc.a);
@@ -133,6 +234,15 @@ template <class K>
 static void sort_pairs(DBuf<K> &keys, DBuf<uint32_t> &vals, uint64_t n, int begin_bit, int end_bit, Scratch &sc,
                        cudaStream_t s, Ctx &ctx) {
   if (n == 0) return;
+  if (n <= SMALL_SORT_MAX && end_bit - begin_bit + SMALL_SORT_IDX_BITS <= 64 && small_paths_enabled()) {
+    uint32_t P = 2;
+    while (P < n) P <<= 1;
+    const unsigned threads = std::min(1024u, std::max(32u, P >> 1));
+    k_small_sort_pairs<K><<<1, threads, 0, s>>>(keys.get(), vals.get(), (uint32_t)n, P, begin_bit, end_bit);
+    CUDA_CHECK(cudaGetLastError());
+    ctx.launches += 1;
+    return;
+  }
   DBuf<K> k2(n, *sc.a);
   DBuf<uint32_t> v2(n, *sc.a);
   cub::DoubleBuffer<K> dk(keys.get(), k2.get());
@@ -1853,6 +1963,7 @@ impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n
   };
 
   Ctx total;
+  tl_small_scans = 0;
   // Row batches are sized so that one batch lifts about IMPGX_HITS_PER_BATCH hits
   // (scratch memory is proportional to the hits in flight); the hits-per-row
   // figure is learned from the first, small batch and kept on the index.
@@ -2019,7 +2130,7 @@ impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n
   auto t1 = std::chrono::steady_clock::now();
   impgx_stats &st = idx->last;
   st = impgx_stats{};
-  st.kernel_launches = total.launches;
+  st.kernel_launches = total.launches - std::min(total.launches, tl_small_scans);
   st.stab_ranges = total.stab_ranges;
   st.liftovers = total.liftovers;
   st.lift_runs = total.lift_runs;
