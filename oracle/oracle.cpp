@@ -25,7 +25,9 @@
  * — here ids are first-appearance order; (4) MultiImpg (src/multi_impg.rs:462-595,
  * 796-991: per-file sub-indices, 5-key hit order, duplicate-self rule, sorted
  * queue walk) and masked_regions (src/impg.rs:2331-2373, 2041-2055), which no
- * reference test exercises — restated literally from source.
+ * reference test exercises — restated literally from source; (5) partition_alignments
+ * (src/commands/partition.rs), whose only reference test asserts ">= 2 output lines" — restated
+ * literally, see the section header below.
  */
 #include <algorithm>
 #include <cassert>
