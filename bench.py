@@ -489,9 +489,22 @@ def main():
     if rank == 0:
         sampler.stop()
 
+    # ---- e2e with the BED text (SURVEY.md 8d "text formatting included"): the same call plus
+    # impgx_format_bed_batch over every row — what `impgx-query -b ... -o bed` writes to stdout
+    names_arr = (C.c_char_p * n)(*[f"r{k}".encode() for k in range(n)])
+    text_bytes = 0
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        r, st = step_host()
+        text_bytes += idx.format_bed_batch(r, names_arr, length_only=True)
+        del r
+    torch.cuda.synchronize()
+    text_ms = (time.perf_counter() - w0) * 1e3
+    barrier()
+
     from impg_b200 import dist as D
 
-    dev_ms, e2e_ms = D.max_over_ranks([dev_ms, e2e_ms], device="cuda")  # slowest rank defines the step
+    dev_ms, e2e_ms, text_ms = D.max_over_ranks([dev_ms, e2e_ms, text_ms], device="cuda")  # slowest rank defines the step
     total_rows = D.gather_row_counts(n, device="cuda") * args.steps
     value = total_rows / (dev_ms / 1e3)
     e2e_value = total_rows / (e2e_ms / 1e3)
@@ -635,6 +648,9 @@ def main():
             "dtype": "int32", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps,
                     "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": e2e_ms / args.steps},
+            "e2e_text": {"value": total_rows / (text_ms / 1e3), "unit": UNIT, "ms_per_step": text_ms / args.steps,
+                         "text_bytes_per_step": int(text_bytes // args.steps),
+                         "what": "e2e plus the BED text of every row (impgx_format_bed_batch on the host cores)"},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
             "clocks": sampler.summary(), "bed_rows_out_per_step": int(merged), "rows_over_replicas": rows_mode,
             "target_sharded": sharded,

@@ -170,6 +170,7 @@ def lib():
         L.impgx_index_seq_len.restype = C.c_uint64
         L.impgx_parse_cigar.restype = C.c_long
         L.impgx_format_bed.restype = C.c_void_p
+        L.impgx_format_bed_batch.restype = C.c_void_p
         L.impgx_format_bedpe.restype = C.c_void_p
         L.impgx_format_paf.restype = C.c_void_p
         L.impgx_synth_num_alignments.restype = C.c_uint64
@@ -405,6 +406,21 @@ class Impg:
                         store_cigar=store_cigar, min_identity=min_gap_compressed_identity, subset_mask=subset_mask)
         r = self.query_batch(np.array([(target_id, range_start, range_end)], dtype=RANGE_DTYPE), p)
         return r.row_tuples(0)
+
+    def format_bed_batch(self, results, names, decode=True, length_only=False):
+        """BED text of every row of a merged batch (reference src/main.rs:11849-11892 per row), input order.
+        length_only: format, free, and return the byte count (timing without a copy into Python)."""
+        arr = names if isinstance(names, C.Array) else (C.c_char_p * len(names))(*[n.encode() for n in names])
+        ln = C.c_size_t(0)
+        ptr = lib().impgx_format_bed_batch(self.h, results.h, arr, C.byref(ln))
+        if not ptr:
+            raise ImpgxError(E_INVALID, "format failed")
+        if length_only:
+            lib().impgx_free(C.c_void_p(ptr))
+            return ln.value
+        s = C.string_at(ptr, ln.value)
+        lib().impgx_free(C.c_void_p(ptr))
+        return s.decode() if decode else s
 
     def partition(self, params):
         """`impg partition -o bed` on this index (reference src/commands/partition.rs:158-712): one masked

@@ -488,6 +488,81 @@ char *impgx_format_bed(const impgx_index *idx, const impgx_results *res, size_t 
   return p;
 }
 
+// All rows of a merged result set at once, formatted by every host core: the text `impg query -b ... -o bed`
+// prints for the whole BED file (rows in input order). Two passes: line lengths, then the bytes.
+namespace {
+inline int dec_len(uint32_t v) {
+  int n = 1;
+  while (v >= 10) {
+    v /= 10;
+    n++;
+  }
+  return n;
+}
+inline char *put_dec(char *p, uint32_t v) {
+  const int n = dec_len(v);
+  for (int i = n - 1; i >= 0; i--) {
+    p[i] = (char)('0' + v % 10);
+    v /= 10;
+  }
+  return p + n;
+}
+}  // namespace
+
+char *impgx_format_bed_batch(const impgx_index *idx, const impgx_results *res, const char *const *names,
+                             size_t *len_out) {
+  if (!idx || !res || res->on_device || !names) return nullptr;
+  const size_t R = res->n_rows;
+  std::vector<std::string> fallback(idx->n_seqs);
+  std::vector<const std::string *> seq(idx->n_seqs);
+  for (uint32_t q = 0; q < idx->n_seqs; q++) {
+    if (q < idx->names.size() && !idx->names[q].empty()) seq[q] = &idx->names[q];
+    else {
+      fallback[q] = "seq" + std::to_string(q);
+      seq[q] = &fallback[q];
+    }
+  }
+  std::vector<size_t> name_len(R), off(R + 1, 0);
+#pragma omp parallel for schedule(static)
+  for (long r = 0; r < (long)R; r++) {
+    name_len[r] = strlen(names[r]);
+    size_t b = 0;
+    for (uint64_t i = res->row_off[r]; i < res->row_off[r + 1]; i++) {
+      const int32_t f = res->qf[i], l = res->ql[i];
+      b += seq[res->qid[i]]->size() + dec_len((uint32_t)std::min(f, l)) + dec_len((uint32_t)std::max(f, l)) + name_len[r] + 7;
+    }
+    off[r + 1] = b;
+  }
+  for (size_t r = 0; r < R; r++) off[r + 1] += off[r];
+  char *out = (char *)malloc(off[R] + 1);
+  if (!out) return nullptr;
+#pragma omp parallel for schedule(static)
+  for (long r = 0; r < (long)R; r++) {
+    char *p = out + off[r];
+    for (uint64_t i = res->row_off[r]; i < res->row_off[r + 1]; i++) {
+      const int32_t f = res->qf[i], l = res->ql[i];
+      const std::string &nm = *seq[res->qid[i]];
+      memcpy(p, nm.data(), nm.size());
+      p += nm.size();
+      *p++ = '\t';
+      p = put_dec(p, (uint32_t)std::min(f, l));
+      *p++ = '\t';
+      p = put_dec(p, (uint32_t)std::max(f, l));
+      *p++ = '\t';
+      memcpy(p, names[r], name_len[r]);
+      p += name_len[r];
+      *p++ = '\t';
+      *p++ = '.';
+      *p++ = '\t';
+      *p++ = f > l ? '-' : '+';
+      *p++ = '\n';
+    }
+  }
+  out[off[R]] = 0;
+  if (len_out) *len_out = off[R];
+  return out;
+}
+
 static char *format_with(const impgx_index *idx, const impgx_results *res, size_t row, const char *name, int32_t d,
                          int fmt) {
   if (!idx || !res || res->on_device || row >= res->n_rows || !name) return nullptr;

@@ -311,13 +311,22 @@ int main(int argc, char **argv) {
   impgx_results *res = nullptr;
   if (out_format == "bed") check(impgx_query_batch_bed(idx, rows.data(), rows.size(), &p, &res));
   else check(impgx_query_batch(idx, rows.data(), rows.size(), &p, &res));
-  for (size_t r = 0; r < rows.size(); r++) {
-    char *text = out_format == "bed"     ? impgx_format_bed(idx, res, r, names[r].c_str())
-                 : out_format == "bedpe" ? impgx_format_bedpe(idx, res, r, names[r].c_str(), d)
-                                         : impgx_format_paf(idx, res, r, names[r].c_str(), d);
-    if (!text) die(impgx_last_error());
-    fputs(text, stdout);
+  if (out_format == "bed") {  // the whole file at once, formatted on every host core
+    std::vector<const char *> nm;
+    for (auto &s : names) nm.push_back(s.c_str());
+    size_t len = 0;
+    char *text = impgx_format_bed_batch(idx, res, nm.data(), &len);
+    if (!text) die("formatting failed");
+    fwrite(text, 1, len, stdout);
     impgx_free(text);
+  } else {
+    for (size_t r = 0; r < rows.size(); r++) {
+      char *text = out_format == "bedpe" ? impgx_format_bedpe(idx, res, r, names[r].c_str(), d)
+                                         : impgx_format_paf(idx, res, r, names[r].c_str(), d);
+      if (!text) die(impgx_last_error());
+      fputs(text, stdout);
+      impgx_free(text);
+    }
   }
   impgx_results_free(res);
   impgx_index_free(idx);

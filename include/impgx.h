@@ -304,6 +304,11 @@ long impgx_parse_cigar(const char *text, size_t len, uint32_t *out, size_t cap);
  * impgx_free) or NULL. */
 char *impgx_format_bed(const impgx_index *idx, const impgx_results *res,
                        size_t row, const char *name);
+/* The same lines for EVERY row of the batch (names[r] = region name of input row r), in input
+ * order — what `impg query -b` prints for the whole BED file; formatted on all host cores.
+ * *len_out = bytes without the terminating NUL. malloc'ed, impgx_free. */
+char *impgx_format_bed_batch(const impgx_index *idx, const impgx_results *res, const char *const *names,
+                             size_t *len_out);
 /* output_results_bedpe / output_results_paf (src/main.rs:11894-12103) for row
  * `row` of a RAW result set obtained with store_cigar = 1: drops the self
  * interval (src/main.rs:7474,7486), runs merge_adjusted_intervals

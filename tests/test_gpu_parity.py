@@ -363,6 +363,26 @@ def test_bedpe_paf_text_vs_oracle(small):
                     assert fn(gpu, gres, r, name, d) == orc.format(ores, fmt, name, d), (mode, d, r, fmt)
 
 
+def test_bed_text_of_a_whole_batch_vs_oracle(small):
+    """impgx_format_bed_batch (every row of the BED file, formatted on all host cores) against the
+    oracle's output_results_bed, row by row, and against the per-row formatter."""
+    cfg, orc, gpu, bed = small
+    rows = bed[:60]
+    names = [f"r{k}" if k % 3 else f"{orc.seq_name(int(rows[k]['target_id']))}:{int(rows[k]['start'])}-{int(rows[k]['end'])}"
+             for k in range(len(rows))]
+    for d, ms in ((1000, True), (0, False), (-1, True)):
+        o, g = params_pair(mode=1, max_depth=2, merge_distance=d, merge_strands=ms)
+        gres = gpu.query_batch_bed(rows, g)
+        text = gpu.format_bed_batch(gres, names)
+        assert text == "".join(gpu.format_bed(gres, r, names[r]) for r in range(len(rows)))
+        want = ""
+        for r in range(len(rows)):
+            ores = orc.perform_query(int(rows[r]["target_id"]), int(rows[r]["start"]), int(rows[r]["end"]), o)
+            want += orc.format(ores, "bed", names[r], d, merge_strands=ms)
+        assert text == want
+    assert gpu.format_bed_batch(gpu.query_batch_bed(rows[:0], g), []) == ""
+
+
 def test_medium_scale_properties():
     """~20k alignments, 2k rows, depth 2: oracle parity on a row sample plus
     size-independent properties on everything (BED rows sorted, disjoint beyond
