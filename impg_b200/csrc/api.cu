@@ -529,7 +529,7 @@ char *impgx_format_bed_batch(const impgx_index *idx, const impgx_results *res, c
     size_t b = 0;
     for (uint64_t i = res->row_off[r]; i < res->row_off[r + 1]; i++) {
       const int32_t f = res->qf[i], l = res->ql[i];
-      b += seq[res->qid[i]]->size() + dec_len((uint32_t)std::min(f, l)) + dec_len((uint32_t)std::max(f, l)) + name_len[r] + 7;
+      b += seq[res->qid[i]]->size() + dec_len((uint32_t)std::min(f, l)) + dec_len((uint32_t)std::max(f, l)) + name_len[r] + 8;
     }
     off[r + 1] = b;
   }
