@@ -30,7 +30,12 @@ import tempfile
 import threading
 import time
 
-import numpy as np
+# torchrun exports OMP_NUM_THREADS=1; the host-side legs (BED text of a batch, CPU reference) split the
+# box's cores over the ranks instead (set before any OpenMP runtime is loaded)
+if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // int(os.environ.get("LOCAL_WORLD_SIZE", os.environ["WORLD_SIZE"]))))
+
+import numpy as np  # noqa: E402
 
 # stdout carries exactly one JSON line: NCCL's banner ("NCCL version ...", printed at NCCL_DEBUG=VERSION/WARN)
 # and any other NCCL log go to stderr
