@@ -260,12 +260,34 @@ static void sort_pairs(DBuf<K> &keys, DBuf<uint32_t> &vals, uint64_t n, int begi
   if (dv.Current() != vals.get()) CUDA_CHECK(cudaMemcpyAsync(vals.get(), v2.get(), n * 4, cudaMemcpyDeviceToDevice, s));
 }
 
+// Size readbacks between the count / scan / fill stages land in a small pinned buffer (a copy into
+// pageable memory is staged by the driver and costs several microseconds more per call).
+static uint64_t *readback_slot() {
+  static thread_local uint64_t *slot = nullptr;
+  if (!slot && cudaMallocHost((void **)&slot, 64) != cudaSuccess) {
+    cudaGetLastError();
+    throw Error(IMPGX_E_NOMEM, "pinned host allocation failed");
+  }
+  return slot;
+}
+
 static uint64_t read_u64(const uint64_t *d, cudaStream_t s, Ctx &ctx) {
-  uint64_t v = 0;
-  CUDA_CHECK(cudaMemcpyAsync(&v, d, 8, cudaMemcpyDeviceToHost, s));
+  uint64_t *h = readback_slot();
+  CUDA_CHECK(cudaMemcpyAsync(h, d, 8, cudaMemcpyDeviceToHost, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
   ctx.d2h_bytes += 8;
-  return v;
+  return h[0];
+}
+
+// two sizes, one synchronisation
+static void read_u64x2(const uint64_t *d0, const uint64_t *d1, uint64_t &v0, uint64_t &v1, cudaStream_t s, Ctx &ctx) {
+  uint64_t *h = readback_slot();
+  CUDA_CHECK(cudaMemcpyAsync(h, d0, 8, cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaMemcpyAsync(h + 1, d1, 8, cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  ctx.d2h_bytes += 16;
+  v0 = h[0];
+  v1 = h[1];
 }
 
 struct WallTimer {
@@ -648,8 +670,12 @@ void Runner::lift_core(const DBuf<Frontier> &fr_ref, uint64_t nF, bool closed, b
            d_counters_.get());
   CUDA_CHECK(cudaEventRecord(e2, s_));
   unsigned long long cnt[4];
-  CUDA_CHECK(cudaMemcpyAsync(cnt, d_counters_.get(), 32, cudaMemcpyDeviceToHost, s_));
-  CUDA_CHECK(cudaStreamSynchronize(s_));
+  {
+    uint64_t *h = readback_slot();
+    CUDA_CHECK(cudaMemcpyAsync(h, d_counters_.get(), 32, cudaMemcpyDeviceToHost, s_));
+    CUDA_CHECK(cudaStreamSynchronize(s_));
+    memcpy(cnt, h, 32);
+  }
   ctx.d2h_bytes += 32;
   float ms = 0;
   cudaEventElapsedTime(&ms, e0, e1);
@@ -783,8 +809,8 @@ void Runner::fold(const LevelHits &lvl, uint32_t n_rows, Visited &V, DBuf<Fronti
   exclusive_scan_u64(list_off.get(), G + 1, sc_, s_);
   exclusive_scan_u64(piece_off.get(), G + 1, sc_, s_);
   ctx.launches += 4;
-  const uint64_t list_total = read_u64(list_off.get() + G, s_, ctx);
-  const uint64_t piece_total = read_u64(piece_off.get() + G, s_, ctx);
+  uint64_t list_total = 0, piece_total = 0;
+  read_u64x2(list_off.get() + G, piece_off.get() + G, list_total, piece_total, s_, ctx);
   LAUNCH(k_set_group_offsets, grid_threads(G), 256, s_, groups.get(), G, list_off.get(), piece_off.get());
 
   DBuf<int2> lists(list_total, ar_);
@@ -804,16 +830,25 @@ void Runner::fold(const LevelHits &lvl, uint32_t n_rows, Visited &V, DBuf<Fronti
   exclusive_scan_u64(lo.get(), G + 1, sc_, s_);
   exclusive_scan_u64(po.get(), G + 1, sc_, s_);
   ctx.launches += 4;
-  const uint64_t new_lists = read_u64(lo.get() + G, s_, ctx);
-  const uint64_t n_pieces = read_u64(po.get() + G, s_, ctx);
-
   DBuf<uint64_t> keep(V.n + 1, ar_), keep_scan(V.n + 1, ar_);
   CUDA_CHECK(cudaMemsetAsync(keep.get() + V.n, 0, 8, s_));
   if (V.n) LAUNCH(k_visited_keep_flags, grid_threads(V.n), 256, s_, V.keys.get(), V.n, groups.get(), G, keep.get());
   CUDA_CHECK(cudaMemcpyAsync(keep_scan.get(), keep.get(), (V.n + 1) * 8, cudaMemcpyDeviceToDevice, s_));
   exclusive_scan_u64(keep_scan.get(), V.n + 1, sc_, s_);
   ctx.launches += 2;
-  const uint64_t kept = read_u64(keep_scan.get() + V.n, s_, ctx);
+  // the three sizes of this stage in one synchronisation
+  uint64_t new_lists = 0, n_pieces = 0, kept = 0;
+  {
+    uint64_t *h = readback_slot();
+    CUDA_CHECK(cudaMemcpyAsync(h, lo.get() + G, 8, cudaMemcpyDeviceToHost, s_));
+    CUDA_CHECK(cudaMemcpyAsync(h + 1, po.get() + G, 8, cudaMemcpyDeviceToHost, s_));
+    CUDA_CHECK(cudaMemcpyAsync(h + 2, keep_scan.get() + V.n, 8, cudaMemcpyDeviceToHost, s_));
+    CUDA_CHECK(cudaStreamSynchronize(s_));
+    ctx.d2h_bytes += 24;
+    new_lists = h[0];
+    n_pieces = h[1];
+    kept = h[2];
+  }
   const uint64_t vn = kept + new_lists;
   Visited nv;
   nv.keys.alloc(vn, ar_);
@@ -1068,7 +1103,8 @@ void Runner::run(const impgx_range *d_ranges, uint32_t n_rows, bool bed, BatchOu
       exclusive_scan_u64(ls.get(), (uint64_t)n_rows + 1, sc_, s_);
       exclusive_scan_u64(ps.get(), (uint64_t)n_rows + 1, sc_, s_);
       ctx.launches += 4;
-      const uint64_t nl = read_u64(ls.get() + n_rows, s_, ctx), np = read_u64(ps.get() + n_rows, s_, ctx);
+      uint64_t nl = 0, np = 0;
+      read_u64x2(ls.get() + n_rows, ps.get() + n_rows, nl, np, s_, ctx);
       V.keys.alloc(nl, ar_);
       V.start.alloc(nl, ar_);
       V.end.alloc(nl, ar_);
@@ -1371,10 +1407,7 @@ bool Runner::merge_fused(const BoxSrc &src, uint64_t nB, BatchOut &out, uint32_t
   CUDA_CHECK(cudaMemsetAsync(d_counters_.get(), 0, 8, s_));
   LAUNCH(k_bd_key_a_src, grid_threads(nB), 256, s_, src, nB, seq_bits, 1ull << bits_a_, ka0.get(), perm0.get(),
          d_counters_.get());
-  unsigned long long nv = 0;
-  CUDA_CHECK(cudaMemcpyAsync(&nv, d_counters_.get(), 8, cudaMemcpyDeviceToHost, s_));
-  CUDA_CHECK(cudaStreamSynchronize(s_));
-  ctx.d2h_bytes += 8;
+  const uint64_t nv = read_u64((const uint64_t *)d_counters_.get(), s_, ctx);
   if (nv == 0) return true;
   DBuf<BoxD> swept(nv, ar_);
   DBuf<uint32_t> cnt;
@@ -1394,9 +1427,10 @@ bool Runner::merge_fused(const BoxSrc &src, uint64_t nB, BatchOut &out, uint32_t
       g.G = read_u64(scan.get() + nv, s_, ctx);
       g.begins.alloc(g.G + 1, ar_);
       LAUNCH(k_group_begins, grid_threads(nv), 256, s_, head.get(), scan.get(), nv, g.begins.get());
-      uint32_t n32 = (uint32_t)nv;
-      CUDA_CHECK(cudaMemcpyAsync(g.begins.get() + g.G, &n32, 4, cudaMemcpyHostToDevice, s_));
-      CUDA_CHECK(cudaStreamSynchronize(s_));
+      // begins[G] = nv from a pinned word that no readback touches: the copy needs no synchronisation
+      uint32_t *n32 = reinterpret_cast<uint32_t *>(readback_slot() + 7);
+      *n32 = (uint32_t)nv;
+      CUDA_CHECK(cudaMemcpyAsync(g.begins.get() + g.G, n32, 4, cudaMemcpyHostToDevice, s_));
     }
     DBuf<uint32_t> lists((uint64_t)SEG_CLASSES * g.G, ar_);
     DBuf<unsigned int> cls(SEG_CLASSES + 1, ar_);
@@ -1405,8 +1439,13 @@ bool Runner::merge_fused(const BoxSrc &src, uint64_t nB, BatchOut &out, uint32_t
     if (min_class < 0 || min_class >= SEG_CLASSES) min_class = 0;
     LAUNCH(k_seg_classify, grid_threads(g.G), 256, s_, g.begins.get(), g.G, lists.get(), cls.get(), min_class);
     unsigned int hc[SEG_CLASSES + 1];
-    CUDA_CHECK(cudaMemcpyAsync(hc, cls.get(), sizeof(hc), cudaMemcpyDeviceToHost, s_));
-    CUDA_CHECK(cudaStreamSynchronize(s_));
+    {
+      static_assert(sizeof(hc) <= 32, "class counters must fit the readback slot");
+      uint64_t *h = readback_slot();
+      CUDA_CHECK(cudaMemcpyAsync(h, cls.get(), sizeof(hc), cudaMemcpyDeviceToHost, s_));
+      CUDA_CHECK(cudaStreamSynchronize(s_));
+      memcpy(hc, h, sizeof(hc));
+    }
     ctx.d2h_bytes += sizeof(hc);
     if (hc[SEG_CLASSES] != 0) return false;
     cnt.alloc(g.G, ar_);
