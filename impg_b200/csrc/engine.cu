@@ -2051,8 +2051,8 @@ impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n
         WallTimer wcopy(total.w_copy);
 
         const uint64_t R = bo.n_results;
-        std::vector<uint64_t> ro(m + 1);
-        CUDA_CHECK(cudaMemcpyAsync(ro.data(), bo.row_off.get(), (m + 1) * 8, cudaMemcpyDeviceToHost, s));
+        // chunk-relative row offsets straight into the (pinned) result column; rebased after the sync
+        CUDA_CHECK(cudaMemcpyAsync(res->row_off.data() + done + 1, bo.row_off.get() + 1, m * 8, cudaMemcpyDeviceToHost, s));
         total.d2h_bytes += (m + 1) * 8;
         if (results_to_host) {
           const size_t old = res->qid.size();
@@ -2105,7 +2105,8 @@ impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n
           }
         }
         CUDA_CHECK(cudaStreamSynchronize(s));
-        for (size_t i = 1; i <= m; i++) res->row_off[done + i] = res_base + ro[i];
+        if (res_base)
+          for (size_t i = 1; i <= m; i++) res->row_off[done + i] += res_base;
         res_base += R;
       }
       // every arena block of this batch is out of scope and the stream is idle
