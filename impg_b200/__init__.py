@@ -175,6 +175,11 @@ def lib():
         L.impgx_format_paf.restype = C.c_void_p
         L.impgx_synth_num_alignments.restype = C.c_uint64
         L.impgx_partitions_format_bed.restype = C.c_void_p
+        L.impgx_impg_num_seqs.restype = C.c_uint32
+        L.impgx_impg_seq_name.restype = C.c_char_p
+        L.impgx_impg_seq_len.restype = C.c_uint64
+        L.impgx_impg_num_entries.restype = C.c_uint64
+        L.impgx_impg_num_records.restype = C.c_uint64
         L.impgx_debug_host_columns.restype = C.c_long
         L.impgx_debug_host_columns_shard.restype = C.c_long
         _lib = L
@@ -301,6 +306,15 @@ class Impg:
         return cls(h.value)
 
     # -- SequenceIndex accessors (reference src/seqidx.rs)
+    @classmethod
+    def from_impg(cls, impg_path, alignment_files, device=0):
+        """Impg::load_from_file (reference src/impg.rs:1777-1850) + the CIGARs of the alignment files."""
+        arr = (C.c_char_p * len(alignment_files))(*[p.encode() for p in alignment_files])
+        h = C.c_void_p()
+        _check(lib().impgx_index_from_impg(impg_path.encode(), arr, C.c_size_t(len(alignment_files)), C.c_int(device),
+                                           C.byref(h)))
+        return cls(h.value)
+
     def set_names(self, names):
         arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
         _check(lib().impgx_index_set_names(self.h, arr, C.c_uint32(len(names))))
@@ -436,6 +450,44 @@ class Impg:
         s = C.string_at(ptr).decode()
         lib().impgx_free(C.c_void_p(ptr))
         return s
+
+
+def impg_write(paf_paths, out_path, bidirectional=True):
+    """`impg index`: the .impg file stock impg would load for these PAF files (reference
+    src/impg.rs:1655-1720). Host only."""
+    arr = (C.c_char_p * len(paf_paths))(*[p.encode() for p in paf_paths])
+    _check(lib().impgx_impg_write(arr, C.c_size_t(len(paf_paths)), C.c_int(1 if bidirectional else 0), out_path.encode()))
+
+
+class ImpgFile:
+    """A parsed .impg index file (reference src/impg.rs:1777-1850): sequence index + the alignments
+    with where their CIGAR text lives in the alignment files. Host only."""
+
+    def __init__(self, path):
+        h = C.c_void_p()
+        _check(lib().impgx_impg_open(path.encode(), C.byref(h)))
+        self.h = h
+        L = lib()
+        self.version = L.impgx_impg_version(h)
+        self.bidirectional = bool(L.impgx_impg_bidirectional(h))
+        n = L.impgx_impg_num_seqs(h)
+        self.names = [L.impgx_impg_seq_name(h, C.c_uint32(i)).decode() for i in range(n)]
+        self.lens = np.array([L.impgx_impg_seq_len(h, C.c_uint32(i)) for i in range(n)], np.uint64)
+        self.n_entries = L.impgx_impg_num_entries(h)
+        self.n_records = L.impgx_impg_num_records(h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().impgx_impg_close(self.h)
+            self.h = None
+
+    def records(self):
+        """(records, file_index, data_offset, data_bytes) in alignment-file order."""
+        n = self.n_records
+        recs = np.zeros(n, RECORD_DTYPE)
+        fi, off, ln = np.zeros(n, np.uint32), np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+        _check(lib().impgx_impg_records(self.h, _p(recs), _p(fi), _p(off), _p(ln)))
+        return recs, fi, off, ln
 
 
 class Partitions:

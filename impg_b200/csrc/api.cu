@@ -47,15 +47,6 @@ long parse_cigar(const char *s, size_t n, std::vector<uint32_t> &out) {
   return cnt;
 }
 
-struct PafData {
-  std::vector<impgx_record> recs;
-  std::vector<uint32_t> runs;
-  std::vector<uint64_t> run_off{0};
-  std::vector<std::string> names;
-  std::vector<uint64_t> lens;
-  std::unordered_map<std::string, uint32_t> ids;
-};
-
 static bool parse_usize(const char *b, const char *e, uint64_t &v) {
   if (b < e && *b == '+') b++;
   if (b >= e) return false;
@@ -85,6 +76,7 @@ void parse_paf(const std::string &path, PafData &out) {
     REQUIRE(!bad, IMPGX_E_IO, "error while reading / inflating '" + path + "'");
   }
   size_t pos = 0, line_no = 0;
+  uint64_t ref_pos = 0;
   auto get_id = [&](const char *b, const char *e, uint64_t len) {
     std::string name(b, e);
     auto it = out.ids.find(name);
@@ -134,21 +126,32 @@ void parse_paf(const std::string &path, PafData &out) {
     r.strand = sc == '-' ? 1 : 0;
     r.reserved = 0;
     bool have = false;
+    // byte offset / length of the CIGAR text as the reference records them (src/paf.rs:150-162, :182-191:
+    // line lengths are counted without the line terminator, plus one)
+    uint64_t cg_off = ref_pos, cg_len = 0;
     for (auto &t : fld) {
       if (t.second - t.first >= 5 && memcmp(t.first, "cg:Z:", 5) == 0) {
         long k = parse_cigar(t.first + 5, (size_t)(t.second - t.first - 5), out.runs);
         REQUIRE(k >= 0, IMPGX_E_PARSE, "Invalid CIGAR operation" + where);
         have = k > 0;
+        cg_off += 5;
+        cg_len = (uint64_t)(t.second - t.first - 5);
         break;
       }
+      cg_off += (uint64_t)(t.second - t.first) + 1;
     }
+    ref_pos += (uint64_t)(end - pos) + 1;
     // the reference panics at query time when an alignment has no cg:Z tag
     // (src/impg.rs:506-511); here it is a build-time error
     REQUIRE(have, IMPGX_E_PARSE, "The alignment file does not contain CIGAR strings ('cg:Z' tag)" + where);
     out.recs.push_back(r);
     out.run_off.push_back(out.runs.size());
+    out.cg_off.push_back(cg_off);
+    out.cg_len.push_back(cg_len);
+    out.file_idx.push_back(out.n_files);
     pos = eol + 1;
   }
+  out.n_files++;
 }
 
 }  // namespace impgx

@@ -2,6 +2,9 @@
 #pragma once
 #include <cstring>
 #include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
 
 #include "index.cuh"
 
@@ -27,6 +30,22 @@ impgx_index *index_build(const impgx_record *recs, size_t n, const uint32_t *run
 // Runs the whole batch (chunked into row batches), ranges on host or device.
 impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n, const impgx_params &p, bool bed,
                            bool ranges_on_device, bool results_to_host, void *stream, class Comm *comm = nullptr);
+
+// One or more parsed PAF files over a shared SequenceIndex (ids by first appearance, src/seqidx.rs:22-35).
+struct PafData {
+  std::vector<impgx_record> recs;
+  std::vector<uint32_t> runs;
+  std::vector<uint64_t> run_off{0};
+  std::vector<std::string> names;
+  std::vector<uint64_t> lens;
+  std::unordered_map<std::string, uint32_t> ids;
+  // where the reference would find the CIGAR text again (AlignmentRecord.strand_and_data_offset / data_bytes)
+  std::vector<uint64_t> cg_off, cg_len;
+  std::vector<uint32_t> file_idx;
+  uint32_t n_files = 0;
+};
+void parse_paf(const std::string &path, PafData &out);
+long parse_cigar(const char *s, size_t n, std::vector<uint32_t> &out);
 
 void project_batch(int device, size_t n, const int32_t *req_start, const int32_t *req_end, const impgx_record *records,
                    const uint32_t *runs, const uint64_t *run_offsets, int32_t *out4, uint8_t *ok,

@@ -320,6 +320,33 @@ char *impgx_format_paf(const impgx_index *idx, const impgx_results *res,
                        size_t row, const char *name, int32_t merge_distance);
 void impgx_free(void *p);
 
+/* ---- `.impg` index files (Impg::serialize_with_forest_map / load_from_file,
+ * src/impg.rs:1655-1850; bincode 2 standard config, see csrc/impg_file.cu). An index file holds the
+ * sequence index and, per target, the interval entries with (alignment file index, byte offset,
+ * byte length) of their CIGAR text — no CIGARs — so opening one needs the alignment files it was
+ * built from (uncompressed PAF). Byte parity with stock impg is unpinned: no fixture, bincode not
+ * vendored. */
+typedef struct impgx_impg impgx_impg; /* a parsed index file, host memory only */
+int impgx_impg_open(const char *path, impgx_impg **out);
+void impgx_impg_close(impgx_impg *f);
+int impgx_impg_version(const impgx_impg *f);       /* 2 = "IMPGIDX2", 1 = legacy "IMPGIDX1" */
+int impgx_impg_bidirectional(const impgx_impg *f); /* reversed entries present (src/impg.rs:1588-1605) */
+uint32_t impgx_impg_num_seqs(const impgx_impg *f);
+const char *impgx_impg_seq_name(const impgx_impg *f, uint32_t id);
+uint64_t impgx_impg_seq_len(const impgx_impg *f, uint32_t id);
+uint64_t impgx_impg_num_entries(const impgx_impg *f); /* tree intervals, both directions */
+uint64_t impgx_impg_num_records(const impgx_impg *f); /* alignments = entries without the REVERSED bit */
+/* the alignments in alignment-file order (file index, then byte offset); any output may be NULL */
+int impgx_impg_records(const impgx_impg *f, impgx_record *records, uint32_t *file_index, uint64_t *data_offset,
+                       uint64_t *data_bytes);
+/* Impg::load_from_file + the CIGARs decoded once from alignment_files[alignment_file_index]: the HBM
+ * index with the sequence ids of the file (so results are in stock impg's id space). */
+int impgx_index_from_impg(const char *impg_path, const char *const *alignment_files, size_t n_files, int device,
+                          impgx_index **out);
+/* parse the PAF files (ids by first appearance over the files in order) and write the index file
+ * stock impg would load for them (`impg index`); host only, no device needed. */
+int impgx_impg_write(const char *const *paf_paths, size_t n_paths, int bidirectional, const char *out_path);
+
 /* ---- partition: the second driver of the same kernels ----
  * partition_alignments (src/commands/partition.rs:158-712) for `-o bed`: windows are
  * taken from the sequences still missing, each window runs ONE transitive query with

@@ -1,0 +1,60 @@
+"""An index opened from a `.impg` file (reference src/impg.rs:1777-1850) answers exactly like
+the index built from the PAF itself — same sequence ids, same result order, same CIGARs — and like the oracle."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import _impg_format as F
+import _oracle as O
+import impg_b200 as ix
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+PAFS = sorted(glob.glob(os.path.join(GOLD, "*.paf")))
+
+
+def all_rows(idx):
+    return np.array([(s, 0, idx.seq_len(s)) for s in range(idx.n_seqs)], ix.RANGE_DTYPE)
+
+
+@pytest.mark.parametrize("paf", PAFS, ids=[os.path.basename(p) for p in PAFS])
+def test_index_from_impg_equals_index_from_paf(paf, tmp_path):
+    out = str(tmp_path / "x.impg")
+    ix.impg_write([paf], out)
+    a, b = ix.Impg.from_paf(paf), ix.Impg.from_impg(out, [paf])
+    assert b.n_seqs == a.n_seqs and b.n_entries == a.n_entries
+    assert [b.seq_name(i) for i in range(b.n_seqs)] == [a.seq_name(i) for i in range(a.n_seqs)]
+    orc = O.Index.from_paf(paf)
+    for mode, depth in ((ix.MODE_QUERY, 1), (ix.MODE_BFS, 0)):
+        p = ix.make_params(mode=mode, max_depth=depth, min_transitive_len=0, store_cigar=True)
+        ra, rb = a.query_batch(all_rows(a), p), b.query_batch(all_rows(b), p)
+        ca, cb = ra.columns(), rb.columns()
+        assert all((ca[k] == cb[k]).all() for k in ca)
+        op = O.make_params(mode=mode, max_depth=depth, min_transitive_len=0, store_cigar=True)
+        for r in range(min(b.n_seqs, 6)):
+            want = orc.perform_query(r, 0, orc.seq_len(r), op).tuples()
+            assert rb.row_tuples(r, cb) == want
+
+
+def test_index_from_a_scrambled_multi_file_impg(tmp_path):
+    # the file as stock impg could have written it: hash-ordered maps and trees, two alignment files
+    pafs = PAFS[:2]
+    names, lens, recs = F.parse_paf_like_reference(pafs)
+    trees = F.entries_by_target(recs)
+    p = tmp_path / "m.impg"
+    p.write_bytes(F.encode(names, lens, trees, map_order=list(reversed(range(len(names)))), tree_order=sorted(trees, reverse=True)))
+    b = ix.Impg.from_impg(str(p), pafs)
+    a = ix.MultiImpg.from_pafs(pafs).idx
+    assert [b.seq_name(i) for i in range(b.n_seqs)] == names
+    prm = ix.make_params(mode=ix.MODE_BFS, max_depth=2, min_transitive_len=0, merge_distance=100)
+    ca, cb = a.query_batch_bed(all_rows(a), prm).columns(), b.query_batch_bed(all_rows(b), prm).columns()
+    assert all((ca[k] == cb[k]).all() for k in ca)
+    with pytest.raises(ix.ImpgxError) as e:  # the second alignment file is missing
+        ix.Impg.from_impg(str(p), pafs[:1])
+    assert e.value.code == ix.E_INVALID
+    with pytest.raises(ix.ImpgxError) as e:  # a different file under the same index: offsets do not hold CIGARs
+        ix.Impg.from_impg(str(p), [pafs[1], pafs[0]])
+    assert e.value.code == ix.E_PARSE
