@@ -48,7 +48,7 @@ static int32_t parse_distance(const std::string &s) {
 // src/commands/partition.rs:158-712): partitions.bed, or partition<N>.bed with --separate-files.
 static int partition_main(int argc, char **argv) {
   std::vector<std::string> pafs;
-  std::string start_file, mode = "longest", folder, out_format = "bed";
+  std::string start_file, mode = "longest", folder, out_format = "bed", index_path;
   bool have_d = false, no_merge = false, separate = false, unidirectional = false;
   impgx_partition_params pp;
   memset(&pp, 0, sizeof pp);
@@ -69,7 +69,8 @@ static int partition_main(int argc, char **argv) {
     if (a == "-a" || a == "--alignment-files") {
       pafs.push_back(val());
       while (i + 1 < argc && argv[i + 1][0] != '-') pafs.push_back(argv[++i]);
-    } else if (a == "-w" || a == "--window-size") pp.window_size = strtoull(val().c_str(), nullptr, 10);
+    } else if (a == "-i" || a == "--index") index_path = val();
+    else if (a == "-w" || a == "--window-size") pp.window_size = strtoull(val().c_str(), nullptr, 10);
     else if (a == "--starting-sequences-file") start_file = val();
     else if (a == "--selection-mode") mode = val();
     else if (a == "--min-missing-size") pp.min_missing_size = atoi(val().c_str());
@@ -108,7 +109,8 @@ static int partition_main(int argc, char **argv) {
   {
     std::vector<const char *> paths;
     for (auto &f : pafs) paths.push_back(f.c_str());
-    check(impgx_index_from_pafs(paths.data(), paths.size(), unidirectional ? 0 : 1, device, &idx));
+    if (!index_path.empty()) check(impgx_index_from_impg(index_path.c_str(), paths.data(), paths.size(), device, &idx));
+    else check(impgx_index_from_pafs(paths.data(), paths.size(), unidirectional ? 0 : 1, device, &idx));
   }
   std::vector<uint32_t> starting;
   if (!start_file.empty()) {  // first tab field of every line that is not blank or a comment (:184-212)
@@ -164,10 +166,35 @@ static int partition_main(int argc, char **argv) {
   return 0;
 }
 
+// impgx-query index -a X.paf [Y.paf ...] -i out.impg [--unidirectional] — `impg index` (src/impg.rs:1655-1720)
+static int index_main(int argc, char **argv) {
+  std::vector<std::string> pafs;
+  std::string out;
+  bool unidirectional = false;
+  for (int i = 1; i < argc; i++) {
+    std::string a = argv[i];
+    if (a == "-a" || a == "--alignment-files") {
+      if (i + 1 >= argc) die("missing value for " + a);
+      pafs.push_back(argv[++i]);
+      while (i + 1 < argc && argv[i + 1][0] != '-') pafs.push_back(argv[++i]);
+    } else if (a == "-i" || a == "--index") {
+      if (i + 1 >= argc) die("missing value for " + a);
+      out = argv[++i];
+    } else if (a == "--unidirectional") unidirectional = true;
+    else die("unsupported option '" + a + "'");
+  }
+  if (pafs.empty() || out.empty()) die("usage: impgx-query index -a X.paf [Y.paf ...] -i out.impg [--unidirectional]");
+  std::vector<const char *> paths;
+  for (auto &f : pafs) paths.push_back(f.c_str());
+  check(impgx_impg_write(paths.data(), paths.size(), unidirectional ? 0 : 1, out.c_str()));
+  return 0;
+}
+
 int main(int argc, char **argv) {
   if (argc > 1 && !strcmp(argv[1], "partition")) return partition_main(argc - 1, argv + 1);
+  if (argc > 1 && !strcmp(argv[1], "index")) return index_main(argc - 1, argv + 1);
   std::vector<std::string> pafs;
-  std::string bed_path, range_text, out_format = "auto", subset_path, index_mode = "auto";
+  std::string bed_path, range_text, out_format = "auto", subset_path, index_mode = "auto", index_path;
   bool transitive = false, dfs = false, unidirectional = false, consider_strand = false, no_merge = false, have_d = false;
   int32_t d = 0, min_transitive_len = 101, min_dist = 10, min_out = -1;
   uint32_t max_depth = 2;
@@ -192,6 +219,7 @@ int main(int argc, char **argv) {
         if (!line.empty() && line[0] != '#') pafs.push_back(line);
       }
     } else if (a == "--index-mode") index_mode = val();
+    else if (a == "-i" || a == "--index") index_path = val();
     else if (a == "-b" || a == "--target-bed") bed_path = val();
     else if (a == "-r" || a == "--target-range") range_text = val();
     else if (a == "-x" || a == "--transitive") transitive = true;
@@ -209,7 +237,7 @@ int main(int argc, char **argv) {
     else if (a == "--subset-sequence-list") subset_path = val();
     else if (a == "--device") device = atoi(val().c_str());
     else if (a == "-h" || a == "--help") {
-      printf("usage: impgx-query (-a X.paf [Y.paf ...] | --alignment-list FILE) [--index-mode auto|single|per-file]\n"
+      printf("usage: impgx-query (-a X.paf [Y.paf ...] | --alignment-list FILE) [-i X.impg] [--index-mode auto|single|per-file]\n"
              "       (-b BED | -r seq:start-end) [-x] [-m N] (-d D | --no-merge) [-l L]\n"
              "       [-o auto|bed|bedpe|paf] [--min-transitive-len N] [--min-distance-between-ranges N]\n"
              "       [--transitive-dfs] [--unidirectional] [--consider-strandness] [--min-result-identity F]\n"
@@ -237,7 +265,9 @@ int main(int argc, char **argv) {
   {
     std::vector<const char *> pp;
     for (auto &f : pafs) pp.push_back(f.c_str());
-    check(impgx_index_from_pafs(pp.data(), pp.size(), unidirectional ? 0 : 1, device, &idx));
+    // -i: an index file written by `impg index` (or `impgx-query index`) over the same alignment files
+    if (!index_path.empty()) check(impgx_index_from_impg(index_path.c_str(), pp.data(), pp.size(), device, &idx));
+    else check(impgx_index_from_pafs(pp.data(), pp.size(), unidirectional ? 0 : 1, device, &idx));
   }
 
   // rows

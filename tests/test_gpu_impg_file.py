@@ -55,6 +55,28 @@ def test_index_from_a_scrambled_multi_file_impg(tmp_path):
     with pytest.raises(ix.ImpgxError) as e:  # the second alignment file is missing
         ix.Impg.from_impg(str(p), pafs[:1])
     assert e.value.code == ix.E_INVALID
-    with pytest.raises(ix.ImpgxError) as e:  # a different file under the same index: offsets do not hold CIGARs
-        ix.Impg.from_impg(str(p), [pafs[1], pafs[0]])
+    short = tmp_path / "short.paf"  # not the file the index was built from: the offsets fall off its end
+    short.write_bytes(open(pafs[1], "rb").read()[:40])
+    with pytest.raises(ix.ImpgxError) as e:
+        ix.Impg.from_impg(str(p), [pafs[0], str(short)])
     assert e.value.code == ix.E_PARSE
+
+
+def test_cli_index_then_query_with_index(tmp_path):
+    import subprocess
+    cli = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "impg_b200", "impgx-query")
+    paf = os.path.join(GOLD, "short_floor.paf")
+    impg = str(tmp_path / "sf.impg")
+    r = subprocess.run([cli, "index", "-a", paf, "-i", impg], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    args = ["-r", "C4FIXTURE#0#short_floor:0-250:0-250", "-d", "0", "--min-transitive-len", "0", "-x", "-o", "bed"]
+    a = subprocess.run([cli, "-a", paf] + args, capture_output=True, text=True)
+    b = subprocess.run([cli, "-a", paf, "-i", impg] + args, capture_output=True, text=True)
+    assert a.returncode == 0 and b.returncode == 0, (a.stderr, b.stderr)
+    assert a.stdout == b.stdout and a.stdout.count("\n") >= 2
+    p1 = subprocess.run([cli, "partition", "-a", paf, "-i", impg, "-w", "200", "-d", "50", "--output-folder", str(tmp_path / "p1")],
+                        capture_output=True, text=True)
+    p2 = subprocess.run([cli, "partition", "-a", paf, "-w", "200", "-d", "50", "--output-folder", str(tmp_path / "p2")],
+                        capture_output=True, text=True)
+    assert p1.returncode == 0 and p2.returncode == 0, (p1.stderr, p2.stderr)
+    assert (tmp_path / "p1" / "partitions.bed").read_text() == (tmp_path / "p2" / "partitions.bed").read_text()
