@@ -6,9 +6,10 @@ reference's cost structure (CIGAR text on disk, pread + parse per hit) on the co
 sub-world of the same index (contigs never align to one another in the synthetic world, so the
 windows, masks and partitions of contig-0 sequences are the same in both).
 
-    python tools/partition_bench.py [--workload c3] [--window 1000000] [-d 10000] [--keep 1.0] [--cpu-budget 30]
+    python tests/partition_bench.py [--workload c3] [--window 1000000] [-d 10000] [--keep 1.0] [--cpu-budget 30]
 
-Not a bench.py line: partition's unit of work (a window) is not BASELINE.json's metric."""
+Not a bench.py line: partition's unit of work (a window) is not BASELINE.json's metric. It lives under
+tests/ because its CPU leg runs the oracle (test infrastructure) as checker and baseline."""
 import argparse
 import json
 import os
@@ -19,7 +20,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import bench as B  # noqa: E402
 import impg_b200 as ix  # noqa: E402
 
