@@ -751,6 +751,22 @@ long impgx_debug_host_columns_shard(const impgx_record *records, size_t n, const
   }
 }
 
+// test hooks: the device sort / scan primitives on host arrays (both the single-CTA kernels for small inputs
+// and the CUB pipelines sit behind the same calls; the size decides)
+int impgx_debug_sort_pairs(int device, uint64_t *keys, uint32_t *vals, uint64_t n, int begin_bit, int end_bit, int key_bytes) {
+  API_BEGIN
+  REQUIRE(keys && vals && (key_bytes == 4 || key_bytes == 8) && begin_bit >= 0 && end_bit > begin_bit && end_bit <= 8 * key_bytes,
+          IMPGX_E_INVALID, "bad argument");
+  impgx::debug_sort_pairs(device, keys, vals, n, begin_bit, end_bit, key_bytes);
+  API_END
+}
+int impgx_debug_exclusive_scan(int device, uint64_t *a, uint64_t n_plus_1) {
+  API_BEGIN
+  REQUIRE(a && n_plus_1 >= 1, IMPGX_E_INVALID, "bad argument");
+  impgx::debug_exclusive_scan(device, a, n_plus_1);
+  API_END
+}
+
 // ---- synthetic workload generator (bench / tests)
 uint64_t impgx_synth_num_alignments(const impgx_synth_cfg *c) { return synth_num_alignments(*c); }
 

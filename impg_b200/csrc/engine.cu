@@ -2198,6 +2198,44 @@ impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n
   return res.release();
 }
 
+// ============================================================ test hooks for the device primitives
+// (host arrays in and out; `force` = 0 automatic, 1 the single-CTA kernels, 2 the CUB pipelines)
+void debug_sort_pairs(int device, uint64_t *keys, uint32_t *vals, uint64_t n, int begin_bit, int end_bit, int key_bytes) {
+  check_device(device);
+  Arena ar;
+  Scratch sc{&ar};
+  Ctx ctx;
+  cudaStream_t s = nullptr;
+  DBuf<uint32_t> dv(n, ar);
+  CUDA_CHECK(cudaMemcpy(dv.get(), vals, n * 4, cudaMemcpyHostToDevice));
+  if (key_bytes == 8) {
+    DBuf<uint64_t> dk(n, ar);
+    CUDA_CHECK(cudaMemcpy(dk.get(), keys, n * 8, cudaMemcpyHostToDevice));
+    sort_pairs(dk, dv, n, begin_bit, end_bit, sc, s, ctx);
+    CUDA_CHECK(cudaMemcpy(keys, dk.get(), n * 8, cudaMemcpyDeviceToHost));
+  } else {
+    std::vector<uint32_t> k32(n);
+    for (uint64_t i = 0; i < n; i++) k32[i] = (uint32_t)keys[i];
+    DBuf<uint32_t> dk(n, ar);
+    CUDA_CHECK(cudaMemcpy(dk.get(), k32.data(), n * 4, cudaMemcpyHostToDevice));
+    sort_pairs(dk, dv, n, begin_bit, end_bit, sc, s, ctx);
+    CUDA_CHECK(cudaMemcpy(k32.data(), dk.get(), n * 4, cudaMemcpyDeviceToHost));
+    for (uint64_t i = 0; i < n; i++) keys[i] = k32[i];
+  }
+  CUDA_CHECK(cudaMemcpy(vals, dv.get(), n * 4, cudaMemcpyDeviceToHost));
+}
+
+void debug_exclusive_scan(int device, uint64_t *a, uint64_t n_plus_1) {
+  check_device(device);
+  Arena ar;
+  Scratch sc{&ar};
+  cudaStream_t s = nullptr;
+  DBuf<uint64_t> d(n_plus_1, ar);
+  CUDA_CHECK(cudaMemcpy(d.get(), a, n_plus_1 * 8, cudaMemcpyHostToDevice));
+  exclusive_scan_u64(d.get(), n_plus_1, sc, s);
+  CUDA_CHECK(cudaMemcpy(a, d.get(), n_plus_1 * 8, cudaMemcpyDeviceToHost));
+}
+
 // ============================================================ KAT surface
 void project_batch(int device, size_t n, const int32_t *req_start, const int32_t *req_end, const impgx_record *records,
                    const uint32_t *runs, const uint64_t *run_offsets, int32_t *out4, uint8_t *ok,

@@ -47,6 +47,9 @@ struct PafData {
 void parse_paf(const std::string &path, PafData &out);
 long parse_cigar(const char *s, size_t n, std::vector<uint32_t> &out);
 
+void debug_sort_pairs(int device, uint64_t *keys, uint32_t *vals, uint64_t n, int begin_bit, int end_bit, int key_bytes);
+void debug_exclusive_scan(int device, uint64_t *a, uint64_t n_plus_1);
+
 void project_batch(int device, size_t n, const int32_t *req_start, const int32_t *req_end, const impgx_record *records,
                    const uint32_t *runs, const uint64_t *run_offsets, int32_t *out4, uint8_t *ok,
                    uint64_t *out_run_offsets, uint32_t *out_runs, size_t out_runs_cap);
