@@ -676,6 +676,8 @@ __global__ void __launch_bounds__(T == 32 ? 256 : T)
   m.parent = reinterpret_cast<uint16_t *>(m.tid + CAP);
   m.heads = m.parent + CAP;
   __shared__ unsigned int s_cnt[GROUPS][2];  // [0] roots, [1] multi-member group heads
+  __shared__ uint64_t s_rk[(T == 32) ? 1 : T / 32], s_ro[(T == 32) ? 1 : T / 32];  // cross-warp argmin of the prefilter
+  __shared__ uint32_t s_ri[(T == 32) ? 1 : T / 32];
   auto sync = [&]() {
     if (T == 32) __syncwarp();
     else __syncthreads();
@@ -784,16 +786,113 @@ __global__ void __launch_bounds__(T == 32 ? 256 : T)
       }
       sync();
     }
-    // ---- roots -> stage-B sort keys: (start, !forward, box index); equal (start, strand) are
-    // put into ord order afterwards (src/main.rs:12481-12494 is a stable sort of the input order)
+    // ---- roots -> list of box indices (the union-find is done: `heads` and `parent` become scratch)
     for (uint32_t i = lt; i < n; i += T)
-      if (m.parent[i] == i) {
-        const bool fwd = m.qlo[i] <= m.qhi[i];
-        const uint32_t st = (uint32_t)(fwd ? m.qlo[i] : m.qhi[i]);
-        m.skey[atomicAdd(&s_cnt[gi][0], 1u)] = ((uint64_t)st << 17) | ((uint64_t)(fwd ? 0u : 1u) << 16) | i;
-      }
+      if (m.parent[i] == i) m.heads[atomicAdd(&s_cnt[gi][0], 1u)] = (uint16_t)i;
     sync();
-    const uint32_t nr = s_cnt[gi][0];
+    uint32_t nr = s_cnt[gi][0];
+    uint16_t *live = m.heads, *spare = m.parent;
+    // ---- prefilter: drop the boxes the sweep of src/main.rs:12496-12556 cannot see. In the sorted order
+    // (start, !forward, input order) a box D that comes after a box J with end(J) >= end(D) never opens a
+    // row (its start lies inside the span merged so far), never extends the span and is never "longer than
+    // the span merged before it" (that span contains it), so with merge_strands and d >= 0 it changes
+    // neither the rows nor their orientation. Round r takes the first box of the remaining ones in sorted
+    // order (the pivot: an argmin, no sort needed), keeps it, and drops every other box that ends at or
+    // before it; what survives ends later than every pivot. Hits of one (row, q) segment are mostly
+    // near-copies of one interval, so each round roughly halves the list the bitonic network has to sort.
+    if (merge_strands && md >= 0) {
+      constexpr uint32_t STOP = (T == 32) ? 32u : 64u;  // short enough for a quick sort
+      uint32_t n_piv = 0;
+      while (nr - n_piv > STOP && n_piv < 8) {
+        uint64_t bk = ~0ull, bo = ~0ull;
+        uint32_t bi = 0xffffu;
+        for (uint32_t c = n_piv + lt; c < nr; c += T) {
+          const uint32_t i = live[c];
+          const bool fwd = m.qlo[i] <= m.qhi[i];
+          const uint64_t k = ((uint64_t)(uint32_t)(fwd ? m.qlo[i] : m.qhi[i]) << 1) | (fwd ? 0u : 1u);
+          const uint64_t o = m.ord[i];
+          if (k < bk || (k == bk && o < bo)) {
+            bk = k;
+            bo = o;
+            bi = i;
+          }
+        }
+#pragma unroll
+        for (int dlt = 16; dlt > 0; dlt >>= 1) {
+          const uint64_t ok = __shfl_xor_sync(FULL, bk, dlt), oo = __shfl_xor_sync(FULL, bo, dlt);
+          const uint32_t oi = __shfl_xor_sync(FULL, bi, dlt);
+          if (ok < bk || (ok == bk && oo < bo)) {
+            bk = ok;
+            bo = oo;
+            bi = oi;
+          }
+        }
+        if (T != 32) {
+          if (lane == 0) {
+            s_rk[threadIdx.x >> 5] = bk;
+            s_ro[threadIdx.x >> 5] = bo;
+            s_ri[threadIdx.x >> 5] = bi;
+          }
+          __syncthreads();
+#pragma unroll
+          for (int w = 0; w < T / 32; w++) {
+            const uint64_t ok = s_rk[w], oo = s_ro[w];
+            if (ok < bk || (ok == bk && oo < bo)) {
+              bk = ok;
+              bo = oo;
+              bi = s_ri[w];
+            }
+          }
+        }
+        // every thread holds the pivot; new list = old pivots, the pivot, the boxes that end after it
+        const int32_t pe = max(m.qlo[bi], m.qhi[bi]);
+        for (uint32_t c = lt; c < n_piv; c += T) spare[c] = live[c];
+        if (lt == 0) {
+          spare[n_piv] = (uint16_t)bi;
+          s_cnt[gi][0] = n_piv + 1;
+        }
+        sync();
+        uint32_t base = n_piv + 1;  // warp classes: the running count lives in a register
+        for (uint32_t c0 = n_piv; c0 < nr; c0 += T) {
+          const uint32_t c = c0 + lt;
+          uint32_t i = 0;
+          bool keep = false;
+          if (c < nr) {
+            i = live[c];
+            keep = i != bi && max(m.qlo[i], m.qhi[i]) > pe;
+          }
+          const unsigned bm = __ballot_sync(FULL, keep);
+          uint32_t wb;
+          if (T == 32) {
+            wb = base;
+            base += __popc(bm);
+          } else {
+            wb = 0;
+            if (lane == 0 && bm) wb = atomicAdd(&s_cnt[gi][0], (unsigned)__popc(bm));
+            wb = __shfl_sync(FULL, wb, 0);
+          }
+          if (keep) spare[wb + __popc(bm & lanemask_lt())] = (uint16_t)i;
+        }
+        if (T == 32 && lt == 0) s_cnt[gi][0] = base;
+        sync();
+        const uint32_t before = nr - n_piv;
+        nr = s_cnt[gi][0];
+        n_piv++;
+        uint16_t *t = live;
+        live = spare;
+        spare = t;
+        if ((before - (nr - n_piv)) * 4 < before) break;  // little was dominated: the ends grow with the starts
+      }
+    }
+    // ---- stage-B sort keys: (start, !forward, box index); equal (start, strand) are put into ord
+    // order afterwards (src/main.rs:12481-12494 is a stable sort of the input order)
+    for (uint32_t c = lt; c < nr; c += T) {
+      const uint32_t i = live[c];
+      const bool fwd = m.qlo[i] <= m.qhi[i];
+      const uint32_t st = (uint32_t)(fwd ? m.qlo[i] : m.qhi[i]);
+      m.skey[c] = ((uint64_t)st << 17) | ((uint64_t)(fwd ? 0u : 1u) << 16) | i;
+    }
+    sync();
     uint32_t P = 1;
     while (P < nr) P <<= 1;
     for (uint32_t i = nr + lt; i < P; i += T) m.skey[i] = ~0ull;
