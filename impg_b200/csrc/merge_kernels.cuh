@@ -676,8 +676,7 @@ __global__ void __launch_bounds__(T == 32 ? 256 : T)
   m.parent = reinterpret_cast<uint16_t *>(m.tid + CAP);
   m.heads = m.parent + CAP;
   __shared__ unsigned int s_cnt[GROUPS][2];  // [0] roots, [1] multi-member group heads
-  __shared__ uint64_t s_rk[(T == 32) ? 1 : T / 32], s_ro[(T == 32) ? 1 : T / 32];  // cross-warp argmin of the prefilter
-  __shared__ uint32_t s_ri[(T == 32) ? 1 : T / 32];
+  __shared__ uint64_t s_rk[(T == 32) ? 1 : T / 32];  // cross-warp argmax of the prefilter
   auto sync = [&]() {
     if (T == 32) __syncwarp();
     else __syncthreads();
@@ -796,56 +795,34 @@ __global__ void __launch_bounds__(T == 32 ? 256 : T)
     // (start, !forward, input order) a box D that comes after a box J with end(J) >= end(D) never opens a
     // row (its start lies inside the span merged so far), never extends the span and is never "longer than
     // the span merged before it" (that span contains it), so with merge_strands and d >= 0 it changes
-    // neither the rows nor their orientation. Round r takes the first box of the remaining ones in sorted
-    // order (the pivot: an argmin, no sort needed), keeps it, and drops every other box that ends at or
-    // before it; what survives ends later than every pivot. Hits of one (row, q) segment are mostly
-    // near-copies of one interval, so each round roughly halves the list the bitonic network has to sort.
+    // neither the rows nor their orientation. The hits of one (row, q) segment are mostly near-copies of one
+    // interval, so the LONGEST box contains about half of the others: each round takes the longest
+    // remaining box as the pivot J (an argmax, no sort), keeps it, and drops what it dominates; the
+    // bitonic network below then sorts a third of the compare-exchanges it would otherwise need.
     if (merge_strands && md >= 0) {
       constexpr uint32_t STOP = (T == 32) ? 32u : 64u;  // short enough for a quick sort
       uint32_t n_piv = 0;
-      while (nr - n_piv > STOP && n_piv < 8) {
-        uint64_t bk = ~0ull, bo = ~0ull;
-        uint32_t bi = 0xffffu;
+      while (nr - n_piv > STOP && n_piv < 6) {
+        uint64_t best = 0;  // (length + 1) << 16 | box index; 0 = none
         for (uint32_t c = n_piv + lt; c < nr; c += T) {
           const uint32_t i = live[c];
-          const bool fwd = m.qlo[i] <= m.qhi[i];
-          const uint64_t k = ((uint64_t)(uint32_t)(fwd ? m.qlo[i] : m.qhi[i]) << 1) | (fwd ? 0u : 1u);
-          const uint64_t o = m.ord[i];
-          if (k < bk || (k == bk && o < bo)) {
-            bk = k;
-            bo = o;
-            bi = i;
-          }
+          const uint64_t len = (uint64_t)((int64_t)max(m.qlo[i], m.qhi[i]) - (int64_t)min(m.qlo[i], m.qhi[i])) + 1;
+          best = max(best, (len << 16) | i);
         }
 #pragma unroll
-        for (int dlt = 16; dlt > 0; dlt >>= 1) {
-          const uint64_t ok = __shfl_xor_sync(FULL, bk, dlt), oo = __shfl_xor_sync(FULL, bo, dlt);
-          const uint32_t oi = __shfl_xor_sync(FULL, bi, dlt);
-          if (ok < bk || (ok == bk && oo < bo)) {
-            bk = ok;
-            bo = oo;
-            bi = oi;
-          }
-        }
+        for (int dlt = 16; dlt > 0; dlt >>= 1) best = max(best, __shfl_xor_sync(FULL, best, dlt));
         if (T != 32) {
-          if (lane == 0) {
-            s_rk[threadIdx.x >> 5] = bk;
-            s_ro[threadIdx.x >> 5] = bo;
-            s_ri[threadIdx.x >> 5] = bi;
-          }
+          if (lane == 0) s_rk[threadIdx.x >> 5] = best;
           __syncthreads();
 #pragma unroll
-          for (int w = 0; w < T / 32; w++) {
-            const uint64_t ok = s_rk[w], oo = s_ro[w];
-            if (ok < bk || (ok == bk && oo < bo)) {
-              bk = ok;
-              bo = oo;
-              bi = s_ri[w];
-            }
-          }
+          for (int w = 0; w < T / 32; w++) best = max(best, s_rk[w]);
         }
-        // every thread holds the pivot; new list = old pivots, the pivot, the boxes that end after it
-        const int32_t pe = max(m.qlo[bi], m.qhi[bi]);
+        // every thread holds the pivot; new list = old pivots, the pivot, the boxes it does not dominate
+        const uint32_t bi = (uint32_t)(best & 0xffffu);
+        const bool pf = m.qlo[bi] <= m.qhi[bi];
+        const int32_t pe = pf ? m.qhi[bi] : m.qlo[bi];
+        const uint64_t pk = ((uint64_t)(uint32_t)(pf ? m.qlo[bi] : m.qhi[bi]) << 1) | (pf ? 0u : 1u);
+        const uint64_t po = m.ord[bi];
         for (uint32_t c = lt; c < n_piv; c += T) spare[c] = live[c];
         if (lt == 0) {
           spare[n_piv] = (uint16_t)bi;
@@ -859,7 +836,10 @@ __global__ void __launch_bounds__(T == 32 ? 256 : T)
           bool keep = false;
           if (c < nr) {
             i = live[c];
-            keep = i != bi && max(m.qlo[i], m.qhi[i]) > pe;
+            const bool fwd = m.qlo[i] <= m.qhi[i];
+            const uint64_t k = ((uint64_t)(uint32_t)(fwd ? m.qlo[i] : m.qhi[i]) << 1) | (fwd ? 0u : 1u);
+            const bool after = k > pk || (k == pk && m.ord[i] > po);  // sorts after the pivot
+            keep = i != bi && !(after && (fwd ? m.qhi[i] : m.qlo[i]) <= pe);
           }
           const unsigned bm = __ballot_sync(FULL, keep);
           uint32_t wb;
@@ -881,7 +861,7 @@ __global__ void __launch_bounds__(T == 32 ? 256 : T)
         uint16_t *t = live;
         live = spare;
         spare = t;
-        if ((before - (nr - n_piv)) * 4 < before) break;  // little was dominated: the ends grow with the starts
+        if ((before - (nr - n_piv)) * 10 < before) break;  // the pivot dominated next to nothing: stop
       }
     }
     // ---- stage-B sort keys: (start, !forward, box index); equal (start, strand) are put into ord
