@@ -884,23 +884,28 @@ __global__ void __launch_bounds__(T == 32 ? 256 : T)
       const uint32_t half = P >> 1;
       const uint32_t ppw = (T == 32) ? half : max(32u, half / (uint32_t)(T / 32));
       const uint32_t wbase = (T == 32) ? 0u : (uint32_t)(threadIdx.x >> 5) * ppw;
-      for (uint32_t k = 2; k <= P; k <<= 1) {
-        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-          for (uint32_t r = lane; r < ppw; r += 32) {
-            const uint32_t i = wbase + r;  // i-th compare-exchange of this step: lo has bit j clear
-            if (i < half) {
-              const uint32_t lo = ((i & ~(j - 1)) << 1) | (i & (j - 1)), hi = lo | j;
-              const uint64_t x = m.skey[lo], y = m.skey[hi];
-              const bool up = (lo & k) == 0;
-              if ((y < x) == up) {
-                m.skey[lo] = y;
-                m.skey[hi] = x;
+      // A short list (after the prefilter) keeps only the first warps busy: the others skip the network
+      // and wait at the CTA barrier below; the working warps meet at a named barrier of their own.
+      const uint32_t n_work = (T == 32) ? 32u : min((uint32_t)T, ((half + ppw - 1) / ppw) * 32u);
+      if (T == 32 || wbase < half) {
+        for (uint32_t k = 2; k <= P; k <<= 1) {
+          for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t r = lane; r < ppw; r += 32) {
+              const uint32_t i = wbase + r;  // i-th compare-exchange of this step: lo has bit j clear
+              if (i < half) {
+                const uint32_t lo = ((i & ~(j - 1)) << 1) | (i & (j - 1)), hi = lo | j;
+                const uint64_t x = m.skey[lo], y = m.skey[hi];
+                const bool up = (lo & k) == 0;
+                if ((y < x) == up) {
+                  m.skey[lo] = y;
+                  m.skey[hi] = x;
+                }
               }
             }
+            const uint32_t j_next = j > 1 ? (j >> 1) : k;  // first step of the next level has j = k
+            if (T != 32 && (j > ppw || j_next > ppw)) asm volatile("bar.sync 1, %0;" ::"r"(n_work) : "memory");
+            else __syncwarp();
           }
-          const uint32_t j_next = j > 1 ? (j >> 1) : k;  // first step of the next level has j = k
-          if (T != 32 && (j > ppw || j_next > ppw)) __syncthreads();
-          else __syncwarp();
         }
       }
       sync();
