@@ -136,6 +136,19 @@ def test_stepper_matches_oracle_partition_patchy(k):
         assert windows2 == windows and got2.rows() == got.rows()
 
 
+def test_group_selection_modes_with_other_separators():
+    # names without the separator, a multi-character separator, the empty separator (str::split("") semantics)
+    (recs, runs, offs, lens, names), _ = patchy_world(seed=42, keep=0.3)
+    for sep_names, mode in (([n.replace("#", "::") for n in names], "haplotype,::"),
+                            ([n.replace("#", "") for n in names], "sample"),
+                            (names, "sample,"), (names, "haplotype,"), (names, "sample,1#")):
+        oidx = O.Index.build(recs, runs, offs, lens, names=sep_names)
+        kw = dict(window_size=9000, merge_distance=300, selection_mode=mode)
+        want = oidx.partition(O.make_partition_params(**kw))
+        got, windows = step_with_oracle(oidx, lens, sep_names, kw)
+        assert windows == want["windows"] and got.rows() == norm(want["rows"]), mode
+
+
 def test_partitions_tile_every_sequence_exactly_once():
     oidx, lens, names = small_world(seed=3, genomes=6, rev=500)
     for kw in (dict(window_size=10000, merge_distance=1000), dict(window_size=33333, merge_distance=0, max_depth=1)):
