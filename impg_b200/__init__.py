@@ -68,7 +68,8 @@ class PartitionParams(C.Structure):
                 ("selection_mode", C.c_char_p), ("merge_distance", C.c_int32), ("min_missing_size", C.c_int32),
                 ("min_boundary_distance", C.c_int32), ("transitive_dfs", C.c_uint32), ("max_depth", C.c_uint32),
                 ("min_transitive_len", C.c_int32), ("min_distance_between_ranges", C.c_int32),
-                ("rehome_singletons", C.c_uint32), ("min_identity", C.c_double)]
+                ("rehome_singletons", C.c_uint32), ("min_identity", C.c_double), ("multi_impg", C.c_uint32),
+                ("reserved", C.c_uint32)]
 
 
 class PartitionView(C.Structure):
@@ -80,7 +81,7 @@ class PartitionView(C.Structure):
 def make_partition_params(window_size, merge_distance, starting_seqs=None, selection_mode="longest",
                           min_missing_size=3000, min_boundary_distance=3000, transitive_dfs=False, max_depth=2,
                           min_transitive_len=101, min_distance_between_ranges=10, rehome_singletons=True,
-                          min_identity=None):
+                          min_identity=None, multi_impg=False):
     """Arguments of partition_alignments (reference src/commands/partition.rs:158-181); defaults are
     `impg partition`'s CLI defaults (src/main.rs:4765-4880, :4259-4279). -d has no default there."""
     p = PartitionParams()
@@ -101,6 +102,8 @@ def make_partition_params(window_size, merge_distance, starting_seqs=None, selec
     p.min_distance_between_ranges = min_distance_between_ranges
     p.rehome_singletons = 1 if rehome_singletons else 0
     p.min_identity = float("nan") if min_identity is None else float(min_identity)
+    p.multi_impg = 1 if multi_impg else 0
+    p.reserved = 0
     return p
 
 

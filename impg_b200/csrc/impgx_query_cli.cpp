@@ -48,7 +48,7 @@ static int32_t parse_distance(const std::string &s) {
 // src/commands/partition.rs:158-712): partitions.bed, or partition<N>.bed with --separate-files.
 static int partition_main(int argc, char **argv) {
   std::vector<std::string> pafs;
-  std::string start_file, mode = "longest", folder, out_format = "bed", index_path;
+  std::string start_file, mode = "longest", folder, out_format = "bed", index_path, index_mode = "auto";
   bool have_d = false, no_merge = false, separate = false, unidirectional = false;
   impgx_partition_params pp;
   memset(&pp, 0, sizeof pp);
@@ -70,6 +70,7 @@ static int partition_main(int argc, char **argv) {
       pafs.push_back(val());
       while (i + 1 < argc && argv[i + 1][0] != '-') pafs.push_back(argv[++i]);
     } else if (a == "-i" || a == "--index") index_path = val();
+    else if (a == "--index-mode") index_mode = val();
     else if (a == "-w" || a == "--window-size") pp.window_size = strtoull(val().c_str(), nullptr, 10);
     else if (a == "--starting-sequences-file") start_file = val();
     else if (a == "--selection-mode") mode = val();
@@ -103,6 +104,10 @@ static int partition_main(int argc, char **argv) {
   if (!have_d && !no_merge) die("-d/--merge-distance is required. Use `--no-merge` to explicitly disable merging.");
   if (no_merge) pp.merge_distance = -1;
   if (out_format != "bed") die("output format '" + out_format + "' needs sequence files and is outside the accelerated path (bed)");
+  if (index_mode != "auto" && index_mode != "single" && index_mode != "per-file")
+    die("invalid --index-mode '" + index_mode + "' (auto, single, per-file)");
+  // with one sub-index per file the reference's windows are answered by MultiImpg's walk (src/multi_impg.rs:687-755)
+  pp.multi_impg = (index_mode == "per-file" || (index_mode == "auto" && pafs.size() >= 100)) ? 1 : 0;
   pp.selection_mode = mode.c_str();
 
   impgx_index *idx = nullptr;

@@ -537,7 +537,8 @@ int impgx_partition(impgx_index *idx, const impgx_partition_params *params, impg
   std::unique_ptr<impgx_partitioner> p(
       make_partitioner(idx->seq_lens.data(), nm.empty() ? nullptr : nm.data(), idx->n_seqs, *params));
   impgx_params q{};
-  q.mode = params->transitive_dfs ? IMPGX_MODE_DFS : IMPGX_MODE_BFS;
+  q.mode = params->multi_impg ? (params->transitive_dfs ? IMPGX_MODE_MULTI_DFS : IMPGX_MODE_MULTI_BFS)
+                              : (params->transitive_dfs ? IMPGX_MODE_DFS : IMPGX_MODE_BFS);
   q.max_depth = params->max_depth;
   q.min_transitive_len = params->min_transitive_len;
   q.min_distance_between_ranges = params->min_distance_between_ranges;

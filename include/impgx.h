@@ -372,6 +372,9 @@ typedef struct impgx_partition_params {
   int32_t min_distance_between_ranges; /* default 10 */
   uint32_t rehome_singletons;          /* !--no-rehome-singletons (rehome_singleton_slivers :45-156) */
   double min_identity;                 /* --min-result-identity; NaN = None */
+  uint32_t multi_impg;                 /* the windows use MultiImpg's transitive walk (src/multi_impg.rs:796-991; the
+                                          reference's index is a MultiImpg with --index-mode per-file or >= 100 files) */
+  uint32_t reserved;
 } impgx_partition_params;
 
 typedef struct impgx_partitions impgx_partitions;

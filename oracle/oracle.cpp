@@ -2105,7 +2105,12 @@ std::vector<PInterval> mask_and_update_regions(std::vector<PInterval> &overlaps,
 }
 
 // :715-937
-bool select_and_window_sequences(std::vector<impgx_range> &windows, const Index &idx, const RegionMap &missing_regions,
+struct SeqInfo {  // what partition reads from impg.seq_index()
+  const std::vector<uint64_t> &seq_lens;
+  const std::vector<std::string> &names;
+};
+
+bool select_and_window_sequences(std::vector<impgx_range> &windows, const SeqInfo &idx, const RegionMap &missing_regions,
                                  const std::string &selection_mode, int64_t window_size) {
   std::vector<impgx_range> ranges_to_window;
   if (selection_mode == "longest") {
@@ -2281,8 +2286,10 @@ struct PartitionOut {
   std::string error;
 };
 
-// :158-712, output_format "bed", separate_files = false (single partitions.bed)
-void partition_alignments(const Index &idx, const impgx_partition_params &pp, int threads, PartitionOut &out) {
+// :158-712, output_format "bed", separate_files = false (single partitions.bed). Generic over the ImpgIndex
+// implementor (:159): `query` answers one window with the current masked_regions.
+template <class Query>
+void partition_alignments(const SeqInfo &idx, Query &&query, const impgx_partition_params &pp, PartitionOut &out) {
   const int64_t window_size = (int64_t)pp.window_size;
   const std::string selection_mode = pp.selection_mode ? pp.selection_mode : "longest";
   const uint32_t n_seqs = (uint32_t)idx.seq_lens.size();
@@ -2342,8 +2349,7 @@ void partition_alignments(const Index &idx, const impgx_partition_params &pp, in
       mask_off[n_seqs] = mask_rng.size() / 2;
       q.mask_offsets = mask_off.data();
       q.mask_ranges = mask_rng.data();
-      std::vector<Result> res = pp.transitive_dfs ? query_transitive_dfs(idx, w.target_id, w.start, w.end, q)
-                                                  : query_transitive_bfs(idx, w.target_id, w.start, w.end, q, threads);
+      std::vector<Result> res = query(w, q);
       std::vector<PInterval> overlaps;
       overlaps.reserve(res.size());
       for (auto &r : res) overlaps.push_back({r.q_first, r.q_last, r.q_id});
@@ -2379,7 +2385,28 @@ extern "C" {
 
 void *orc_partition(void *h, const impgx_partition_params *pp, int threads) {
   PartitionOut *o = new PartitionOut();
-  partition_alignments(*(Index *)h, *pp, threads, *o);
+  const Index &idx = *(Index *)h;
+  const bool dfs = pp->transitive_dfs != 0;
+  partition_alignments(SeqInfo{idx.seq_lens, idx.names},
+                       [&](const impgx_range &w, const QParams &q) {
+                         return dfs ? query_transitive_dfs(idx, w.target_id, w.start, w.end, q)
+                                    : query_transitive_bfs(idx, w.target_id, w.start, w.end, q, threads);
+                       },
+                       *pp, *o);
+  return o;
+}
+// the same over a MultiImpg (src/multi_impg.rs:687-755 implement the trait's transitive queries)
+void *orc_multi_partition(void *h, const impgx_partition_params *pp, const char *const *names, uint32_t n_names) {
+  PartitionOut *o = new PartitionOut();
+  const MultiIndex &mi = *(MultiIndex *)h;
+  std::vector<std::string> nm(mi.seq_lens.size());
+  for (uint32_t i = 0; i < n_names && i < nm.size(); i++) nm[i] = names[i] ? names[i] : "";
+  const uint32_t mode = pp->transitive_dfs ? IMPGX_MODE_MULTI_DFS : IMPGX_MODE_MULTI_BFS;
+  partition_alignments(SeqInfo{mi.seq_lens, nm},
+                       [&](const impgx_range &w, const QParams &q) {
+                         return perform_query_multi(mi, w.target_id, w.start, w.end, mode, q);
+                       },
+                       *pp, *o);
   return o;
 }
 const char *orc_partition_error(void *o) { return ((PartitionOut *)o)->error.c_str(); }

@@ -125,13 +125,14 @@ class PartitionParams(C.Structure):
                 ("selection_mode", C.c_char_p), ("merge_distance", C.c_int32), ("min_missing_size", C.c_int32),
                 ("min_boundary_distance", C.c_int32), ("transitive_dfs", C.c_uint32), ("max_depth", C.c_uint32),
                 ("min_transitive_len", C.c_int32), ("min_distance_between_ranges", C.c_int32),
-                ("rehome_singletons", C.c_uint32), ("min_identity", C.c_double)]
+                ("rehome_singletons", C.c_uint32), ("min_identity", C.c_double), ("multi_impg", C.c_uint32),
+                ("reserved", C.c_uint32)]
 
 
 def make_partition_params(window_size, merge_distance, starting_seqs=None, selection_mode="longest",
                           min_missing_size=3000, min_boundary_distance=3000, transitive_dfs=False, max_depth=2,
                           min_transitive_len=101, min_distance_between_ranges=10, rehome_singletons=True,
-                          min_identity=None):
+                          min_identity=None, multi_impg=False):
     """Defaults are `impg partition`'s (reference src/main.rs:4765-4880, :4259-4279)."""
     p = PartitionParams()
     p.window_size = window_size
@@ -151,6 +152,8 @@ def make_partition_params(window_size, merge_distance, starting_seqs=None, selec
     p.min_distance_between_ranges = min_distance_between_ranges
     p.rehome_singletons = 1 if rehome_singletons else 0
     p.min_identity = float("nan") if min_identity is None else float(min_identity)
+    p.multi_impg = 1 if multi_impg else 0
+    p.reserved = 0
     return p
 
 
@@ -170,7 +173,7 @@ def lib():
         L.orc_identity.restype = C.c_double
         L.orc_sorted_ranges_insert.restype = C.c_size_t
         for f in ("orc_index_build", "orc_index_from_paf", "orc_perform_query", "orc_results_from_arrays",
-                  "orc_query_batch", "orc_multi_build", "orc_multi_query_batch", "orc_partition",
+                  "orc_query_batch", "orc_multi_build", "orc_multi_query_batch", "orc_partition", "orc_multi_partition",
                   "orc_partition_format_bed"):
             getattr(L, f).restype = C.c_void_p
         L.orc_index_num_seqs.restype = C.c_uint32
@@ -311,6 +314,23 @@ class Results:
                                                      _p(off), _p(flat)))
 
 
+def _partition_result(h):
+    L = lib()
+    err = L.orc_partition_error(h).decode()
+    if err:
+        raise ValueError(err)
+    n, nw = L.orc_partition_len(h), L.orc_partition_num_windows(h)
+    pnum, seq = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+    first, last = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    win = np.zeros(max(nw, 1), RANGE_DTYPE)
+    L.orc_partition_copy(h, _p(pnum), _p(seq), _p(first), _p(last), _p(win))
+    npart, pbp, tbp = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+    L.orc_partition_totals(h, C.byref(npart), C.byref(pbp), C.byref(tbp))
+    return {"rows": list(zip(pnum.tolist(), seq.tolist(), first.tolist(), last.tolist())),
+            "windows": [tuple(int(x) for x in w) for w in win[:nw]], "n_partitions": npart.value,
+            "partitioned_bp": pbp.value, "total_bp": tbp.value}
+
+
 class MultiIndex:
     """The oracle's MultiImpg (reference src/multi_impg.rs): one sub-index per alignment file."""
 
@@ -337,6 +357,16 @@ class MultiIndex:
         return MultiIndex(lib().orc_multi_build(_p(records), C.c_size_t(len(records)), _p(runs), _p(run_offsets),
                                                 _p(seq_lens), C.c_uint32(len(seq_lens)), _p(fo), C.c_uint32(n_files),
                                                 C.c_int(1 if bidirectional else 0)))
+
+    def partition(self, pp, names):
+        """partition_alignments over a MultiImpg (its transitive walk answers the windows)."""
+        L = lib()
+        arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        h = C.c_void_p(L.orc_multi_partition(self.h, C.byref(pp), arr, C.c_uint32(len(names))))
+        try:
+            return _partition_result(h)
+        finally:
+            L.orc_partition_free(h)
 
     def query_batch(self, ranges, params, bed_merge=False):
         ranges = np.ascontiguousarray(ranges, dtype=RANGE_DTYPE)
@@ -453,22 +483,11 @@ class Index:
         L = lib()
         h = C.c_void_p(L.orc_partition(self.h, C.byref(pp), C.c_int(threads)))
         try:
-            err = L.orc_partition_error(h).decode()
-            if err:
-                raise ValueError(err)
-            n, nw = L.orc_partition_len(h), L.orc_partition_num_windows(h)
-            pnum, seq = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
-            first, last = np.zeros(n, np.int32), np.zeros(n, np.int32)
-            win = np.zeros(max(nw, 1), RANGE_DTYPE)
-            L.orc_partition_copy(h, _p(pnum), _p(seq), _p(first), _p(last), _p(win))
-            npart, pbp, tbp = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
-            L.orc_partition_totals(h, C.byref(npart), C.byref(pbp), C.byref(tbp))
+            out = _partition_result(h)
             ptr = L.orc_partition_format_bed(self.h, h)
-            text = C.string_at(ptr).decode()
+            out["bed"] = C.string_at(ptr).decode()
             L.orc_free(C.c_void_p(ptr))
-            return {"rows": list(zip(pnum.tolist(), seq.tolist(), first.tolist(), last.tolist())),
-                    "windows": [tuple(int(x) for x in w) for w in win[:nw]], "n_partitions": npart.value,
-                    "partitioned_bp": pbp.value, "total_bp": tbp.value, "bed": text}
+            return out
         finally:
             L.orc_partition_free(h)
 

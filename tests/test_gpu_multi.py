@@ -175,3 +175,19 @@ def test_cli_per_file_index_mode(tmp_path):
             f, l = int(c["q_first"][i]), int(c["q_last"][i])
             want += f"{names[int(c['q_id'][i])]}\t{min(f, l)}\t{max(f, l)}\t{a}:{b}-{e}\t.\t{'+' if f <= l else '-'}\n"
     assert got == want
+
+
+@pytest.mark.parametrize("kw", [dict(window_size=15000, merge_distance=500),
+                                dict(window_size=9000, merge_distance=0, transitive_dfs=True, max_depth=3),
+                                dict(window_size=20000, merge_distance=-1, selection_mode="total")])
+def test_partition_over_a_multi_impg(world, kw):
+    """`partition` with --index-mode per-file: the windows are answered by MultiImpg's transitive walk
+    (reference src/multi_impg.rs:687-755 behind src/commands/partition.rs:359-391)."""
+    cfg, recs, orc, gpu, bed = world
+    names = [gpu.idx.seq_name(i) for i in range(gpu.idx.n_seqs)]
+    want = orc.partition(O.make_partition_params(multi_impg=True, **kw), names)
+    got = gpu.idx.partition(ix.make_partition_params(multi_impg=True, **kw))
+    assert got.rows() == [(p, s, min(a, b), max(a, b)) for p, s, a, b in want["rows"]]
+    assert (got.n_partitions, got.partitioned_bp, got.n_windows) == (want["n_partitions"], want["partitioned_bp"],
+                                                                     len(want["windows"]))
+    assert got.partitioned_bp == got.total_bp
