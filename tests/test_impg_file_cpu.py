@@ -92,6 +92,19 @@ def test_every_varint_width_and_legacy_magic(tmp_path):
         assert f.n_entries == 5 and f.n_records == 3  # the self alignment has no reversed copy
 
 
+def test_crlf_paf_offsets_follow_the_reference_rule(tmp_path):
+    # BufRead::lines strips "\r\n" and the reference adds len + 1 per line (src/paf.rs:182-191), so on a CRLF
+    # file its recorded offsets drift by one byte per line; an index written here must carry the same numbers
+    crlf = tmp_path / "crlf.paf"
+    crlf.write_bytes(open(PAFS[0], "rb").read().replace(b"\n", b"\r\n"))
+    out = str(tmp_path / "c.impg")
+    ix.impg_write([str(crlf)], out)
+    names, lens, recs = F.parse_paf_like_reference([str(crlf)])
+    assert open(out, "rb").read() == F.encode(names, lens, F.entries_by_target(recs))
+    plain = F.parse_paf_like_reference([PAFS[0]])[2]
+    assert [r[8] for r in recs] == [r[8] for r in plain] and [r[9] for r in recs] == [r[9] for r in plain]
+
+
 def test_reader_rejects_damaged_files(tmp_path):
     out = str(tmp_path / "x.impg")
     ix.impg_write([PAFS[0]], out)
