@@ -797,6 +797,24 @@ def format_paf(idx, results, row, name, merge_distance):
     return _format_rows(lib().impgx_format_paf, idx, results, row, name, merge_distance)
 
 
+def subset_matches(list_text, name):
+    """SubsetFilter::matches for one sequence name (reference src/subset_filter.rs:23-42)."""
+    r = lib().impgx_subset_matches(list_text.encode(), name.encode())
+    if r < 0:
+        _check(r)
+    return bool(r)
+
+
+def subset_mask(impg, list_text):
+    """The per-sequence keep mask of --subset-sequence-list for make_params(subset_mask=...)."""
+    m = np.zeros(impg.n_seqs, np.uint8)
+    lib().impgx_subset_mask.restype = C.c_long
+    r = lib().impgx_subset_mask(impg.h, list_text.encode(), _p(m))
+    if r < 0:
+        _check(int(r))
+    return m
+
+
 def parse_bed_file(path):
     """parse_bed_file (reference src/commands/partition.rs:1719-1753) -> [(seq, (start, end), name)]."""
     L = lib()

@@ -3,6 +3,7 @@
 
 #include <cstring>
 #include <fstream>
+#include <set>
 #include <sstream>
 
 #include "engine.cuh"
@@ -748,6 +749,112 @@ long impgx_debug_host_columns_shard(const impgx_record *records, size_t n, const
   } catch (const std::exception &e) {
     impgx::set_last_error(e.what());
     return -1;
+  }
+}
+
+// ---- --subset-sequence-list (src/subset_filter.rs): which sequences a list file keeps
+namespace {
+struct SubsetList {
+  std::set<std::string> exact, normalized, sample_ids;
+  std::set<std::pair<std::string, std::string>> sample_haps;
+};
+std::string trim_ws(const std::string &t) {
+  size_t b = 0, e = t.size();
+  while (b < e && isspace((unsigned char)t[b])) b++;
+  while (e > b && isspace((unsigned char)t[e - 1])) e--;
+  return t.substr(b, e - b);
+}
+std::string leading_digits(const std::string &t) {
+  size_t k = 0;
+  while (k < t.size() && t[k] >= '0' && t[k] <= '9') k++;
+  return t.substr(0, k);
+}
+// extract_sample_and_hap (:147-178): "<sample>_hap<digits>…", PanSN "<sample>#<hap>#…", or a bare name
+bool sample_and_hap(const std::string &name, std::string &sample, std::string &hap, bool &has_hap) {
+  size_t k = name.find("_hap");
+  if (k != std::string::npos) {
+    sample = name.substr(0, k);
+    hap = leading_digits(name.substr(k + 4));
+    has_hap = !hap.empty();
+    return true;
+  }
+  k = name.find('#');
+  if (k != std::string::npos) {
+    sample = name.substr(0, k);
+    const std::string rest = name.substr(k + 1);
+    hap = leading_digits(rest.substr(0, rest.find('#')));
+    has_hap = !hap.empty();
+    return true;
+  }
+  if (name.find(':') == std::string::npos && !trim_ws(name).empty()) {
+    sample = name;
+    hap.clear();
+    has_hap = false;
+    return true;
+  }
+  return false;
+}
+SubsetList parse_subset_list(const std::string &text) {  // parse_subset_filter (:117-145)
+  SubsetList f;
+  size_t pos = 0;
+  while (pos < text.size()) {
+    size_t eol = text.find('\n', pos);
+    if (eol == std::string::npos) eol = text.size();
+    const std::string t = trim_ws(text.substr(pos, eol - pos));
+    pos = eol + 1;
+    if (t.empty() || t[0] == '#') continue;
+    f.exact.insert(t);
+    const std::string no_coords = t.substr(0, t.find(':'));
+    f.normalized.insert(no_coords);
+    std::string sample, hap;
+    bool has_hap = false;
+    if (sample_and_hap(no_coords, sample, hap, has_hap)) {
+      if (has_hap) f.sample_haps.insert({sample, hap});
+      else f.sample_ids.insert(sample);
+    }
+  }
+  return f;
+}
+bool sample_keys_match(const SubsetList &f, const std::string &name) {  // :44-58
+  std::string sample, hap;
+  bool has_hap = false;
+  if (!sample_and_hap(name, sample, hap, has_hap)) return false;
+  if (has_hap && f.sample_haps.count({sample, hap})) return true;
+  return f.sample_ids.count(sample) != 0;
+}
+bool subset_matches(const SubsetList &f, const std::string &name) {  // SubsetFilter::matches (:23-42)
+  if (f.exact.count(name)) return true;
+  const std::string no_coords = name.substr(0, name.find(':'));
+  if (name != no_coords && f.exact.count(no_coords)) return true;
+  if (f.normalized.count(no_coords)) return true;
+  if (sample_keys_match(f, no_coords)) return true;
+  return sample_keys_match(f, name);
+}
+}  // namespace
+
+long impgx_subset_mask(const impgx_index *idx, const char *list_text, uint8_t *mask_out) {
+  try {
+    REQUIRE(idx && list_text && mask_out, IMPGX_E_INVALID, "NULL argument");
+    const SubsetList f = parse_subset_list(list_text);
+    REQUIRE(!f.exact.empty(), IMPGX_E_PARSE, "Subset sequence list did not contain any sequence names");
+    for (uint32_t s = 0; s < idx->n_seqs; s++)
+      mask_out[s] = (s < idx->names.size() && subset_matches(f, idx->names[s])) ? 1 : 0;
+    return (long)f.exact.size();
+  } catch (const impgx::Error &e) {
+    impgx::set_last_error(e.what());
+    return e.code;
+  } catch (const std::exception &e) {
+    impgx::set_last_error(e.what());
+    return IMPGX_E_INVALID;
+  }
+}
+int impgx_subset_matches(const char *list_text, const char *seq_name) {
+  if (!list_text || !seq_name) return IMPGX_E_INVALID;
+  try {
+    return subset_matches(parse_subset_list(list_text), seq_name) ? 1 : 0;
+  } catch (const std::exception &e) {
+    impgx::set_last_error(e.what());
+    return IMPGX_E_INVALID;
   }
 }
 

@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <iterator>
 #include <string>
 #include <vector>
 
@@ -306,27 +307,15 @@ int main(int argc, char **argv) {
     impgx_bed_free(bed);
   }
 
-  // subset list: exact names, or names without the ":coords" suffix (src/subset_filter.rs:23-41;
-  // the PanSN sample / haplotype shorthands of the reference are not implemented)
+  // --subset-sequence-list: SubsetFilter's matching rules live in the library (src/subset_filter.rs)
   std::vector<uint8_t> mask;
   if (!subset_path.empty()) {
     std::ifstream f(subset_path);
     if (!f.good()) die("Failed to read subset sequence list '" + subset_path + "'");
+    std::string text((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
     mask.assign(impgx_index_num_seqs(idx), 0);
-    std::string line;
-    size_t entries = 0;
-    while (std::getline(f, line)) {
-      while (!line.empty() && isspace((unsigned char)line.back())) line.pop_back();
-      if (line.empty() || line[0] == '#') continue;
-      entries++;
-      for (uint32_t s = 0; s < mask.size(); s++) {
-        const char *nm = impgx_index_seq_name(idx, s);
-        if (!nm) continue;
-        std::string n(nm);
-        if (n == line || n.substr(0, n.find(':')) == line) mask[s] = 1;
-      }
-    }
-    if (!entries) die("Subset sequence list '" + subset_path + "' did not contain any sequence names");
+    if (impgx_subset_mask(idx, text.c_str(), mask.data()) <= 0)
+      die("Subset sequence list '" + subset_path + "' did not contain any sequence names");
   }
 
   impgx_params p;

@@ -296,6 +296,14 @@ void impgx_bed_free(impgx_bed *bed);
 int impgx_parse_target_range(const char *text, char *seq_out, size_t seq_cap,
                              int32_t *start, int32_t *end, char *name_out, size_t name_cap);
 
+/* --subset-sequence-list (src/subset_filter.rs:17-178): `list_text` = the contents of the list file (one
+ * name per line, '#' comments). A sequence is kept if the list holds its name, its name without ":coords",
+ * or its sample / sample+haplotype ("<sample>_hap<N>…" or PanSN "<sample>#<N>#…"). Fills mask_out[n_seqs]
+ * for impgx_params.subset_mask; returns the number of list entries (an empty list is IMPGX_E_PARSE, :72-77). */
+long impgx_subset_mask(const impgx_index *idx, const char *list_text, uint8_t *mask_out);
+/* SubsetFilter::matches on one name (1 / 0): the surface of the reference's own test (:185-206). */
+int impgx_subset_matches(const char *list_text, const char *seq_name);
+
 /* Host-side text helpers mirroring the reference's parsers and writers. */
 /* parse_cigar_to_delta (src/impg.rs:2935-2950). Returns run count or <0. */
 long impgx_parse_cigar(const char *text, size_t len, uint32_t *out, size_t cap);

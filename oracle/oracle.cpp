@@ -2442,6 +2442,100 @@ char *orc_partition_format_bed(void *h, void *o) {
   return dup_string(s);
 }
 void orc_partition_free(void *o) { delete (PartitionOut *)o; }
+}  // extern "C"
+
+// ================================================================ subset filter
+// src/subset_filter.rs — pinned by its own test (:185-206, replayed in tests/test_oracle_kat.py)
+namespace {
+struct SubsetFilter {
+  std::vector<std::string> exact, normalized, sample_ids;   // HashSets; linear search keeps this obviously literal
+  std::vector<std::pair<std::string, std::string>> sample_haps;
+  static bool has(const std::vector<std::string> &v, const std::string &x) { return std::find(v.begin(), v.end(), x) != v.end(); }
+};
+std::string rust_trim(const std::string &t) {
+  size_t b = 0, e = t.size();
+  while (b < e && isspace((unsigned char)t[b])) b++;
+  while (e > b && isspace((unsigned char)t[e - 1])) e--;
+  return t.substr(b, e - b);
+}
+std::string first_field(const std::string &t, char sep) { return t.substr(0, t.find(sep)); }  // split(sep).next()
+std::string take_digits(const std::string &t) {
+  std::string d;
+  for (char c : t) {
+    if (c < '0' || c > '9') break;
+    d += c;
+  }
+  return d;
+}
+// :147-178; returns false for None. hap empty = None.
+bool extract_sample_and_hap(const std::string &name, std::string &sample, std::string &hap) {
+  size_t idx = name.find("_hap");
+  if (idx != std::string::npos) {
+    sample = name.substr(0, idx);
+    hap = take_digits(name.substr(idx + 4));
+    return true;
+  }
+  size_t h = name.find('#');
+  if (h != std::string::npos) {  // split_once('#')
+    sample = name.substr(0, h);
+    hap = take_digits(first_field(name.substr(h + 1), '#'));
+    return true;
+  }
+  if (name.find(':') == std::string::npos && !rust_trim(name).empty()) {
+    sample = name;
+    hap.clear();
+    return true;
+  }
+  return false;
+}
+SubsetFilter parse_subset_filter(const std::string &contents) {  // :117-145
+  SubsetFilter f;
+  size_t pos = 0;
+  while (pos <= contents.size()) {
+    size_t eol = contents.find('\n', pos);
+    std::string line = contents.substr(pos, eol == std::string::npos ? std::string::npos : eol - pos);
+    pos = eol == std::string::npos ? contents.size() + 1 : eol + 1;
+    std::string trimmed = rust_trim(line);
+    if (trimmed.empty() || trimmed[0] == '#') continue;
+    if (!SubsetFilter::has(f.exact, trimmed)) f.exact.push_back(trimmed);
+    std::string no_coords = first_field(trimmed, ':');
+    f.normalized.push_back(no_coords);
+    std::string sample, hap;
+    if (extract_sample_and_hap(no_coords, sample, hap)) {
+      if (!hap.empty()) f.sample_haps.push_back({sample, hap});
+      else f.sample_ids.push_back(sample);
+    }
+  }
+  return f;
+}
+bool matches_sample_keys(const SubsetFilter &f, const std::string &seq_name) {  // :44-58
+  std::string sample, hap;
+  if (extract_sample_and_hap(seq_name, sample, hap)) {
+    if (!hap.empty() && std::find(f.sample_haps.begin(), f.sample_haps.end(), std::make_pair(sample, hap)) != f.sample_haps.end())
+      return true;
+    if (SubsetFilter::has(f.sample_ids, sample)) return true;
+  }
+  return false;
+}
+bool subset_filter_matches(const SubsetFilter &f, const std::string &seq_name) {  // :23-42
+  if (SubsetFilter::has(f.exact, seq_name)) return true;
+  std::string no_coords = first_field(seq_name, ':');
+  if (seq_name != no_coords && SubsetFilter::has(f.exact, no_coords)) return true;
+  if (SubsetFilter::has(f.normalized, no_coords)) return true;
+  if (matches_sample_keys(f, no_coords)) return true;
+  return matches_sample_keys(f, seq_name);
+}
+}  // namespace
+
+extern "C" {
+
+// returns 1 / 0; *entry_count = exact.len() (:18-20)
+int orc_subset_matches(const char *contents, const char *seq_name, size_t *entry_count) {
+  SubsetFilter f = parse_subset_filter(contents);
+  if (entry_count) *entry_count = f.exact.size();
+  return subset_filter_matches(f, seq_name) ? 1 : 0;
+}
+
 int orc_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -234,6 +234,13 @@ def identity(ops):
     return lib().orc_identity(_p(ops), C.c_size_t(len(ops)))
 
 
+def subset_matches(list_text, name):
+    """SubsetFilter::matches after parse_subset_filter (reference src/subset_filter.rs). -> (bool, entry_count)"""
+    n = C.c_size_t(0)
+    r = lib().orc_subset_matches(list_text.encode(), name.encode(), C.byref(n))
+    return bool(r), n.value
+
+
 def sorted_ranges_insert(ranges, seq_len, min_dist, new):
     cap = len(ranges) + 2
     buf = np.zeros(2 * cap, dtype=np.int32)

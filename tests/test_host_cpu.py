@@ -273,3 +273,30 @@ def test_bench_contig_subworld_is_exact():
     b, bo = sub.query_batch(rows[:25], p)
     ac, bc = a.columns(), b.columns()
     assert ao.tolist() == bo.tolist() and all((ac[k] == bc[k]).all() for k in ac)
+
+
+def test_subset_filter_kat_and_fuzz_against_oracle():
+    """--subset-sequence-list matching (reference src/subset_filter.rs): the reference's own test on the
+    product, then random lists / names against the oracle's restatement."""
+    contents = "# comment\nchr1\nchr2\n\nchr1\t\n  chr3  \nHG00097_hap1_hprc_r2_v1.0.1\nHG00098#2#chr5\n"
+    for name in ["chr1", "chr1:10-20", "chr3", "HG00097#1#chr7", "HG00097#1", "HG00098#2#chr5"]:
+        assert ix.subset_matches(contents, name), name
+    assert not ix.subset_matches(contents, "HG00098#1#chr5")
+    import random
+    rnd = random.Random(3)
+    atoms = ["HG1", "HG2", "NA3", "chr1", "chr2", "c", ""]
+
+    def name():
+        k = rnd.randrange(8)
+        a, b = rnd.choice(atoms), rnd.choice(atoms)
+        h = rnd.choice(["1", "2", "", "x", "12"])
+        base = [a, f"{a}#{h}#{b}", f"{a}#{h}", f"{a}_hap{h}_{b}", f"{a}_hap{h}", f"{a}#{b}", f" {a} ", f"#{a}"][k]
+        return base + (f":{rnd.randrange(100)}-{rnd.randrange(100, 200)}" if rnd.random() < 0.3 else "")
+
+    for _ in range(300):
+        text = "".join(name() + rnd.choice(["\n", "\r\n", "\t\n"]) for _ in range(rnd.randrange(1, 6)))
+        if rnd.random() < 0.5:
+            text = text.rstrip("\n")
+        for _ in range(10):
+            q = name().strip() or "q"
+            assert ix.subset_matches(text, q) == O.subset_matches(text, q)[0], (text, q)

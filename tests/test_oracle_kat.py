@@ -6,6 +6,7 @@ import os
 import numpy as np
 import pytest
 
+import _oracle as O
 from _oracle import cigar, cigar_str
 
 F, R = False, True
@@ -130,3 +131,15 @@ def test_sorted_ranges_insert(oracle):
     # end beyond the sequence is clamped
     r, p = oracle.sorted_ranges_insert([], 250, 0, (200, 400))
     assert r == [(200, 250)] and p == [(200, 250)]
+
+
+def test_subset_filter_matches_variants():
+    # reference src/subset_filter.rs:185-206, verbatim
+    contents = "# comment\nchr1\nchr2\n\nchr1\t\n  chr3  \nHG00097_hap1_hprc_r2_v1.0.1\nHG00098#2#chr5\n"
+    yes = ["chr1", "chr1:10-20", "chr3", "HG00097#1#chr7", "HG00097#1", "HG00098#2#chr5"]
+    no = ["HG00098#1#chr5"]
+    for name in yes:
+        assert O.subset_matches(contents, name)[0], name
+    for name in no:
+        assert not O.subset_matches(contents, name)[0], name
+    assert O.subset_matches(contents, "chr1")[1] == 5  # entry_count = distinct trimmed lines
