@@ -80,3 +80,29 @@ def test_cli_index_then_query_with_index(tmp_path):
                         capture_output=True, text=True)
     assert p1.returncode == 0 and p2.returncode == 0, (p1.stderr, p2.stderr)
     assert (tmp_path / "p1" / "partitions.bed").read_text() == (tmp_path / "p2" / "partitions.bed").read_text()
+
+
+def test_cli_subset_sequence_list_uses_the_reference_matching_rules(tmp_path):
+    """--subset-sequence-list through impgx_subset_mask: exact names with coordinates select single sequences,
+    the sample+haplotype key `C4FIXTURE#0` (reference src/subset_filter.rs:147-178) selects all of them."""
+    import subprocess
+    cli = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "impg_b200", "impgx-query")
+    paf = os.path.join(GOLD, "short_floor.paf")
+    args = [cli, "-a", paf, "-r", "C4FIXTURE#0#short_floor:0-250:0-250", "-d", "0", "-o", "bed"]
+    full = subprocess.run(args, capture_output=True, text=True)
+    assert full.returncode == 0, full.stderr
+    lst = tmp_path / "subset.txt"
+    lst.write_text("# two sequences by exact name\nC4FIXTURE#0#short_floor:2-252\n  C4FIXTURE#0#short_floor:60-360\t\n")
+    two = subprocess.run(args + ["--subset-sequence-list", str(lst)], capture_output=True, text=True)
+    assert two.returncode == 0, two.stderr
+    seqs = {l.split("\t")[0] for l in two.stdout.splitlines()}
+    assert seqs == {"C4FIXTURE#0#short_floor:0-250", "C4FIXTURE#0#short_floor:2-252", "C4FIXTURE#0#short_floor:60-360"}
+    lst.write_text("C4FIXTURE#0\n")  # sample + haplotype: every sequence of the fixture
+    allseq = subprocess.run(args + ["--subset-sequence-list", str(lst)], capture_output=True, text=True)
+    assert allseq.returncode == 0 and allseq.stdout == full.stdout
+    lst.write_text("OTHER#1\n")
+    none = subprocess.run(args + ["--subset-sequence-list", str(lst)], capture_output=True, text=True)
+    assert none.returncode == 0 and {l.split("\t")[0] for l in none.stdout.splitlines()} == {"C4FIXTURE#0#short_floor:0-250"}
+    lst.write_text("# nothing\n\n")
+    bad = subprocess.run(args + ["--subset-sequence-list", str(lst)], capture_output=True, text=True)
+    assert bad.returncode != 0 and "did not contain any sequence names" in bad.stderr
