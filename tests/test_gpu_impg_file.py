@@ -92,11 +92,14 @@ def test_cli_subset_sequence_list_uses_the_reference_matching_rules(tmp_path):
     full = subprocess.run(args, capture_output=True, text=True)
     assert full.returncode == 0, full.stderr
     lst = tmp_path / "subset.txt"
-    lst.write_text("# two sequences by exact name\nC4FIXTURE#0#short_floor:2-252\n  C4FIXTURE#0#short_floor:60-360\t\n")
-    two = subprocess.run(args + ["--subset-sequence-list", str(lst)], capture_output=True, text=True)
-    assert two.returncode == 0, two.stderr
-    seqs = {l.split("\t")[0] for l in two.stdout.splitlines()}
-    assert seqs == {"C4FIXTURE#0#short_floor:0-250", "C4FIXTURE#0#short_floor:2-252", "C4FIXTURE#0#short_floor:60-360"}
+    # an exact name also registers its sample + haplotype key (parse_subset_filter, :117-145), and every sequence
+    # of this fixture is C4FIXTURE haplotype 0 — so one listed sequence keeps them all, as in the reference
+    lst.write_text("# one sequence by exact name\n  C4FIXTURE#0#short_floor:60-360\t\n")
+    one = subprocess.run(args + ["--subset-sequence-list", str(lst)], capture_output=True, text=True)
+    assert one.returncode == 0 and one.stdout == full.stdout, one.stderr
+    lst.write_text("C4FIXTURE#1\n")  # the other haplotype: nothing but the query sequence itself is kept
+    hap1 = subprocess.run(args + ["--subset-sequence-list", str(lst)], capture_output=True, text=True)
+    assert hap1.returncode == 0 and {l.split("\t")[0] for l in hap1.stdout.splitlines()} == {"C4FIXTURE#0#short_floor:0-250"}
     lst.write_text("C4FIXTURE#0\n")  # sample + haplotype: every sequence of the fixture
     allseq = subprocess.run(args + ["--subset-sequence-list", str(lst)], capture_output=True, text=True)
     assert allseq.returncode == 0 and allseq.stdout == full.stdout
