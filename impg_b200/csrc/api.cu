@@ -1,6 +1,7 @@
 // api.cu — the extern "C" boundary (include/impgx.h). No exception crosses it.
 #include <zlib.h>
 
+#include <cmath>
 #include <cstring>
 #include <fstream>
 #include <set>
@@ -750,6 +751,44 @@ long impgx_debug_host_columns_shard(const impgx_record *records, size_t n, const
     impgx::set_last_error(e.what());
     return -1;
   }
+}
+
+// parse_merge_distance (src/main.rs:47-55 over sweepga::parse_metric_number, un-vendored): a non-negative
+// decimal number with an optional k / m / g suffix (either case), at most i32::MAX after scaling; pinned by the
+// reference's tests (src/main.rs:13702-13715: 50000, 50k, 1m, 1M, 1.5k accepted; 10kb, 3g rejected)
+int impgx_parse_merge_distance(const char *text, int32_t *out) {
+  if (!text || !out) return IMPGX_E_INVALID;
+  std::string t(text);
+  while (!t.empty() && isspace((unsigned char)t.back())) t.pop_back();
+  size_t b = 0;
+  while (b < t.size() && isspace((unsigned char)t[b])) b++;
+  t = t.substr(b);
+  double mul = 1;
+  if (!t.empty()) {
+    const char c = (char)tolower((unsigned char)t.back());
+    if (c == 'k' || c == 'm' || c == 'g') {
+      mul = c == 'k' ? 1e3 : (c == 'm' ? 1e6 : 1e9);
+      t.pop_back();
+    }
+  }
+  bool digits = false, ok = !t.empty();
+  int dots = 0;
+  for (char c : t) {
+    if (c >= '0' && c <= '9') digits = true;
+    else if (c == '.') dots++;
+    else ok = false;
+  }
+  if (!ok || !digits || dots > 1) {
+    impgx::set_last_error(std::string("invalid merge distance '") + text + "'");
+    return IMPGX_E_PARSE;
+  }
+  const double v = strtod(t.c_str(), nullptr) * mul;
+  if (v > 2147483647.0) {
+    impgx::set_last_error(std::string("merge distance ") + text + " exceeds maximum supported value 2147483647");
+    return IMPGX_E_PARSE;
+  }
+  *out = (int32_t)llround(v);
+  return IMPGX_OK;
 }
 
 // ---- --subset-sequence-list (src/subset_filter.rs): which sequences a list file keeps

@@ -29,20 +29,11 @@ static void check(int code) {
   if (code != 0) die(impgx_last_error());
 }
 
-// parse_merge_distance: integer with optional k/m/g suffix (src/main.rs: parse_merge_distance)
+// parse_merge_distance (src/main.rs:47-55) lives in the library
 static int32_t parse_distance(const std::string &s) {
-  if (s.empty()) die("empty merge distance");
-  double mul = 1;
-  std::string num = s;
-  char c = (char)tolower((unsigned char)s.back());
-  if (c == 'k' || c == 'm' || c == 'g') {
-    mul = c == 'k' ? 1e3 : (c == 'm' ? 1e6 : 1e9);
-    num = s.substr(0, s.size() - 1);
-  }
-  char *end = nullptr;
-  double v = strtod(num.c_str(), &end);
-  if (!end || *end || v < 0 || v * mul > 2147483647.0) die("invalid merge distance '" + s + "'");
-  return (int32_t)llround(v * mul);
+  int32_t v = 0;
+  if (impgx_parse_merge_distance(s.c_str(), &v) != 0) die(impgx_last_error());
+  return v;
 }
 
 // impgx-query partition — `impg partition -o bed` (src/main.rs:4765-4880, :6286-6420;

@@ -304,6 +304,9 @@ long impgx_subset_mask(const impgx_index *idx, const char *list_text, uint8_t *m
 /* SubsetFilter::matches on one name (1 / 0): the surface of the reference's own test (:185-206). */
 int impgx_subset_matches(const char *list_text, const char *seq_name);
 
+/* parse_merge_distance (src/main.rs:47-55): "50000", "50k", "1.5k", "1m", "1M"; rejects "10kb", "3g" (> i32). */
+int impgx_parse_merge_distance(const char *text, int32_t *out);
+
 /* Host-side text helpers mirroring the reference's parsers and writers. */
 /* parse_cigar_to_delta (src/impg.rs:2935-2950). Returns run count or <0. */
 long impgx_parse_cigar(const char *text, size_t len, uint32_t *out, size_t cap);

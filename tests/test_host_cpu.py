@@ -300,3 +300,19 @@ def test_subset_filter_kat_and_fuzz_against_oracle():
         for _ in range(10):
             q = name().strip() or "q"
             assert ix.subset_matches(text, q) == O.subset_matches(text, q)[0], (text, q)
+
+
+def test_parse_merge_distance_reference_kats():
+    # reference src/main.rs:13702-13715
+    import ctypes as C
+
+    def parse(t):
+        v = C.c_int32(0)
+        code = ix.lib().impgx_parse_merge_distance(t.encode(), C.byref(v))
+        return v.value if code == 0 else None
+
+    assert parse("50000") == 50_000 and parse("50k") == 50_000 and parse("1m") == 1_000_000
+    assert parse("1M") == 1_000_000 and parse("1.5k") == 1_500 and parse(" 7 ") == 7 and parse("0") == 0
+    assert parse("2147483647") == 2147483647 and parse("2g") == 2_000_000_000
+    for bad in ("10kb", "3g", "", "k", "-5", "1..5k", "abc", "2147483648"):
+        assert parse(bad) is None, bad
