@@ -318,6 +318,10 @@ class Impg:
                                            C.byref(h)))
         return cls(h.value)
 
+    def set_original_coordinates(self, on=True):
+        """--original-sequence-coordinates for the BED / BEDPE writers (reference src/main.rs:4661-4678)."""
+        _check(lib().impgx_index_set_original_coordinates(self.h, C.c_int(1 if on else 0)))
+
     def set_names(self, names):
         arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
         _check(lib().impgx_index_set_names(self.h, arr, C.c_uint32(len(names))))
@@ -795,6 +799,16 @@ def format_bedpe(idx, results, row, name, merge_distance):
 def format_paf(idx, results, row, name, merge_distance):
     """output_results_paf (reference src/main.rs:11989) on a raw result set with CIGARs."""
     return _format_rows(lib().impgx_format_paf, idx, results, row, name, merge_distance)
+
+
+def parse_subsequence_coordinates(name):
+    """parse_subsequence_coordinates (reference src/main.rs:4642-4659): (base, start) or None."""
+    buf = C.create_string_buffer(len(name.encode()) + 1)
+    st = C.c_int32(0)
+    r = lib().impgx_parse_subsequence_coordinates(name.encode(), buf, C.c_size_t(len(buf)), C.byref(st))
+    if r < 0:
+        _check(r)
+    return (buf.value.decode(), st.value) if r == 1 else None
 
 
 def subset_matches(list_text, name):

@@ -476,12 +476,19 @@ char *impgx_format_bed(const impgx_index *idx, const impgx_results *res, size_t 
       strand = '-';
     }
     uint32_t id = res->qid[i];
-    if (id < idx->names.size() && !idx->names[id].empty()) s += idx->names[id];
-    else s += "seq" + std::to_string(id);
+    std::string qn = (id < idx->names.size() && !idx->names[id].empty()) ? idx->names[id] : "seq" + std::to_string(id);
+    uint32_t uf = (uint32_t)f, ul = (uint32_t)l, off = 0;
+    std::string base;
+    if (idx->original_coordinates && impgx::to_original_coordinates(qn, base, off)) {
+      qn = base;
+      uf += off;
+      ul += off;
+    }
+    s += qn;
     s += '\t';
-    s += std::to_string((uint32_t)f);
+    s += std::to_string(uf);
     s += '\t';
-    s += std::to_string((uint32_t)l);
+    s += std::to_string(ul);
     s += '\t';
     s += name;
     s += "\t.\t";
@@ -520,11 +527,19 @@ char *impgx_format_bed_batch(const impgx_index *idx, const impgx_results *res, c
   const size_t R = res->n_rows;
   std::vector<std::string> fallback(idx->n_seqs);
   std::vector<const std::string *> seq(idx->n_seqs);
+  std::vector<uint32_t> shift(idx->n_seqs, 0);  // --original-sequence-coordinates: subsequence start per sequence
   for (uint32_t q = 0; q < idx->n_seqs; q++) {
     if (q < idx->names.size() && !idx->names[q].empty()) seq[q] = &idx->names[q];
     else {
       fallback[q] = "seq" + std::to_string(q);
       seq[q] = &fallback[q];
+    }
+    std::string base;
+    uint32_t off = 0;
+    if (idx->original_coordinates && impgx::to_original_coordinates(*seq[q], base, off)) {
+      fallback[q] = base;
+      seq[q] = &fallback[q];
+      shift[q] = off;
     }
   }
   std::vector<size_t> name_len(R), off(R + 1, 0);
@@ -534,7 +549,8 @@ char *impgx_format_bed_batch(const impgx_index *idx, const impgx_results *res, c
     size_t b = 0;
     for (uint64_t i = res->row_off[r]; i < res->row_off[r + 1]; i++) {
       const int32_t f = res->qf[i], l = res->ql[i];
-      b += seq[res->qid[i]]->size() + dec_len((uint32_t)std::min(f, l)) + dec_len((uint32_t)std::max(f, l)) + name_len[r] + 8;
+      const uint32_t sh = shift[res->qid[i]];
+      b += seq[res->qid[i]]->size() + dec_len((uint32_t)std::min(f, l) + sh) + dec_len((uint32_t)std::max(f, l) + sh) + name_len[r] + 8;
     }
     off[r + 1] = b;
   }
@@ -550,9 +566,10 @@ char *impgx_format_bed_batch(const impgx_index *idx, const impgx_results *res, c
       memcpy(p, nm.data(), nm.size());
       p += nm.size();
       *p++ = '\t';
-      p = put_dec(p, (uint32_t)std::min(f, l));
+      const uint32_t sh = shift[res->qid[i]];
+      p = put_dec(p, (uint32_t)std::min(f, l) + sh);
       *p++ = '\t';
-      p = put_dec(p, (uint32_t)std::max(f, l));
+      p = put_dec(p, (uint32_t)std::max(f, l) + sh);
       *p++ = '\t';
       memcpy(p, names[r], name_len[r]);
       p += name_len[r];
@@ -572,6 +589,10 @@ static char *format_with(const impgx_index *idx, const impgx_results *res, size_
                          int fmt) {
   if (!idx || !res || res->on_device || row >= res->n_rows || !name) return nullptr;
   try {
+    // PAF in original coordinates needs the lengths of the original sequences from the FASTA / AGC index
+    // (get_original_sequence_length, src/main.rs:4680-4705): sequence access is outside the path
+    REQUIRE(!(fmt == 2 && idx->original_coordinates), IMPGX_E_UNSUPPORTED,
+            "--original-sequence-coordinates with PAF output needs the sequence files (outside the accelerated path)");
     std::string s = impgx::format_rows(idx, res, row, name, d, fmt);
     char *p = (char *)malloc(s.size() + 1);
     if (p) memcpy(p, s.c_str(), s.size() + 1);
@@ -751,6 +772,25 @@ long impgx_debug_host_columns_shard(const impgx_record *records, size_t n, const
     impgx::set_last_error(e.what());
     return -1;
   }
+}
+
+int impgx_index_set_original_coordinates(impgx_index *idx, int on) {
+  if (!idx) return IMPGX_E_INVALID;
+  idx->original_coordinates = on != 0;
+  return IMPGX_OK;
+}
+int impgx_parse_subsequence_coordinates(const char *seq_name, char *base_out, size_t base_cap, int32_t *start_out) {
+  if (!seq_name) return IMPGX_E_INVALID;
+  std::string base;
+  uint32_t off = 0;
+  if (!impgx::to_original_coordinates(seq_name, base, off)) return 0;
+  if (base_out && base_cap) {
+    const size_t n = std::min(base.size(), base_cap - 1);
+    memcpy(base_out, base.data(), n);
+    base_out[n] = 0;
+  }
+  if (start_out) *start_out = (int32_t)off;
+  return 1;
 }
 
 // parse_merge_distance (src/main.rs:47-55 over sweepga::parse_metric_number, un-vendored): a non-negative

@@ -47,6 +47,10 @@ struct PafData {
 void parse_paf(const std::string &path, PafData &out);
 long parse_cigar(const char *s, size_t n, std::vector<uint32_t> &out);
 
+// transform_coordinates_to_original (src/main.rs:4642-4678): "base:start-end" names are reported as `base` with
+// the subsequence start added to both coordinates. Returns false (nothing changed) for any other name.
+bool to_original_coordinates(const std::string &seq_name, std::string &base, uint32_t &offset);
+
 void debug_sort_pairs(int device, uint64_t *keys, uint32_t *vals, uint64_t n, int begin_bit, int end_bit, int key_bytes);
 void debug_exclusive_scan(int device, uint64_t *a, uint64_t n_plus_1);
 

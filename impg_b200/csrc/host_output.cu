@@ -332,6 +332,30 @@ std::vector<Row> rows_of(const impgx_results *res, size_t row) {
 }  // namespace
 
 // format: 1 = bedpe (src/main.rs:11894-11987), 2 = paf (src/main.rs:11989-12103)
+// parse_subsequence_coordinates (src/main.rs:4642-4659): split at the LAST ':', the range part must hold a '-'
+// and an i32 before it; pinned by the reference's test (src/main.rs:13330-13346)
+bool to_original_coordinates(const std::string &seq_name, std::string &base, uint32_t &offset) {
+  const size_t colon = seq_name.rfind(':');
+  if (colon == std::string::npos) return false;
+  const std::string range = seq_name.substr(colon + 1);
+  const size_t dash = range.find('-');
+  if (dash == std::string::npos) return false;
+  const std::string st = range.substr(0, dash);  // str::parse::<i32>: optional sign, digits only, in range
+  size_t k = (!st.empty() && (st[0] == '+' || st[0] == '-')) ? 1 : 0;
+  if (k >= st.size()) return false;
+  int64_t v = 0;
+  for (size_t i = k; i < st.size(); i++) {
+    if (st[i] < '0' || st[i] > '9') return false;
+    v = v * 10 + (st[i] - '0');
+    if (v > 2147483648ll) return false;
+  }
+  if (st[0] == '-') v = -v;
+  if (v > 2147483647ll || v < -2147483648ll) return false;
+  base = seq_name.substr(0, colon);
+  offset = (uint32_t)(int32_t)v;  // `offset as u32`
+  return true;
+}
+
 std::string format_rows(const impgx_index *idx, const impgx_results *res, size_t row, const char *name, int32_t d,
                         int format) {
   std::vector<Row> rows = rows_of(res, row);
@@ -356,10 +380,21 @@ std::string format_rows(const impgx_index *idx, const impgx_results *res, size_t
     float gi = (float)k.m / (float)(k.m + k.x + k.ni + k.nd);
     float bi = (float)k.m / (float)(k.m + (k.x + k.ibp + k.dbp));
     if (format == 1) {
-      out += name_of(idx, r.q_id) + "\t" + std::to_string((uint32_t)f) + "\t" + std::to_string((uint32_t)l) + "\t" +
-             name_of(idx, r.t_id) + "\t" + std::to_string((uint32_t)r.t_first) + "\t" +
-             std::to_string((uint32_t)r.t_last) + "\t" + name + "\t0\t" + strand + "\t+\tgi:f:" + f32_trim(gi) +
-             "\tbi:f:" + f32_trim(bi) + "\n";
+      // --original-sequence-coordinates (src/main.rs:11920-11934): both sides, each by its own subsequence start
+      std::string qn = name_of(idx, r.q_id), tn = name_of(idx, r.t_id), base;
+      uint32_t qf = (uint32_t)f, ql = (uint32_t)l, tf = (uint32_t)r.t_first, tl = (uint32_t)r.t_last, off = 0;
+      if (idx->original_coordinates && to_original_coordinates(qn, base, off)) {
+        qn = base;
+        qf += off;
+        ql += off;
+      }
+      if (idx->original_coordinates && to_original_coordinates(tn, base, off)) {
+        tn = base;
+        tf += off;
+        tl += off;
+      }
+      out += qn + "\t" + std::to_string(qf) + "\t" + std::to_string(ql) + "\t" + tn + "\t" + std::to_string(tf) + "\t" +
+             std::to_string(tl) + "\t" + name + "\t0\t" + strand + "\t+\tgi:f:" + f32_trim(gi) + "\tbi:f:" + f32_trim(bi) + "\n";
     } else {
       std::string cg;
       for (uint32_t v : r.cg) {

@@ -193,6 +193,7 @@ int main(int argc, char **argv) {
   std::vector<std::string> pafs;
   std::string bed_path, range_text, out_format = "auto", subset_path, index_mode = "auto", index_path;
   bool transitive = false, dfs = false, unidirectional = false, consider_strand = false, no_merge = false, have_d = false;
+  bool original_coords = false;
   int32_t d = 0, min_transitive_len = 101, min_dist = 10, min_out = -1;
   uint32_t max_depth = 2;
   double min_identity = NAN;
@@ -230,6 +231,7 @@ int main(int argc, char **argv) {
     else if (a == "--min-distance-between-ranges") min_dist = atoi(val().c_str());
     else if (a == "--unidirectional") unidirectional = true;
     else if (a == "--consider-strandness") consider_strand = true;
+    else if (a == "--original-sequence-coordinates") original_coords = true;
     else if (a == "--min-result-identity") min_identity = atof(val().c_str());
     else if (a == "--subset-sequence-list") subset_path = val();
     else if (a == "--device") device = atoi(val().c_str());
@@ -238,6 +240,7 @@ int main(int argc, char **argv) {
              "       (-b BED | -r seq:start-end) [-x] [-m N] (-d D | --no-merge) [-l L]\n"
              "       [-o auto|bed|bedpe|paf] [--min-transitive-len N] [--min-distance-between-ranges N]\n"
              "       [--transitive-dfs] [--unidirectional] [--consider-strandness] [--min-result-identity F]\n"
+             "       [--original-sequence-coordinates]\n"
              "       [--subset-sequence-list FILE] [--device N]\n");
       return 0;
     } else die("unsupported option '" + a + "' (only the PAF -> BED/BEDPE/PAF query path is implemented)");
@@ -265,6 +268,11 @@ int main(int argc, char **argv) {
     // -i: an index file written by `impg index` (or `impgx-query index`) over the same alignment files
     if (!index_path.empty()) check(impgx_index_from_impg(index_path.c_str(), pp.data(), pp.size(), device, &idx));
     else check(impgx_index_from_pafs(pp.data(), pp.size(), unidirectional ? 0 : 1, device, &idx));
+  }
+
+  if (original_coords) {
+    if (out_format == "paf") die("--original-sequence-coordinates with PAF output needs the sequence files (outside the accelerated path)");
+    check(impgx_index_set_original_coordinates(idx, 1));
   }
 
   // rows

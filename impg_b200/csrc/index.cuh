@@ -62,6 +62,7 @@ struct impgx_index {
   impgx::Arena arena;  // device scratch of the query pipeline
   impgx_stats last{};
   double hits_per_row = 0;  // observed liftovers per row (sizes the row batches)
+  bool original_coordinates = false;  // writers: --original-sequence-coordinates (src/main.rs:4661-4678)
   // target-sharded index: this object holds the entries of the
   // sequences with owner[seq] == shard_rank; empty owner = the whole index
   std::vector<uint32_t> owner;

@@ -304,6 +304,12 @@ long impgx_subset_mask(const impgx_index *idx, const char *list_text, uint8_t *m
 /* SubsetFilter::matches on one name (1 / 0): the surface of the reference's own test (:185-206). */
 int impgx_subset_matches(const char *list_text, const char *seq_name);
 
+/* --original-sequence-coordinates (transform_coordinates_to_original, src/main.rs:4642-4678): when on, the BED and
+ * BEDPE writers report a sequence named "base:start-end" as `base` with `start` added to its coordinates; the
+ * PAF writer then fails (it needs the original sequences' lengths from the sequence files). Default off. */
+int impgx_index_set_original_coordinates(impgx_index *idx, int on);
+/* parse_subsequence_coordinates (src/main.rs:4642-4659): 1 and (base name, start) for "base:start-end", else 0. */
+int impgx_parse_subsequence_coordinates(const char *seq_name, char *base_out, size_t base_cap, int32_t *start_out);
 /* parse_merge_distance (src/main.rs:47-55): "50000", "50k", "1.5k", "1m", "1M"; rejects "10kb", "3g" (> i32). */
 int impgx_parse_merge_distance(const char *text, int32_t *out);
 

@@ -450,6 +450,7 @@ struct Index {
   std::vector<uint64_t> run_offsets;
   // faithful source (per-hit pread + parse, src/impg.rs:495-552,:2903-2950)
   bool faithful = false;
+  bool original_coordinates = false;  // --original-sequence-coordinates of the writers (src/main.rs:4661-4678)
   std::string paf_path;
   int fd = -1;
   size_t n_records = 0;
@@ -1304,6 +1305,42 @@ std::string seq_name(const Index &idx, uint32_t id) {
   return "seq" + std::to_string(id);
 }
 
+// src/main.rs:4642-4659; pinned by src/main.rs:13330-13346
+bool parse_subsequence_coordinates(const std::string &seq_name, std::string &base_name, int32_t &start_offset) {
+  size_t colon_pos = seq_name.rfind(':');
+  if (colon_pos == std::string::npos) return false;
+  std::string range_part = seq_name.substr(colon_pos + 1);
+  size_t dash_pos = range_part.find('-');
+  if (dash_pos == std::string::npos) return false;
+  std::string start_str = range_part.substr(0, dash_pos);
+  // str::parse::<i32>(): optional sign, at least one digit, nothing else, no overflow
+  if (start_str.empty()) return false;
+  size_t k = (start_str[0] == '+' || start_str[0] == '-') ? 1 : 0;
+  if (k == start_str.size()) return false;
+  long long v = 0;
+  for (size_t i = k; i < start_str.size(); i++) {
+    if (!isdigit((unsigned char)start_str[i])) return false;
+    v = v * 10 + (start_str[i] - '0');
+    if (v > 4294967296ll) return false;
+  }
+  if (start_str[0] == '-') v = -v;
+  if (v < INT32_MIN || v > INT32_MAX) return false;
+  base_name = seq_name.substr(0, colon_pos);
+  start_offset = (int32_t)v;
+  return true;
+}
+// src/main.rs:4661-4678
+void transform_coordinates_to_original(std::string &seq_name, uint32_t &start, uint32_t &end, bool original_coordinates) {
+  if (!original_coordinates) return;
+  std::string base;
+  int32_t off = 0;
+  if (parse_subsequence_coordinates(seq_name, base, off)) {
+    seq_name = base;
+    start += (uint32_t)off;
+    end += (uint32_t)off;
+  }
+}
+
 // src/main.rs:11849-11892
 std::string output_results_bed(const Index &idx, std::vector<Result> &results, const std::string &name,
                                int32_t d, bool merge_strands) {
@@ -1320,8 +1357,10 @@ std::string output_results_bed(const Index &idx, std::vector<Result> &results, c
     } else {
       first = r.q_last; last = r.q_first; strand = '-';
     }
-    out += seq_name(idx, r.q_id) + "\t" + std::to_string((uint32_t)first) + "\t" +
-           std::to_string((uint32_t)last) + "\t" + name + "\t.\t" + strand + "\n";
+    std::string qn = seq_name(idx, r.q_id);
+    uint32_t tf = (uint32_t)first, tl = (uint32_t)last;
+    transform_coordinates_to_original(qn, tf, tl, idx.original_coordinates);
+    out += qn + "\t" + std::to_string(tf) + "\t" + std::to_string(tl) + "\t" + name + "\t.\t" + strand + "\n";
   }
   return out;
 }
@@ -1363,9 +1402,12 @@ std::string output_results_bedpe(const Index &idx, std::vector<Result> &results,
     float gi = (float)s.matches / (float)(s.matches + s.mismatches + s.insertions + s.deletions);
     int32_t edit = s.mismatches + s.inserted_bp + s.deleted_bp;
     float bi = (float)s.matches / (float)(s.matches + edit);
-    out += seq_name(idx, r.q_id) + "\t" + std::to_string((uint32_t)first) + "\t" + std::to_string((uint32_t)last) +
-           "\t" + seq_name(idx, r.t_id) + "\t" + std::to_string((uint32_t)r.t_first) + "\t" +
-           std::to_string((uint32_t)r.t_last) + "\t" + name + "\t0\t" + strand + "\t+\tgi:f:" + fmt_f32_trim(gi) +
+    std::string qn = seq_name(idx, r.q_id), tn = seq_name(idx, r.t_id);
+    uint32_t qf = (uint32_t)first, ql = (uint32_t)last, tf = (uint32_t)r.t_first, tl = (uint32_t)r.t_last;
+    transform_coordinates_to_original(qn, qf, ql, idx.original_coordinates);
+    transform_coordinates_to_original(tn, tf, tl, idx.original_coordinates);
+    out += qn + "\t" + std::to_string(qf) + "\t" + std::to_string(ql) + "\t" + tn + "\t" + std::to_string(tf) + "\t" +
+           std::to_string(tl) + "\t" + name + "\t0\t" + strand + "\t+\tgi:f:" + fmt_f32_trim(gi) +
            "\tbi:f:" + fmt_f32_trim(bi) + "\n";
   }
   return out;
@@ -1651,6 +1693,16 @@ int orc_index_attach_cigar_file(void *h, const char *path, const uint64_t *offse
     }
   idx->faithful = true;
   return 0;
+}
+void orc_index_set_original_coordinates(void *h, int on) { ((Index *)h)->original_coordinates = on != 0; }
+// 1 and (base, start) for "base:start-end", else 0
+int orc_parse_subsequence_coordinates(const char *name, char *base_out, size_t cap, int32_t *start) {
+  std::string base;
+  int32_t off = 0;
+  if (!parse_subsequence_coordinates(name, base, off)) return 0;
+  snprintf(base_out, cap, "%s", base.c_str());
+  *start = off;
+  return 1;
 }
 void orc_index_set_faithful(void *h, int on) { ((Index *)h)->faithful = on != 0 && ((Index *)h)->fd >= 0; }
 

@@ -234,6 +234,14 @@ def identity(ops):
     return lib().orc_identity(_p(ops), C.c_size_t(len(ops)))
 
 
+def parse_subsequence_coordinates(name):
+    """reference src/main.rs:4642-4659 -> (base, start) or None"""
+    buf = C.create_string_buffer(len(name.encode()) + 1)
+    st = C.c_int32(0)
+    r = lib().orc_parse_subsequence_coordinates(name.encode(), buf, C.c_size_t(len(buf)), C.byref(st))
+    return (buf.value.decode(), st.value) if r else None
+
+
 def subset_matches(list_text, name):
     """SubsetFilter::matches after parse_subset_filter (reference src/subset_filter.rs). -> (bool, entry_count)"""
     n = C.c_size_t(0)
@@ -424,6 +432,9 @@ class Index:
         lens = np.ascontiguousarray(lens, np.uint64)
         if lib().orc_index_attach_cigar_file(self.h, path.encode(), _p(offsets), _p(lens)) != 0:
             raise OSError("cannot open " + path)
+
+    def set_original_coordinates(self, on=True):
+        lib().orc_index_set_original_coordinates(self.h, C.c_int(1 if on else 0))
 
     def set_faithful(self, on):
         lib().orc_index_set_faithful(self.h, C.c_int(1 if on else 0))

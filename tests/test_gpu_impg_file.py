@@ -109,3 +109,35 @@ def test_cli_subset_sequence_list_uses_the_reference_matching_rules(tmp_path):
     lst.write_text("# nothing\n\n")
     bad = subprocess.run(args + ["--subset-sequence-list", str(lst)], capture_output=True, text=True)
     assert bad.returncode != 0 and "did not contain any sequence names" in bad.stderr
+
+
+def test_original_sequence_coordinates_in_the_writers(tmp_path):
+    """--original-sequence-coordinates (reference src/main.rs:4642-4678, :11869-11881, :11913-11934): names of
+    the form base:start-end are reported in the coordinates of `base`, by BED (per row and per batch) and BEDPE."""
+    paf = os.path.join(GOLD, "short_floor.paf")
+    gpu, orc = ix.Impg.from_paf(paf), O.Index.from_paf(paf)
+    rows = np.array([(s, 0, orc.seq_len(s)) for s in range(orc.n_seqs)], ix.RANGE_DTYPE)
+    names = [f"r{k}" for k in range(len(rows))]
+    for on in (True, False):
+        gpu.set_original_coordinates(on)
+        orc.set_original_coordinates(on)
+        gp = ix.make_params(mode=ix.MODE_BFS, max_depth=2, min_transitive_len=0, merge_distance=10)
+        op = O.make_params(mode=O.MODE_BFS, max_depth=2, min_transitive_len=0, merge_distance=10)
+        res = gpu.query_batch_bed(rows, gp)
+        want = "".join(orc.format(orc.perform_query(int(r["target_id"]), int(r["start"]), int(r["end"]), op), "bed", names[k], 10)
+                       for k, r in enumerate(rows))
+        assert gpu.format_bed_batch(res, names) == want
+        assert "".join(gpu.format_bed(res, k, names[k]) for k in range(len(rows))) == want
+        assert (":0-250" not in want) == on and ("C4FIXTURE#0#short_floor\t" in want) == on
+        gc = ix.make_params(mode=ix.MODE_QUERY, store_cigar=True)
+        oc = O.make_params(mode=O.MODE_QUERY, store_cigar=True)
+        raw = gpu.query_batch(rows, gc)
+        for k, r in enumerate(rows):
+            ores = orc.perform_query(int(r["target_id"]), int(r["start"]), int(r["end"]), oc)
+            ores.drop_first()
+            assert ix.format_bedpe(gpu, raw, k, names[k], 0) == orc.format(ores, "bedpe", names[k], 0)
+        if on:
+            with pytest.raises(ix.ImpgxError):
+                ix.format_paf(gpu, raw, 0, names[0], 0)
+        else:
+            assert ix.format_paf(gpu, raw, 0, names[0], 0)

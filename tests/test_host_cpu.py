@@ -316,3 +316,15 @@ def test_parse_merge_distance_reference_kats():
     assert parse("2147483647") == 2147483647 and parse("2g") == 2_000_000_000
     for bad in ("10kb", "3g", "", "k", "-5", "1..5k", "abc", "2147483648"):
         assert parse(bad) is None, bad
+
+
+def test_parse_subsequence_coordinates_kat_and_fuzz():
+    from test_oracle_kat import SUBSEQ_KATS
+    for name, want in SUBSEQ_KATS:
+        assert ix.parse_subsequence_coordinates(name) == want, name
+    import random
+    rnd = random.Random(9)
+    pieces = ["chr1", "a#1#b", ":", "-", "12", "0", "+5", "-7", "99999999999", "2147483647", "2147483648", "x", "", "3-4", ":8-9"]
+    for _ in range(2000):
+        name = "".join(rnd.choice(pieces) for _ in range(rnd.randrange(1, 6)))
+        assert ix.parse_subsequence_coordinates(name) == O.parse_subsequence_coordinates(name), name

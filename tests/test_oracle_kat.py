@@ -143,3 +143,13 @@ def test_subset_filter_matches_variants():
     for name in no:
         assert not O.subset_matches(contents, name)[0], name
     assert O.subset_matches(contents, "chr1")[1] == 5  # entry_count = distinct trimmed lines
+
+
+SUBSEQ_KATS = [("HG002#1#chr1:5116130-6116563", ("HG002#1#chr1", 5116130)),   # reference src/main.rs:13330-13346
+               ("GRCh38#0#chr1:5477602-6474357", ("GRCh38#0#chr1", 5477602)),
+               ("chr1", None), ("chr1:invalid", None)]
+
+
+def test_parse_subsequence_coordinates():
+    for name, want in SUBSEQ_KATS:
+        assert O.parse_subsequence_coordinates(name) == want, name
