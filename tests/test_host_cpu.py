@@ -328,3 +328,39 @@ def test_parse_subsequence_coordinates_kat_and_fuzz():
     for _ in range(2000):
         name = "".join(rnd.choice(pieces) for _ in range(rnd.randrange(1, 6)))
         assert ix.parse_subsequence_coordinates(name) == O.parse_subsequence_coordinates(name), name
+
+
+def test_new_entry_points_reject_null_arguments_without_crashing():
+    """No exception, abort or crash crosses the ABI: NULL / out-of-range arguments come back as codes."""
+    import ctypes as C
+    L = ix.lib()
+    L.impgx_partitions_format_bed.restype = C.c_void_p
+    L.impgx_format_bed_batch.restype = C.c_void_p
+    L.impgx_impg_seq_name.restype = C.c_char_p
+    assert L.impgx_partition(None, None, None) == ix.E_INVALID
+    assert L.impgx_partitions_view(None, None) == ix.E_INVALID
+    assert L.impgx_partitions_format_bed(None, None, C.c_int64(-1)) is None
+    L.impgx_partitions_free(None)
+    assert L.impgx_partitioner_new(None, None, C.c_uint32(3), None, None) == ix.E_INVALID
+    assert L.impgx_partitioner_next(None, None, None, None) == ix.E_INVALID
+    assert L.impgx_partitioner_feed(None, C.c_size_t(0), None, None, None) == ix.E_INVALID
+    assert L.impgx_partitioner_finish(None, None) == ix.E_INVALID
+    L.impgx_partitioner_free(None)
+    assert L.impgx_impg_open(None, None) == ix.E_INVALID
+    assert L.impgx_impg_records(None, None, None, None, None) == ix.E_INVALID
+    assert L.impgx_impg_version(None) == 0 and L.impgx_impg_num_seqs(None) == 0
+    assert L.impgx_impg_seq_name(None, C.c_uint32(0)) is None
+    L.impgx_impg_close(None)
+    assert L.impgx_impg_write(None, C.c_size_t(0), C.c_int(1), None) == ix.E_INVALID
+    assert L.impgx_index_from_impg(None, None, C.c_size_t(0), C.c_int(0), None) == ix.E_INVALID
+    assert L.impgx_format_bed_batch(None, None, None, None) is None
+    assert L.impgx_subset_matches(None, None) == ix.E_INVALID
+    L.impgx_subset_mask.restype = C.c_long
+    assert L.impgx_subset_mask(None, None, None) == ix.E_INVALID
+    assert L.impgx_parse_merge_distance(None, None) == ix.E_INVALID
+    assert L.impgx_parse_subsequence_coordinates(None, None, C.c_size_t(0), None) == ix.E_INVALID
+    assert L.impgx_index_set_original_coordinates(None, C.c_int(1)) == ix.E_INVALID
+    # a stepper over zero sequences is done at once
+    pp = ix.make_partition_params(window_size=10, merge_distance=0)
+    st = ix.Partitioner(np.zeros(0, np.uint64), pp)
+    assert st.next() is None and st.finish().rows() == []
