@@ -202,3 +202,28 @@ def test_partition_without_device_fails_loudly():
     with pytest.raises(ix.ImpgxError) as e:
         ix.Impg.from_records(recs, runs, offs, lens, names=names)
     assert e.value.code == ix.E_NO_DEVICE
+
+
+def test_stepper_matches_oracle_on_random_worlds_and_parameters():
+    """A sweep over random worlds / parameter combinations (the host logic of impgx_partition against the
+    oracle's literal restatement of partition_alignments)."""
+    import random
+    rnd = random.Random(2024)
+    modes = ["longest", "total", "sample", "haplotype", "sample,#1#", "haplotype,#"]
+    for trial in range(24):
+        world, oidx = patchy_world(seed=500 + trial, keep=rnd.choice([0.15, 0.3, 0.6, 1.0]), genomes=rnd.choice([3, 5, 7]),
+                                   contigs=rnd.choice([1, 2, 3]), contig_len=rnd.choice([20000, 45000]),
+                                   tiles=rnd.choice([3, 7, 11]), rev=rnd.choice([0, 200, 700]))
+        lens, names = world[3], world[4]
+        kw = dict(window_size=rnd.choice([2500, 6000, 15000, 50000]), merge_distance=rnd.choice([-1, 0, 100, 3000, 100000]),
+                  selection_mode=rnd.choice(modes), min_missing_size=rnd.choice([0, 500, 3000, 20000]),
+                  min_boundary_distance=rnd.choice([0, 700, 3000]), transitive_dfs=rnd.random() < 0.3,
+                  max_depth=rnd.choice([0, 1, 2, 3]), min_transitive_len=rnd.choice([0, 101, 1500]),
+                  min_distance_between_ranges=rnd.choice([0, 10, 400]), rehome_singletons=rnd.random() < 0.7)
+        if rnd.random() < 0.3:
+            kw["starting_seqs"] = [rnd.randrange(len(lens)) for _ in range(rnd.randrange(1, 4))]
+        want = oidx.partition(O.make_partition_params(**kw))
+        got, windows = step_with_oracle(oidx, lens, names, kw)
+        assert windows == want["windows"], (trial, kw)
+        assert got.rows() == norm(want["rows"]), (trial, kw)
+        assert got.partitioned_bp == want["partitioned_bp"] == want["total_bp"], (trial, kw)
