@@ -12,6 +12,8 @@
 #include <algorithm>
 #include <cmath>
 #include <map>
+#include <set>
+#include <tuple>
 #include <string>
 #include <vector>
 
@@ -103,6 +105,17 @@ struct impgx_partitioner {
   bool awaiting_feed = false;
   std::vector<uint64_t> mask_off;
   std::vector<int32_t> mask_rng;
+  std::vector<uint32_t> touched;  // sequences whose mask changed since the CSR above was brought up to date
+  int32_t no_ranges[2] = {0, 0};
+  const int32_t *mask_ranges_ptr() const { return mask_rng.empty() ? no_ranges : mask_rng.data(); }  // never NULL
+  // what select_round asks for, kept up to date as regions go missing -> masked (only the active mode's index)
+  std::set<std::tuple<int32_t, uint32_t, int32_t, int32_t>> by_len;  // LONGEST: (length, sequence, start, end)
+  std::set<std::pair<int64_t, uint32_t>> by_total;                   // TOTAL: (missing bases, sequence), non-empty only
+  std::vector<uint32_t> group_of;                                    // GROUP: sequence -> group (ascending prefix)
+  std::vector<int64_t> group_missing;
+  std::vector<uint32_t> group_live;                                  // sequences of the group that still miss something
+  std::vector<std::vector<uint32_t>> group_members;                  // longest first, then by id
+  void index_missing(uint32_t seq, bool add);
   // collected partitions: intervals of partition k are ivs[part_off[k] .. part_off[k+1])
   std::vector<impgx::Iv> ivs;
   std::vector<size_t> part_off{0};
@@ -134,74 +147,55 @@ void impgx_partitioner::add_windows(uint32_t seq, int32_t a, int32_t b, bool sta
   }
 }
 
+// The missing regions of `seq` enter (add) or leave the selection index of the active mode; called around
+// every change of missing[seq], so a round costs O(log) instead of a scan over all sequences.
+void impgx_partitioner::index_missing(uint32_t seq, bool add) {
+  const Ranges &ms = missing[seq];
+  if (select == LONGEST) {
+    for (auto &x : ms.r) {
+      const auto key = std::make_tuple(x.y - x.x, seq, x.x, x.y);
+      if (add) by_len.insert(key);
+      else by_len.erase(key);
+    }
+  } else if (ms.r.empty()) {
+    return;  // a sequence without missing regions is not in the map (:1313-1316)
+  } else if (select == TOTAL) {
+    const auto key = std::make_pair(ms.total(), seq);
+    if (add) by_total.insert(key);
+    else by_total.erase(key);
+  } else {
+    const uint32_t g = group_of[seq];
+    group_missing[g] += add ? ms.total() : -ms.total();
+    group_live[g] += add ? 1u : (uint32_t)-1;
+  }
+}
+
 // select_and_window_sequences (:715-937)
 void impgx_partitioner::select_round() {
   queue.clear();
   head = 0;
   if (select == LONGEST) {
     // max_by (length, id); of equal keys (two regions of one sequence) the later one wins
-    bool any = false;
-    int32_t best_len = 0;
-    uint32_t best_seq = 0;
-    int2 best = make_int2(0, 0);
-    for (uint32_t s = 0; s < n_seqs; s++)
-      for (auto &x : missing[s].r) {
-        const int32_t len = x.y - x.x;
-        if (!any || len >= best_len) {  // s ascends, so on equal lengths the greater id / later region wins
-          any = true;
-          best_len = len;
-          best_seq = s;
-          best = x;
-        }
-      }
-    if (any) add_windows(best_seq, best.x, best.y, false);
+    if (!by_len.empty()) {
+      const auto &k = *by_len.rbegin();
+      add_windows(std::get<1>(k), std::get<2>(k), std::get<3>(k), false);
+    }
   } else if (select == TOTAL) {
-    bool any = false;
-    int64_t best = 0;
-    uint32_t best_seq = 0;
-    for (uint32_t s = 0; s < n_seqs; s++) {
-      if (missing[s].r.empty()) continue;
-      const int64_t t = missing[s].total();
-      if (!any || t > best || (t == best && s > best_seq)) {
-        any = true;
-        best = t;
-        best_seq = s;
-      }
+    // max_by (total missing, id)
+    if (!by_total.empty()) {
+      const uint32_t s = by_total.rbegin()->second;
+      add_windows(s, 0, missing[s].seq_len, false);
     }
-    if (any) add_windows(best_seq, 0, (int32_t)missing[best_seq].seq_len, false);
   } else {
-    // sample / haplotype: group the sequences that still miss something by name prefix (:807-839)
-    std::map<std::string, std::pair<int64_t, std::vector<uint32_t>>> groups;
-    for (uint32_t s = 0; s < n_seqs; s++) {
-      if (missing[s].r.empty()) continue;
-      const std::string &nm = names[s];
-      std::string key;
-      if (sep.empty()) {
-        // str::split("") yields "", c1, c2, …, "": the first field is empty, the second the first char
-        key = group_fields == 1 ? std::string() : nm.substr(0, nm.empty() ? 0 : 1);
-      } else {
-        size_t f1 = nm.find(sep);
-        if (group_fields == 1) key = nm.substr(0, f1);
-        else if (f1 == std::string::npos) key = nm + sep;
-        else {
-          size_t f2 = nm.find(sep, f1 + sep.size());
-          key = nm.substr(0, f2);
-        }
-      }
-      auto &g = groups[key];
-      g.first += missing[s].total();
-      g.second.push_back(s);
-    }
-    const std::pair<int64_t, std::vector<uint32_t>> *bestg = nullptr;
-    for (auto &kv : groups)  // ascending prefix; max_by (missing, prefix) -> ties go to the greater prefix
-      if (!bestg || kv.second.first >= bestg->first) bestg = &kv.second;
-    if (bestg) {
-      // longest sequence first (:877-885; equal lengths: the reference's order is hash order, here by id)
-      std::vector<uint32_t> order = bestg->second;
-      std::stable_sort(order.begin(), order.end(),
-                       [&](uint32_t a, uint32_t b) { return missing[a].seq_len > missing[b].seq_len; });
-      for (uint32_t s : order) add_windows(s, 0, missing[s].seq_len, false);
-    }
+    // sample / haplotype (:807-895): the group (name prefix) with the most missing bases, ties to the greater
+    // prefix; its sequences that still miss something, longest first (equal lengths: the reference's order is
+    // hash order, here by id)
+    long best = -1;
+    for (size_t g = 0; g < group_missing.size(); g++)  // groups are numbered by ascending prefix
+      if (group_live[g] && (best < 0 || group_missing[g] >= group_missing[(size_t)best])) best = (long)g;
+    if (best >= 0)
+      for (uint32_t s : group_members[(size_t)best])
+        if (!missing[s].r.empty()) add_windows(s, 0, missing[s].seq_len, false);
   }
 }
 
@@ -267,6 +261,8 @@ void impgx_partitioner::cut_by_mask(uint32_t seq, const Iv *first, const Iv *las
   }
   // 3. the claimed intervals join the mask; missing = missing minus mask
   for (auto &c : claimed) mk.insert(c.x, c.y);
+  touched.push_back(seq);
+  index_missing(seq, false);
   if (!ms.r.empty()) {
     std::vector<int2> old;
     old.swap(ms.r);
@@ -282,6 +278,7 @@ void impgx_partitioner::cut_by_mask(uint32_t seq, const Iv *first, const Iv *las
       if (cur < m.y) ms.insert(cur, m.y);
     }
   }
+  index_missing(seq, true);
 }
 
 void impgx_partitioner::feed(size_t n, const uint32_t *q_id, const int32_t *q_first, const int32_t *q_last) {
@@ -430,6 +427,37 @@ static impgx_partitioner *make_partitioner(const uint64_t *seq_lens, const char 
     p->missing[s].insert(0, len);  // :259-267 (an empty sequence leaves the degenerate range (0, 0) behind)
     p->total_bp += seq_lens[s];
   }
+  if (p->select == impgx_partitioner::GROUP) {
+    // sequences grouped by name prefix (:807-839): the first field, or the first two joined by the separator
+    std::map<std::string, std::vector<uint32_t>> by_prefix;
+    for (uint32_t s = 0; s < n_seqs; s++) {
+      const std::string &nm = p->names[s];
+      const std::string &sep = p->sep;
+      std::string key;
+      if (sep.empty()) {
+        // str::split("") yields "", c1, c2, …, "": the first field is empty, the second the first char
+        key = p->group_fields == 1 ? std::string() : nm.substr(0, nm.empty() ? 0 : 1);
+      } else {
+        const size_t f1 = nm.find(sep);
+        if (p->group_fields == 1) key = nm.substr(0, f1);
+        else if (f1 == std::string::npos) key = nm + sep;
+        else key = nm.substr(0, nm.find(sep, f1 + sep.size()));
+      }
+      by_prefix[key].push_back(s);
+    }
+    p->group_of.assign(n_seqs, 0);
+    for (auto &kv : by_prefix) {  // ascending prefix = ascending group number
+      const uint32_t g = (uint32_t)p->group_members.size();
+      std::vector<uint32_t> members = kv.second;
+      std::stable_sort(members.begin(), members.end(),
+                       [&](uint32_t a, uint32_t b) { return p->missing[a].seq_len > p->missing[b].seq_len; });
+      for (uint32_t m : members) p->group_of[m] = g;
+      p->group_members.push_back(std::move(members));
+    }
+    p->group_missing.assign(p->group_members.size(), 0);
+    p->group_live.assign(p->group_members.size(), 0);
+  }
+  for (uint32_t s = 0; s < n_seqs; s++) p->index_missing(s, true);
   for (size_t k = 0; k < pp.n_starting_seqs; k++) {
     REQUIRE(pp.starting_seqs && pp.starting_seqs[k] < n_seqs, IMPGX_E_INVALID, "starting sequence id out of range");
     p->add_windows(pp.starting_seqs[k], 0, (int32_t)seq_lens[pp.starting_seqs[k]], true);
@@ -451,17 +479,35 @@ static bool next_window(impgx_partitioner *p, impgx_range *w) {
   *w = p->queue[p->head++];
   p->n_windows++;
   p->awaiting_feed = true;
-  // masked_regions as CSR over all sequences
-  p->mask_rng.clear();
-  for (uint32_t s = 0; s < p->n_seqs; s++) {
-    p->mask_off[s] = p->mask_rng.size() / 2;
-    for (auto &x : p->masked[s].r) {
-      p->mask_rng.push_back(x.x);
-      p->mask_rng.push_back(x.y);
+  // masked_regions as CSR over all sequences, spliced: the slices of the sequences the last feed touched are
+  // rebuilt from their range lists, everything else is copied in bulk from the previous arrays (no walk over
+  // every sequence's list; the offsets are one sequential pass)
+  if (!p->touched.empty()) {
+    std::sort(p->touched.begin(), p->touched.end());
+    p->touched.erase(std::unique(p->touched.begin(), p->touched.end()), p->touched.end());
+    const std::vector<uint64_t> &old_off = p->mask_off;
+    const std::vector<int32_t> &old_rng = p->mask_rng;
+    std::vector<uint64_t> off((size_t)p->n_seqs + 1);
+    std::vector<int32_t> rng;
+    rng.reserve(old_rng.size() + 4 * p->touched.size());
+    uint32_t from = 0;  // first sequence not yet emitted
+    int64_t delta = 0;  // new offset - old offset from `from` on
+    for (uint32_t t : p->touched) {
+      for (uint32_t s = from; s <= t; s++) off[s] = (uint64_t)((int64_t)old_off[s] + delta);
+      rng.insert(rng.end(), old_rng.begin() + 2 * old_off[from], old_rng.begin() + 2 * old_off[t]);
+      for (auto &x : p->masked[t].r) {
+        rng.push_back(x.x);
+        rng.push_back(x.y);
+      }
+      delta += (int64_t)p->masked[t].r.size() - (int64_t)(old_off[t + 1] - old_off[t]);
+      from = t + 1;
     }
+    for (uint32_t s = from; s <= p->n_seqs; s++) off[s] = (uint64_t)((int64_t)old_off[s] + delta);
+    rng.insert(rng.end(), old_rng.begin() + 2 * old_off[from], old_rng.begin() + 2 * old_off[p->n_seqs]);
+    p->mask_off.swap(off);
+    p->mask_rng.swap(rng);
+    p->touched.clear();
   }
-  p->mask_off[p->n_seqs] = p->mask_rng.size() / 2;
-  if (p->mask_rng.empty()) p->mask_rng.assign(2, 0);  // keep the pointer non-NULL
   return true;
 }
 
@@ -499,7 +545,7 @@ int impgx_partitioner_next(impgx_partitioner *p, impgx_range *window, const uint
   REQUIRE(p && window, IMPGX_E_INVALID, "NULL argument");
   if (!next_window(p, window)) return 0;
   if (mask_offsets) *mask_offsets = p->mask_off.data();
-  if (mask_ranges) *mask_ranges = p->mask_rng.data();
+  if (mask_ranges) *mask_ranges = p->mask_ranges_ptr();
   return 1;
   API_END
   return IMPGX_E_INVALID;
@@ -553,7 +599,7 @@ int impgx_partition(impgx_index *idx, const impgx_partition_params *params, impg
   impgx_range w;
   while (next_window(p.get(), &w)) {
     q.mask_offsets = p->mask_off.data();
-    q.mask_ranges = p->mask_rng.data();
+    q.mask_ranges = p->mask_ranges_ptr();
     std::unique_ptr<impgx_results> res(
         impgx::query_batch(idx, &w, 1, q, device_merge, /*ranges_on_device=*/false, /*results_to_host=*/true, nullptr));
     p->awaiting_feed = false;
