@@ -937,6 +937,26 @@ int impgx_subset_matches(const char *list_text, const char *seq_name) {
   }
 }
 
+// test hook: output_results_bedpe / _paf (merge_adjusted_intervals + writer, host code) on rows given as arrays, so the
+// CIGAR surgery can be compared with the oracle on adversarial rows without a device. format 1 = bedpe, 2 = paf.
+char *impgx_debug_format_rows(const char *const *names, const uint64_t *lens, uint32_t n_seqs, size_t n,
+                              const uint32_t *q_id, const int32_t *q_first, const int32_t *q_last, const uint32_t *t_id,
+                              const int32_t *t_first, const int32_t *t_last, const uint64_t *cig_off, const uint32_t *cig,
+                              const char *name, int32_t d, int format, int original_coordinates) {
+  try {
+    REQUIRE(name && (n == 0 || (q_id && q_first && q_last && t_id && t_first && t_last)) && (format == 1 || format == 2),
+            IMPGX_E_INVALID, "bad argument");
+    const std::string s = impgx::debug_format_rows(names, lens, n_seqs, n, q_id, q_first, q_last, t_id, t_first, t_last, cig_off,
+                                                   cig, name, d, format, original_coordinates != 0);
+    char *p = (char *)malloc(s.size() + 1);
+    if (p) memcpy(p, s.c_str(), s.size() + 1);
+    return p;
+  } catch (const std::exception &e) {
+    impgx::set_last_error(e.what());
+    return nullptr;
+  }
+}
+
 // test hooks: the device sort / scan primitives on host arrays (both the single-CTA kernels for small inputs
 // and the CUB pipelines sit behind the same calls; the size decides)
 int impgx_debug_sort_pairs(int device, uint64_t *keys, uint32_t *vals, uint64_t n, int begin_bit, int end_bit, int key_bytes) {

@@ -51,6 +51,10 @@ long parse_cigar(const char *s, size_t n, std::vector<uint32_t> &out);
 // the subsequence start added to both coordinates. Returns false (nothing changed) for any other name.
 bool to_original_coordinates(const std::string &seq_name, std::string &base, uint32_t &offset);
 
+std::string debug_format_rows(const char *const *names, const uint64_t *lens, uint32_t n_seqs, size_t n, const uint32_t *q_id,
+                              const int32_t *q_first, const int32_t *q_last, const uint32_t *t_id, const int32_t *t_first,
+                              const int32_t *t_last, const uint64_t *cig_off, const uint32_t *cig, const char *name, int32_t d,
+                              int format, bool original_coordinates);
 void debug_sort_pairs(int device, uint64_t *keys, uint32_t *vals, uint64_t n, int begin_bit, int end_bit, int key_bytes);
 void debug_exclusive_scan(int device, uint64_t *a, uint64_t n_plus_1);
 

@@ -356,9 +356,37 @@ bool to_original_coordinates(const std::string &seq_name, std::string &base, uin
   return true;
 }
 
+static std::string format_row_vector(const impgx_index *idx, std::vector<Row> rows, const char *name, int32_t d, int format);
+
 std::string format_rows(const impgx_index *idx, const impgx_results *res, size_t row, const char *name, int32_t d,
                         int format) {
-  std::vector<Row> rows = rows_of(res, row);
+  return format_row_vector(idx, rows_of(res, row), name, d, format);
+}
+
+// Test hook: the same merge + writer on rows given as host arrays (no result object, no device): row i =
+// (q_id, q_first, q_last, t_id, t_first, t_last, cigar runs [cig_off[i], cig_off[i+1])); names / lengths by id.
+std::string debug_format_rows(const char *const *names, const uint64_t *lens, uint32_t n_seqs, size_t n,
+                              const uint32_t *q_id, const int32_t *q_first, const int32_t *q_last, const uint32_t *t_id,
+                              const int32_t *t_first, const int32_t *t_last, const uint64_t *cig_off, const uint32_t *cig,
+                              const char *name, int32_t d, int format, bool original_coordinates) {
+  impgx_index idx;  // host fields only; nothing of it lives on a device
+  idx.n_seqs = n_seqs;
+  idx.original_coordinates = original_coordinates;
+  for (uint32_t s = 0; s < n_seqs; s++) {
+    idx.names.push_back(names && names[s] ? names[s] : "");
+    idx.seq_lens.push_back(lens ? lens[s] : 0);
+  }
+  std::vector<Row> rows;
+  for (size_t i = 0; i < n; i++) {
+    REQUIRE(q_id[i] < n_seqs && t_id[i] < n_seqs, IMPGX_E_INVALID, "sequence id out of range");
+    Row r{q_id[i], t_id[i], q_first[i], q_last[i], t_first[i], t_last[i], {}};
+    if (cig_off) r.cg.assign(cig + cig_off[i], cig + cig_off[i + 1]);
+    rows.push_back(std::move(r));
+  }
+  return format_row_vector(&idx, std::move(rows), name, d, format);
+}
+
+static std::string format_row_vector(const impgx_index *idx, std::vector<Row> rows, const char *name, int32_t d, int format) {
   if (format == 1) {
     bool any_empty = false;
     for (auto &r : rows) any_empty |= r.cg.empty();

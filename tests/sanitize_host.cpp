@@ -9,6 +9,11 @@
 #include <string>
 #include <vector>
 #include "impgx.h"
+// test hook of libimpgx (csrc/api.cu), not part of the public header
+extern "C" char *impgx_debug_format_rows(const char *const *names, const uint64_t *lens, uint32_t n_seqs, size_t n,
+                                         const uint32_t *q_id, const int32_t *q_first, const int32_t *q_last, const uint32_t *t_id,
+                                         const int32_t *t_first, const int32_t *t_last, const uint64_t *cig_off, const uint32_t *cig,
+                                         const char *name, int32_t d, int format, int original_coordinates);
 int main(int argc, char **argv) {
   std::mt19937_64 rng(7);
   const char *modes[] = {"longest", "total", "sample", "haplotype,#", "sample,"};
@@ -85,6 +90,62 @@ int main(int argc, char **argv) {
       fp = fopen((std::string(argv[0]) + ".bad.impg").c_str(), "wb"); fwrite(e.data(), 1, e.size(), fp); fclose(fp);
       impgx_impg *g = nullptr;
       if (impgx_impg_open((std::string(argv[0]) + ".bad.impg").c_str(), &g) == 0) impgx_impg_close(g);
+    }
+  }
+  // BEDPE / PAF merge with CIGAR surgery (csrc/host_output.cu) on random chains of alignments
+  {
+    const char *nm[4] = {"s0#1#a", "s1#1#b:5-900", "s2", "s3#2#c"};
+    const uint64_t ln[4] = {100000, 100001, 100002, 100003};
+    const char opc[] = {0, 0, 1, 2, 3, 4};  // = = X I D M
+    for (int trial = 0; trial < 3000; trial++) {
+      std::vector<uint32_t> q, t, cig;
+      std::vector<int32_t> qf, ql, tf, tl;
+      std::vector<uint64_t> off{0};
+      int chains = 1 + (int)(rng() % 4);
+      for (int c = 0; c < chains; c++) {
+        uint32_t qi = (uint32_t)(rng() % 4), ti = (uint32_t)(rng() % 4);
+        bool rev = rng() % 5 < 2;
+        long qs = (long)(rng() % 2000), ts = (long)(rng() % 2000);
+        int m = 1 + (int)(rng() % 5);
+        for (int k = 0; k < m; k++) {
+          long qlen = 0, tlen = 0;
+          int nops = 1 + (int)(rng() % 6), last = -1;
+          std::vector<uint32_t> ops;
+          for (int o = 0; o < nops; o++) {
+            int op = opc[rng() % 6];
+            if (op == last) continue;
+            last = op;
+            uint32_t len = 1 + (uint32_t)(rng() % 40);
+            ops.push_back(IMPGX_RUN(op, len));
+            if (op != IMPGX_OP_D) qlen += len;
+            if (op != IMPGX_OP_I) tlen += len;
+          }
+          if (!qlen || !tlen) continue;
+          static const long steps[] = {0, 0, 0, 3, 60, 2000, -5, -15};
+          long step = steps[rng() % 8];
+          if (rev) {
+            if (qs - qlen < 0) break;
+            q.push_back(qi); qf.push_back((int32_t)qs); ql.push_back((int32_t)(qs - qlen));
+            qs = qs - qlen - step;
+          } else {
+            q.push_back(qi); qf.push_back((int32_t)qs); ql.push_back((int32_t)(qs + qlen));
+            qs = qs + qlen + step;
+          }
+          t.push_back(ti); tf.push_back((int32_t)ts); tl.push_back((int32_t)(ts + tlen));
+          cig.insert(cig.end(), ops.begin(), ops.end());
+          off.push_back(cig.size());
+          ts = ts + tlen + (rng() % 2 ? step : (long)(rng() % 9) - 3);
+          if (qs < 0 || ts < 0) break;
+        }
+      }
+      if (q.empty()) continue;
+      static const int32_t ds[] = {0, 50, 1000, -1};
+      for (int fmt = 1; fmt <= 2; fmt++) {
+        char *text = impgx_debug_format_rows(nm, ln, 4, q.size(), q.data(), qf.data(), ql.data(), t.data(), tf.data(), tl.data(),
+                                             off.data(), cig.data(), "reg", ds[rng() % 4], fmt, fmt == 1 ? (int)(rng() % 2) : 0);
+        if (!text) { printf("format failed: %s\n", impgx_last_error()); return 1; }
+        impgx_free(text);
+      }
     }
   }
   printf("ok\n");
