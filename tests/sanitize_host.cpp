@@ -9,7 +9,12 @@
 #include <string>
 #include <vector>
 #include "impgx.h"
-// test hook of libimpgx (csrc/api.cu), not part of the public header
+// test hooks of libimpgx (csrc/api.cu), not part of the public header
+extern "C" long impgx_debug_host_columns_shard(const impgx_record *records, size_t n, const uint64_t *run_offsets, uint32_t n_seqs,
+                                               int bidirectional, int32_t *e_start, int32_t *e_end, int32_t *e_pmax,
+                                               uint32_t *e_vrank, uint32_t *e_query_id, uint32_t *e_flags, uint32_t *e_aln,
+                                               uint64_t *tgt_off, const uint32_t *owner, uint32_t rank);
+extern "C" void impgx_debug_visit_ranks(size_t n, uint32_t *rank);
 extern "C" char *impgx_debug_format_rows(const char *const *names, const uint64_t *lens, uint32_t n_seqs, size_t n,
                                          const uint32_t *q_id, const int32_t *q_first, const int32_t *q_last, const uint32_t *t_id,
                                          const int32_t *t_first, const int32_t *t_last, const uint64_t *cig_off, const uint32_t *cig,
@@ -147,6 +152,45 @@ int main(int argc, char **argv) {
         impgx_free(text);
       }
     }
+  }
+  // index build on the host (csrc/index_host.cu): entry columns, visit ranks, owner map, for random record sets
+  // (self alignments, equal starts, empty targets, one shard of several)
+  for (int trial = 0; trial < 400; trial++) {
+    const uint32_t n_seqs = 1 + (uint32_t)(rng() % 12);
+    const size_t n = (size_t)(rng() % 200);
+    std::vector<impgx_record> recs(n);
+    std::vector<uint64_t> ro(n + 1, 0);
+    for (size_t i = 0; i < n; i++) {
+      impgx_record &r = recs[i];
+      r.query_id = (uint32_t)(rng() % n_seqs);
+      r.target_id = rng() % 6 ? (uint32_t)(rng() % n_seqs) : r.query_id;
+      r.query_start = (int32_t)(rng() % 50) * 10;
+      r.query_end = r.query_start + 1 + (int32_t)(rng() % 500);
+      r.target_start = (int32_t)(rng() % 50) * 10;
+      r.target_end = r.target_start + 1 + (int32_t)(rng() % 500);
+      r.strand = (uint32_t)(rng() % 2);
+      r.reserved = 0;
+      ro[i + 1] = ro[i] + 1 + rng() % 40;
+    }
+    const int bidir = (int)(rng() % 2);
+    const uint32_t n_ranks = 1 + (uint32_t)(rng() % 4);
+    std::vector<uint32_t> owner(n_seqs);
+    if (impgx_assign_owners(recs.data(), n, ro.data(), n_seqs, bidir, n_ranks, owner.data()) != 0) { printf("owners: %s\n", impgx_last_error()); return 1; }
+    for (uint32_t rank = 0; rank < n_ranks; rank++) {
+      long E = impgx_debug_host_columns_shard(recs.data(), n, ro.data(), n_seqs, bidir, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                              nullptr, nullptr, nullptr, n_ranks > 1 ? owner.data() : nullptr, rank);
+      if (E < 0) { printf("columns: %s\n", impgx_last_error()); return 1; }
+      std::vector<int32_t> a(E), b(E), c(E);
+      std::vector<uint32_t> d(E), e(E), f(E), g(E);
+      std::vector<uint64_t> to(n_seqs + 1);
+      impgx_debug_host_columns_shard(recs.data(), n, ro.data(), n_seqs, bidir, a.data(), b.data(), c.data(), d.data(), e.data(),
+                                     f.data(), g.data(), to.data(), n_ranks > 1 ? owner.data() : nullptr, rank);
+      for (uint32_t s2 = 0; s2 < n_seqs; s2++)
+        for (uint64_t k = to[s2] + 1; k < to[s2 + 1]; k++)
+          if (a[k - 1] > a[k]) { printf("entries of a target not sorted by start\n"); return 1; }
+    }
+    std::vector<uint32_t> vr(1 + rng() % 300);
+    impgx_debug_visit_ranks(vr.size(), vr.data());
   }
   printf("ok\n");
   return 0;

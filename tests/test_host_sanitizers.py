@@ -21,7 +21,7 @@ def test_host_code_is_clean_under_asan_and_ubsan(tmp_path):
     flags = [CXX, "-std=c++17", "-g", "-O1", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
              "-fno-omit-frame-pointer", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC, "-I" + CUDA_INC]
     objs = []
-    for src in ("partition.cu", "impg_file.cu", "host_output.cu", "api.cu"):
+    for src in ("partition.cu", "impg_file.cu", "host_output.cu", "index_host.cu", "api.cu"):
         obj = str(tmp_path / (src + ".o"))
         subprocess.run(flags + ["-fopenmp", "-x", "c++", "-c", os.path.join(CSRC, src), "-o", obj], check=True)
         objs.append(obj)
