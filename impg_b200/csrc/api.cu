@@ -1,5 +1,8 @@
 // api.cu — the extern "C" boundary (include/impgx.h). No exception crosses it.
 #include <zlib.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #include <cmath>
 #include <cstring>
@@ -60,22 +63,208 @@ static bool parse_usize(const char *b, const char *e, uint64_t &v) {
   return true;
 }
 
+// The same parse with the lines spread over the host cores. Per line: fields, coordinates, the CIGAR decoded into
+// the thread's own run buffer (threads own contiguous blocks of lines, so the buffers concatenate in file order).
+// What depends on file order is done in two cheap sequential passes: the reference's byte offsets (a prefix sum over
+// line lengths) and the sequence ids by first appearance (query column first). The first bad line in file order
+// reports its error, exactly as the serial loop would.
+static void parse_paf_parallel(const std::string &data, const std::string &path, PafData &out) {
+  std::vector<size_t> starts;
+  for (size_t pos = 0; pos < data.size();) {
+    starts.push_back(pos);
+    const void *nl = memchr(data.data() + pos, '\n', data.size() - pos);
+    pos = nl ? (size_t)((const char *)nl - data.data()) + 1 : data.size();
+  }
+  const size_t n_lines = starts.size();
+  struct Line {
+    impgx_record r;
+    const char *qn_b, *qn_e, *tn_b, *tn_e;
+    uint64_t ql, tl, cg_rel, cg_len, ref_len;
+    uint32_t n_runs;
+    const char *err;  // nullptr = fine
+  };
+  std::vector<Line> lines(n_lines);
+  int n_threads = 1;
+#ifdef _OPENMP
+  n_threads = std::max(1, omp_get_max_threads());
+#endif
+  n_threads = (int)std::min<size_t>((size_t)n_threads, std::max<size_t>(n_lines, 1));
+  std::vector<std::vector<uint32_t>> runs_of((size_t)n_threads);
+  std::vector<size_t> first_line((size_t)n_threads + 1);
+  for (int t = 0; t <= n_threads; t++) first_line[t] = n_lines * (size_t)t / (size_t)n_threads;
+#pragma omp parallel for schedule(static, 1) num_threads(n_threads)
+  for (int t = 0; t < n_threads; t++) {
+    std::vector<uint32_t> &my_runs = runs_of[t];
+    std::vector<std::pair<const char *, const char *>> fld;
+    for (size_t i = first_line[t]; i < first_line[t + 1]; i++) {
+      Line &ln = lines[i];
+      ln.err = nullptr;
+      ln.n_runs = 0;
+      const size_t pos = starts[i];
+      size_t eol = (i + 1 < n_lines) ? starts[i + 1] - 1 : data.size();
+      if (i + 1 == n_lines && eol > pos && data[eol - 1] == '\n') eol--;  // last line with its terminator
+      size_t end = eol;
+      if (end > pos && data[end - 1] == '\r') end--;
+      ln.ref_len = (uint64_t)(end - pos) + 1;
+      fld.clear();
+      {
+        const char *b = data.data() + pos, *e = data.data() + end, *p = b;
+        for (;;) {
+          const char *tb = (const char *)memchr(p, '\t', (size_t)(e - p));
+          if (!tb) {
+            fld.emplace_back(p, e);
+            break;
+          }
+          fld.emplace_back(p, tb);
+          p = tb + 1;
+        }
+      }
+      if (fld.size() < 12) {
+        ln.err = "Not enough fields in PAF record";
+        continue;
+      }
+      uint64_t qs, qe, ts, te;
+      if (!(parse_usize(fld[1].first, fld[1].second, ln.ql) && parse_usize(fld[2].first, fld[2].second, qs) &&
+            parse_usize(fld[3].first, fld[3].second, qe) && parse_usize(fld[6].first, fld[6].second, ln.tl) &&
+            parse_usize(fld[7].first, fld[7].second, ts) && parse_usize(fld[8].first, fld[8].second, te))) {
+        ln.err = "Invalid field";
+        continue;
+      }
+      if (!(fld[4].first < fld[4].second)) {
+        ln.err = "Expected '+' or '-' for strand";
+        continue;
+      }
+      const char sc = *fld[4].first;
+      if (sc != '+' && sc != '-') {
+        ln.err = "Invalid strand";
+        continue;
+      }
+      if (!(ln.ql <= INT32_MAX && ln.tl <= INT32_MAX && qe <= INT32_MAX && te <= INT32_MAX)) {
+        ln.err = "coordinate beyond 2^31-1";
+        continue;
+      }
+      ln.qn_b = fld[0].first; ln.qn_e = fld[0].second;
+      ln.tn_b = fld[5].first; ln.tn_e = fld[5].second;
+      ln.r.query_start = (int32_t)qs; ln.r.query_end = (int32_t)qe;
+      ln.r.target_start = (int32_t)ts; ln.r.target_end = (int32_t)te;
+      ln.r.strand = sc == '-' ? 1 : 0;
+      ln.r.reserved = 0;
+      bool have = false;
+      uint64_t rel = 0;
+      ln.cg_len = 0;
+      for (auto &tg : fld) {
+        if (tg.second - tg.first >= 5 && memcmp(tg.first, "cg:Z:", 5) == 0) {
+          const size_t before = my_runs.size();
+          const long k = parse_cigar(tg.first + 5, (size_t)(tg.second - tg.first - 5), my_runs);
+          if (k < 0) {
+            my_runs.resize(before);
+            ln.err = "Invalid CIGAR operation";
+            break;
+          }
+          have = k > 0;
+          ln.n_runs = (uint32_t)k;
+          rel += 5;
+          ln.cg_len = (uint64_t)(tg.second - tg.first - 5);
+          break;
+        }
+        rel += (uint64_t)(tg.second - tg.first) + 1;
+      }
+      ln.cg_rel = rel;
+      if (!ln.err && !have) ln.err = "The alignment file does not contain CIGAR strings ('cg:Z' tag)";
+    }
+  }
+  for (size_t i = 0; i < n_lines; i++)
+    if (lines[i].err)
+      throw Error(IMPGX_E_PARSE, std::string(lines[i].err) + " (line " + std::to_string(i + 1) + " of '" + path + "')");
+  // sequential passes: ids by first appearance, the reference's byte offsets
+  auto get_id = [&](const char *b, const char *e, uint64_t len) {
+    std::string name(b, e);
+    auto it = out.ids.find(name);
+    if (it != out.ids.end()) return it->second;
+    uint32_t id = (uint32_t)out.names.size();
+    out.ids.emplace(name, id);
+    out.names.push_back(name);
+    out.lens.push_back(len);
+    return id;
+  };
+  out.recs.reserve(out.recs.size() + n_lines);
+  uint64_t ref_pos = 0, run_total = out.run_off.back();
+  for (size_t i = 0; i < n_lines; i++) {
+    Line &ln = lines[i];
+    ln.r.query_id = get_id(ln.qn_b, ln.qn_e, ln.ql);
+    ln.r.target_id = get_id(ln.tn_b, ln.tn_e, ln.tl);
+    out.recs.push_back(ln.r);
+    run_total += ln.n_runs;
+    out.run_off.push_back(run_total);
+    out.cg_off.push_back(ref_pos + ln.cg_rel);
+    out.cg_len.push_back(ln.cg_len);
+    out.file_idx.push_back(out.n_files);
+    ref_pos += ln.ref_len;
+  }
+  size_t base = out.runs.size(), add = 0;
+  for (auto &v : runs_of) add += v.size();
+  out.runs.resize(base + add);
+  std::vector<size_t> dst((size_t)n_threads);
+  for (int t = 0; t < n_threads; t++) {
+    dst[t] = base;
+    base += runs_of[t].size();
+  }
+#pragma omp parallel for schedule(static, 1) num_threads(n_threads)
+  for (int t = 0; t < n_threads; t++)
+    if (!runs_of[t].empty()) memcpy(out.runs.data() + dst[t], runs_of[t].data(), runs_of[t].size() * 4);
+  out.n_files++;
+}
+
 // parse_paf_line / parse_paf (src/paf.rs:118-194) with SequenceIndex ids by
 // first appearance (src/seqidx.rs:22-35). The CIGAR is decoded here, once.
 void parse_paf(const std::string &path, PafData &out) {
   // gzopen reads plain text transparently and inflates gzip / BGZF (a BGZF file
   // is a series of gzip members, src/paf.rs:199-302); the CIGARs are decoded
   // here once, so no virtual offsets need to be kept.
-  gzFile gz = gzopen(path.c_str(), "rb");
-  REQUIRE(gz != nullptr, IMPGX_E_IO, "cannot open PAF file '" + path + "'");
   std::string data;
+  bool plain = false;
   {
+    // plain text is read in one piece; only gzip / BGZF input goes through zlib
+    FILE *f = fopen(path.c_str(), "rb");
+    REQUIRE(f != nullptr, IMPGX_E_IO, "cannot open PAF file '" + path + "'");
+    unsigned char magic[2] = {0, 0};
+    const size_t got = fread(magic, 1, 2, f);
+    plain = !(got == 2 && magic[0] == 0x1f && magic[1] == 0x8b);
+    if (plain && fseek(f, 0, SEEK_END) == 0) {
+      const long size = ftell(f);
+      if (size >= 0 && fseek(f, 0, SEEK_SET) == 0) {
+        data.resize((size_t)size);
+        const size_t rd = size ? fread(&data[0], 1, (size_t)size, f) : 0;
+        if (rd != (size_t)size) plain = false;  // e.g. a pipe: fall back to the streaming reader
+      } else {
+        plain = false;
+      }
+    } else {
+      plain = false;
+    }
+    fclose(f);
+  }
+  if (!plain) {
+    data.clear();
+    gzFile gz = gzopen(path.c_str(), "rb");
+    REQUIRE(gz != nullptr, IMPGX_E_IO, "cannot open PAF file '" + path + "'");
     std::vector<char> buf(1 << 20);
     int k;
     while ((k = gzread(gz, buf.data(), (unsigned)buf.size())) > 0) data.append(buf.data(), (size_t)k);
     const bool bad = k < 0;
     gzclose(gz);
     REQUIRE(!bad, IMPGX_E_IO, "error while reading / inflating '" + path + "'");
+  }
+  // large files: lines parsed on every host core (below); small ones keep the plain loop
+  {
+    static const size_t min_parallel = [] {
+      const char *v = getenv("IMPGX_PAF_PARALLEL_MIN_BYTES");
+      return (v && *v) ? (size_t)strtoull(v, nullptr, 10) : (size_t)(8u << 20);
+    }();
+    if (data.size() >= min_parallel) {
+      parse_paf_parallel(data, path, out);
+      return;
+    }
   }
   size_t pos = 0, line_no = 0;
   uint64_t ref_pos = 0;
@@ -934,6 +1123,47 @@ int impgx_subset_matches(const char *list_text, const char *seq_name) {
   } catch (const std::exception &e) {
     impgx::set_last_error(e.what());
     return IMPGX_E_INVALID;
+  }
+}
+
+// test hook: what parse_paf extracts from a PAF file (records, decoded runs, the reference's CIGAR offsets), without a
+// device. Arrays may be NULL (sizes only). Returns the number of records or a negative status.
+long impgx_debug_parse_paf(const char *path, impgx_record *recs, uint64_t *run_off, uint32_t *runs, uint64_t *cg_off,
+                           uint64_t *cg_len, uint64_t *n_runs_out, uint32_t *n_seqs_out) {
+  try {
+    REQUIRE(path, IMPGX_E_INVALID, "NULL path");
+    impgx::PafData pd;
+    impgx::parse_paf(path, pd);
+    const size_t n = pd.recs.size();
+    if (recs) memcpy(recs, pd.recs.data(), n * sizeof(impgx_record));
+    if (run_off) memcpy(run_off, pd.run_off.data(), (n + 1) * 8);
+    if (runs && !pd.runs.empty()) memcpy(runs, pd.runs.data(), pd.runs.size() * 4);
+    if (cg_off && n) memcpy(cg_off, pd.cg_off.data(), n * 8);
+    if (cg_len && n) memcpy(cg_len, pd.cg_len.data(), n * 8);
+    if (n_runs_out) *n_runs_out = pd.runs.size();
+    if (n_seqs_out) *n_seqs_out = (uint32_t)pd.names.size();
+    return (long)n;
+  } catch (const impgx::Error &e) {
+    impgx::set_last_error(e.what());
+    return e.code;
+  } catch (const std::exception &e) {
+    impgx::set_last_error(e.what());
+    return IMPGX_E_INVALID;
+  }
+}
+// "name\tlength\n" per sequence id of the same parse; malloc'ed, impgx_free
+char *impgx_debug_parse_paf_seqs(const char *path) {
+  try {
+    impgx::PafData pd;
+    impgx::parse_paf(path, pd);
+    std::string s;
+    for (size_t i = 0; i < pd.names.size(); i++) s += pd.names[i] + "\t" + std::to_string(pd.lens[i]) + "\n";
+    char *p = (char *)malloc(s.size() + 1);
+    if (p) memcpy(p, s.c_str(), s.size() + 1);
+    return p;
+  } catch (const std::exception &e) {
+    impgx::set_last_error(e.what());
+    return nullptr;
   }
 }
 

@@ -60,6 +60,11 @@ def test_text_parsers_survive_mutated_inputs_under_asan_and_ubsan(tmp_path):
         pytest.skip("the sanitizer runtimes or libcudart are not available to the host linker")
     assert probe.returncode == 0, probe.stderr
     pafs = [os.path.join(ROOT, "tests", "golden", n) for n in ("short_floor.paf", "easy_shared_flank.paf")]
-    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=0:protect_shadow_gap=0")
-    r = subprocess.run([exe] + pafs, capture_output=True, text=True, env=env, timeout=900)
-    assert r.returncode == 0 and r.stdout.strip().startswith("ok"), r.stdout[-2000:] + r.stderr[-4000:]
+    outs = []
+    for min_bytes in (str(1 << 40), "0"):  # the plain loop, then the multi-threaded PAF parse on the same inputs
+        env = dict(os.environ, ASAN_OPTIONS="detect_leaks=0:protect_shadow_gap=0", IMPGX_PAF_PARALLEL_MIN_BYTES=min_bytes,
+                   OMP_NUM_THREADS="4")
+        r = subprocess.run([exe] + pafs, capture_output=True, text=True, env=env, timeout=900)
+        assert r.returncode == 0 and r.stdout.strip().startswith("ok"), r.stdout[-2000:] + r.stderr[-4000:]
+        outs.append(r.stdout.strip())
+    assert outs[0] == outs[1]  # both paths accept exactly the same mutated files
