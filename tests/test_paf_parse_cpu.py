@@ -106,3 +106,11 @@ def test_both_paths_report_the_same_first_error(tmp_path):
         a, b = product_parse(str(p), False), product_parse(str(p), True)
         assert "error" in a and a == b, (name, a, b)
         assert "line 6 of" in a["error"] and a["code"] == ix.E_PARSE
+
+
+def test_gzip_input_parses_like_plain_text(tmp_path):
+    import gzip
+    gz = tmp_path / "x.paf.gz"
+    gz.write_bytes(gzip.compress(open(PAFS[1], "rb").read()))
+    plain = product_parse(PAFS[1], False)
+    assert product_parse(str(gz), False) == plain and product_parse(str(gz), True) == plain
