@@ -1,4 +1,8 @@
 // api.cu — the extern "C" boundary (include/impgx.h). No exception crosses it.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 #ifdef _OPENMP
 #include <omp.h>
@@ -63,12 +67,35 @@ static bool parse_usize(const char *b, const char *e, uint64_t &v) {
   return true;
 }
 
+// The bytes of a PAF file: a read-only mapping of a plain file, or the inflated text of a gzip / BGZF one.
+struct PafText {
+  const char *p = nullptr;
+  size_t n = 0;
+  void *map = nullptr;
+  size_t map_len = 0;
+  std::string owned;
+  PafText() {}
+  PafText(const PafText &) = delete;
+  PafText &operator=(const PafText &) = delete;
+  ~PafText() {
+    if (map) munmap(map, map_len);
+  }
+  const char *data() const { return p; }
+  size_t size() const { return n; }
+  char operator[](size_t i) const { return p[i]; }
+  size_t find(char c, size_t pos) const {
+    if (pos >= n) return std::string::npos;
+    const void *q = memchr(p + pos, c, n - pos);
+    return q ? (size_t)((const char *)q - p) : std::string::npos;
+  }
+};
+
 // The same parse with the lines spread over the host cores. Per line: fields, coordinates, the CIGAR decoded into
 // the thread's own run buffer (threads own contiguous blocks of lines, so the buffers concatenate in file order).
 // What depends on file order is done in two cheap sequential passes: the reference's byte offsets (a prefix sum over
 // line lengths) and the sequence ids by first appearance (query column first). The first bad line in file order
 // reports its error, exactly as the serial loop would.
-static void parse_paf_parallel(const std::string &data, const std::string &path, PafData &out) {
+static void parse_paf_parallel(const PafText &data, const std::string &path, PafData &out) {
   std::vector<size_t> starts;
   for (size_t pos = 0; pos < data.size();) {
     starts.push_back(pos);
@@ -201,17 +228,13 @@ static void parse_paf_parallel(const std::string &data, const std::string &path,
     out.file_idx.push_back(out.n_files);
     ref_pos += ln.ref_len;
   }
-  size_t base = out.runs.size(), add = 0;
+  size_t add = 0;
   for (auto &v : runs_of) add += v.size();
-  out.runs.resize(base + add);
-  std::vector<size_t> dst((size_t)n_threads);
-  for (int t = 0; t < n_threads; t++) {
-    dst[t] = base;
-    base += runs_of[t].size();
+  out.runs.reserve(out.runs.size() + add);
+  for (auto &v : runs_of) {  // thread blocks are in file order
+    out.runs.insert(out.runs.end(), v.begin(), v.end());
+    std::vector<uint32_t>().swap(v);
   }
-#pragma omp parallel for schedule(static, 1) num_threads(n_threads)
-  for (int t = 0; t < n_threads; t++)
-    if (!runs_of[t].empty()) memcpy(out.runs.data() + dst[t], runs_of[t].data(), runs_of[t].size() * 4);
   out.n_files++;
 }
 
@@ -221,39 +244,42 @@ void parse_paf(const std::string &path, PafData &out) {
   // gzopen reads plain text transparently and inflates gzip / BGZF (a BGZF file
   // is a series of gzip members, src/paf.rs:199-302); the CIGARs are decoded
   // here once, so no virtual offsets need to be kept.
-  std::string data;
-  bool plain = false;
+  PafText data;
   {
-    // plain text is read in one piece; only gzip / BGZF input goes through zlib
-    FILE *f = fopen(path.c_str(), "rb");
-    REQUIRE(f != nullptr, IMPGX_E_IO, "cannot open PAF file '" + path + "'");
+    // a plain file is mapped; only gzip / BGZF input goes through zlib
+    bool mapped = false;
+    const int fd = open(path.c_str(), O_RDONLY);
+    REQUIRE(fd >= 0, IMPGX_E_IO, "cannot open PAF file '" + path + "'");
     unsigned char magic[2] = {0, 0};
-    const size_t got = fread(magic, 1, 2, f);
-    plain = !(got == 2 && magic[0] == 0x1f && magic[1] == 0x8b);
-    if (plain && fseek(f, 0, SEEK_END) == 0) {
-      const long size = ftell(f);
-      if (size >= 0 && fseek(f, 0, SEEK_SET) == 0) {
-        data.resize((size_t)size);
-        const size_t rd = size ? fread(&data[0], 1, (size_t)size, f) : 0;
-        if (rd != (size_t)size) plain = false;  // e.g. a pipe: fall back to the streaming reader
+    const ssize_t got = pread(fd, magic, 2, 0);
+    struct stat st;
+    if (!(got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) && fstat(fd, &st) == 0 && S_ISREG(st.st_mode)) {
+      if (st.st_size == 0) {
+        mapped = true;  // an empty file: no records
       } else {
-        plain = false;
+        void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m != MAP_FAILED) {
+          data.map = m;
+          data.map_len = (size_t)st.st_size;
+          data.p = (const char *)m;
+          data.n = (size_t)st.st_size;
+          mapped = true;
+        }
       }
-    } else {
-      plain = false;
     }
-    fclose(f);
-  }
-  if (!plain) {
-    data.clear();
-    gzFile gz = gzopen(path.c_str(), "rb");
-    REQUIRE(gz != nullptr, IMPGX_E_IO, "cannot open PAF file '" + path + "'");
-    std::vector<char> buf(1 << 20);
-    int k;
-    while ((k = gzread(gz, buf.data(), (unsigned)buf.size())) > 0) data.append(buf.data(), (size_t)k);
-    const bool bad = k < 0;
-    gzclose(gz);
-    REQUIRE(!bad, IMPGX_E_IO, "error while reading / inflating '" + path + "'");
+    close(fd);
+    if (!mapped) {
+      gzFile gz = gzopen(path.c_str(), "rb");
+      REQUIRE(gz != nullptr, IMPGX_E_IO, "cannot open PAF file '" + path + "'");
+      std::vector<char> buf(1 << 20);
+      int k;
+      while ((k = gzread(gz, buf.data(), (unsigned)buf.size())) > 0) data.owned.append(buf.data(), (size_t)k);
+      const bool bad = k < 0;
+      gzclose(gz);
+      REQUIRE(!bad, IMPGX_E_IO, "error while reading / inflating '" + path + "'");
+      data.p = data.owned.data();
+      data.n = data.owned.size();
+    }
   }
   // large files: lines parsed on every host core (below); small ones keep the plain loop
   {
