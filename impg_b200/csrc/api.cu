@@ -122,6 +122,12 @@ static void parse_paf_parallel(const PafText &data, const std::string &path, Paf
 #pragma omp parallel for schedule(static, 1) num_threads(n_threads)
   for (int t = 0; t < n_threads; t++) {
     std::vector<uint32_t> &my_runs = runs_of[t];
+    {
+      // a run takes at least two bytes of text: reserving once spares the growth copies (untouched pages cost nothing)
+      const size_t b0 = first_line[t] < n_lines ? starts[first_line[t]] : data.size();
+      const size_t b1 = first_line[t + 1] < n_lines ? starts[first_line[t + 1]] : data.size();
+      my_runs.reserve((b1 - b0) / 2 + 16);
+    }
     std::vector<std::pair<const char *, const char *>> fld;
     for (size_t i = first_line[t]; i < first_line[t + 1]; i++) {
       Line &ln = lines[i];
