@@ -227,3 +227,23 @@ def test_stepper_matches_oracle_on_random_worlds_and_parameters():
         assert windows == want["windows"], (trial, kw)
         assert got.rows() == norm(want["rows"]), (trial, kw)
         assert got.partitioned_bp == want["partitioned_bp"] == want["total_bp"], (trial, kw)
+
+
+def test_stepper_reproduces_the_committed_partition_golden():
+    """The product's partition bookkeeping, windows answered by the oracle, on the reference's fixture PAFs against
+    tests/golden/golden_partition.json — raw result lists and BED-merged rows (what the device returns) alike."""
+    import hashlib
+    import json
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    pgold = json.load(open(os.path.join(gold, "golden_partition.json")))
+    for fixture in sorted(pgold):
+        oidx = O.Index.from_paf(os.path.join(gold, fixture))
+        names = [oidx.seq_name(i) for i in range(oidx.n_seqs)]
+        lens = np.array([oidx.seq_len(i) for i in range(oidx.n_seqs)], np.uint64)
+        for c in pgold[fixture]["partition"]:
+            kw = c["params"]
+            for bed_rows in ((False, True) if kw["merge_distance"] >= 0 else (False,)):
+                got, windows = step_with_oracle(oidx, lens, names, kw, bed_rows=bed_rows)
+                text = "".join(f"{names[s]}\t{a}\t{b}\t{p}\n" for p, s, a, b in got.rows())
+                assert hashlib.sha256(text.encode()).hexdigest() == c["sha256"], (fixture, kw, bed_rows)
+                assert (len(windows), got.n_partitions) == (c["windows"], c["n_partitions"])
