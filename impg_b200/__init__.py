@@ -935,6 +935,29 @@ def synth_generate_shard(cfg, n_ranks, rank, bidirectional=True):
     return recs[keep], runs[: int(sub_offs[-1])], sub_offs, lens, names, owner
 
 
+def synth_generate_contig(cfg, contig=0):
+    """The alignments of ONE contig of gen_synth. The synthetic world only aligns contig c of one genome with
+    contig c of another, so the trees, hits and transitive closure of a BED row on contig c are the same in
+    this sub-world as in the full index. Returns (records, runs, run_offsets, seq_lens, names); sequence ids
+    are those of the full world."""
+    L = lib()
+    n = L.impgx_synth_num_alignments(C.byref(cfg))
+    recs = np.zeros(n, dtype=RECORD_DTYPE)
+    nr = np.zeros(n, dtype=np.uint32)
+    _check(L.impgx_synth_records(C.byref(cfg), C.c_uint64(0), C.c_uint64(n), _p(recs), _p(nr)))
+    pairs = cfg.genomes * (cfg.genomes - 1)
+    keep = ((np.arange(pairs, dtype=np.uint64)[:, None] * np.uint64(cfg.contigs) + np.uint64(contig))
+            * np.uint64(cfg.tiles) + np.arange(cfg.tiles, dtype=np.uint64)[None, :]).ravel()
+    sub_offs = np.zeros(len(keep) + 1, dtype=np.uint64)
+    np.cumsum(nr[keep], out=sub_offs[1:], dtype=np.uint64)
+    runs = np.zeros(max(int(sub_offs[-1]), 1), dtype=np.uint32)
+    _check(L.impgx_synth_runs_subset(C.byref(cfg), _p(keep), C.c_uint64(len(keep)), _p(sub_offs), _p(runs)))
+    n_seqs = cfg.genomes * cfg.contigs
+    lens = np.full(n_seqs, cfg.contig_len, dtype=np.uint64)
+    names = [f"g{g}#1#c{c}" for g in range(cfg.genomes) for c in range(cfg.contigs)]
+    return recs[keep], runs[: int(sub_offs[-1])], sub_offs, lens, names
+
+
 def synth_bed(cfg, n_rows, seed=2, min_len=1000, max_len=10000):
     out = np.zeros(n_rows, dtype=RANGE_DTYPE)
     _check(lib().impgx_synth_bed(C.byref(cfg), C.c_uint64(seed), C.c_uint64(n_rows), C.c_uint32(min_len),

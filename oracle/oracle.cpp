@@ -1883,6 +1883,33 @@ double orc_run_batch(void *h, const impgx_range *ranges, size_t n, const impgx_p
   return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
 
+// "CPU-batched" driver (second baseline): the same per-row work as orc_run_batch, but the
+// BED rows run in PARALLEL (one OpenMP thread per row, no threads inside a BFS level) — meant for an
+// index built with the CIGARs pre-decoded in RAM (no per-hit pread + parse). It separates what the
+// device path gains from batching rows and keeping the run stream resident from what it gains from
+// the hardware; it is NOT the reference's driver (src/main.rs:7435 is a serial loop).
+double orc_run_batch_rows_parallel(void *h, const impgx_range *ranges, size_t n, const impgx_params *p, int threads,
+                                   int format, uint64_t *n_results, uint64_t *n_out_bytes) {
+  Index *idx = (Index *)h;
+  QParams q = to_qparams(p);
+  uint64_t total = 0, bytes = 0;
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads) reduction(+ : total, bytes)
+  for (size_t i = 0; i < n; i++) {
+    auto res = perform_query(*idx, ranges[i].target_id, ranges[i].start, ranges[i].end, p->mode, q, 1);
+    total += res.size();
+    if (format == 0) {
+      std::string name = "r" + std::to_string(i);
+      bytes += output_results_bed(*idx, res, name, p->merge_distance, p->merge_strands != 0).size();
+    }
+  }
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  if (n_results) *n_results = total;
+  if (n_out_bytes) *n_out_bytes = bytes;
+  return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
 // Batch query returning every row's (optionally BED-merged) results as flat
 // columns, for parity tests against impgx_query_batch[_bed].
 void *orc_query_batch(void *h, const impgx_range *ranges, size_t n, const impgx_params *p, int bed_merge,

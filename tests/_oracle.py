@@ -187,6 +187,7 @@ def lib():
         L.orc_stab_order.restype = C.c_size_t
         L.orc_format.restype = C.c_void_p
         L.orc_run_batch.restype = C.c_double
+        L.orc_run_batch_rows_parallel.restype = C.c_double
         L.orc_index_attach_cigar_file.restype = C.c_int
         L.orc_partition_error.restype = C.c_char_p
         L.orc_partition_len.restype = C.c_size_t
@@ -526,3 +527,12 @@ class Index:
         secs = lib().orc_run_batch(self.h, _p(ranges), C.c_size_t(len(ranges)), C.byref(params), C.c_int(threads),
                                    C.c_int(code), C.byref(nres), C.byref(nbytes), C.byref(csum))
         return secs, nres.value, nbytes.value, csum.value
+
+    def run_batch_rows_parallel(self, ranges, params, threads=1, fmt="bed"):
+        """The "CPU-batched" driver: rows in parallel, one thread per row. Returns (seconds, n_results, out_bytes)."""
+        ranges = np.ascontiguousarray(ranges, dtype=RANGE_DTYPE)
+        code = {None: -1, "bed": 0}[fmt]
+        nres, nbytes = C.c_uint64(0), C.c_uint64(0)
+        secs = lib().orc_run_batch_rows_parallel(self.h, _p(ranges), C.c_size_t(len(ranges)), C.byref(params),
+                                                 C.c_int(threads), C.c_int(code), C.byref(nres), C.byref(nbytes))
+        return secs, nres.value, nbytes.value
