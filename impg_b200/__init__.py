@@ -56,7 +56,8 @@ class Stats(C.Structure):
                 ("lift_touched_bytes", C.c_uint64), ("lift_window_runs", C.c_uint64),
                 ("results", C.c_uint64), ("merged", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("lift_ms", C.c_float), ("stab_ms", C.c_float), ("fold_ms", C.c_float), ("merge_ms", C.c_float),
-                ("total_ms", C.c_float), ("exchange_ms", C.c_float)]
+                ("total_ms", C.c_float), ("exchange_ms", C.c_float), ("merge_kernel_ms", C.c_float),
+                ("reserved0", C.c_float), ("merge_boxes", C.c_uint64), ("exchange_bytes", C.c_uint64)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}

@@ -103,12 +103,32 @@ struct __align__(32) Hit {
 };
 static_assert(sizeof(Hit) == 32, "Hit must be one sector");
 
+// One result of the direct BED path as it sits in its (row, query sequence) bucket: the liftover
+// epilogue writes it, the segment merge reads it once. Row and query sequence are implied by the
+// bucket. 32 bytes = one sector.
+struct __align__(32) BoxRec {
+  uint64_t ord;              // position in the reference's result order of the row (merge_kernels.cuh, make_ord)
+  int32_t q_first, q_last;   // q_first > q_last on the reverse strand
+  uint32_t t_id;
+  int32_t t_first, t_last;
+  uint32_t pad;
+};
+static_assert(sizeof(BoxRec) == 32, "BoxRec must be one sector");
+
+// One merged BED row of a bucket, staged at the bucket's first slots until the rows are compacted.
+struct __align__(4) SegOut {
+  int32_t q_first, q_last;
+  uint32_t t_id;
+  int32_t t_first, t_last;
+};
+
 struct DevIndexView {
   // entry columns, sorted by (target, start), stable in PAF order
   const int32_t *e_start;
   const int32_t *e_end;
   const int32_t *e_pmax;    // running max of e_end within the target
   const EntryRec *e_rec;
+  const uint32_t *e_qid;    // e_rec[i].query_id as a column of its own (bucket counting in the stab scan)
   const uint64_t *tgt_off;  // n_seqs + 1
   const int32_t *seq_len;   // n_seqs
   const uint32_t *stream;   // per alignment: checkpoints, then 8-run blocks (see aln_* helpers)

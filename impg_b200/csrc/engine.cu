@@ -12,6 +12,7 @@
 #include "bfs_kernels.cuh"
 #include "comm.cuh"
 #include "engine.cuh"
+#include "bucket_kernels.cuh"
 #include "merge_kernels.cuh"
 #include "shard_kernels.cuh"
 
@@ -224,6 +225,14 @@ static void exclusive_scan_u64(uint64_t *a, uint64_t n_plus_1, Scratch &sc, cuda
   CUDA_CHECK(cub::DeviceScan::ExclusiveSum(tmp.get(), bytes, a, a, n_plus_1, s));
 }
 
+// exclusive sum over n u32 values into `out` (may alias `in`); the caller appends a zero to get the total
+static void exclusive_scan_u32(const uint32_t *in, uint32_t *out, uint64_t n, Scratch &sc, cudaStream_t s) {
+  size_t bytes = 0;
+  CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, n, s));
+  DBuf<uint8_t> tmp(bytes, *sc.a);
+  CUDA_CHECK(cub::DeviceScan::ExclusiveSum(tmp.get(), bytes, in, out, n, s));
+}
+
 static int bits_for(uint64_t max_value) {
   int b = 1;
   while (b < 64 && (max_value >> b)) b++;
@@ -310,7 +319,7 @@ struct WallTimer {
 impgx_index::~impgx_index() {
   cudaSetDevice(device);
   cudaFree(d_start); cudaFree(d_end); cudaFree(d_pmax); cudaFree(d_seq_len);
-  cudaFree(d_stream); cudaFree(d_rec); cudaFree(d_tgt_off); cudaFree(d_owner);
+  cudaFree(d_stream); cudaFree(d_rec); cudaFree(d_tgt_off); cudaFree(d_owner); cudaFree(d_qid);
 }
 
 namespace impgx {
@@ -372,6 +381,7 @@ impgx_index *index_build(const impgx_record *recs, size_t n, const uint32_t *run
   idx->d_end = upload(hc.e_end, bytes);
   idx->d_pmax = upload(hc.e_pmax, bytes);
   idx->d_rec = upload(hc.e_rec, bytes);
+  idx->d_qid = upload(hc.e_qid, bytes);
   idx->d_tgt_off = upload(hc.tgt_off, bytes);
   std::vector<int32_t> sl(n_seqs);
   for (uint32_t s = 0; s < n_seqs; s++) sl[s] = (int32_t)seq_lens[s];
@@ -506,6 +516,21 @@ struct BedSink {
   bool filled = false;
 };
 
+// (row, query sequence) buckets of the direct BED path (bucket_kernels.cuh): dense tables over
+// rows x n_seqs, the boxes of bucket b at boxes[beg[b] .. cur[b]).
+struct Buckets {
+  uint64_t NB = 0;      // rows x n_seqs
+  DBuf<uint32_t> cnt;   // NB + 1 (the last stays 0): boxes counted per bucket = its capacity
+  DBuf<uint32_t> beg;   // NB + 1: exclusive scan of cnt, beg[NB] = slots in all
+  DBuf<uint32_t> cur;   // NB: fill cursor, starts at beg
+  DBuf<BoxRec> boxes;
+  uint64_t total = 0;
+  uint64_t expect = 0;  // host-side upper bound of the boxes counted so far (the tables are u32)
+  uint32_t level = 0;   // ord level of the hop that fills the buckets directly
+  const uint32_t *gmap = nullptr;  // sharded index: local -> global frontier index of that hop
+  bool laid_out = false;
+};
+
 struct BatchOut {
   // device columns of the assembled results
   DBuf<uint64_t> row_off;
@@ -569,19 +594,30 @@ class Runner {
 
   void prepare(const impgx_range *d_ranges, uint32_t n_rows);
   void lift_core(const DBuf<Frontier> &fr, uint64_t nF, bool closed, bool clip,
-                 const std::function<void(uint64_t)> &alloc_outputs, Lifted &L);
+                 const std::function<void(uint64_t)> &alloc_outputs, Lifted &L, Buckets *bk = nullptr,
+                 const std::function<void()> &bk_after_layout = nullptr);
+  bool bucket_mode(uint32_t n_rows) const;
+  void bk_begin(Buckets &bk, uint32_t n_rows);
+  void bk_layout(Buckets &bk);
+  void bk_add_boxd(Buckets &bk, const BoxD *boxes, uint64_t n, bool scatter);
+  void merge_buckets(Buckets &bk, uint32_t n_rows, BatchOut &out);
+  void merge_oversized(Buckets &bk, const uint32_t *list, uint32_t n_over, uint32_t *out_cnt);
+  void prefix_boxes(BedSink &sink, const impgx_range *d_ranges, uint32_t n_rows, std::vector<LevelHits> &levels,
+                    bool query_mode);
   int bits_a_ = 0, bits_b_ = 0;  // widths of the packed merge keys of this batch
   OutCols alloc_out_cols(BatchOut &out, uint64_t n);
   void stage_a(const BoxD *boxes, uint64_t nB, uint64_t nv, DBuf<BoxD> &acc, DBuf<uint64_t> &is_root);
   void stage_b(const BoxD *acc, const uint64_t *is_root, uint64_t n, unsigned long long *d_root_counter,
-               uint32_t n_rows, BatchOut &out, uint32_t *row_cnt);
+               uint32_t n_rows, BatchOut &out, uint32_t *row_cnt, Buckets *to_buckets = nullptr,
+               uint32_t *bucket_out_cnt = nullptr);
   bool merge_fused(const BoxSrc &src, uint64_t nB, BatchOut &out, uint32_t *row_cnt);
   void materialize_boxes(BedSink &sink);
   void route_boxes(const BoxSrc &src, uint64_t nB, DBuf<BoxD> &recv, uint64_t &n_recv);
   void route_hits(const Lifted &L, const uint32_t *gmap, LevelHits &lvl);
   void global_frontier(DBuf<Frontier> &fr, uint64_t &nF, DBuf<uint32_t> &gmap, uint64_t total,
                        const std::vector<uint64_t> &cnt);
-  void stab_and_lift(const DBuf<Frontier> &fr, uint64_t nF, bool closed, bool clip, BedSink *sink, LevelHits &lvl);
+  void stab_and_lift(const DBuf<Frontier> &fr, uint64_t nF, bool closed, bool clip, BedSink *sink, LevelHits &lvl,
+                     Buckets *bk = nullptr, const std::function<void()> &bk_after_layout = nullptr);
   void bed_merge_direct(BedSink &sink, uint32_t n_rows, BatchOut &out);
   void fold(const LevelHits &lvl, uint32_t n_rows, Visited &V, DBuf<Frontier> &next, uint64_t &n_next,
             bool raw_pieces = false);
@@ -597,7 +633,8 @@ class Runner {
 // order. `alloc_outputs(H)` runs as soon as the hit count is known, before the
 // temporaries, so that what the caller keeps sits below them in the arena.
 void Runner::lift_core(const DBuf<Frontier> &fr_ref, uint64_t nF, bool closed, bool clip,
-                       const std::function<void(uint64_t)> &alloc_outputs, Lifted &L) {
+                       const std::function<void(uint64_t)> &alloc_outputs, Lifted &L, Buckets *bk,
+                       const std::function<void()> &bk_after_layout) {
   L.H = L.n_ok = 0;
   if (nF == 0) return;
   std::unique_ptr<WallTimer> wt(new WallTimer(ctx.w_stab));
@@ -625,8 +662,12 @@ void Runner::lift_core(const DBuf<Frontier> &fr_ref, uint64_t nF, bool closed, b
   L.win.alloc(nF, ar_);
   L.counts.alloc(nF, ar_);
   L.offs.alloc(nF + 1, ar_);
-  if (closed) LAUNCH(k_stab_count<true>, grid_warps(nF), 256, s_, ix_, L.fr, nF, L.win.get(), L.counts.get());
-  else LAUNCH(k_stab_count<false>, grid_warps(nF), 256, s_, ix_, L.fr, nF, L.win.get(), L.counts.get());
+  uint32_t *bcnt = bk ? bk->cnt.get() : nullptr;
+  {
+    auto kern = closed ? (bk ? k_stab_count<true, true> : k_stab_count<true, false>)
+                       : (bk ? k_stab_count<false, true> : k_stab_count<false, false>);
+    LAUNCH(kern, grid_warps(nF), 256, s_, ix_, L.fr, nF, L.win.get(), L.counts.get(), bcnt);
+  }
   CUDA_CHECK(cudaMemsetAsync(L.offs.get() + nF, 0, 8, s_));
   LAUNCH(k_u32_to_u64, grid_threads(nF), 256, s_, L.counts.get(), nF, L.offs.get());
   exclusive_scan_u64(L.offs.get(), nF + 1, sc_, s_);
@@ -636,6 +677,12 @@ void Runner::lift_core(const DBuf<Frontier> &fr_ref, uint64_t nF, bool closed, b
   ctx.stab_ranges += nF;
   ctx.liftovers += H;
   L.H = H;
+  if (bk) {
+    // every hit is counted: bucket offsets, the box array, and the boxes that already exist
+    bk->expect += H;
+    bk_layout(*bk);
+    if (bk_after_layout) bk_after_layout();
+  }
   if (H == 0) {
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     return;
@@ -648,7 +695,7 @@ void Runner::lift_core(const DBuf<Frontier> &fr_ref, uint64_t nF, bool closed, b
   CUDA_CHECK(cudaEventRecord(e1, s_));
   wt.reset(new WallTimer(ctx.w_lift));
 
-  L.hits.alloc(H, ar_);
+  if (!bk) L.hits.alloc(H, ar_);
   if (p_.store_cigar) L.slices.alloc(H, ar_);
   CUDA_CHECK(cudaMemsetAsync(d_counters_.get(), 0, 32, s_));
   LiftParams lp;
@@ -662,9 +709,13 @@ void Runner::lift_core(const DBuf<Frontier> &fr_ref, uint64_t nF, bool closed, b
   lp.row_target = d_row_target_.get();
   // endpoint kernel when neither the clipped CIGAR nor the identity is needed
   const bool ends = !p_.store_cigar && !lp.use_identity && !getenv("IMPGX_FULL_SCAN");
-  if (ends)
-    LAUNCH(k_liftover_ends, grid_threads(H, 256, 8), 256, s_, ix_, L.fr, L.tasks.get(), H, lp, L.hits.get(),
-           d_counters_.get());
+  REQUIRE(ends || !bk, IMPGX_E_CUDA, "internal: the bucket path needs the endpoint liftover");
+  if (ends && bk)
+    LAUNCH(k_liftover_ends<true>, grid_threads(H, 256, 8), 256, s_, ix_, L.fr, L.tasks.get(), H, lp, (Hit *)nullptr,
+           d_counters_.get(), (BucketOut{bk->cur.get(), bk->boxes.get(), L.d_orig, bk->gmap, bk->level}));
+  else if (ends)
+    LAUNCH(k_liftover_ends<false>, grid_threads(H, 256, 8), 256, s_, ix_, L.fr, L.tasks.get(), H, lp, L.hits.get(),
+           d_counters_.get(), BucketOut{});
   else
     LAUNCH(k_liftover, grid_warps(H, 256, 8), 256, s_, ix_, L.fr, L.tasks.get(), H, lp, L.hits.get(), L.slices.get(),
            d_counters_.get());
@@ -700,7 +751,7 @@ void Runner::lift_core(const DBuf<Frontier> &fr_ref, uint64_t nF, bool closed, b
 // (frontier index, visit rank) in lvl, or — last hop of the direct BED path —
 // writes their boxes straight into the sink.
 void Runner::stab_and_lift(const DBuf<Frontier> &fr_ref, uint64_t nF, bool closed, bool clip, BedSink *sink,
-                           LevelHits &lvl) {
+                           LevelHits &lvl, Buckets *bk, const std::function<void()> &bk_after_layout) {
   lvl.n = 0;
   if (nF == 0) return;
   Lifted L;
@@ -712,7 +763,11 @@ void Runner::stab_and_lift(const DBuf<Frontier> &fr_ref, uint64_t nF, bool close
                 lvl.slices.alloc(H, ar_);
               }
             },
-            L);
+            L, bk, bk_after_layout);
+  if (bk) {  // the accepted hits of this hop sit in their buckets
+    if (sink) sink->filled = true;
+    return;
+  }
   const uint64_t H = L.H;
   uint64_t n_ok = L.n_ok;
   if (H == 0) return;
@@ -999,6 +1054,179 @@ void Runner::assemble(const impgx_range *d_ranges, uint32_t n_rows, std::vector<
   }
 }
 
+// seeds, then the levels that were ordered for the fold (their index is their ordinal), as BoxD records
+void Runner::prefix_boxes(BedSink &sink, const impgx_range *d_ranges, uint32_t n_rows, std::vector<LevelHits> &levels,
+                          bool query_mode) {
+  uint64_t held = 0;  // hits held by the ordered levels (BFS hops or DFS rounds)
+  for (auto &l : levels) held += l.n;
+  sink.prefix = (uint64_t)n_rows + held;
+  sink.boxes.alloc(sink.prefix, ar_);
+  if (masked_)  // the self intervals are the seed level below; the per-row seed slots stay invalid
+    CUDA_CHECK(cudaMemsetAsync(sink.boxes.get(), 0, (size_t)n_rows * sizeof(BoxD), s_));
+  else
+    LAUNCH(k_boxes_from_seeds, grid_threads(n_rows), 256, s_, d_ranges, n_rows, p_.min_output_length,
+           query_mode ? 1 : 0, sink.boxes.get(), sink.counters.get(), (const uint32_t *)nullptr, 0u);
+  uint64_t off = n_rows;
+  for (size_t l = 0; l < levels.size(); l++) {
+    if (!levels[l].n) continue;
+    LAUNCH(k_boxes_from_sorted_level, grid_threads(levels[l].n), 256, s_, levels[l].hits.get(), levels[l].n,
+           (uint32_t)l + 1, levels[l].seeds ? -1 : p_.min_output_length, sink.boxes.get() + off, sink.counters.get());
+    off += levels[l].n;
+  }
+}
+
+// ---- (row, query sequence) buckets of the direct BED path (bucket_kernels.cuh)
+bool Runner::bucket_mode(uint32_t n_rows) const {
+  if (getenv("IMPGX_MERGE_SORTED") || getenv("IMPGX_MERGE_GLOBAL") || getenv("IMPGX_BED_GENERIC") || getenv("IMPGX_FULL_SCAN"))
+    return false;  // test / diagnostic switches of the sort-based paths
+  if (comm_) return false;
+  if (p_.store_cigar || !std::isnan(p_.min_identity)) return false;  // the last hop must be the endpoint liftover
+  if (p_.merge_distance < 0 && !p_.merge_strands) return false;      // unsorted output: reference order per row
+  return (uint64_t)n_rows * ix_.n_seqs <= (1ull << 27);
+}
+
+void Runner::bk_begin(Buckets &bk, uint32_t n_rows) {
+  bk.NB = (uint64_t)n_rows * ix_.n_seqs;
+  bk.cnt.alloc(bk.NB + 1, ar_);
+  bk.beg.alloc(bk.NB + 1, ar_);
+  bk.cur.alloc(bk.NB, ar_);
+  CUDA_CHECK(cudaMemsetAsync(bk.cnt.get(), 0, (bk.NB + 1) * 4, s_));
+}
+
+// counts -> bucket offsets, cursors and the box array
+void Runner::bk_layout(Buckets &bk) {
+  REQUIRE(bk.expect < (1ull << 32), IMPGX_E_INVALID, "more than 2^32 results in one batch; lower IMPGX_ROWS_PER_BATCH");
+  exclusive_scan_u32(bk.cnt.get(), bk.beg.get(), bk.NB + 1, sc_, s_);
+  ctx.launches += 2;
+  CUDA_CHECK(cudaMemcpyAsync(bk.cur.get(), bk.beg.get(), bk.NB * 4, cudaMemcpyDeviceToDevice, s_));
+  {
+    uint64_t *h = readback_slot();
+    h[0] = 0;
+    CUDA_CHECK(cudaMemcpyAsync(h, bk.beg.get() + bk.NB, 4, cudaMemcpyDeviceToHost, s_));
+    CUDA_CHECK(cudaStreamSynchronize(s_));
+    ctx.d2h_bytes += 4;
+    bk.total = (uint32_t)h[0];
+  }
+  bk.boxes.alloc(bk.total, ar_);
+  bk.laid_out = true;
+}
+
+// boxes that exist as BoxD records: counted into the buckets (before the layout) / written into them (after it)
+void Runner::bk_add_boxd(Buckets &bk, const BoxD *boxes, uint64_t n, bool scatter) {
+  if (n == 0) return;
+  if (!scatter) bk.expect += n;
+  if (scatter) LAUNCH(k_bucket_scatter_boxd, grid_threads(n), 256, s_, boxes, n, ix_.n_seqs, bk.cur.get(), bk.boxes.get());
+  else LAUNCH(k_bucket_count_boxd, grid_threads(n), 256, s_, boxes, n, ix_.n_seqs, bk.cnt.get());
+}
+
+// Both BED merges, one (row, q) bucket per warp / CTA; the rows come out in (row, q, start) order.
+void Runner::merge_buckets(Buckets &bk, uint32_t n_rows, BatchOut &out) {
+  WallTimer wt(ctx.w_merge);
+  cudaEvent_t e0, e1, k0, k1;
+  CUDA_CHECK(cudaEventCreate(&e0));
+  CUDA_CHECK(cudaEventCreate(&e1));
+  CUDA_CHECK(cudaEventCreate(&k0));
+  CUDA_CHECK(cudaEventCreate(&k1));
+  CUDA_CHECK(cudaEventRecord(e0, s_));
+  out.row_off.alloc((uint64_t)n_rows + 1, ar_);
+  out.n_results = 0;
+  ctx.merge_boxes += bk.total;
+  float kms = 0;
+  if (bk.total == 0) {
+    CUDA_CHECK(cudaMemsetAsync(out.row_off.get(), 0, ((size_t)n_rows + 1) * 8, s_));
+  } else {
+    const uint64_t NB = bk.NB;
+    const uint64_t cap = std::min<uint64_t>(NB, bk.total);
+    DBuf<uint32_t> lists((uint64_t)(SEG_CLASSES + 1) * cap, ar_);
+    DBuf<unsigned int> cls(SEG_CLASSES + 1, ar_);
+    DBuf<uint32_t> out_cnt(NB + 1, ar_), out_off(NB + 1, ar_);
+    CUDA_CHECK(cudaMemsetAsync(cls.get(), 0, (SEG_CLASSES + 1) * 4, s_));
+    CUDA_CHECK(cudaMemsetAsync(out_cnt.get(), 0, (NB + 1) * 4, s_));
+    int min_class = (int)env_u64("IMPGX_SEG_MIN_CLASS", 0);  // test hook: run the larger-bucket kernels on small data
+    if (min_class < 0 || min_class >= SEG_CLASSES) min_class = 0;
+    LAUNCH(k_bucket_classify, grid_threads(NB), 256, s_, bk.beg.get(), bk.cur.get(), NB, lists.get(), cap, cls.get(), min_class);
+    unsigned int hc[SEG_CLASSES + 1];
+    {
+      static_assert(sizeof(hc) <= 32, "class counters must fit the readback slot");
+      uint64_t *h = readback_slot();
+      CUDA_CHECK(cudaMemcpyAsync(h, cls.get(), sizeof(hc), cudaMemcpyDeviceToHost, s_));
+      CUDA_CHECK(cudaStreamSynchronize(s_));
+      memcpy(hc, h, sizeof(hc));
+    }
+    ctx.d2h_bytes += sizeof(hc);
+    const int64_t d = p_.merge_distance;
+    const int ms = p_.merge_strands ? 1 : 0;
+    auto launch = [&](auto kern, unsigned threads, size_t smem, unsigned per_sm, unsigned seg_per_cta, int c) {
+      if (!hc[c]) return;
+      CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const unsigned grid =
+          (unsigned)std::min<uint64_t>(((uint64_t)hc[c] + seg_per_cta - 1) / seg_per_cta, (uint64_t)sm_count() * per_sm);
+      kern<<<grid, threads, smem, s_>>>(bk.boxes.get(), bk.beg.get(), bk.cur.get(), lists.get() + (uint64_t)c * cap, hc[c], d,
+                                        ms, out_cnt.get());
+      CUDA_CHECK(cudaGetLastError());
+      ctx.launches++;
+    };
+    CUDA_CHECK(cudaEventRecord(k0, s_));
+    launch(k_merge_buckets<32, seg_cap(0)>, 256, (size_t)8 * seg_cap(0) * BK_BYTES, 4, 8, 0);
+    launch(k_merge_buckets<32, seg_cap(1)>, 256, (size_t)8 * seg_cap(1) * BK_BYTES, 2, 8, 1);
+    launch(k_merge_buckets<256, seg_cap(2)>, 256, (size_t)seg_cap(2) * BK_BYTES, 8, 1, 2);
+    launch(k_merge_buckets<128, seg_cap(3)>, 128, (size_t)seg_cap(3) * BK_BYTES, 4, 1, 3);
+    launch(k_merge_buckets<512, seg_cap(4)>, 512, (size_t)seg_cap(4) * BK_BYTES, 1, 1, 4);
+    CUDA_CHECK(cudaEventRecord(k1, s_));
+    if (hc[SEG_CLASSES]) merge_oversized(bk, lists.get() + (uint64_t)SEG_CLASSES * cap, hc[SEG_CLASSES], out_cnt.get());
+    exclusive_scan_u32(out_cnt.get(), out_off.get(), NB + 1, sc_, s_);
+    ctx.launches += 2;
+    uint64_t M = 0;
+    {
+      uint64_t *h = readback_slot();
+      h[0] = 0;
+      CUDA_CHECK(cudaMemcpyAsync(h, out_off.get() + NB, 4, cudaMemcpyDeviceToHost, s_));
+      CUDA_CHECK(cudaStreamSynchronize(s_));
+      ctx.d2h_bytes += 4;
+      M = (uint32_t)h[0];
+      cudaEventElapsedTime(&kms, k0, k1);
+    }
+    OutCols oc = alloc_out_cols(out, M);
+    LAUNCH(k_bucket_compact, grid_threads(NB), 256, s_, bk.boxes.get(), bk.beg.get(), out_cnt.get(), out_off.get(), NB,
+           ix_.n_seqs, oc);
+    LAUNCH(k_bucket_row_offsets, grid_threads((uint64_t)n_rows + 1), 256, s_, out_off.get(), n_rows, ix_.n_seqs,
+           out.row_off.get());
+  }
+  CUDA_CHECK(cudaEventRecord(e1, s_));
+  CUDA_CHECK(cudaStreamSynchronize(s_));  // the tables are released on return
+  float msf = 0;
+  cudaEventElapsedTime(&msf, e0, e1);
+  ctx.merge_ms += msf;
+  ctx.merge_kernel_ms += kms;
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(k0); cudaEventDestroy(k1);
+}
+
+// Buckets beyond SEG_MAX boxes — and only those — through the global two-sort merge; their rows land in
+// the same staging slots as the rows of the on-chip merge.
+void Runner::merge_oversized(Buckets &bk, const uint32_t *list, uint32_t n_over, uint32_t *out_cnt) {
+  DBuf<uint64_t> offs((uint64_t)n_over + 1, ar_);
+  CUDA_CHECK(cudaMemsetAsync(offs.get() + n_over, 0, 8, s_));
+  LAUNCH(k_oversized_sizes, grid_threads(n_over), 256, s_, list, n_over, bk.beg.get(), bk.cur.get(), offs.get());
+  exclusive_scan_u64(offs.get(), (uint64_t)n_over + 1, sc_, s_);
+  ctx.launches += 2;
+  const uint64_t n = read_u64(offs.get() + n_over, s_, ctx);
+  DBuf<BoxD> bx(n, ar_);
+  LAUNCH(k_oversized_to_boxd, grid_warps(n_over), 256, s_, list, n_over, offs.get(), bk.boxes.get(), bk.beg.get(), ix_.n_seqs,
+         bx.get());
+  const uint32_t n_rows = (uint32_t)(bk.NB / ix_.n_seqs);
+  const int row_bits = bits_for(n_rows > 1 ? n_rows - 1 : 1);
+  const int seq_bits = bits_for(ix_.n_seqs > 1 ? ix_.n_seqs - 1 : 1);
+  bits_a_ = row_bits + 2 * seq_bits + 1;
+  bits_b_ = row_bits + seq_bits + 33;
+  REQUIRE(bits_a_ <= 63 && bits_b_ <= 63, IMPGX_E_INVALID, "batch too large for the packed merge keys; lower IMPGX_ROWS_PER_BATCH");
+  DBuf<BoxD> acc;
+  DBuf<uint64_t> is_root;
+  DBuf<unsigned long long> rc(2, ar_);
+  stage_a(bx.get(), n, n, acc, is_root);
+  BatchOut none;
+  stage_b(acc.get(), is_root.get(), n, rc.get(), n_rows, none, nullptr, &bk, out_cnt);
+}
+
 void Runner::prepare(const impgx_range *d_ranges, uint32_t n_rows) {
   d_counters_.alloc(4, ar_);
   // validation (perform_query bounds checks)
@@ -1070,13 +1298,31 @@ void Runner::run(const impgx_range *d_ranges, uint32_t n_rows, bool bed, BatchOu
     // MultiImpg order is not (range, visit rank): those levels are always sorted
     if (!direct || multi || nF >= (1ull << 26) || level >= 58) return nullptr;
     sink.prefix = (uint64_t)n_rows + prior;
-    sink.level = level + 1;
+    sink.level = (uint32_t)levels.size() + 1;  // ord level behind the seeds and every ordered level so far
     return &sink;
+  };
+  // Bucket path of the direct BED merge (bucket_kernels.cuh): the boxes that already exist (seeds, ordered
+  // levels) are counted first, the last hop counts its hits while it stabs and writes them into the buckets.
+  const bool buckets = direct && bucket_mode(n_rows);
+  Buckets bk;
+  auto last_hop = [&](bool closed, bool clip, uint32_t level) {
+    BedSink *sk = sink_for(level);
+    if (sk && buckets && nF > 0) {
+      prefix_boxes(sink, d_ranges, n_rows, levels, query_mode);
+      bk_begin(bk, n_rows);
+      bk.level = sink.level;
+      bk_add_boxd(bk, sink.boxes.get(), sink.prefix, /*scatter=*/false);
+      levels.emplace_back();
+      stab_and_lift(fr, nF, closed, clip, sk, levels.back(), &bk,
+                    [&]() { bk_add_boxd(bk, sink.boxes.get(), sink.prefix, /*scatter=*/true); });
+    } else {
+      levels.emplace_back();
+      stab_and_lift(fr, nF, closed, clip, sk, levels.back());
+    }
   };
 
   if (query_mode) {
-    levels.emplace_back();
-    stab_and_lift(fr, nF, /*closed=*/true, /*clip=*/false, sink_for(0), levels.back());
+    last_hop(/*closed=*/true, /*clip=*/false, 0);
   } else {
     // seed: visited[target].insert(range) on an empty set returns the range
     // itself (bounds were validated), which is output and, if long enough,
@@ -1157,8 +1403,12 @@ void Runner::run(const impgx_range *d_ranges, uint32_t n_rows, bool bed, BatchOu
     }
     while (nF > 0 && (p_.max_depth == 0 || depth < p_.max_depth)) {
       const bool last = p_.max_depth != 0 && depth + 1 >= p_.max_depth;
-      levels.emplace_back();
-      stab_and_lift(fr, nF, /*closed=*/false, /*clip=*/true, last ? sink_for(depth) : nullptr, levels.back());
+      if (last) {
+        last_hop(/*closed=*/false, /*clip=*/true, depth);
+      } else {
+        levels.emplace_back();
+        stab_and_lift(fr, nF, /*closed=*/false, /*clip=*/true, nullptr, levels.back());
+      }
       prior += levels.back().n;
       depth++;
       DBuf<Frontier> next;
@@ -1168,27 +1418,23 @@ void Runner::run(const impgx_range *d_ranges, uint32_t n_rows, bool bed, BatchOu
       nF = n_next;
     }
   }
+  if (bk.laid_out) {
+    merge_buckets(bk, n_rows, out);
+    return;
+  }
   if (direct && levels.size() < 60) {
-    WallTimer wt(ctx.w_assemble);
     {
-      uint64_t held = 0;  // hits held by the ordered levels (BFS hops or DFS rounds)
-      for (auto &l : levels) held += l.n;
-      sink.prefix = (uint64_t)n_rows + held;
-      sink.boxes.alloc(sink.prefix, ar_);
+      WallTimer wt(ctx.w_assemble);
+      prefix_boxes(sink, d_ranges, n_rows, levels, query_mode);
       sink.n = sink.prefix + sink.n_raw;
     }
-    // seeds, then the levels that were ordered for the fold (their index is their ordinal)
-    if (masked_)  // the self intervals are the seed level below; the per-row seed slots stay invalid
-      CUDA_CHECK(cudaMemsetAsync(sink.boxes.get(), 0, (size_t)n_rows * sizeof(BoxD), s_));
-    else
-      LAUNCH(k_boxes_from_seeds, grid_threads(n_rows), 256, s_, d_ranges, n_rows, p_.min_output_length,
-             query_mode ? 1 : 0, sink.boxes.get(), sink.counters.get(), (const uint32_t *)nullptr, 0u);
-    uint64_t off = n_rows;
-    for (size_t l = 0; l < levels.size(); l++) {
-      if (!levels[l].n) continue;
-      LAUNCH(k_boxes_from_sorted_level, grid_threads(levels[l].n), 256, s_, levels[l].hits.get(), levels[l].n,
-             (uint32_t)l + 1, levels[l].seeds ? -1 : p_.min_output_length, sink.boxes.get() + off, sink.counters.get());
-      off += levels[l].n;
+    if (buckets && sink.n_raw == 0) {  // no hop wrote into buckets (the walk ended early, or a DFS-like walk)
+      bk_begin(bk, n_rows);
+      bk_add_boxd(bk, sink.boxes.get(), sink.prefix, /*scatter=*/false);
+      bk_layout(bk);
+      bk_add_boxd(bk, sink.boxes.get(), sink.prefix, /*scatter=*/true);
+      merge_buckets(bk, n_rows, out);
+      return;
     }
     bed_merge_direct(sink, n_rows, out);
     return;
@@ -1357,7 +1603,7 @@ void Runner::stage_a(const BoxD *boxes, uint64_t nB, uint64_t nv, DBuf<BoxD> &ac
 // the roots by (row, q, start, strand), sweep per (row, q), compaction into `out`.
 // is_root == nullptr: every box is a root.
 void Runner::stage_b(const BoxD *acc, const uint64_t *is_root, uint64_t n, unsigned long long *d_root_counter,
-                     uint32_t n_rows, BatchOut &out, uint32_t *row_cnt) {
+                     uint32_t n_rows, BatchOut &out, uint32_t *row_cnt, Buckets *to_buckets, uint32_t *bucket_out_cnt) {
   if (n == 0) return;
   const int seq_bits = bits_for(ix_.n_seqs > 1 ? ix_.n_seqs - 1 : 1);
   const int bits_b = bits_b_;
@@ -1385,6 +1631,12 @@ void Runner::stage_b(const BoxD *acc, const uint64_t *is_root, uint64_t n, unsig
   DBuf<uint32_t> cnt(g.G, ar_);
   LAUNCH(k_sweep_direct, grid_threads(g.G, 128, 16), 128, s_, sorted.get(), kb.get(), g.begins.get(), g.G, d, ms ? 1 : 0,
          swept.get(), cnt.get());
+  if (to_buckets) {  // the rows of these (row, q) segments join the staging slots of the bucket merge
+    LAUNCH(k_groups_to_buckets, grid_threads(g.G), 256, s_, swept.get(), g.begins.get(), cnt.get(), g.G, ix_.n_seqs,
+           to_buckets->beg.get(), to_buckets->boxes.get(), bucket_out_cnt);
+    CUDA_CHECK(cudaStreamSynchronize(s_));
+    return;
+  }
   DBuf<uint64_t> scan(g.G + 1, ar_);
   CUDA_CHECK(cudaMemsetAsync(scan.get() + g.G, 0, 8, s_));
   LAUNCH(k_u32_to_u64, grid_threads(g.G), 256, s_, cnt.get(), g.G, scan.get());
@@ -2012,6 +2264,9 @@ impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n
     if (fixed_chunk) return fixed_chunk;
     if (idx->hits_per_row <= 0) return 512;
     double c = target_hits / idx->hits_per_row;
+    // the direct BED path keeps dense tables over rows x sequences (bucket_kernels.cuh)
+    const double table_rows = (double)(1ull << 27) / (double)std::max<uint32_t>(idx->n_seqs, 1u);
+    if (bed && c > table_rows) c = table_rows;
     if (c < 64) c = 64;
     if (c > 4194304) c = 4194304;
     return (size_t)c;
@@ -2046,6 +2301,8 @@ impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n
         total.h2d_bytes += c.h2d_bytes; total.d2h_bytes += c.d2h_bytes;
         total.lift_ms += c.lift_ms; total.stab_ms += c.stab_ms; total.fold_ms += c.fold_ms; total.merge_ms += c.merge_ms;
         total.exch_ms += c.exch_ms;
+        total.merge_boxes += c.merge_boxes;
+        total.merge_kernel_ms += c.merge_kernel_ms;
         total.w_stab += c.w_stab; total.w_lift += c.w_lift; total.w_order += c.w_order; total.w_fold += c.w_fold;
         total.w_assemble += c.w_assemble; total.w_merge += c.w_merge;
         WallTimer wcopy(total.w_copy);
@@ -2187,6 +2444,8 @@ impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n
   st.fold_ms = total.fold_ms;
   st.merge_ms = total.merge_ms;
   st.exchange_ms = total.exch_ms;
+  st.merge_kernel_ms = total.merge_kernel_ms;
+  st.merge_boxes = total.merge_boxes;
   st.total_ms = std::chrono::duration<float, std::milli>(t1 - t0).count();
   if (getenv("IMPGX_TRACE"))
     fprintf(stderr,
@@ -2292,8 +2551,8 @@ void project_batch(int device, size_t n, const int32_t *req_start, const int32_t
   lp.min_output_len = -1;
   if (!out_runs) {
     CUDA_CHECK(cudaMemsetAsync(d_slices.get(), 0, n * sizeof(CigarSlice), s));
-    LAUNCH(k_liftover_ends, grid_threads(n), 256, s, ix, d_fr.get(), d_tasks.get(), (uint64_t)n, lp, d_hits.get(),
-           (unsigned long long *)nullptr);
+    LAUNCH(k_liftover_ends<false>, grid_threads(n), 256, s, ix, d_fr.get(), d_tasks.get(), (uint64_t)n, lp, d_hits.get(),
+           (unsigned long long *)nullptr, BucketOut{});
   } else {
     LAUNCH(k_liftover, grid_warps(n), 256, s, ix, d_fr.get(), d_tasks.get(), (uint64_t)n, lp, d_hits.get(),
            d_slices.get(), (unsigned long long *)nullptr);

@@ -15,6 +15,8 @@ struct Ctx {
   uint64_t launches = 0, lift_launches = 0;
   uint64_t stab_ranges = 0, stab_candidates = 0, liftovers = 0, lift_runs = 0, lift_bytes = 0;
   uint64_t lift_touched = 0, lift_rov = 0;
+  uint64_t merge_boxes = 0;   // boxes that went through the BED merge
+  float merge_kernel_ms = 0;  // device time of the segment-merge launches alone
   uint64_t h2d_bytes = 0, d2h_bytes = 0;
   float lift_ms = 0, stab_ms = 0, fold_ms = 0, merge_ms = 0, exch_ms = 0;
   // host wall-clock per phase (IMPGX_TRACE=1 prints them)

@@ -15,6 +15,7 @@ struct HostColumns {
   std::vector<int32_t> e_start, e_end, e_pmax;
   std::vector<uint32_t> e_vrank;   // also stored in e_rec
   std::vector<uint32_t> e_aln;     // alignment ordinal of each entry (host only, tests)
+  std::vector<uint32_t> e_qid;     // query sequence of each entry (also stored in e_rec)
   std::vector<EntryRec> e_rec;
   std::vector<uint64_t> tgt_off;   // n_seqs + 1
   std::vector<uint32_t> aln_off;   // n_records + 1, stream offset of each alignment in 32-byte sectors
@@ -55,7 +56,7 @@ struct impgx_index {
   std::unordered_map<std::string, uint32_t> name_to_id;
   // device columns
   int32_t *d_start = nullptr, *d_end = nullptr, *d_pmax = nullptr, *d_seq_len = nullptr;
-  uint32_t *d_stream = nullptr;
+  uint32_t *d_stream = nullptr, *d_qid = nullptr;
   impgx::EntryRec *d_rec = nullptr;
   uint64_t *d_tgt_off = nullptr;
   std::mutex mu;  // one query batch at a time per index (handle is thread-safe)
@@ -71,7 +72,7 @@ struct impgx_index {
 
   impgx::DevIndexView view() const {
     impgx::DevIndexView v;
-    v.e_start = d_start; v.e_end = d_end; v.e_pmax = d_pmax; v.e_rec = d_rec;
+    v.e_start = d_start; v.e_end = d_end; v.e_pmax = d_pmax; v.e_rec = d_rec; v.e_qid = d_qid;
     v.tgt_off = d_tgt_off; v.seq_len = d_seq_len; v.stream = d_stream;
     v.n_seqs = n_seqs; v.n_entries = n_entries;
     return v;

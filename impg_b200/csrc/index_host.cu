@@ -131,6 +131,7 @@ void build_host_columns(const impgx_record *recs, size_t n, const uint64_t *run_
   out.e_pmax.resize(E);
   out.e_vrank.resize(E);
   out.e_aln.resize(E);
+  out.e_qid.resize(E);
   out.e_rec.resize(E);
 #pragma omp parallel for schedule(dynamic, 16)
   for (long s = 0; s < (long)n_seqs; s++) {
@@ -159,6 +160,7 @@ void build_host_columns(const impgx_record *recs, size_t n, const uint64_t *run_
       e.vrank = out.e_vrank[k];
       out.e_aln[k] = ri;
       out.e_rec[k] = e;
+      out.e_qid[k] = e.query_id;
       out.e_start[k] = e.t_start;
       out.e_end[k] = e.t_end;
       pm = std::max(pm, e.t_end);

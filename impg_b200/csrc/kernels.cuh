@@ -184,9 +184,12 @@ __device__ __forceinline__ void stab_scan_tiles(const int32_t *__restrict__ col,
   }
 }
 
-template <bool CLOSED>
+// BUCKET: the hop feeds the direct BED path — every hit also counts into its (row, query sequence)
+// bucket (dense table rows x n_seqs), which sizes the buckets the liftover epilogue writes into.
+template <bool CLOSED, bool BUCKET>
 __global__ void __launch_bounds__(32 * STAB_WARPS) k_stab_count(DevIndexView ix, const Frontier *__restrict__ fr, uint64_t n,
-                                                                Window *__restrict__ win, uint32_t *__restrict__ counts) {
+                                                                Window *__restrict__ win, uint32_t *__restrict__ counts,
+                                                                uint32_t *__restrict__ bucket_cnt) {
   __shared__ __align__(16) int32_t tiles[STAB_WARPS][STAB_TILE];
   __shared__ uint64_t bars[STAB_WARPS];
   const unsigned lane = lane_id(), wib = threadIdx.x >> 5;
@@ -199,8 +202,11 @@ __global__ void __launch_bounds__(32 * STAB_WARPS) k_stab_count(DevIndexView ix,
     Frontier f = fr[w];
     Window wd = stab_window<CLOSED>(ix, f.seq, f.start, f.end);
     uint32_t c = 0;
-    stab_scan_tiles(ix.e_end, wd.lb, wd.ub, tiles[wib], &bars[wib], phase, [&](uint64_t, int32_t e, bool live) {
-      c += (live && (CLOSED ? e >= f.start : e > f.start)) ? 1u : 0u;
+    uint32_t *brow = BUCKET ? bucket_cnt + (uint64_t)f.row * ix.n_seqs : nullptr;
+    stab_scan_tiles(ix.e_end, wd.lb, wd.ub, tiles[wib], &bars[wib], phase, [&](uint64_t i, int32_t e, bool live) {
+      const bool hit = live && (CLOSED ? e >= f.start : e > f.start);
+      c += hit ? 1u : 0u;
+      if (BUCKET && hit) atomicAdd(brow + ld_stream_u32(ix.e_qid + i), 1u);
     });
 #pragma unroll
     for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(FULL, c, d);
@@ -652,10 +658,22 @@ __device__ __forceinline__ void ends_last(const EndsAcc &acc, uint32_t op_t0, ui
   l_q = is_ins ? qp + q * dir : (is_del ? qp : pqs + (oe - os) * dir);
 }
 
+// Where the accepted hits of the last hop of the direct BED path go: straight into their
+// (row, query sequence) bucket as 32-byte BoxRecs (slot = atomic cursor of the bucket), so the
+// segment merge reads contiguous memory and no global sort is needed.
+struct BucketOut {
+  uint32_t *cursor;      // rows x n_seqs, initialised with the bucket begins
+  BoxRec *boxes;
+  const uint32_t *orig;  // processing index -> frontier index of the hop, or nullptr
+  const uint32_t *gmap;  // sharded index: local frontier index -> index in the GLOBAL frontier, or nullptr
+  uint32_t level;        // ord level of the hop
+};
+
+template <bool BUCKET>
 __global__ void __launch_bounds__(256, 3) k_liftover_ends(DevIndexView ix, const Frontier *__restrict__ fr,
                                                        const LiftTask *__restrict__ tasks, uint64_t n_tasks,
                                                        LiftParams lp, Hit *__restrict__ hits,
-                                                       unsigned long long *__restrict__ counters) {
+                                                       unsigned long long *__restrict__ counters, BucketOut bo) {
   unsigned long long runs_acc = 0, ok_acc = 0, ck_acc = 0, rov_acc = 0;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_tasks; w += stride) {
@@ -772,16 +790,32 @@ __global__ void __launch_bounds__(256, 3) k_liftover_ends(DevIndexView ix, const
     ck_acc += nck;
     rov_acc += r_ov;
     ok_acc += ok ? 1 : 0;
-    Hit h;
-    h.row = ok ? f.row : INVALID_ID;
-    h.q_id = query_id;
-    h.q_first = f_q;
-    h.q_last = l_q;
-    h.t_id = f.seq;
-    h.t_first = f_t;
-    h.t_last = l_t;
-    h.vrank = vrank;
-    hits[w] = h;
+    if (BUCKET) {
+      if (ok && lp.min_output_len >= 0) {
+        const long long dq = (long long)l_q - (long long)f_q;
+        ok = (dq < 0 ? -dq : dq) >= lp.min_output_len;
+      }
+      if (ok) {
+        uint32_t r = bo.orig ? bo.orig[t.range] : t.range;
+        r = bo.gmap ? bo.gmap[r] : r;
+        const uint32_t slot = atomicAdd(bo.cursor + (uint64_t)f.row * ix.n_seqs + query_id, 1u);
+        const uint64_t ord = ((uint64_t)bo.level << 58) | ((uint64_t)r << 32) | vrank;
+        uint4 *dst = reinterpret_cast<uint4 *>(bo.boxes + slot);
+        dst[0] = make_uint4((uint32_t)ord, (uint32_t)(ord >> 32), (uint32_t)f_q, (uint32_t)l_q);
+        dst[1] = make_uint4(f.seq, (uint32_t)f_t, (uint32_t)l_t, 0u);
+      }
+    } else {
+      Hit h;
+      h.row = ok ? f.row : INVALID_ID;
+      h.q_id = query_id;
+      h.q_first = f_q;
+      h.q_last = l_q;
+      h.t_id = f.seq;
+      h.t_first = f_t;
+      h.t_last = l_t;
+      h.vrank = vrank;
+      hits[w] = h;
+    }
   }
   // one atomic per warp
 #pragma unroll

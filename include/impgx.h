@@ -154,6 +154,10 @@ typedef struct impgx_stats {
   float merge_ms;
   float total_ms;
   float exchange_ms;        /* sharded index: device time of the hit / frontier / box exchanges (CUDA events) */
+  float merge_kernel_ms;    /* device time of the segment-merge launches alone (inside merge_ms) */
+  float reserved0;
+  uint64_t merge_boxes;     /* boxes (results before merging) that went through the BED merge */
+  uint64_t exchange_bytes;  /* sharded index: bytes this rank sent in the exchanges of the call */
 } impgx_stats;
 
 int impgx_abi_version(void);

@@ -489,7 +489,7 @@ def test_full_size_c3_properties_and_sample_parity():
         assert (gc[k] == gc2[k]).all()
     # oracle parity on a sample of rows (the oracle needs seconds per row at this size)
     orc = O.Index.build(recs, runs, offs, lens, names=names)
-    sample = np.array([0, 1234, 5000, 7777, 9999])
+    sample = np.unique(np.linspace(0, 9999, 64).astype(np.int64))
     ores, ooffs = orc.query_batch(bed[sample], o, bed_merge=True)
     oc = ores.columns()
     for j, r in enumerate(sample):
@@ -576,6 +576,17 @@ def test_every_segment_kernel_variant(small, monkeypatch, min_class):
     compare_bed(orc, gpu, b, *params_pair(mode=1, max_depth=0, merge_distance=0, merge_strands=False))
     compare_bed(orc, gpu, b, *params_pair(mode=1, max_depth=3, merge_distance=-1, merge_strands=True))
     compare_bed(orc, gpu, b, *params_pair(mode=0, merge_distance=50000))
+
+
+def test_sort_based_segment_merge_still_matches(small, monkeypatch):
+    """The bucket merge is the default of the direct BED path; IMPGX_MERGE_SORTED selects the older fused merge
+    behind one global sort (still used on a sharded index and with the identity filter)."""
+    cfg, orc, gpu, bed = small
+    monkeypatch.setenv("IMPGX_MERGE_SORTED", "1")
+    b = bed[:150]
+    compare_bed(orc, gpu, b, *params_pair(mode=1, max_depth=2, merge_distance=1000))
+    compare_bed(orc, gpu, b, *params_pair(mode=1, max_depth=0, merge_distance=0, merge_strands=False))
+    compare_bed(orc, gpu, b, *params_pair(mode=0, merge_distance=-1, merge_strands=True))
 
 
 def test_large_segments_and_global_fallback(monkeypatch):

@@ -259,13 +259,11 @@ def test_synth_generate_shard_matches_the_full_generator():
 def test_bench_contig_subworld_is_exact():
     """bench.py times the CPU reference of c4 on the alignments of one contig: rows on that contig
     must give identical results in the sub-world and in the full index."""
-    import sys
-    sys.path.insert(0, ROOT)
-    import bench
     cfg = ix.synth_cfg(6, 3, 60000, 8, 30, 300, 3)
     recs, runs, offs, lens, names = ix.synth_generate(cfg)
     bed = ix.synth_bed(cfg, 120, seed=9, min_len=200, max_len=12000)
-    sr, sruns, soffs, rows = bench.contig_subworld(cfg, recs, runs, offs, bed)
+    sr, sruns, soffs, _, _ = ix.synth_generate_contig(cfg, 0)  # what bench.py's CpuWorld builds for c4
+    rows = bed[bed["target_id"] % cfg.contigs == 0]
     assert len(sr) * 3 == len(recs) and 0 < len(rows) < len(bed)
     full, sub = O.Index.build(recs, runs, offs, lens), O.Index.build(sr, sruns, soffs, lens)
     p = O.make_params(mode=O.MODE_BFS, max_depth=3, store_cigar=True)
