@@ -21,6 +21,7 @@ namespace impgx {
 constexpr int BK_BYTES = 46;  // shared memory per box
 constexpr uint32_t NIL32 = 0xffffffffu;
 constexpr uint32_t NIL16 = 0xffffu;
+constexpr uint32_t SKIP16 = 0xfffeu;  // in `nxt` before stage A: the box is a stage-A result already, it joins no group
 
 // ---- boxes that already exist as BoxD records (seeds, the hops that were ordered for the fold,
 // boxes received from peer ranks) join the buckets through a count and a scatter pass
@@ -38,7 +39,7 @@ __global__ void k_bucket_scatter_boxd(const BoxD *__restrict__ b, uint64_t n, ui
     const uint32_t slot = atomicAdd(cursor + (uint64_t)x.row * n_seqs + x.q_id, 1u);
     uint4 *dst = reinterpret_cast<uint4 *>(boxes + slot);
     dst[0] = make_uint4((uint32_t)x.ord, (uint32_t)(x.ord >> 32), (uint32_t)x.q_lo, (uint32_t)x.q_hi);
-    dst[1] = make_uint4(x.t_id, (uint32_t)x.t_lo, (uint32_t)x.t_hi, 0u);
+    dst[1] = make_uint4(x.t_id, (uint32_t)x.t_lo, (uint32_t)x.t_hi, (x.valid & BOXD_MERGED_A) ? BOX_MERGED_A : 0u);
   }
 }
 
@@ -77,8 +78,10 @@ struct BkMem {
 // One (row, q) bucket per warp (T == 32, eight buckets in flight per CTA) or per CTA. The merged BED rows
 // of bucket `bk` are staged over its own first slots (SegOut records at a BoxRec stride), out_cnt[bk] rows.
 //
-// stage_a == 0: the boxes are stage-A results already (they were merged where they were produced; running
-//   the pairwise relation again on merged boxes would union components that no original pair connects).
+// A box flagged BOX_MERGED_A is a stage-A result already (it was merged where it was produced; testing the
+//   pairwise relation again on merged boxes would union components that no original pair connects): it joins
+//   no (t, strand) group here. The members of one group are all flagged or all raw, because a group is
+//   produced by one rank (the owner of t) in one bucket.
 // reduce == 1 (sharded index, on the rank that PRODUCED the boxes): stage A, then instead of the sweep only
 //   the boxes a sweep over ANY superset of this bucket can still see are kept, as BoxRecs over the bucket's
 //   first slots: in the sweep's sort order (start, !forward, ord) a box D behind a box J with end(J) >= end(D)
@@ -88,7 +91,7 @@ struct BkMem {
 template <int T, int CAP>
 __global__ void __launch_bounds__(T == 32 ? 256 : T)
     k_merge_buckets(BoxRec *__restrict__ boxes, const uint32_t *__restrict__ beg, const uint32_t *__restrict__ cur,
-                    const uint32_t *__restrict__ list, uint32_t n_list, int64_t d, int merge_strands, int stage_a, int reduce,
+                    const uint32_t *__restrict__ list, uint32_t n_list, int64_t d, int merge_strands, int reduce,
                     uint32_t *__restrict__ out_cnt) {
   extern __shared__ __align__(16) unsigned char seg_smem[];
   constexpr int GROUPS = (T == 32) ? 8 : 1;  // buckets in flight per CTA
@@ -119,7 +122,10 @@ __global__ void __launch_bounds__(T == 32 ? 256 : T)
     const uint32_t b = beg[bk], n = cur[bk] - b;
     BoxRec *seg = boxes + b;
     if (n == 1) {
-      if (lt == 0 && reduce) out_cnt[bk] = 1;  // the box stays as it is
+      if (lt == 0 && reduce) {  // the box stays as it is: a group of one
+        seg->flags = BOX_MERGED_A;
+        out_cnt[bk] = 1;
+      }
       if (lt == 0 && !reduce) {
         const uint4 *src = reinterpret_cast<const uint4 *>(seg);
         const uint4 a = src[0], c = src[1];
@@ -149,19 +155,21 @@ __global__ void __launch_bounds__(T == 32 ? 256 : T)
           m.tid[i] = c[u].x; m.tlo[i] = (int32_t)c[u].y; m.thi[i] = (int32_t)c[u].z;
           m.parent[i] = (uint16_t)i;
           m.chain[i] = NIL32;
+          m.nxt[i] = (uint16_t)((c[u].w & BOX_MERGED_A) ? SKIP16 : NIL16);
         }
       }
     }
     if (lt == 0) s_cnt[gi][0] = s_cnt[gi][1] = 0;
     // ---- stage A: (t, strand) groups through a hash table (open addressing, the first box inserted under a key
     // represents its group; every member is chained behind the representative)
-    if (d >= 0 && stage_a) {
+    if (d >= 0) {
       uint32_t TS = 2;
       while (TS < 2 * n) TS <<= 1;  // <= 2 * CAP slots: load factor <= 1/2
       uint32_t *tab = reinterpret_cast<uint32_t *>(m.skey);
       for (uint32_t i = lt; i < TS; i += T) tab[i] = 0u;
       sync();
       for (uint32_t i = lt; i < n; i += T) {
+        if (m.nxt[i] == SKIP16) continue;
         const uint32_t t = m.tid[i];
         const bool fwd = m.qlo[i] <= m.qhi[i];
         uint32_t h = ((((t << 1) | (fwd ? 1u : 0u)) * 2654435761u) >> 7) & (TS - 1);
@@ -408,7 +416,7 @@ __global__ void __launch_bounds__(T == 32 ? 256 : T)
             const uint64_t o = m.ord[c];
             uint4 *dst = reinterpret_cast<uint4 *>(seg + carry_cnt + __popc(bm & lanemask_lt()));
             dst[0] = make_uint4((uint32_t)o, (uint32_t)(o >> 32), (uint32_t)m.qlo[c], (uint32_t)m.qhi[c]);
-            dst[1] = make_uint4(m.tid[c], (uint32_t)m.tlo[c], (uint32_t)m.thi[c], 0u);
+            dst[1] = make_uint4(m.tid[c], (uint32_t)m.tlo[c], (uint32_t)m.thi[c], BOX_MERGED_A);
           }
           carry_pm = __shfl_sync(FULL, pm_in, 31);
           carry_cnt += __popc(bm);
@@ -515,6 +523,10 @@ __global__ void k_oversized_sizes(const uint32_t *__restrict__ list, uint32_t n_
                                   const uint32_t *__restrict__ cur, uint64_t *__restrict__ sizes) {
   for (uint64_t i = gtid(); i < n_list; i += gstride()) sizes[i] = cur[list[i]] - beg[list[i]];
 }
+__global__ void k_oversized_keep(const uint32_t *__restrict__ list, uint32_t n_list, const uint32_t *__restrict__ beg,
+                                 const uint32_t *__restrict__ cur, uint32_t *__restrict__ out_cnt) {
+  for (uint64_t i = gtid(); i < n_list; i += gstride()) out_cnt[list[i]] = cur[list[i]] - beg[list[i]];
+}
 __global__ void k_oversized_to_boxd(const uint32_t *__restrict__ list, uint32_t n_list, const uint64_t *__restrict__ offs,
                                     const BoxRec *__restrict__ boxes, const uint32_t *__restrict__ beg, uint32_t n_seqs,
                                     BoxD *__restrict__ out) {
@@ -529,7 +541,8 @@ __global__ void k_oversized_to_boxd(const uint32_t *__restrict__ list, uint32_t 
     const BoxRec *seg = boxes + beg[bk];
     for (uint64_t i = lane; i < n; i += 32) {
       const BoxRec x = seg[i];
-      out[o0 + i] = BoxD{x.q_first, x.q_last, x.t_first, x.t_last, q, x.t_id, row, 1u, x.ord};
+      out[o0 + i] = BoxD{x.q_first, x.q_last, x.t_first, x.t_last, q, x.t_id, row,
+                         1u | ((x.flags & BOX_MERGED_A) ? BOXD_MERGED_A : 0u), x.ord};
     }
   }
 }

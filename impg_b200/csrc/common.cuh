@@ -111,8 +111,9 @@ struct __align__(32) BoxRec {
   int32_t q_first, q_last;   // q_first > q_last on the reverse strand
   uint32_t t_id;
   int32_t t_first, t_last;
-  uint32_t pad;
+  uint32_t flags;            // BOX_MERGED_A: a stage-A result already (merged on the rank that produced it)
 };
+constexpr uint32_t BOX_MERGED_A = 1u;
 static_assert(sizeof(BoxRec) == 32, "BoxRec must be one sector");
 
 // One merged BED row of a bucket, staged at the bucket's first slots until the rows are compacted.

@@ -319,7 +319,7 @@ struct WallTimer {
 impgx_index::~impgx_index() {
   cudaSetDevice(device);
   cudaFree(d_start); cudaFree(d_end); cudaFree(d_pmax); cudaFree(d_seq_len);
-  cudaFree(d_stream); cudaFree(d_rec); cudaFree(d_tgt_off); cudaFree(d_owner); cudaFree(d_qid);
+  cudaFree(d_stream); cudaFree(d_rec); cudaFree(d_tgt_off); cudaFree(d_owner); cudaFree(d_qid); cudaFree(d_qorder);
 }
 
 namespace impgx {
@@ -391,6 +391,15 @@ impgx_index *index_build(const impgx_record *recs, size_t n, const uint32_t *run
     idx->shard_rank = rank;
     idx->shard_size = n_ranks;
     idx->d_owner = upload(idx->owner, bytes);
+    idx->q_order.resize(n_seqs);
+    idx->q_first.assign((size_t)n_ranks + 1, 0);
+    for (uint32_t s2 = 0; s2 < n_seqs; s2++) idx->q_first[owner[s2] + 1]++;
+    for (uint32_t r = 0; r < n_ranks; r++) idx->q_first[r + 1] += idx->q_first[r];
+    {
+      std::vector<uint32_t> cur(idx->q_first.begin(), idx->q_first.end() - 1);
+      for (uint32_t s2 = 0; s2 < n_seqs; s2++) idx->q_order[cur[owner[s2]]++] = s2;
+    }
+    idx->d_qorder = upload(idx->q_order, bytes);
   }
 
   // stream: per alignment checkpoints + 8-run blocks, built on the device from
@@ -601,6 +610,8 @@ class Runner {
   void bk_layout(Buckets &bk);
   void bk_add_boxd(Buckets &bk, const BoxD *boxes, uint64_t n, bool scatter);
   void merge_buckets(Buckets &bk, uint32_t n_rows, BatchOut &out);
+  float run_bucket_kernels(Buckets &bk, uint32_t *out_cnt, bool reduce);
+  void reduce_and_route(Buckets &bk, uint32_t n_rows, DBuf<BoxD> &recv, uint64_t &n_recv);
   void merge_oversized(Buckets &bk, const uint32_t *list, uint32_t n_over, uint32_t *out_cnt);
   void prefix_boxes(BedSink &sink, const impgx_range *d_ranges, uint32_t n_rows, std::vector<LevelHits> &levels,
                     bool query_mode);
@@ -1079,7 +1090,6 @@ void Runner::prefix_boxes(BedSink &sink, const impgx_range *d_ranges, uint32_t n
 bool Runner::bucket_mode(uint32_t n_rows) const {
   if (getenv("IMPGX_MERGE_SORTED") || getenv("IMPGX_MERGE_GLOBAL") || getenv("IMPGX_BED_GENERIC") || getenv("IMPGX_FULL_SCAN"))
     return false;  // test / diagnostic switches of the sort-based paths
-  if (comm_) return false;
   if (p_.store_cigar || !std::isnan(p_.min_identity)) return false;  // the last hop must be the endpoint liftover
   if (p_.merge_distance < 0 && !p_.merge_strands) return false;      // unsorted output: reference order per row
   return (uint64_t)n_rows * ix_.n_seqs <= (1ull << 27);
@@ -1119,61 +1129,80 @@ void Runner::bk_add_boxd(Buckets &bk, const BoxD *boxes, uint64_t n, bool scatte
   else LAUNCH(k_bucket_count_boxd, grid_threads(n), 256, s_, boxes, n, ix_.n_seqs, bk.cnt.get());
 }
 
+// The bucket kernels over every non-empty bucket: out_cnt[b] = rows (merge) or surviving boxes (reduce) staged
+// over the first slots of bucket b. Returns the device time of the launches.
+float Runner::run_bucket_kernels(Buckets &bk, uint32_t *out_cnt, bool reduce) {
+  const uint64_t NB = bk.NB;
+  const uint64_t cap = std::min<uint64_t>(NB, bk.total);
+  DBuf<uint32_t> lists((uint64_t)(SEG_CLASSES + 1) * cap, ar_);
+  DBuf<unsigned int> cls(SEG_CLASSES + 1, ar_);
+  CUDA_CHECK(cudaMemsetAsync(cls.get(), 0, (SEG_CLASSES + 1) * 4, s_));
+  int min_class = (int)env_u64("IMPGX_SEG_MIN_CLASS", 0);  // test hook: run the larger-bucket kernels on small data
+  if (min_class < 0 || min_class >= SEG_CLASSES) min_class = 0;
+  LAUNCH(k_bucket_classify, grid_threads(NB), 256, s_, bk.beg.get(), bk.cur.get(), NB, lists.get(), cap, cls.get(), min_class);
+  unsigned int hc[SEG_CLASSES + 1];
+  {
+    static_assert(sizeof(hc) <= 32, "class counters must fit the readback slot");
+    uint64_t *h = readback_slot();
+    CUDA_CHECK(cudaMemcpyAsync(h, cls.get(), sizeof(hc), cudaMemcpyDeviceToHost, s_));
+    CUDA_CHECK(cudaStreamSynchronize(s_));
+    memcpy(hc, h, sizeof(hc));
+  }
+  ctx.d2h_bytes += sizeof(hc);
+  const int64_t d = p_.merge_distance;
+  const int ms = p_.merge_strands ? 1 : 0;
+  auto launch = [&](auto kern, unsigned threads, size_t smem, unsigned per_sm, unsigned seg_per_cta, int c) {
+    if (!hc[c]) return;
+    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid =
+        (unsigned)std::min<uint64_t>(((uint64_t)hc[c] + seg_per_cta - 1) / seg_per_cta, (uint64_t)sm_count() * per_sm);
+    kern<<<grid, threads, smem, s_>>>(bk.boxes.get(), bk.beg.get(), bk.cur.get(), lists.get() + (uint64_t)c * cap, hc[c], d,
+                                      ms, reduce ? 1 : 0, out_cnt);
+    CUDA_CHECK(cudaGetLastError());
+    ctx.launches++;
+  };
+  cudaEvent_t k0, k1;
+  CUDA_CHECK(cudaEventCreate(&k0));
+  CUDA_CHECK(cudaEventCreate(&k1));
+  CUDA_CHECK(cudaEventRecord(k0, s_));
+  launch(k_merge_buckets<32, seg_cap(0)>, 256, (size_t)8 * seg_cap(0) * BK_BYTES, 4, 8, 0);
+  launch(k_merge_buckets<32, seg_cap(1)>, 256, (size_t)8 * seg_cap(1) * BK_BYTES, 2, 8, 1);
+  launch(k_merge_buckets<256, seg_cap(2)>, 256, (size_t)seg_cap(2) * BK_BYTES, 8, 1, 2);
+  launch(k_merge_buckets<128, seg_cap(3)>, 128, (size_t)seg_cap(3) * BK_BYTES, 4, 1, 3);
+  launch(k_merge_buckets<512, seg_cap(4)>, 512, (size_t)seg_cap(4) * BK_BYTES, 1, 1, 4);
+  CUDA_CHECK(cudaEventRecord(k1, s_));
+  if (hc[SEG_CLASSES]) {
+    const uint32_t *over = lists.get() + (uint64_t)SEG_CLASSES * cap;
+    if (reduce)  // every box of such a bucket travels as it is (raw: stage A runs where it arrives)
+      LAUNCH(k_oversized_keep, grid_threads(hc[SEG_CLASSES]), 256, s_, over, hc[SEG_CLASSES], bk.beg.get(), bk.cur.get(), out_cnt);
+    else
+      merge_oversized(bk, over, hc[SEG_CLASSES], out_cnt);
+  }
+  CUDA_CHECK(cudaStreamSynchronize(s_));  // the lists are released on return
+  float kms = 0;
+  cudaEventElapsedTime(&kms, k0, k1);
+  cudaEventDestroy(k0);
+  cudaEventDestroy(k1);
+  return kms;
+}
+
 // Both BED merges, one (row, q) bucket per warp / CTA; the rows come out in (row, q, start) order.
 void Runner::merge_buckets(Buckets &bk, uint32_t n_rows, BatchOut &out) {
   WallTimer wt(ctx.w_merge);
-  cudaEvent_t e0, e1, k0, k1;
+  cudaEvent_t e0, e1;
   CUDA_CHECK(cudaEventCreate(&e0));
   CUDA_CHECK(cudaEventCreate(&e1));
-  CUDA_CHECK(cudaEventCreate(&k0));
-  CUDA_CHECK(cudaEventCreate(&k1));
   CUDA_CHECK(cudaEventRecord(e0, s_));
   out.row_off.alloc((uint64_t)n_rows + 1, ar_);
   out.n_results = 0;
   ctx.merge_boxes += bk.total;
-  float kms = 0;
   if (bk.total == 0) {
     CUDA_CHECK(cudaMemsetAsync(out.row_off.get(), 0, ((size_t)n_rows + 1) * 8, s_));
   } else {
     const uint64_t NB = bk.NB;
-    const uint64_t cap = std::min<uint64_t>(NB, bk.total);
-    DBuf<uint32_t> lists((uint64_t)(SEG_CLASSES + 1) * cap, ar_);
-    DBuf<unsigned int> cls(SEG_CLASSES + 1, ar_);
     DBuf<uint32_t> out_cnt(NB + 1, ar_), out_off(NB + 1, ar_);
-    CUDA_CHECK(cudaMemsetAsync(cls.get(), 0, (SEG_CLASSES + 1) * 4, s_));
     CUDA_CHECK(cudaMemsetAsync(out_cnt.get(), 0, (NB + 1) * 4, s_));
-    int min_class = (int)env_u64("IMPGX_SEG_MIN_CLASS", 0);  // test hook: run the larger-bucket kernels on small data
-    if (min_class < 0 || min_class >= SEG_CLASSES) min_class = 0;
-    LAUNCH(k_bucket_classify, grid_threads(NB), 256, s_, bk.beg.get(), bk.cur.get(), NB, lists.get(), cap, cls.get(), min_class);
-    unsigned int hc[SEG_CLASSES + 1];
-    {
-      static_assert(sizeof(hc) <= 32, "class counters must fit the readback slot");
-      uint64_t *h = readback_slot();
-      CUDA_CHECK(cudaMemcpyAsync(h, cls.get(), sizeof(hc), cudaMemcpyDeviceToHost, s_));
-      CUDA_CHECK(cudaStreamSynchronize(s_));
-      memcpy(hc, h, sizeof(hc));
-    }
-    ctx.d2h_bytes += sizeof(hc);
-    const int64_t d = p_.merge_distance;
-    const int ms = p_.merge_strands ? 1 : 0;
-    auto launch = [&](auto kern, unsigned threads, size_t smem, unsigned per_sm, unsigned seg_per_cta, int c) {
-      if (!hc[c]) return;
-      CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      const unsigned grid =
-          (unsigned)std::min<uint64_t>(((uint64_t)hc[c] + seg_per_cta - 1) / seg_per_cta, (uint64_t)sm_count() * per_sm);
-      kern<<<grid, threads, smem, s_>>>(bk.boxes.get(), bk.beg.get(), bk.cur.get(), lists.get() + (uint64_t)c * cap, hc[c], d,
-                                        ms, out_cnt.get());
-      CUDA_CHECK(cudaGetLastError());
-      ctx.launches++;
-    };
-    CUDA_CHECK(cudaEventRecord(k0, s_));
-    launch(k_merge_buckets<32, seg_cap(0)>, 256, (size_t)8 * seg_cap(0) * BK_BYTES, 4, 8, 0);
-    launch(k_merge_buckets<32, seg_cap(1)>, 256, (size_t)8 * seg_cap(1) * BK_BYTES, 2, 8, 1);
-    launch(k_merge_buckets<256, seg_cap(2)>, 256, (size_t)seg_cap(2) * BK_BYTES, 8, 1, 2);
-    launch(k_merge_buckets<128, seg_cap(3)>, 128, (size_t)seg_cap(3) * BK_BYTES, 4, 1, 3);
-    launch(k_merge_buckets<512, seg_cap(4)>, 512, (size_t)seg_cap(4) * BK_BYTES, 1, 1, 4);
-    CUDA_CHECK(cudaEventRecord(k1, s_));
-    if (hc[SEG_CLASSES]) merge_oversized(bk, lists.get() + (uint64_t)SEG_CLASSES * cap, hc[SEG_CLASSES], out_cnt.get());
+    ctx.merge_kernel_ms += run_bucket_kernels(bk, out_cnt.get(), /*reduce=*/false);
     exclusive_scan_u32(out_cnt.get(), out_off.get(), NB + 1, sc_, s_);
     ctx.launches += 2;
     uint64_t M = 0;
@@ -1184,7 +1213,6 @@ void Runner::merge_buckets(Buckets &bk, uint32_t n_rows, BatchOut &out) {
       CUDA_CHECK(cudaStreamSynchronize(s_));
       ctx.d2h_bytes += 4;
       M = (uint32_t)h[0];
-      cudaEventElapsedTime(&kms, k0, k1);
     }
     OutCols oc = alloc_out_cols(out, M);
     LAUNCH(k_bucket_compact, grid_threads(NB), 256, s_, bk.boxes.get(), bk.beg.get(), out_cnt.get(), out_off.get(), NB,
@@ -1197,8 +1225,8 @@ void Runner::merge_buckets(Buckets &bk, uint32_t n_rows, BatchOut &out) {
   float msf = 0;
   cudaEventElapsedTime(&msf, e0, e1);
   ctx.merge_ms += msf;
-  ctx.merge_kernel_ms += kms;
-  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(k0); cudaEventDestroy(k1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
 }
 
 // Buckets beyond SEG_MAX boxes — and only those — through the global two-sort merge; their rows land in
@@ -1999,6 +2027,67 @@ void Runner::route_boxes(const BoxSrc &src, uint64_t nB, DBuf<BoxD> &recv, uint6
       dest, idx, dcnt.get(), nB, recv, n_recv, ar_, sc_, s_, ctx);
 }
 
+// Sharded index, after the last hop: every bucket is reduced where its boxes were produced (stage A + the
+// boxes no sweep can see dropped, bucket_kernels.cuh), what survives travels to the owner of the query
+// sequence (all-to-all-v over the comm), grouped by destination through a destination-major scan.
+void Runner::reduce_and_route(Buckets &bk, uint32_t n_rows, DBuf<BoxD> &recv, uint64_t &n_recv) {
+  WallTimer wt(ctx.w_merge);
+  Comm &cm = *comm_;
+  const int N = cm.size();
+  cudaEvent_t e0, e1, x0, x1;
+  CUDA_CHECK(cudaEventCreate(&e0));
+  CUDA_CHECK(cudaEventCreate(&e1));
+  CUDA_CHECK(cudaEventCreate(&x0));
+  CUDA_CHECK(cudaEventCreate(&x1));
+  CUDA_CHECK(cudaEventRecord(e0, s_));
+  const uint64_t NB = bk.NB;
+  ctx.merge_boxes += bk.total;
+  DBuf<uint32_t> out_cnt(NB + 1, ar_), cv(NB + 1, ar_), sv(NB + 1, ar_);
+  CUDA_CHECK(cudaMemsetAsync(out_cnt.get(), 0, (NB + 1) * 4, s_));
+  if (bk.total) ctx.merge_kernel_ms += run_bucket_kernels(bk, out_cnt.get(), /*reduce=*/true);
+  CUDA_CHECK(cudaMemsetAsync(cv.get() + NB, 0, 4, s_));
+  LAUNCH(k_send_counts, grid_threads(NB), 256, s_, out_cnt.get(), NB, n_rows, ix_.n_seqs, idx_->d_qorder, cv.get());
+  exclusive_scan_u32(cv.get(), sv.get(), NB + 1, sc_, s_);
+  ctx.launches += 2;
+  std::vector<uint32_t> bnd((size_t)N + 1, 0);
+  for (int p = 0; p <= N; p++)
+    CUDA_CHECK(cudaMemcpyAsync(&bnd[p], sv.get() + (uint64_t)idx_->q_first[p] * n_rows, 4, cudaMemcpyDeviceToHost, s_));
+  CUDA_CHECK(cudaStreamSynchronize(s_));
+  ctx.d2h_bytes += ((size_t)N + 1) * 4;
+  std::vector<uint64_t> cnt((size_t)N + 1, 0), send_off((size_t)N, 0), recv_cnt((size_t)N, 0), recv_off((size_t)N, 0);
+  for (int p = 0; p < N; p++) {
+    cnt[p] = bnd[p + 1] - bnd[p];
+    send_off[p] = bnd[p];
+  }
+  const uint64_t n_send = bnd[N];
+  std::vector<uint64_t> all((size_t)N * N);
+  cm.allgather_u64(cnt.data(), (size_t)N, all.data(), s_);
+  uint64_t ro = 0;
+  for (int p = 0; p < N; p++) {
+    recv_cnt[p] = all[(size_t)p * N + cm.rank()];
+    recv_off[p] = ro;
+    ro += recv_cnt[p];
+  }
+  n_recv = ro;
+  REQUIRE(n_recv < (1ull << 32), IMPGX_E_INVALID, "more than 2^32 records received in one exchange; lower IMPGX_ROWS_PER_BATCH");
+  recv.alloc(n_recv, ar_);
+  DBuf<BoxD> send(n_send, ar_);
+  if (n_send)
+    LAUNCH(k_send_copy, grid_threads(NB), 256, s_, bk.boxes.get(), bk.beg.get(), out_cnt.get(), sv.get(), NB, n_rows,
+           ix_.n_seqs, idx_->d_qorder, send.get());
+  CUDA_CHECK(cudaEventRecord(x0, s_));
+  cm.alltoallv(send.get(), cnt.data(), send_off.data(), recv.get(), recv_cnt.data(), recv_off.data(), sizeof(BoxD), s_);
+  CUDA_CHECK(cudaEventRecord(x1, s_));
+  CUDA_CHECK(cudaEventRecord(e1, s_));
+  CUDA_CHECK(cudaStreamSynchronize(s_));  // `send` and the tables are released on return
+  float ms = 0;
+  cudaEventElapsedTime(&ms, x0, x1);
+  ctx.exch_ms += ms;
+  cudaEventElapsedTime(&ms, e0, e1);
+  ctx.merge_ms += ms;
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(x0); cudaEventDestroy(x1);
+}
+
 void Runner::run_sharded(const impgx_range *d_ranges, uint32_t n_rows, BatchOut &out) {
   REQUIRE(comm_ && !idx_->owner.empty() && idx_->d_owner, IMPGX_E_INVALID, "run_sharded needs a shard index and a comm");
   REQUIRE((uint32_t)comm_->size() == idx_->shard_size && (uint32_t)comm_->rank() == idx_->shard_rank, IMPGX_E_INVALID,
@@ -2057,6 +2146,30 @@ void Runner::run_sharded(const impgx_range *d_ranges, uint32_t n_rows, BatchOut 
   uint64_t prior = 0;
   uint32_t depth = 0;
   std::vector<uint64_t> cnt((size_t)N);
+  // the seeds of the rows on owned targets and the boxes of the earlier hops as one BoxD array
+  bool prefix_built = false;
+  auto build_prefix = [&]() {
+    WallTimer wt(ctx.w_assemble);
+    sink.prefix = (uint64_t)n_rows + prior;
+    sink.boxes.alloc(sink.prefix, ar_);
+    sink.n = sink.prefix + sink.n_raw;
+    LAUNCH(k_boxes_from_seeds, grid_threads(n_rows), 256, s_, d_ranges, n_rows, p_.min_output_length, bfs ? 0 : 1,
+           sink.boxes.get(), sink.counters.get(), (const uint32_t *)idx_->d_owner, me);
+    uint64_t off = n_rows;
+    for (size_t l = 0; l < level_boxes.size(); l++) {
+      if (level_n[l])
+        CUDA_CHECK(cudaMemcpyAsync(sink.boxes.get() + off, level_boxes[l].get(), level_n[l] * sizeof(BoxD),
+                                   cudaMemcpyDeviceToDevice, s_));
+      off += level_n[l];
+    }
+    CUDA_CHECK(cudaStreamSynchronize(s_));
+    level_boxes.clear();
+    prefix_built = true;
+  };
+  // bucket path (bucket_kernels.cuh): local buckets, reduced where the boxes are produced, then routed
+  const bool buckets = bucket_mode(n_rows);
+  Buckets bk;
+  bool bk_begun = false;
   for (;;) {
     // every rank learns every rank's frontier size: loop control must agree
     cm.allgather_u64(&nF, 1, cnt.data(), s_);
@@ -2069,6 +2182,19 @@ void Runner::run_sharded(const impgx_range *d_ranges, uint32_t n_rows, BatchOut 
             "global frontier exceeds 2^26 ranges in one batch; lower IMPGX_ROWS_PER_BATCH");
     if (depth > 0) global_frontier(fr, nF, gmap, total, cnt);
     const bool last = !bfs || (p_.max_depth != 0 && depth + 1 >= p_.max_depth);
+    if (last && buckets) {
+      // the last hop counts its hits per (row, q) while it stabs and writes them into the local buckets
+      build_prefix();
+      bk_begin(bk, n_rows);
+      bk_begun = true;
+      bk.level = depth + 1;
+      bk.gmap = gmap.get();
+      bk_add_boxd(bk, sink.boxes.get(), sink.prefix, /*scatter=*/false);
+      Lifted L;
+      lift_core(fr, nF, /*closed=*/!bfs, /*clip=*/bfs, nullptr, L, &bk,
+                [&]() { bk_add_boxd(bk, sink.boxes.get(), sink.prefix, /*scatter=*/true); });
+      break;
+    }
     Lifted L;
     DBuf<BoxD> boxes_h;
     BoxD *dst = nullptr;
@@ -2110,22 +2236,27 @@ void Runner::run_sharded(const impgx_range *d_ranges, uint32_t n_rows, BatchOut 
     fr = std::move(next);
     nF = n_next;
   }
-  {
-    WallTimer wt(ctx.w_assemble);
-    sink.prefix = (uint64_t)n_rows + prior;
-    sink.boxes.alloc(sink.prefix, ar_);
-    sink.n = sink.prefix + sink.n_raw;
-    LAUNCH(k_boxes_from_seeds, grid_threads(n_rows), 256, s_, d_ranges, n_rows, p_.min_output_length, bfs ? 0 : 1,
-           sink.boxes.get(), sink.counters.get(), (const uint32_t *)idx_->d_owner, me);
-    uint64_t off = n_rows;
-    for (size_t l = 0; l < level_boxes.size(); l++) {
-      if (level_n[l])
-        CUDA_CHECK(cudaMemcpyAsync(sink.boxes.get() + off, level_boxes[l].get(), level_n[l] * sizeof(BoxD),
-                                   cudaMemcpyDeviceToDevice, s_));
-      off += level_n[l];
+  if (!prefix_built) build_prefix();
+  if (buckets) {
+    if (!bk_begun) {
+      bk_begin(bk, n_rows);
+      bk_add_boxd(bk, sink.boxes.get(), sink.prefix, /*scatter=*/false);
     }
-    CUDA_CHECK(cudaStreamSynchronize(s_));
-    level_boxes.clear();
+    if (!bk.laid_out) {  // this rank had nothing to lift in the last hop (or the walk ended early)
+      bk_layout(bk);
+      bk_add_boxd(bk, sink.boxes.get(), sink.prefix, /*scatter=*/true);
+    }
+    DBuf<BoxD> recv;
+    uint64_t n_recv = 0;
+    reduce_and_route(bk, n_rows, recv, n_recv);
+    // what arrives is merged like an unsharded batch (stage-A results carry their flag)
+    Buckets fb;
+    bk_begin(fb, n_rows);
+    bk_add_boxd(fb, recv.get(), n_recv, /*scatter=*/false);
+    bk_layout(fb);
+    bk_add_boxd(fb, recv.get(), n_recv, /*scatter=*/true);
+    merge_buckets(fb, n_rows, out);
+    return;
   }
   bed_merge_direct(sink, n_rows, out);
 }

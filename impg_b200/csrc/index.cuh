@@ -69,6 +69,9 @@ struct impgx_index {
   std::vector<uint32_t> owner;
   uint32_t *d_owner = nullptr;
   uint32_t shard_rank = 0, shard_size = 1;
+  // the sequences ordered by (owner, id) and the first position of every rank in that order (n_ranks + 1)
+  std::vector<uint32_t> q_order, q_first;
+  uint32_t *d_qorder = nullptr;
 
   impgx::DevIndexView view() const {
     impgx::DevIndexView v;

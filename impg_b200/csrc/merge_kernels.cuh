@@ -269,9 +269,11 @@ namespace impgx {
 
 struct __align__(16) BoxD {
   int32_t q_lo, q_hi, t_lo, t_hi;
-  uint32_t q_id, t_id, row, valid;
+  uint32_t q_id, t_id, row, valid;  // valid: bit 0 = a result, BOXD_MERGED_A = a stage-A result already
   uint64_t ord;  // position in the reference's result order of the row: level << 58 | (range << 32 | vrank) or index
 };
+
+constexpr uint32_t BOXD_MERGED_A = 2u;
 
 __device__ __forceinline__ uint64_t make_ord(uint32_t level, uint64_t low) { return ((uint64_t)level << 58) | low; }
 
@@ -403,7 +405,9 @@ __global__ void __launch_bounds__(128) k_merge2d_direct(const BoxD *__restrict__
                                                         uint64_t *__restrict__ is_root) {
   for (uint64_t g = gtid(); g < n_groups; g += gstride()) {
     const uint32_t b = begins[g], e = begins[g + 1];
-    if (e - b == 1 || d < 0) {  // singleton (the common case), or merging disabled (:12859)
+    // singleton (the common case), merging disabled (:12859), or a group of stage-A results (merged where
+    // they were produced: all members of a group carry the flag or none does)
+    if (e - b == 1 || d < 0 || (boxes[perm[b]].valid & BOXD_MERGED_A)) {
       for (uint32_t a = b; a < e; a++) {
         acc[a] = boxes[perm[a]];
         is_root[a] = 1;

@@ -5,7 +5,7 @@
 // Lifted hits travel to owner(hit.q_id); the reference's result order travels
 // with them as (global frontier index, coitrees visit rank).
 #pragma once
-#include "merge_kernels.cuh"
+#include "bucket_kernels.cuh"
 
 namespace impgx {
 
@@ -93,6 +93,35 @@ __global__ void k_frontier_take_owned(const Frontier *__restrict__ f, const uint
       out[scan[i]] = f[perm[i]];
       gmap[scan[i]] = (uint32_t)i;
     }
+}
+
+// ---- what survives the local reduction of the buckets (bucket_kernels.cuh, reduce mode) travels to the owner of
+// its query sequence. Destination-major view of the bucket table: v = slot * n_rows + row, slot = position of the
+// query sequence in the list of sequences ordered by (owner, id); the buckets one peer receives are contiguous in v.
+__global__ void k_send_counts(const uint32_t *__restrict__ out_cnt, uint64_t n_buckets, uint32_t n_rows, uint32_t n_seqs,
+                              const uint32_t *__restrict__ qorder, uint32_t *__restrict__ cv) {
+  for (uint64_t v = gtid(); v < n_buckets; v += gstride()) {
+    const uint32_t slot = (uint32_t)(v / n_rows), row = (uint32_t)(v % n_rows);
+    cv[v] = out_cnt[(uint64_t)row * n_seqs + qorder[slot]];
+  }
+}
+__global__ void k_send_copy(const BoxRec *__restrict__ boxes, const uint32_t *__restrict__ beg,
+                            const uint32_t *__restrict__ out_cnt, const uint32_t *__restrict__ sv, uint64_t n_buckets,
+                            uint32_t n_rows, uint32_t n_seqs, const uint32_t *__restrict__ qorder, BoxD *__restrict__ send) {
+  for (uint64_t v = gtid(); v < n_buckets; v += gstride()) {
+    const uint32_t slot = (uint32_t)(v / n_rows), row = (uint32_t)(v % n_rows);
+    const uint32_t q = qorder[slot];
+    const uint64_t b = (uint64_t)row * n_seqs + q;
+    const uint32_t c = out_cnt[b];
+    if (!c) continue;
+    const BoxRec *seg = boxes + beg[b];
+    BoxD *dst = send + sv[v];
+    for (uint32_t k = 0; k < c; k++) {
+      const BoxRec x = seg[k];
+      dst[k] = BoxD{x.q_first, x.q_last, x.t_first, x.t_last, q, x.t_id, row,
+                    1u | ((x.flags & BOX_MERGED_A) ? BOXD_MERGED_A : 0u), x.ord};
+    }
+  }
 }
 
 // valid boxes -> destination rank = owner of the query sequence (invalid ones go nowhere)
