@@ -1,4 +1,5 @@
 // api.cu — the extern "C" boundary (include/impgx.h). No exception crosses it.
+#include <exception>
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -62,7 +63,9 @@ static bool parse_usize(const char *b, const char *e, uint64_t &v) {
   v = 0;
   for (; b < e; b++) {
     if (*b < '0' || *b > '9') return false;
-    v = v * 10 + (uint64_t)(*b - '0');
+    const uint64_t dgt = (uint64_t)(*b - '0');
+    if (v > (UINT64_MAX - dgt) / 10) return false;  // Rust's parse::<usize> fails on overflow, it never wraps
+    v = v * 10 + dgt;
   }
   return true;
 }
@@ -119,8 +122,10 @@ static void parse_paf_parallel(const PafText &data, const std::string &path, Paf
   std::vector<std::vector<uint32_t>> runs_of((size_t)n_threads);
   std::vector<size_t> first_line((size_t)n_threads + 1);
   for (int t = 0; t <= n_threads; t++) first_line[t] = n_lines * (size_t)t / (size_t)n_threads;
+  // an exception (std::bad_alloc of a run buffer) must not leave the OpenMP region: it is kept and rethrown after it
+  std::vector<std::exception_ptr> thread_err((size_t)n_threads);
 #pragma omp parallel for schedule(static, 1) num_threads(n_threads)
-  for (int t = 0; t < n_threads; t++) {
+  for (int t = 0; t < n_threads; t++) try {
     std::vector<uint32_t> &my_runs = runs_of[t];
     {
       // a run takes at least two bytes of text: reserving once spares the growth copies (untouched pages cost nothing)
@@ -172,7 +177,8 @@ static void parse_paf_parallel(const PafText &data, const std::string &path, Paf
         ln.err = "Invalid strand";
         continue;
       }
-      if (!(ln.ql <= INT32_MAX && ln.tl <= INT32_MAX && qe <= INT32_MAX && te <= INT32_MAX)) {
+      if (!(ln.ql <= INT32_MAX && ln.tl <= INT32_MAX && qe <= INT32_MAX && te <= INT32_MAX && qs <= INT32_MAX &&
+            ts <= INT32_MAX)) {
         ln.err = "coordinate beyond 2^31-1";
         continue;
       }
@@ -205,7 +211,11 @@ static void parse_paf_parallel(const PafText &data, const std::string &path, Paf
       ln.cg_rel = rel;
       if (!ln.err && !have) ln.err = "The alignment file does not contain CIGAR strings ('cg:Z' tag)";
     }
+  } catch (...) {
+    thread_err[t] = std::current_exception();
   }
+  for (auto &ep : thread_err)
+    if (ep) std::rethrow_exception(ep);
   for (size_t i = 0; i < n_lines; i++)
     if (lines[i].err)
       throw Error(IMPGX_E_PARSE, std::string(lines[i].err) + " (line " + std::to_string(i + 1) + " of '" + path + "')");
@@ -339,7 +349,8 @@ void parse_paf(const std::string &path, PafData &out) {
     REQUIRE(fld[4].first < fld[4].second, IMPGX_E_PARSE, "Expected '+' or '-' for strand" + where);
     const char sc = *fld[4].first;
     REQUIRE(sc == '+' || sc == '-', IMPGX_E_PARSE, "Invalid strand" + where);
-    REQUIRE(ql <= INT32_MAX && tl <= INT32_MAX && qe <= INT32_MAX && te <= INT32_MAX, IMPGX_E_PARSE,
+    REQUIRE(ql <= INT32_MAX && tl <= INT32_MAX && qe <= INT32_MAX && te <= INT32_MAX && qs <= INT32_MAX && ts <= INT32_MAX,
+            IMPGX_E_PARSE,
             "coordinate beyond 2^31-1" + where);
     impgx_record r;
     r.query_id = get_id(fld[0].first, fld[0].second, ql);

@@ -413,6 +413,9 @@ impgx_index *index_build(const impgx_record *recs, size_t n, const uint32_t *run
     uint32_t *d_raw = nullptr;
     uint64_t *d_off = nullptr;
     uint32_t *d_blk = nullptr;
+    int *d_bad = nullptr;
+    CUDA_CHECK(cudaMalloc((void **)&d_bad, 4));
+    CUDA_CHECK(cudaMemset(d_bad, 0, 4));
     size_t cap_raw = 0, cap_aln = 0;
     std::vector<uint64_t> rel;
     std::vector<uint32_t> blk, stage;
@@ -466,14 +469,18 @@ impgx_index *index_build(const impgx_record *recs, size_t n, const uint32_t *run
         }
         CUDA_CHECK(cudaMemcpy(d_off, rel.data(), (na + 1) * 8, cudaMemcpyHostToDevice));
         CUDA_CHECK(cudaMemcpy(d_blk, blk.data(), na * 4, cudaMemcpyHostToDevice));
-        LAUNCH(k_build_blocks, grid_warps(na), 256, 0, d_raw, d_off, d_blk, (uint64_t)na, idx->d_stream);
+        LAUNCH(k_build_blocks, grid_warps(na), 256, 0, d_raw, d_off, d_blk, (uint64_t)na, idx->d_stream, d_bad);
         CUDA_CHECK(cudaDeviceSynchronize());
       }
       a = b;
     }
+    int bad = 0;
+    cudaMemcpy(&bad, d_bad, 4, cudaMemcpyDeviceToHost);
     cudaFree(d_raw);
     cudaFree(d_off);
     cudaFree(d_blk);
+    cudaFree(d_bad);
+    REQUIRE(bad == 0, IMPGX_E_INVALID, "a CIGAR run carries an op code beyond IMPGX_OP_M (the packing is op << 29 | length, ops = X I D M)");
   }
   idx->device_bytes = bytes;
   return idx.release();
@@ -2673,7 +2680,8 @@ void project_batch(int device, size_t n, const int32_t *req_start, const int32_t
   CUDA_CHECK(cudaMemcpyAsync(d_rec.get(), recs.data(), n * sizeof(EntryRec), cudaMemcpyHostToDevice, s));
   CUDA_CHECK(cudaMemcpyAsync(d_fr.get(), fr.data(), n * sizeof(Frontier), cudaMemcpyHostToDevice, s));
   CUDA_CHECK(cudaMemcpyAsync(d_tasks.get(), tasks.data(), n * sizeof(LiftTask), cudaMemcpyHostToDevice, s));
-  LAUNCH(k_build_blocks, grid_warps(n), 256, s, d_raw.get(), d_off.get(), d_blk.get(), (uint64_t)n, d_stream.get());
+  LAUNCH(k_build_blocks, grid_warps(n), 256, s, d_raw.get(), d_off.get(), d_blk.get(), (uint64_t)n, d_stream.get(),
+         (int *)nullptr);
   DevIndexView ix{};
   ix.e_rec = d_rec.get();
   ix.stream = d_stream.get();

@@ -36,7 +36,9 @@ void merge_consecutive(std::vector<uint32_t> &c) {
   if (c.size() <= 1) return;
   size_t w = 0;
   for (size_t r = 1; r < c.size(); r++) {
-    if (op_of(c[w]) == op_of(c[r])) c[w] = mk(len_of(c[w]) + len_of(c[r]), op_of(c[w]));
+    // a combined length of 2^29 or more would spill into the op bits: such runs stay apart
+    if (op_of(c[w]) == op_of(c[r]) && (int64_t)len_of(c[w]) + len_of(c[r]) < (1ll << 29))
+      c[w] = mk(len_of(c[w]) + len_of(c[r]), op_of(c[w]));
     else c[++w] = c[r];
   }
   c.resize(w + 1);

@@ -167,6 +167,8 @@ static impgx_impg *open_impg(const std::string &path) {
     id_len[id] = r.varint();
   }
   const uint32_t next_id = r.u32();
+  // a crafted next_id must not size the tables: every id below it that is in use costs bytes of this file
+  REQUIRE((uint64_t)next_id <= d.size(), IMPGX_E_PARSE, "next_id larger than the .impg file itself");
   f->names.assign(next_id, std::string());
   f->lens.assign(next_id, 0);
   for (auto &kv : id_name) {

@@ -16,6 +16,7 @@
 #include <cstring>
 #include <fstream>
 #include <iterator>
+#include <filesystem>
 #include <string>
 #include <vector>
 
@@ -130,12 +131,13 @@ static int partition_main(int argc, char **argv) {
   check(impgx_partition(idx, &pp, &parts));
   impgx_partition_view v;
   check(impgx_partitions_view(parts, &v));
+  if (!folder.empty()) {  // --output-folder: created once, without a shell (reference: std::fs::create_dir_all)
+    std::error_code ec;
+    std::filesystem::create_directories(folder, ec);
+    if (ec) die("cannot create " + folder + ": " + ec.message());
+  }
   auto write_file = [&](const std::string &name, int64_t which) {
     std::string path = folder.empty() ? name : folder + "/" + name;
-    if (!folder.empty()) {
-      std::string cmd = "mkdir -p '" + folder + "'";
-      if (system(cmd.c_str()) != 0) die("cannot create " + folder);
-    }
     char *text = impgx_partitions_format_bed(idx, parts, which);
     if (!text) die("formatting failed");
     FILE *f = fopen(path.c_str(), "w");

@@ -77,7 +77,7 @@ __device__ __forceinline__ int warp_incl_scan(int v) {
 __global__ void __launch_bounds__(256) k_build_blocks(const uint32_t *__restrict__ raw,
                                                       const uint64_t *__restrict__ run_off,
                                                       const uint32_t *__restrict__ aln_off, uint64_t n_aln,
-                                                      uint32_t *__restrict__ stream) {
+                                                      uint32_t *__restrict__ stream, int *__restrict__ bad_op) {
   const unsigned lane = lane_id();
   uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(256) k_build_blocks(const uint32_t *__restrict
       const uint32_t v = i < n ? raw[off + i] : 0u;
       if (i < padded) runs[i] = v;
       const uint32_t op = v >> 29, len = v & 0x1fffffffu;
+      if (op > IMPGX_OP_M && bad_op) atomicExch(bad_op, 1);  // not one of = X I D M: the build is rejected
       const int td = op == IMPGX_OP_I ? 0 : (int)len;
       const int qd = op == IMPGX_OP_D ? 0 : (int)len;
       const int ts = warp_incl_scan(td), qs = warp_incl_scan(qd);
