@@ -190,9 +190,20 @@ __global__ void __launch_bounds__(T == 32 ? 256 : T)
         m.nxt[i] = (uint16_t)atomicExch(&m.chain[rep], i);  // NIL32 truncates to NIL16
       }
       sync();
-      for (uint32_t i = lt; i < n; i += T) {
-        const uint32_t c = m.chain[i];
-        if (c != NIL32 && m.nxt[c] != NIL16) m.heads[atomicAdd(&s_cnt[gi][1], 1u)] = (uint16_t)i;
+      for (uint32_t i0 = 0; i0 < n; i0 += T) {  // warp-aggregated append
+        const uint32_t i = i0 + lt;
+        bool is_head = false;
+        if (i < n) {
+          const uint32_t c = m.chain[i];
+          is_head = c != NIL32 && m.nxt[c] != NIL16;
+        }
+        const unsigned bm = __ballot_sync(FULL, is_head);
+        if (bm) {
+          uint32_t wb = 0;
+          if (lane == (unsigned)(__ffs(bm) - 1)) wb = atomicAdd(&s_cnt[gi][1], (unsigned)__popc(bm));
+          wb = __shfl_sync(FULL, wb, __ffs(bm) - 1);
+          if (is_head) m.heads[wb + __popc(bm & lanemask_lt())] = (uint16_t)i;
+        }
       }
       sync();
       const uint32_t nh = s_cnt[gi][1];
@@ -250,8 +261,17 @@ __global__ void __launch_bounds__(T == 32 ? 256 : T)
     }
     sync();
     // ---- roots -> list of box indices (the union-find is done: `heads` and `parent` become scratch)
-    for (uint32_t i = lt; i < n; i += T)
-      if (m.parent[i] == i) m.heads[atomicAdd(&s_cnt[gi][0], 1u)] = (uint16_t)i;
+    for (uint32_t i0 = 0; i0 < n; i0 += T) {  // warp-aggregated append
+      const uint32_t i = i0 + lt;
+      const bool root = i < n && m.parent[i] == i;
+      const unsigned bm = __ballot_sync(FULL, root);
+      if (bm) {
+        uint32_t wb = 0;
+        if (lane == (unsigned)(__ffs(bm) - 1)) wb = atomicAdd(&s_cnt[gi][0], (unsigned)__popc(bm));
+        wb = __shfl_sync(FULL, wb, __ffs(bm) - 1);
+        if (root) m.heads[wb + __popc(bm & lanemask_lt())] = (uint16_t)i;
+      }
+    }
     sync();
     uint32_t nr = s_cnt[gi][0];
     uint16_t *live = m.heads, *spare = m.parent;

@@ -728,13 +728,18 @@ void Runner::lift_core(const DBuf<Frontier> &fr_ref, uint64_t nF, bool closed, b
   // endpoint kernel when neither the clipped CIGAR nor the identity is needed
   const bool ends = !p_.store_cigar && !lp.use_identity && !getenv("IMPGX_FULL_SCAN");
   REQUIRE(ends || !bk, IMPGX_E_CUDA, "internal: the bucket path needs the endpoint liftover");
-  if (ends && bk)
-    LAUNCH(k_liftover_ends<true>, grid_threads(H, 256, 8), 256, s_, ix_, L.fr, L.tasks.get(), H, lp, (Hit *)nullptr,
-           d_counters_.get(), (BucketOut{bk->cur.get(), bk->boxes.get(), L.d_orig, bk->gmap, bk->level}));
-  else if (ends)
-    LAUNCH(k_liftover_ends<false>, grid_threads(H, 256, 8), 256, s_, ix_, L.fr, L.tasks.get(), H, lp, L.hits.get(),
-           d_counters_.get(), BucketOut{});
-  else
+  // A/B switches: the variant with overlapped gathers; 3 or 4 resident CTAs per SM (80 or 64 registers per thread)
+  static const bool pipe = env_u64("IMPGX_LIFT_OVL", 0) != 0;
+  static const bool minb4 = env_u64("IMPGX_LIFT_MINB", 3) == 4;
+  if (ends) {
+    auto kern = bk ? (pipe ? (minb4 ? k_liftover_ends<true, true, 4> : k_liftover_ends<true, true, 3>)
+                           : (minb4 ? k_liftover_ends<true, false, 4> : k_liftover_ends<true, false, 3>))
+                   : (pipe ? (minb4 ? k_liftover_ends<false, true, 4> : k_liftover_ends<false, true, 3>)
+                           : (minb4 ? k_liftover_ends<false, false, 4> : k_liftover_ends<false, false, 3>));
+    const BucketOut bo = bk ? BucketOut{bk->cur.get(), bk->boxes.get(), L.d_orig, bk->gmap, bk->level} : BucketOut{};
+    LAUNCH(kern, grid_threads(H, 256, 8), 256, s_, ix_, L.fr, L.tasks.get(), H, lp, bk ? (Hit *)nullptr : L.hits.get(),
+           d_counters_.get(), bo);
+  } else
     LAUNCH(k_liftover, grid_warps(H, 256, 8), 256, s_, ix_, L.fr, L.tasks.get(), H, lp, L.hits.get(), L.slices.get(),
            d_counters_.get());
   CUDA_CHECK(cudaEventRecord(e2, s_));
@@ -1174,7 +1179,12 @@ float Runner::run_bucket_kernels(Buckets &bk, uint32_t *out_cnt, bool reduce) {
   CUDA_CHECK(cudaEventRecord(k0, s_));
   launch(k_merge_buckets<32, seg_cap(0)>, 256, (size_t)8 * seg_cap(0) * BK_BYTES, 4, 8, 0);
   launch(k_merge_buckets<32, seg_cap(1)>, 256, (size_t)8 * seg_cap(1) * BK_BYTES, 2, 8, 1);
-  launch(k_merge_buckets<256, seg_cap(2)>, 256, (size_t)seg_cap(2) * BK_BYTES, 8, 1, 2);
+  {
+    static const uint64_t t2 = env_u64("IMPGX_BK_T2", 128);  // threads per CTA of the <= 512 class (A/B switch)
+    if (t2 == 64) launch(k_merge_buckets<64, seg_cap(2)>, 64, (size_t)seg_cap(2) * BK_BYTES, 9, 1, 2);
+    else if (t2 == 256) launch(k_merge_buckets<256, seg_cap(2)>, 256, (size_t)seg_cap(2) * BK_BYTES, 8, 1, 2);
+    else launch(k_merge_buckets<128, seg_cap(2)>, 128, (size_t)seg_cap(2) * BK_BYTES, 8, 1, 2);
+  }
   launch(k_merge_buckets<128, seg_cap(3)>, 128, (size_t)seg_cap(3) * BK_BYTES, 4, 1, 3);
   launch(k_merge_buckets<512, seg_cap(4)>, 512, (size_t)seg_cap(4) * BK_BYTES, 1, 1, 4);
   CUDA_CHECK(cudaEventRecord(k1, s_));
@@ -2690,8 +2700,8 @@ void project_batch(int device, size_t n, const int32_t *req_start, const int32_t
   lp.min_output_len = -1;
   if (!out_runs) {
     CUDA_CHECK(cudaMemsetAsync(d_slices.get(), 0, n * sizeof(CigarSlice), s));
-    LAUNCH(k_liftover_ends<false>, grid_threads(n), 256, s, ix, d_fr.get(), d_tasks.get(), (uint64_t)n, lp, d_hits.get(),
-           (unsigned long long *)nullptr, BucketOut{});
+    LAUNCH((k_liftover_ends<false, false, 3>), grid_threads(n), 256, s, ix, d_fr.get(), d_tasks.get(), (uint64_t)n, lp,
+           d_hits.get(), (unsigned long long *)nullptr, BucketOut{});
   } else {
     LAUNCH(k_liftover, grid_warps(n), 256, s, ix, d_fr.get(), d_tasks.get(), (uint64_t)n, lp, d_hits.get(),
            d_slices.get(), (unsigned long long *)nullptr);

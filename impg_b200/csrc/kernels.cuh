@@ -34,6 +34,18 @@ __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t *p) {
   return v;
 }
 
+// Loads of the liftover's software pipeline: volatile, so they are issued where they are written.
+__device__ __forceinline__ uint2 ld_pipe_u2(const void *p) {
+  uint2 v;
+  asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint4 ld_pipe_u4(const void *p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
 // Warp-cooperative partition point: pred is monotone (true...true false...false)
 // over [lo, hi); returns the first index where it is false. 32-ary search: each
 // round every lane probes one position, a ballot narrows the range 32-fold.
@@ -511,22 +523,35 @@ __global__ void __launch_bounds__(256) k_liftover(DevIndexView ix, const Frontie
 // answer and the probes stay inside one or two 32-byte sectors (a plain binary
 // search touched ~7 different sectors per lookup and dominated the DRAM
 // traffic of the kernel).
-__device__ __forceinline__ uint32_t ck_partition(const Checkpoint *__restrict__ ck, bool swap_id, uint32_t lo,
-                                                 uint32_t hi, int64_t x, bool inclusive, uint32_t guess) {
-  if (lo >= hi) return lo;
+// The 32-byte checkpoint sector (4 checkpoints) around a clamped guess; loading it is split from the search so
+// that the sectors of both lookups of a hit can be in flight together.
+struct CkSector {
+  uint4 a, b;
+};
+__device__ __forceinline__ uint32_t ck_clamp(uint32_t guess, uint32_t lo, uint32_t hi) {
+  return guess < lo ? lo : (guess >= hi ? hi - 1 : guess);
+}
+__device__ __forceinline__ CkSector ck_load_sector(const Checkpoint *__restrict__ ck, uint32_t g) {
+  const uint4 *sp = reinterpret_cast<const uint4 *>(ck + (g & ~3u));
+  CkSector s;
+  s.a = ld_pipe_u4(sp);
+  s.b = ld_pipe_u4(sp + 1);
+  return s;
+}
+// `g` = ck_clamp(guess, lo, hi) with lo < hi, `sec` = ck_load_sector(ck, g)
+__device__ __forceinline__ uint32_t ck_partition_s(const Checkpoint *__restrict__ ck, bool swap_id, uint32_t lo,
+                                                   uint32_t hi, int64_t x, bool inclusive, uint32_t g, const CkSector &sec) {
   auto pred = [&](uint32_t i) {
     const Checkpoint v = ck[i];
     const int64_t p = swap_id ? v.q_off : v.t_off;
     return inclusive ? p <= x : p < x;
   };
-  uint32_t g = guess < lo ? lo : (guess >= hi ? hi - 1 : guess);
   {
     // fast path: the whole 32-byte sector of the guess (4 checkpoints; the array is padded to whole
     // sectors with the totals, which keeps it nondecreasing) in one go. If the partition point lies
     // inside it — the common case — no further probe is needed.
     const uint32_t s4 = g & ~3u;
-    const uint4 *sp = reinterpret_cast<const uint4 *>(ck + s4);
-    const uint4 a = sp[0], b = sp[1];
+    const uint4 a = sec.a, b = sec.b;
     const int64_t p0 = swap_id ? a.y : a.x, p1 = swap_id ? a.w : a.z, p2 = swap_id ? b.y : b.x, p3 = swap_id ? b.w : b.z;
     const bool t0 = inclusive ? p0 <= x : p0 < x, t1 = inclusive ? p1 <= x : p1 < x;
     const bool t2 = inclusive ? p2 <= x : p2 < x, t3 = inclusive ? p3 <= x : p3 < x;
@@ -579,6 +604,12 @@ __device__ __forceinline__ uint32_t ck_partition(const Checkpoint *__restrict__ 
   }
   return lo;
 }
+__device__ __forceinline__ uint32_t ck_partition(const Checkpoint *__restrict__ ck, bool swap_id, uint32_t lo,
+                                                 uint32_t hi, int64_t x, bool inclusive, uint32_t guess) {
+  if (lo >= hi) return lo;
+  const uint32_t g = ck_clamp(guess, lo, hi);
+  return ck_partition_s(ck, swap_id, lo, hi, x, inclusive, g, ck_load_sector(ck, g));
+}
 
 struct EndsAcc {
   // the first / last overlapping op of the walk so far: packed run + walk position before it
@@ -590,16 +621,26 @@ struct EndsAcc {
 
 // evaluates the (up to) 8 runs of physical block pb in walk order; only the per-op overlap test runs
 // for every op — the projection arithmetic is done once, by ends_first / ends_last, on the selected ops
-__device__ __forceinline__ void thread_eval_block(const uint32_t *__restrict__ blk, uint32_t n, uint32_t pb, uint32_t op_t0,
+// the two 128-bit halves of physical block pb
+struct RunBlock {
+  uint4 lo, hi;
+};
+__device__ __forceinline__ RunBlock load_block(const uint32_t *__restrict__ blk, uint32_t pb) {
+  const uint4 *src = reinterpret_cast<const uint4 *>(blk + pb * RUNS_PER_BLOCK);
+  RunBlock b;
+  b.lo = ld_pipe_u4(src);
+  b.hi = ld_pipe_u4(src + 1);
+  return b;
+}
+__device__ __forceinline__ void thread_eval_block(const RunBlock &rb, uint32_t n, uint32_t pb, uint32_t op_t0,
                                                   uint32_t op_q0, bool backward, int32_t dir, int32_t tp, int32_t qp,
                                                   int32_t rs, int32_t re, int32_t last_target_pos, EndsAcc &acc) {
   const uint32_t base = pb * RUNS_PER_BLOCK;
   const uint32_t cnt = min((uint32_t)RUNS_PER_BLOCK, n - base);
-  const uint4 *src = reinterpret_cast<const uint4 *>(blk + base);
 #pragma unroll
   for (int c = 0; c < RUNS_PER_BLOCK / 4; c++) {
     const int ci = backward ? RUNS_PER_BLOCK / 4 - 1 - c : c;
-    uint4 v4 = src[ci];
+    uint4 v4 = ci ? rb.hi : rb.lo;
     if (backward) {  // walk order within the chunk is reversed too
       uint32_t t0 = v4.x, t1 = v4.y;
       v4.x = v4.w; v4.y = v4.z; v4.z = t1; v4.w = t0;
@@ -670,8 +711,11 @@ struct BucketOut {
   uint32_t level;        // ord level of the hop
 };
 
-template <bool BUCKET>
-__global__ void __launch_bounds__(256, 3) k_liftover_ends(DevIndexView ix, const Frontier *__restrict__ fr,
+// OVL: the dependent gathers of a hit are issued in two waves instead of four steps — both checkpoint sectors
+// (the end-side guess is absolute instead of relative to the start-side result), then the checkpoints and run
+// blocks of both ends — so a hit waits for three memory round trips (entry, sectors, blocks) instead of five.
+template <bool BUCKET, bool OVL, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_liftover_ends(DevIndexView ix, const Frontier *__restrict__ fr,
                                                        const LiftTask *__restrict__ tasks, uint64_t n_tasks,
                                                        LiftParams lp, Hit *__restrict__ hits,
                                                        unsigned long long *__restrict__ counters, BucketOut bo) {
@@ -722,7 +766,20 @@ __global__ void __launch_bounds__(256, 3) k_liftover_ends(DevIndexView ix, const
       const float scale = __fdividef((float)nblk, (float)(w_tot > 0 ? w_tot : 1));  // only seeds the search
       // walk blocks j in [0, nblk): js = last block starting before rs, je = last block starting at or before L
       uint32_t js, je;
-      if (!backward) {
+      if (OVL) {
+        // both lookups search the same range, so their sectors are requested together. Forward: the point of
+        // (P <= rel_l) over [0, nblk) is the point over [js, nblk) because rel <= rel_l puts it at or above js.
+        const uint32_t lo = backward ? 1u : 0u, hi = backward ? nblk + 1 : nblk;
+        const int64_t x0 = backward ? w_tot - rel : rel, x1 = backward ? w_tot - rel_l : rel_l;
+        const uint32_t g0 = ck_clamp(x0 > 0 ? (uint32_t)((float)x0 * scale) : 0u, lo, hi);
+        const uint32_t g1 = ck_clamp((x1 > 0 ? (uint32_t)((float)x1 * scale) : 0u) + (backward ? 0u : 1u), lo, hi);
+        const CkSector s0 = ck_load_sector(ck, g0), s1 = ck_load_sector(ck, g1);
+        const uint32_t p0 = ck_partition_s(ck, swap_id, lo, hi, x0, backward, g0, s0);
+        const uint32_t p1 = ck_partition_s(ck, swap_id, lo, hi, x1, !backward, g1, s1);
+        const uint32_t a = backward ? nblk - (p0 - 1) : p0, b = backward ? nblk - (p1 - 1) : p1;
+        js = a ? a - 1 : 0;
+        je = b ? b - 1 : 0;
+      } else if (!backward) {
         const uint32_t g0 = rel > 0 ? (uint32_t)((float)rel * scale) : 0u;
         const uint32_t a = ck_partition(ck, swap_id, 0, nblk, rel, false, g0);
         js = a ? a - 1 : 0;
@@ -742,14 +799,34 @@ __global__ void __launch_bounds__(256, 3) k_liftover_ends(DevIndexView ix, const
       nck = 8;  // ~2 sectors of checkpoints per lookup (galloping from an interpolated guess)
       // ---- start side: walk forward from block js until the first overlap (or the loop break)
       uint32_t j = js;
+      // OVL: the checkpoint and the run block of the end side are requested together with those of the start side
+      const uint32_t jl0 = je > js ? je : js;
+      uint2 kE = make_uint2(0, 0);
+      RunBlock rbE;
+      rbE.lo = rbE.hi = make_uint4(0, 0, 0, 0);
+      uint2 kS = make_uint2(0, 0);
+      RunBlock rbS;
+      rbS.lo = rbS.hi = make_uint4(0, 0, 0, 0);
+      if (OVL) {
+        const uint32_t pbs = backward ? nblk - 1 - js : js;
+        kS = ld_pipe_u2(backward ? ck + pbs + 1 : ck + pbs);
+        rbS = load_block(blk, pbs);
+        if (jl0 != js) {
+          const uint32_t pbe = backward ? nblk - 1 - jl0 : jl0;
+          kE = ld_pipe_u2(backward ? ck + pbe + 1 : ck + pbe);
+          rbE = load_block(blk, pbe);
+        }
+      }
       for (;;) {
         const uint32_t pb = backward ? nblk - 1 - j : j;
-        const Checkpoint k = backward ? ck[pb + 1] : ck[pb];
-        const int64_t pt = swap_id ? k.q_off : k.t_off, pq = swap_id ? k.t_off : k.q_off;
+        const bool pre = OVL && j == js;
+        const uint2 kk = pre ? kS : ld_pipe_u2(backward ? ck + pb + 1 : ck + pb);
+        const int64_t pt = swap_id ? kk.y : kk.x, pq = swap_id ? kk.x : kk.y;
         const int64_t tcons = backward ? w_tot - pt : pt, qcons = backward ? wq_tot - pq : pq;
         const int32_t tp0 = (int32_t)(t_start + tcons);
         const int32_t qp0 = rev_strand ? (int32_t)(q_end - qcons) : (int32_t)(q_start + qcons);
-        thread_eval_block(blk, n, pb, op_t0, op_q0, backward, dir, tp0, qp0, rs, re, last_target_pos, acc);
+        const RunBlock rb = pre ? rbS : load_block(blk, pb);
+        thread_eval_block(rb, n, pb, op_t0, op_q0, backward, dir, tp0, qp0, rs, re, last_target_pos, acc);
         nread += RUNS_PER_BLOCK;
         if (acc.found || acc.broke || j + 1 >= nblk) break;
         j++;
@@ -762,18 +839,20 @@ __global__ void __launch_bounds__(256, 3) k_liftover_ends(DevIndexView ix, const
         ends_last(acc, op_t0, op_q0, dir, rs, re, last_target_pos, l_q, l_t);
         while (jl > j) {
           const uint32_t pb = backward ? nblk - 1 - jl : jl;
-          const Checkpoint k = backward ? ck[pb + 1] : ck[pb];
-          const int64_t pt = swap_id ? k.q_off : k.t_off, pq = swap_id ? k.t_off : k.q_off;
+          const bool pre = OVL && jl == jl0 && jl0 != js;
+          const uint2 kk = pre ? kE : ld_pipe_u2(backward ? ck + pb + 1 : ck + pb);
+          const int64_t pt = swap_id ? kk.y : kk.x, pq = swap_id ? kk.x : kk.y;
           const int64_t tcons = backward ? w_tot - pt : pt, qcons = backward ? wq_tot - pq : pq;
           const int32_t tp0 = (int32_t)(t_start + tcons);
           const int32_t qp0 = rev_strand ? (int32_t)(q_end - qcons) : (int32_t)(q_start + qcons);
+          const RunBlock rb = pre ? rbE : load_block(blk, pb);
           EndsAcc a2;
           a2.f_v = a2.l_v = 0;
           a2.f_tp = a2.f_qp = a2.l_tp = a2.l_qp = 0;
           a2.n_ov = 0;
           a2.found = false;
           a2.broke = false;
-          thread_eval_block(blk, n, pb, op_t0, op_q0, backward, dir, tp0, qp0, rs, re, last_target_pos, a2);
+          thread_eval_block(rb, n, pb, op_t0, op_q0, backward, dir, tp0, qp0, rs, re, last_target_pos, a2);
           nread += RUNS_PER_BLOCK;
           if (a2.found) {
             ends_last(a2, op_t0, op_q0, dir, rs, re, last_target_pos, l_q, l_t);
