@@ -108,6 +108,47 @@ def make_partition_params(window_size, merge_distance, starting_seqs=None, selec
     return p
 
 
+class RefineParams(C.Structure):
+    """impgx_refine_params (include/impgx.h): the options of `impg refine` (reference src/main.rs:4411-4450)."""
+    _fields_ = [("span_bp", C.c_int32), ("extension_step", C.c_int32), ("max_extension", C.c_double),
+                ("support_level", C.c_uint32), ("merge_distance", C.c_int32), ("min_identity", C.c_double),
+                ("transitive", C.c_uint32), ("max_depth", C.c_uint32), ("min_transitive_len", C.c_int32),
+                ("min_distance_between_ranges", C.c_int32), ("subset_mask", C.c_void_p),
+                ("blacklist_offsets", C.c_void_p), ("blacklist_ranges", C.c_void_p)]
+
+
+class RefineView(C.Structure):
+    _fields_ = [("n", C.c_size_t), ("refined_start", C.c_void_p), ("refined_end", C.c_void_p),
+                ("original_start", C.c_void_p), ("original_end", C.c_void_p), ("applied_left_extension", C.c_void_p),
+                ("applied_right_extension", C.c_void_p), ("support_count", C.c_void_p),
+                ("original_support_count", C.c_void_p), ("entity_offsets", C.c_void_p), ("entity_seq", C.c_void_p),
+                ("entity_start", C.c_void_p), ("entity_end", C.c_void_p), ("candidates_evaluated", C.c_uint64),
+                ("batches", C.c_uint64)]
+
+
+def make_refine_params(span_bp=1000, max_extension=0.5, extension_step=1000, support_level=0, merge_distance=0,
+                       min_identity=None, transitive=0, max_depth=2, min_transitive_len=101,
+                       min_distance_between_ranges=10, subset_mask=None, blacklist=None, n_seqs=None):
+    """`blacklist`: {seq_id: [(start, end), ...]} as the blacklist BED gives them (needs n_seqs)."""
+    p = RefineParams()
+    p.span_bp, p.extension_step, p.max_extension = span_bp, extension_step, max_extension
+    p.support_level, p.merge_distance = support_level, merge_distance
+    p.min_identity = float("nan") if min_identity is None else min_identity
+    p.transitive, p.max_depth = transitive, max_depth
+    p.min_transitive_len, p.min_distance_between_ranges = min_transitive_len, min_distance_between_ranges
+    keep = []
+    if subset_mask is not None:
+        m = np.ascontiguousarray(subset_mask, np.uint8)
+        keep.append(m)
+        p.subset_mask = m.ctypes.data
+    if blacklist is not None:
+        offs, rng = mask_csr(blacklist, n_seqs)
+        keep += [offs, rng]
+        p.blacklist_offsets, p.blacklist_ranges = offs.ctypes.data, rng.ctypes.data
+    p._keep = keep
+    return p
+
+
 class SynthCfg(C.Structure):
     _fields_ = [("genomes", C.c_uint32), ("contigs", C.c_uint32), ("contig_len", C.c_uint32), ("tiles", C.c_uint32),
                 ("eq_mean", C.c_uint32), ("rev_permille", C.c_uint32), ("seed", C.c_uint64)]
@@ -406,6 +447,53 @@ class Impg:
         _check(lib().impgx_query_batch_bed_sharded_device(self.h, comm.h, C.c_void_p(d_ranges_ptr), C.c_size_t(n),
                                                           C.byref(params), C.c_void_p(stream), C.byref(h)))
         return Results(h.value, on_device=True)
+
+    # -- refine and its cache entry points (reference src/commands/refine.rs, src/impg.rs:1930-2035)
+    def populate_cigar_cache(self, target_id, range_start, range_end):
+        """Number of CIGARs Impg::populate_cigar_cache would cache for the range (they are resident in HBM here)."""
+        n = C.c_uint64()
+        _check(lib().impgx_populate_cigar_cache(self.h, C.c_uint32(target_id), C.c_int32(range_start), C.c_int32(range_end),
+                                                C.byref(n)))
+        return n.value
+
+    def query_with_cache_batch(self, target_id, orig_start, orig_end, left, right, params):
+        """Impg::query_with_cache for every (left, right) flank pair of one locus, as one batch."""
+        left = np.ascontiguousarray(left, np.int32)
+        right = np.ascontiguousarray(right, np.int32)
+        h = C.c_void_p()
+        _check(lib().impgx_query_with_cache_batch(self.h, C.c_uint32(target_id), C.c_int32(orig_start), C.c_int32(orig_end),
+                                                  _p(left), _p(right), C.c_size_t(len(left)), C.byref(params), C.byref(h)))
+        return Results(h.value)
+
+    def refine(self, loci, params):
+        """run_refine over RANGE_DTYPE loci: list of dict records (RefineRecord) + (candidates, batches)."""
+        loci = np.ascontiguousarray(loci, dtype=RANGE_DTYPE)
+        h = C.c_void_p()
+        _check(lib().impgx_refine(self.h, _p(loci), C.c_size_t(len(loci)), C.byref(params), C.byref(h)))
+        try:
+            v = RefineView()
+            _check(lib().impgx_refine_view_get(h, C.byref(v)))
+            arr = Results._arr
+            n = v.n
+            cols = {k: arr(None, getattr(v, k), n, np.int32).copy() for k in
+                    ("refined_start", "refined_end", "original_start", "original_end", "applied_left_extension",
+                     "applied_right_extension")}
+            sup = arr(None, v.support_count, n, np.uint64).copy()
+            osup = arr(None, v.original_support_count, n, np.uint64).copy()
+            eo = arr(None, v.entity_offsets, n + 1, np.uint64).copy()
+            ne = int(eo[-1]) if n else 0
+            es = arr(None, v.entity_seq, ne, np.uint32).copy()
+            ea = arr(None, v.entity_start, ne, np.int32).copy()
+            eb = arr(None, v.entity_end, ne, np.int32).copy()
+            recs = []
+            for i in range(n):
+                a, b = int(eo[i]), int(eo[i + 1])
+                recs.append(dict({k: int(c[i]) for k, c in cols.items()}, support_count=int(sup[i]),
+                                 original_support_count=int(osup[i]),
+                                 support_entities=list(zip(es[a:b].tolist(), ea[a:b].tolist(), eb[a:b].tolist()))))
+            return recs, (int(v.candidates_evaluated), int(v.batches))
+        finally:
+            lib().impgx_refine_results_free(h)
 
     def stats(self):
         s = Stats()

@@ -320,6 +320,7 @@ impgx_index::~impgx_index() {
   cudaSetDevice(device);
   cudaFree(d_start); cudaFree(d_end); cudaFree(d_pmax); cudaFree(d_seq_len);
   cudaFree(d_stream); cudaFree(d_rec); cudaFree(d_tgt_off); cudaFree(d_owner); cudaFree(d_qid); cudaFree(d_qorder);
+  for (cudaStream_t st : stream_pool) cudaStreamDestroy(st);
 }
 
 namespace impgx {
@@ -574,8 +575,8 @@ struct Lifted {
 
 class Runner {
  public:
-  Runner(impgx_index *idx, const impgx_params &p, cudaStream_t s, Comm *comm = nullptr)
-      : idx_(idx), p_(p), s_(s), ix_(idx->view()), ar_(idx->arena), comm_(comm) {
+  Runner(impgx_index *idx, const impgx_params &p, cudaStream_t s, Arena &arena, Comm *comm = nullptr)
+      : idx_(idx), p_(p), s_(s), ix_(idx->view()), ar_(arena), comm_(comm) {
     sc_.a = &ar_;
   }
 
@@ -2358,6 +2359,35 @@ void Runner::run_dfs(const impgx_range *d_ranges, uint32_t n_rows, DBuf<Frontier
 }
 
 // ============================================================ batch driver
+// Scratch of one call: an arena and (host entry points) a stream of its own, leased from the index.
+struct CallScratch {
+  impgx_index *idx;
+  std::unique_ptr<Arena> arena;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  CallScratch(impgx_index *i, bool want_stream) : idx(i), own_stream(want_stream) {
+    {
+      std::lock_guard<std::mutex> lock(idx->mu);
+      if (!idx->arena_pool.empty()) {
+        arena = std::move(idx->arena_pool.back());
+        idx->arena_pool.pop_back();
+      }
+      if (own_stream && !idx->stream_pool.empty()) {
+        stream = idx->stream_pool.back();
+        idx->stream_pool.pop_back();
+      }
+    }
+    if (!arena) arena.reset(new Arena());
+    if (own_stream && !stream) CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  }
+  ~CallScratch() {
+    arena->reset();
+    std::lock_guard<std::mutex> lock(idx->mu);
+    idx->arena_pool.push_back(std::move(arena));
+    if (own_stream && stream) idx->stream_pool.push_back(stream);
+  }
+};
+
 struct TooManyHits {};
 
 static uint64_t env_u64(const char *name, uint64_t dflt) {
@@ -2373,9 +2403,12 @@ impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n
   REQUIRE(ranges || n == 0, IMPGX_E_INVALID, "ranges is NULL");
   REQUIRE(p.mode <= IMPGX_MODE_MULTI_DFS, IMPGX_E_INVALID, "unknown mode");
   REQUIRE(p.max_depth <= 65535, IMPGX_E_INVALID, "max_depth is a u16 in the reference");
-  std::lock_guard<std::mutex> lock(idx->mu);
   check_device(idx->device);
-  cudaStream_t s = (cudaStream_t)stream;
+  // a call with host buffers on both sides and no caller stream runs on a stream of its own, so that concurrent
+  // callers overlap; the device entry points stay on the stream they were given (0 = the legacy default stream)
+  CallScratch scratch(idx, /*want_stream=*/!ranges_on_device && results_to_host && stream == nullptr);
+  Arena &arena = *scratch.arena;
+  cudaStream_t s = scratch.own_stream ? scratch.stream : (cudaStream_t)stream;
   auto t0 = std::chrono::steady_clock::now();
 
   std::unique_ptr<impgx_results> res(new impgx_results());
@@ -2408,10 +2441,15 @@ impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n
   // figure is learned from the first, small batch and kept on the index.
   const size_t fixed_chunk = (size_t)env_u64("IMPGX_ROWS_PER_BATCH", 0);
   const double target_hits = (double)env_u64("IMPGX_HITS_PER_BATCH", 200000000ull);
+  double hits_per_row;
+  {
+    std::lock_guard<std::mutex> lock(idx->mu);
+    hits_per_row = idx->hits_per_row;
+  }
   auto next_chunk = [&]() -> size_t {
     if (fixed_chunk) return fixed_chunk;
-    if (idx->hits_per_row <= 0) return 512;
-    double c = target_hits / idx->hits_per_row;
+    if (hits_per_row <= 0) return 512;
+    double c = target_hits / hits_per_row;
     // the direct BED path keeps dense tables over rows x sequences (bucket_kernels.cuh)
     const double table_rows = (double)(1ull << 27) / (double)std::max<uint32_t>(idx->n_seqs, 1u);
     if (bed && c > table_rows) c = table_rows;
@@ -2431,13 +2469,13 @@ impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n
         if (ranges_on_device) {
           d_r = ranges + done;
         } else {
-          d_stage.alloc(m, idx->arena);
+          d_stage.alloc(m, arena);
           CUDA_CHECK(cudaMemcpyAsync(d_stage.get(), ranges + done, m * sizeof(impgx_range), cudaMemcpyHostToDevice, s));
           total.h2d_bytes += m * sizeof(impgx_range);
           d_r = d_stage.get();
         }
         BatchOut bo;
-        Runner runner(idx, p, s, comm);
+        Runner runner(idx, p, s, arena, comm);
         if (comm) runner.run_sharded(d_r, (uint32_t)m, bo);
         else runner.run(d_r, (uint32_t)m, bed, bo);
         const Ctx &c = runner.ctx;
@@ -2515,21 +2553,25 @@ impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n
         res_base += R;
       }
       // every arena block of this batch is out of scope and the stream is idle
-      idx->arena.reset();
+      arena.reset();
       if (comm) {
         // every rank must cut the same row batches: size them by the busiest rank
         std::vector<uint64_t> all((size_t)comm->size());
         comm->allgather_u64(&chunk_hits, 1, all.data(), s);
         chunk_hits = *std::max_element(all.begin(), all.end());
       }
-      idx->hits_per_row = std::max(idx->hits_per_row * 0.9, (double)chunk_hits / (double)m + 1.0);
+      hits_per_row = std::max(hits_per_row * 0.9, (double)chunk_hits / (double)m + 1.0);
+      {
+        std::lock_guard<std::mutex> lock(idx->mu);
+        idx->hits_per_row = hits_per_row;
+      }
       done += m;
     }
   } catch (...) {
     if (comm) comm->abort();  // release peers blocked in an exchange
     cudaStreamSynchronize(s);
     free_chunks();
-    idx->arena.reset();
+    arena.reset();
     throw;
   }
   res->n_results = res_base;
@@ -2573,8 +2615,7 @@ impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n
   }
 
   auto t1 = std::chrono::steady_clock::now();
-  impgx_stats &st = idx->last;
-  st = impgx_stats{};
+  impgx_stats st = impgx_stats{};
   st.kernel_launches = total.launches - std::min(total.launches, tl_small_scans);
   st.stab_ranges = total.stab_ranges;
   st.liftovers = total.liftovers;
@@ -2601,8 +2642,34 @@ impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n
             "copy %.2f | dev: stab %.2f lift %.2f fold %.2f merge %.2f | launches %llu | arena %.2f GB peak %.2f GB\n",
             n, st.total_ms, total.w_stab, total.w_lift, total.w_order, total.w_fold, total.w_assemble, total.w_merge,
             total.w_copy, st.stab_ms, st.lift_ms, st.fold_ms, st.merge_ms, (unsigned long long)st.kernel_launches,
-            idx->arena.capacity() / 1e9, idx->arena.peak() / 1e9);
+            arena.capacity() / 1e9, arena.peak() / 1e9);
+  {
+    std::lock_guard<std::mutex> lock(idx->mu);
+    idx->last = st;
+  }
   return res.release();
+}
+
+// Number of tree entries the closed stab of [start, end] on `target` visits (coitrees' closed-interval test,
+// src/impg.rs:1940): what populate_cigar_cache would cache (refine.cu).
+uint64_t stab_count_closed(impgx_index *idx, uint32_t target, int32_t start, int32_t end) {
+  check_device(idx->device);
+  CallScratch scratch(idx, /*want_stream=*/true);
+  Arena &arena = *scratch.arena;
+  Ctx ctx;
+  cudaStream_t s = scratch.stream;
+  DBuf<Frontier> fr(1, arena);
+  DBuf<Window> win(1, arena);
+  DBuf<uint32_t> cnt(1, arena);
+  const Frontier f{0u, target, start, end};
+  CUDA_CHECK(cudaMemcpyAsync(fr.get(), &f, sizeof(f), cudaMemcpyHostToDevice, s));
+  auto kern = k_stab_count<true, false>;
+  LAUNCH(kern, 1, 32, s, idx->view(), fr.get(), (uint64_t)1, win.get(), cnt.get(), (uint32_t *)nullptr);
+  uint32_t c = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&c, cnt.get(), 4, cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  fr.release(); win.release(); cnt.release();
+  return c;
 }
 
 // ============================================================ test hooks for the device primitives

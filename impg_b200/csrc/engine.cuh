@@ -33,6 +33,8 @@ impgx_index *index_build(const impgx_record *recs, size_t n, const uint32_t *run
 impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n, const impgx_params &p, bool bed,
                            bool ranges_on_device, bool results_to_host, void *stream, class Comm *comm = nullptr);
 
+uint64_t stab_count_closed(impgx_index *idx, uint32_t target, int32_t start, int32_t end);
+
 // One or more parsed PAF files over a shared SequenceIndex (ids by first appearance, src/seqidx.rs:22-35).
 struct PafData {
   std::vector<impgx_record> recs;

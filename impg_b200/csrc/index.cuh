@@ -2,6 +2,7 @@
 // per-target coitrees (Impg.trees, src/impg.rs:226,394-404) and its on-disk
 // CIGAR text (src/impg.rs:495-552).
 #pragma once
+#include <memory>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -59,8 +60,13 @@ struct impgx_index {
   uint32_t *d_stream = nullptr, *d_qid = nullptr;
   impgx::EntryRec *d_rec = nullptr;
   uint64_t *d_tgt_off = nullptr;
-  std::mutex mu;  // one query batch at a time per index (handle is thread-safe)
-  impgx::Arena arena;  // device scratch of the query pipeline
+  // The handle is Send + Sync like the reference's ImpgIndex (src/impg_index.rs:21; refine calls it from rayon
+  // workers, src/commands/refine.rs:525): concurrent calls each lease their own scratch arena (and, for the
+  // host entry points, their own stream) from these pools, so they overlap on the device. `mu` guards the
+  // pools, `last` and `hits_per_row`; it is never held while a query runs.
+  std::mutex mu;
+  std::vector<std::unique_ptr<impgx::Arena>> arena_pool;
+  std::vector<cudaStream_t> stream_pool;
   impgx_stats last{};
   double hits_per_row = 0;  // observed liftovers per row (sizes the row batches)
   bool original_coordinates = false;  // writers: --original-sequence-coordinates (src/main.rs:4661-4678)

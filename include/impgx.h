@@ -438,6 +438,64 @@ int impgx_partitioner_feed(impgx_partitioner *p, size_t n, const uint32_t *q_id,
 int impgx_partitioner_finish(impgx_partitioner *p, impgx_partitions **out);
 void impgx_partitioner_free(impgx_partitioner *p);
 
+/* ---------------------------------------------------------------- refine
+ * Replaces Impg::populate_cigar_cache / Impg::query_with_cache (src/impg.rs:1930-2035; trait
+ * src/impg_index.rs) and their caller, refine's flank search (src/commands/refine.rs:144-545).
+ *
+ * The reference decodes the CIGAR of every alignment under the widest candidate interval once
+ * (populate_cigar_cache) so that the many overlapping candidate queries of one locus do not re-read and
+ * re-parse them (query_with_cache). Here every CIGAR has been resident in HBM since the index was built:
+ * there is nothing to populate, and query_with_cache is Impg::query. What the library adds is the batch:
+ * the candidates of a whole phase of the flank search — for every locus of the call — are ONE batch of rows. */
+
+/* What populate_cigar_cache(target_id, start, end) would cache: *n_keys = number of distinct alignments
+ * (cache keys: alignment file index + data offset) whose tree entries the closed stab of [start, end] visits. */
+int impgx_populate_cigar_cache(impgx_index *idx, uint32_t target_id, int32_t start, int32_t end, uint64_t *n_keys);
+
+/* query_with_cache for a grid of candidates of one locus (evaluate_candidate, refine.rs:412-479): candidate k is
+ * [max(0, orig_start - left[k]), min(seq_len, orig_end + right[k])) on target_id; candidates that are empty after
+ * clamping get zero results (the reference skips them). Results per candidate as Impg::query returns them (self
+ * interval first, reference order); params->mode must be IMPGX_MODE_QUERY. */
+int impgx_query_with_cache_batch(impgx_index *idx, uint32_t target_id, int32_t orig_start, int32_t orig_end,
+                                 const int32_t *left, const int32_t *right, size_t n_candidates,
+                                 const impgx_params *params, impgx_results **out);
+
+typedef struct impgx_refine_params {
+  int32_t span_bp;                     /* --span-bp (default 1000) */
+  int32_t extension_step;              /* --extension-step (default 1000), > 0 */
+  double max_extension;                /* --max-extension (default 0.5): <= 1 a fraction of the locus, > 1 bp */
+  uint32_t support_level;              /* --pansn-mode: 0 sequence (default), 1 sample, 2 haplotype */
+  int32_t merge_distance;              /* -d; < 0 = --no-merge */
+  double min_identity;                 /* --min-result-identity; NaN = None */
+  uint32_t transitive;                 /* 0: query_with_cache, 1: -x (BFS), 2: --transitive-dfs */
+  uint32_t max_depth;                  /* -m */
+  int32_t min_transitive_len;
+  int32_t min_distance_between_ranges;
+  const uint8_t *subset_mask;          /* --subset-sequence-list as a per-sequence mask (impgx_subset_mask) or NULL */
+  const uint64_t *blacklist_offsets;   /* --blacklist-bed after name->id: CSR over all sequences (n_seqs + 1) or NULL */
+  const int32_t *blacklist_ranges;     /* (start, end) pairs exactly as the BED gives them */
+} impgx_refine_params;
+
+typedef struct impgx_refine_results impgx_refine_results;
+typedef struct impgx_refine_view {      /* RefineRecord, refine.rs:41-54, one per locus, in input order */
+  size_t n;
+  const int32_t *refined_start, *refined_end, *original_start, *original_end;
+  const int32_t *applied_left_extension, *applied_right_extension;
+  const uint64_t *support_count, *original_support_count;
+  const uint64_t *entity_offsets;       /* n + 1: support_entities of locus i = entities [off[i], off[i+1]) */
+  const uint32_t *entity_seq;           /* sorted by (sequence name, start) */
+  const int32_t *entity_start, *entity_end;
+  uint64_t candidates_evaluated;        /* candidate ranges queried */
+  uint64_t batches;                     /* device batches they were answered in */
+} impgx_refine_view;
+
+/* run_refine (refine.rs:81-142) over `n` loci. Errors like the reference: end <= start, unknown target id, or no
+ * candidate of a locus evaluable -> IMPGX_E_INVALID. */
+int impgx_refine(impgx_index *idx, const impgx_range *loci, size_t n, const impgx_refine_params *params,
+                 impgx_refine_results **out);
+int impgx_refine_view_get(const impgx_refine_results *res, impgx_refine_view *view);
+void impgx_refine_results_free(impgx_refine_results *res);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,8 @@
 #include <omp.h>
 #endif
 
+#include <set>
+
 #include "../include/impgx.h"
 
 namespace {
@@ -1556,6 +1558,296 @@ struct ResultSet {
 }  // namespace
 
 // =================================================================== C API
+// ---------------------------------------------------------------- refine
+// src/impg.rs:1930-1949 populate_cigar_cache: every tree entry the (closed) stab visits gets its decoded CIGAR
+// cached under (alignment file index, data offset); with one alignment file the key is the alignment record.
+typedef std::map<std::pair<uint32_t, uint64_t>, std::vector<CigarOp>> CigarCache;
+void populate_cigar_cache(const Index &idx, uint32_t target_id, int32_t rs, int32_t re, CigarCache &cache) {
+  auto it = idx.trees.find(target_id);
+  if (it == idx.trees.end()) return;
+  it->second.query(rs, re, [&](const Node &iv) {
+    const auto key = std::make_pair(0u, (uint64_t)iv.meta.aln);
+    if (!cache.count(key)) {
+      std::vector<CigarOp> ops;
+      if (!idx.get_cigar_ops(iv.meta, ops)) abort();
+      cache.emplace(key, std::move(ops));
+    }
+  });
+}
+// src/impg.rs:1951-2035 query_with_cache: Impg::query with the CIGAR taken from the cache when it is there
+std::vector<Result> query_with_cache(const Index &idx, uint32_t target_id, int32_t rs, int32_t re, bool store_cigar,
+                                     double min_identity, const CigarCache &cache) {
+  std::vector<Result> results;
+  results.push_back(make_self_interval(target_id, rs, re, store_cigar));
+  auto it = idx.trees.find(target_id);
+  if (it == idx.trees.end()) return results;
+  it->second.query(rs, re, [&](const Node &iv) {
+    const QueryMetadata &m = iv.meta;
+    std::vector<CigarOp> ops;
+    auto c = cache.find(std::make_pair(0u, (uint64_t)m.aln));
+    if (c != cache.end()) ops = c->second;
+    else if (!idx.get_cigar_ops(m, ops)) abort();
+    Projection p;
+    if (!project_target_range_through_alignment(rs, re, m.target_start, m.target_end, m.query_start, m.query_end,
+                                                m.strand_rev, ops.data(), ops.size(), p))
+      return;
+    if (!std::isnan(min_identity) && calculate_gap_compressed_identity(p.ops) < min_identity) return;
+    Result r;
+    r.q_id = m.query_id; r.q_first = p.q_start; r.q_last = p.q_end;
+    if (store_cigar) r.cigar = std::move(p.ops);
+    r.t_id = target_id; r.t_first = p.t_start; r.t_last = p.t_end;
+    results.push_back(std::move(r));
+  });
+  return results;
+}
+
+// sweepga::pansn::extract_pansn_key (un-vendored crate, restated; unpinned): PanSN names are
+// sample#haplotype#contig; level 0 = the sequence name, 1 = the sample, 2 = sample#haplotype.
+std::string pansn_key(const std::string &name, int level) {
+  if (level == 0) return name;
+  size_t a = name.find('#');
+  if (a == std::string::npos) return name;
+  if (level == 1) return name.substr(0, a);
+  size_t b = name.find('#', a + 1);
+  return b == std::string::npos ? name : name.substr(0, b);
+}
+
+struct RefineConfig {  // src/commands/refine.rs:21-38
+  int32_t span_bp;
+  double max_extension;
+  int level;
+  int32_t extension_step, merge_distance;
+  double min_identity;
+  bool bfs, dfs;
+  uint32_t max_depth;
+  int32_t min_transitive_len, min_distance_between_ranges;
+  const uint8_t *subset;
+  const uint64_t *bl_off;  // blacklist: CSR per sequence of (start, end) as the BED gives them
+  const int32_t *bl_rng;
+};
+struct SupportEntity { uint32_t seq; int32_t start, end; };
+struct RefineRecord {
+  int32_t refined_start, refined_end, original_start, original_end, left, right;
+  uint64_t support_count, original_support_count;
+  std::vector<SupportEntity> entities;
+};
+struct SampleInterval { int32_t query_start, query_end, target_start, target_end; };
+struct Candidate {
+  int32_t start, end, left_extension, right_extension;
+  uint64_t support_count;
+  std::vector<SupportEntity> entities;
+};
+
+static uint32_t abs_diff_i32(int32_t a, int32_t b) { return a > b ? (uint32_t)a - (uint32_t)b : (uint32_t)b - (uint32_t)a; }
+// :834-850
+static bool should_merge(const SampleInterval &a, const SampleInterval &b, int32_t merge_distance) {
+  if (merge_distance < 0) return false;
+  const uint32_t distance = (uint32_t)merge_distance;
+  const bool query_adjacent = std::min(abs_diff_i32(a.query_end, b.query_start), abs_diff_i32(a.query_start, b.query_end)) <= distance;
+  const bool target_adjacent = std::min(abs_diff_i32(a.target_end, b.target_start), abs_diff_i32(a.target_start, b.target_end)) <= distance;
+  return query_adjacent || target_adjacent;
+}
+// :799-832
+static std::vector<SampleInterval> merge_sample_intervals(std::vector<SampleInterval> iv, int32_t merge_distance) {
+  if (iv.empty() || merge_distance < 0) return iv;
+  std::stable_sort(iv.begin(), iv.end(), [](const SampleInterval &a, const SampleInterval &b) {
+    return a.query_start != b.query_start ? a.query_start < b.query_start : a.query_end < b.query_end;
+  });
+  std::vector<SampleInterval> merged;
+  SampleInterval cur = iv[0];
+  for (size_t i = 1; i < iv.size(); i++) {
+    const SampleInterval &nx = iv[i];
+    if (should_merge(cur, nx, merge_distance)) {
+      cur.query_start = std::min(cur.query_start, nx.query_start);
+      cur.query_end = std::max(cur.query_end, nx.query_end);
+      cur.target_start = std::min(cur.target_start, nx.target_start);
+      cur.target_end = std::max(cur.target_end, nx.target_end);
+    } else {
+      merged.push_back(cur);
+      cur = nx;
+    }
+  }
+  merged.push_back(cur);
+  return merged;
+}
+// :852-877
+static std::vector<int32_t> build_flanks(int32_t max_extension, int32_t step) {
+  std::vector<int32_t> flanks;
+  int32_t current = 0;
+  if (max_extension == 0) return {0};
+  while (current <= max_extension) {
+    flanks.push_back(current);
+    if (max_extension - current < step) break;
+    current = (int32_t)std::min<int64_t>((int64_t)current + step, INT32_MAX);
+  }
+  if (flanks.back() != max_extension) flanks.push_back(max_extension);
+  std::sort(flanks.begin(), flanks.end());
+  flanks.erase(std::unique(flanks.begin(), flanks.end()), flanks.end());
+  return flanks;
+}
+// :591-632 (the reference walks the tree; every entry of the target counts)
+static uint64_t compute_max_entities(const Index &idx, uint32_t target_id, const RefineConfig &c) {
+  std::set<std::string> uniq;
+  const std::string target_key = pansn_key(idx.names[target_id], c.level);
+  auto it = idx.trees.find(target_id);
+  if (it == idx.trees.end()) return 0;
+  for (const Node &nd : it->second.nodes) {
+    const uint32_t q = nd.meta.query_id;
+    if (q == target_id) continue;
+    if (c.subset && !c.subset[q]) continue;
+    const std::string key = pansn_key(idx.names[q], c.level);
+    if (key != target_key) uniq.insert(key);
+  }
+  return uniq.size();
+}
+// :665-783. per_sample is a hash map in the reference: the iteration order only matters for WHICH entities are
+// listed when the early termination fires; here ascending sequence id (unpinned).
+static void compute_support_sets(const Index &idx, const RefineConfig &c, uint32_t target_id, const std::vector<Result> &overlaps,
+                                 int32_t region_start, int32_t region_end, bool have_max, uint64_t max_possible,
+                                 std::set<std::string> &aggregated, std::vector<SupportEntity> &survivors) {
+  aggregated.clear();
+  survivors.clear();
+  if (overlaps.size() <= 1) return;
+  std::map<uint32_t, std::vector<SampleInterval>> per_sample;
+  for (const Result &r : overlaps) {
+    if (r.q_id == target_id) continue;
+    per_sample[r.q_id].push_back(SampleInterval{std::min(r.q_first, r.q_last), std::max(r.q_first, r.q_last),
+                                                std::min(r.t_first, r.t_last), std::max(r.t_first, r.t_last)});
+  }
+  const int32_t effective_span = std::min(std::max(region_end - region_start, 0), std::max(c.span_bp, 0));
+  const int32_t left_threshold = region_start + effective_span, right_threshold = region_end - effective_span;
+  std::map<uint32_t, std::pair<int32_t, int32_t>> sequence_ranges;
+  for (auto &kv : per_sample) {
+    auto merged = merge_sample_intervals(kv.second, c.merge_distance);
+    bool have = false;
+    int32_t qs = 0, qe = 0;
+    for (const SampleInterval &iv : merged) {
+      // covers_boundaries :785-797
+      if (iv.target_start <= region_start && iv.target_end >= region_end && iv.target_end >= left_threshold &&
+          iv.target_start <= right_threshold) {
+        const int32_t a = std::min(iv.query_start, iv.query_end), b = std::max(iv.query_start, iv.query_end);
+        if (have) {
+          qs = std::min(qs, a);
+          qe = std::max(qe, b);
+        } else {
+          qs = a;
+          qe = b;
+          have = true;
+        }
+      }
+    }
+    if (!have) continue;
+    if (c.bl_off) {  // closed overlap test of the blacklist tree (first = BED start, last = BED end)
+      bool hit = false;
+      for (uint64_t k = c.bl_off[kv.first]; k < c.bl_off[kv.first + 1]; k++)
+        if (c.bl_rng[2 * k] <= qe && qs <= c.bl_rng[2 * k + 1]) hit = true;
+      if (hit) continue;
+    }
+    auto ins = sequence_ranges.emplace(kv.first, std::make_pair(qs, qe));
+    ins.first->second.first = std::min(ins.first->second.first, qs);
+    ins.first->second.second = std::max(ins.first->second.second, qe);
+    aggregated.insert(pansn_key(idx.names[kv.first], c.level));
+    if (have_max && aggregated.size() >= max_possible) break;
+  }
+  for (auto &kv : sequence_ranges) survivors.push_back(SupportEntity{kv.first, kv.second.first, kv.second.second});
+  std::sort(survivors.begin(), survivors.end(), [&](const SupportEntity &a, const SupportEntity &b) {
+    return idx.names[a.seq] != idx.names[b.seq] ? idx.names[a.seq] < idx.names[b.seq] : a.start < b.start;
+  });
+}
+// :564-582
+static int compare_candidates(const Candidate &a, const Candidate &b) {
+  if (a.support_count != b.support_count) return a.support_count < b.support_count ? -1 : 1;
+  const int64_t at = (int64_t)a.left_extension + a.right_extension, bt = (int64_t)b.left_extension + b.right_extension;
+  if (at != bt) return bt < at ? -1 : 1;
+  const int32_t am = std::max(a.left_extension, a.right_extension), bm = std::max(b.left_extension, b.right_extension);
+  if (am != bm) return bm < am ? -1 : 1;
+  const int64_t al = (int64_t)a.end - a.start, bl = (int64_t)b.end - b.start;
+  if (al != bl) return bl < al ? -1 : 1;
+  return 0;
+}
+// :144-410 refine_single_range
+bool refine_single_range(const Index &idx, uint32_t target_id, int32_t orig_start, int32_t orig_end, const RefineConfig &c,
+                         RefineRecord &out) {
+  if (orig_end <= orig_start) return false;
+  const int32_t seq_len = (int32_t)idx.seq_lens[target_id];
+  const int32_t locus_len = std::max(orig_end - orig_start, 0);
+  double mx = c.max_extension <= 1.0 ? std::ceil((double)locus_len * c.max_extension) : std::ceil(c.max_extension);
+  mx = std::min(std::max(mx, 0.0), (double)INT32_MAX);
+  const int32_t max_extension_bp = std::max((int32_t)mx, 0);
+  const bool have_max = c.level != 0;
+  const uint64_t max_entities = have_max ? compute_max_entities(idx, target_id, c) : 0;
+  CigarCache cache;
+  if (!c.bfs && !c.dfs) {
+    const int32_t max_start = std::max((int32_t)std::max<int64_t>((int64_t)orig_start - max_extension_bp, INT32_MIN), 0);
+    const int32_t max_end = std::min((int32_t)std::min<int64_t>((int64_t)orig_end + max_extension_bp, INT32_MAX), seq_len);
+    populate_cigar_cache(idx, target_id, max_start, max_end, cache);
+  }
+  const std::vector<int32_t> flanks = build_flanks(max_extension_bp, c.extension_step);
+  QParams qp{c.max_depth, c.min_transitive_len, c.min_distance_between_ranges, -1, false, c.min_identity, c.subset};
+  auto evaluate = [&](int32_t left, int32_t right, Candidate &cand) -> bool {  // evaluate_candidate :412-479
+    const int32_t start = std::max((int32_t)std::max<int64_t>((int64_t)orig_start - left, INT32_MIN), 0);
+    const int32_t end = std::min((int32_t)std::min<int64_t>((int64_t)orig_end + right, INT32_MAX), seq_len);
+    if (end <= start) return false;
+    std::vector<Result> overlaps;  // query_overlaps :481-545
+    if (c.bfs) overlaps = query_transitive_bfs(idx, target_id, start, end, qp, 1);
+    else if (c.dfs) overlaps = query_transitive_dfs(idx, target_id, start, end, qp);
+    else overlaps = query_with_cache(idx, target_id, start, end, false, c.min_identity, cache);
+    if (c.subset)  // apply_subset_filter (src/subset_filter.rs:84-115)
+      overlaps.erase(std::remove_if(overlaps.begin(), overlaps.end(),
+                                    [&](const Result &r) { return !(r.q_id == target_id || c.subset[r.q_id]); }),
+                     overlaps.end());
+    std::set<std::string> agg;
+    compute_support_sets(idx, c, target_id, overlaps, start, end, have_max, max_entities, agg, cand.entities);
+    cand.start = start;
+    cand.end = end;
+    cand.left_extension = orig_start - start;
+    cand.right_extension = end - orig_end;
+    cand.support_count = agg.size();
+    return true;
+  };
+  bool have_best = false;
+  Candidate best;
+  auto update_best = [&](Candidate &&cand) {
+    if (!have_best || compare_candidates(cand, best) > 0) best = std::move(cand);
+    have_best = true;
+  };
+  auto check_max = [&]() { return have_max && have_best && best.support_count >= max_entities; };
+  // the reduce over a parallel sweep keeps the first of equal candidates in flank order (:230-236)
+  auto sweep = [&](bool vary_left, int32_t fixed, bool skip_zero) {
+    bool have = false;
+    Candidate red;
+    for (int32_t f : flanks) {
+      if (skip_zero && f <= 0) continue;
+      Candidate cand;
+      if (!(vary_left ? evaluate(f, fixed, cand) : evaluate(fixed, f, cand))) continue;
+      if (!have || compare_candidates(cand, red) > 0) red = std::move(cand);
+      have = true;
+    }
+    if (have) update_best(std::move(red));
+  };
+  Candidate base;
+  uint64_t original_support = 0;
+  if (evaluate(0, 0, base)) {
+    original_support = base.support_count;
+    update_best(std::move(base));
+  }
+  if (!check_max()) {
+    sweep(true, 0, true);
+    if (!check_max()) {
+      sweep(false, have_best ? best.left_extension : 0, false);
+      if (!check_max()) sweep(true, have_best ? best.right_extension : 0, false);
+    }
+  }
+  if (!have_best) return false;
+  out.refined_start = best.start; out.refined_end = best.end;
+  out.original_start = orig_start; out.original_end = orig_end;
+  out.left = best.left_extension; out.right = best.right_extension;
+  out.support_count = best.support_count;
+  out.original_support_count = original_support;
+  out.entities = std::move(best.entities);
+  return true;
+}
+
 extern "C" {
 
 int orc_project(int32_t rs, int32_t re, int32_t ts, int32_t te, int32_t qs, int32_t qe, int strand_rev,
@@ -1881,6 +2173,49 @@ double orc_run_batch(void *h, const impgx_range *ranges, size_t n, const impgx_p
   if (n_out_bytes) *n_out_bytes = bytes;
   if (checksum) *checksum = sum;
   return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
+// refine over a list of loci (run_refine :81-142). params: the impgx_refine_params of include/impgx.h.
+// rec8[i] = {refined_start, refined_end, original_start, original_end, left, right, support, original support};
+// returns the number of support entities (all loci); fills up to `cap` of them, ent_off[n + 1]; -1 - i if locus i fails
+int64_t orc_refine(void *h, const impgx_range *loci, size_t n, const impgx_refine_params *p, int64_t *rec8,
+                   uint64_t *ent_off, uint32_t *ent_seq, int32_t *ent_start, int32_t *ent_end, size_t cap) {
+  Index *idx = (Index *)h;
+  RefineConfig c{p->span_bp, p->max_extension, (int)p->support_level, p->extension_step, p->merge_distance, p->min_identity,
+                 p->transitive == 1, p->transitive == 2, p->max_depth, p->min_transitive_len,
+                 p->min_distance_between_ranges, p->subset_mask, p->blacklist_offsets, p->blacklist_ranges};
+  uint64_t total = 0;
+  ent_off[0] = 0;
+  for (size_t i = 0; i < n; i++) {
+    RefineRecord r;
+    if (!refine_single_range(*idx, loci[i].target_id, loci[i].start, loci[i].end, c, r)) return -1 - (int64_t)i;
+    int64_t *o = rec8 + 8 * i;
+    o[0] = r.refined_start; o[1] = r.refined_end; o[2] = r.original_start; o[3] = r.original_end;
+    o[4] = r.left; o[5] = r.right; o[6] = (int64_t)r.support_count; o[7] = (int64_t)r.original_support_count;
+    for (auto &e : r.entities) {
+      if (total < cap) {
+        ent_seq[total] = e.seq; ent_start[total] = e.start; ent_end[total] = e.end;
+      }
+      total++;
+    }
+    ent_off[i + 1] = total;
+  }
+  return (int64_t)total;
+}
+// populate_cigar_cache: the number of cache keys; query_with_cache through that cache: the results
+uint64_t orc_populate_cigar_cache(void *h, uint32_t target_id, int32_t s, int32_t e) {
+  CigarCache cache;
+  populate_cigar_cache(*(Index *)h, target_id, s, e, cache);
+  return cache.size();
+}
+void *orc_query_with_cache(void *h, uint32_t target_id, int32_t s, int32_t e, int store_cigar, double min_identity,
+                           int32_t cache_s, int32_t cache_e) {
+  Index *idx = (Index *)h;
+  CigarCache cache;
+  populate_cigar_cache(*idx, target_id, cache_s, cache_e, cache);
+  ResultSet *rs = new ResultSet();
+  rs->r = query_with_cache(*idx, target_id, s, e, store_cigar != 0, min_identity, cache);
+  return rs;
 }
 
 // "CPU-batched" driver (second baseline): the same per-row work as orc_run_batch, but the

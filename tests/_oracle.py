@@ -188,6 +188,9 @@ def lib():
         L.orc_format.restype = C.c_void_p
         L.orc_run_batch.restype = C.c_double
         L.orc_run_batch_rows_parallel.restype = C.c_double
+        L.orc_refine.restype = C.c_int64
+        L.orc_populate_cigar_cache.restype = C.c_uint64
+        L.orc_query_with_cache.restype = C.c_void_p
         L.orc_index_attach_cigar_file.restype = C.c_int
         L.orc_partition_error.restype = C.c_char_p
         L.orc_partition_len.restype = C.c_size_t
@@ -527,6 +530,43 @@ class Index:
         secs = lib().orc_run_batch(self.h, _p(ranges), C.c_size_t(len(ranges)), C.byref(params), C.c_int(threads),
                                    C.c_int(code), C.byref(nres), C.byref(nbytes), C.byref(csum))
         return secs, nres.value, nbytes.value, csum.value
+
+    def refine(self, loci, params):
+        """refine_single_range per locus (reference src/commands/refine.rs:144-410); `params` is an
+        impg_b200.RefineParams (the same C struct the product takes). Returns the list of records."""
+        loci = np.ascontiguousarray(loci, dtype=RANGE_DTYPE)
+        n = len(loci)
+        rec = np.zeros((n, 8), np.int64)
+        eo = np.zeros(n + 1, np.uint64)
+        cap = 1 << 16
+        while True:
+            es, ea, eb = np.zeros(cap, np.uint32), np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+            tot = lib().orc_refine(self.h, _p(loci), C.c_size_t(n), C.byref(params), _p(rec), _p(eo), _p(es), _p(ea), _p(eb),
+                                   C.c_size_t(cap))
+            if tot < 0:
+                raise ValueError(f"refine failed for locus {-1 - tot}")
+            if tot <= cap:
+                break
+            cap = int(tot)
+        keys = ("refined_start", "refined_end", "original_start", "original_end", "applied_left_extension",
+                "applied_right_extension", "support_count", "original_support_count")
+        out = []
+        for i in range(n):
+            a, b = int(eo[i]), int(eo[i + 1])
+            out.append(dict({k: int(rec[i, j]) for j, k in enumerate(keys)},
+                            support_entities=list(zip(es[a:b].tolist(), ea[a:b].tolist(), eb[a:b].tolist()))))
+        return out
+
+    def populate_cigar_cache(self, target_id, s, e):
+        return int(lib().orc_populate_cigar_cache(self.h, C.c_uint32(target_id), C.c_int32(s), C.c_int32(e)))
+
+    def query_with_cache(self, target_id, s, e, cache_range, store_cigar=False, min_identity=None):
+        """populate_cigar_cache over `cache_range`, then Impg::query_with_cache(s, e) through that cache."""
+        h = lib().orc_query_with_cache(self.h, C.c_uint32(target_id), C.c_int32(s), C.c_int32(e),
+                                       C.c_int(1 if store_cigar else 0),
+                                       C.c_double(float("nan") if min_identity is None else min_identity),
+                                       C.c_int32(cache_range[0]), C.c_int32(cache_range[1]))
+        return Results(h)
 
     def run_batch_rows_parallel(self, ranges, params, threads=1, fmt="bed"):
         """The "CPU-batched" driver: rows in parallel, one thread per row. Returns (seconds, n_results, out_bytes)."""
