@@ -21,10 +21,14 @@
 // same alignment files; their CIGARs are decoded once into the HBM run stream as for any build.
 #include <algorithm>
 #include <cstdio>
+#include <cstring>
 #include <fstream>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
+
+#include <zlib.h>
 
 #include "engine.cuh"
 
@@ -237,6 +241,74 @@ static impgx_record record_of(const Entry &e) {
   return r;
 }
 
+// ---- BGZF alignment files behind an index (src/paf.rs:47-114, :199-302). The reference treats a path that ends
+// in .gz / .bgz as compressed, insists on BGZF (a plain gzip file is an error) and addresses a CIGAR by the BGZF
+// VIRTUAL POSITION of its first byte: (offset of the compressed block in the file) << 16 | (offset inside the
+// inflated block). A position at the very end of a block is reported as offset 0 of the next block (noodles'
+// Block::virtual_position; the GZI lookup of parse_paf_bgzf_with_gzi picks the same block).
+static bool has_compressed_suffix(const std::string &p) {
+  auto ends = [&](const char *sfx) {
+    const size_t k = strlen(sfx);
+    return p.size() >= k && p.compare(p.size() - k, k, sfx) == 0;
+  };
+  return ends(".gz") || ends(".bgz");
+}
+struct BgzfFile {
+  std::vector<uint64_t> coff, ustart;  // per block, ascending; a final sentinel holds (file size, inflated size)
+  std::vector<uint8_t> text;           // the inflated file
+  // virtual position -> offset in `text`
+  uint64_t to_offset(uint64_t vpos, const std::string &path) const {
+    const uint64_t c = vpos >> 16, w = vpos & 0xffffu;
+    auto it = std::lower_bound(coff.begin(), coff.end() - 1, c);
+    REQUIRE(it != coff.end() - 1 && *it == c, IMPGX_E_PARSE,
+            "virtual position " + std::to_string(vpos) + " does not start at a BGZF block of '" + path + "'");
+    return ustart[it - coff.begin()] + w;
+  }
+  // offset in `text` -> virtual position: the block that holds the byte (the later one at a block border)
+  uint64_t to_vpos(uint64_t off) const {
+    size_t b = (size_t)(std::upper_bound(ustart.begin(), ustart.end() - 1, off) - ustart.begin());
+    b = b ? b - 1 : 0;
+    return (coff[b] << 16) | (off - ustart[b]);
+  }
+};
+static void load_bgzf(const std::string &path, BgzfFile &out) {
+  const std::vector<uint8_t> d = slurp(path);
+  size_t p = 0;
+  while (p < d.size()) {
+    // is_bgzf (src/paf.rs:47-66): gzip, DEFLATE, FEXTRA, XLEN = 6, subfield 'B' 'C' of length 2
+    const bool hdr = d.size() - p >= 18 && d[p] == 0x1f && d[p + 1] == 0x8b && d[p + 2] == 0x08 && (d[p + 3] & 0x04) &&
+                     d[p + 10] == 6 && d[p + 11] == 0 && d[p + 12] == 'B' && d[p + 13] == 'C' && d[p + 14] == 2 && d[p + 15] == 0;
+    REQUIRE(hdr, IMPGX_E_PARSE,
+            p == 0 ? "'" + path + "' is regular gzip, not BGZF. Convert with: zcat '" + path + "' | bgzip > output.paf.gz"
+                   : "damaged BGZF block header in '" + path + "'");
+    const size_t bsize = (size_t)(d[p + 16] | (d[p + 17] << 8)) + 1;
+    REQUIRE(bsize >= 26 && bsize <= d.size() - p, IMPGX_E_PARSE, "truncated BGZF block in '" + path + "'");
+    const uint32_t isize = (uint32_t)d[p + bsize - 4] | ((uint32_t)d[p + bsize - 3] << 8) | ((uint32_t)d[p + bsize - 2] << 16) |
+                           ((uint32_t)d[p + bsize - 1] << 24);
+    REQUIRE(isize <= 65536, IMPGX_E_PARSE, "BGZF block inflates to more than 64 KiB in '" + path + "'");
+    out.coff.push_back(p);
+    out.ustart.push_back(out.text.size());
+    if (isize) {
+      const size_t at = out.text.size();
+      out.text.resize(at + isize);
+      z_stream zs;
+      memset(&zs, 0, sizeof(zs));
+      REQUIRE(inflateInit2(&zs, -15) == Z_OK, IMPGX_E_IO, "zlib initialisation failed");
+      zs.next_in = const_cast<Bytef *>(d.data() + p + 18);
+      zs.avail_in = (uInt)(bsize - 18 - 8);
+      zs.next_out = out.text.data() + at;
+      zs.avail_out = isize;
+      const int rc = inflate(&zs, Z_FINISH);
+      const bool ok = rc == Z_STREAM_END && zs.avail_out == 0;
+      inflateEnd(&zs);
+      REQUIRE(ok, IMPGX_E_PARSE, "BGZF block of '" + path + "' does not inflate");
+    }
+    p += bsize;
+  }
+  out.coff.push_back(d.size());
+  out.ustart.push_back(out.text.size());
+}
+
 static bool looks_compressed(const std::string &path) {
   FILE *f = fopen(path.c_str(), "rb");
   REQUIRE(f != nullptr, IMPGX_E_IO, "cannot open alignment file '" + path + "'");
@@ -393,10 +465,21 @@ int impgx_impg_write(const char *const *paf_paths, size_t n_paths, int bidirecti
   impgx::PafData pd;
   for (size_t k = 0; k < n_paths; k++) {
     REQUIRE(paf_paths[k], IMPGX_E_INVALID, "NULL path");
-    REQUIRE(!impgx::looks_compressed(paf_paths[k]), IMPGX_E_UNSUPPORTED,
-            "compressed alignment files are indexed by BGZF virtual positions (src/paf.rs:199-302), which this writer "
-            "does not produce; decompress the PAF first");
-    impgx::parse_paf(paf_paths[k], pd);
+    const std::string path = paf_paths[k];
+    const bool bgzf = impgx::has_compressed_suffix(path);  // parse_paf_file (src/paf.rs:306-362) goes by the suffix
+    REQUIRE(bgzf || !impgx::looks_compressed(path), IMPGX_E_UNSUPPORTED,
+            "'" + path + "' is compressed but not named .gz / .bgz: the reference would read it as plain text");
+    const size_t first = pd.recs.size();
+    impgx::parse_paf(path, pd);
+    if (bgzf) {
+      // the parser counted offsets in the inflated text; the index stores the virtual position of every CIGAR
+      impgx::BgzfFile bz;
+      impgx::load_bgzf(path, bz);
+      for (size_t i = first; i < pd.recs.size(); i++) {
+        REQUIRE(pd.cg_off[i] < bz.text.size(), IMPGX_E_PARSE, "CIGAR offset beyond the inflated size of '" + path + "'");
+        pd.cg_off[i] = bz.to_vpos(pd.cg_off[i]);
+      }
+    }
   }
   impgx::write_impg(pd, bidirectional != 0, out_path);
   API_END
@@ -410,6 +493,7 @@ int impgx_index_from_impg(const char *impg_path, const char *const *alignment_fi
   impgx::check_device(device);
   std::unique_ptr<impgx_impg> f(impgx::open_impg(impg_path));
   std::vector<std::vector<uint8_t>> text(n_files);
+  std::vector<std::unique_ptr<impgx::BgzfFile>> bgzf(n_files);
   std::vector<char> loaded(n_files, 0);
   std::vector<impgx_record> recs;
   std::vector<uint32_t> runs;
@@ -423,14 +507,20 @@ int impgx_index_from_impg(const char *impg_path, const char *const *alignment_fi
       const std::string p = alignment_files[e.file_index] ? alignment_files[e.file_index] : "";
       const bool tp = p.size() > 5 && (p.rfind(".1aln") == p.size() - 5 || p.rfind(".tpa") == p.size() - 4);
       REQUIRE(!tp, IMPGX_E_UNSUPPORTED, "tracepoint alignment files (.1aln / .tpa) are outside the path");
-      REQUIRE(!impgx::looks_compressed(p), IMPGX_E_UNSUPPORTED,
-              "the index addresses a compressed PAF by BGZF virtual positions (src/paf.rs:199-302); decompress it and "
-              "rebuild the index");
-      text[e.file_index] = impgx::slurp(p);
+      if (impgx::has_compressed_suffix(p)) {  // read_cigar_data (src/paf.rs:68-114): BGZF, offsets are virtual positions
+        bgzf[e.file_index].reset(new impgx::BgzfFile());
+        impgx::load_bgzf(p, *bgzf[e.file_index]);
+      } else {
+        REQUIRE(!impgx::looks_compressed(p), IMPGX_E_UNSUPPORTED,
+                "'" + p + "' is compressed but not named .gz / .bgz: the reference would read it as plain text");
+        text[e.file_index] = impgx::slurp(p);
+      }
       loaded[e.file_index] = 1;
     }
-    const std::vector<uint8_t> &t = text[e.file_index];
-    const uint64_t off = e.strand_and_data_offset & ~(impgx::STRAND_BIT | impgx::REVERSED_BIT);
+    const bool bz = bgzf[e.file_index] != nullptr;
+    const std::vector<uint8_t> &t = bz ? bgzf[e.file_index]->text : text[e.file_index];
+    uint64_t off = e.strand_and_data_offset & ~(impgx::STRAND_BIT | impgx::REVERSED_BIT);
+    if (bz) off = bgzf[e.file_index]->to_offset(off, alignment_files[e.file_index]);
     REQUIRE(off <= t.size() && e.data_bytes <= t.size() - off, IMPGX_E_PARSE,
             "CIGAR offset beyond the end of '" + std::string(alignment_files[e.file_index]) + "' (is it the file the index was built from?)");
     const long n = impgx::parse_cigar((const char *)t.data() + off, (size_t)e.data_bytes, runs);

@@ -159,3 +159,31 @@ def decode(data):
                         tr.varint(), tr.varint(), tr.varint()))
         trees[t] = ent
     return [i2n.get(i, "") for i in range(nxt)], [i2l.get(i, 0) for i in range(nxt)], trees
+
+
+# ---------------------------------------------------------------- BGZF (src/paf.rs:47-114, :199-302)
+def bgzf_compress(data, block=700):
+    """`data` as a BGZF file with small blocks (so that lines and CIGARs straddle block borders) plus the EOF
+    marker block; returns (file bytes, [(compressed offset, inflated start, inflated length)])."""
+    import zlib
+
+    out, table, u = bytearray(), [], 0
+    chunks = [data[i:i + block] for i in range(0, len(data), block)] + [b""]
+    for ch in chunks:
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        body = co.compress(ch) + co.flush()
+        bsize = 18 + len(body) + 8
+        hdr = b"\x1f\x8b\x08\x04" + b"\0\0\0\0" + b"\0\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1)
+        table.append((len(out), u, len(ch)))
+        out += hdr + body + struct.pack("<II", zlib.crc32(ch) & 0xffffffff, len(ch))
+        u += len(ch)
+    return bytes(out), table
+
+
+def virtual_position(table, uoff):
+    """Virtual position of inflated offset `uoff`: the block that holds the byte (noodles reports the end of a block as
+    offset 0 of the next one)."""
+    for coff, ustart, ulen in table:
+        if ustart <= uoff < ustart + ulen:
+            return (coff << 16) | (uoff - ustart)
+    raise ValueError(uoff)

@@ -141,3 +141,25 @@ def test_original_sequence_coordinates_in_the_writers(tmp_path):
                 ix.format_paf(gpu, raw, 0, names[0], 0)
         else:
             assert ix.format_paf(gpu, raw, 0, names[0], 0)
+
+
+@pytest.mark.parametrize("block", [64, 900])
+def test_index_from_impg_over_a_bgzf_paf(block, tmp_path):
+    """The alignment file behind the index is BGZF: every CIGAR is fetched through its virtual position
+    (reference src/paf.rs:68-114). Same answers as the index over the plain PAF."""
+    paf = PAFS[1]
+    bz, _ = F.bgzf_compress(open(paf, "rb").read(), block)
+    gz = str(tmp_path / "x.paf.bgz")
+    open(gz, "wb").write(bz)
+    out = str(tmp_path / "x.impg")
+    ix.impg_write([gz], out)
+    a, b = ix.Impg.from_paf(paf), ix.Impg.from_impg(out, [gz])
+    assert b.n_seqs == a.n_seqs and b.n_entries == a.n_entries
+    p = ix.make_params(mode=ix.MODE_BFS, max_depth=0, min_transitive_len=0, store_cigar=True)
+    ca, cb = a.query_batch(all_rows(a), p).columns(), b.query_batch(all_rows(b), p).columns()
+    assert all((ca[k] == cb[k]).all() for k in ca)
+    # the index of the PLAIN file does not open the compressed one (its offsets are not virtual positions)
+    plain = str(tmp_path / "plain.impg")
+    ix.impg_write([paf], plain)
+    with pytest.raises(ix.ImpgxError):
+        ix.Impg.from_impg(plain, [gz])

@@ -121,6 +121,32 @@ def test_reader_rejects_damaged_files(tmp_path):
     import gzip
     gz = tmp_path / "a.paf.gz"
     gz.write_bytes(gzip.compress(open(PAFS[0], "rb").read()))
-    with pytest.raises(ix.ImpgxError) as e:
+    with pytest.raises(ix.ImpgxError, match="regular gzip, not BGZF") as e:  # the reference's error (src/paf.rs:310-318)
         ix.impg_write([str(gz)], out)
-    assert e.value.code == ix.E_UNSUPPORTED
+    assert e.value.code == ix.E_PARSE
+
+
+@pytest.mark.parametrize("paf", PAFS[:3], ids=[os.path.basename(p) for p in PAFS[:3]])
+def test_bgzf_paf_behind_an_index_uses_virtual_positions(paf, tmp_path):
+    """A .gz / .bgz alignment file is BGZF and its CIGARs are addressed by virtual positions
+    (reference src/paf.rs:68-114, :199-302): the writer must produce what the Python restatement computes from its
+    own block table, for blocks small enough that CIGARs start right at and straddle block borders."""
+    text = open(paf, "rb").read()
+    for block in (700, 64, 65280):
+        bz, table = F.bgzf_compress(text, block)
+        gz = str(tmp_path / f"x{block}.paf.gz")
+        open(gz, "wb").write(bz)
+        out = str(tmp_path / f"x{block}.impg")
+        ix.impg_write([gz], out)
+        names, lens, recs = F.parse_paf_like_reference([paf])
+        vrecs = [r[:8] + (F.virtual_position(table, r[8]), r[9]) for r in recs]
+        assert open(out, "rb").read() == F.encode(names, lens, F.entries_by_target(vrecs))
+        got, fi, off, ln = ix.ImpgFile(out).records()
+        assert off.tolist() == [r[8] for r in vrecs] and ln.tolist() == [r[9] for r in recs]
+    # a plain gzip file under a .gz name is refused like the reference does (src/paf.rs:306-318)
+    import gzip
+    plain = str(tmp_path / "plain.paf.gz")
+    with gzip.open(plain, "wb") as f:
+        f.write(text)
+    with pytest.raises(ix.ImpgxError, match="not BGZF"):
+        ix.impg_write([plain], str(tmp_path / "p.impg"))
