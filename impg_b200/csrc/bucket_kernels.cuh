@@ -111,6 +111,9 @@ __global__ void __launch_bounds__(T == 32 ? 256 : T)
   m.nxt = m.heads + CAP;
   __shared__ unsigned int s_cnt[GROUPS][2];  // [0] roots, [1] multi-member groups
   __shared__ uint64_t s_rk[(T == 32) ? 1 : T / 32];  // cross-warp argmax of the prefilter
+  constexpr int BINS = 64;                        // start bins of the staircase filter
+  __shared__ int s_bin[GROUPS][BINS];             // max end per start bin, then the exclusive prefix max
+  __shared__ int s_mm[(T == 32) ? 1 : T / 32][2];  // cross-warp min / max start
   auto sync = [&]() {
     if (T == 32) __syncwarp();
     else __syncthreads();
@@ -278,6 +281,90 @@ __global__ void __launch_bounds__(T == 32 ? 256 : T)
     // ---- prefilter (see k_merge_segments): drop the boxes the sweep of src/main.rs:12496-12556 cannot see
     if (merge_strands && md >= 0) {
       constexpr uint32_t STOP = (T == 32) ? 32u : 64u;  // short enough for a quick sort
+      // Staircase filter. The hits of a (row, q) bucket are mostly SHIFTED copies of one interval (start and end
+      // move together), which the longest-box pivots below do not dominate. Bin the boxes by start, take the max
+      // end per bin and its exclusive prefix max over the bins: a box whose end does not exceed the max end of the
+      // EARLIER bins lies behind a box that starts strictly before it and ends no earlier — the sweep cannot see it
+      // (same argument as for the pivots). What is left is little more than the staircase of growing ends.
+      if (nr > STOP) {
+        int smin = INT32_MAX, smax = INT32_MIN;
+        for (uint32_t c = lt; c < nr; c += T) {
+          const uint32_t i = live[c];
+          const int st = min(m.qlo[i], m.qhi[i]);
+          smin = min(smin, st);
+          smax = max(smax, st);
+        }
+#pragma unroll
+        for (int dlt = 16; dlt > 0; dlt >>= 1) {
+          smin = min(smin, __shfl_xor_sync(FULL, smin, dlt));
+          smax = max(smax, __shfl_xor_sync(FULL, smax, dlt));
+        }
+        if (T != 32) {
+          if (lane == 0) {
+            s_mm[threadIdx.x >> 5][0] = smin;
+            s_mm[threadIdx.x >> 5][1] = smax;
+          }
+        }
+        for (int k = lt; k < BINS; k += T) s_bin[gi][k] = INT32_MIN;
+        sync();
+        if (T != 32) {
+#pragma unroll
+          for (int w = 0; w < T / 32; w++) {
+            smin = min(smin, s_mm[w][0]);
+            smax = max(smax, s_mm[w][1]);
+          }
+        }
+        const uint64_t width = (uint64_t)((int64_t)smax - (int64_t)smin) + 1;
+        for (uint32_t c = lt; c < nr; c += T) {
+          const uint32_t i = live[c];
+          const uint32_t k = (uint32_t)(((uint64_t)((int64_t)min(m.qlo[i], m.qhi[i]) - (int64_t)smin) * BINS) / width);
+          atomicMax(&s_bin[gi][k], max(m.qlo[i], m.qhi[i]));
+        }
+        sync();
+        if (threadIdx.x < 32 || T == 32) {  // exclusive prefix max over the 64 bins, two per lane
+          const int v0 = s_bin[gi][lane], v1 = s_bin[gi][lane + 32];
+          const int i0 = warp_incl_max(v0);
+          const int t0 = __shfl_sync(FULL, i0, 31);
+          const int i1 = max(t0, warp_incl_max(v1));
+          int e0 = __shfl_up_sync(FULL, i0, 1), e1 = __shfl_up_sync(FULL, i1, 1);
+          if (lane == 0) {
+            e0 = INT32_MIN;
+            e1 = t0;
+          }
+          s_bin[gi][lane] = e0;
+          s_bin[gi][lane + 32] = e1;
+        }
+        if (lt == 0) s_cnt[gi][0] = 0;
+        sync();
+        uint32_t wbase_ = 0;
+        for (uint32_t c0 = 0; c0 < nr; c0 += T) {
+          const uint32_t c = c0 + lt;
+          uint32_t i = 0;
+          bool keep = false;
+          if (c < nr) {
+            i = live[c];
+            const uint32_t k = (uint32_t)(((uint64_t)((int64_t)min(m.qlo[i], m.qhi[i]) - (int64_t)smin) * BINS) / width);
+            keep = max(m.qlo[i], m.qhi[i]) > s_bin[gi][k];
+          }
+          const unsigned bm = __ballot_sync(FULL, keep);
+          uint32_t wb;
+          if (T == 32) {
+            wb = wbase_;
+            wbase_ += __popc(bm);
+          } else {
+            wb = 0;
+            if (lane == 0 && bm) wb = atomicAdd(&s_cnt[gi][0], (unsigned)__popc(bm));
+            wb = __shfl_sync(FULL, wb, 0);
+          }
+          if (keep) spare[wb + __popc(bm & lanemask_lt())] = (uint16_t)i;
+        }
+        if (T == 32 && lt == 0) s_cnt[gi][0] = wbase_;
+        sync();
+        nr = s_cnt[gi][0];
+        uint16_t *t = live;
+        live = spare;
+        spare = t;
+      }
       uint32_t n_piv = 0;
       while (nr - n_piv > STOP && n_piv < 6) {
         uint64_t best = 0;  // (length + 1) << 16 | box index; 0 = none

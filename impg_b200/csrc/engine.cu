@@ -758,6 +758,12 @@ void Runner::lift_core(const DBuf<Frontier> &fr_ref, uint64_t nF, bool closed, b
   cudaEventElapsedTime(&ms, e1, e2);
   ctx.lift_ms += ms;
   ctx.lift_launches++;
+  {
+    static const bool trace_launches = env_u64("IMPGX_TRACE", 0) >= 2;  // one line per liftover launch (ncu captures are matched by it)
+    if (trace_launches)
+      fprintf(stderr, "[impgx] liftover launch: ranges %llu hits %llu ok %llu %.3f ms%s\n", (unsigned long long)nF,
+              (unsigned long long)H, cnt[1], ms, bk ? " (into buckets)" : "");
+  }
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
   ctx.lift_runs += cnt[0];
   // bytes the kernel's own algorithm touches: task 8 + range 16 + entry 32 + hit 32 (+ slice 16),

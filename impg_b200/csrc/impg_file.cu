@@ -262,7 +262,10 @@ struct BgzfFile {
     auto it = std::lower_bound(coff.begin(), coff.end() - 1, c);
     REQUIRE(it != coff.end() - 1 && *it == c, IMPGX_E_PARSE,
             "virtual position " + std::to_string(vpos) + " does not start at a BGZF block of '" + path + "'");
-    return ustart[it - coff.begin()] + w;
+    const size_t b = (size_t)(it - coff.begin());
+    REQUIRE(w < ustart[b + 1] - ustart[b], IMPGX_E_PARSE,
+            "virtual position " + std::to_string(vpos) + " lies beyond its BGZF block of '" + path + "'");
+    return ustart[b] + w;
   }
   // offset in `text` -> virtual position: the block that holds the byte (the later one at a block border)
   uint64_t to_vpos(uint64_t off) const {
