@@ -218,7 +218,6 @@ def lib():
         L.impgx_format_bed_batch.restype = C.c_void_p
         L.impgx_format_bedpe.restype = C.c_void_p
         L.impgx_format_paf.restype = C.c_void_p
-        L.impgx_synth_num_alignments.restype = C.c_uint64
         L.impgx_partitions_format_bed.restype = C.c_void_p
         L.impgx_impg_num_seqs.restype = C.c_uint32
         L.impgx_impg_seq_name.restype = C.c_char_p
@@ -229,6 +228,29 @@ def lib():
         L.impgx_debug_host_columns_shard.restype = C.c_long
         _lib = L
     return _lib
+
+
+_synth = None
+SYNTH_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libimpgx_synth.so")
+
+
+def synth_lib():
+    """The synthetic workload generator and the CIGAR text writer of the CPU reference arm: bench / test tooling in a
+    library of its own (csrc/synth_tool.cpp), so that generating a workload does not load the product."""
+    global _synth
+    if _synth is None:
+        if not os.path.exists(SYNTH_LIB_PATH):
+            raise ImportError(f"{SYNTH_LIB_PATH} is missing: build it with `make -C impg_b200/csrc`")
+        L = C.CDLL(SYNTH_LIB_PATH)
+        L.impgx_synth_num_alignments.restype = C.c_uint64
+        L.impgx_synth_last_error.restype = C.c_char_p
+        _synth = L
+    return _synth
+
+
+def _check_synth(code):
+    if code != 0:
+        raise ImpgxError(code, synth_lib().impgx_synth_last_error().decode(errors="replace"))
 
 
 def _check(code):
@@ -986,15 +1008,15 @@ def synth_cfg(genomes, contigs, contig_len, tiles, eq_mean, rev_permille=100, se
 
 def synth_generate(cfg):
     """gen_synth: returns (records, runs, run_offsets, seq_lens, names)."""
-    L = lib()
+    L = synth_lib()
     n = L.impgx_synth_num_alignments(C.byref(cfg))
     recs = np.zeros(n, dtype=RECORD_DTYPE)
     nr = np.zeros(n, dtype=np.uint32)
-    _check(L.impgx_synth_records(C.byref(cfg), C.c_uint64(0), C.c_uint64(n), _p(recs), _p(nr)))
+    _check_synth(L.impgx_synth_records(C.byref(cfg), C.c_uint64(0), C.c_uint64(n), _p(recs), _p(nr)))
     offs = np.zeros(n + 1, dtype=np.uint64)
     np.cumsum(nr, out=offs[1:], dtype=np.uint64)
     runs = np.zeros(max(int(offs[-1]), 1), dtype=np.uint32)
-    _check(L.impgx_synth_runs(C.byref(cfg), C.c_uint64(0), C.c_uint64(n), _p(offs), _p(runs)))
+    _check_synth(L.impgx_synth_runs(C.byref(cfg), C.c_uint64(0), C.c_uint64(n), _p(offs), _p(runs)))
     n_seqs = cfg.genomes * cfg.contigs
     lens = np.full(n_seqs, cfg.contig_len, dtype=np.uint64)
     names = [f"g{g}#1#c{c}" for g in range(cfg.genomes) for c in range(cfg.contigs)]
@@ -1005,11 +1027,11 @@ def synth_generate_shard(cfg, n_ranks, rank, bidirectional=True):
     """The part of gen_synth shard `rank` of `n_ranks` needs: records of every alignment are
     generated (cheap) to derive the owner map, runs only for the alignments that have an entry
     on an owned sequence. Returns (records, runs, run_offsets, seq_lens, names, owner)."""
-    L = lib()
+    L = synth_lib()
     n = L.impgx_synth_num_alignments(C.byref(cfg))
     recs = np.zeros(n, dtype=RECORD_DTYPE)
     nr = np.zeros(n, dtype=np.uint32)
-    _check(L.impgx_synth_records(C.byref(cfg), C.c_uint64(0), C.c_uint64(n), _p(recs), _p(nr)))
+    _check_synth(L.impgx_synth_records(C.byref(cfg), C.c_uint64(0), C.c_uint64(n), _p(recs), _p(nr)))
     offs = np.zeros(n + 1, dtype=np.uint64)
     np.cumsum(nr, out=offs[1:], dtype=np.uint64)
     n_seqs = cfg.genomes * cfg.contigs
@@ -1018,7 +1040,7 @@ def synth_generate_shard(cfg, n_ranks, rank, bidirectional=True):
     sub_offs = np.zeros(len(keep) + 1, dtype=np.uint64)
     np.cumsum(nr[keep], out=sub_offs[1:], dtype=np.uint64)
     runs = np.zeros(max(int(sub_offs[-1]), 1), dtype=np.uint32)
-    _check(L.impgx_synth_runs_subset(C.byref(cfg), _p(keep), C.c_uint64(len(keep)), _p(sub_offs), _p(runs)))
+    _check_synth(L.impgx_synth_runs_subset(C.byref(cfg), _p(keep), C.c_uint64(len(keep)), _p(sub_offs), _p(runs)))
     lens = np.full(n_seqs, cfg.contig_len, dtype=np.uint64)
     names = [f"g{g}#1#c{c}" for g in range(cfg.genomes) for c in range(cfg.contigs)]
     return recs[keep], runs[: int(sub_offs[-1])], sub_offs, lens, names, owner
@@ -1029,18 +1051,18 @@ def synth_generate_contig(cfg, contig=0):
     contig c of another, so the trees, hits and transitive closure of a BED row on contig c are the same in
     this sub-world as in the full index. Returns (records, runs, run_offsets, seq_lens, names); sequence ids
     are those of the full world."""
-    L = lib()
+    L = synth_lib()
     n = L.impgx_synth_num_alignments(C.byref(cfg))
     recs = np.zeros(n, dtype=RECORD_DTYPE)
     nr = np.zeros(n, dtype=np.uint32)
-    _check(L.impgx_synth_records(C.byref(cfg), C.c_uint64(0), C.c_uint64(n), _p(recs), _p(nr)))
+    _check_synth(L.impgx_synth_records(C.byref(cfg), C.c_uint64(0), C.c_uint64(n), _p(recs), _p(nr)))
     pairs = cfg.genomes * (cfg.genomes - 1)
     keep = ((np.arange(pairs, dtype=np.uint64)[:, None] * np.uint64(cfg.contigs) + np.uint64(contig))
             * np.uint64(cfg.tiles) + np.arange(cfg.tiles, dtype=np.uint64)[None, :]).ravel()
     sub_offs = np.zeros(len(keep) + 1, dtype=np.uint64)
     np.cumsum(nr[keep], out=sub_offs[1:], dtype=np.uint64)
     runs = np.zeros(max(int(sub_offs[-1]), 1), dtype=np.uint32)
-    _check(L.impgx_synth_runs_subset(C.byref(cfg), _p(keep), C.c_uint64(len(keep)), _p(sub_offs), _p(runs)))
+    _check_synth(L.impgx_synth_runs_subset(C.byref(cfg), _p(keep), C.c_uint64(len(keep)), _p(sub_offs), _p(runs)))
     n_seqs = cfg.genomes * cfg.contigs
     lens = np.full(n_seqs, cfg.contig_len, dtype=np.uint64)
     names = [f"g{g}#1#c{c}" for g in range(cfg.genomes) for c in range(cfg.contigs)]
@@ -1049,7 +1071,7 @@ def synth_generate_contig(cfg, contig=0):
 
 def synth_bed(cfg, n_rows, seed=2, min_len=1000, max_len=10000):
     out = np.zeros(n_rows, dtype=RANGE_DTYPE)
-    _check(lib().impgx_synth_bed(C.byref(cfg), C.c_uint64(seed), C.c_uint64(n_rows), C.c_uint32(min_len),
+    _check_synth(synth_lib().impgx_synth_bed(C.byref(cfg), C.c_uint64(seed), C.c_uint64(n_rows), C.c_uint32(min_len),
                                  C.c_uint32(max_len), _p(out)))
     return out
 
@@ -1060,7 +1082,7 @@ def write_cigar_text(runs, run_offsets, path):
     n = len(run_offsets) - 1
     offs = np.zeros(n, np.uint64)
     lens = np.zeros(n, np.uint64)
-    _check(lib().impgx_write_cigar_text(_p(runs), _p(run_offsets), C.c_uint64(n), path.encode(), _p(offs), _p(lens)))
+    _check_synth(synth_lib().impgx_write_cigar_text(_p(runs), _p(run_offsets), C.c_uint64(n), path.encode(), _p(offs), _p(lens)))
     return offs, lens
 
 

@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(T == 32 ? 256 : T)
       // end per bin and its exclusive prefix max over the bins: a box whose end does not exceed the max end of the
       // EARLIER bins lies behind a box that starts strictly before it and ends no earlier — the sweep cannot see it
       // (same argument as for the pivots). What is left is little more than the staircase of growing ends.
-      if (nr > STOP) {
+      if (T != 32 && nr > 2 * STOP) {  // the warp classes (<= 256 boxes) go straight to the pivots
         int smin = INT32_MAX, smax = INT32_MIN;
         for (uint32_t c = lt; c < nr; c += T) {
           const uint32_t i = live[c];
