@@ -2120,7 +2120,6 @@ void Runner::run_sharded(const impgx_range *d_ranges, uint32_t n_rows, BatchOut 
   REQUIRE(p_.mode == IMPGX_MODE_QUERY || p_.mode == IMPGX_MODE_BFS, IMPGX_E_UNSUPPORTED,
           "the sharded index runs Impg::query and the transitive BFS (DFS: use an unsharded index)");
   REQUIRE(!p_.store_cigar, IMPGX_E_INVALID, "BED output carries no CIGAR (src/main.rs:7447)");
-  REQUIRE(!p_.mask_offsets, IMPGX_E_UNSUPPORTED, "masked_regions need an unsharded index");
   REQUIRE(n_rows < (1u << 26), IMPGX_E_INVALID, "more than 2^26 rows in one batch; lower IMPGX_ROWS_PER_BATCH");
   Comm &cm = *comm_;
   const int N = cm.size();
@@ -2128,38 +2127,90 @@ void Runner::run_sharded(const impgx_range *d_ranges, uint32_t n_rows, BatchOut 
   const bool bfs = p_.mode == IMPGX_MODE_BFS;
   prepare(d_ranges, n_rows);
 
-  // level-0 frontier: the rows on targets this rank owns; the global frontier
-  // index of a row is the row itself
+  // Level-0 frontier: the seed ranges on targets this rank owns. Every rank derives the GLOBAL seed list (one range
+  // per row, or — under masked_regions — the unmasked pieces of every row, src/impg.rs:2337-2373) on its own: that
+  // is rows-sized work and needs no exchange; the global frontier index of a seed is its index in that list.
+  // Visited sets are seeded for every row; only the owner of a sequence ever touches its entries.
   DBuf<Frontier> fr;
   DBuf<uint32_t> gmap;
   uint64_t nF = 0;
+  Visited V;
+  DBuf<BoxD> seed_boxes;  // masked: the self-interval pieces are a level of their own (ord level 1)
+  uint64_t n_seed_boxes = 0;
+  const uint32_t level_base = masked_ ? 1u : 0u;  // ord level of hop d is d + 1 + level_base
   {
-    DBuf<Frontier> all(n_rows, ar_);
-    LAUNCH(k_init_frontier, grid_threads(n_rows), 256, s_, d_ranges, n_rows, all.get());
-    DBuf<uint64_t> flag((uint64_t)n_rows + 1, ar_), scan((uint64_t)n_rows + 1, ar_);
-    CUDA_CHECK(cudaMemsetAsync(flag.get() + n_rows, 0, 8, s_));
-    LAUNCH(k_shard_seed_flags, grid_threads(n_rows), 256, s_, all.get(), (uint64_t)n_rows,
-           bfs ? p_.min_transitive_len : 0, idx_->d_owner, me, flag.get());
-    CUDA_CHECK(cudaMemcpyAsync(scan.get(), flag.get(), ((uint64_t)n_rows + 1) * 8, cudaMemcpyDeviceToDevice, s_));
-    exclusive_scan_u64(scan.get(), (uint64_t)n_rows + 1, sc_, s_);
+    DBuf<Frontier> all;
+    uint64_t n_all = n_rows;
+    if (masked_) {
+      DBuf<uint64_t> off((uint64_t)n_rows + 1, ar_);
+      CUDA_CHECK(cudaMemsetAsync(off.get() + n_rows, 0, 8, s_));
+      LAUNCH(k_seed_mask_caps, grid_threads(n_rows), 256, s_, d_ranges, n_rows, d_mask_off_.get(), off.get());
+      exclusive_scan_u64(off.get(), (uint64_t)n_rows + 1, sc_, s_);
+      ctx.launches += 2;
+      const uint64_t cap = read_u64(off.get() + n_rows, s_, ctx);
+      DBuf<int2> lists(cap, ar_), pieces(cap, ar_);
+      DBuf<uint32_t> list_len(n_rows, ar_), piece_cnt(n_rows, ar_);
+      LAUNCH(k_seed_masked, grid_threads(n_rows), 256, s_, d_ranges, n_rows, d_mask_off_.get(), d_mask_rng_.get(),
+             ix_.seq_len, off.get(), lists.get(), pieces.get(), list_len.get(), piece_cnt.get());
+      DBuf<uint64_t> ls((uint64_t)n_rows + 1, ar_), ps((uint64_t)n_rows + 1, ar_);
+      CUDA_CHECK(cudaMemsetAsync(ls.get() + n_rows, 0, 8, s_));
+      CUDA_CHECK(cudaMemsetAsync(ps.get() + n_rows, 0, 8, s_));
+      LAUNCH(k_u32_to_u64, grid_threads(n_rows), 256, s_, list_len.get(), (uint64_t)n_rows, ls.get());
+      LAUNCH(k_u32_to_u64, grid_threads(n_rows), 256, s_, piece_cnt.get(), (uint64_t)n_rows, ps.get());
+      exclusive_scan_u64(ls.get(), (uint64_t)n_rows + 1, sc_, s_);
+      exclusive_scan_u64(ps.get(), (uint64_t)n_rows + 1, sc_, s_);
+      ctx.launches += 4;
+      uint64_t nl = 0, np = 0;
+      read_u64x2(ls.get() + n_rows, ps.get() + n_rows, nl, np, s_, ctx);
+      V.keys.alloc(nl, ar_);
+      V.start.alloc(nl, ar_);
+      V.end.alloc(nl, ar_);
+      V.n = nl;
+      DBuf<Hit> seed_hits(np, ar_);
+      all.alloc(np, ar_);
+      LAUNCH(k_seed_masked_compact, grid_threads(n_rows), 256, s_, d_ranges, n_rows, off.get(), lists.get(), pieces.get(),
+             list_len.get(), piece_cnt.get(), ls.get(), ps.get(), V.keys.get(), V.start.get(), V.end.get(),
+             seed_hits.get(), all.get());
+      n_all = np;
+      // the seed pieces as boxes (never filtered by min_output_length), valid on the owner of the row's target only
+      seed_boxes.alloc(np, ar_);
+      n_seed_boxes = np;
+      DBuf<unsigned long long> scratch_cnt(1, ar_);
+      if (np) {
+        LAUNCH(k_boxes_from_sorted_level, grid_threads(np), 256, s_, seed_hits.get(), np, 1u, -1, seed_boxes.get(),
+               scratch_cnt.get());
+        LAUNCH(k_boxes_keep_owned, grid_threads(np), 256, s_, seed_boxes.get(), np, idx_->d_owner, me);
+      }
+      CUDA_CHECK(cudaStreamSynchronize(s_));
+    } else {
+      all.alloc(n_rows, ar_);
+      LAUNCH(k_init_frontier, grid_threads(n_rows), 256, s_, d_ranges, n_rows, all.get());
+      if (bfs) {
+        V.keys.alloc(n_rows, ar_);
+        V.start.alloc(n_rows, ar_);
+        V.end.alloc(n_rows, ar_);
+        V.n = n_rows;
+        LAUNCH(k_seed_visited, grid_threads(n_rows), 256, s_, d_ranges, n_rows, V.keys.get(), V.start.get(), V.end.get());
+      }
+    }
+    DBuf<uint64_t> flag(n_all + 1, ar_), scan(n_all + 1, ar_);
+    CUDA_CHECK(cudaMemsetAsync(flag.get() + n_all, 0, 8, s_));
+    if (n_all)
+      LAUNCH(k_shard_seed_flags, grid_threads(n_all), 256, s_, all.get(), n_all, bfs ? p_.min_transitive_len : 0,
+             idx_->d_owner, me, flag.get());
+    CUDA_CHECK(cudaMemcpyAsync(scan.get(), flag.get(), (n_all + 1) * 8, cudaMemcpyDeviceToDevice, s_));
+    exclusive_scan_u64(scan.get(), n_all + 1, sc_, s_);
     ctx.launches += 2;
-    nF = read_u64(scan.get() + n_rows, s_, ctx);
+    nF = read_u64(scan.get() + n_all, s_, ctx);
     DBuf<Frontier> f2(nF, ar_);
     DBuf<uint32_t> g2(nF, ar_);
-    LAUNCH(k_frontier_compact, grid_threads(n_rows), 256, s_, all.get(), (uint64_t)n_rows, flag.get(), scan.get(), f2.get());
-    if (nF) LAUNCH(k_frontier_rows, grid_threads(nF), 256, s_, f2.get(), nF, g2.get());
+    if (n_all) {
+      LAUNCH(k_frontier_compact, grid_threads(n_all), 256, s_, all.get(), n_all, flag.get(), scan.get(), f2.get());
+      LAUNCH(k_compact_indices, grid_threads(n_all), 256, s_, flag.get(), scan.get(), n_all, g2.get());
+    }
     CUDA_CHECK(cudaStreamSynchronize(s_));
     fr = std::move(f2);
     gmap = std::move(g2);
-  }
-  // visited sets: seeded for every row; only the owner of a row's target ever touches its entry
-  Visited V;
-  if (bfs) {
-    V.keys.alloc(n_rows, ar_);
-    V.start.alloc(n_rows, ar_);
-    V.end.alloc(n_rows, ar_);
-    V.n = n_rows;
-    LAUNCH(k_seed_visited, grid_threads(n_rows), 256, s_, d_ranges, n_rows, V.keys.get(), V.start.get(), V.end.get());
   }
 
   BedSink sink;
@@ -2174,12 +2225,19 @@ void Runner::run_sharded(const impgx_range *d_ranges, uint32_t n_rows, BatchOut 
   bool prefix_built = false;
   auto build_prefix = [&]() {
     WallTimer wt(ctx.w_assemble);
-    sink.prefix = (uint64_t)n_rows + prior;
+    sink.prefix = (uint64_t)n_rows + n_seed_boxes + prior;
     sink.boxes.alloc(sink.prefix, ar_);
     sink.n = sink.prefix + sink.n_raw;
-    LAUNCH(k_boxes_from_seeds, grid_threads(n_rows), 256, s_, d_ranges, n_rows, p_.min_output_length, bfs ? 0 : 1,
-           sink.boxes.get(), sink.counters.get(), (const uint32_t *)idx_->d_owner, me);
-    uint64_t off = n_rows;
+    if (masked_) {  // the self intervals are the seed level; the per-row seed slots stay invalid
+      CUDA_CHECK(cudaMemsetAsync(sink.boxes.get(), 0, (size_t)n_rows * sizeof(BoxD), s_));
+      if (n_seed_boxes)
+        CUDA_CHECK(cudaMemcpyAsync(sink.boxes.get() + n_rows, seed_boxes.get(), n_seed_boxes * sizeof(BoxD),
+                                   cudaMemcpyDeviceToDevice, s_));
+    } else {
+      LAUNCH(k_boxes_from_seeds, grid_threads(n_rows), 256, s_, d_ranges, n_rows, p_.min_output_length, bfs ? 0 : 1,
+             sink.boxes.get(), sink.counters.get(), (const uint32_t *)idx_->d_owner, me);
+    }
+    uint64_t off = (uint64_t)n_rows + n_seed_boxes;
     for (size_t l = 0; l < level_boxes.size(); l++) {
       if (level_n[l])
         CUDA_CHECK(cudaMemcpyAsync(sink.boxes.get() + off, level_boxes[l].get(), level_n[l] * sizeof(BoxD),
@@ -2211,7 +2269,7 @@ void Runner::run_sharded(const impgx_range *d_ranges, uint32_t n_rows, BatchOut 
       build_prefix();
       bk_begin(bk, n_rows);
       bk_begun = true;
-      bk.level = depth + 1;
+      bk.level = depth + 1 + level_base;
       bk.gmap = gmap.get();
       bk_add_boxd(bk, sink.boxes.get(), sink.prefix, /*scatter=*/false);
       Lifted L;
@@ -2240,14 +2298,15 @@ void Runner::run_sharded(const impgx_range *d_ranges, uint32_t n_rows, BatchOut 
         if (sink.raw_has_orig) sink.raw_orig = std::move(L.orig);
         sink.n_raw = L.H;
         sink.raw_gmap = gmap.get();
-        sink.level = depth + 1;
+        sink.level = depth + 1 + level_base;
       }
       sink.filled = true;
       break;
     }
     if (L.H)
       LAUNCH(k_boxes_from_raw_level, grid_threads(L.H), 256, s_, L.hits.get(), L.tasks.get(), L.d_orig, L.offs.get(),
-             (const uint64_t *)nullptr, L.H, depth + 1, p_.min_output_length, dst, sink.counters.get(), gmap.get());
+             (const uint64_t *)nullptr, L.H, depth + 1 + level_base, p_.min_output_length, dst, sink.counters.get(),
+             gmap.get());
     depth++;
     prior += L.H;
     level_n.push_back(L.H);

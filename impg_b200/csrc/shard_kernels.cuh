@@ -35,6 +35,18 @@ __global__ void k_frontier_rows(const Frontier *__restrict__ f, uint64_t n, uint
   for (uint64_t i = gtid(); i < n; i += gstride()) gmap[i] = f[i].row;
 }
 
+// boxes of rows whose box sequence is not owned here are someone else's (masked seeds: every rank derives them all)
+__global__ void k_boxes_keep_owned(BoxD *__restrict__ b, uint64_t n, const uint32_t *__restrict__ owner, uint32_t rank) {
+  for (uint64_t i = gtid(); i < n; i += gstride())
+    if (owner[b[i].q_id] != rank) b[i].valid = 0;
+}
+// position in the uncompacted list of every element that was kept
+__global__ void k_compact_indices(const uint64_t *__restrict__ flag, const uint64_t *__restrict__ scan, uint64_t n,
+                                  uint32_t *__restrict__ out) {
+  for (uint64_t i = gtid(); i < n; i += gstride())
+    if (flag[i]) out[scan[i]] = (uint32_t)i;
+}
+
 // accepted hits -> routed records + destination rank (rejected hits: dest = n_ranks, sorted last)
 __global__ void k_route_hits(const Hit *__restrict__ hits, const LiftTask *__restrict__ tasks,
                              const uint32_t *__restrict__ orig, const uint32_t *__restrict__ gmap,

@@ -185,3 +185,25 @@ def test_nccl_two_ranks(tmp_path):
     assert got["row_offsets"].tolist() == ooffs.tolist()
     for k in ("q_id", "q_first", "q_last"):
         assert (got[k] == oc[k]).all(), k
+
+
+@pytest.mark.parametrize("n_ranks", [2, 3, 5])
+def test_sharded_masked_regions(world, n_ranks):
+    """masked_regions (what partition passes, reference src/commands/partition.rs:359-391; src/impg.rs:2331-2373) on a
+    sharded index: every rank derives the unmasked seed pieces of all rows, the owner of a row's target walks them."""
+    from test_gpu_parity import random_mask
+    cfg, orc, shards, bed = world
+    sh = shards[n_ranks]
+    rng = np.random.default_rng(40 + n_ranks)
+    b = bed[:90]
+    for density, depth, d in ((0.5, 2, 1000), (0.9, 3, 0), (0.0, 2, 1000), (0.97, 0, 100)):
+        mask = random_mask(rng, 12, 60000, density)
+        compare_bed_sharded(orc, sh, b, *params_pair(mode=1, max_depth=depth, masked_regions=mask, merge_distance=d))
+    mask = random_mask(rng, 12, 60000, 0.8)
+    compare_bed_sharded(orc, sh, b, *params_pair(mode=1, max_depth=2, masked_regions=mask, merge_distance=-1, merge_strands=True))
+    compare_bed_sharded(orc, sh, b, *params_pair(mode=1, max_depth=3, masked_regions=mask, merge_distance=500,
+                                                 merge_strands=False, min_transitive_len=0, min_dist=0))
+    # a mask that covers every row entirely: nothing comes back
+    full = ix.mask_csr({s: [(0, 60000)] for s in range(12)}, 12)
+    parts = sh.query_batch_bed_parts(b, params_pair(mode=1, masked_regions=full, merge_distance=1000)[1])
+    assert sum(p.n_results for p in parts) == 0
