@@ -60,10 +60,17 @@ WORKLOADS = {
     "c3": (50, 8, 2500000, 51, 100, 100, 1, 10000),   # BASELINE configs[2]: -x -m 2
     "c4": (200, 8, 2500000, 63, 200, 100, 1, 100000),  # BASELINE configs[3]: the config the metric is quoted on
     "c4p": (200, 8, 2500000, 63, 200, 100, 1, 5000),   # the c4 index with a short BED (profiling: two row batches)
+    # BASELINE configs[4], sparsified as SURVEY.md 8d allows: 500 genomes, every genome aligned against k = 50 others
+    # (12.6 M alignments, ~100 neighbours per genome in the bidirectional index), 125,000 rows per GPU = 1 M rows on
+    # 8 GPUs, -x -m 3
+    "c5": (500, 8, 2500000, 63, 400, 100, 1, 125000),
+    "c5p": (500, 8, 2500000, 63, 400, 100, 1, 4000),   # the c5 index with a short BED (one-GPU check of the depth-3 path)
 }
+PARTNERS = {"c5": 50, "c5p": 50}
+DEPTH = {"c2": 1, "c5": 3, "c5p": 3}
 # workloads whose CPU reference / parity oracle runs on the alignments of contig 0 only (per-row work is
 # identical to the full index: the synthetic world never aligns across contigs)
-SUBWORLD = {"c4", "c4p"}
+SUBWORLD = {"c4", "c4p", "c5", "c5p"}
 
 
 def peaks():
@@ -152,15 +159,16 @@ def host_threads():
 
 def workload_cfg(ix, name):
     g, c, L, a, eq, rev, seed, rows = WORKLOADS[name]
-    return ix.synth_cfg(g, c, L, a, eq, rev, seed), rows
+    return ix.synth_cfg(g, c, L, a, eq, rev, seed, partners=PARTNERS.get(name, 0)), rows
 
 
 def mode_params(ix_or_O, name, is_oracle=False):
-    depth1 = name == "c2"
+    depth = DEPTH.get(name, 2)
+    depth1 = depth == 1
     if is_oracle:
-        return ix_or_O.make_params(mode=ix_or_O.MODE_QUERY if depth1 else ix_or_O.MODE_BFS, max_depth=2,
+        return ix_or_O.make_params(mode=ix_or_O.MODE_QUERY if depth1 else ix_or_O.MODE_BFS, max_depth=depth,
                                    min_transitive_len=101, min_dist=10, merge_distance=1000, merge_strands=True)
-    return ix_or_O.make_params(mode=ix_or_O.MODE_QUERY if depth1 else ix_or_O.MODE_BFS, max_depth=2,
+    return ix_or_O.make_params(mode=ix_or_O.MODE_QUERY if depth1 else ix_or_O.MODE_BFS, max_depth=depth,
                                min_transitive_len=101, min_distance_between_ranges=10, merge_distance=1000,
                                merge_strands=True)
 
@@ -541,9 +549,12 @@ def main():
     g, c, L, a, eq, rev, seed, rows = WORKLOADS[name]
     if args.with_replicas is None:
         args.with_replicas = name in ("tiny", "c2", "c3")
-    config = {"workload": f"{name}: synthetic {g}-genome all-vs-all PAF, {g * (g - 1) * c * a} alignments, "
-                          f"{rows}-row BED per GPU, " + ("depth 1" if name == "c2" else "-x -m 2") + ", -d 1000 -o bed",
-              "genomes": g, "contigs": c, "contig_len": L, "alignments": g * (g - 1) * c * a, "bed_rows_per_gpu": rows,
+    k_partners = PARTNERS.get(name, 0) or g - 1
+    depth = DEPTH.get(name, 2)
+    config = {"workload": f"{name}: synthetic {g}-genome " + ("all-vs-all" if k_partners == g - 1 else f"sparsified (each genome vs {k_partners} others)") +
+                          f" PAF, {g * k_partners * c * a} alignments, "
+                          f"{rows}-row BED per GPU, " + ("depth 1" if depth == 1 else f"-x -m {depth}") + ", -d 1000 -o bed",
+              "genomes": g, "contigs": c, "contig_len": L, "alignments": g * k_partners * c * a, "bed_rows_per_gpu": rows,
               "parallelism": "one GPU holds the whole index", "cache": "inputs larger than L2 "
               "(index run stream >> 126 MB; every step re-reads it from HBM)"}
     import impg_b200 as ix

@@ -149,9 +149,10 @@ def make_refine_params(span_bp=1000, max_extension=0.5, extension_step=1000, sup
     return p
 
 
-class SynthCfg(C.Structure):
+class SynthCfg(C.Structure):  # impgx_synth_cfg (csrc/synth_core.h)
     _fields_ = [("genomes", C.c_uint32), ("contigs", C.c_uint32), ("contig_len", C.c_uint32), ("tiles", C.c_uint32),
-                ("eq_mean", C.c_uint32), ("rev_permille", C.c_uint32), ("seed", C.c_uint64)]
+                ("eq_mean", C.c_uint32), ("rev_permille", C.c_uint32), ("seed", C.c_uint64),
+                ("partners", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 def mask_csr(masked_regions, n_seqs):
@@ -999,10 +1000,12 @@ def project_batch(req, records, runs, run_offsets, device=0, want_cigar=True):
 
 
 # ---------------------------------------------------------------- synthetic data
-def synth_cfg(genomes, contigs, contig_len, tiles, eq_mean, rev_permille=100, seed=1):
+def synth_cfg(genomes, contigs, contig_len, tiles, eq_mean, rev_permille=100, seed=1, partners=0):
+    """`partners` = k > 0: every genome is aligned (as query) against k others only (sparsified pairs)."""
     c = SynthCfg()
     c.genomes, c.contigs, c.contig_len, c.tiles = genomes, contigs, contig_len, tiles
     c.eq_mean, c.rev_permille, c.seed = eq_mean, rev_permille, seed
+    c.partners = partners if 0 < partners < genomes - 1 else 0
     return c
 
 
@@ -1056,7 +1059,7 @@ def synth_generate_contig(cfg, contig=0):
     recs = np.zeros(n, dtype=RECORD_DTYPE)
     nr = np.zeros(n, dtype=np.uint32)
     _check_synth(L.impgx_synth_records(C.byref(cfg), C.c_uint64(0), C.c_uint64(n), _p(recs), _p(nr)))
-    pairs = cfg.genomes * (cfg.genomes - 1)
+    pairs = cfg.genomes * (cfg.partners if cfg.partners else cfg.genomes - 1)
     keep = ((np.arange(pairs, dtype=np.uint64)[:, None] * np.uint64(cfg.contigs) + np.uint64(contig))
             * np.uint64(cfg.tiles) + np.arange(cfg.tiles, dtype=np.uint64)[None, :]).ravel()
     sub_offs = np.zeros(len(keep) + 1, dtype=np.uint64)

@@ -26,6 +26,9 @@ typedef struct impgx_synth_cfg {
   uint32_t eq_mean;      /* mean '=' run length = 1 / divergence */
   uint32_t rev_permille; /* probability of '-' strand, in 1/1000 */
   uint64_t seed;
+  uint32_t partners;     /* 0: all-vs-all; k > 0: genome i is aligned (as query) against k others only,
+                            j = (i + 1 + m * ((G - 1) / k)) mod G for m < k (sparsified pairs) */
+  uint32_t reserved;
 } impgx_synth_cfg;
 
 struct SynthRng {
@@ -46,8 +49,11 @@ SYNTH_HD uint32_t synth_clz32(uint32_t v) {
 #endif
 }
 
+SYNTH_HD uint32_t synth_partners(const impgx_synth_cfg &c) {
+  return c.partners && c.partners < c.genomes - 1 ? c.partners : c.genomes - 1;
+}
 SYNTH_HD uint64_t synth_num_alignments(const impgx_synth_cfg &c) {
-  return (uint64_t)c.genomes * (c.genomes - 1) * c.contigs * c.tiles;
+  return (uint64_t)c.genomes * synth_partners(c) * c.contigs * c.tiles;
 }
 
 // Walks alignment n. With runs == nullptr only counts. Returns the run count
@@ -57,9 +63,11 @@ SYNTH_HD uint32_t synth_alignment(const impgx_synth_cfg &c, uint64_t n, impgx_re
   const uint32_t k = (uint32_t)(n % A);
   const uint32_t ctg = (uint32_t)((n / A) % C);
   const uint64_t p = n / ((uint64_t)A * C);
-  const uint32_t i = (uint32_t)(p / (G - 1));
-  const uint32_t jj = (uint32_t)(p % (G - 1));
-  const uint32_t j = jj < i ? jj : jj + 1;
+  const uint32_t K = synth_partners(c);
+  const uint32_t i = (uint32_t)(p / K);
+  const uint32_t jj = (uint32_t)(p % K);
+  // all-vs-all: every other genome in ascending order; sparsified: K partners spread evenly around the circle
+  const uint32_t j = K == G - 1 ? (jj < i ? jj : jj + 1) : (uint32_t)(((uint64_t)i + 1 + (uint64_t)jj * ((G - 1) / K)) % G);
   const uint32_t T = c.contig_len / A;
   uint32_t margin = T / 32;
   if (margin < 64) margin = 64;
