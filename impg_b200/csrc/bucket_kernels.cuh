@@ -43,24 +43,174 @@ __global__ void k_bucket_scatter_boxd(const BoxD *__restrict__ b, uint64_t n, ui
   }
 }
 
+__device__ __forceinline__ void store_seg_out(BoxRec *slot, int32_t qf, int32_t ql, uint32_t tid, int32_t tf, int32_t tl) {
+  SegOut *o = reinterpret_cast<SegOut *>(slot);
+  o->q_first = qf; o->q_last = ql; o->t_id = tid; o->t_first = tf; o->t_last = tl;
+}
+
+constexpr int TINY_MAX = 4;                 // buckets of up to this many boxes: one THREAD per bucket (k_merge_tiny)
+constexpr int TINY_CLASS = SEG_CLASSES + 1;  // list / counter index of the tiny buckets
+
 // bucket -> size class list; cls[c] = buckets of class c, cls[SEG_CLASSES] = buckets beyond SEG_MAX
-// (listed too, lists[SEG_CLASSES * cap ...]); min_class > 0 pushes small buckets into a larger class
-// (tests run every kernel variant on small data)
+// (listed too, lists[SEG_CLASSES * cap ...]), cls[TINY_CLASS] = buckets of <= TINY_MAX boxes; min_class > 0 pushes
+// small buckets into a larger class (tests run every kernel variant on small data)
 __global__ void k_bucket_classify(const uint32_t *__restrict__ beg, const uint32_t *__restrict__ cur, uint64_t n_buckets,
                                   uint32_t *__restrict__ lists, uint64_t cap, unsigned int *__restrict__ cls, int min_class) {
   for (uint64_t b = gtid(); b < n_buckets; b += gstride()) {
     const uint32_t n = cur[b] - beg[b];
     if (n == 0) continue;
     int c = min_class;
-    while (c < SEG_CLASSES && n > (uint32_t)seg_cap(c)) c++;
+    if (min_class == 0 && n <= (uint32_t)TINY_MAX) c = TINY_CLASS;
+    else
+      while (c < SEG_CLASSES && n > (uint32_t)seg_cap(c)) c++;
     const unsigned int k = atomicAdd(&cls[c], 1u);
     lists[(uint64_t)c * cap + k] = (uint32_t)b;
   }
 }
 
-__device__ __forceinline__ void store_seg_out(BoxRec *slot, int32_t qf, int32_t ql, uint32_t tid, int32_t tf, int32_t tl) {
-  SegOut *o = reinterpret_cast<SegOut *>(slot);
-  o->q_first = qf; o->q_last = ql; o->t_id = tid; o->t_first = tf; o->t_last = tl;
+// Buckets of at most TINY_MAX boxes (depth-1 queries: the two alignments of a genome pair; sparse worlds), one thread
+// each, everything in registers: stage A (pairwise relation on the original coordinates, then the hulls), the sort by
+// (start, !forward, ordinal) and the literal sweep of src/main.rs:12496-12556 — or, in reduce mode, the boxes whose end
+// exceeds every earlier end. Same semantics as k_merge_buckets, which spends a warp on such a bucket.
+__global__ void __launch_bounds__(128) k_merge_tiny(BoxRec *__restrict__ boxes, const uint32_t *__restrict__ beg,
+                                                    const uint32_t *__restrict__ cur, const uint32_t *__restrict__ list,
+                                                    uint32_t n_list, int64_t d, int merge_strands, int reduce,
+                                                    uint32_t *__restrict__ out_cnt) {
+  for (uint64_t li = gtid(); li < n_list; li += gstride()) {
+    const uint32_t bk = list[li];
+    const uint32_t b = beg[bk];
+    const int n = (int)(cur[bk] - b);
+    BoxRec *seg = boxes + b;
+    BoxRec x[TINY_MAX];
+#pragma unroll
+    for (int i = 0; i < TINY_MAX; i++)
+      if (i < n) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(seg + i);
+        const uint4 a = src[0], c = src[1];
+        x[i].ord = ((uint64_t)a.y << 32) | a.x;
+        x[i].q_first = (int32_t)a.z; x[i].q_last = (int32_t)a.w;
+        x[i].t_id = c.x; x[i].t_first = (int32_t)c.y; x[i].t_last = (int32_t)c.z; x[i].flags = c.w;
+      }
+    // ---- stage A: unions from the ORIGINAL coordinates of every pair of one (t, strand) group, then the hulls
+    int parent[TINY_MAX] = {0, 1, 2, 3};
+    if (d >= 0) {
+#pragma unroll
+      for (int i = 0; i < TINY_MAX; i++)
+#pragma unroll
+        for (int j = i + 1; j < TINY_MAX; j++) {
+          if (j >= n) continue;
+          const bool fi = x[i].q_first <= x[i].q_last, fj = x[j].q_first <= x[j].q_last;
+          if (x[i].t_id != x[j].t_id || fi != fj || ((x[i].flags | x[j].flags) & BOX_MERGED_A)) continue;
+          const int64_t ki = fi ? (int64_t)x[i].q_first : -(int64_t)x[i].q_first;
+          const int64_t kj = fi ? (int64_t)x[j].q_first : -(int64_t)x[j].q_first;
+          const bool i_first = ki < kj || (ki == kj && x[i].ord < x[j].ord);
+          const BoxRec &A = i_first ? x[i] : x[j];
+          const BoxRec &B = i_first ? x[j] : x[i];
+          const int64_t qa_start = fi ? A.q_first : A.q_last, qa_end = fi ? A.q_last : A.q_first;
+          const int64_t qb_start = fi ? B.q_first : B.q_last;
+          if (qb_start < qa_start || qb_start - qa_end > d) continue;
+          const int64_t t_gap = fi ? (int64_t)B.t_first - A.t_last : (int64_t)A.t_first - B.t_last;
+          const bool t_forward = fi ? B.t_first > A.t_first : B.t_last < A.t_last;
+          if (!t_forward || t_gap > d) continue;
+          int ri = i, rj = j;
+          while (parent[ri] != ri) ri = parent[ri];
+          while (parent[rj] != rj) rj = parent[rj];
+          if (ri != rj) parent[ri] = rj;
+        }
+    }
+    BoxRec r[TINY_MAX];
+    bool is_root[TINY_MAX];
+#pragma unroll
+    for (int i = 0; i < TINY_MAX; i++) {
+      is_root[i] = i < n && parent[i] == i;
+      if (i < n) r[i] = x[i];
+    }
+#pragma unroll
+    for (int i = 0; i < TINY_MAX; i++) {
+      if (i >= n || parent[i] == i) continue;
+      int rt = i;
+      while (parent[rt] != rt) rt = parent[rt];
+      const bool fwd = x[i].q_first <= x[i].q_last;
+#pragma unroll
+      for (int k = 0; k < TINY_MAX; k++)  // r[rt] with a compile-time index
+        if (k == rt) {
+          r[k].q_first = fwd ? min(r[k].q_first, x[i].q_first) : max(r[k].q_first, x[i].q_first);
+          r[k].q_last = fwd ? max(r[k].q_last, x[i].q_last) : min(r[k].q_last, x[i].q_last);
+          r[k].t_first = min(r[k].t_first, x[i].t_first);
+          r[k].t_last = max(r[k].t_last, x[i].t_last);
+          r[k].ord = min(r[k].ord, x[i].ord);
+        }
+    }
+    // ---- the roots in the order of the sweep: (start, !forward, ordinal)
+    int ordv[TINY_MAX];
+    int nr = 0;
+#pragma unroll
+    for (int i = 0; i < TINY_MAX; i++)
+      if (is_root[i]) {
+        const bool fi = r[i].q_first <= r[i].q_last;
+        const int32_t si = fi ? r[i].q_first : r[i].q_last;
+        int pos = 0;  // number of roots that sort before root i
+#pragma unroll
+        for (int j = 0; j < TINY_MAX; j++)
+          if (j != i && is_root[j]) {
+            const bool fj = r[j].q_first <= r[j].q_last;
+            const int32_t sj = fj ? r[j].q_first : r[j].q_last;
+            const bool before = sj < si || (sj == si && ((fj && !fi) || (fj == fi && r[j].ord < r[i].ord)));
+            pos += before ? 1 : 0;
+          }
+#pragma unroll
+        for (int k = 0; k < TINY_MAX; k++)
+          if (k == pos) ordv[k] = i;
+        nr++;
+      }
+    auto get = [&](int k) -> BoxRec {  // root at sorted position k
+      BoxRec o = r[0];
+#pragma unroll
+      for (int i = 1; i < TINY_MAX; i++)
+        if (ordv[k] == i) o = r[i];
+      return o;
+    };
+    uint32_t w = 0;
+    const int32_t md = (int32_t)d;
+    if (reduce) {
+      const bool prune = merge_strands && md >= 0;
+      int32_t pm = INT32_MIN;
+      for (int k = 0; k < nr; k++) {
+        const BoxRec o = get(k);
+        const int32_t en = max(o.q_first, o.q_last);
+        if (!prune || k == 0 || en > pm) {
+          uint4 *dst = reinterpret_cast<uint4 *>(seg + w);
+          dst[0] = make_uint4((uint32_t)o.ord, (uint32_t)(o.ord >> 32), (uint32_t)o.q_first, (uint32_t)o.q_last);
+          dst[1] = make_uint4(o.t_id, (uint32_t)o.t_first, (uint32_t)o.t_last, BOX_MERGED_A);
+          w++;
+        }
+        pm = max(pm, en);
+      }
+    } else {
+      BoxRec c0 = get(0);
+      bool cf = c0.q_first <= c0.q_last;
+      int32_t cs = cf ? c0.q_first : c0.q_last, ce = cf ? c0.q_last : c0.q_first;
+      uint32_t ct = c0.t_id;
+      int32_t ctf = c0.t_first, ctl = c0.t_last;
+      for (int k = 1; k < nr; k++) {
+        const BoxRec nx = get(k);
+        const bool nf = nx.q_first <= nx.q_last;
+        const int32_t ns = nf ? nx.q_first : nx.q_last, ne = nf ? nx.q_last : nx.q_first;
+        if (md < 0 || (!merge_strands && cf != nf) || (int64_t)ns > (int64_t)ce + md) {
+          store_seg_out(seg + w, cf ? cs : ce, cf ? ce : cs, ct, ctf, ctl);
+          w++;
+          cs = ns; ce = ne; cf = nf; ct = nx.t_id; ctf = nx.t_first; ctl = nx.t_last;
+        } else {
+          if (merge_strands && cf != nf && ((int64_t)ne - ns) > ((int64_t)ce - cs)) cf = nf;
+          cs = min(cs, ns);
+          ce = max(ce, ne);
+        }
+      }
+      store_seg_out(seg + w, cf ? cs : ce, cf ? ce : cs, ct, ctf, ctl);
+      w++;
+    }
+    out_cnt[bk] = w;
+  }
 }
 
 // Shared-memory view of one bucket (46 bytes per box).

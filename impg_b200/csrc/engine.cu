@@ -1153,13 +1153,13 @@ void Runner::bk_add_boxd(Buckets &bk, const BoxD *boxes, uint64_t n, bool scatte
 float Runner::run_bucket_kernels(Buckets &bk, uint32_t *out_cnt, bool reduce) {
   const uint64_t NB = bk.NB;
   const uint64_t cap = std::min<uint64_t>(NB, bk.total);
-  DBuf<uint32_t> lists((uint64_t)(SEG_CLASSES + 1) * cap, ar_);
-  DBuf<unsigned int> cls(SEG_CLASSES + 1, ar_);
-  CUDA_CHECK(cudaMemsetAsync(cls.get(), 0, (SEG_CLASSES + 1) * 4, s_));
+  DBuf<uint32_t> lists((uint64_t)(SEG_CLASSES + 2) * cap, ar_);
+  DBuf<unsigned int> cls(SEG_CLASSES + 2, ar_);
+  CUDA_CHECK(cudaMemsetAsync(cls.get(), 0, (SEG_CLASSES + 2) * 4, s_));
   int min_class = (int)env_u64("IMPGX_SEG_MIN_CLASS", 0);  // test hook: run the larger-bucket kernels on small data
   if (min_class < 0 || min_class >= SEG_CLASSES) min_class = 0;
   LAUNCH(k_bucket_classify, grid_threads(NB), 256, s_, bk.beg.get(), bk.cur.get(), NB, lists.get(), cap, cls.get(), min_class);
-  unsigned int hc[SEG_CLASSES + 1];
+  unsigned int hc[SEG_CLASSES + 2];
   {
     static_assert(sizeof(hc) <= 32, "class counters must fit the readback slot");
     uint64_t *h = readback_slot();
@@ -1170,6 +1170,13 @@ float Runner::run_bucket_kernels(Buckets &bk, uint32_t *out_cnt, bool reduce) {
   ctx.d2h_bytes += sizeof(hc);
   const int64_t d = p_.merge_distance;
   const int ms = p_.merge_strands ? 1 : 0;
+  cudaEvent_t k0, k1;
+  CUDA_CHECK(cudaEventCreate(&k0));
+  CUDA_CHECK(cudaEventCreate(&k1));
+  CUDA_CHECK(cudaEventRecord(k0, s_));
+  if (hc[TINY_CLASS])  // one thread per bucket of <= 4 boxes
+    LAUNCH(k_merge_tiny, grid_threads(hc[TINY_CLASS], 128, 16), 128, s_, bk.boxes.get(), bk.beg.get(), bk.cur.get(),
+           lists.get() + (uint64_t)TINY_CLASS * cap, hc[TINY_CLASS], d, ms, reduce ? 1 : 0, out_cnt);
   auto launch = [&](auto kern, unsigned threads, size_t smem, unsigned per_sm, unsigned seg_per_cta, int c) {
     if (!hc[c]) return;
     CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1180,10 +1187,6 @@ float Runner::run_bucket_kernels(Buckets &bk, uint32_t *out_cnt, bool reduce) {
     CUDA_CHECK(cudaGetLastError());
     ctx.launches++;
   };
-  cudaEvent_t k0, k1;
-  CUDA_CHECK(cudaEventCreate(&k0));
-  CUDA_CHECK(cudaEventCreate(&k1));
-  CUDA_CHECK(cudaEventRecord(k0, s_));
   launch(k_merge_buckets<32, seg_cap(0)>, 256, (size_t)8 * seg_cap(0) * BK_BYTES, 4, 8, 0);
   launch(k_merge_buckets<32, seg_cap(1)>, 256, (size_t)8 * seg_cap(1) * BK_BYTES, 2, 8, 1);
   {
