@@ -256,6 +256,49 @@ __device__ __forceinline__ void ranges_insert(int2 *L, uint32_t &m, int32_t seq_
 // one thread per (row, query sequence): the visited set is keyed by sequence,
 // so hits only interact within such a group; inside the group they are
 // processed in the reference's order (frontier order, then visit order).
+__device__ __forceinline__ void fold_one_group(const FoldGroup &fg, const Hit *__restrict__ hits,
+                                               const int32_t *__restrict__ v_start, const int32_t *__restrict__ v_end,
+                                               const int32_t *__restrict__ seq_len, int32_t min_dist,
+                                               int32_t min_transitive_len, int2 *__restrict__ lists,
+                                               Frontier *__restrict__ pieces, const uint64_t *__restrict__ mask_off,
+                                               const int2 *__restrict__ mask_rng, uint32_t &list_len_out,
+                                               uint32_t &piece_cnt_out) {
+  int2 *L = lists + fg.list_off;
+  uint32_t m = 0;
+  const uint32_t row = (uint32_t)(fg.key >> 32), seq = (uint32_t)fg.key;
+  for (uint32_t v = fg.v_begin; v < fg.v_end; v++) L[m++] = make_int2(v_start[v], v_end[v]);
+  if (fg.v_begin == fg.v_end && mask_off)
+    for (uint64_t k = mask_off[seq]; k < mask_off[seq + 1]; k++) L[m++] = mask_rng[k];
+  const int32_t slen = seq_len[seq];
+  Frontier *P = pieces + fg.piece_off;
+  uint32_t np = 0;
+  for (uint32_t h = fg.hit_begin; h < fg.hit_end; h++) {
+    const Hit hit = hits[h];
+    const int32_t a = hit.q_first, b = hit.q_last;
+    bool should_add = true;
+    if (min_dist > 0) {
+      const int32_t new_min = min(a, b), new_max = max(a, b);
+      const uint32_t idx = ranges_lower_bound(L, m, new_min);
+      if (idx > 0) {
+        long long d = (long long)new_min - (long long)L[idx - 1].y;
+        if ((d < 0 ? -d : d) < min_dist) should_add = false;
+      }
+      if (should_add && idx < m) {
+        long long d = (long long)L[idx].x - (long long)new_max;
+        if ((d < 0 ? -d : d) < min_dist) should_add = false;
+      }
+    }
+    if (should_add) {
+      ranges_insert(L, m, slen, a, b, [&](int32_t s, int32_t e) {
+        long long len = (long long)e - (long long)s;
+        if ((len < 0 ? -len : len) >= min_transitive_len) P[np++] = Frontier{row, seq, s, e};
+      });
+    }
+  }
+  list_len_out = m;
+  piece_cnt_out = np;
+}
+
 __global__ void __launch_bounds__(128) k_fold(const FoldGroup *__restrict__ groups, uint64_t n_groups,
                                               const Hit *__restrict__ hits, const int32_t *__restrict__ v_start,
                                               const int32_t *__restrict__ v_end, const int32_t *__restrict__ seq_len,
@@ -264,39 +307,9 @@ __global__ void __launch_bounds__(128) k_fold(const FoldGroup *__restrict__ grou
                                               uint32_t *__restrict__ piece_cnt, const uint64_t *__restrict__ mask_off,
                                               const int2 *__restrict__ mask_rng) {
   for (uint64_t g = gtid(); g < n_groups; g += gstride()) {
-    const FoldGroup fg = groups[g];
-    int2 *L = lists + fg.list_off;
-    uint32_t m = 0;
-    const uint32_t row = (uint32_t)(fg.key >> 32), seq = (uint32_t)fg.key;
-    for (uint32_t v = fg.v_begin; v < fg.v_end; v++) L[m++] = make_int2(v_start[v], v_end[v]);
-    if (fg.v_begin == fg.v_end && mask_off)
-      for (uint64_t k = mask_off[seq]; k < mask_off[seq + 1]; k++) L[m++] = mask_rng[k];
-    const int32_t slen = seq_len[seq];
-    Frontier *P = pieces + fg.piece_off;
-    uint32_t np = 0;
-    for (uint32_t h = fg.hit_begin; h < fg.hit_end; h++) {
-      const Hit hit = hits[h];
-      const int32_t a = hit.q_first, b = hit.q_last;
-      bool should_add = true;
-      if (min_dist > 0) {
-        const int32_t new_min = min(a, b), new_max = max(a, b);
-        const uint32_t idx = ranges_lower_bound(L, m, new_min);
-        if (idx > 0) {
-          long long d = (long long)new_min - (long long)L[idx - 1].y;
-          if ((d < 0 ? -d : d) < min_dist) should_add = false;
-        }
-        if (should_add && idx < m) {
-          long long d = (long long)L[idx].x - (long long)new_max;
-          if ((d < 0 ? -d : d) < min_dist) should_add = false;
-        }
-      }
-      if (should_add) {
-        ranges_insert(L, m, slen, a, b, [&](int32_t s, int32_t e) {
-          long long len = (long long)e - (long long)s;
-          if ((len < 0 ? -len : len) >= min_transitive_len) P[np++] = Frontier{row, seq, s, e};
-        });
-      }
-    }
+    uint32_t m = 0, np = 0;
+    fold_one_group(groups[g], hits, v_start, v_end, seq_len, min_dist, min_transitive_len, lists, pieces, mask_off,
+                   mask_rng, m, np);
     list_len[g] = m;
     piece_cnt[g] = np;
   }

@@ -75,7 +75,9 @@ __global__ void k_bucket_classify(const uint32_t *__restrict__ beg, const uint32
 __global__ void __launch_bounds__(128) k_merge_tiny(BoxRec *__restrict__ boxes, const uint32_t *__restrict__ beg,
                                                     const uint32_t *__restrict__ cur, const uint32_t *__restrict__ list,
                                                     uint32_t n_list, int64_t d, int merge_strands, int reduce,
-                                                    uint32_t *__restrict__ out_cnt) {
+                                                    uint32_t *__restrict__ out_cnt,
+                                                    const unsigned int *__restrict__ n_list_dev) {
+  if (n_list_dev) n_list = *n_list_dev;  // small_bfs.cuh: the list was built by the launch before, nobody read its length
   for (uint64_t li = gtid(); li < n_list; li += gstride()) {
     const uint32_t bk = list[li];
     const uint32_t b = beg[bk];
@@ -242,8 +244,9 @@ template <int T, int CAP>
 __global__ void __launch_bounds__(T == 32 ? 256 : T)
     k_merge_buckets(BoxRec *__restrict__ boxes, const uint32_t *__restrict__ beg, const uint32_t *__restrict__ cur,
                     const uint32_t *__restrict__ list, uint32_t n_list, int64_t d, int merge_strands, int reduce,
-                    uint32_t *__restrict__ out_cnt) {
+                    uint32_t *__restrict__ out_cnt, const unsigned int *__restrict__ n_list_dev) {
   extern __shared__ __align__(16) unsigned char seg_smem[];
+  if (n_list_dev) n_list = *n_list_dev;  // small_bfs.cuh: list length left on the device
   constexpr int GROUPS = (T == 32) ? 8 : 1;  // buckets in flight per CTA
   const int gi = (T == 32) ? (int)(threadIdx.x >> 5) : 0;
   const int lt = (T == 32) ? (int)(threadIdx.x & 31u) : (int)threadIdx.x;

@@ -15,6 +15,7 @@
 #include "bucket_kernels.cuh"
 #include "merge_kernels.cuh"
 #include "shard_kernels.cuh"
+#include "small_bfs.cuh"
 
 namespace impgx {
 
@@ -1176,14 +1177,15 @@ float Runner::run_bucket_kernels(Buckets &bk, uint32_t *out_cnt, bool reduce) {
   CUDA_CHECK(cudaEventRecord(k0, s_));
   if (hc[TINY_CLASS])  // one thread per bucket of <= 4 boxes
     LAUNCH(k_merge_tiny, grid_threads(hc[TINY_CLASS], 128, 16), 128, s_, bk.boxes.get(), bk.beg.get(), bk.cur.get(),
-           lists.get() + (uint64_t)TINY_CLASS * cap, hc[TINY_CLASS], d, ms, reduce ? 1 : 0, out_cnt);
+           lists.get() + (uint64_t)TINY_CLASS * cap, hc[TINY_CLASS], d, ms, reduce ? 1 : 0, out_cnt,
+           (const unsigned int *)nullptr);
   auto launch = [&](auto kern, unsigned threads, size_t smem, unsigned per_sm, unsigned seg_per_cta, int c) {
     if (!hc[c]) return;
     CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid =
         (unsigned)std::min<uint64_t>(((uint64_t)hc[c] + seg_per_cta - 1) / seg_per_cta, (uint64_t)sm_count() * per_sm);
     kern<<<grid, threads, smem, s_>>>(bk.boxes.get(), bk.beg.get(), bk.cur.get(), lists.get() + (uint64_t)c * cap, hc[c], d,
-                                      ms, reduce ? 1 : 0, out_cnt);
+                                      ms, reduce ? 1 : 0, out_cnt, (const unsigned int *)nullptr);
     CUDA_CHECK(cudaGetLastError());
     ctx.launches++;
   };
@@ -1282,6 +1284,20 @@ void Runner::merge_oversized(Buckets &bk, const uint32_t *list, uint32_t n_over,
   stage_b(acc.get(), is_root.get(), n, rc.get(), n_rows, none, nullptr, &bk, out_cnt);
 }
 
+// masked_regions as the reference holds them: one SortedRanges per sequence. Returns the number of ranges.
+static uint64_t validate_masks(const impgx_params &p, uint32_t n_seqs) {
+  REQUIRE(p.mask_ranges || p.mask_offsets[n_seqs] == 0, IMPGX_E_INVALID, "mask_ranges is NULL");
+  for (uint32_t q = 0; q < n_seqs; q++) {
+    REQUIRE(p.mask_offsets[q] <= p.mask_offsets[q + 1], IMPGX_E_INVALID, "mask_offsets not monotone");
+    for (uint64_t k = p.mask_offsets[q]; k < p.mask_offsets[q + 1]; k++) {
+      const int32_t a = p.mask_ranges[2 * k], b = p.mask_ranges[2 * k + 1];
+      REQUIRE(a <= b && (k == p.mask_offsets[q] || p.mask_ranges[2 * k - 1] < a), IMPGX_E_INVALID,
+              "masked regions of a sequence must be sorted and disjoint (a SortedRanges)");
+    }
+  }
+  return p.mask_offsets[n_seqs];
+}
+
 void Runner::prepare(const impgx_range *d_ranges, uint32_t n_rows) {
   d_counters_.alloc(4, ar_);
   // validation (perform_query bounds checks)
@@ -1306,16 +1322,7 @@ void Runner::prepare(const impgx_range *d_ranges, uint32_t n_rows) {
   const bool transitive = p_.mode != IMPGX_MODE_QUERY && p_.mode != IMPGX_MODE_MULTI_QUERY;
   masked_ = transitive && p_.mask_offsets != nullptr;
   if (masked_) {
-    REQUIRE(p_.mask_ranges || p_.mask_offsets[ix_.n_seqs] == 0, IMPGX_E_INVALID, "mask_ranges is NULL");
-    const uint64_t nm = p_.mask_offsets[ix_.n_seqs];
-    for (uint32_t q = 0; q < ix_.n_seqs; q++) {
-      REQUIRE(p_.mask_offsets[q] <= p_.mask_offsets[q + 1], IMPGX_E_INVALID, "mask_offsets not monotone");
-      for (uint64_t k = p_.mask_offsets[q]; k < p_.mask_offsets[q + 1]; k++) {
-        const int32_t a = p_.mask_ranges[2 * k], b = p_.mask_ranges[2 * k + 1];
-        REQUIRE(a <= b && (k == p_.mask_offsets[q] || p_.mask_ranges[2 * k - 1] < a), IMPGX_E_INVALID,
-                "masked regions of a sequence must be sorted and disjoint (a SortedRanges)");
-      }
-    }
+    const uint64_t nm = validate_masks(p_, ix_.n_seqs);
     d_mask_off_.alloc((uint64_t)ix_.n_seqs + 1, ar_);
     d_mask_rng_.alloc(std::max<uint64_t>(nm, 1), ar_);
     CUDA_CHECK(cudaMemcpyAsync(d_mask_off_.get(), p_.mask_offsets, ((size_t)ix_.n_seqs + 1) * 8, cudaMemcpyHostToDevice, s_));
@@ -2464,6 +2471,197 @@ static uint64_t env_u64(const char *name, uint64_t dflt) {
   return strtoull(v, nullptr, 10);
 }
 
+
+// ---- calls of a few rows: the whole walk in one launch (small_bfs.cuh). Returns false when the call is not
+// eligible or a row did not fit the capacities; the caller then runs the batched path.
+static bool small_eligible(const impgx_index *idx, size_t n, const impgx_params &p, bool bed, bool results_to_host,
+                           const Comm *comm) {
+  if (n == 0 || n > SB_MAX_ROWS || comm || !results_to_host || !idx->owner.empty()) return false;
+  if (p.mode != IMPGX_MODE_BFS && p.mode != IMPGX_MODE_QUERY) return false;
+  if (p.store_cigar || !std::isnan(p.min_identity)) return false;  // the endpoint liftover carries no CIGAR
+  if (bed && p.merge_distance < 0 && !p.merge_strands) return false;  // unsorted output: reference order per row
+  // diagnostic / test switches of the batched path keep selecting it
+  for (const char *v : {"IMPGX_NO_SMALL_BFS", "IMPGX_MERGE_SORTED", "IMPGX_MERGE_GLOBAL", "IMPGX_BED_GENERIC",
+                        "IMPGX_FULL_SCAN", "IMPGX_SEG_MIN_CLASS", "IMPGX_ROWS_PER_BATCH", "IMPGX_NO_LOCALITY"})
+    if (getenv(v)) return false;
+  return true;
+}
+
+static bool try_small(impgx_index *idx, const impgx_range *ranges, size_t n, const impgx_params &p, bool bed,
+                      bool ranges_on_device, cudaStream_t s, Arena &arena, impgx_results *res, Ctx &ctx) {
+  {
+    std::lock_guard<std::mutex> lock(idx->mu);
+    if (idx->small_skip > 0) {  // recent calls did not fit: do not pay for the attempt every time
+      idx->small_skip--;
+      return false;
+    }
+  }
+  const uint32_t R = (uint32_t)n;
+  const DevIndexView view = idx->view();
+  const bool query_mode = p.mode == IMPGX_MODE_QUERY;
+  const bool masked = !query_mode && p.mask_offsets != nullptr;
+  SbParams sp{};
+  sp.n_rows = R;
+  sp.max_depth = p.max_depth;
+  sp.min_transitive_len = p.min_transitive_len;
+  sp.min_dist = p.min_distance_between_ranges;
+  sp.min_out = p.min_output_length;
+  sp.query_mode = query_mode ? 1 : 0;
+  sp.bed = bed ? 1 : 0;
+
+  const impgx_range *d_r = ranges;
+  DBuf<impgx_range> d_stage;
+  if (!ranges_on_device) {
+    d_stage.alloc(R, arena);
+    CUDA_CHECK(cudaMemcpyAsync(d_stage.get(), ranges, (size_t)R * sizeof(impgx_range), cudaMemcpyHostToDevice, s));
+    ctx.h2d_bytes += (size_t)R * sizeof(impgx_range);
+    d_r = d_stage.get();
+  }
+  DBuf<uint64_t> d_mask_off;
+  DBuf<int2> d_mask_rng;
+  if (masked) {
+    const uint64_t nm = validate_masks(p, view.n_seqs);
+    d_mask_off.alloc((uint64_t)view.n_seqs + 1, arena);
+    d_mask_rng.alloc(std::max<uint64_t>(nm, 1), arena);
+    CUDA_CHECK(cudaMemcpyAsync(d_mask_off.get(), p.mask_offsets, ((size_t)view.n_seqs + 1) * 8, cudaMemcpyHostToDevice, s));
+    if (nm) CUDA_CHECK(cudaMemcpyAsync(d_mask_rng.get(), p.mask_ranges, nm * 8, cudaMemcpyHostToDevice, s));
+    ctx.h2d_bytes += ((size_t)view.n_seqs + 1) * 8 + nm * 8;
+    sp.mask_off = d_mask_off.get();
+    sp.mask_rng = d_mask_rng.get();
+  }
+  DBuf<uint8_t> d_subset;
+  if (p.subset_mask) {
+    d_subset.alloc(view.n_seqs, arena);
+    CUDA_CHECK(cudaMemcpyAsync(d_subset.get(), p.subset_mask, view.n_seqs, cudaMemcpyHostToDevice, s));
+    ctx.h2d_bytes += view.n_seqs;
+    sp.subset = d_subset.get();
+  }
+
+  SbCall c{};
+  c.row_bytes = sb_row_bytes();
+  DBuf<char> rows((size_t)R * c.row_bytes, arena);
+  c.rows = rows.get();
+  DBuf<uint32_t> per_row((size_t)4 * R, arena);
+  c.row_target = per_row.get();
+  c.status = per_row.get() + R;
+  c.n_res = per_row.get() + 2 * (size_t)R;
+  c.n_bk = per_row.get() + 3 * (size_t)R;
+  // zeroed counters: [0..1] stats, then the class list lengths
+  DBuf<unsigned long long> zeroed(2 + (SEG_CLASSES + 2 + 1) / 2, arena);
+  CUDA_CHECK(cudaMemsetAsync(zeroed.get(), 0, zeroed.bytes(), s));
+  c.stats = zeroed.get();
+  c.cls = reinterpret_cast<unsigned int *>(zeroed.get() + 2);
+  const uint64_t cap = (uint64_t)R * SB_CAP;
+  DBuf<BoxRec> boxes;
+  DBuf<uint32_t> bk, lists;
+  if (bed) {
+    boxes.alloc(cap, arena);
+    bk.alloc(4 * cap, arena);
+    lists.alloc((uint64_t)(SEG_CLASSES + 2) * cap, arena);
+    c.boxes = boxes.get();
+    c.bk_beg = bk.get();
+    c.bk_cur = bk.get() + cap;
+    c.bk_q = bk.get() + 2 * cap;
+    c.out_cnt = bk.get() + 3 * cap;
+    c.lists = lists.get();
+  }
+  const size_t hdr_bytes = (((size_t)R + 4) * 4 + 7) & ~(size_t)7;
+  DBuf<char> outbuf(hdr_bytes + cap * sizeof(SbOut), arena);
+  c.hdr = reinterpret_cast<uint32_t *>(outbuf.get());
+  c.out = reinterpret_cast<SbOut *>(outbuf.get() + hdr_bytes);
+
+  {
+    static std::mutex attr_mu;
+    static bool attr_done[64] = {false};
+    std::lock_guard<std::mutex> lock(attr_mu);
+    if (idx->device < 0 || idx->device >= 64 || !attr_done[idx->device]) {
+      CUDA_CHECK(cudaFuncSetAttribute(k_small_bfs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SB_SMEM));
+      CUDA_CHECK(cudaFuncSetAttribute(k_merge_buckets<32, seg_cap(0)>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * seg_cap(0) * BK_BYTES));
+      CUDA_CHECK(cudaFuncSetAttribute(k_merge_buckets<32, seg_cap(1)>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * seg_cap(1) * BK_BYTES));
+      CUDA_CHECK(cudaFuncSetAttribute(k_merge_buckets<128, seg_cap(2)>, cudaFuncAttributeMaxDynamicSharedMemorySize, seg_cap(2) * BK_BYTES));
+      CUDA_CHECK(cudaFuncSetAttribute(k_merge_buckets<128, seg_cap(3)>, cudaFuncAttributeMaxDynamicSharedMemorySize, seg_cap(3) * BK_BYTES));
+      CUDA_CHECK(cudaFuncSetAttribute(k_merge_buckets<512, seg_cap(4)>, cudaFuncAttributeMaxDynamicSharedMemorySize, seg_cap(4) * BK_BYTES));
+      if (idx->device >= 0 && idx->device < 64) attr_done[idx->device] = true;
+    }
+  }
+  k_small_bfs<<<R, SB_THREADS, SB_SMEM, s>>>(view, d_r, sp, c);
+  CUDA_CHECK(cudaGetLastError());
+  ctx.launches++;
+  if (bed) {
+    // the bucket merge of the batched path, on the lists the walk left on the device (fixed grids, strided loops)
+    const int64_t d = p.merge_distance;
+    const int ms = p.merge_strands ? 1 : 0;
+    auto list_of = [&](int cl) { return c.lists + (uint64_t)cl * cap; };
+    k_merge_tiny<<<4 * R, 128, 0, s>>>(c.boxes, c.bk_beg, c.bk_cur, list_of(TINY_CLASS), 0u, d, ms, 0, c.out_cnt,
+                                       c.cls + TINY_CLASS);
+    k_merge_buckets<32, seg_cap(0)><<<4 * R, 256, 8 * seg_cap(0) * BK_BYTES, s>>>(c.boxes, c.bk_beg, c.bk_cur, list_of(0), 0u,
+                                                                                 d, ms, 0, c.out_cnt, c.cls + 0);
+    k_merge_buckets<32, seg_cap(1)><<<2 * R, 256, 8 * seg_cap(1) * BK_BYTES, s>>>(c.boxes, c.bk_beg, c.bk_cur, list_of(1), 0u,
+                                                                                 d, ms, 0, c.out_cnt, c.cls + 1);
+    k_merge_buckets<128, seg_cap(2)><<<8 * R, 128, seg_cap(2) * BK_BYTES, s>>>(c.boxes, c.bk_beg, c.bk_cur, list_of(2), 0u, d,
+                                                                              ms, 0, c.out_cnt, c.cls + 2);
+    k_merge_buckets<128, seg_cap(3)><<<4 * R, 128, seg_cap(3) * BK_BYTES, s>>>(c.boxes, c.bk_beg, c.bk_cur, list_of(3), 0u, d,
+                                                                              ms, 0, c.out_cnt, c.cls + 3);
+    k_merge_buckets<512, seg_cap(4)><<<2 * R, 512, seg_cap(4) * BK_BYTES, s>>>(c.boxes, c.bk_beg, c.bk_cur, list_of(4), 0u, d,
+                                                                              ms, 0, c.out_cnt, c.cls + 4);
+    CUDA_CHECK(cudaGetLastError());
+    ctx.launches += 6;
+  }
+  k_small_finish<<<1, SB_THREADS, 0, s>>>(sp, c);
+  CUDA_CHECK(cudaGetLastError());
+  ctx.launches++;
+
+  // header + the first rows in one copy; the rest only when there is more
+  constexpr size_t SPEC = 2048;
+  const size_t spec_bytes = hdr_bytes + std::min<size_t>(SPEC, cap) * sizeof(SbOut);
+  size_t pcap = 0;
+  char *h = (char *)pinned_acquire(spec_bytes, &pcap);
+  struct Release {
+    void *p;
+    size_t cap;
+    ~Release() { pinned_release(p, cap); }
+  } rel{h, pcap};
+  CUDA_CHECK(cudaMemcpyAsync(h, outbuf.get(), spec_bytes, cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  ctx.d2h_bytes += spec_bytes;
+  const uint32_t *hdr = reinterpret_cast<const uint32_t *>(h);
+  const uint32_t worst = hdr[R + 1];
+  if (worst != SB_OK) {
+    if (worst == SB_OVERFLOW) {
+      std::lock_guard<std::mutex> lock(idx->mu);
+      idx->small_penalty = std::min<uint32_t>(std::max<uint32_t>(idx->small_penalty * 2, 1u), 256u);
+      idx->small_skip = idx->small_penalty;
+    }
+    return false;  // SB_INVALID: the batched path words the error
+  }
+  {
+    std::lock_guard<std::mutex> lock(idx->mu);
+    idx->small_penalty = 0;
+  }
+  const size_t total = hdr[R];
+  std::vector<SbOut> rest;
+  if (total > SPEC) {
+    rest.resize(total - SPEC);
+    CUDA_CHECK(cudaMemcpyAsync(rest.data(), c.out + SPEC, (total - SPEC) * sizeof(SbOut), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    ctx.d2h_bytes += (total - SPEC) * sizeof(SbOut);
+  }
+  for (uint32_t i = 0; i <= R; i++) res->row_off[i] = hdr[i];
+  res->qid.resize(total); res->tid.resize(total);
+  res->qf.resize(total); res->ql.resize(total);
+  res->tf.resize(total); res->tl.resize(total);
+  const SbOut *first = reinterpret_cast<const SbOut *>(h + hdr_bytes);
+  for (size_t i = 0; i < total; i++) {
+    const SbOut &o = i < SPEC ? first[i] : rest[i - SPEC];
+    res->qid[i] = o.q_id; res->qf[i] = o.q_first; res->ql[i] = o.q_last;
+    res->tid[i] = o.t_id; res->tf[i] = o.t_first; res->tl[i] = o.t_last;
+  }
+  ctx.stab_ranges += hdr[R + 2];
+  ctx.liftovers += hdr[R + 3];
+  ctx.lift_launches++;
+  return true;
+}
+
 impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n, const impgx_params &p, bool bed,
                            bool ranges_on_device, bool results_to_host, void *stream, Comm *comm) {
   REQUIRE(idx, IMPGX_E_INVALID, "index is NULL");
@@ -2528,6 +2726,14 @@ impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n
   size_t done = 0;
   uint64_t res_base = 0, cig_base = 0;
   try {
+    if (small_eligible(idx, n, p, bed, results_to_host, comm)) {
+      REQUIRE(!(bed && p.store_cigar), IMPGX_E_INVALID, "BED output carries no CIGAR (src/main.rs:7447)");
+      if (try_small(idx, ranges, n, p, bed, ranges_on_device, s, arena, res.get(), total)) {
+        done = n;
+        res_base = res->qid.size();
+      }
+      arena.reset();
+    }
     while (done < n) {
       const size_t m = std::min(next_chunk(), n - done);
       uint64_t chunk_hits = 0;

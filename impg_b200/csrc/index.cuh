@@ -69,6 +69,9 @@ struct impgx_index {
   std::vector<cudaStream_t> stream_pool;
   impgx_stats last{};
   double hits_per_row = 0;  // observed liftovers per row (sizes the row batches)
+  // single-launch path for calls of a few rows (small_bfs.cuh): calls still to skip after a row did not fit, and
+  // the current back-off (doubles per overflow, cleared by a call that fits)
+  uint32_t small_skip = 0, small_penalty = 0;
   bool original_coordinates = false;  // writers: --original-sequence-coordinates (src/main.rs:4661-4678)
   // target-sharded index: this object holds the entries of the
   // sequences with owner[seq] == shard_rank; empty owner = the whole index

@@ -711,9 +711,173 @@ struct BucketOut {
   uint32_t level;        // ord level of the hop
 };
 
+// One endpoint liftover: project_target_range_through_alignment (src/impg.rs:2760-2898) of the range `f` through tree
+// entry `entry`, by one thread; only the first and the last overlapping op are located (checkpoint search from an
+// interpolated guess + one or two run blocks per end).
+struct EndsHit {
+  bool ok;
+  uint32_t query_id, vrank;
+  int32_t f_q, l_q, f_t, l_t;
+  uint32_t nread, nck, r_ov;  // runs read, checkpoints probed, runs inside the window (roofline accounting)
+};
+
 // OVL: the dependent gathers of a hit are issued in two waves instead of four steps — both checkpoint sectors
 // (the end-side guess is absolute instead of relative to the start-side result), then the checkpoints and run
 // blocks of both ends — so a hit waits for three memory round trips (entry, sectors, blocks) instead of five.
+template <bool OVL>
+__device__ __forceinline__ EndsHit lift_ends_hit(const DevIndexView &ix, const Frontier &f, uint32_t entry,
+                                                 const LiftParams &lp) {
+  const uint4 *rp = reinterpret_cast<const uint4 *>(ix.e_rec + entry);
+  const uint4 r0 = rp[0], r1 = rp[1];
+  const int32_t t_start = (int32_t)r0.x, t_end = (int32_t)r0.y, q_start = (int32_t)r0.z, q_end = (int32_t)r0.w;
+  const uint32_t query_id = r1.x, nruns_flags = r1.y, aln_off = r1.z, vrank = r1.w;
+  int32_t rs = f.start, re = f.end;
+  if (lp.clip) {
+    rs = max(rs, t_start);
+    re = min(re, t_end);
+  }
+  const uint32_t n = nruns_flags >> 2;
+  const bool rev_strand = nruns_flags & FLAG_STRAND;
+  const bool swap_id = nruns_flags & FLAG_REVERSED;
+  const bool backward = swap_id && rev_strand;
+  const int32_t dir = rev_strand ? -1 : 1;
+  const uint32_t nblk = aln_nblk(n);
+  const Checkpoint *ck = aln_ck(ix.stream, aln_off);
+  const uint32_t *blk = aln_runs(ix.stream, aln_off, nblk);
+  const int32_t last_target_pos = min(t_end, re);
+  const int64_t rel = (int64_t)rs - t_start, rel_l = (int64_t)last_target_pos - t_start;
+
+  // in this orientation: the op that consumes no target (insertion) / no query (deletion)
+  const uint32_t op_t0 = swap_id ? IMPGX_OP_D : IMPGX_OP_I, op_q0 = swap_id ? IMPGX_OP_I : IMPGX_OP_D;
+  EndsAcc acc;
+  acc.f_v = acc.l_v = 0;
+  acc.f_tp = acc.f_qp = acc.l_tp = acc.l_qp = 0;
+  acc.n_ov = 0;
+  acc.found = false;
+  acc.broke = false;
+  int32_t f_q = -1, f_t = -1, l_q = -1, l_t = -1;
+  uint32_t nread = 0, nck = 0, r_ov = 1;
+  if (nblk > 0 && rel_l >= 0) {
+    // totals: needed exactly only when walking backwards; otherwise the record's
+    // own span is a good enough denominator for the interpolation guess
+    int64_t w_tot = (int64_t)t_end - t_start, wq_tot = 0;
+    if (backward) {
+      const Checkpoint tot = ck[nblk];
+      w_tot = swap_id ? tot.q_off : tot.t_off;
+      wq_tot = swap_id ? tot.t_off : tot.q_off;
+    }
+    const float scale = __fdividef((float)nblk, (float)(w_tot > 0 ? w_tot : 1));  // only seeds the search
+    // walk blocks j in [0, nblk): js = last block starting before rs, je = last block starting at or before L
+    uint32_t js, je;
+    if (OVL) {
+      // both lookups search the same range, so their sectors are requested together. Forward: the point of
+      // (P <= rel_l) over [0, nblk) is the point over [js, nblk) because rel <= rel_l puts it at or above js.
+      const uint32_t lo = backward ? 1u : 0u, hi = backward ? nblk + 1 : nblk;
+      const int64_t x0 = backward ? w_tot - rel : rel, x1 = backward ? w_tot - rel_l : rel_l;
+      const uint32_t g0 = ck_clamp(x0 > 0 ? (uint32_t)((float)x0 * scale) : 0u, lo, hi);
+      const uint32_t g1 = ck_clamp((x1 > 0 ? (uint32_t)((float)x1 * scale) : 0u) + (backward ? 0u : 1u), lo, hi);
+      const CkSector s0 = ck_load_sector(ck, g0), s1 = ck_load_sector(ck, g1);
+      const uint32_t p0 = ck_partition_s(ck, swap_id, lo, hi, x0, backward, g0, s0);
+      const uint32_t p1 = ck_partition_s(ck, swap_id, lo, hi, x1, !backward, g1, s1);
+      const uint32_t a = backward ? nblk - (p0 - 1) : p0, b = backward ? nblk - (p1 - 1) : p1;
+      js = a ? a - 1 : 0;
+      je = b ? b - 1 : 0;
+    } else if (!backward) {
+      const uint32_t g0 = rel > 0 ? (uint32_t)((float)rel * scale) : 0u;
+      const uint32_t a = ck_partition(ck, swap_id, 0, nblk, rel, false, g0);
+      js = a ? a - 1 : 0;
+      const uint32_t g1 = js + (uint32_t)((float)(rel_l - (rel > 0 ? rel : 0)) * scale) + 1;
+      const uint32_t b = ck_partition(ck, swap_id, js, nblk, rel_l, true, g1);
+      je = b ? b - 1 : 0;
+    } else {
+      // walk block j starts at W - P(nblk - j):  #{j : W - P(nblk-j) < rel} = nblk - #{b in [1,nblk] : P(b) <= W - rel}
+      const int64_t x0 = w_tot - rel, x1 = w_tot - rel_l;
+      const uint32_t g0 = x0 > 0 ? (uint32_t)((float)x0 * scale) : 0u;
+      const uint32_t a = nblk - (ck_partition(ck, swap_id, 1, nblk + 1, x0, true, g0) - 1);
+      const uint32_t g1 = x1 > 0 ? (uint32_t)((float)x1 * scale) : 0u;
+      const uint32_t b = nblk - (ck_partition(ck, swap_id, 1, nblk + 1, x1, false, g1) - 1);
+      js = a ? a - 1 : 0;
+      je = b ? b - 1 : 0;
+    }
+    nck = 8;  // ~2 sectors of checkpoints per lookup (galloping from an interpolated guess)
+    // ---- start side: walk forward from block js until the first overlap (or the loop break)
+    uint32_t j = js;
+    // OVL: the checkpoint and the run block of the end side are requested together with those of the start side
+    const uint32_t jl0 = je > js ? je : js;
+    uint2 kE = make_uint2(0, 0);
+    RunBlock rbE;
+    rbE.lo = rbE.hi = make_uint4(0, 0, 0, 0);
+    uint2 kS = make_uint2(0, 0);
+    RunBlock rbS;
+    rbS.lo = rbS.hi = make_uint4(0, 0, 0, 0);
+    if (OVL) {
+      const uint32_t pbs = backward ? nblk - 1 - js : js;
+      kS = ld_pipe_u2(backward ? ck + pbs + 1 : ck + pbs);
+      rbS = load_block(blk, pbs);
+      if (jl0 != js) {
+        const uint32_t pbe = backward ? nblk - 1 - jl0 : jl0;
+        kE = ld_pipe_u2(backward ? ck + pbe + 1 : ck + pbe);
+        rbE = load_block(blk, pbe);
+      }
+    }
+    for (;;) {
+      const uint32_t pb = backward ? nblk - 1 - j : j;
+      const bool pre = OVL && j == js;
+      const uint2 kk = pre ? kS : ld_pipe_u2(backward ? ck + pb + 1 : ck + pb);
+      const int64_t pt = swap_id ? kk.y : kk.x, pq = swap_id ? kk.x : kk.y;
+      const int64_t tcons = backward ? w_tot - pt : pt, qcons = backward ? wq_tot - pq : pq;
+      const int32_t tp0 = (int32_t)(t_start + tcons);
+      const int32_t qp0 = rev_strand ? (int32_t)(q_end - qcons) : (int32_t)(q_start + qcons);
+      const RunBlock rb = pre ? rbS : load_block(blk, pb);
+      thread_eval_block(rb, n, pb, op_t0, op_q0, backward, dir, tp0, qp0, rs, re, last_target_pos, acc);
+      nread += RUNS_PER_BLOCK;
+      if (acc.found || acc.broke || j + 1 >= nblk) break;
+      j++;
+    }
+    // ---- end side: the last overlapping op lies in blocks [j, max(je, j)]; walk backward from the top
+    if (acc.found) {
+      uint32_t jl = je > j ? je : j;
+      r_ov = acc.n_ov;
+      ends_first(acc, op_t0, op_q0, dir, rs, f_q, f_t);
+      ends_last(acc, op_t0, op_q0, dir, rs, re, last_target_pos, l_q, l_t);
+      while (jl > j) {
+        const uint32_t pb = backward ? nblk - 1 - jl : jl;
+        const bool pre = OVL && jl == jl0 && jl0 != js;
+        const uint2 kk = pre ? kE : ld_pipe_u2(backward ? ck + pb + 1 : ck + pb);
+        const int64_t pt = swap_id ? kk.y : kk.x, pq = swap_id ? kk.x : kk.y;
+        const int64_t tcons = backward ? w_tot - pt : pt, qcons = backward ? wq_tot - pq : pq;
+        const int32_t tp0 = (int32_t)(t_start + tcons);
+        const int32_t qp0 = rev_strand ? (int32_t)(q_end - qcons) : (int32_t)(q_start + qcons);
+        const RunBlock rb = pre ? rbE : load_block(blk, pb);
+        EndsAcc a2;
+        a2.f_v = a2.l_v = 0;
+        a2.f_tp = a2.f_qp = a2.l_tp = a2.l_qp = 0;
+        a2.n_ov = 0;
+        a2.found = false;
+        a2.broke = false;
+        thread_eval_block(rb, n, pb, op_t0, op_q0, backward, dir, tp0, qp0, rs, re, last_target_pos, a2);
+        nread += RUNS_PER_BLOCK;
+        if (a2.found) {
+          ends_last(a2, op_t0, op_q0, dir, rs, re, last_target_pos, l_q, l_t);
+          // ops of block j from its first overlap on, whole blocks in between, ops of block jl up to its last overlap
+          r_ov = acc.n_ov + (jl - j - 1) * RUNS_PER_BLOCK + a2.n_ov;
+          break;
+        }
+        jl--;  // nothing overlapped up there: try the block below (block j already holds its own last)
+      }
+    }
+  }
+  bool ok = acc.found && f_q != l_q && f_t != l_t;
+  if (ok && lp.subset) ok = query_id == lp.row_target[f.row] || lp.subset[query_id] != 0;
+  EndsHit out;
+  out.ok = ok;
+  out.query_id = query_id;
+  out.vrank = vrank;
+  out.f_q = f_q; out.l_q = l_q; out.f_t = f_t; out.l_t = l_t;
+  out.nread = nread; out.nck = nck; out.r_ov = r_ov;
+  return out;
+}
+
 template <bool BUCKET, bool OVL, int MINB>
 __global__ void __launch_bounds__(256, MINB) k_liftover_ends(DevIndexView ix, const Frontier *__restrict__ fr,
                                                        const LiftTask *__restrict__ tasks, uint64_t n_tasks,
@@ -724,148 +888,11 @@ __global__ void __launch_bounds__(256, MINB) k_liftover_ends(DevIndexView ix, co
   for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_tasks; w += stride) {
     const LiftTask t = tasks[w];
     const Frontier f = fr[t.range];
-    const uint4 *rp = reinterpret_cast<const uint4 *>(ix.e_rec + t.entry);
-    const uint4 r0 = rp[0], r1 = rp[1];
-    const int32_t t_start = (int32_t)r0.x, t_end = (int32_t)r0.y, q_start = (int32_t)r0.z, q_end = (int32_t)r0.w;
-    const uint32_t query_id = r1.x, nruns_flags = r1.y, aln_off = r1.z, vrank = r1.w;
-    int32_t rs = f.start, re = f.end;
-    if (lp.clip) {
-      rs = max(rs, t_start);
-      re = min(re, t_end);
-    }
-    const uint32_t n = nruns_flags >> 2;
-    const bool rev_strand = nruns_flags & FLAG_STRAND;
-    const bool swap_id = nruns_flags & FLAG_REVERSED;
-    const bool backward = swap_id && rev_strand;
-    const int32_t dir = rev_strand ? -1 : 1;
-    const uint32_t nblk = aln_nblk(n);
-    const Checkpoint *ck = aln_ck(ix.stream, aln_off);
-    const uint32_t *blk = aln_runs(ix.stream, aln_off, nblk);
-    const int32_t last_target_pos = min(t_end, re);
-    const int64_t rel = (int64_t)rs - t_start, rel_l = (int64_t)last_target_pos - t_start;
-
-    // in this orientation: the op that consumes no target (insertion) / no query (deletion)
-    const uint32_t op_t0 = swap_id ? IMPGX_OP_D : IMPGX_OP_I, op_q0 = swap_id ? IMPGX_OP_I : IMPGX_OP_D;
-    EndsAcc acc;
-    acc.f_v = acc.l_v = 0;
-    acc.f_tp = acc.f_qp = acc.l_tp = acc.l_qp = 0;
-    acc.n_ov = 0;
-    acc.found = false;
-    acc.broke = false;
-    int32_t f_q = -1, f_t = -1, l_q = -1, l_t = -1;
-    uint32_t nread = 0, nck = 0, r_ov = 1;
-    if (nblk > 0 && rel_l >= 0) {
-      // totals: needed exactly only when walking backwards; otherwise the record's
-      // own span is a good enough denominator for the interpolation guess
-      int64_t w_tot = (int64_t)t_end - t_start, wq_tot = 0;
-      if (backward) {
-        const Checkpoint tot = ck[nblk];
-        w_tot = swap_id ? tot.q_off : tot.t_off;
-        wq_tot = swap_id ? tot.t_off : tot.q_off;
-      }
-      const float scale = __fdividef((float)nblk, (float)(w_tot > 0 ? w_tot : 1));  // only seeds the search
-      // walk blocks j in [0, nblk): js = last block starting before rs, je = last block starting at or before L
-      uint32_t js, je;
-      if (OVL) {
-        // both lookups search the same range, so their sectors are requested together. Forward: the point of
-        // (P <= rel_l) over [0, nblk) is the point over [js, nblk) because rel <= rel_l puts it at or above js.
-        const uint32_t lo = backward ? 1u : 0u, hi = backward ? nblk + 1 : nblk;
-        const int64_t x0 = backward ? w_tot - rel : rel, x1 = backward ? w_tot - rel_l : rel_l;
-        const uint32_t g0 = ck_clamp(x0 > 0 ? (uint32_t)((float)x0 * scale) : 0u, lo, hi);
-        const uint32_t g1 = ck_clamp((x1 > 0 ? (uint32_t)((float)x1 * scale) : 0u) + (backward ? 0u : 1u), lo, hi);
-        const CkSector s0 = ck_load_sector(ck, g0), s1 = ck_load_sector(ck, g1);
-        const uint32_t p0 = ck_partition_s(ck, swap_id, lo, hi, x0, backward, g0, s0);
-        const uint32_t p1 = ck_partition_s(ck, swap_id, lo, hi, x1, !backward, g1, s1);
-        const uint32_t a = backward ? nblk - (p0 - 1) : p0, b = backward ? nblk - (p1 - 1) : p1;
-        js = a ? a - 1 : 0;
-        je = b ? b - 1 : 0;
-      } else if (!backward) {
-        const uint32_t g0 = rel > 0 ? (uint32_t)((float)rel * scale) : 0u;
-        const uint32_t a = ck_partition(ck, swap_id, 0, nblk, rel, false, g0);
-        js = a ? a - 1 : 0;
-        const uint32_t g1 = js + (uint32_t)((float)(rel_l - (rel > 0 ? rel : 0)) * scale) + 1;
-        const uint32_t b = ck_partition(ck, swap_id, js, nblk, rel_l, true, g1);
-        je = b ? b - 1 : 0;
-      } else {
-        // walk block j starts at W - P(nblk - j):  #{j : W - P(nblk-j) < rel} = nblk - #{b in [1,nblk] : P(b) <= W - rel}
-        const int64_t x0 = w_tot - rel, x1 = w_tot - rel_l;
-        const uint32_t g0 = x0 > 0 ? (uint32_t)((float)x0 * scale) : 0u;
-        const uint32_t a = nblk - (ck_partition(ck, swap_id, 1, nblk + 1, x0, true, g0) - 1);
-        const uint32_t g1 = x1 > 0 ? (uint32_t)((float)x1 * scale) : 0u;
-        const uint32_t b = nblk - (ck_partition(ck, swap_id, 1, nblk + 1, x1, false, g1) - 1);
-        js = a ? a - 1 : 0;
-        je = b ? b - 1 : 0;
-      }
-      nck = 8;  // ~2 sectors of checkpoints per lookup (galloping from an interpolated guess)
-      // ---- start side: walk forward from block js until the first overlap (or the loop break)
-      uint32_t j = js;
-      // OVL: the checkpoint and the run block of the end side are requested together with those of the start side
-      const uint32_t jl0 = je > js ? je : js;
-      uint2 kE = make_uint2(0, 0);
-      RunBlock rbE;
-      rbE.lo = rbE.hi = make_uint4(0, 0, 0, 0);
-      uint2 kS = make_uint2(0, 0);
-      RunBlock rbS;
-      rbS.lo = rbS.hi = make_uint4(0, 0, 0, 0);
-      if (OVL) {
-        const uint32_t pbs = backward ? nblk - 1 - js : js;
-        kS = ld_pipe_u2(backward ? ck + pbs + 1 : ck + pbs);
-        rbS = load_block(blk, pbs);
-        if (jl0 != js) {
-          const uint32_t pbe = backward ? nblk - 1 - jl0 : jl0;
-          kE = ld_pipe_u2(backward ? ck + pbe + 1 : ck + pbe);
-          rbE = load_block(blk, pbe);
-        }
-      }
-      for (;;) {
-        const uint32_t pb = backward ? nblk - 1 - j : j;
-        const bool pre = OVL && j == js;
-        const uint2 kk = pre ? kS : ld_pipe_u2(backward ? ck + pb + 1 : ck + pb);
-        const int64_t pt = swap_id ? kk.y : kk.x, pq = swap_id ? kk.x : kk.y;
-        const int64_t tcons = backward ? w_tot - pt : pt, qcons = backward ? wq_tot - pq : pq;
-        const int32_t tp0 = (int32_t)(t_start + tcons);
-        const int32_t qp0 = rev_strand ? (int32_t)(q_end - qcons) : (int32_t)(q_start + qcons);
-        const RunBlock rb = pre ? rbS : load_block(blk, pb);
-        thread_eval_block(rb, n, pb, op_t0, op_q0, backward, dir, tp0, qp0, rs, re, last_target_pos, acc);
-        nread += RUNS_PER_BLOCK;
-        if (acc.found || acc.broke || j + 1 >= nblk) break;
-        j++;
-      }
-      // ---- end side: the last overlapping op lies in blocks [j, max(je, j)]; walk backward from the top
-      if (acc.found) {
-        uint32_t jl = je > j ? je : j;
-        r_ov = acc.n_ov;
-        ends_first(acc, op_t0, op_q0, dir, rs, f_q, f_t);
-        ends_last(acc, op_t0, op_q0, dir, rs, re, last_target_pos, l_q, l_t);
-        while (jl > j) {
-          const uint32_t pb = backward ? nblk - 1 - jl : jl;
-          const bool pre = OVL && jl == jl0 && jl0 != js;
-          const uint2 kk = pre ? kE : ld_pipe_u2(backward ? ck + pb + 1 : ck + pb);
-          const int64_t pt = swap_id ? kk.y : kk.x, pq = swap_id ? kk.x : kk.y;
-          const int64_t tcons = backward ? w_tot - pt : pt, qcons = backward ? wq_tot - pq : pq;
-          const int32_t tp0 = (int32_t)(t_start + tcons);
-          const int32_t qp0 = rev_strand ? (int32_t)(q_end - qcons) : (int32_t)(q_start + qcons);
-          const RunBlock rb = pre ? rbE : load_block(blk, pb);
-          EndsAcc a2;
-          a2.f_v = a2.l_v = 0;
-          a2.f_tp = a2.f_qp = a2.l_tp = a2.l_qp = 0;
-          a2.n_ov = 0;
-          a2.found = false;
-          a2.broke = false;
-          thread_eval_block(rb, n, pb, op_t0, op_q0, backward, dir, tp0, qp0, rs, re, last_target_pos, a2);
-          nread += RUNS_PER_BLOCK;
-          if (a2.found) {
-            ends_last(a2, op_t0, op_q0, dir, rs, re, last_target_pos, l_q, l_t);
-            // ops of block j from its first overlap on, whole blocks in between, ops of block jl up to its last overlap
-            r_ov = acc.n_ov + (jl - j - 1) * RUNS_PER_BLOCK + a2.n_ov;
-            break;
-          }
-          jl--;  // nothing overlapped up there: try the block below (block j already holds its own last)
-        }
-      }
-    }
-    bool ok = acc.found && f_q != l_q && f_t != l_t;
-    if (ok && lp.subset) ok = query_id == lp.row_target[f.row] || lp.subset[query_id] != 0;
+    const EndsHit eh = lift_ends_hit<OVL>(ix, f, t.entry, lp);
+    bool ok = eh.ok;
+    const uint32_t query_id = eh.query_id, vrank = eh.vrank;
+    const int32_t f_q = eh.f_q, l_q = eh.l_q, f_t = eh.f_t, l_t = eh.l_t;
+    const uint32_t nread = eh.nread, nck = eh.nck, r_ov = eh.r_ov;
     runs_acc += nread;
     ck_acc += nck;
     rov_acc += r_ov;

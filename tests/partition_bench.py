@@ -55,6 +55,7 @@ def main():
     build_s = time.perf_counter() - t0
     kw = dict(window_size=args.window, merge_distance=args.merge_distance, max_depth=args.max_depth)
     idx.query_batch_bed(np.array([(0, 0, 5000)], dtype=ix.RANGE_DTYPE), ix.make_params(mode=ix.MODE_BFS))  # warm-up
+    idx.partition(ix.make_partition_params(**kw))  # warm-up: scratch arena growth, pinned staging
     t0 = time.perf_counter()
     parts = idx.partition(ix.make_partition_params(**kw))
     gpu_s = time.perf_counter() - t0
@@ -65,36 +66,46 @@ def main():
            "gpu": {"wall_s": round(gpu_s, 4), "windows": int(parts.n_windows), "partitions": int(parts.n_partitions),
                    "intervals": int(len(parts.start)), "ms_per_window": round(1e3 * gpu_s / max(parts.n_windows, 1), 4),
                    "bp_per_s": round(parts.total_bp / gpu_s, 1)}}
+    st = idx.stats()
+    out["gpu"]["launches_last_window"] = int(st["kernel_launches"])
     if args.cpu_budget > 0:
+        import tempfile
+
         import _oracle as O
-        dummy_bed = np.zeros(0, dtype=ix.RANGE_DTYPE)
-        s_recs, s_runs, s_offs, _ = B.contig_subworld(cfg, recs, runs, offs, dummy_bed) if args.keep >= 1.0 else (None,) * 4
-        if s_recs is None:  # patchy: filter by contig directly
-            keep = np.flatnonzero(recs["target_id"] % cfg.contigs == 0)
-            n = np.diff(offs.astype(np.int64))[keep]
-            s_offs = np.zeros(len(keep) + 1, np.uint64)
-            np.cumsum(n, out=s_offs[1:])
-            gi = np.repeat(offs[keep].astype(np.int64) - s_offs[:-1].astype(np.int64), n) + np.arange(int(s_offs[-1]))
-            s_recs, s_runs = recs[keep], runs[gi]
-        # only the sequences of contig 0 take part: renumber them densely (id = genome * contigs + contig)
-        s_recs = s_recs.copy()
+        # the sequences of contig 0 form a closed sub-world (contigs never align to one another): same windows,
+        # masks and partitions there as in the full index; renumber them densely (id = genome * contigs + contig)
+        keep = np.flatnonzero(recs["target_id"] % cfg.contigs == 0)
+        n = np.diff(offs.astype(np.int64))[keep]
+        s_offs = np.zeros(len(keep) + 1, np.uint64)
+        np.cumsum(n, out=s_offs[1:])
+        gi = np.repeat(offs[keep].astype(np.int64) - s_offs[:-1].astype(np.int64), n) + np.arange(int(s_offs[-1]))
+        s_recs, s_runs = recs[keep].copy(), runs[gi]
         s_recs["query_id"] //= cfg.contigs
         s_recs["target_id"] //= cfg.contigs
         s_lens = lens[::cfg.contigs].copy()
-        names = names[::cfg.contigs]
-        Omod, orc, path, _ = B.cpu_reference_setup("part_" + args.workload, s_recs, s_runs, s_offs, s_lens, names, ix)
+        s_names = names[::cfg.contigs]
+        # reference cost structure: CIGAR text on disk, pread + parse per hit (src/impg.rs:495-552)
+        path = os.path.join(os.environ.get("IMPGX_TMP", tempfile.gettempdir()), f"impgx_part_{os.getpid()}.txt")
+        o_off, o_len = ix.write_cigar_text(s_runs, s_offs, path)
+        orc = O.Index.build(s_recs, np.zeros(1, np.uint32), np.zeros(len(s_recs) + 1, np.uint64), s_lens, names=s_names)
+        orc.attach_cigar_file(path, o_off, o_len)
         threads = B.host_threads()
         t0 = time.perf_counter()
-        want = orc.partition(Omod.make_partition_params(**kw), threads=threads)
+        want = orc.partition(O.make_partition_params(**kw), threads=threads)
         cpu_s = time.perf_counter() - t0
         os.unlink(path)
-        sub = ix.Impg.from_records(s_recs, s_runs, s_offs, s_lens, names=names)
+        sub = ix.Impg.from_records(s_recs, s_runs, s_offs, s_lens, names=s_names)
+        sub.partition(ix.make_partition_params(**kw))  # warm-up: arena growth
         t0 = time.perf_counter()
         got = sub.partition(ix.make_partition_params(**kw))
         sub_gpu_s = time.perf_counter() - t0
         norm = [(p, s, min(x, y), max(x, y)) for p, s, x, y in want["rows"]]
+        nw = max(len(want["windows"]), 1)
         out["contig0_subworld"] = {"cpu_wall_s": round(cpu_s, 3), "cpu_threads": threads, "gpu_wall_s": round(sub_gpu_s, 4),
                                    "windows": len(want["windows"]), "bit_exact": got.rows() == norm,
+                                   "cpu_ms_per_window": round(1e3 * cpu_s / nw, 4),
+                                   "gpu_ms_per_window": round(1e3 * sub_gpu_s / nw, 4),
+                                   "launches_last_window": int(sub.stats()["kernel_launches"]),
                                    "cpu_kind": "oracle port, reference cost structure (pread + CIGAR parse per hit)"}
     print(json.dumps(out))
 
