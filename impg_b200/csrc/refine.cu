@@ -255,7 +255,6 @@ impgx_refine_results *refine(impgx_index *idx, const impgx_range *loci, size_t n
     size_t locus;
     int32_t left, right;
   };
-  std::vector<Piece> buf;
   // phase 0: the baseline (0, 0); 1: left > 0 with right 0; 2: right sweep, left fixed; 3: left sweep, right fixed
   for (int phase = 0; phase < 4; phase++) {
     std::vector<Job> jobs;
@@ -286,25 +285,54 @@ impgx_refine_results *refine(impgx_index *idx, const impgx_range *loci, size_t n
       out->candidates += rows.size();
       out->batches++;
       // the candidates of one locus are consecutive and in flank order: the reduce of a sweep keeps the first of
-      // equal candidates, then the sweep's winner meets the best so far (update_best_candidate, refine.rs:548-562)
-      size_t k = 0;
-      while (k < jobs.size()) {
-        const size_t li = jobs[k].locus;
-        Locus &l = L[li];
-        bool have = false;
-        Cand win;
-        for (; k < jobs.size() && jobs[k].locus == li; k++) {
-          Cand c;
-          c.start = rows[k].start; c.end = rows[k].end;
-          c.left = l.s - c.start; c.right = c.end - l.e;
-          support_of(idx, p, l, *res, k, c, buf);
-          if (phase == 0) l.original_support = c.support;
-          if (!have || better(c, win)) win = std::move(c);
-          have = true;
-        }
-        if (have && (!l.have_best || better(win, l.best))) l.best = std::move(win);
-        l.have_best = l.have_best || have;
+      // equal candidates, then the sweep's winner meets the best so far (update_best_candidate, refine.rs:548-562).
+      // Loci are independent (the reference runs them on rayon workers, refine.rs:116-132): one OpenMP task each.
+      std::vector<std::pair<size_t, size_t>> groups;
+      for (size_t k = 0; k < jobs.size();) {
+        size_t e = k + 1;
+        while (e < jobs.size() && jobs[e].locus == jobs[k].locus) e++;
+        groups.emplace_back(k, e);
+        k = e;
       }
+      std::string failure;
+      int fail_code = 0;
+#pragma omp parallel
+      {
+        std::vector<Piece> buf;
+#pragma omp for schedule(dynamic, 4)
+        for (long long gi = 0; gi < (long long)groups.size(); gi++) {
+          try {
+            const size_t li = jobs[groups[gi].first].locus;
+            Locus &l = L[li];
+            bool have = false;
+            Cand win;
+            for (size_t k = groups[gi].first; k < groups[gi].second; k++) {
+              Cand c;
+              c.start = rows[k].start; c.end = rows[k].end;
+              c.left = l.s - c.start; c.right = c.end - l.e;
+              support_of(idx, p, l, *res, k, c, buf);
+              if (phase == 0) l.original_support = c.support;
+              if (!have || better(c, win)) win = std::move(c);
+              have = true;
+            }
+            if (have && (!l.have_best || better(win, l.best))) l.best = std::move(win);
+            l.have_best = l.have_best || have;
+          } catch (const Error &e) {
+#pragma omp critical(impgx_refine_fail)
+            if (!fail_code) {
+              fail_code = e.code;
+              failure = e.what();
+            }
+          } catch (const std::exception &e) {
+#pragma omp critical(impgx_refine_fail)
+            if (!fail_code) {
+              fail_code = IMPGX_E_INVALID;
+              failure = e.what();
+            }
+          }
+        }
+      }
+      if (fail_code) throw Error(fail_code, failure);
     }
     for (auto &l : L)
       if (!l.done && l.capped && l.have_best && l.best.support >= l.max_entities) l.done = true;  // check_max

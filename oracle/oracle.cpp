@@ -2202,6 +2202,31 @@ int64_t orc_refine(void *h, const impgx_range *loci, size_t n, const impgx_refin
   }
   return (int64_t)total;
 }
+// run_refine's driver (src/commands/refine.rs:116-132): the loci in parallel (rayon par_iter there, OpenMP here),
+// records only. Returns the wall seconds, < 0 if a locus fails. Baseline of tests/refine_bench.py.
+double orc_refine_parallel(void *h, const impgx_range *loci, size_t n, const impgx_refine_params *p, int threads,
+                           int64_t *rec8) {
+  Index *idx = (Index *)h;
+  RefineConfig c{p->span_bp, p->max_extension, (int)p->support_level, p->extension_step, p->merge_distance, p->min_identity,
+                 p->transitive == 1, p->transitive == 2, p->max_depth, p->min_transitive_len,
+                 p->min_distance_between_ranges, p->subset_mask, p->blacklist_offsets, p->blacklist_ranges};
+  int failed = 0;
+  const double t0 = omp_get_wtime();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads > 0 ? threads : 1)
+  for (long long i = 0; i < (long long)n; i++) {
+    RefineRecord r;
+    if (!refine_single_range(*idx, loci[i].target_id, loci[i].start, loci[i].end, c, r)) {
+#pragma omp atomic write
+      failed = 1;
+      continue;
+    }
+    int64_t *o = rec8 + 8 * i;
+    o[0] = r.refined_start; o[1] = r.refined_end; o[2] = r.original_start; o[3] = r.original_end;
+    o[4] = r.left; o[5] = r.right; o[6] = (int64_t)r.support_count; o[7] = (int64_t)r.original_support_count;
+  }
+  const double t1 = omp_get_wtime();
+  return failed ? -1.0 : t1 - t0;
+}
 // populate_cigar_cache: the number of cache keys; query_with_cache through that cache: the results
 uint64_t orc_populate_cigar_cache(void *h, uint32_t target_id, int32_t s, int32_t e) {
   CigarCache cache;

@@ -557,6 +557,17 @@ class Index:
                             support_entities=list(zip(es[a:b].tolist(), ea[a:b].tolist(), eb[a:b].tolist()))))
         return out
 
+    def refine_parallel(self, loci, params, threads):
+        """The loci in parallel like run_refine's par_iter; returns (seconds, records as an (n, 8) int64 array)."""
+        loci = np.ascontiguousarray(loci, dtype=RANGE_DTYPE)
+        rec = np.zeros((len(loci), 8), np.int64)
+        L = lib()
+        L.orc_refine_parallel.restype = C.c_double
+        secs = L.orc_refine_parallel(self.h, _p(loci), C.c_size_t(len(loci)), C.byref(params), C.c_int(threads), _p(rec))
+        if secs < 0:
+            raise ValueError("refine failed for a locus")
+        return secs, rec
+
     def populate_cigar_cache(self, target_id, s, e):
         return int(lib().orc_populate_cigar_cache(self.h, C.c_uint32(target_id), C.c_int32(s), C.c_int32(e)))
 
