@@ -272,9 +272,11 @@ __device__ __forceinline__ void fold_one_group(const FoldGroup &fg, const Hit *_
   const int32_t slen = seq_len[seq];
   Frontier *P = pieces + fg.piece_off;
   uint32_t np = 0;
+  int2 nxt = fg.hit_begin < fg.hit_end ? *reinterpret_cast<const int2 *>(&hits[fg.hit_begin].q_first) : make_int2(0, 0);
   for (uint32_t h = fg.hit_begin; h < fg.hit_end; h++) {
-    const Hit hit = hits[h];
-    const int32_t a = hit.q_first, b = hit.q_last;
+    // the next hit's interval is requested before this one's dependent walk through the list
+    const int32_t a = nxt.x, b = nxt.y;
+    if (h + 1 < fg.hit_end) nxt = *reinterpret_cast<const int2 *>(&hits[h + 1].q_first);
     bool should_add = true;
     if (min_dist > 0) {
       const int32_t new_min = min(a, b), new_max = max(a, b);

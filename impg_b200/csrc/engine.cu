@@ -2546,11 +2546,13 @@ static bool try_small(impgx_index *idx, const impgx_range *ranges, size_t n, con
   c.status = per_row.get() + R;
   c.n_res = per_row.get() + 2 * (size_t)R;
   c.n_bk = per_row.get() + 3 * (size_t)R;
+  DBuf<SbCtl> ctl(R, arena);
+  c.ctl = ctl.get();
   // zeroed counters: [0..1] stats, then the class list lengths
-  DBuf<unsigned long long> zeroed(2 + (SEG_CLASSES + 2 + 1) / 2, arena);
+  DBuf<unsigned long long> zeroed(2 + SB_PHASES + (SEG_CLASSES + 2 + 1) / 2, arena);
   CUDA_CHECK(cudaMemsetAsync(zeroed.get(), 0, zeroed.bytes(), s));
   c.stats = zeroed.get();
-  c.cls = reinterpret_cast<unsigned int *>(zeroed.get() + 2);
+  c.cls = reinterpret_cast<unsigned int *>(zeroed.get() + 2 + SB_PHASES);
   const uint64_t cap = (uint64_t)R * SB_CAP;
   DBuf<BoxRec> boxes;
   DBuf<uint32_t> bk, lists;
@@ -2584,9 +2586,28 @@ static bool try_small(impgx_index *idx, const impgx_range *ranges, size_t n, con
       if (idx->device >= 0 && idx->device < 64) attr_done[idx->device] = true;
     }
   }
-  k_small_bfs<<<R, SB_THREADS, SB_SMEM, s>>>(view, d_r, sp, c);
-  CUDA_CHECK(cudaGetLastError());
-  ctx.launches++;
+  {
+    // a cluster of CTAs per row while every cluster of the call is resident at once (one CTA per SM: registers),
+    // single CTAs beyond that
+    static const uint32_t forced = (uint32_t)env_u64("IMPGX_SMALL_CLUSTER", 0);
+    uint32_t cl = 8;
+    while (cl > 1 && (uint64_t)R * cl > (uint64_t)sm_count()) cl >>= 1;
+    if (forced == 1 || forced == 2 || forced == 4 || forced == 8) cl = forced;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(R * cl);
+    cfg.blockDim = dim3(SB_THREADS);
+    cfg.dynamicSmemBytes = SB_SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cl;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_small_bfs, view, d_r, sp, c));
+    ctx.launches++;
+  }
   if (bed) {
     // the bucket merge of the batched path, on the lists the walk left on the device (fixed grids, strided loops)
     const int64_t d = p.merge_distance;
@@ -2659,6 +2680,17 @@ static bool try_small(impgx_index *idx, const impgx_range *ranges, size_t n, con
   ctx.stab_ranges += hdr[R + 2];
   ctx.liftovers += hdr[R + 3];
   ctx.lift_launches++;
+  {
+    static const bool trace = env_u64("IMPGX_TRACE", 0) >= 2;  // cycles per phase of the walk, summed over the rows
+    if (trace) {
+      unsigned long long cyc[SB_PHASES];
+      CUDA_CHECK(cudaMemcpy(cyc, c.stats + 2, sizeof(cyc), cudaMemcpyDeviceToHost));
+      static const char *names[SB_PHASES] = {"stab", "fill", "lift", "order", "results", "group", "fold", "visited", "frontier", "buckets"};
+      fprintf(stderr, "[impgx] single-launch walk, kcycles:");
+      for (int k = 0; k < SB_PHASES; k++) fprintf(stderr, " %s %.1f", names[k], cyc[k] / 1e3);
+      fprintf(stderr, " | ranges %u hits %u rows out %zu\n", hdr[R + 2], hdr[R + 3], total);
+    }
+  }
   return true;
 }
 

@@ -22,7 +22,8 @@ namespace impgx {
 constexpr int SB_THREADS = 512;
 constexpr uint32_t SB_CAP = 8192;           // ranges, hits of one hop, results, visited ranges of ONE row
 constexpr uint32_t SB_LISTS = 3 * SB_CAP;   // fold scratch (lists / pieces) of one row
-constexpr uint32_t SB_MAX_ROWS = 16;
+constexpr uint32_t SB_MAX_ROWS = 64;  // one CTA each: they all run at once on 148 SMs
+constexpr int SB_PHASES = 10;  // stab, fill, liftover, order, results, group, fold, visited, frontier, buckets
 constexpr size_t SB_SMEM = (size_t)SB_CAP * 12;  // sort keys (u64) + values (u32)
 
 enum : uint32_t { SB_OK = 0, SB_OVERFLOW = 1, SB_INVALID = 2 };
@@ -51,6 +52,7 @@ struct SbRowMem {
   uint32_t *cnt;  // SB_CAP + 1
   LiftTask *tasks;
   Hit *hits, *ordered, *sorted, *res;
+  uint32_t *gvr;  // visit rank per hit slot (~0 = rejected), written by every CTA of the row's cluster
   uint64_t *vkey[2], *tkey;
   int32_t *vstart[2], *vend[2], *tstart, *tend;
   FoldGroup *grp;
@@ -76,6 +78,7 @@ __host__ __device__ inline size_t sb_carve(SbRowMem *m, char *base) {
   t.ordered = (Hit *)take(C * sizeof(Hit));
   t.sorted = (Hit *)take(C * sizeof(Hit));
   t.res = (Hit *)take(C * sizeof(Hit));
+  t.gvr = (uint32_t *)take(C * 4);
   t.vkey[0] = (uint64_t *)take(C * 8);
   t.vkey[1] = (uint64_t *)take(C * 8);
   t.tkey = (uint64_t *)take(C * 8);
@@ -98,6 +101,14 @@ __host__ __device__ inline size_t sb_carve(SbRowMem *m, char *base) {
 }
 inline size_t sb_row_bytes() { return sb_carve(nullptr, nullptr); }
 
+// A row is walked by a thread-block CLUSTER: CTA 0 (the leader) runs the walk, the other CTAs join it for the
+// liftover of a hop — the one stage that is bound by memory latency per thread, so more threads in flight is the
+// only lever — and otherwise wait at the cluster barrier. The leader posts the request here before the barrier.
+enum : uint32_t { SB_OP_EXIT = 0, SB_OP_LIFT = 1 };
+struct SbCtl {
+  uint32_t op, n_hits, fb, clip;
+};
+
 // memory of one call
 struct SbCall {
   char *rows;            // n_rows x row_bytes
@@ -106,7 +117,8 @@ struct SbCall {
   uint32_t *status;      // n_rows
   uint32_t *n_res;       // n_rows: results (raw) of the row
   uint32_t *n_bk;        // n_rows: buckets of the row (bed)
-  unsigned long long *stats;  // [0] ranges stabbed, [1] hits lifted (zeroed by the host)
+  SbCtl *ctl;            // n_rows: what the leader CTA of a row asks of the other CTAs of its cluster
+  unsigned long long *stats;  // [0] ranges stabbed, [1] hits lifted, [2 + k] clock cycles of phase k (zeroed by the host)
   // bed: bucket b of row r is slot r * SB_CAP + b
   BoxRec *boxes;
   uint32_t *bk_beg, *bk_cur, *bk_q, *out_cnt;
@@ -196,6 +208,31 @@ __device__ __forceinline__ void sb_sort(uint64_t *key, uint32_t *val, uint32_t n
     }
 }
 
+// the same network over keys that carry their payload in the low bits (half the shared-memory traffic)
+__device__ __forceinline__ void sb_sort_keys(uint64_t *key, uint32_t n) {
+  uint32_t P = 2;
+  while (P < n) P <<= 1;
+  for (uint32_t i = n + threadIdx.x; i < P; i += SB_THREADS) key[i] = ~0ull;
+  __syncthreads();
+  for (uint32_t k = 2; k <= P; k <<= 1)
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t t = threadIdx.x; t < P / 2; t += SB_THREADS) {
+        const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const uint32_t l = i | j;
+        const bool up = (i & k) == 0;
+        const uint64_t a = key[i], b = key[l];
+        if ((a > b) == up) {
+          key[i] = b;
+          key[l] = a;
+        }
+      }
+      __syncthreads();
+    }
+}
+constexpr uint32_t SB_IDX_BITS = 13;  // SB_CAP = 2^13: an index into any per-row array
+constexpr uint64_t SB_IDX_MASK = (1ull << SB_IDX_BITS) - 1;
+static_assert(SB_CAP == (1u << SB_IDX_BITS), "index bits");
+
 __device__ __forceinline__ uint32_t sb_lower_bound_u64(const uint64_t *a, uint32_t n, uint64_t key) {
   uint32_t lo = 0, hi = n;
   while (lo < hi) {
@@ -206,6 +243,46 @@ __device__ __forceinline__ uint32_t sb_lower_bound_u64(const uint64_t *a, uint32
   return lo;
 }
 
+__device__ __forceinline__ uint32_t sb_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t sb_cluster_size() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+// release / acquire at cluster scope: what a CTA wrote to global memory before the barrier is visible to the
+// other CTAs of the cluster after it
+__device__ __forceinline__ void sb_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// The share of one CTA in the liftover of a hop: hit slot t -> hits[t], gvr[t].
+__device__ __forceinline__ void sb_lift_share(const DevIndexView &ix, const SbRowMem &m, const Frontier *F, uint32_t H,
+                                              const LiftParams &lp, uint32_t row, uint32_t first, uint32_t stride) {
+  for (uint32_t t = first; t < H; t += stride) {
+    const uint2 tv = __ldcg(reinterpret_cast<const uint2 *>(m.tasks + t));
+    const LiftTask task{tv.x, tv.y};
+    const uint4 fv = __ldcg(reinterpret_cast<const uint4 *>(F + task.range));
+    Frontier f;
+    f.row = fv.x; f.seq = fv.y; f.start = (int32_t)fv.z; f.end = (int32_t)fv.w;
+    const EndsHit eh = lift_ends_hit<false>(ix, f, task.entry, lp);
+    uint4 *dst = reinterpret_cast<uint4 *>(m.hits + t);
+    dst[0] = make_uint4(eh.ok ? row : INVALID_ID, eh.query_id, (uint32_t)eh.f_q, (uint32_t)eh.l_q);
+    dst[1] = make_uint4(f.seq, (uint32_t)eh.f_t, (uint32_t)eh.l_t, eh.vrank);
+    m.gvr[t] = eh.ok ? eh.vrank : 0xffffffffu;
+  }
+}
+__device__ __forceinline__ Hit sb_load_hit_cg(const Hit *p) {
+  const uint4 a = __ldcg(reinterpret_cast<const uint4 *>(p)), b = __ldcg(reinterpret_cast<const uint4 *>(p) + 1);
+  Hit h;
+  h.row = a.x; h.q_id = a.y; h.q_first = (int32_t)a.z; h.q_last = (int32_t)a.w;
+  h.t_id = b.x; h.t_first = (int32_t)b.y; h.t_last = (int32_t)b.z; h.vrank = b.w;
+  return h;
+}
+
 __global__ void __launch_bounds__(SB_THREADS, 1)
     k_small_bfs(DevIndexView ix, const impgx_range *__restrict__ ranges, SbParams p, SbCall c) {
   extern __shared__ __align__(16) unsigned char sb_smem[];
@@ -213,18 +290,42 @@ __global__ void __launch_bounds__(SB_THREADS, 1)
   uint32_t *sval = reinterpret_cast<uint32_t *>(skey + SB_CAP);
   __shared__ SbSync sh;
   __shared__ uint32_t s_u[4];
-  const uint32_t row = blockIdx.x, tid = threadIdx.x;
+  const uint32_t CL = sb_cluster_size(), crank = sb_cluster_rank();
+  const uint32_t row = blockIdx.x / CL, tid = threadIdx.x;
   const unsigned lane = tid & 31u, warp = tid >> 5;
   constexpr uint32_t NW = SB_THREADS / 32, T = SB_THREADS;
   SbRowMem m;
   sb_carve(&m, c.rows + (size_t)row * c.row_bytes);
+  LiftParams lp;
+  lp.clip = p.query_mode ? 0 : 1;
+  lp.min_output_len = -1;
+  lp.use_identity = 0;
+  lp.min_identity = 0.0;
+  lp.subset = p.subset;
+  lp.row_target = c.row_target;
+  if (crank != 0) {
+    // a helper CTA: liftover shares until the leader says the walk is over
+    for (;;) {
+      sb_cluster_sync();
+      const volatile SbCtl *ctl = c.ctl + row;
+      if (ctl->op == SB_OP_EXIT) return;
+      sb_lift_share(ix, m, m.fr[ctl->fb], ctl->n_hits, lp, row, crank * T + tid, CL * T);
+      sb_cluster_sync();
+    }
+  }
   const impgx_range r = ranges[row];
+  // every way out of the leader passes here: the helpers are released first
+  auto release_cluster = [&]() {
+    if (tid == 0) c.ctl[row].op = SB_OP_EXIT;
+    sb_cluster_sync();
+  };
   auto leave = [&](uint32_t status) {
     if (tid == 0) {
       c.status[row] = status;
       c.n_res[row] = 0;
       c.n_bk[row] = 0;
     }
+    release_cluster();
   };
   {
     // perform_query's bounds checks (k_validate); the batched path words the error
@@ -295,12 +396,21 @@ __global__ void __launch_bounds__(SB_THREADS, 1)
   __syncthreads();
 
   unsigned long long st_ranges = 0, st_hits = 0;
+  // cycles per phase (thread 0; IMPGX_TRACE=2 prints them)
+  long long ph[SB_PHASES] = {0}, t_prev = clock64();
+  auto lap = [&](int k) {
+    const long long t = clock64();
+    ph[k] += t - t_prev;
+    t_prev = t;
+  };
   uint32_t depth = 0;
   while (nF > 0 && (p.query_mode ? depth == 0 : (p.max_depth == 0 || depth < p.max_depth))) {
     const bool last = p.query_mode || (p.max_depth != 0 && depth + 1 >= p.max_depth);
     const bool closed = p.query_mode != 0;
     const Frontier *F = m.fr[fb];
     st_ranges += nF;
+    if (tid == 0) s_u[0] = 0;
+    __syncthreads();
     // ---- stab: windows and hit counts, one warp per range
     for (uint32_t i = warp; i < nF; i += NW) {
       const Frontier f = F[i];
@@ -315,9 +425,12 @@ __global__ void __launch_bounds__(SB_THREADS, 1)
       if (lane == 0) {
         m.win[i] = wd;
         m.cnt[i] = cn;
+        atomicMax(&s_u[0], cn);
       }
     }
     __syncthreads();
+    const uint32_t max_per_range = s_u[0];
+    lap(0);
     const uint32_t H = sb_scan_array(m.cnt, nF, sh);
     if (H > SB_CAP) {
       leave(SB_OVERFLOW);
@@ -342,57 +455,72 @@ __global__ void __launch_bounds__(SB_THREADS, 1)
       }
     }
     __syncthreads();
-    // ---- endpoint liftover, one thread per hit; order key = (range, coitrees visit rank)
-    LiftParams lp;
-    lp.clip = p.query_mode ? 0 : 1;
-    lp.min_output_len = -1;
-    lp.use_identity = 0;
-    lp.min_identity = 0.0;
-    lp.subset = p.subset;
-    lp.row_target = c.row_target;
+    lap(1);
+    // ---- endpoint liftover, one thread per hit, over every CTA of the cluster; order key = (range, visit rank)
+    if (tid == 0) c.ctl[row] = SbCtl{SB_OP_LIFT, H, (uint32_t)fb, 0u};
+    sb_cluster_sync();
+    sb_lift_share(ix, m, F, H, lp, row, tid, CL * T);
+    sb_cluster_sync();
+    // Ranges with few hits each (the common case): the rank of a hit among the accepted hits of its range is
+    // counted directly (vrank is unique within a target), O(hits of the range) shared-memory reads per hit and no
+    // sorting network. A range with many hits takes the bitonic sort instead.
+    const bool enumerate = max_per_range <= 512;
+    uint32_t *vr = sval;                                   // visit rank per hit slot, ~0 = rejected
+    uint32_t *okpre = reinterpret_cast<uint32_t *>(skey);  // accepted hits before the slot
     uint32_t okc = 0;
     for (uint32_t t = tid; t < H; t += T) {
-      const LiftTask task = m.tasks[t];
-      const Frontier f = F[task.range];
-      const EndsHit eh = lift_ends_hit<false>(ix, f, task.entry, lp);
-      Hit h;
-      h.row = eh.ok ? row : INVALID_ID;
-      h.q_id = eh.query_id;
-      h.q_first = eh.f_q;
-      h.q_last = eh.l_q;
-      h.t_id = f.seq;
-      h.t_first = eh.f_t;
-      h.t_last = eh.l_t;
-      h.vrank = eh.vrank;
-      m.hits[t] = h;
-      skey[t] = eh.ok ? (((uint64_t)task.range << 32) | eh.vrank) : ~0ull;
-      sval[t] = t;
-      okc += eh.ok ? 1u : 0u;
+      const uint32_t v = __ldcg(m.gvr + t);
+      const bool ok = v != 0xffffffffu;
+      if (enumerate) {
+        vr[t] = v;
+        okpre[t] = ok ? 1u : 0u;
+      } else {
+        // (range: 13 bits, visit rank: 32 bits, hit slot: 13 bits)
+        skey[t] = ok ? (((uint64_t)m.tasks[t].range << (32 + SB_IDX_BITS)) | ((uint64_t)v << SB_IDX_BITS) | t) : ~0ull;
+      }
+      okc += ok ? 1u : 0u;
     }
     uint32_t n_ok;
     sb_block_scan(okc, sh, &n_ok);
-    sb_sort(skey, sval, H);
-    for (uint32_t k = tid; k < n_ok; k += T) m.ordered[k] = m.hits[sval[k]];
-    __syncthreads();
-    // ---- results of the hop, in reference order, filtered by min_output_length
-    for (uint32_t k0 = 0; k0 < n_ok; k0 += T) {
-      const uint32_t k = k0 + tid;
-      Hit h;
-      bool pass = false;
-      if (k < n_ok) {
-        h = m.ordered[k];
-        pass = passes_len(h, p.min_out);
+    lap(2);
+    if (enumerate) {
+      sb_scan_array(okpre, H, sh);
+      for (uint32_t t = tid; t < H; t += T) {
+        const uint32_t mine = vr[t];
+        if (mine == 0xffffffffu) continue;
+        const uint32_t r = m.tasks[t].range;
+        const uint32_t lo = m.cnt[r], hi = r + 1 < nF ? m.cnt[r + 1] : H;
+        uint32_t rank = 0;
+        for (uint32_t u = lo; u < hi; u++) rank += vr[u] < mine ? 1u : 0u;
+        m.ordered[okpre[lo] + rank] = sb_load_hit_cg(m.hits + t);
       }
-      uint32_t round;
-      const uint32_t pos = sb_block_scan(pass ? 1u : 0u, sh, &round);
-      if (nR + round > SB_CAP) {
+    } else {
+      sb_sort_keys(skey, H);
+      for (uint32_t k = tid; k < n_ok; k += T) m.ordered[k] = sb_load_hit_cg(m.hits + (uint32_t)(skey[k] & SB_IDX_MASK));
+    }
+    __syncthreads();
+    lap(3);
+    // ---- results of the hop, in reference order, filtered by min_output_length
+    {
+      uint32_t *pass = reinterpret_cast<uint32_t *>(skey);  // flag, then position among the passing hits
+      for (uint32_t k = tid; k < n_ok; k += T) pass[k] = passes_len(m.ordered[k], p.min_out) ? 1u : 0u;
+      __syncthreads();
+      uint32_t last_flag = 0;
+      if (n_ok) last_flag = pass[n_ok - 1];
+      __syncthreads();
+      const uint32_t n_pass = sb_scan_array(pass, n_ok, sh);
+      if (nR + n_pass > SB_CAP) {
         leave(SB_OVERFLOW);
         return;
       }
-      if (pass) m.res[nR + pos] = h;
-      nR += round;
+      for (uint32_t k = tid; k < n_ok; k += T) {
+        const bool is_pass = k + 1 < n_ok ? pass[k + 1] != pass[k] : last_flag != 0;
+        if (is_pass) m.res[nR + pass[k]] = m.ordered[k];
+      }
+      nR += n_pass;
     }
     __syncthreads();
+    lap(4);
     if (last) break;
 
     // ---- fold (src/impg.rs:2467-2560): hits grouped by query sequence, stable in reference order; hits back onto
@@ -401,14 +529,13 @@ __global__ void __launch_bounds__(SB_THREADS, 1)
     for (uint32_t k = tid; k < n_ok; k += T) {
       const Hit h = m.ordered[k];
       const bool inc = h.q_id != h.t_id;
-      skey[k] = inc ? (((uint64_t)h.q_id << 13) | k) : ~0ull;
-      sval[k] = k;
+      skey[k] = inc ? (((uint64_t)h.q_id << SB_IDX_BITS) | k) : ~0ull;
       incc += inc ? 1u : 0u;
     }
     uint32_t n_inc;
     sb_block_scan(incc, sh, &n_inc);
-    sb_sort(skey, sval, n_ok);
-    for (uint32_t k = tid; k < n_inc; k += T) m.sorted[k] = m.ordered[sval[k]];
+    sb_sort_keys(skey, n_ok);
+    for (uint32_t k = tid; k < n_inc; k += T) m.sorted[k] = m.ordered[(uint32_t)(skey[k] & SB_IDX_MASK)];
     __syncthreads();
     // group heads -> group starts (cnt is free again)
     uint32_t G = 0;
@@ -445,18 +572,23 @@ __global__ void __launch_bounds__(SB_THREADS, 1)
       leave(SB_OVERFLOW);
       return;
     }
+    lap(5);
+    // the lists the fold edits live in the (idle) sort buffer when they fit: shared-memory instead of L2 latency
+    // on every step of the sequential insertions
+    int2 *LS = l_tot <= SB_SMEM / sizeof(int2) ? reinterpret_cast<int2 *>(sb_smem) : m.lists;
     for (uint32_t g = tid; g < G; g += T) {
       FoldGroup fg = m.grp[g];
       fg.list_off = m.loff[g];
       fg.piece_off = m.poff[g];
       m.grp[g] = fg;
       uint32_t ll = 0, np = 0;
-      fold_one_group(fg, m.sorted, m.vstart[vb], m.vend[vb], ix.seq_len, p.min_dist, p.min_transitive_len, m.lists,
+      fold_one_group(fg, m.sorted, m.vstart[vb], m.vend[vb], ix.seq_len, p.min_dist, p.min_transitive_len, LS,
                      m.pieces, p.mask_off, p.mask_rng, ll, np);
       m.llen[g] = ll;
       m.pcnt[g] = np;
     }
     __syncthreads();
+    lap(6);
     // ---- new visited set: untouched old entries + the groups' lists, sorted by (sequence, start)
     uint32_t kept = 0;
     for (uint32_t i0 = 0; i0 < nV; i0 += T) {
@@ -475,7 +607,7 @@ __global__ void __launch_bounds__(SB_THREADS, 1)
       }
       uint32_t round;
       const uint32_t pos = sb_block_scan(keep ? 1u : 0u, sh, &round);
-      if (keep) {  // kept + pos <= i: the slot was read in this or an earlier round
+      if (keep) {
         m.tkey[kept + pos] = k;
         m.tstart[kept + pos] = m.vstart[vb][i];
         m.tend[kept + pos] = m.vend[vb][i];
@@ -492,7 +624,7 @@ __global__ void __launch_bounds__(SB_THREADS, 1)
     }
     for (uint32_t g = tid; g < G; g += T) {
       const FoldGroup fg = m.grp[g];
-      const int2 *L = m.lists + fg.list_off;
+      const int2 *L = LS + fg.list_off;
       const uint32_t o = kept + m.loff[g];
       for (uint32_t k = 0; k < m.llen[g]; k++) {
         m.tkey[o + k] = fg.key;
@@ -503,8 +635,7 @@ __global__ void __launch_bounds__(SB_THREADS, 1)
     __syncthreads();
     const uint32_t nV2 = kept + n_new;
     for (uint32_t i = tid; i < nV2; i += T) {
-      // ranges of a visited list start at >= 0 (SortedRanges::insert clamps), so the unsigned order is the signed one
-      skey[i] = ((uint64_t)(uint32_t)m.tkey[i] << 32) | (uint32_t)m.tstart[i];
+      skey[i] = ((uint64_t)(uint32_t)m.tkey[i] << 32) | ((uint32_t)m.tstart[i] ^ 0x80000000u);
       sval[i] = i;
     }
     __syncthreads();
@@ -518,6 +649,7 @@ __global__ void __launch_bounds__(SB_THREADS, 1)
     __syncthreads();
     vb ^= 1;
     nV = nV2;
+    lap(7);
     // ---- next frontier: the uncovered pieces sorted by (sequence, start), touching ones joined (:2566-2584)
     for (uint32_t g = tid; g < G; g += T) m.poff[g] = m.pcnt[g];
     __syncthreads();
@@ -573,6 +705,7 @@ __global__ void __launch_bounds__(SB_THREADS, 1)
     fb ^= 1;
     nF = n_next;
     depth++;
+    lap(8);
   }
 
   if (tid == 0) {
@@ -580,40 +713,102 @@ __global__ void __launch_bounds__(SB_THREADS, 1)
     atomicAdd(&c.stats[1], st_hits);
   }
   if (!p.bed) {
+    if (tid == 0)
+      for (int k = 0; k < SB_PHASES; k++) atomicAdd(&c.stats[2 + k], (unsigned long long)ph[k]);
     if (tid == 0) {
       c.status[row] = SB_OK;
       c.n_res[row] = nR;
       c.n_bk[row] = 0;
     }
+    release_cluster();
     return;
   }
+  release_cluster();  // the bucket stage is the leader's alone
   // ---- BED: the results as BoxRecs grouped by query sequence (ord = position in the reference's result order),
   // one bucket per query sequence, listed by size class for the bucket merge kernels
+  const uint32_t slot0 = row * SB_CAP;
+  uint32_t nb = 0;
+  // Grouping through a shared-memory hash table of the query sequences (no sort of the results): count per
+  // sequence, sort the DISTINCT sequences (a few dozen to a few hundred), scan, scatter through per-bucket cursors.
+  // The order inside a bucket is arbitrary, which the bucket merge allows (it works on the box set, ties by ord).
+  constexpr uint32_t HT = 4096, HD = 2048;  // slots, distinct sequences the table path takes
+  uint32_t *tabk = reinterpret_cast<uint32_t *>(sb_smem);          // q + 1, 0 = empty
+  uint32_t *tabc = tabk + HT;                                      // count, then cursor
+  uint64_t *dkey = reinterpret_cast<uint64_t *>(tabc + HT);        // (q << 12 | slot) of the distinct sequences
+  uint32_t *rslot = reinterpret_cast<uint32_t *>(dkey + HD);       // table slot of every result (SB_CAP entries)
+  static_assert((size_t)HT * 8 + (size_t)HD * 8 + (size_t)SB_CAP * 4 <= SB_SMEM, "hash bucketing layout");
+  for (uint32_t i = tid; i < 2 * HT; i += T) tabk[i] = 0u;  // keys and counts
+  if (tid == 0) s_u[0] = s_u[1] = 0;  // distinct sequences, table gave up
+  __syncthreads();
   for (uint32_t k = tid; k < nR; k += T) {
-    skey[k] = ((uint64_t)m.res[k].q_id << 13) | k;
-    sval[k] = k;
+    const uint32_t q = m.res[k].q_id;
+    uint32_t h = (q * 2654435761u) >> 20;  // 12 bits
+    uint32_t probes = 0;
+    for (;;) {
+      const uint32_t old = atomicCAS(&tabk[h], 0u, q + 1);
+      if (old == 0u) {
+        const uint32_t d = atomicAdd(&s_u[0], 1u);
+        if (d < HD) dkey[d] = ((uint64_t)q << 12) | h;
+      }
+      if (old == 0u || old == q + 1) break;
+      h = (h + 1) & (HT - 1);
+      if (++probes >= HT) {
+        s_u[1] = 1;
+        break;
+      }
+    }
+    rslot[k] = h;
+    atomicAdd(&tabc[h], 1u);
   }
   __syncthreads();
-  sb_sort(skey, sval, nR);
-  const uint32_t slot0 = row * SB_CAP;
-  for (uint32_t j = tid; j < nR; j += T) {
-    const uint32_t k = sval[j];
-    const Hit h = m.res[k];
-    uint4 *dst = reinterpret_cast<uint4 *>(c.boxes + slot0 + j);
-    dst[0] = make_uint4(k, 0u, (uint32_t)h.q_first, (uint32_t)h.q_last);
-    dst[1] = make_uint4(h.t_id, (uint32_t)h.t_first, (uint32_t)h.t_last, 0u);
-  }
-  uint32_t nb = 0;
-  for (uint32_t j0 = 0; j0 < nR; j0 += T) {
-    const uint32_t j = j0 + tid;
-    const bool head = j < nR && (j == 0 || (skey[j - 1] >> 13) != (skey[j] >> 13));
-    uint32_t round;
-    const uint32_t pos = sb_block_scan(head ? 1u : 0u, sh, &round);
-    if (head) {
-      c.bk_beg[slot0 + nb + pos] = slot0 + j;
-      c.bk_q[slot0 + nb + pos] = (uint32_t)(skey[j] >> 13);
+  const uint32_t n_distinct = s_u[0];
+  const bool table_ok = s_u[1] == 0 && n_distinct <= HD;
+  __syncthreads();
+  if (table_ok) {
+    sb_sort_keys(dkey, n_distinct);
+    nb = n_distinct;
+    // bucket b = the b-th distinct sequence in ascending order; its boxes start at the scan of the counts
+    uint32_t *bcount = c.bk_cur + slot0;  // scratch until the ends are written below
+    for (uint32_t b = tid; b < nb; b += T) bcount[b] = tabc[(uint32_t)(dkey[b] & (HT - 1))];
+    __syncthreads();
+    sb_scan_array(bcount, nb, sh);
+    for (uint32_t b = tid; b < nb; b += T) {
+      const uint32_t hs = (uint32_t)(dkey[b] & (HT - 1));
+      c.bk_beg[slot0 + b] = slot0 + bcount[b];
+      c.bk_q[slot0 + b] = (uint32_t)(dkey[b] >> 12);
+      tabc[hs] = slot0 + bcount[b];  // cursor
     }
-    nb += round;
+    __syncthreads();
+    for (uint32_t k = tid; k < nR; k += T) {
+      const Hit h = m.res[k];
+      const uint32_t pos = atomicAdd(&tabc[rslot[k]], 1u);
+      uint4 *dst = reinterpret_cast<uint4 *>(c.boxes + pos);
+      dst[0] = make_uint4(k, 0u, (uint32_t)h.q_first, (uint32_t)h.q_last);
+      dst[1] = make_uint4(h.t_id, (uint32_t)h.t_first, (uint32_t)h.t_last, 0u);
+    }
+  } else {
+    // thousands of distinct query sequences in one row: sort the results by (sequence, ordinal)
+    for (uint32_t k = tid; k < nR; k += T) skey[k] = ((uint64_t)m.res[k].q_id << SB_IDX_BITS) | k;
+    __syncthreads();
+    sb_sort_keys(skey, nR);
+    for (uint32_t j = tid; j < nR; j += T) {
+      const uint32_t k = (uint32_t)(skey[j] & SB_IDX_MASK);
+      const Hit h = m.res[k];
+      uint4 *dst = reinterpret_cast<uint4 *>(c.boxes + slot0 + j);
+      dst[0] = make_uint4(k, 0u, (uint32_t)h.q_first, (uint32_t)h.q_last);
+      dst[1] = make_uint4(h.t_id, (uint32_t)h.t_first, (uint32_t)h.t_last, 0u);
+    }
+    for (uint32_t j0 = 0; j0 < nR; j0 += T) {
+      const uint32_t j = j0 + tid;
+      const bool head = j < nR && (j == 0 || (skey[j - 1] >> SB_IDX_BITS) != (skey[j] >> SB_IDX_BITS));
+      uint32_t round;
+      const uint32_t pos = sb_block_scan(head ? 1u : 0u, sh, &round);
+      if (head) {
+        c.bk_beg[slot0 + nb + pos] = slot0 + j;
+        c.bk_q[slot0 + nb + pos] = (uint32_t)(skey[j] >> SB_IDX_BITS);
+      }
+      nb += round;
+    }
   }
   __syncthreads();
   bool over = false;
@@ -635,7 +830,9 @@ __global__ void __launch_bounds__(SB_THREADS, 1)
     c.lists[(size_t)cl * ((size_t)p.n_rows * SB_CAP) + k] = slot0 + b;
   }
   const int any_over = __syncthreads_or(over ? 1 : 0);
+  lap(9);
   if (tid == 0) {
+    for (int k = 0; k < SB_PHASES; k++) atomicAdd(&c.stats[2 + k], (unsigned long long)ph[k]);
     c.status[row] = any_over ? SB_OVERFLOW : SB_OK;
     c.n_res[row] = nR;
     c.n_bk[row] = nb;

@@ -601,7 +601,7 @@ def test_large_segments_and_global_fallback(monkeypatch):
         n = compare_bed(orc, gpu, rows, *params_pair(mode=1, max_depth=3, merge_distance=d, merge_strands=ms))
     st = gpu.stats()
     assert st["liftovers"] / len(rows) > 2000  # thousands of boxes per row over 3 sequences
-    # the same 12 rows through the batched path (calls of <= 16 rows try the single-launch walk first)
+    # the same 12 rows through the batched path (calls of <= 64 rows try the single-launch walk first)
     monkeypatch.setenv("IMPGX_NO_SMALL_BFS", "1")
     for d, ms in ((1000, True), (0, False), (-1, True)):
         compare_bed(orc, gpu, rows, *params_pair(mode=1, max_depth=3, merge_distance=d, merge_strands=ms))

@@ -36,7 +36,7 @@ def test_one_row_calls_raw(world, depth):
         assert took_small_path(gpu, False)
 
 
-@pytest.mark.parametrize("rows", [2, 5, 16])
+@pytest.mark.parametrize("rows", [2, 5, 16, 48])
 def test_few_row_calls_raw_and_bed(world, rows):
     cfg, orc, gpu, bed = world
     for k in range(0, 96 - rows + 1, rows):
@@ -47,9 +47,11 @@ def test_few_row_calls_raw_and_bed(world, rows):
         assert took_small_path(gpu, True)
 
 
-def test_seventeen_rows_take_the_batched_path(world):
+def test_more_rows_than_ctas_take_the_batched_path(world):
     cfg, orc, gpu, bed = world
-    compare_raw(orc, gpu, bed[:17], *params_pair(mode=1, max_depth=2))
+    compare_raw(orc, gpu, bed[:64], *params_pair(mode=1, max_depth=2))
+    assert took_small_path(gpu, False)
+    compare_raw(orc, gpu, bed[:65], *params_pair(mode=1, max_depth=2))
     assert not took_small_path(gpu, False)
 
 
