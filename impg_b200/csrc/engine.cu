@@ -643,6 +643,13 @@ class Runner {
             bool raw_pieces = false);
   void run_dfs(const impgx_range *d_ranges, uint32_t n_rows, DBuf<Frontier> &fr, uint64_t nF, Visited &V,
                std::vector<LevelHits> &levels);
+  void dfs_pop(const DBuf<DfsEntry> &stack, uint64_t n_stack, uint32_t n_rows, DBuf<uint64_t> &popped,
+               DBuf<uint32_t> &cur_depth, DBuf<Frontier> &fr, uint64_t &nF);
+  bool dfs_restack(DBuf<DfsEntry> &stack, uint64_t &n_stack, const DBuf<uint64_t> &popped, const Frontier *pieces,
+                   uint64_t n_pieces, const uint32_t *cur_depth, uint32_t n_rows);
+  void sharded_dfs(DBuf<Frontier> &fr0, uint64_t nF0, uint32_t n_rows, Visited &V, uint32_t ord_level,
+                   std::vector<DBuf<BoxD>> &level_boxes, std::vector<uint64_t> &level_n, uint64_t &prior,
+                   unsigned long long *box_counter);
   void assemble(const impgx_range *d_ranges, uint32_t n_rows, std::vector<LevelHits> &levels, bool query_mode,
                 BatchOut &out);
   void bed_merge(BatchOut &raw, uint32_t n_rows, BatchOut &out);
@@ -2127,14 +2134,15 @@ void Runner::run_sharded(const impgx_range *d_ranges, uint32_t n_rows, BatchOut 
   REQUIRE((uint32_t)comm_->size() == idx_->shard_size && (uint32_t)comm_->rank() == idx_->shard_rank, IMPGX_E_INVALID,
           "comm rank/size do not match the shard index");
   REQUIRE(comm_->size() <= MAX_RANKS, IMPGX_E_INVALID, "too many ranks");
-  REQUIRE(p_.mode == IMPGX_MODE_QUERY || p_.mode == IMPGX_MODE_BFS, IMPGX_E_UNSUPPORTED,
-          "the sharded index runs Impg::query and the transitive BFS (DFS: use an unsharded index)");
+  REQUIRE(p_.mode == IMPGX_MODE_QUERY || p_.mode == IMPGX_MODE_BFS || p_.mode == IMPGX_MODE_DFS, IMPGX_E_UNSUPPORTED,
+          "the sharded index runs Impg::query and the transitive BFS / DFS (MultiImpg walks: use an unsharded index)");
   REQUIRE(!p_.store_cigar, IMPGX_E_INVALID, "BED output carries no CIGAR (src/main.rs:7447)");
   REQUIRE(n_rows < (1u << 26), IMPGX_E_INVALID, "more than 2^26 rows in one batch; lower IMPGX_ROWS_PER_BATCH");
   Comm &cm = *comm_;
   const int N = cm.size();
   const uint32_t me = (uint32_t)cm.rank();
-  const bool bfs = p_.mode == IMPGX_MODE_BFS;
+  const bool dfs = p_.mode == IMPGX_MODE_DFS;
+  const bool bfs = p_.mode == IMPGX_MODE_BFS || dfs;  // a transitive walk: seeds, visited sets, clipping
   prepare(d_ranges, n_rows);
 
   // Level-0 frontier: the seed ranges on targets this rank owns. Every rank derives the GLOBAL seed list (one range
@@ -2205,7 +2213,9 @@ void Runner::run_sharded(const impgx_range *d_ranges, uint32_t n_rows, BatchOut 
     }
     DBuf<uint64_t> flag(n_all + 1, ar_), scan(n_all + 1, ar_);
     CUDA_CHECK(cudaMemsetAsync(flag.get() + n_all, 0, 8, s_));
-    if (n_all)
+    if (n_all && dfs)  // the stacks are replicated: every seed that is long enough, whoever owns its target
+      LAUNCH(k_frontier_len_flags, grid_threads(n_all), 256, s_, all.get(), n_all, p_.min_transitive_len, flag.get());
+    else if (n_all)
       LAUNCH(k_shard_seed_flags, grid_threads(n_all), 256, s_, all.get(), n_all, bfs ? p_.min_transitive_len : 0,
              idx_->d_owner, me, flag.get());
     CUDA_CHECK(cudaMemcpyAsync(scan.get(), flag.get(), (n_all + 1) * 8, cudaMemcpyDeviceToDevice, s_));
@@ -2262,7 +2272,12 @@ void Runner::run_sharded(const impgx_range *d_ranges, uint32_t n_rows, BatchOut 
   const bool buckets = bucket_mode(n_rows);
   Buckets bk;
   bool bk_begun = false;
+  if (dfs) {
+    sharded_dfs(fr, nF, n_rows, V, 1 + level_base, level_boxes, level_n, prior, sink.counters.get());
+    nF = 0;
+  }
   for (;;) {
+    if (dfs) break;
     // every rank learns every rank's frontier size: loop control must agree
     cm.allgather_u64(&nF, 1, cnt.data(), s_);
     uint64_t total = 0;
@@ -2362,6 +2377,67 @@ void Runner::run_sharded(const impgx_range *d_ranges, uint32_t n_rows, BatchOut 
 // re-sorted by (id, start) and merged exactly like the reference does after
 // each pop (:2289-2304). The stacks of all rows live in one array sorted by
 // (row, id, start); a row's top is the last entry of its segment.
+// pop the top of every non-empty stack: the popped ranges that are walked on (depth below max_depth), one per row
+void Runner::dfs_pop(const DBuf<DfsEntry> &stack, uint64_t n_stack, uint32_t n_rows, DBuf<uint64_t> &popped,
+                     DBuf<uint32_t> &cur_depth, DBuf<Frontier> &fr, uint64_t &nF) {
+  popped.alloc(n_stack + 1, ar_);
+  DBuf<uint64_t> is_fr(n_rows + 1, ar_), fr_scan(n_rows + 1, ar_);
+  CUDA_CHECK(cudaMemsetAsync(popped.get(), 0, (n_stack + 1) * 8, s_));
+  CUDA_CHECK(cudaMemsetAsync(is_fr.get(), 0, ((size_t)n_rows + 1) * 8, s_));
+  DBuf<Frontier> cand(n_rows, ar_);
+  LAUNCH(k_dfs_pop, grid_threads(n_stack), 256, s_, stack.get(), n_stack, p_.max_depth,
+         p_.mode == IMPGX_MODE_MULTI_BFS ? 1 : 0, popped.get(), cand.get(), is_fr.get(), cur_depth.get());
+  CUDA_CHECK(cudaMemcpyAsync(fr_scan.get(), is_fr.get(), ((size_t)n_rows + 1) * 8, cudaMemcpyDeviceToDevice, s_));
+  exclusive_scan_u64(fr_scan.get(), (uint64_t)n_rows + 1, sc_, s_);
+  ctx.launches += 2;
+  nF = read_u64(fr_scan.get() + n_rows, s_, ctx);
+  fr.alloc(nF, ar_);
+  if (nF) LAUNCH(k_frontier_compact, grid_threads(n_rows), 256, s_, cand.get(), (uint64_t)n_rows, is_fr.get(), fr_scan.get(), fr.get());
+  CUDA_CHECK(cudaStreamSynchronize(s_));  // cand / is_fr / fr_scan are released on return
+}
+
+// new stack = kept entries + pushed pieces, sorted by (row, id, start), merged per row. False: every stack is empty.
+bool Runner::dfs_restack(DBuf<DfsEntry> &stack, uint64_t &n_stack, const DBuf<uint64_t> &popped, const Frontier *pieces,
+                         uint64_t n_pieces, const uint32_t *cur_depth, uint32_t n_rows) {
+  DBuf<uint64_t> keep_scan(n_stack + 1, ar_);
+  LAUNCH(k_dfs_keep_flags, grid_threads(n_stack + 1), 256, s_, popped.get(), n_stack, keep_scan.get());
+  exclusive_scan_u64(keep_scan.get(), n_stack + 1, sc_, s_);
+  ctx.launches += 2;
+  const uint64_t kept = read_u64(keep_scan.get() + n_stack, s_, ctx);
+  const uint64_t m = kept + n_pieces;
+  if (m == 0) return false;
+  DBuf<DfsEntry> tmp(m, ar_);
+  LAUNCH(k_dfs_copy_kept, grid_threads(n_stack), 256, s_, stack.get(), n_stack, popped.get(), keep_scan.get(), tmp.get());
+  if (n_pieces) LAUNCH(k_dfs_push, grid_threads(n_pieces), 256, s_, pieces, n_pieces, cur_depth, tmp.get() + kept);
+  DBuf<uint32_t> sk(m, ar_), sp(m, ar_);
+  LAUNCH(k_dfs_start_keys, grid_threads(m), 256, s_, tmp.get(), m, sk.get(), sp.get());
+  sort_pairs(sk, sp, m, 0, 32, sc_, s_, ctx);
+  DBuf<uint64_t> k2(m, ar_);
+  LAUNCH(k_dfs_seq_keys, grid_threads(m), 256, s_, tmp.get(), sp.get(), m, k2.get());
+  sort_pairs(k2, sp, m, 0, 32 + bits_for(n_rows), sc_, s_, ctx);
+  DBuf<DfsEntry> sorted(m, ar_);
+  LAUNCH(k_gather<DfsEntry>, grid_threads(m), 256, s_, tmp.get(), sp.get(), m, sorted.get());
+  // per-row sequential merge (write/read sweep of :2291-2304)
+  DBuf<uint64_t> rowkeys(m, ar_);
+  LAUNCH(k_keys_shift, grid_threads(m), 256, s_, k2.get(), m, 32, rowkeys.get());
+  Groups g;
+  build_groups(rowkeys.get(), m, g, sc_, s_, ctx);
+  DBuf<uint32_t> cnt(g.G, ar_);
+  LAUNCH(k_dfs_merge, grid_threads(g.G, 128, 16), 128, s_, sorted.get(), g.begins.get(), g.G, cnt.get());
+  DBuf<uint64_t> scan(g.G + 1, ar_);
+  CUDA_CHECK(cudaMemsetAsync(scan.get() + g.G, 0, 8, s_));
+  LAUNCH(k_u32_to_u64, grid_threads(g.G), 256, s_, cnt.get(), g.G, scan.get());
+  exclusive_scan_u64(scan.get(), g.G + 1, sc_, s_);
+  ctx.launches += 2;
+  const uint64_t n_new = read_u64(scan.get() + g.G, s_, ctx);
+  DBuf<DfsEntry> ns(n_new, ar_);
+  LAUNCH(k_dfs_compact, grid_threads(g.G), 256, s_, sorted.get(), g.begins.get(), cnt.get(), scan.get(), g.G, ns.get());
+  CUDA_CHECK(cudaStreamSynchronize(s_));  // the temporaries are released on return
+  stack = std::move(ns);
+  n_stack = n_new;
+  return true;
+}
+
 void Runner::run_dfs(const impgx_range *d_ranges, uint32_t n_rows, DBuf<Frontier> &fr0, uint64_t nF0, Visited &V,
                      std::vector<LevelHits> &levels) {
   (void)d_ranges;
@@ -2370,19 +2446,10 @@ void Runner::run_dfs(const impgx_range *d_ranges, uint32_t n_rows, DBuf<Frontier
   if (nF0) LAUNCH(k_dfs_init_stack, grid_threads(nF0), 256, s_, fr0.get(), nF0, stack.get());
   DBuf<uint32_t> cur_depth(n_rows, ar_);
   while (n_stack > 0) {
-    // ---- pop the top of every non-empty stack
-    DBuf<uint64_t> popped(n_stack + 1, ar_), is_fr(n_rows + 1, ar_), fr_scan(n_rows + 1, ar_);
-    CUDA_CHECK(cudaMemsetAsync(popped.get(), 0, (n_stack + 1) * 8, s_));
-    CUDA_CHECK(cudaMemsetAsync(is_fr.get(), 0, ((size_t)n_rows + 1) * 8, s_));
-    DBuf<Frontier> cand(n_rows, ar_);
-    LAUNCH(k_dfs_pop, grid_threads(n_stack), 256, s_, stack.get(), n_stack, p_.max_depth,
-           p_.mode == IMPGX_MODE_MULTI_BFS ? 1 : 0, popped.get(), cand.get(), is_fr.get(), cur_depth.get());
-    CUDA_CHECK(cudaMemcpyAsync(fr_scan.get(), is_fr.get(), ((size_t)n_rows + 1) * 8, cudaMemcpyDeviceToDevice, s_));
-    exclusive_scan_u64(fr_scan.get(), (uint64_t)n_rows + 1, sc_, s_);
-    ctx.launches += 2;
-    const uint64_t nF = read_u64(fr_scan.get() + n_rows, s_, ctx);
-    DBuf<Frontier> fr(nF, ar_);
-    if (nF) LAUNCH(k_frontier_compact, grid_threads(n_rows), 256, s_, cand.get(), (uint64_t)n_rows, is_fr.get(), fr_scan.get(), fr.get());
+    DBuf<uint64_t> popped;
+    DBuf<Frontier> fr;
+    uint64_t nF = 0;
+    dfs_pop(stack, n_stack, n_rows, popped, cur_depth, fr, nF);
     // ---- expand
     DBuf<Frontier> pieces;
     uint64_t n_pieces = 0;
@@ -2393,43 +2460,72 @@ void Runner::run_dfs(const impgx_range *d_ranges, uint32_t n_rows, DBuf<Frontier
       stab_and_lift(fr, nF, /*closed=*/mq, /*clip=*/!mq, nullptr, levels.back());
       fold(levels.back(), n_rows, V, pieces, n_pieces, /*raw_pieces=*/true);
     }
-    // ---- new stack = kept entries + pushed pieces, sorted by (row, id, start), merged per row
-    DBuf<uint64_t> keep_scan(n_stack + 1, ar_);
-    LAUNCH(k_dfs_keep_flags, grid_threads(n_stack + 1), 256, s_, popped.get(), n_stack, keep_scan.get());
-    exclusive_scan_u64(keep_scan.get(), n_stack + 1, sc_, s_);
-    ctx.launches += 2;
-    const uint64_t kept = read_u64(keep_scan.get() + n_stack, s_, ctx);
-    const uint64_t m = kept + n_pieces;
-    if (m == 0) break;
-    DBuf<DfsEntry> tmp(m, ar_);
-    LAUNCH(k_dfs_copy_kept, grid_threads(n_stack), 256, s_, stack.get(), n_stack, popped.get(), keep_scan.get(), tmp.get());
-    if (n_pieces)
-      LAUNCH(k_dfs_push, grid_threads(n_pieces), 256, s_, pieces.get(), n_pieces, cur_depth.get(), tmp.get() + kept);
-    DBuf<uint32_t> sk(m, ar_), sp(m, ar_);
-    LAUNCH(k_dfs_start_keys, grid_threads(m), 256, s_, tmp.get(), m, sk.get(), sp.get());
-    sort_pairs(sk, sp, m, 0, 32, sc_, s_, ctx);
-    DBuf<uint64_t> k2(m, ar_);
-    LAUNCH(k_dfs_seq_keys, grid_threads(m), 256, s_, tmp.get(), sp.get(), m, k2.get());
-    sort_pairs(k2, sp, m, 0, 32 + bits_for(n_rows), sc_, s_, ctx);
-    DBuf<DfsEntry> sorted(m, ar_);
-    LAUNCH(k_gather<DfsEntry>, grid_threads(m), 256, s_, tmp.get(), sp.get(), m, sorted.get());
-    // per-row sequential merge (write/read sweep of :2291-2304)
-    DBuf<uint64_t> rowkeys(m, ar_);
-    LAUNCH(k_keys_shift, grid_threads(m), 256, s_, k2.get(), m, 32, rowkeys.get());
-    Groups g;
-    build_groups(rowkeys.get(), m, g, sc_, s_, ctx);
-    DBuf<uint32_t> cnt(g.G, ar_);
-    LAUNCH(k_dfs_merge, grid_threads(g.G, 128, 16), 128, s_, sorted.get(), g.begins.get(), g.G, cnt.get());
-    DBuf<uint64_t> scan(g.G + 1, ar_);
-    CUDA_CHECK(cudaMemsetAsync(scan.get() + g.G, 0, 8, s_));
-    LAUNCH(k_u32_to_u64, grid_threads(g.G), 256, s_, cnt.get(), g.G, scan.get());
-    exclusive_scan_u64(scan.get(), g.G + 1, sc_, s_);
-    ctx.launches += 2;
-    const uint64_t n_new = read_u64(scan.get() + g.G, s_, ctx);
-    DBuf<DfsEntry> ns(n_new, ar_);
-    LAUNCH(k_dfs_compact, grid_threads(g.G), 256, s_, sorted.get(), g.begins.get(), cnt.get(), scan.get(), g.G, ns.get());
-    stack = std::move(ns);
-    n_stack = n_new;
+    if (!dfs_restack(stack, n_stack, popped, pieces.get(), n_pieces, cur_depth.get(), n_rows)) break;
+  }
+}
+
+// Transitive DFS on a target-sharded index. The stacks of all rows are REPLICATED: every rank pops the same ranges
+// (no exchange needed to agree), lifts the popped ranges on the targets it owns, routes the hits to the owners of the
+// sequences they land on (all-to-all-v, as in the BFS), folds them there, and the uncovered pieces of all ranks are
+// all-gathered, so that every rank pushes the same pieces and re-sorts the same stacks. A row pops at most one range
+// per round, so the reference's result order of a row is (round, visit rank): that is the ordinal of the boxes.
+void Runner::sharded_dfs(DBuf<Frontier> &fr0, uint64_t nF0, uint32_t n_rows, Visited &V, uint32_t ord_level,
+                         std::vector<DBuf<BoxD>> &level_boxes, std::vector<uint64_t> &level_n, uint64_t &prior,
+                         unsigned long long *box_counter) {
+  Comm &cm = *comm_;
+  const int N = cm.size();
+  const uint32_t me = (uint32_t)cm.rank();
+  DBuf<DfsEntry> stack(nF0, ar_);
+  uint64_t n_stack = nF0;
+  if (nF0) LAUNCH(k_dfs_init_stack, grid_threads(nF0), 256, s_, fr0.get(), nF0, stack.get());
+  DBuf<uint32_t> cur_depth(n_rows, ar_);
+  std::vector<uint64_t> cnt((size_t)N), off((size_t)N);
+  uint32_t round = 0;
+  while (n_stack > 0) {
+    REQUIRE(round < (1u << 26), IMPGX_E_INVALID, "transitive DFS on a sharded index: more than 2^26 rounds");
+    DBuf<uint64_t> popped;
+    DBuf<Frontier> fr;
+    uint64_t nF = 0;
+    dfs_pop(stack, n_stack, n_rows, popped, cur_depth, fr, nF);
+    DBuf<Frontier> all_pieces;
+    uint64_t n_all = 0;
+    if (nF) {  // the same on every rank: the exchanges below are entered by all or none
+      // the popped ranges on targets owned here, tagged with their index among the popped
+      DBuf<uint64_t> flag(nF + 1, ar_), scan(nF + 1, ar_);
+      CUDA_CHECK(cudaMemsetAsync(flag.get() + nF, 0, 8, s_));
+      LAUNCH(k_shard_seed_flags, grid_threads(nF), 256, s_, fr.get(), nF, 0, idx_->d_owner, me, flag.get());
+      CUDA_CHECK(cudaMemcpyAsync(scan.get(), flag.get(), (nF + 1) * 8, cudaMemcpyDeviceToDevice, s_));
+      exclusive_scan_u64(scan.get(), nF + 1, sc_, s_);
+      ctx.launches += 2;
+      const uint64_t nM = read_u64(scan.get() + nF, s_, ctx);
+      DBuf<Frontier> mine(nM, ar_);
+      DBuf<uint32_t> gmap(nM, ar_);
+      LAUNCH(k_frontier_compact, grid_threads(nF), 256, s_, fr.get(), nF, flag.get(), scan.get(), mine.get());
+      LAUNCH(k_compact_indices, grid_threads(nF), 256, s_, flag.get(), scan.get(), nF, gmap.get());
+      Lifted L;
+      DBuf<BoxD> boxes_h;
+      lift_core(mine, nM, /*closed=*/false, /*clip=*/true, [&](uint64_t H) { boxes_h.alloc(H, ar_); }, L);
+      if (L.H)
+        LAUNCH(k_boxes_dfs_round, grid_threads(L.H), 256, s_, L.hits.get(), L.H, ord_level, round, p_.min_output_length,
+               boxes_h.get(), box_counter);
+      prior += L.H;
+      level_n.push_back(L.H);
+      level_boxes.push_back(std::move(boxes_h));
+      LevelHits lvl;
+      route_hits(L, gmap.get(), lvl);
+      DBuf<Frontier> pieces;
+      uint64_t n_pieces = 0;
+      fold(lvl, n_rows, V, pieces, n_pieces, /*raw_pieces=*/true);
+      cm.allgather_u64(&n_pieces, 1, cnt.data(), s_);
+      for (int p = 0; p < N; p++) {
+        off[p] = n_all;
+        n_all += cnt[p];
+      }
+      all_pieces.alloc(n_all, ar_);
+      cm.allgatherv(pieces.get(), n_pieces, all_pieces.get(), cnt.data(), off.data(), sizeof(Frontier), s_);
+    }
+    if (!dfs_restack(stack, n_stack, popped, all_pieces.get(), n_all, cur_depth.get(), n_rows)) break;
+    round++;
   }
 }
 

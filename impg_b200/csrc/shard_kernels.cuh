@@ -35,6 +35,21 @@ __global__ void k_frontier_rows(const Frontier *__restrict__ f, uint64_t n, uint
   for (uint64_t i = gtid(); i < n; i += gstride()) gmap[i] = f[i].row;
 }
 
+// hits of one DFS round as boxes: a row pops at most one range per round, so (round, visit rank) is the position
+// of a hit in the reference's result order of its row
+__global__ void k_boxes_dfs_round(const Hit *__restrict__ hits, uint64_t n, uint32_t level, uint32_t round, int32_t min_out,
+                                  BoxD *__restrict__ out, unsigned long long *__restrict__ n_valid) {
+  unsigned long long c = 0;
+  for (uint64_t i = gtid(); i < n; i += gstride()) {
+    const Hit h = hits[i];
+    const bool ok = h.row != INVALID_ID && passes_len(h, min_out);
+    out[i] = BoxD{h.q_first, h.q_last, h.t_first, h.t_last, h.q_id, h.t_id, h.row, ok ? 1u : 0u,
+                  make_ord(level, ((uint64_t)round << 32) | h.vrank)};
+    c += ok ? 1 : 0;
+  }
+  if (c) atomicAdd(n_valid, c);
+}
+
 // boxes of rows whose box sequence is not owned here are someone else's (masked seeds: every rank derives them all)
 __global__ void k_boxes_keep_owned(BoxD *__restrict__ b, uint64_t n, const uint32_t *__restrict__ owner, uint32_t rank) {
   for (uint64_t i = gtid(); i < n; i += gstride())

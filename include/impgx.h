@@ -259,8 +259,8 @@ int impgx_index_build_shard(const impgx_record *records, size_t n_records, const
                             const uint64_t *run_offsets, const uint64_t *seq_lens, uint32_t n_seqs,
                             int bidirectional, int device, const uint32_t *owner, uint32_t rank,
                             uint32_t n_ranks, impgx_index **out);
-/* Collective counterparts of impgx_query_batch_bed / _bed_device. Modes QUERY
- * and BFS; DFS and raw (unmerged) results need an unsharded index. */
+/* Collective counterparts of impgx_query_batch_bed / _bed_device. Modes QUERY,
+ * BFS and DFS; the MultiImpg walks and raw (unmerged) results need an unsharded index. */
 int impgx_query_batch_bed_sharded(impgx_index *shard, impgx_comm *comm, const impgx_range *ranges, size_t n,
                                   const impgx_params *params, impgx_results **out);
 int impgx_query_batch_bed_sharded_device(impgx_index *shard, impgx_comm *comm, const impgx_range *d_ranges,

@@ -117,10 +117,10 @@ def test_sharded_edge_cases(world):
     # rows too short to expand: nothing but the seeds, frontier empty on every rank
     tiny = np.array([(s, 10, 60) for s in range(12)], ix.RANGE_DTYPE)
     compare_bed_sharded(orc, sh, tiny, o, g)
-    # unsupported on a shard: raw results, DFS, unsorted --no-merge output
+    # unsupported on a shard: raw results, the MultiImpg walks, unsorted --no-merge output
     with pytest.raises(ix.ImpgxError):
         sh.shards[0].query_batch(one_seq, g)
-    for bad in (ix.make_params(mode=ix.MODE_DFS), ix.make_params(mode=ix.MODE_BFS, merge_distance=-1, merge_strands=False)):
+    for bad in (ix.make_params(mode=ix.MODE_MULTI_DFS), ix.make_params(mode=ix.MODE_BFS, merge_distance=-1, merge_strands=False)):
         fresh = ix.ShardedImpg(sh.shards, ix.Comm.local_group(2), sh.owner)  # a failed collective poisons its group
         with pytest.raises(ix.ImpgxError) as e:
             fresh.query_batch_bed_parts(one_seq, bad)
@@ -207,3 +207,36 @@ def test_sharded_masked_regions(world, n_ranks):
     full = ix.mask_csr({s: [(0, 60000)] for s in range(12)}, 12)
     parts = sh.query_batch_bed_parts(b, params_pair(mode=1, masked_regions=full, merge_distance=1000)[1])
     assert sum(p.n_results for p in parts) == 0
+
+
+@pytest.mark.parametrize("n_ranks", [1, 2, 3, 5])
+@pytest.mark.parametrize("depth", [1, 2, 3, 0])
+def test_sharded_dfs(world, n_ranks, depth):
+    """Transitive DFS (reference src/impg.rs:2057-2309) on a sharded index: replicated stacks, hits routed to the owner
+    of the sequence they land on, uncovered pieces all-gathered; the boxes carry (round, visit rank) as their ordinal."""
+    cfg, orc, shards, bed = world
+    sh = shards[n_ranks]
+    compare_bed_sharded(orc, sh, bed[:70], *params_pair(mode=2, max_depth=depth, merge_distance=1000))
+
+
+def test_sharded_dfs_options_and_masks(world):
+    from test_gpu_parity import random_mask
+    cfg, orc, shards, bed = world
+    sh = shards[3]
+    b = bed[:50]
+    compare_bed_sharded(orc, sh, b, *params_pair(mode=2, max_depth=0, min_transitive_len=0, min_dist=0, merge_distance=0))
+    compare_bed_sharded(orc, sh, b, *params_pair(mode=2, max_depth=3, min_output_length=2500, merge_distance=500,
+                                                 merge_strands=False))
+    compare_bed_sharded(orc, sh, b, *params_pair(mode=2, max_depth=3, min_transitive_len=2000, min_dist=500,
+                                                 merge_distance=-1, merge_strands=True))
+    rng = np.random.default_rng(91)
+    for density, depth in ((0.5, 2), (0.9, 3), (0.97, 0)):
+        mask = random_mask(rng, 12, 60000, density)
+        compare_bed_sharded(orc, sh, b, *params_pair(mode=2, max_depth=depth, masked_regions=mask, merge_distance=1000))
+    # one sequence only, a single row, rows too short to walk on
+    one_seq = np.array([(3, 100 + 50 * k, 5000 + 50 * k) for k in range(20)], ix.RANGE_DTYPE)
+    compare_bed_sharded(orc, sh, one_seq, *params_pair(mode=2, max_depth=2, merge_distance=0))
+    compare_bed_sharded(orc, sh, one_seq[:1], *params_pair(mode=2, max_depth=0, merge_distance=0))
+    tiny = np.array([(s, 10, 60) for s in range(12)], ix.RANGE_DTYPE)
+    compare_bed_sharded(orc, sh, tiny, *params_pair(mode=2, max_depth=2, merge_distance=0))
+
