@@ -688,6 +688,37 @@ class Partitioner:
         return Partitions(h.value)
 
 
+def partition_with(index, pparams, answer):
+    """partition_alignments (reference src/commands/partition.rs:158-712) over any index that answers a window:
+    the stepper hands out the windows and the masked regions, `answer(window, query_params)` returns the merged BED
+    rows of the window as columns (q_id, q_first, q_last) — e.g. a collective call on a target-sharded index whose
+    per-rank parts were merged. `index` supplies the sequence lengths and names. Needs -d >= 0: a sharded index
+    returns merged rows only."""
+    if pparams.merge_distance < 0:
+        raise ImpgxError(E_UNSUPPORTED, "partition over a sharded index needs a merge distance >= 0 (--no-merge: raw results)")
+    if pparams.multi_impg:
+        raise ImpgxError(E_UNSUPPORTED, "partition over a sharded index: the MultiImpg walk is not sharded")
+    n = index.n_seqs
+    lens = np.array([index.seq_len(i) for i in range(n)], dtype=np.uint64)
+    names = [index.seq_name(i) for i in range(n)]
+    st = Partitioner(lens, pparams, names if all(x is not None for x in names) else None)
+    mi = pparams.min_identity
+    while True:
+        w = st.next()
+        if w is None:
+            break
+        window, mask = w
+        # the query of partition.rs:359-391: no CIGARs, no output length filter, no subset, both strands merged
+        qp = make_params(mode=MODE_DFS if pparams.transitive_dfs else MODE_BFS, max_depth=pparams.max_depth,
+                         min_transitive_len=pparams.min_transitive_len,
+                         min_distance_between_ranges=pparams.min_distance_between_ranges, min_output_length=None,
+                         store_cigar=False, min_identity=None if mi != mi else mi, merge_distance=pparams.merge_distance,
+                         merge_strands=True, masked_regions=mask)
+        cols = answer(np.array([window], dtype=RANGE_DTYPE), qp)
+        st.feed(cols["q_id"], cols["q_first"], cols["q_last"])
+    return st.finish()
+
+
 class MultiImpg:
     """Mirror of the reference's MultiImpg (src/multi_impg.rs): several alignment files behind
     one ImpgIndex. The reference keeps one sub-index per file and re-sorts the union of their
@@ -889,6 +920,10 @@ class ShardedImpg:
 
     def query_batch_bed(self, ranges, params):
         return merge_shards(self.query_batch_bed_parts(ranges, params))
+
+    def partition(self, pparams):
+        """`impg partition -o bed` over the sharded index: every window is one collective masked walk."""
+        return partition_with(self.shards[0], pparams, lambda w, qp: self.query_batch_bed(w, qp).columns())
 
     def stats(self):
         return [s.stats() for s in self.shards]

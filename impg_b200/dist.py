@@ -90,6 +90,19 @@ def gather_columns(cols):
     return out
 
 
+def partition_sharded(shard, comm, pparams):
+    """`impg partition -o bed` over a target-sharded index, one process per GPU: every rank steps through the same
+    windows (the partitioner is deterministic), answers each with the collective masked walk on its shard, and the
+    per-rank BED rows are all-gathered so that every rank feeds the same intervals. Every rank returns the partitions."""
+    import impg_b200 as ix
+
+    def answer(window, qp):
+        part = shard.query_batch_bed_sharded(comm, window, qp).columns()
+        return ix.merge_shard_columns(gather_columns(part))
+
+    return ix.partition_with(shard, pparams, answer)
+
+
 def owner_histogram(owner, world):
     """Sequences per rank of an owner map."""
     return np.bincount(np.asarray(owner, dtype=np.int64), minlength=world)

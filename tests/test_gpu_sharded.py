@@ -240,3 +240,23 @@ def test_sharded_dfs_options_and_masks(world):
     tiny = np.array([(s, 10, 60) for s in range(12)], ix.RANGE_DTYPE)
     compare_bed_sharded(orc, sh, tiny, *params_pair(mode=2, max_depth=2, merge_distance=0))
 
+
+@pytest.mark.parametrize("n_ranks", [2, 3])
+def test_partition_over_the_sharded_index(world, n_ranks):
+    """`impg partition -o bed` (reference src/commands/partition.rs:158-712) with every window answered by the
+    collective masked walk of the sharded index: the same partitions as the oracle's."""
+    cfg, orc, shards, bed = world
+    sh = shards[n_ranks]
+    for kw in (dict(window_size=20000, merge_distance=1000), dict(window_size=7000, merge_distance=0, max_depth=3),
+               dict(window_size=30000, merge_distance=5000, transitive_dfs=True, max_depth=2),
+               dict(window_size=15000, merge_distance=100, selection_mode="total", min_missing_size=500,
+                    min_boundary_distance=200)):
+        want = orc.partition(O.make_partition_params(**kw))
+        got = sh.partition(ix.make_partition_params(**kw))
+        norm = [(p, s, min(x, y), max(x, y)) for p, s, x, y in want["rows"]]
+        assert got.rows() == norm, kw
+        assert got.n_windows == len(want["windows"])
+    with pytest.raises(ix.ImpgxError) as e:
+        sh.partition(ix.make_partition_params(window_size=20000, merge_distance=-1))
+    assert e.value.code == ix.E_UNSUPPORTED
+
