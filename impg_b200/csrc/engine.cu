@@ -2701,7 +2701,15 @@ static bool try_small(impgx_index *idx, const impgx_range *ranges, size_t n, con
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_small_bfs, view, d_r, sp, c));
+    cudaError_t le = cudaLaunchKernelEx(&cfg, k_small_bfs, view, d_r, sp, c);
+    if (le != cudaSuccess && cl > 1) {
+      // a device partition that cannot co-schedule the cluster: the walk is the same with one CTA per row
+      cudaGetLastError();
+      cfg.gridDim = dim3(R);
+      at[0].val.clusterDim.x = 1;
+      le = cudaLaunchKernelEx(&cfg, k_small_bfs, view, d_r, sp, c);
+    }
+    CUDA_CHECK(le);
     ctx.launches++;
   }
   if (bed) {
