@@ -2573,7 +2573,7 @@ static uint64_t env_u64(const char *name, uint64_t dflt) {
 static bool small_eligible(const impgx_index *idx, size_t n, const impgx_params &p, bool bed, bool results_to_host,
                            const Comm *comm) {
   if (n == 0 || n > SB_MAX_ROWS || comm || !results_to_host || !idx->owner.empty()) return false;
-  if (p.mode != IMPGX_MODE_BFS && p.mode != IMPGX_MODE_QUERY) return false;
+  if (p.mode != IMPGX_MODE_BFS && p.mode != IMPGX_MODE_DFS && p.mode != IMPGX_MODE_QUERY) return false;
   if (p.store_cigar || !std::isnan(p.min_identity)) return false;  // the endpoint liftover carries no CIGAR
   if (bed && p.merge_distance < 0 && !p.merge_strands) return false;  // unsorted output: reference order per row
   // diagnostic / test switches of the batched path keep selecting it
@@ -2603,6 +2603,7 @@ static bool try_small(impgx_index *idx, const impgx_range *ranges, size_t n, con
   sp.min_dist = p.min_distance_between_ranges;
   sp.min_out = p.min_output_length;
   sp.query_mode = query_mode ? 1 : 0;
+  sp.dfs = p.mode == IMPGX_MODE_DFS ? 1 : 0;
   sp.bed = bed ? 1 : 0;
 
   const impgx_range *d_r = ranges;

@@ -5,7 +5,7 @@
 // hundred hits. The batched pipeline of engine.cu spends ~65 launches and ~20 size readbacks on such a call
 // (count -> scan -> read the size -> allocate -> fill, per stage); the device work itself is microseconds.
 // Here ONE CTA owns a row and runs every stage of Impg::query_transitive_bfs (src/impg.rs:2316-2593) /
-// Impg::query (:1852-1925) on capacity-bounded buffers, with the sizes kept in shared memory:
+// query_transitive_dfs (:2057-2309) / Impg::query (:1852-1925) on capacity-bounded buffers, with the sizes kept in shared memory:
 //   seed (masked or not) -> per hop: stab count, scan, fill, endpoint liftover, order by (range, visit rank),
 //   append results, fold into the visited set (thread per touched sequence, the same fold_one_group as the
 //   batched path), rebuild the visited set, sort + join the next frontier.
@@ -32,6 +32,7 @@ struct SbParams {
   uint32_t n_rows, max_depth;
   int32_t min_transitive_len, min_dist, min_out;
   int query_mode;            // 1: Impg::query (closed stab, no clipping, no walk)
+  int dfs;                   // 1: query_transitive_dfs (src/impg.rs:2057-2309): one popped range per round
   int bed;                   // 1: BoxRecs in (row, q) buckets for the bucket merge; 0: results in reference order
   const uint64_t *mask_off;  // masked_regions CSR over all sequences, or nullptr
   const int2 *mask_rng;
@@ -59,6 +60,7 @@ struct SbRowMem {
   uint32_t *llen, *pcnt, *loff, *poff;
   int2 *lists;
   Frontier *pieces, *pc;
+  DfsEntry *stk[2];  // DFS: the stack, sorted by (sequence, start); the top is the last entry
 };
 __host__ __device__ inline size_t sb_carve(SbRowMem *m, char *base) {
   size_t off = 0;
@@ -96,6 +98,8 @@ __host__ __device__ inline size_t sb_carve(SbRowMem *m, char *base) {
   t.lists = (int2 *)take((size_t)SB_LISTS * sizeof(int2));
   t.pieces = (Frontier *)take((size_t)SB_LISTS * sizeof(Frontier));
   t.pc = (Frontier *)take(C * sizeof(Frontier));
+  t.stk[0] = (DfsEntry *)take(C * sizeof(DfsEntry));
+  t.stk[1] = (DfsEntry *)take(C * sizeof(DfsEntry));
   if (m) *m = t;
   return off;
 }
@@ -404,8 +408,31 @@ __global__ void __launch_bounds__(SB_THREADS, 1)
     t_prev = t;
   };
   uint32_t depth = 0;
-  while (nF > 0 && (p.query_mode ? depth == 0 : (p.max_depth == 0 || depth < p.max_depth))) {
-    const bool last = p.query_mode || (p.max_depth != 0 && depth + 1 >= p.max_depth);
+  // DFS: the seeds that are walked on are the initial stack (they are in (sequence, start) order)
+  uint32_t n_stack = 0, cur_depth = 0;
+  int sbuf = 0;
+  if (p.dfs) {
+    for (uint32_t i = tid; i < nF; i += T) {
+      const Frontier f = m.fr[0][i];
+      m.stk[0][i] = DfsEntry{row, f.seq, f.start, f.end, 0u, 0u};
+    }
+    n_stack = nF;
+    __syncthreads();
+  }
+  for (;;) {
+    if (p.dfs) {
+      // pop the top; an entry at max_depth is dropped (:2125-2127)
+      if (n_stack == 0) break;
+      const DfsEntry top = m.stk[sbuf][n_stack - 1];
+      n_stack--;
+      if (p.max_depth > 0 && top.depth >= p.max_depth) continue;
+      if (tid == 0) m.fr[fb][0] = Frontier{row, top.id, top.start, top.end};
+      nF = 1;
+      cur_depth = top.depth;
+    } else if (!(nF > 0 && (p.query_mode ? depth == 0 : (p.max_depth == 0 || depth < p.max_depth)))) {
+      break;
+    }
+    const bool last = !p.dfs && (p.query_mode || (p.max_depth != 0 && depth + 1 >= p.max_depth));
     const bool closed = p.query_mode != 0;
     const Frontier *F = m.fr[fb];
     st_ranges += nF;
@@ -664,6 +691,57 @@ __global__ void __launch_bounds__(SB_THREADS, 1)
       for (uint32_t k = 0; k < m.pcnt[g]; k++) O[k] = P[k];
     }
     __syncthreads();
+    if (p.dfs) {
+      // push the pieces with depth + 1, re-sort the stack by (sequence, start), join touching entries keeping the
+      // first one's depth (:2289-2304). Entries of one sequence are disjoint (each is a part that had not been
+      // visited when it was pushed), so an entry joins its predecessor exactly when the two touch.
+      if (n_stack + n_pieces > SB_CAP) {
+        leave(SB_OVERFLOW);
+        return;
+      }
+      DfsEntry *S = m.stk[sbuf], *D = m.stk[sbuf ^ 1];
+      for (uint32_t i = tid; i < n_pieces; i += T) {
+        const Frontier f = m.pc[i];
+        S[n_stack + i] = DfsEntry{row, f.seq, f.start, f.end, cur_depth + 1, 0u};
+      }
+      __syncthreads();
+      const uint32_t ms = n_stack + n_pieces;
+      for (uint32_t i = tid; i < ms; i += T) {
+        skey[i] = ((uint64_t)S[i].id << 32) | ((uint32_t)S[i].start ^ 0x80000000u);
+        sval[i] = i;
+      }
+      __syncthreads();
+      sb_sort(skey, sval, ms);
+      uint32_t n_new = 0;
+      for (uint32_t i0 = 0; i0 < ms; i0 += T) {
+        const uint32_t i = i0 + tid;
+        bool head = false;
+        if (i < ms) {
+          head = true;
+          if (i > 0) {
+            const DfsEntry a = S[sval[i - 1]], b = S[sval[i]];
+            head = !(a.id == b.id && a.end >= b.start);
+          }
+        }
+        uint32_t round;
+        const uint32_t pos = sb_block_scan(head ? 1u : 0u, sh, &round);
+        if (head) {
+          DfsEntry e = S[sval[i]];
+          for (uint32_t j = i + 1; j < ms; j++) {
+            const DfsEntry a = S[sval[j - 1]], b = S[sval[j]];
+            if (!(a.id == b.id && a.end >= b.start)) break;
+            e.end = max(e.end, b.end);
+          }
+          D[n_new + pos] = e;
+        }
+        n_new += round;
+      }
+      __syncthreads();
+      sbuf ^= 1;
+      n_stack = n_new;
+      lap(8);
+      continue;
+    }
     for (uint32_t i = tid; i < n_pieces; i += T) {
       const Frontier f = m.pc[i];
       skey[i] = ((uint64_t)f.seq << 32) | ((uint32_t)f.start ^ 0x80000000u);

@@ -213,3 +213,38 @@ def test_switch_selects_the_batched_path(world, monkeypatch):
     monkeypatch.delenv("IMPGX_NO_SMALL_BFS")
     compare_raw(orc, gpu, bed[:2], *params_pair(mode=1, max_depth=2))
     assert took_small_path(gpu, False)
+
+
+@pytest.mark.parametrize("depth", [1, 2, 3, 0])
+def test_dfs_calls(world, depth):
+    """query_transitive_dfs (reference src/impg.rs:2057-2309) in the single launch: the stack of the row lives in
+    its scratch, every round pops one range, walks it and re-sorts / joins the stack."""
+    cfg, orc, gpu, bed = world
+    for k in range(0, 30, 3):
+        compare_raw(orc, gpu, bed[k:k + 1], *params_pair(mode=2, max_depth=depth))
+        assert took_small_path(gpu, False)
+        compare_raw(orc, gpu, bed[k:k + 3], *params_pair(mode=2, max_depth=depth))
+        assert took_small_path(gpu, False)
+    compare_bed(orc, gpu, bed[:20], *params_pair(mode=2, max_depth=depth, merge_distance=1000))
+    assert took_small_path(gpu, True)
+
+
+def test_dfs_options_and_masks(world):
+    cfg, orc, gpu, bed = world
+    b = bed[40:52]
+    compare_raw(orc, gpu, b, *params_pair(mode=2, max_depth=0, min_transitive_len=0, min_dist=0))
+    compare_raw(orc, gpu, b, *params_pair(mode=2, max_depth=3, min_output_length=2500))
+    compare_raw(orc, gpu, b, *params_pair(mode=2, max_depth=3, min_transitive_len=2000, min_dist=500))
+    mask = np.zeros(12, np.uint8)
+    mask[[0, 2, 3, 7, 8]] = 1
+    compare_raw(orc, gpu, b, *params_pair(mode=2, max_depth=3, subset_mask=mask))
+    compare_bed(orc, gpu, b, *params_pair(mode=2, max_depth=0, merge_distance=0, merge_strands=False))
+    assert took_small_path(gpu, True)
+    rng = np.random.default_rng(5)
+    for density, depth in ((0.5, 2), (0.9, 3), (0.97, 0)):
+        m = random_mask(rng, 12, 60000, density)
+        for k in range(0, 24, 4):
+            compare_raw(orc, gpu, bed[k:k + 4], *params_pair(mode=2, max_depth=depth, masked_regions=m))
+            assert took_small_path(gpu, False)
+            compare_bed(orc, gpu, bed[k:k + 4], *params_pair(mode=2, max_depth=depth, masked_regions=m, merge_distance=500))
+
