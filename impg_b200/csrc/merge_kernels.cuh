@@ -267,7 +267,7 @@ __global__ void k_boxes_to_cols(const Box *__restrict__ b, uint64_t n, OutCols o
 // as the reference's stable sorts would.
 namespace impgx {
 
-struct __align__(16) BoxD {
+struct __align__(8) BoxD {  // 40 bytes: what travels between the ranks of a sharded index
   int32_t q_lo, q_hi, t_lo, t_hi;
   uint32_t q_id, t_id, row, valid;  // valid: bit 0 = a result, BOXD_MERGED_A = a stage-A result already
   uint64_t ord;  // position in the reference's result order of the row: level << 58 | (range << 32 | vrank) or index
