@@ -2925,6 +2925,15 @@ impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n
         total.d2h_bytes += (m + 1) * 8;
         if (results_to_host) {
           const size_t old = res->qid.size();
+          if (done + m < n) {
+            // more batches follow: room for all of them at the rate seen so far, so that the columns are not
+            // re-allocated and copied batch after batch
+            const double per_row = (double)(old + R) / (double)(done + m);
+            const size_t want = (size_t)(per_row * (double)n * 1.05) + 4096;
+            res->qid.reserve(want); res->tid.reserve(want);
+            res->qf.reserve(want); res->ql.reserve(want);
+            res->tf.reserve(want); res->tl.reserve(want);
+          }
           res->qid.resize(old + R); res->tid.resize(old + R);
           res->qf.resize(old + R); res->ql.resize(old + R);
           res->tf.resize(old + R); res->tl.resize(old + R);

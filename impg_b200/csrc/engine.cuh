@@ -106,6 +106,14 @@ class HostCol {
     }
     n_ = n;
   }
+  // capacity for n elements without changing the size (one block instead of a chain of doublings, each of
+  // which copies what is there)
+  void reserve(size_t n) {
+    if (n * sizeof(T) <= cap_bytes_) return;
+    const size_t keep = n_;
+    resize(n);
+    n_ = keep;
+  }
   void assign(size_t n, const T &v) {
     resize(n);
     for (size_t i = 0; i < n; i++) p_[i] = v;
