@@ -247,3 +247,43 @@ def test_stepper_reproduces_the_committed_partition_golden():
                 text = "".join(f"{names[s]}\t{a}\t{b}\t{p}\n" for p, s, a, b in got.rows())
                 assert hashlib.sha256(text.encode()).hexdigest() == c["sha256"], (fixture, kw, bed_rows)
                 assert (len(windows), got.n_partitions) == (c["windows"], c["n_partitions"])
+
+
+def test_partition_with_any_answerer_matches_the_oracle():
+    """impg_b200.partition_with — the driver behind ShardedImpg.partition / dist.partition_sharded — on the CPU:
+    every window answered by the oracle's merged BED rows (what a sharded index returns after its parts are
+    merged); the partitions are the oracle's."""
+    oidx, lens, names = small_world(seed=11)
+
+    class Meta:  # what partition_with needs of an index: the sequence table
+        n_seqs = len(lens)
+
+        def seq_len(self, i):
+            return int(lens[i])
+
+        def seq_name(self, i):
+            return names[i]
+
+    asked = []
+
+    def answer(window, gp):
+        asked.append(tuple(int(x) for x in window[0]))
+        mo = np.ctypeslib.as_array((ix.C.c_uint64 * (len(lens) + 1)).from_address(gp.mask_offsets))
+        nm = int(mo[-1])
+        mr = np.ctypeslib.as_array((ix.C.c_int32 * max(2 * nm, 2)).from_address(gp.mask_ranges))
+        qp = O.make_params(mode=O.MODE_DFS if gp.mode == ix.MODE_DFS else O.MODE_BFS, max_depth=gp.max_depth,
+                           min_transitive_len=gp.min_transitive_len, min_dist=gp.min_distance_between_ranges,
+                           masked_regions=(mo.copy(), mr.copy()), merge_distance=gp.merge_distance, merge_strands=True)
+        res, _ = oidx.query_batch(window, qp, bed_merge=True)
+        return res.columns()
+
+    for kw in (dict(window_size=20000, merge_distance=1000), dict(window_size=9000, merge_distance=0, max_depth=3),
+               dict(window_size=25000, merge_distance=3000, transitive_dfs=True)):
+        asked.clear()
+        got = ix.partition_with(Meta(), ix.make_partition_params(**kw), answer)
+        want = oidx.partition(O.make_partition_params(**kw))
+        assert got.rows() == norm(want["rows"]), kw
+        assert asked == [tuple(w) for w in want["windows"]]
+    with pytest.raises(ix.ImpgxError) as e:
+        ix.partition_with(Meta(), ix.make_partition_params(window_size=20000, merge_distance=-1), answer)
+    assert e.value.code == ix.E_UNSUPPORTED
