@@ -60,6 +60,7 @@ WORKLOADS = {
     "c3": (50, 8, 2500000, 51, 100, 100, 1, 10000),   # BASELINE configs[2]: -x -m 2
     "c4": (200, 8, 2500000, 63, 200, 100, 1, 100000),  # BASELINE configs[3]: the config the metric is quoted on
     "c4p": (200, 8, 2500000, 63, 200, 100, 1, 5000),   # the c4 index with a short BED (profiling: two row batches)
+    "c4d1": (200, 8, 2500000, 63, 200, 100, 1, 100000),  # BASELINE configs[3] at depth 1 ("run both")
     # BASELINE configs[4], sparsified as SURVEY.md 8d allows: 500 genomes, every genome aligned against k = 50 others
     # (12.6 M alignments, ~100 neighbours per genome in the bidirectional index), 125,000 rows per GPU = 1 M rows on
     # 8 GPUs, -x -m 3
@@ -67,10 +68,10 @@ WORKLOADS = {
     "c5p": (500, 8, 2500000, 63, 400, 100, 1, 4000),   # the c5 index with a short BED (one-GPU check of the depth-3 path)
 }
 PARTNERS = {"c5": 50, "c5p": 50}
-DEPTH = {"c2": 1, "c5": 3, "c5p": 3}
+DEPTH = {"c2": 1, "c4d1": 1, "c5": 3, "c5p": 3}
 # workloads whose CPU reference / parity oracle runs on the alignments of contig 0 only (per-row work is
 # identical to the full index: the synthetic world never aligns across contigs)
-SUBWORLD = {"c4", "c4p", "c5", "c5p"}
+SUBWORLD = {"c4", "c4p", "c4d1", "c5", "c5p"}
 
 
 def peaks():
@@ -89,7 +90,7 @@ def ncu_traffic(name):
     from another workload's capture."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
-        return json.load(open(p)).get(name[:2] if name.startswith("c4") else name)
+        return json.load(open(p)).get("c4" if name in ("c4", "c4p") else name)
     except Exception:
         return None
 
