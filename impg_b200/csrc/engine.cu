@@ -2847,7 +2847,8 @@ impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n
   // (C4: 2.09 s per step at 2*10^8 hits per batch, 2.02 s at 10^9), so a batch aims at as many hits as half of the
   // memory the index leaves free will hold, 10^9 at most; the ranks of a sharded index agree on the smallest figure.
   double target_hits = (double)env_u64("IMPGX_HITS_PER_BATCH", 0);
-  if (target_hits <= 0) {
+  auto size_batches = [&]() {  // on the first batch of the batched path only: calls of a few rows never get here
+    if (target_hits > 0) return;
     size_t free_b = 0, total_b = 0;
     CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
     const double left = (double)total_b - (double)idx->device_bytes - 8e9;
@@ -2858,7 +2859,7 @@ impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n
       t = *std::min_element(all.begin(), all.end());
     }
     target_hits = (double)t;
-  }
+  };
   double hits_per_row;
   {
     std::lock_guard<std::mutex> lock(idx->mu);
@@ -2866,6 +2867,7 @@ impgx_results *query_batch(impgx_index *idx, const impgx_range *ranges, size_t n
   }
   auto next_chunk = [&]() -> size_t {
     if (fixed_chunk) return fixed_chunk;
+    size_batches();
     if (hits_per_row <= 0) return 512;
     double c = target_hits / hits_per_row;
     // the direct BED path keeps dense tables over rows x sequences (bucket_kernels.cuh)
