@@ -103,3 +103,69 @@ def test_two_rank_gloo_sharded_host_logic(tmp_path):
     want = [r * 1000 + s for r in range(4) for s in range(10)]
     assert o[0]["merged"] == want and o[1]["merged"] == want
     assert o[0]["ro"] == [0, 10, 20, 30, 40]
+
+
+def test_two_rank_gloo_partition_over_shards(tmp_path):
+    """dist.partition_sharded over gloo, the device replaced by the oracle: every rank steps through the same windows,
+    answers each with the BED rows of the sequences IT owns (what impgx_query_batch_bed_sharded returns on a shard),
+    the parts are all-gathered and merged, and both ranks arrive at the oracle's partitions."""
+    script = tmp_path / "w.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys, json
+        sys.path.insert(0, {ROOT!r})
+        sys.path.insert(0, os.path.join({ROOT!r}, "tests"))
+        import numpy as np
+        from impg_b200 import dist as D
+        import impg_b200 as ix
+        import _oracle as O
+        rank, local, world = D.env_rank()
+        D.init("gloo")
+        cfg = ix.synth_cfg(5, 2, 40000, 5, 30, 200, 3)
+        recs, runs, offs, lens, names = ix.synth_generate(cfg)
+        owner = ix.assign_owners(recs, offs, len(lens), world)
+        orc = O.Index.build(recs, runs, offs, lens, names=names)
+
+        class Cols:
+            def __init__(self, c):
+                self.c = c
+            def columns(self):
+                return self.c
+
+        class OracleShard:  # the part of a sharded answer this rank would hold: rows of the sequences it owns
+            n_seqs = len(lens)
+            def seq_len(self, i):
+                return int(lens[i])
+            def seq_name(self, i):
+                return names[i]
+            def query_batch_bed_sharded(self, comm, window, gp):
+                mo = np.ctypeslib.as_array((ix.C.c_uint64 * (len(lens) + 1)).from_address(gp.mask_offsets)).copy()
+                mr = np.ctypeslib.as_array((ix.C.c_int32 * max(2 * int(mo[-1]), 2)).from_address(gp.mask_ranges)).copy()
+                qp = O.make_params(mode=O.MODE_DFS if gp.mode == ix.MODE_DFS else O.MODE_BFS, max_depth=gp.max_depth,
+                                   min_transitive_len=gp.min_transitive_len, min_dist=gp.min_distance_between_ranges,
+                                   masked_regions=(mo, mr), merge_distance=gp.merge_distance, merge_strands=True)
+                res, roff = orc.query_batch(window, qp, bed_merge=True)
+                c = res.columns()
+                sel = owner[c["q_id"]] == rank
+                out = {{k: np.asarray(c[k])[sel] for k in ("q_id", "q_first", "q_last", "t_id", "t_first", "t_last")}}
+                out["row_offsets"] = np.array([0, int(sel.sum())], np.uint64)
+                return Cols(out)
+
+        kw = dict(window_size=15000, merge_distance=1000)
+        got = D.partition_sharded(OracleShard(), None, ix.make_partition_params(**kw))
+        want = orc.partition(O.make_partition_params(**kw))
+        norm = [[p, s, min(a, b), max(a, b)] for p, s, a, b in want["rows"]]
+        out = dict(rank=rank, equal=[list(r) for r in got.rows()] == norm, windows=int(got.n_windows),
+                   want_windows=len(want["windows"]), owned=int((owner == rank).sum()))
+        open(os.path.join({str(tmp_path)!r}, f"out{{rank}}.json"), "w").write(json.dumps(out))
+    """))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29613")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29613", str(script)],
+                       env=env, capture_output=True, text=True, timeout=400)
+    assert r.returncode == 0, r.stderr[-3000:]
+    import json
+    o = [json.load(open(tmp_path / f"out{k}.json")) for k in range(2)]
+    for k in range(2):
+        assert o[k]["equal"], o[k]
+        assert o[k]["windows"] == o[k]["want_windows"] > 1
+        assert o[k]["owned"] > 0  # both ranks contribute rows
